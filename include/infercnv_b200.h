@@ -1,0 +1,196 @@
+/*
+ * infercnv_b200.h - C ABI of libinfercnv_b200.so: the B200 (sm_100a) drop-in for the
+ * smoothing + HMM hot path of broadinstitute/infercnv.
+ *
+ * The reference is pure R (DESCRIPTION: "NeedsCompilation: no"; NAMESPACE has no useDynLib), so it
+ * has no native interface to bind to.  The boundary is the set of internal R functions that
+ * infercnv::run() calls on this path; each entry point below replaces the body of one of them
+ * (file:line of the reference given per function) and is what a `.Call()` shim binds
+ * (see INTEGRATION.md and infercnv_b200/r/).
+ *
+ * Conventions
+ *   layout   R column-major, X[g + G*c]: g = gene (row, chromosome-ordered), c = cell (column).
+ *            A cell's gene vector is contiguous.  Sizes are int64 (R long vectors).
+ *   dtype    float64 across the ABI (R `double`); states are int32 (1..m, -1 = not assigned).
+ *   indices  0-based everywhere (the R shim subtracts 1).  Index lists are CSR style:
+ *            group k owns grp_idx[grp_off[k] .. grp_off[k+1]).
+ *   chromosomes  K contiguous row ranges [chr_start[k], chr_start[k]+chr_len[k]) - the reference
+ *            pre-sorts rows by chr,start,stop (R/inferCNV.R:407-413).
+ *   ownership  caller owns every buffer it passes; inputs are never modified; outputs may alias
+ *            inputs only where stated.  The library owns all device memory, streams and pinned
+ *            staging and frees them in icnv_shutdown().
+ *   errors   every entry returns 0 or a negative icnv_status and records a per-thread message
+ *            readable through icnv_last_error().  Nothing throws across the ABI.  There is no CPU
+ *            fallback: without a usable CUDA device every compute entry returns ICNV_E_NO_DEVICE.
+ *   threading  calls are synchronous (result resident in the caller's buffer at return) and
+ *            serialised internally; call from one host thread at a time per process.
+ *
+ * Two families:
+ *   icnv_*      host pointers in / host pointers out (what R binds).  H2D / D2H inside.
+ *   icnv_dev_*  device pointers on the library's current device + a cudaStream_t (as void*);
+ *               asynchronous on that stream.  Used by the multi-GPU driver and the benchmark.
+ */
+#ifndef INFERCNV_B200_H
+#define INFERCNV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ICNV_API __attribute__((visibility("default")))
+#else
+#define ICNV_API
+#endif
+
+typedef enum icnv_status {
+    ICNV_OK = 0,
+    ICNV_E_NO_DEVICE = -1,   /* no CUDA device / driver, or icnv_init failed */
+    ICNV_E_CUDA = -2,        /* a CUDA runtime call or kernel failed */
+    ICNV_E_BAD_ARG = -3,     /* NULL pointer, negative size, inconsistent ranges, even window, ... */
+    ICNV_E_UNSUPPORTED = -4, /* outside the kernels' envelope (e.g. G too large for shared memory) */
+    ICNV_E_NONFINITE = -5,   /* NA/NaN/Inf in the input where the reference would stop() */
+    ICNV_E_UNDERFLOW = -6,   /* "Problems With Underflow" (R/inferCNV_HMM.R:1165-1166) */
+    ICNV_E_NOMEM = -7
+} icnv_status;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Select `device` (cudaSetDevice), create the library's stream and scratch pools.  Idempotent for
+ * the same device; re-initialises when called with another one.  device < 0 -> device 0. */
+ICNV_API int icnv_init(int device);
+ICNV_API void icnv_shutdown(void);
+ICNV_API int icnv_device_count(void);          /* >= 0, or a negative icnv_status */
+ICNV_API const char *icnv_last_error(void);    /* never NULL */
+ICNV_API const char *icnv_version(void);
+/* Number of kernel launches issued by this library since icnv_init (for bench `gpu_launches`). */
+ICNV_API int64_t icnv_launch_count(void);
+
+/* ---- host-pointer entry points (what the R shim binds) ---------------------------------------- */
+
+/* .get_normal_gene_mean_bounds, R/inferCNV_ops.R:1708-1735.
+ * means[g + G*k] = mean(X[g, group k]);  inv_log != 0: log2(mean(2^x - 1) + 1). */
+ICNV_API int icnv_ref_means_f64(const double *X, int64_t G, int64_t C, const int32_t *grp_off,
+                                const int32_t *grp_idx, int n_grp, int inv_log, double *means);
+
+/* .subtract_expr, R/inferCNV_ops.R:1742-1786 (body of subtract_ref_expr_from_obs, :1678-1702).
+ * use_bounds: y = x-max_k(means) if x>max; x-min_k(means) if x<min; else 0.  Otherwise x-mean_k(means).
+ * Y may alias X. */
+ICNV_API int icnv_subtract_ref_f64(const double *X, double *Y, int64_t G, int64_t C, const double *means,
+                                   int n_grp, int use_bounds);
+
+/* smooth_by_chromosome -> .smooth_window -> .smooth_helper, R/inferCNV_ops.R:2406-2532, 2640-2661.
+ * Truncated, renormalised triangular ("pyramidinal") moving average per cell per chromosome.
+ * window < 2: copy.  Even window: ICNV_E_BAD_ARG (the reference's behaviour is accidental there).
+ * Chromosomes with < 2 genes are left untouched (:2417).  NA input: ICNV_E_NONFINITE. */
+ICNV_API int icnv_smooth_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                             const int32_t *chr_len, int K, int window);
+
+/* .center_columns, R/inferCNV_ops.R:2094-2109 (center_cell_expr_across_chromosome, :2074-2088).
+ * use_median != 0: subtract the per-cell median over all G genes; else the per-cell mean. */
+ICNV_API int icnv_center_f64(const double *X, double *Y, int64_t G, int64_t C, int use_median);
+
+/* Fused run() steps 4, 8, 9, 10, 11, 12, 14 (R/inferCNV_ops.R:614, 771, 817, 865, 911, 952, 1031):
+ * [log2(x+1)] -> subtract ref (bounds) -> clamp +-threshold -> smooth(window) -> centre by
+ * median -> subtract ref again -> 2^x.  X is the depth-normalised matrix (after step 3).
+ * n_grp == 0 is BAD_ARG (callers pass the proxy group of all observation cells when there are no
+ * references, as the reference does at ops.R:1686-1689).  threshold <= 0 disables the clamp. */
+ICNV_API int icnv_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                                   const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx,
+                                   int n_grp, int apply_log, double threshold, int window, int use_bounds);
+
+/* Viterbi.dthmm.adj, R/inferCNV_HMM.R:1101-1176, batched over the drivers
+ * predict_CNV_via_HMM_on_indiv_cells (HMM.R:284-324), ..._on_tumor_subclusters (:345-408),
+ * ..._on_whole_tumor_samples (:509-567) and the i3 twins (R/inferCNV_i3HMM.R:180-389).
+ * m = 6 (i6) or 3 (i3).  Pi: m x m column-major, Pi[j + m*k] = P(j -> k); delta[m]; mean[m].
+ * n_grp == 0: one sequence per (cell, chromosome), sd[m].
+ * n_grp  > 0: one sequence per (group, chromosome) on rowMeans(X[chr, group]); sd[m*n_grp]
+ *             (per-group sds as .get_state_emission_params, HMM.R:586-614, computes them);
+ *             the trace is written to every cell of the group, other cells get -1.
+ * states: int32 G x C.  margins: optional (may be NULL) K x (C or n_grp) doubles receiving, per
+ * sequence, the smallest winner/runner-up gap over the traceback decisions (diagnostic).
+ * Sequences with < 2 genes get state 3 (HMM.R:1104-1107). */
+ICNV_API int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start,
+                              const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx,
+                              int n_grp, int m, const double *Pi, const double *delta, const double *mean,
+                              const double *sd, int32_t *states, double *margins);
+
+/* apply_median_filtering / .median_filter, R/noise_reduction.R:43-113.  Blocks = chromosome x one
+ * index list (a subcluster for observations, a whole group for references), cells in list order.
+ * Window radius is (window_size+1)/2 as in the reference (noise_reduction.R:102-106).
+ * Cells in no list are copied.  window_size even or < 3: ICNV_E_BAD_ARG. */
+ICNV_API int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                                    const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx,
+                                    int n_grp, int window_size);
+
+/* .i3HMM_get_sd_trend_by_num_cells_fit, R/inferCNV_i3HMM.R:17-30: mean and sd (n-1) over all
+ * values of the listed cells. */
+ICNV_API int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mu,
+                              double *sigma);
+
+/* ---- device-pointer entry points ------------------------------------------------------------- */
+/* All pointers are device pointers on the icnv_init() device unless marked host.  `stream` is a
+ * cudaStream_t; NULL = the library's own stream.  Asynchronous: the caller synchronises. */
+
+/* Partial sums for group means, fixed summation order so results do not depend on the number of
+ * GPUs: cells[0..n_cells) (device, column indices into X) are cut into chunks of `chunk` list
+ * entries; partial[g + G*q] = sum over chunk q, in list order, of f(X[g, cell]) with
+ * f = identity, or log2(x+1) when apply_log.  n_chunks = ceil(n_cells/chunk). */
+ICNV_API int icnv_dev_group_partial_sums_f64(const double *X, int64_t G, int64_t ldx, const int32_t *cells,
+                                             int64_t n_cells, int chunk, int apply_log, double *partial,
+                                             void *stream);
+/* means[g] = (sum_q partial[g + G*q], q ascending) / count */
+ICNV_API int icnv_dev_combine_partials_f64(const double *partial, int64_t G, int64_t n_chunks, int64_t count,
+                                           double *means, void *stream);
+/* lo/hi/mid over the n_grp columns of means (each length G). */
+ICNV_API int icnv_dev_bounds_from_means_f64(const double *means, int64_t G, int n_grp, double *lo, double *hi,
+                                            double *mid, void *stream);
+
+/* The fused per-cell kernel.  For every listed column (cols == NULL: columns 0..n_cols-1 of X):
+ *   v = X[:, col]; [v = log2(v+1)]; [v = dead-band subtract (lo1, hi1) or v - mid1];
+ *   [clamp +-threshold]; [smooth(window) per chromosome]; [v -= median(v) | mean(v)];
+ *   [dead-band subtract (lo2, hi2) or v - mid2]; [v = 2^v]; Y[:, i] = v   (output column i, ld = ldy)
+ * Stage selection: lo1/hi1 NULL -> skip; mid1 used when lo1 == NULL && mid1 != NULL; threshold <= 0
+ * -> skip; window < 2 -> skip; center: 0 none, 1 median, 2 mean; lo2/hi2/mid2 likewise; apply_exp2.
+ * err_flag (device int*, may be NULL) is set to 1 when a non-finite value is seen. */
+ICNV_API int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const int32_t *cols, int64_t n_cols,
+                                        double *Y, int64_t ldy, const int32_t *chr_start /*host*/,
+                                        const int32_t *chr_len /*host*/, int K, int apply_log, const double *lo1,
+                                        const double *hi1, const double *mid1, double threshold, int window,
+                                        int center, const double *lo2, const double *hi2, const double *mid2,
+                                        int apply_exp2, int *err_flag, void *stream);
+
+/* Whole smooth block on device-resident data (single GPU): X, Y are G x C (ld = G). */
+ICNV_API int icnv_dev_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C,
+                                       const int32_t *chr_start /*host*/, const int32_t *chr_len /*host*/, int K,
+                                       const int32_t *grp_off /*host*/, const int32_t *grp_idx /*host*/, int n_grp,
+                                       int apply_log, double threshold, int window, int use_bounds, void *stream);
+
+/* Per-sequence Viterbi on device-resident X (G x C, ld = G), one sequence per (column, chromosome).
+ * states_u8: uint8 G x C (1..m).  margins: device K x C doubles or NULL.  Model arrays are host.
+ * sd has m entries (sd_per_col == 0) or m per column (sd_per_col != 0, device-order = column). */
+ICNV_API int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start /*host*/,
+                                  const int32_t *chr_len /*host*/, int K, int m, const double *Pi /*host*/,
+                                  const double *delta /*host*/, const double *mean /*host*/,
+                                  const double *sd /*host*/, int sd_per_col, uint8_t *states_u8, double *margins,
+                                  int *err_flag, void *stream);
+
+/* Median filter on device-resident data; index lists are host arrays. */
+ICNV_API int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C,
+                                        const int32_t *chr_start /*host*/, const int32_t *chr_len /*host*/, int K,
+                                        const int32_t *grp_off /*host*/, const int32_t *grp_idx /*host*/, int n_grp,
+                                        int window_size, void *stream);
+
+/* Deterministic synthetic workload of SURVEY section 8(d) written straight into HBM: counter-based
+ * generator keyed by (seed, global cell, gene), so any sharding of the cells yields identical data.
+ * Fills X (G x n_cells, ld = G) for global cells [cell0, cell0 + n_cells). */
+ICNV_API int icnv_dev_synth_f64(double *X, int64_t G, int64_t cell0, int64_t n_cells, int64_t C_total,
+                                const int32_t *chr_start /*host*/, const int32_t *chr_len /*host*/, int K,
+                                uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFERCNV_B200_H */

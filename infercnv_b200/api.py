@@ -1,0 +1,161 @@
+"""NumPy-facing wrappers of the host-pointer C ABI (the same entry points the R shim binds).
+
+Matrices are (G genes, C cells) float64, Fortran order (R column-major: a cell's genes are
+contiguous).  Indices are 0-based.  Every call goes H2D -> sm_100a kernels -> D2H inside the
+library; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+
+import numpy as np
+
+from . import _lib
+
+
+def _f64(a) -> np.ndarray:
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a genes x cells matrix")
+    return np.asfortranarray(a)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data
+
+
+def chr_ranges(chr_codes):
+    """Contiguous row range of every chromosome in order of appearance (rows are pre-sorted by
+    chr in the reference, R/inferCNV.R:407-413).  A chromosome that re-appears is an error."""
+    codes = np.asarray(chr_codes)
+    change = np.flatnonzero(codes[1:] != codes[:-1]) + 1
+    starts = np.concatenate([[0], change]).astype(np.int32)
+    lens = np.diff(np.concatenate([starts, [len(codes)]])).astype(np.int32)
+    if len(set(codes[starts].tolist())) != len(starts):
+        raise ValueError("gene_order$chr is not sorted: a chromosome appears in two separate runs")
+    return starts, lens
+
+
+def groups_to_csr(groups):
+    off = np.cumsum([0] + [len(g) for g in groups]).astype(np.int32)
+    idx = np.concatenate([np.asarray(g, dtype=np.int32) for g in groups]) if len(groups) else np.zeros(1, np.int32)
+    return off, _i32(idx)
+
+
+def init(device: int = 0) -> None:
+    _lib.check(_lib.load().icnv_init(int(device)))
+
+
+def shutdown() -> None:
+    _lib.load().icnv_shutdown()
+
+
+def device_count() -> int:
+    return int(_lib.load().icnv_device_count())
+
+
+def launch_count() -> int:
+    return int(_lib.load().icnv_launch_count())
+
+
+def ref_means(X, groups, inv_log=False) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    off, idx = groups_to_csr(groups)
+    M = np.empty((G, len(groups)), dtype=np.float64, order="F")
+    _lib.check(_lib.load().icnv_ref_means_f64(_p(X), G, C, _p(off), _p(idx), len(groups), int(bool(inv_log)), _p(M)))
+    return M
+
+
+def subtract_ref(X, means, use_bounds=True) -> np.ndarray:
+    X = _f64(X)
+    M = _f64(means)
+    G, C = X.shape
+    if M.shape[0] != G:
+        raise ValueError("means must have one row per gene")
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_subtract_ref_f64(_p(X), _p(Y), G, C, _p(M), M.shape[1], int(bool(use_bounds))))
+    return Y
+
+
+def smooth(X, chr_start, chr_len, window_length) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_smooth_f64(_p(X), _p(Y), G, C, _p(cs), _p(cl), len(cs), int(window_length)))
+    return Y
+
+
+def center(X, method="median") -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_center_f64(_p(X), _p(Y), G, C, int(method == "median")))
+    return Y
+
+
+def smooth_block(X, chr_start, chr_len, ref_groups, apply_log=True, threshold=3.0, window_length=101,
+                 use_bounds=True, out=None) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    off, idx = groups_to_csr(ref_groups)
+    Y = np.empty_like(X, order="F") if out is None else out
+    _lib.check(_lib.load().icnv_smooth_block_f64(_p(X), _p(Y), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx),
+                                                 len(ref_groups), int(bool(apply_log)), float(threshold),
+                                                 int(window_length), int(bool(use_bounds))))
+    return Y
+
+
+def viterbi(X, chr_start, chr_len, Pi, delta, mean, sd, groups=None, want_margins=False, out=None):
+    X = _f64(X)
+    G, C = X.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    K = len(cs)
+    Pi = np.asfortranarray(Pi, dtype=np.float64)
+    m = Pi.shape[0]
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    mean = np.ascontiguousarray(mean, dtype=np.float64)
+    sd = np.ascontiguousarray(sd, dtype=np.float64)
+    if groups is None:
+        off = idx = None
+        ng, nseq = 0, C
+        if sd.size != m:
+            raise ValueError("sd must have m entries in per-cell mode")
+    else:
+        off, idx = groups_to_csr(groups)
+        ng = nseq = len(groups)
+        if sd.size == m:
+            sd = np.tile(sd, ng)
+        if sd.size != m * ng:
+            raise ValueError("sd must have m entries per group")
+    states = np.empty((G, C), dtype=np.int32, order="F") if out is None else out
+    margins = np.empty((K, nseq), dtype=np.float64, order="F") if want_margins else None
+    _lib.check(_lib.load().icnv_viterbi_f64(_p(X), G, C, _p(cs), _p(cl), K, _p(off), _p(idx), ng, m, _p(Pi), _p(delta),
+                                            _p(mean), _p(sd), _p(states), _p(margins)))
+    return (states, margins) if want_margins else states
+
+
+def median_filter(X, chr_start, chr_len, groups, window_size=7) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    off, idx = groups_to_csr(groups)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_median_filter_f64(_p(X), _p(Y), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx),
+                                                  len(groups), int(window_size)))
+    return Y
+
+
+def mean_sd(X, cells):
+    X = _f64(X)
+    G, C = X.shape
+    idx = _i32(cells)
+    mu, sg = ct.c_double(), ct.c_double()
+    _lib.check(_lib.load().icnv_mean_sd_f64(_p(X), G, C, _p(idx), len(idx), ct.addressof(mu), ct.addressof(sg)))
+    return mu.value, sg.value

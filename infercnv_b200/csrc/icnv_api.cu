@@ -1,0 +1,465 @@
+// icnv_api.cu - C ABI of libinfercnv_b200.so: lifecycle, the host-pointer entry points the R shim
+// binds, and the device-side composition of the smooth block.  See include/infercnv_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "icnv_common.cuh"
+
+// device-pointer helpers defined in the other translation units
+extern "C" {
+int icnv_dev_invlog_finish_f64(double *means, int64_t n, void *stream);
+int icnv_dev_widen_states(const uint8_t *s, int32_t *out, int64_t n, void *stream);
+int icnv_dev_scatter_group_states(const uint8_t *gs, int64_t G, int64_t C, const int32_t *grp_of, int32_t *out,
+                                  void *stream);
+int icnv_dev_mean_sd_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *out2,
+                         void *stream);
+}
+
+namespace icnv {
+
+static thread_local char g_err[512] = "";
+
+Ctx &ctx() {
+    static Ctx c;
+    return c;
+}
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void *scratch(int slot, size_t bytes) {
+    Ctx &c = ctx();
+    if (bytes == 0) bytes = 16;
+    if (c.slot_bytes[slot] >= bytes) return c.slot_ptr[slot];
+    if (c.slot_ptr[slot]) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(c.slot_ptr[slot]);
+        c.slot_ptr[slot] = nullptr;
+        c.slot_bytes[slot] = 0;
+    }
+    size_t want = bytes + 256;  // slack so 16-byte over-reads at a column tail stay inside
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        set_error(ICNV_E_NOMEM, "cudaMalloc(%zu) for scratch slot %d failed: %s", want, slot, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    c.slot_ptr[slot] = p;
+    c.slot_bytes[slot] = bytes;
+    return p;
+}
+
+static int validate_chr(int64_t G, const int32_t *chr_start, const int32_t *chr_len, int K) {
+    if (!chr_start || !chr_len || K <= 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges missing");
+    int64_t pos = 0;
+    for (int k = 0; k < K; ++k) {
+        if (chr_start[k] != pos || chr_len[k] < 0)
+            return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously (chr %d)", k);
+        pos += chr_len[k];
+    }
+    if (pos != G) return set_error(ICNV_E_BAD_ARG, "chromosome ranges cover %lld genes, G = %lld", (long long)pos, (long long)G);
+    return ICNV_OK;
+}
+
+static int validate_groups(int64_t C, const int32_t *grp_off, const int32_t *grp_idx, int n_grp, bool allow_empty) {
+    if (n_grp < 0) return set_error(ICNV_E_BAD_ARG, "n_grp < 0");
+    if (n_grp == 0) return allow_empty ? ICNV_OK : set_error(ICNV_E_BAD_ARG, "at least one cell group is required");
+    if (!grp_off || !grp_idx) return set_error(ICNV_E_BAD_ARG, "group index lists missing");
+    if (grp_off[0] != 0) return set_error(ICNV_E_BAD_ARG, "grp_off[0] must be 0");
+    for (int k = 0; k < n_grp; ++k) {
+        if (grp_off[k + 1] <= grp_off[k]) return set_error(ICNV_E_BAD_ARG, "group %d is empty", k);
+    }
+    for (int32_t i = 0; i < grp_off[n_grp]; ++i)
+        if (grp_idx[i] < 0 || grp_idx[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index %d out of range", grp_idx[i]);
+    return ICNV_OK;
+}
+
+static int check_flag(int *d_flag, cudaStream_t st) {
+    int h = 0;
+    ICNV_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    if (h & 1) return set_error(ICNV_E_NONFINITE, "non-finite value (NA/NaN/Inf) in the expression matrix");
+    if (h & 2) return set_error(ICNV_E_UNDERFLOW, "Problems With Underflow");
+    return ICNV_OK;
+}
+
+// group means of the columns listed in d_cells[off[k]..off[k+1]) -> d_means (G x n_grp)
+static int dev_group_means(const double *dX, int64_t G, int64_t ldx, const int32_t *d_cells, const int32_t *h_off,
+                           int n_grp, int apply_log, double *d_means, cudaStream_t st) {
+    const int chunk = 32;  // fixed: the summation tree must not depend on the device count
+    int64_t max_chunks = 0;
+    for (int k = 0; k < n_grp; ++k) max_chunks = std::max<int64_t>(max_chunks, (h_off[k + 1] - h_off[k] + chunk - 1) / chunk);
+    double *d_part = (double *)scratch(SLOT_PARTIAL, sizeof(double) * (size_t)G * (size_t)max_chunks);
+    if (!d_part) return ICNV_E_NOMEM;
+    for (int k = 0; k < n_grp; ++k) {
+        int64_t n = h_off[k + 1] - h_off[k];
+        int64_t n_chunks = (n + chunk - 1) / chunk;
+        int rc = icnv_dev_group_partial_sums_f64(dX, G, ldx, d_cells + h_off[k], n, chunk, apply_log, d_part, st);
+        if (rc) return rc;
+        rc = icnv_dev_combine_partials_f64(d_part, G, n_chunks, n, d_means + G * k, st);
+        if (rc) return rc;
+    }
+    return ICNV_OK;
+}
+
+}  // namespace icnv
+
+using namespace icnv;
+
+extern "C" {
+
+// ---- lifecycle ------------------------------------------------------------------------------------
+
+int icnv_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(ICNV_E_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int icnv_init(int device) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (device < 0) device = c.ready ? c.device : 0;
+    if (c.ready && c.device == device) return ICNV_OK;
+    int n = icnv_device_count();
+    if (n <= 0) return set_error(ICNV_E_NO_DEVICE, "no CUDA device available (the library has no CPU fallback)");
+    if (device >= n) return set_error(ICNV_E_BAD_ARG, "device %d out of range (%d devices)", device, n);
+    if (c.ready) {
+        cudaSetDevice(c.device);
+        for (int s = 0; s < SLOT_COUNT; ++s) {
+            if (c.slot_ptr[s]) cudaFree(c.slot_ptr[s]);
+            c.slot_ptr[s] = nullptr;
+            c.slot_bytes[s] = 0;
+        }
+        if (c.stream) cudaStreamDestroy(c.stream);
+        c.stream = nullptr;
+        c.ready = false;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return set_error(ICNV_E_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return set_error(ICNV_E_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return set_error(ICNV_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    c.sm_count = prop.multiProcessorCount;
+    c.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return set_error(ICNV_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    c.device = device;
+    c.launches = 0;
+    c.ready = true;
+    return ICNV_OK;
+}
+
+void icnv_shutdown(void) {
+    Ctx &c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    for (int s = 0; s < SLOT_COUNT; ++s) {
+        if (c.slot_ptr[s]) cudaFree(c.slot_ptr[s]);
+        c.slot_ptr[s] = nullptr;
+        c.slot_bytes[s] = 0;
+    }
+    cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+    c.ready = false;
+}
+
+const char *icnv_last_error(void) { return g_err; }
+const char *icnv_version(void) { return "infercnv_b200 0.1.0 (sm_100a)"; }
+int64_t icnv_launch_count(void) { return ctx().launches.load(); }
+
+// ---- device-side composition of the smooth block ---------------------------------------------------------
+
+int icnv_dev_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                              const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                              int apply_log, double threshold, int window, int use_bounds, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_smooth_block_f64: bad argument");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    rc = validate_groups(C, grp_off, grp_idx, n_grp, false);
+    if (rc) return rc;
+    cudaStream_t st = pick_stream(stream);
+    const int64_t n_ref = grp_off[n_grp];
+
+    // index lists: [ref cells as given | 0..n_ref-1 (columns of the compact pass-1 buffer)]
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * 2 * (size_t)n_ref);
+    if (!d_idx) return ICNV_E_NOMEM;
+    std::vector<int32_t> iota((size_t)n_ref);
+    std::iota(iota.begin(), iota.end(), 0);
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, grp_idx, sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemcpyAsync(d_idx + n_ref, iota.data(), sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));  // iota is a stack-lifetime host buffer
+
+    double *d_means = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
+    double *d_b = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)G * 6);
+    double *d_T = (double *)scratch(SLOT_TMP, sizeof(double) * (size_t)G * (size_t)n_ref);
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!d_means || !d_b || !d_T || !d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    double *lo1 = d_b, *hi1 = d_b + G, *mid1 = d_b + 2 * G, *lo2 = d_b + 3 * G, *hi2 = d_b + 4 * G, *mid2 = d_b + 5 * G;
+
+    // pass 0: step-8 reference means on (log-transformed) input   (ops.R:771 -> :1708)
+    rc = dev_group_means(X, G, G, d_idx, grp_off, n_grp, apply_log ? 1 : 0, d_means, st);
+    if (rc) return rc;
+    rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo1, hi1, mid1, st);
+    if (rc) return rc;
+    // pass 1: steps 4..11 on the reference cells only -> compact buffer T (one column per list entry)
+    rc = icnv_dev_cell_pipeline_f64(X, G, G, d_idx, n_ref, d_T, G, chr_start, chr_len, K, apply_log,
+                                    use_bounds ? lo1 : nullptr, use_bounds ? hi1 : nullptr, use_bounds ? nullptr : mid1,
+                                    threshold, window, 1, nullptr, nullptr, nullptr, 0, d_flag, st);
+    if (rc) return rc;
+    // step-12 reference means on the centred, smoothed reference cells   (ops.R:952)
+    rc = dev_group_means(d_T, G, G, d_idx + n_ref, grp_off, n_grp, 0, d_means, st);
+    if (rc) return rc;
+    rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo2, hi2, mid2, st);
+    if (rc) return rc;
+    // pass 2: every cell, read once, written once
+    rc = icnv_dev_cell_pipeline_f64(X, G, G, nullptr, C, Y, G, chr_start, chr_len, K, apply_log,
+                                    use_bounds ? lo1 : nullptr, use_bounds ? hi1 : nullptr, use_bounds ? nullptr : mid1,
+                                    threshold, window, 1, use_bounds ? lo2 : nullptr, use_bounds ? hi2 : nullptr,
+                                    use_bounds ? nullptr : mid2, 1, d_flag, st);
+    if (rc) return rc;
+    return ICNV_OK;
+}
+
+// ---- host-pointer entry points --------------------------------------------------------------------------------
+
+#define ICNV_HOST_PROLOGUE()                       \
+    ICNV_REQUIRE_READY();                          \
+    Ctx &c = ctx();                                \
+    std::lock_guard<std::mutex> lk(c.mu);          \
+    ICNV_CUDA(cudaSetDevice(c.device));            \
+    cudaStream_t st = c.stream;                    \
+    (void)st
+
+static int upload_matrix(const double *X, int64_t n, double **dX, int slot, cudaStream_t st) {
+    *dX = (double *)scratch(slot, sizeof(double) * (size_t)n);
+    if (!*dX) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(*dX, X, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    return ICNV_OK;
+}
+
+int icnv_ref_means_f64(const double *X, int64_t G, int64_t C, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                       int inv_log, double *means) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !means || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_ref_means_f64: bad argument");
+    int rc = validate_groups(C, grp_off, grp_idx, n_grp, false);
+    if (rc) return rc;
+    double *dX;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    int64_t n_ref = grp_off[n_grp];
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_ref);
+    double *d_means = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
+    if (!d_idx || !d_means) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, grp_idx, sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    rc = dev_group_means(dX, G, G, d_idx, grp_off, n_grp, inv_log ? 2 : 0, d_means, st);
+    if (rc) return rc;
+    if (inv_log && (rc = icnv_dev_invlog_finish_f64(d_means, G * n_grp, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(means, d_means, sizeof(double) * (size_t)G * (size_t)n_grp, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+// one pass of the per-cell kernel over a host matrix: upload, run, download
+static int host_cell_pipeline(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                              const int32_t *chr_len, int K, const double *h_means, int n_grp, int use_bounds,
+                              int window, int center, cudaStream_t st) {
+    double *dX, *dY;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!dY || !d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    double *lo = nullptr, *hi = nullptr, *mid = nullptr;
+    if (h_means) {
+        double *d_means = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
+        double *d_b = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)G * 6);
+        if (!d_means || !d_b) return ICNV_E_NOMEM;
+        ICNV_CUDA(cudaMemcpyAsync(d_means, h_means, sizeof(double) * (size_t)G * (size_t)n_grp, cudaMemcpyHostToDevice, st));
+        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, d_b, d_b + G, d_b + 2 * G, st))) return rc;
+        if (use_bounds) {
+            lo = d_b;
+            hi = d_b + G;
+        } else {
+            mid = d_b + 2 * G;
+        }
+    }
+    std::vector<int32_t> one_start{0}, one_len{(int32_t)G};
+    const int32_t *cs = chr_start ? chr_start : one_start.data();
+    const int32_t *cl = chr_len ? chr_len : one_len.data();
+    int kk = chr_start ? K : 1;
+    rc = icnv_dev_cell_pipeline_f64(dX, G, G, nullptr, C, dY, G, cs, cl, kk, 0, lo, hi, mid, 0.0, window, center, nullptr,
+                                    nullptr, nullptr, 0, d_flag, st);
+    if (rc) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    return check_flag(d_flag, st);
+}
+
+int icnv_subtract_ref_f64(const double *X, double *Y, int64_t G, int64_t C, const double *means, int n_grp,
+                          int use_bounds) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || !means || G <= 0 || C <= 0 || n_grp <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_subtract_ref_f64: bad argument");
+    return host_cell_pipeline(X, Y, G, C, nullptr, nullptr, 0, means, n_grp, use_bounds, 0, 0, st);
+}
+
+int icnv_smooth_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len,
+                    int K, int window) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_smooth_f64: bad argument");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if (window >= 2 && (window & 1) == 0)
+        return set_error(ICNV_E_BAD_ARG, "window_length %d is even: refusing (the reference's result is accidental)", window);
+    return host_cell_pipeline(X, Y, G, C, chr_start, chr_len, K, nullptr, 0, 0, window, 0, st);
+}
+
+int icnv_center_f64(const double *X, double *Y, int64_t G, int64_t C, int use_median) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_center_f64: bad argument");
+    return host_cell_pipeline(X, Y, G, C, nullptr, nullptr, 0, nullptr, 0, 0, 0, use_median ? 1 : 2, st);
+}
+
+int icnv_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                          const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                          int apply_log, double threshold, int window, int use_bounds) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_smooth_block_f64: bad argument");
+    double *dX, *dY;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    if (!dY) return ICNV_E_NOMEM;
+    rc = icnv_dev_smooth_block_f64(dX, dY, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, apply_log, threshold,
+                                   window, use_bounds, st);
+    if (rc) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    return check_flag((int *)c.slot_ptr[SLOT_MISC], st);
+}
+
+int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
+                     const int32_t *grp_off, const int32_t *grp_idx, int n_grp, int m, const double *Pi,
+                     const double *delta, const double *mean, const double *sd, int32_t *states, double *margins) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !states || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd)
+        return set_error(ICNV_E_BAD_ARG, "icnv_viterbi_f64: bad argument");
+    if (m != 6 && m != 3) return set_error(ICNV_E_BAD_ARG, "m must be 6 or 3");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    rc = validate_groups(C, grp_off, grp_idx, n_grp, true);
+    if (rc) return rc;
+    double *dX;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    int32_t *d_out = (int32_t *)scratch(SLOT_OUT, sizeof(int32_t) * (size_t)(G * C));
+    if (!d_out) return ICNV_E_NOMEM;
+
+    if (n_grp == 0) {
+        uint8_t *d_st = (uint8_t *)scratch(SLOT_STATES, (size_t)(G * C));
+        double *d_mg = margins ? (double *)scratch(SLOT_TMP, sizeof(double) * (size_t)K * (size_t)C) : nullptr;
+        if (!d_st || (margins && !d_mg)) return ICNV_E_NOMEM;
+        rc = icnv_dev_viterbi_f64(dX, G, C, chr_start, chr_len, K, m, Pi, delta, mean, sd, 0, d_st, d_mg, d_flag, st);
+        if (rc) return rc;
+        if ((rc = icnv_dev_widen_states(d_st, d_out, G * C, st))) return rc;
+        if (margins)
+            ICNV_CUDA(cudaMemcpyAsync(margins, d_mg, sizeof(double) * (size_t)K * (size_t)C, cudaMemcpyDeviceToHost, st));
+    } else {
+        // group modes: x = rowMeans(X[chr, group]) (HMM.R:383), per-group median sd, trace broadcast
+        const int64_t n_idx = grp_off[n_grp];
+        int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)(n_idx + C));
+        double *d_xm = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
+        double *d_sd = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)std::max<int64_t>(n_grp, 6 * G));
+        uint8_t *d_st = (uint8_t *)scratch(SLOT_STATES, (size_t)G * (size_t)n_grp);
+        double *d_mg = margins ? (double *)scratch(SLOT_TMP, sizeof(double) * (size_t)K * (size_t)n_grp) : nullptr;
+        if (!d_idx || !d_xm || !d_sd || !d_st || (margins && !d_mg)) return ICNV_E_NOMEM;
+        std::vector<int32_t> grp_of((size_t)C, -1);
+        std::vector<double> sdm((size_t)n_grp);
+        for (int b = 0; b < n_grp; ++b) {
+            for (int32_t i = grp_off[b]; i < grp_off[b + 1]; ++i) grp_of[grp_idx[i]] = b;
+            std::vector<double> v(sd + (size_t)m * b, sd + (size_t)m * (b + 1));
+            std::sort(v.begin(), v.end());
+            sdm[b] = (m & 1) ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+            if (!(sdm[b] > 0.0)) return set_error(ICNV_E_BAD_ARG, "state sd must be positive (group %d)", b);
+        }
+        ICNV_CUDA(cudaMemcpyAsync(d_idx, grp_idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+        ICNV_CUDA(cudaMemcpyAsync(d_idx + n_idx, grp_of.data(), sizeof(int32_t) * (size_t)C, cudaMemcpyHostToDevice, st));
+        ICNV_CUDA(cudaMemcpyAsync(d_sd, sdm.data(), sizeof(double) * (size_t)n_grp, cudaMemcpyHostToDevice, st));
+        if ((rc = dev_group_means(dX, G, G, d_idx, grp_off, n_grp, 0, d_xm, st))) return rc;
+        rc = icnv_dev_viterbi_f64(d_xm, G, n_grp, chr_start, chr_len, K, m, Pi, delta, mean, d_sd, 1, d_st, d_mg, d_flag, st);
+        if (rc) return rc;
+        if ((rc = icnv_dev_scatter_group_states(d_st, G, C, d_idx + n_idx, d_out, st))) return rc;
+        if (margins)
+            ICNV_CUDA(cudaMemcpyAsync(margins, d_mg, sizeof(double) * (size_t)K * (size_t)n_grp, cudaMemcpyDeviceToHost, st));
+        ICNV_CUDA(cudaStreamSynchronize(st));  // grp_of / sdm are stack-lifetime host buffers
+    }
+    ICNV_CUDA(cudaMemcpyAsync(states, d_out, sizeof(int32_t) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    return check_flag(d_flag, st);
+}
+
+int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
+                           const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                           int window_size) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_median_filter_f64: bad argument");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, true))) return rc;
+    double *dX, *dY;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!dY || !d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    rc = icnv_dev_median_filter_f64(dX, dY, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, window_size, st);
+    if (rc) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    return check_flag(d_flag, st);
+}
+
+int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mu,
+                     double *sigma) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !idx || !mu || !sigma || G <= 0 || C <= 0 || n_idx <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_mean_sd_f64: bad argument");
+    for (int64_t i = 0; i < n_idx; ++i)
+        if (idx[i] < 0 || idx[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index out of range");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_idx);
+    double *d_out = (double *)scratch(SLOT_MISC2, 64);
+    if (!d_idx || !d_out) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+    if ((rc = icnv_dev_mean_sd_f64(dX, G, d_idx, n_idx, d_out, st))) return rc;
+    double h[2];
+    ICNV_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    *mu = h[0];
+    *sigma = h[1];
+    return ICNV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// icnv_common.cuh - context, error plumbing and small device helpers shared by the kernels of
+// libinfercnv_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <vector>
+
+#include "../../include/infercnv_b200.h"
+
+namespace icnv {
+
+// ---- per-process context -----------------------------------------------------------------------
+
+enum ScratchSlot {
+    SLOT_IN = 0,      // staged input matrix (host API)
+    SLOT_OUT,         // staged output matrix (host API)
+    SLOT_TMP,         // centred/smoothed reference columns (smooth block pass 1)
+    SLOT_PARTIAL,     // partial sums for group means
+    SLOT_MEANS,       // G x n_grp means
+    SLOT_BOUNDS,      // lo1,hi1,mid1,lo2,hi2,mid2 (6 x G)
+    SLOT_IDX,         // device copies of index lists
+    SLOT_SEGS,        // segment table of the cell pipeline
+    SLOT_BP,          // Viterbi backpointer scratch
+    SLOT_STATES,      // uint8 states
+    SLOT_MISC,        // flags, margins, small things
+    SLOT_MISC2,
+    SLOT_IDX2,
+    SLOT_SYNTH,
+    SLOT_MF,          // median-filter tile tables
+    SLOT_COUNT
+};
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    int smem_optin = 0;      // max dynamic shared memory per block (opt-in), bytes
+    cudaStream_t stream = nullptr;
+    void *slot_ptr[SLOT_COUNT] = {};
+    size_t slot_bytes[SLOT_COUNT] = {};
+    std::atomic<int64_t> launches{0};
+    std::mutex mu;
+};
+
+Ctx &ctx();
+int set_error(int code, const char *fmt, ...);
+// grow-only device scratch; returns nullptr (and sets the error) on failure
+void *scratch(int slot, size_t bytes);
+inline cudaStream_t pick_stream(void *s) { return s ? reinterpret_cast<cudaStream_t>(s) : ctx().stream; }
+inline void count_launch(int n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define ICNV_REQUIRE_READY()                                                                   \
+    do {                                                                                       \
+        if (!icnv::ctx().ready) {                                                              \
+            int rc__ = icnv_init(-1);                                                          \
+            if (rc__ != ICNV_OK) return rc__;                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define ICNV_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return icnv::set_error(ICNV_E_CUDA, "%s failed at %s:%d: %s", #call, __FILE__,     \
+                                   __LINE__, cudaGetErrorString(e__));                         \
+    } while (0)
+
+#define ICNV_CHECK_LAUNCH(name)                                                                \
+    do {                                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess)                                                                \
+            return icnv::set_error(ICNV_E_CUDA, "launch of %s failed: %s", name,               \
+                                   cudaGetErrorString(e__));                                   \
+        icnv::count_launch();                                                                  \
+    } while (0)
+
+// ---- device helpers ----------------------------------------------------------------------------
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ bool is_finite_d(double v) {
+    // exponent all ones <=> inf / nan
+    return ((__double2hiint(v) >> 20) & 0x7ff) != 0x7ff;
+}
+
+// order-preserving map double -> uint64 (and back), for bisection in "key space"
+__device__ __forceinline__ unsigned long long key_of(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double double_of_key(unsigned long long k) {
+    unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace icnv

@@ -1,0 +1,401 @@
+// icnv_viterbi.cu - K3: the i6 / i3 HMM of inferCNV as an sm_100a kernel.
+//
+// Restates Viterbi.dthmm.adj (R/inferCNV_HMM.R:1101-1176) for every (cell-or-group, chromosome)
+// sequence at once.  One thread owns one sequence; the 32 lanes of a warp are 32 consecutive
+// cells on the SAME chromosome, so the lanes run the same trip count and never diverge on length.
+// The m-state trellis row, the running path margins and the emission work all live in registers;
+// mean / log Pi / log delta sit in the kernel-parameter constant bank (warp-uniform operands).
+// Backpointers (3 bits per state, one 32-bit word per gene) go to a per-warp scratch ring laid out
+// [gene][lane], i.e. one coalesced 128-byte line per gene, sized for the longest chromosome and
+// re-used for every work item, so it stays resident in the 126 MB L2.
+//
+// Arithmetic: "exact" mode follows the reference's operation order in IEEE double without FMA
+// contraction (explicit __dmul_rn/__dadd_rn/__ddiv_rn), including nmath's pnorm_both
+// (Cody 1969) for pnorm(log.p=TRUE, lower.tail=FALSE) at HMM.R:1129,1156.  What can still differ
+// from R on x86-64 by an ulp: log() (CUDA vs glibc) and sum() (R accumulates in long double).
+// State calls only change if an arg-max is decided by less than that, which the per-sequence
+// margin output makes checkable.
+//
+// This kernel is FP64-pipe bound (6 pnorm + 12 divisions + 12 logs per cell-gene against 9 bytes
+// of HBM traffic); see DESIGN.md for the roofline discussion.
+#include <cfloat>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+#include "icnv_common.cuh"
+
+namespace icnv {
+
+constexpr int MAXM = 6;
+
+struct VitParams {
+    const double *X;
+    int64_t G, C;
+    const int32_t *item_chr_start;  // per sorted chromosome
+    const int32_t *item_chr_len;
+    int K;
+    int64_t n_tiles;   // ceil(C / 32)
+    int64_t n_items;   // K * n_tiles
+    int max_len;
+    double logPi[MAXM * MAXM];  // [j*M + k] = log P(j -> k)
+    double logdelta[MAXM];
+    double mean[MAXM];
+    double sd;             // median of the state sds (HMM.R:1122)
+    const double *sd_col;  // optional per-column median sd (group modes)
+    uint8_t *states;
+    double *margins;   // K x C (original chromosome order) or nullptr
+    const int32_t *item_chr_id;  // original chromosome index of each sorted chromosome
+    uint32_t *bp;      // n_warps * max_len * 32 words
+    unsigned long long *counter;
+    int *err_flag;     // bit 0: non-finite input, bit 1: underflow
+};
+
+// ---- nmath pnorm_both, upper tail, log.p, argument y >= 0 (Cody 1969) -------------------------------
+__device__ __forceinline__ double pnorm_upper_log_exact(double y) {
+    const double a0 = 2.2352520354606839287, a1 = 161.02823106855587881, a2 = 1067.6894854603709582,
+                 a3 = 18154.981253343561249, a4 = 0.065682337918207449113;
+    const double b0 = 47.20258190468824187, b1 = 976.09855173777669322, b2 = 10260.932208618978205,
+                 b3 = 45507.789335026729956;
+    const double c0 = 0.39894151208813466764, c1 = 8.8831497943883759412, c2 = 93.506656132177855979,
+                 c3 = 597.27027639480026226, c4 = 2494.5375852903726711, c5 = 6848.1904505362823326,
+                 c6 = 11602.651437647350124, c7 = 9842.7148383839780218, c8 = 1.0765576773720192317e-8;
+    const double d0 = 22.266688044328115691, d1 = 235.38790178262499861, d2 = 1519.377599407554805,
+                 d3 = 6485.558298266760755, d4 = 18615.571640885098091, d5 = 34900.952721145977266,
+                 d6 = 38912.003286093271411, d7 = 19685.429676859990727;
+    const double p0 = 0.21589853405795699, p1 = 0.1274011611602473639, p2 = 0.022235277870649807,
+                 p3 = 0.001421619193227893466, p4 = 2.9112874951168792e-5, p5 = 0.02307344176494017303;
+    const double q0 = 1.28426009614491121, q1 = 0.468238212480865118, q2 = 0.0659881378689285515,
+                 q3 = 0.00378239633202758244, q4 = 7.29751555083966205e-5;
+    const double SQRT32 = 5.656854249492380195206754896838;
+    const double INV_SQRT_2PI = 0.398942280401432677939946059934;
+#define M_(a, b) __dmul_rn((a), (b))
+#define A_(a, b) __dadd_rn((a), (b))
+#define D_(a, b) __ddiv_rn((a), (b))
+    double arg, A = 0.0;
+    bool central = false;
+    if (y <= 0.67448975) {
+        double xnum = 0.0, xden = 0.0;
+        if (y > DBL_EPSILON * 0.5) {
+            double xsq = M_(y, y);
+            xnum = M_(a4, xsq);
+            xden = xsq;
+            xnum = M_(A_(xnum, a0), xsq);
+            xden = M_(A_(xden, b0), xsq);
+            xnum = M_(A_(xnum, a1), xsq);
+            xden = M_(A_(xden, b1), xsq);
+            xnum = M_(A_(xnum, a2), xsq);
+            xden = M_(A_(xden, b2), xsq);
+        }
+        double temp = D_(M_(y, A_(xnum, a3)), A_(xden, b3));
+        arg = A_(0.5, -temp);
+        central = true;
+    } else if (y <= SQRT32) {
+        double xnum = M_(c8, y), xden = y;
+        xnum = M_(A_(xnum, c0), y);
+        xden = M_(A_(xden, d0), y);
+        xnum = M_(A_(xnum, c1), y);
+        xden = M_(A_(xden, d1), y);
+        xnum = M_(A_(xnum, c2), y);
+        xden = M_(A_(xden, d2), y);
+        xnum = M_(A_(xnum, c3), y);
+        xden = M_(A_(xden, d3), y);
+        xnum = M_(A_(xnum, c4), y);
+        xden = M_(A_(xden, d4), y);
+        xnum = M_(A_(xnum, c5), y);
+        xden = M_(A_(xden, d5), y);
+        xnum = M_(A_(xnum, c6), y);
+        xden = M_(A_(xden, d6), y);
+        arg = D_(A_(xnum, c7), A_(xden, d7));
+        double xsq = trunc(M_(y, 16.0)) * 0.0625;
+        double del = M_(A_(y, -xsq), A_(y, xsq));
+        A = A_(M_(M_(-xsq, xsq), 0.5), M_(-del, 0.5));
+    } else if (y < 1e170) {
+        double xsq = D_(1.0, M_(y, y));
+        double xnum = M_(p5, xsq), xden = xsq;
+        xnum = M_(A_(xnum, p0), xsq);
+        xden = M_(A_(xden, q0), xsq);
+        xnum = M_(A_(xnum, p1), xsq);
+        xden = M_(A_(xden, q1), xsq);
+        xnum = M_(A_(xnum, p2), xsq);
+        xden = M_(A_(xden, q2), xsq);
+        xnum = M_(A_(xnum, p3), xsq);
+        xden = M_(A_(xden, q3), xsq);
+        double temp = D_(M_(xsq, A_(xnum, p4)), A_(xden, q4));
+        arg = D_(A_(INV_SQRT_2PI, -temp), y);
+        double xs = trunc(M_(y, 16.0)) * 0.0625;
+        double del = M_(A_(y, -xs), A_(y, xs));
+        A = A_(M_(M_(-xs, xs), 0.5), M_(-del, 0.5));
+    } else {
+        return -INFINITY;
+    }
+    double r = log(arg);
+    return central ? r : A_(A, r);
+#undef M_
+#undef A_
+#undef D_
+}
+
+// log emission of every state for one observation, HMM.R:1129-1133 / 1156-1160
+template <int M>
+__device__ __forceinline__ void emission_exact(double x, const double (&mean)[MAXM], double sd, double (&le)[MAXM]) {
+    double e[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        double z = __ddiv_rn(fabs(__dadd_rn(x, -mean[k])), sd);
+        double lq = pnorm_upper_log_exact(z);
+        e[k] = __ddiv_rn(1.0, -lq);  // 1 / (-1 * emission)
+    }
+    double s = e[0];
+#pragma unroll
+    for (int k = 1; k < M; ++k) s = __dadd_rn(s, e[k]);
+#pragma unroll
+    for (int k = 0; k < M; ++k) le[k] = log(__ddiv_rn(e[k], s));
+}
+
+template <int M, bool MARGIN>
+__global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
+    int err = 0;
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(p.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= p.n_items) break;
+        const int ks = (int)(item / (unsigned long long)p.n_tiles);   // sorted chromosome (longest first)
+        const int64_t tile = (int64_t)(item % (unsigned long long)p.n_tiles);
+        const int cs = p.item_chr_start[ks];
+        const int n = p.item_chr_len[ks];
+        const int64_t c = tile * 32 + lane;
+        const bool active = c < p.C;
+        const int64_t cc = active ? c : (p.C - 1);  // idle lanes shadow the last cell, stores masked
+        const double *__restrict__ xcol = p.X + p.G * cc + cs;
+        uint8_t *__restrict__ scol = p.states + p.G * cc + cs;
+        if (n < 2) {  // HMM.R:1104-1107: not enough to run a trace on -> state 3
+            if (active && n == 1) scol[0] = 3;
+            if (MARGIN && active && p.margins) p.margins[p.item_chr_id[ks] + (int64_t)p.K * c] = INFINITY;
+            continue;
+        }
+        const double sd = p.sd_col ? p.sd_col[cc] : p.sd;
+
+        double nu[MAXM], mg[MAXM], le[MAXM];
+        // ---- forward ---------------------------------------------------------------------------------
+        {
+            double x = xcol[0];
+            if (!is_finite_d(x)) err |= 1;
+            emission_exact<M>(x, p.mean, sd, le);
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                nu[k] = __dadd_rn(p.logdelta[k], le[k]);
+                mg[k] = INFINITY;
+            }
+        }
+        double xnext = xcol[1];
+        for (int i = 1; i < n; ++i) {
+            double x = xnext;
+            if (i + 1 < n) xnext = xcol[i + 1];
+            if (!is_finite_d(x)) err |= 1;
+            emission_exact<M>(x, p.mean, sd, le);
+            double nn[MAXM], mgn[MAXM];
+            uint32_t word = 0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                // max_j(nu[j] + logPi[j,k]) with which.max's first-index tie rule (HMM.R:1162,1173)
+                double best = __dadd_rn(nu[0], p.logPi[0 * M + k]);
+                double second = -INFINITY;
+                int arg = 0;
+                double mga = mg[0];
+#pragma unroll
+                for (int j = 1; j < M; ++j) {
+                    double v = __dadd_rn(nu[j], p.logPi[j * M + k]);
+                    if (v > best) {
+                        second = best;
+                        best = v;
+                        arg = j;
+                        if (MARGIN) mga = mg[j];
+                    } else if (MARGIN && v > second) {
+                        second = v;
+                    }
+                }
+                nn[k] = __dadd_rn(best, le[k]);
+                word |= (uint32_t)arg << (3 * k);
+                if (MARGIN) mgn[k] = fmin(mga, best - second);
+            }
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                nu[k] = nn[k];
+                if (MARGIN) mg[k] = mgn[k];
+            }
+            bp[(int64_t)i * 32 + lane] = word;
+        }
+        // ---- termination: any(nu[n,] == -Inf) -> "Problems With Underflow" (HMM.R:1165) ---------
+        int y = 0;
+        {
+            double best = nu[0], second = -INFINITY;
+            bool under = (nu[0] == -INFINITY);
+#pragma unroll
+            for (int k = 1; k < M; ++k) {
+                under |= (nu[k] == -INFINITY);
+                if (nu[k] > best) {
+                    second = best;
+                    best = nu[k];
+                    y = k;
+                } else if (nu[k] > second) {
+                    second = nu[k];
+                }
+            }
+            if (under && active) err |= 2;
+            if (MARGIN && active && p.margins) {
+                double m = mg[0];
+#pragma unroll
+                for (int k = 1; k < M; ++k)
+                    if (y == k) m = mg[k];
+                p.margins[p.item_chr_id[ks] + (int64_t)p.K * c] = fmin(m, best - second);
+            }
+        }
+        // ---- traceback: y[i] = which.max(logPi[, y[i+1]] + nu[i, ]) = stored first arg-max ------------
+        if (active) scol[n - 1] = (uint8_t)(y + 1);
+        for (int i = n - 1; i >= 1; --i) {
+            uint32_t word = bp[(int64_t)i * 32 + lane];
+            y = (int)((word >> (3 * y)) & 7u);
+            if (active) scol[i - 1] = (uint8_t)(y + 1);
+        }
+        __syncwarp();
+    }
+    if (err && p.err_flag) atomicOr(p.err_flag, err);
+}
+
+// uint8 states -> int32 (255 = unassigned -> -1)
+__global__ void __launch_bounds__(256) widen_states_kernel(const uint8_t *__restrict__ s, int32_t *__restrict__ out,
+                                                           int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint8_t v = s[i];
+        out[i] = (v == 255) ? -1 : (int32_t)v;
+    }
+}
+
+// group-mode broadcast: states[g, c] = grp_states[g, grp_of[c]] or -1 (HMM.R:368, 399)
+__global__ void __launch_bounds__(256) scatter_group_states_kernel(const uint8_t *__restrict__ gs, int64_t G, int64_t C,
+                                                                   const int32_t *__restrict__ grp_of,
+                                                                   int32_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < G * C; i += stride) {
+        int64_t c = i / G, g = i - c * G;
+        int grp = grp_of[c];
+        out[i] = grp < 0 ? -1 : (int32_t)gs[g + G * grp];
+    }
+}
+
+}  // namespace icnv
+
+using namespace icnv;
+
+extern "C" {
+
+int icnv_dev_widen_states(const uint8_t *s, int32_t *out, int64_t n, void *stream) {
+    ICNV_REQUIRE_READY();
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    widen_states_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(s, out, n);
+    ICNV_CHECK_LAUNCH("widen_states_kernel");
+    return ICNV_OK;
+}
+
+int icnv_dev_scatter_group_states(const uint8_t *gs, int64_t G, int64_t C, const int32_t *grp_of, int32_t *out,
+                                  void *stream) {
+    ICNV_REQUIRE_READY();
+    int64_t blocks = (G * C + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    scatter_group_states_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(gs, G, C, grp_of, out);
+    ICNV_CHECK_LAUNCH("scatter_group_states_kernel");
+    return ICNV_OK;
+}
+
+int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
+                         int m, const double *Pi, const double *delta, const double *mean, const double *sd,
+                         int sd_per_col, uint8_t *states_u8, double *margins, int *err_flag, void *stream) {
+    ICNV_REQUIRE_READY();
+    Ctx &c = ctx();
+    if (!X || !states_u8 || G <= 0 || C <= 0 || !chr_start || !chr_len || K <= 0 || !Pi || !delta || !mean || !sd)
+        return set_error(ICNV_E_BAD_ARG, "icnv_dev_viterbi_f64: bad argument");
+    if (m != 6 && m != 3) return set_error(ICNV_E_BAD_ARG, "m must be 6 (i6) or 3 (i3), got %d", m);
+    cudaStream_t st = pick_stream(stream);
+
+    VitParams p;
+    p.X = X; p.G = G; p.C = C; p.K = K;
+    for (int j = 0; j < m; ++j)
+        for (int k = 0; k < m; ++k) p.logPi[j * m + k] = std::log(Pi[j + m * k]);
+    for (int k = 0; k < m; ++k) {
+        p.logdelta[k] = std::log(delta[k]);
+        p.mean[k] = mean[k];
+    }
+    const double *d_sd_col = nullptr;
+    p.sd = 0.0;
+    if (sd_per_col) {
+        d_sd_col = sd;  // device array, one median sd per column
+    } else {
+        // object$pm$sd = median(object$pm$sd), HMM.R:1122
+        std::vector<double> v(sd, sd + m);
+        std::sort(v.begin(), v.end());
+        p.sd = (m & 1) ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+        if (!(p.sd > 0.0)) return set_error(ICNV_E_BAD_ARG, "state sd must be positive");
+    }
+    p.sd_col = d_sd_col;
+
+    // chromosomes longest first, so the dynamic scheduler ends with the short ones (LPT)
+    std::vector<int> order(K);
+    for (int k = 0; k < K; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chr_len[a] > chr_len[b]; });
+    std::vector<int32_t> h(3 * (size_t)K);
+    int max_len = 1;
+    for (int k = 0; k < K; ++k) {
+        int o = order[k];
+        if (chr_len[o] < 0 || chr_start[o] < 0 || (int64_t)chr_start[o] + chr_len[o] > G)
+            return set_error(ICNV_E_BAD_ARG, "chromosome %d out of range", o);
+        h[k] = chr_start[o];
+        h[K + k] = chr_len[o];
+        h[2 * K + k] = o;
+        max_len = std::max(max_len, (int)chr_len[o]);
+    }
+    int32_t *d_items = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * 3 * (size_t)K + 64);
+    if (!d_items) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_items, h.data(), sizeof(int32_t) * 3 * (size_t)K, cudaMemcpyHostToDevice, st));
+    p.item_chr_start = d_items;
+    p.item_chr_len = d_items + K;
+    p.item_chr_id = d_items + 2 * K;
+    p.n_tiles = (C + 31) / 32;
+    p.n_items = p.n_tiles * K;
+    p.max_len = max_len;
+
+    int per_sm = 0;
+    const bool want_margin = margins != nullptr;
+    auto kern = (m == 6) ? (want_margin ? viterbi_kernel<6, true> : viterbi_kernel<6, false>)
+                         : (want_margin ? viterbi_kernel<3, true> : viterbi_kernel<3, false>);
+    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)c.sm_count * per_sm;
+    int64_t need_blocks = (p.n_items + 3) / 4;
+    if (blocks > need_blocks) blocks = need_blocks;
+    int64_t n_warps = blocks * 4;
+    uint32_t *d_bp = (uint32_t *)scratch(SLOT_BP, sizeof(uint32_t) * (size_t)n_warps * (size_t)max_len * 32);
+    if (!d_bp) return ICNV_E_NOMEM;
+    unsigned long long *d_counter = (unsigned long long *)scratch(SLOT_MISC2, 64);
+    if (!d_counter) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
+    p.bp = d_bp;
+    p.counter = d_counter;
+    p.states = states_u8;
+    p.margins = margins;
+    p.err_flag = err_flag;
+    kern<<<(unsigned)blocks, 128, 0, st>>>(p);
+    ICNV_CHECK_LAUNCH("viterbi_kernel");
+    return ICNV_OK;
+}
+
+}  // extern "C"

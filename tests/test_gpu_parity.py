@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's own
+known answers.  Needs a B200: run with `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): smoothed matrix within 1e-5 relative; HMM state calls
+bit-identical.  The smooth tests additionally report how far below that the kernels actually are.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star tolerance for the smooth block
+
+
+@pytest.fixture(scope="module")
+def api():
+    from infercnv_b200 import api as a
+    a.init(0)
+    return a
+
+
+def _close(got, want, rtol=RTOL, atol_scale=1e-12):
+    want = np.asarray(want)
+    atol = atol_scale * max(1.0, float(np.max(np.abs(want))))
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+# ---- reference known answers (tests/testthat/test_infer_cnv.R:89-172) through the ABI ---------------
+def test_subtract_ref_known_answers(api):
+    from tests.test_oracle_known_answers import (matrix_averef_five, matrix_averef_five_answer, matrix_five,
+                                                 matrix_three)
+    for mat, groups, want in [
+        (matrix_three.T, [[0, 2]], np.tile(np.arange(-1, 4, dtype=float), (3, 1))),
+        (matrix_five.T, [[1, 4]], np.tile(np.arange(-3, 2) + 0.5, (5, 1))),
+        (matrix_averef_five, [[1], [3, 5, 7], [9]], matrix_averef_five_answer),
+    ]:
+        M = api.ref_means(mat, groups)
+        np.testing.assert_allclose(M, orc.ref_means(mat, groups), rtol=1e-14)
+        got = api.subtract_ref(mat, M, use_bounds=True)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+        got_nb = api.subtract_ref(mat, M, use_bounds=False)
+        np.testing.assert_allclose(got_nb, orc.subtract_ref(mat, M, False), rtol=0, atol=1e-12)
+
+
+def test_ref_means_inv_log(api):
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(300, 50))
+    groups = [np.arange(0, 20), np.arange(25, 50)]
+    np.testing.assert_allclose(api.ref_means(X, groups, inv_log=True), orc.ref_means(X, groups, inv_log=True),
+                               rtol=1e-12)
+
+
+def test_center_known_answers_and_median(api):
+    m = np.arange(1, 22, dtype=float).reshape(7, 3, order="F")
+    want = np.tile(np.array([-3, -2, -1, 0, 1, 2, 3], dtype=float), (3, 1)).T
+    np.testing.assert_allclose(api.center(m, "mean"), want, atol=1e-12)
+    rng = np.random.default_rng(1)
+    for G in [1, 2, 3, 10, 11, 64, 65, 257, 1000, 4613, 8508, 10000, 11500]:
+        X = rng.normal(size=(G, 7))
+        X[:, 1] = 0.25                      # all equal
+        X[: G // 2, 2] = 1.0                # two big tie clusters
+        X[G // 2:, 2] = -1.0
+        X[:, 3] = np.round(X[:, 3], 1)      # many ties
+        X[:, 4] = np.exp(5 * X[:, 4])       # heavy tail
+        X[:, 5] = rng.integers(0, 3, size=G)  # three values
+        got = api.center(X, "median")
+        want = X - np.median(X, axis=0)[None, :]
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(X)))
+
+
+def test_smooth_known_answer_w5_and_identity(api):
+    from tests.test_oracle_known_answers import SMOOTH_W5, matrix_one, matrix_one_long_2
+    x = np.column_stack([matrix_one_long_2, matrix_one_long_2])
+    got = api.smooth(x, [0], [20], 5)
+    np.testing.assert_allclose(got[:, 0], SMOOTH_W5, atol=6e-3)
+    np.testing.assert_allclose(got, orc.smooth_by_chromosome(x, [0], [20], 5, literal=True), rtol=1e-13)
+    for w in (0, 1):
+        np.testing.assert_array_equal(api.smooth(matrix_one, [0], [5], w), matrix_one)
+    got = api.smooth(matrix_one, [0], [5], 5)[:, 0]
+    np.testing.assert_allclose(got, [1.67, 2.25, 3, 3.75, 4.33], atol=6e-3)
+
+
+def test_smooth_lengths_and_windows_vs_literal_oracle(api):
+    rng = np.random.default_rng(2)
+    lens = [1, 2, 3, 4, 5, 6, 50, 51, 100, 101, 102, 150, 201, 202, 203, 500, 1, 852]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G = int(np.sum(lens))
+    X = rng.normal(size=(G, 9))
+    for w in [3, 5, 51, 101, 201]:
+        got = api.smooth(X, cs, lens, w)
+        want = orc.smooth_by_chromosome(X, cs, lens, w, literal=True)
+        err = np.max(np.abs(got - want))
+        assert err < 1e-12, (w, err)
+        # single-gene chromosomes are skipped (ops.R:2417)
+        np.testing.assert_array_equal(got[cs[0]], X[cs[0]])
+        np.testing.assert_array_equal(got[cs[16]], X[cs[16]])
+
+
+def test_smooth_rejects_even_window_and_nonfinite(api):
+    from infercnv_b200._lib import InfercnvB200Error
+    X = np.ones((30, 3))
+    with pytest.raises(InfercnvB200Error) as e:
+        api.smooth(X, [0], [30], 4)
+    assert e.value.code == -3
+    X[3, 1] = np.nan
+    with pytest.raises(InfercnvB200Error) as e:
+        api.smooth(X, [0], [30], 5)
+    assert e.value.code == -5
+    with pytest.raises(InfercnvB200Error):
+        api.smooth(np.ones((30, 3)), [0, 10], [10, 10], 5)   # ranges do not tile [0, G)
+
+
+# ---- the bundled golden of the reference: count.data -> expr.data ------------------------------------
+def test_golden_example_object_smooth_block(api, example_object):
+    ex = example_object
+    cs, cl = orc.chr_ranges(ex["chr_codes"])
+    X = orc.normalize_by_seq_depth(ex["counts"])
+    got = api.smooth_block(X, cs, cl, ex["ref_groups"], apply_log=True, threshold=3.0, window_length=101)
+    want = orc.smooth_block(X, cs, cl, ex["ref_groups"])
+    rel = np.max(np.abs(got - want) / np.abs(want))
+    print(f"\n[golden 4613x20] smooth block max rel err vs oracle: {rel:.3e}")
+    assert rel < RTOL
+    assert rel < 1e-11   # what the FP64 kernels actually deliver
+    # against the reference's own stored output (needs the denoise step that follows the block)
+    ref = np.concatenate(ex["ref_groups"])
+    final = orc.clear_noise_via_ref_mean_sd(got, ref, 1.5)
+    rel_ref = np.max(np.abs(final - ex["expr"]) / np.abs(ex["expr"]))
+    print(f"[golden 4613x20] max rel err vs the reference's expr.data: {rel_ref:.3e}")
+    assert rel_ref < RTOL
+
+
+def test_oligodendroglioma_smooth_block_two_ref_groups(api, oligo):
+    cs, cl = orc.chr_ranges(oligo["chr_codes"])
+    X = orc.normalize_by_seq_depth(oligo["counts"])
+    got = api.smooth_block(X, cs, cl, oligo["ref_groups"])
+    want = orc.smooth_block(X, cs, cl, oligo["ref_groups"], nthreads=orc.max_threads())
+    rel = np.max(np.abs(got - want) / np.abs(want))
+    print(f"\n[oligodendroglioma 8508x184] smooth block max rel err vs oracle: {rel:.3e}")
+    assert rel < RTOL and rel < 1e-11
+    # no-bounds variant and no reference cells (proxy group of all observation cells, ops.R:1686-1689)
+    allobs = [np.concatenate(oligo["obs_groups"])]
+    got2 = api.smooth_block(X, cs, cl, allobs, use_bounds=False, window_length=51, threshold=2.0)
+    want2 = orc.smooth_block(X, cs, cl, allobs, use_bounds=False, window=51, threshold=2.0, nthreads=orc.max_threads())
+    assert np.max(np.abs(got2 - want2) / np.abs(want2)) < 1e-11
+
+
+# ---- HMM ------------------------------------------------------------------------------------------------------
+def _hmm_input(rng, G, C, mean, sd_noise=0.08):
+    lv = rng.integers(1, len(mean) - 1, size=(G // 50 + 1, C))
+    X = np.repeat(np.asarray(mean)[lv], 50, axis=0)[:G] + rng.normal(scale=sd_noise, size=(G, C))
+    return np.asfortranarray(X)
+
+
+@pytest.mark.parametrize("m", [6, 3])
+def test_viterbi_cells_bit_identical(api, hmm_fixture, m):
+    rng = np.random.default_rng(10 + m)
+    lens = [300, 1, 2, 90, 455, 852, 17]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(np.sum(lens)), 77
+    if m == 6:
+        mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    else:
+        mean, sd = np.array([0.9, 1.0, 1.1]), np.array([0.05] * 3)
+    X = _hmm_input(rng, G, C, mean)
+    Pi, delta = orc.hmm_params(m)
+    want, wm = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sd, want_margins=True, nthreads=orc.max_threads())
+    got, gm = api.viterbi(X, cs, lens, Pi, delta, mean, sd, want_margins=True)
+    mism = int(np.sum(got != want))
+    print(f"\n[viterbi m={m}] {G}x{C}: mismatching states {mism}; min decision margin gpu {gm.min():.3e} "
+          f"oracle {wm.min():.3e}")
+    np.testing.assert_array_equal(got, want)
+    fin = np.isfinite(wm)
+    np.testing.assert_allclose(gm[fin], wm[fin], rtol=1e-6, atol=1e-9)
+    assert (got[cs[1]] == 3).all()          # single-gene chromosome -> state 3 (HMM.R:1104-1107)
+    got2 = api.viterbi(X, cs, lens, Pi, delta, mean, sd)   # margin-free kernel instantiation
+    np.testing.assert_array_equal(got2, want)
+
+
+def test_viterbi_group_modes(api, hmm_fixture):
+    rng = np.random.default_rng(21)
+    lens = [200, 120, 1, 333]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(np.sum(lens)), 60
+    mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    X = _hmm_input(rng, G, C, mean, sd_noise=0.2)
+    Pi, delta = orc.hmm_params(6)
+    groups = [rng.permutation(np.arange(0, 25)), np.arange(30, 41), np.array([59, 45, 50])]
+    sds = np.concatenate([sd * f for f in (0.5, 0.8, 1.0)])
+    want = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sds, groups=groups)
+    got = api.viterbi(X, cs, lens, Pi, delta, mean, sds, groups=groups)
+    np.testing.assert_array_equal(got, want)
+    assert (got[:, 26] == -1).all()
+
+
+def test_viterbi_nonfinite_is_an_error(api, hmm_fixture):
+    from infercnv_b200._lib import InfercnvB200Error
+    X = np.ones((50, 4))
+    X[7, 2] = np.inf
+    Pi, delta = orc.hmm_params(6)
+    with pytest.raises(InfercnvB200Error) as e:
+        api.viterbi(X, [0], [50], Pi, delta, hmm_fixture["mean"], hmm_fixture["sd"])
+    assert e.value.code == -5
+
+
+def test_oligodendroglioma_hmm_cells_and_samples(api, oligo, hmm_fixture):
+    """config c1: real matrix through the smooth block, then i6 HMM per cell and per sample,
+    and i3 per cell, against the oracle (no R on the box: SURVEY section 8d 'c1 caveat')."""
+    cs, cl = orc.chr_ranges(oligo["chr_codes"])
+    X = orc.normalize_by_seq_depth(oligo["counts"])
+    S = api.smooth_block(X, cs, cl, oligo["ref_groups"])
+    mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    Pi, delta = orc.hmm_params(6)
+    nt = orc.max_threads()
+    want = orc.viterbi_matrix(S, cs, cl, Pi, delta, mean, sd, nthreads=nt)
+    got, gm = api.viterbi(S, cs, cl, Pi, delta, mean, sd, want_margins=True)
+    print(f"\n[c1 i6 cells] mismatches {int(np.sum(got != want))} of {got.size}; min margin {gm.min():.3e}")
+    np.testing.assert_array_equal(got, want)
+    groups = oligo["obs_groups"]
+    wantg = orc.viterbi_matrix(S, cs, cl, Pi, delta, mean, sd, groups=groups, nthreads=nt)
+    gotg = api.viterbi(S, cs, cl, Pi, delta, mean, sd, groups=groups)
+    np.testing.assert_array_equal(gotg, wantg)
+    ref = np.concatenate(oligo["ref_groups"])
+    mu, sg = api.mean_sd(S, ref)
+    mu0, sg0 = orc.mean_sd_over_cells(S, ref)
+    assert abs(mu - mu0) < 1e-12 * abs(mu0) + 1e-15 and abs(sg - sg0) < 1e-11 * sg0
+    Pi3, d3, mean3, sd3 = orc.i3_hmm_params(S, ref)
+    want3 = orc.viterbi_matrix(S, cs, cl, Pi3, d3, mean3, sd3, nthreads=nt)
+    got3 = api.viterbi(S, cs, cl, Pi3, d3, mean3, sd3)
+    np.testing.assert_array_equal(got3, want3)
+
+
+# ---- median filter ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("window_size", [3, 7, 9])
+def test_median_filter_vs_oracle(api, window_size):
+    rng = np.random.default_rng(33)
+    lens = [37, 23, 1, 140]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(np.sum(lens)), 70
+    X = np.asfortranarray(rng.normal(size=(G, C)))
+    X[:, 5] = np.round(X[:, 5])
+    groups = [rng.permutation(np.arange(0, 30)), np.array([40, 41]), np.array([33]), np.arange(45, 70)]
+    got = api.median_filter(X, cs, lens, groups, window_size)
+    want = orc.median_filter(X, cs, lens, groups, window_size, nthreads=orc.max_threads())
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(got[:, 31], X[:, 31])
+
+
+def test_median_filter_example_object_subclusters(api, example_object):
+    ex = example_object
+    cs, cl = orc.chr_ranges(ex["chr_codes"])
+    X = ex["expr"]
+    groups = ex["subclusters"]   # hclust order, as apply_median_filtering walks them
+    got = api.median_filter(X, cs, cl, groups, 7)
+    want = orc.median_filter(X, cs, cl, groups, 7, nthreads=orc.max_threads())
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-15)
