@@ -253,6 +253,7 @@ __device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT /
 
     // invariant: #(x <= lo) <= kA  and  #(x <= hi) >= kB + 1.  lo starts one ulp below the minimum.
     double lo = double_of_key(key_of(MN) - 1ull), hi = MX;
+    if (!(lo < MN)) lo = double_of_key(key_of(MN) - 2ull);  // MN == +0.0: one key below is -0.0 == MN
     int Flo = 0, Fhi = n;
     double p1 = mean - 0.08 * sd, p2 = mean + 0.08 * sd;
     bool force_bisect = false;

@@ -1,0 +1,169 @@
+"""torch-tensor wrappers of the device-pointer C ABI (icnv_dev_*), used by the benchmark and the
+multi-GPU driver.  torch is plumbing only (device memory, streams, torch.distributed); every
+kernel is in libinfercnv_b200.so.
+
+A device matrix is a torch.float64 tensor of shape (C, G), C-contiguous: that is exactly R's
+column-major G x C (a cell's genes contiguous).
+"""
+from __future__ import annotations
+
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import _lib, dist as shard
+from .api import _i32, groups_to_csr
+
+
+def _stream_ptr():
+    return ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One per process / GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        torch.cuda.set_device(self.device)
+        _lib.check(self.lib.icnv_init(self.device))
+        self.tdev = torch.device("cuda", self.device)
+
+    # ---- data ---------------------------------------------------------------------------------------
+    def synth(self, G, chr_start, chr_len, cells_global, C_total, seed) -> torch.Tensor:
+        """Synthetic depth-normalised expression for the given GLOBAL cell indices (runs of
+        consecutive indices are generated with one launch each)."""
+        cells_global = np.asarray(cells_global, dtype=np.int64)
+        cs, cl = _i32(chr_start), _i32(chr_len)
+        X = torch.empty((len(cells_global), G), dtype=torch.float64, device=self.tdev)
+        if len(cells_global) == 0:
+            return X
+        breaks = np.flatnonzero(np.diff(cells_global) != 1) + 1
+        starts = np.concatenate([[0], breaks])
+        ends = np.concatenate([breaks, [len(cells_global)]])
+        for s, e in zip(starts, ends):
+            ptr = X.data_ptr() + int(s) * G * 8
+            _lib.check(self.lib.icnv_dev_synth_f64(ptr, G, int(cells_global[s]), int(e - s), int(C_total), cs.ctypes.data,
+                                                   cl.ctypes.data, len(cs), ct.c_uint64(seed), _stream_ptr()))
+        return X
+
+    # ---- building blocks ----------------------------------------------------------------------------
+    def group_partial_sums(self, X: torch.Tensor, cells: torch.Tensor, apply_log: bool) -> torch.Tensor:
+        """(n_chunks, G) partial sums over chunks of CHUNK list entries (fixed order)."""
+        n = int(cells.numel())
+        G = X.shape[1]
+        n_chunks = (n + shard.CHUNK - 1) // shard.CHUNK
+        out = torch.empty((n_chunks, G), dtype=torch.float64, device=self.tdev)
+        if n:
+            _lib.check(self.lib.icnv_dev_group_partial_sums_f64(X.data_ptr(), G, X.stride(0), cells.data_ptr(), n,
+                                                                shard.CHUNK, int(bool(apply_log)), out.data_ptr(),
+                                                                _stream_ptr()))
+        return out
+
+    def combine_partials(self, partial: torch.Tensor, count: int) -> torch.Tensor:
+        G = partial.shape[1]
+        out = torch.empty(G, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.icnv_dev_combine_partials_f64(partial.data_ptr(), G, partial.shape[0], int(count),
+                                                          out.data_ptr(), _stream_ptr()))
+        return out
+
+    def bounds(self, means: torch.Tensor):
+        """means: (n_grp, G) -> lo, hi, mid (each G)."""
+        n_grp, G = means.shape
+        lo, hi, mid = (torch.empty(G, dtype=torch.float64, device=self.tdev) for _ in range(3))
+        _lib.check(self.lib.icnv_dev_bounds_from_means_f64(means.data_ptr(), G, n_grp, lo.data_ptr(), hi.data_ptr(),
+                                                           mid.data_ptr(), _stream_ptr()))
+        return lo, hi, mid
+
+    def cell_pipeline(self, X, cols, Y, chr_start, chr_len, apply_log, b1, threshold, window, center, b2, apply_exp2,
+                      use_bounds=True, err_flag=None):
+        G = X.shape[1]
+        cs, cl = _i32(chr_start), _i32(chr_len)
+        n_cols = int(cols.numel()) if cols is not None else X.shape[0]
+
+        def sel(b):
+            if b is None:
+                return None, None, None
+            lo, hi, mid = b
+            return (lo.data_ptr(), hi.data_ptr(), None) if use_bounds else (None, None, mid.data_ptr())
+
+        lo1, hi1, mid1 = sel(b1)
+        lo2, hi2, mid2 = sel(b2)
+        _lib.check(self.lib.icnv_dev_cell_pipeline_f64(
+            X.data_ptr(), G, X.stride(0), cols.data_ptr() if cols is not None else None, n_cols, Y.data_ptr(),
+            Y.stride(0), cs.ctypes.data, cl.ctypes.data, len(cs), int(bool(apply_log)), lo1, hi1, mid1, float(threshold),
+            int(window), int(center), lo2, hi2, mid2, int(bool(apply_exp2)),
+            err_flag.data_ptr() if err_flag is not None else None, _stream_ptr()))
+
+    # ---- the hot path ---------------------------------------------------------------------------------------
+    def smooth_block(self, X, chr_start, chr_len, ref_groups_local, ref_sizes=None, max_chunks=None, apply_log=True,
+                     threshold=3.0, window=101, use_bounds=True, out=None):
+        """run() steps 4, 8-12, 14 on this rank's cells.  ref_groups_local: per reference group the
+        LOCAL column indices this rank owns (possibly empty); ref_sizes: GLOBAL group sizes
+        (defaults to the local ones = single GPU).  With a process group initialised the
+        partial sums of the two reference-mean steps are all-gathered (NCCL)."""
+        C, G = X.shape
+        Y = torch.empty_like(X) if out is None else out
+        ref_groups_local = [np.asarray(g, dtype=np.int32) for g in ref_groups_local]
+        n_grp = len(ref_groups_local)
+        if ref_sizes is None:
+            ref_sizes = [len(g) for g in ref_groups_local]
+        if max_chunks is None:
+            max_chunks = [(len(g) + shard.CHUNK - 1) // shard.CHUNK for g in ref_groups_local]
+        d_groups = [torch.from_numpy(g).to(self.tdev) for g in ref_groups_local]
+        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+
+        def group_means(src, lists, log):
+            rows = []
+            for k in range(n_grp):
+                part = self.group_partial_sums(src, lists[k], log)
+                part = shard.allgather_partials(part, max_chunks[k])
+                rows.append(self.combine_partials(part, ref_sizes[k]))
+            return torch.stack(rows)
+
+        b1 = self.bounds(group_means(X, d_groups, apply_log))
+        # pass 1: reference cells only, up to the median centring
+        n_ref = int(sum(len(g) for g in ref_groups_local))
+        T = torch.empty((max(n_ref, 1), G), dtype=torch.float64, device=self.tdev)
+        if n_ref:
+            all_ref = torch.cat(d_groups)
+            self.cell_pipeline(X, all_ref, T, chr_start, chr_len, apply_log, b1, threshold, window, 1, None, False,
+                               use_bounds, flag)
+        t_lists, pos = [], 0
+        for g in ref_groups_local:
+            t_lists.append(torch.arange(pos, pos + len(g), dtype=torch.int32, device=self.tdev))
+            pos += len(g)
+        b2 = self.bounds(group_means(T, t_lists, False))
+        # pass 2: every local cell, one read and one write of the matrix
+        self.cell_pipeline(X, None, Y, chr_start, chr_len, apply_log, b1, threshold, window, 1, b2, True, use_bounds, flag)
+        return Y, flag
+
+    def viterbi(self, X, chr_start, chr_len, Pi, delta, mean, sd, out=None, want_margins=False):
+        """Per-cell i6 / i3 Viterbi on device data -> uint8 states (C, G)."""
+        C, G = X.shape
+        cs, cl = _i32(chr_start), _i32(chr_len)
+        Pi = np.asfortranarray(Pi, dtype=np.float64)
+        m = Pi.shape[0]
+        delta, mean, sd = (np.ascontiguousarray(v, dtype=np.float64) for v in (delta, mean, sd))
+        st = torch.empty((C, G), dtype=torch.uint8, device=self.tdev) if out is None else out
+        mg = torch.empty((C, len(cs)), dtype=torch.float64, device=self.tdev) if want_margins else None
+        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+        _lib.check(self.lib.icnv_dev_viterbi_f64(X.data_ptr(), G, C, cs.ctypes.data, cl.ctypes.data, len(cs), m,
+                                                 Pi.ctypes.data, delta.ctypes.data, mean.ctypes.data, sd.ctypes.data, 0,
+                                                 st.data_ptr(), mg.data_ptr() if mg is not None else None,
+                                                 flag.data_ptr(), _stream_ptr()))
+        return (st, flag, mg) if want_margins else (st, flag)
+
+    def median_filter(self, X, chr_start, chr_len, groups_local, window_size=7, out=None):
+        C, G = X.shape
+        cs, cl = _i32(chr_start), _i32(chr_len)
+        off, idx = groups_to_csr(groups_local)
+        Y = torch.empty_like(X) if out is None else out
+        _lib.check(self.lib.icnv_dev_median_filter_f64(X.data_ptr(), Y.data_ptr(), G, C, cs.ctypes.data, cl.ctypes.data,
+                                                       len(cs), off.ctypes.data, idx.ctypes.data, len(groups_local),
+                                                       int(window_size), _stream_ptr()))
+        return Y
+
+    def launch_count(self) -> int:
+        return int(self.lib.icnv_launch_count())

@@ -1,0 +1,109 @@
+"""Cell sharding for multi-GPU runs: one process per GPU, cells partitioned, no data-path
+collective except the all-gather of the per-gene partial sums behind the two reference-mean steps
+(subtract_ref_expr_from_obs before and after smoothing, R/inferCNV_ops.R:771, :952).
+
+Determinism: group means are summed as fixed chunks of CHUNK consecutive list entries (K1 in
+csrc/icnv_smooth.cu) and the chunks are combined in global list order.  The planner below cuts
+every reference group at multiples of CHUNK, so the chunk contents and their order are the same
+for 1, 2, 4 or 8 ranks and the means - hence the whole output - are bit-identical.
+
+Pure host logic + torch.distributed plumbing (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+CHUNK = 32  # must match dev_group_means() in csrc/icnv_api.cu
+
+
+@dataclass
+class ShardPlan:
+    """What one rank owns.  All indices are GLOBAL cell indices."""
+    rank: int
+    world: int
+    ref_slices: list[np.ndarray]   # per reference group: this rank's part of the group's list
+    other_cells: np.ndarray        # non-reference cells of this rank
+    ref_sizes: list[int]           # global size of every reference group
+    max_chunks: list[int]          # per group: max over ranks of the local chunk count (padding)
+
+    @property
+    def local_cells(self) -> np.ndarray:
+        """Global indices of the local columns, reference slices first (in group order)."""
+        parts = list(self.ref_slices) + [self.other_cells]
+        return np.concatenate(parts) if parts else np.zeros(0, np.int64)
+
+    def local_ref_groups(self) -> list[np.ndarray]:
+        """Reference groups as LOCAL column indices (columns ordered as local_cells)."""
+        out, pos = [], 0
+        for s in self.ref_slices:
+            out.append(np.arange(pos, pos + len(s), dtype=np.int32))
+            pos += len(s)
+        return out
+
+
+def split_chunk_aligned(n: int, world: int, chunk: int = CHUNK) -> list[tuple[int, int]]:
+    """Cut [0, n) into `world` contiguous ranges whose boundaries are multiples of `chunk`
+    (the last range takes the ragged tail).  Ranges may be empty when n is small."""
+    n_chunks = (n + chunk - 1) // chunk
+    base, extra = divmod(n_chunks, world)
+    out, pos = [], 0
+    for r in range(world):
+        c = base + (1 if r < extra else 0)
+        lo = min(pos * chunk, n)
+        hi = min((pos + c) * chunk, n)
+        out.append((lo, hi))
+        pos += c
+    return out
+
+
+def plan_shards(n_cells: int, ref_groups: list[np.ndarray], world: int) -> list[ShardPlan]:
+    """Partition the cells of a run over `world` ranks."""
+    ref_groups = [np.asarray(g, dtype=np.int64) for g in ref_groups]
+    is_ref = np.zeros(n_cells, dtype=bool)
+    for g in ref_groups:
+        is_ref[g] = True
+    others = np.flatnonzero(~is_ref)
+    other_parts = np.array_split(others, world)
+    cuts = [split_chunk_aligned(len(g), world) for g in ref_groups]
+    max_chunks = [max((hi - lo + CHUNK - 1) // CHUNK for lo, hi in c) for c in cuts]
+    plans = []
+    for r in range(world):
+        plans.append(ShardPlan(
+            rank=r, world=world,
+            ref_slices=[g[cuts[k][r][0]:cuts[k][r][1]] for k, g in enumerate(ref_groups)],
+            other_cells=other_parts[r],
+            ref_sizes=[len(g) for g in ref_groups],
+            max_chunks=max_chunks))
+    return plans
+
+
+def allgather_partials(local, max_chunks: int):
+    """All-gather one group's partial sums.  `local` is a torch tensor (n_local_chunks, G) on the
+    device of the process group's backend.  Returns (world * max_chunks, G): rank-major, each
+    rank's block zero-padded to `max_chunks` rows (adding 0.0 chunks does not change a sum), or
+    `local` itself when no process group is initialised (single GPU)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    G = local.shape[1]
+    padded = torch.zeros((max_chunks, G), dtype=local.dtype, device=local.device)
+    if local.shape[0]:
+        padded[: local.shape[0]] = local
+    out = torch.empty((world * max_chunks, G), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda else \
+        _allgather_list(out, padded, world)
+    return out
+
+
+def _allgather_list(out, padded, world):
+    import torch
+    import torch.distributed as dist
+
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    out.copy_(torch.cat(parts, dim=0))

@@ -1,0 +1,259 @@
+"""Host-side mirror of the reference's R interface for the hot path: same function names, argument
+meaning and error behaviour as the R functions whose bodies the GPU library replaces, so the parity
+tests read like the reference's own tests.  Every function is `f(infercnv_obj, ...) -> infercnv_obj`
+that rewrites `expr_data` and mirrors itself onto `hspike` when that slot is set, exactly like
+the R originals (e.g. R/inferCNV_ops.R:1695-1698, 2081-2084, 2427-2430).
+
+All numerics happen in libinfercnv_b200.so (CUDA); nothing here computes on the CPU beyond
+argument marshalling.  R is 1-based, this mirror is 0-based.
+"""
+from __future__ import annotations
+
+import copy
+import logging
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import api
+
+log = logging.getLogger("infercnv_b200")  # the R functions log through futile.logger's flog.info
+
+CNV_LEVELS = ["cnv:0.01", "cnv:0.5", "cnv:1", "cnv:1.5", "cnv:2", "cnv:3"]  # R/inferCNV_HMM.R:244-256
+
+
+@dataclass
+class Infercnv:
+    """The slots of the S4 class `infercnv` (R/inferCNV.R:37-47) the hot path touches."""
+    expr_data: np.ndarray                                   # genes x cells, float64 (Fortran order)
+    gene_order_chr: np.ndarray                              # gene_order$chr as codes, rows pre-sorted by chr
+    reference_grouped_cell_indices: dict = field(default_factory=dict)     # name -> 0-based cell indices
+    observation_grouped_cell_indices: dict = field(default_factory=dict)
+    tumor_subclusters: Optional[dict] = None                # {"subclusters": {group: {name: indices}}}
+    count_data: Optional[np.ndarray] = None
+    options: dict = field(default_factory=dict)
+    hspike: Optional["Infercnv"] = None                     # @.hspike
+
+    def __post_init__(self):
+        self.expr_data = np.asfortranarray(self.expr_data, dtype=np.float64)
+
+    def chr_ranges(self):
+        return api.chr_ranges(self.gene_order_chr)
+
+
+def has_reference_cells(obj: Infercnv) -> bool:
+    """R/inferCNV.R has_reference_cells: length(reference_grouped_cell_indices) != 0."""
+    return len(obj.reference_grouped_cell_indices) != 0
+
+
+def _ref_groups(obj: Infercnv):
+    # subtract_ref_expr_from_obs, R/inferCNV_ops.R:1683-1689
+    if has_reference_cells(obj):
+        log.info("subtracting mean(normal) per gene per cell across all data")
+        return [np.asarray(v) for v in obj.reference_grouped_cell_indices.values()]
+    log.info("-no reference cells specified... using mean of all cells as proxy")
+    return [np.concatenate([np.asarray(v) for v in obj.observation_grouped_cell_indices.values()])]
+
+
+def subtract_ref_expr_from_obs(infercnv_obj: Infercnv, inv_log: bool = False, use_bounds: bool = True) -> Infercnv:
+    """R/inferCNV_ops.R:1678-1702."""
+    log.info("::subtract_ref_expr_from_obs:Start inv_log=%s, use_bounds=%s", inv_log, use_bounds)
+    obj = copy.copy(infercnv_obj)
+    means = api.ref_means(obj.expr_data, _ref_groups(obj), inv_log=inv_log)        # .get_normal_gene_mean_bounds
+    log.info("-subtracting expr per gene, use_bounds=%s", use_bounds)
+    obj.expr_data = api.subtract_ref(obj.expr_data, means, use_bounds=use_bounds)  # .subtract_expr
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = subtract_ref_expr_from_obs(obj.hspike, inv_log=inv_log, use_bounds=use_bounds)
+    return obj
+
+
+def smooth_by_chromosome(infercnv_obj: Infercnv, window_length: int, smooth_ends: bool = True) -> Infercnv:
+    """R/inferCNV_ops.R:2406-2434 (`smooth_ends` is accepted and ignored there too)."""
+    obj = copy.copy(infercnv_obj)
+    if window_length < 2:
+        log.warning("window length < 2, returning original unmodified data")      # ops.R:2444-2447
+    cs, cl = obj.chr_ranges()
+    obj.expr_data = api.smooth(obj.expr_data, cs, cl, window_length)
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = smooth_by_chromosome(obj.hspike, window_length, smooth_ends)
+    return obj
+
+
+def center_cell_expr_across_chromosome(infercnv_obj: Infercnv, method: str = "mean") -> Infercnv:
+    """R/inferCNV_ops.R:2074-2088; any method other than "median" centres by the mean (:2096-2107)."""
+    log.info("::center_smooth across chromosomes per cell")
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.center(obj.expr_data, "median" if method == "median" else "mean")
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = center_cell_expr_across_chromosome(obj.hspike, method)
+    return obj
+
+
+def smooth_block(infercnv_obj: Infercnv, window_length: int = 101, max_centered_threshold: float = 3.0,
+                 apply_log: bool = True, use_bounds: bool = True) -> Infercnv:
+    """run() steps 4, 8, 9, 10, 11, 12, 14 in one library call (R/inferCNV_ops.R:614-1031), for the
+    default option set (smooth_method="pyramidinal", ref_subtract_use_mean_bounds=TRUE)."""
+    obj = copy.copy(infercnv_obj)
+    cs, cl = obj.chr_ranges()
+    obj.expr_data = api.smooth_block(obj.expr_data, cs, cl, _ref_groups(obj), apply_log=apply_log,
+                                     threshold=max_centered_threshold, window_length=window_length,
+                                     use_bounds=use_bounds)
+    if obj.hspike is not None:
+        obj.hspike = smooth_block(obj.hspike, window_length, max_centered_threshold, apply_log, use_bounds)
+    return obj
+
+
+def apply_median_filtering(infercnv_obj: Infercnv, window_size: int = 7, on_observations: bool = True,
+                           on_references: bool = True) -> Infercnv:
+    """R/noise_reduction.R:43-89.  Observations are filtered per tumour subcluster, references per
+    whole reference group, each in the order of its index list."""
+    if window_size % 2 != 1 or window_size < 2:
+        raise ValueError("::apply_median_filtering: Error, window_size is an even or < 2. "
+                         "Please specify an odd number >= 3.")
+    obj = copy.copy(infercnv_obj)
+    lists = []
+    if on_observations:
+        for tumor_type in obj.observation_grouped_cell_indices:
+            for idx in obj.tumor_subclusters["subclusters"][tumor_type].values():
+                lists.append(np.asarray(idx))
+    if on_references:
+        for idx in obj.reference_grouped_cell_indices.values():
+            lists.append(np.asarray(idx))
+    cs, cl = obj.chr_ranges()
+    obj.expr_data = api.median_filter(obj.expr_data, cs, cl, lists, window_size)
+    return obj
+
+
+# ---- HMM -----------------------------------------------------------------------------------------------
+
+def get_HMM(cnv_mean_sd: dict, t: float):
+    """.get_HMM, R/inferCNV_HMM.R:230-265: (state_transitions, delta, mean[6], sd[6])."""
+    Pi = np.full((6, 6), t, dtype=np.float64, order="F")
+    np.fill_diagonal(Pi, 1 - 5 * t)
+    delta = np.array([t, t, 1 - 5 * t, t, t, t])
+    mean = np.array([cnv_mean_sd[k]["mean"] for k in CNV_LEVELS], dtype=np.float64)
+    sd = np.array([cnv_mean_sd[k]["sd"] for k in CNV_LEVELS], dtype=np.float64)
+    return Pi, delta, mean, sd
+
+
+def i3HMM_get_HMM(sd_trend: dict, t: float, i3_p_val: float = 0.05, use_KS: bool = False):
+    """.i3HMM_get_HMM, R/inferCNV_i3HMM.R:99-156 (diagonal 1-5t as written there)."""
+    Pi = np.full((3, 3), t, dtype=np.float64, order="F")
+    np.fill_diagonal(Pi, 1 - 5 * t)
+    delta = np.array([t, 1 - 5 * t, t])
+    mu, sigma = sd_trend["mu"], sd_trend["sigma"]
+    d = sd_trend["KS_delta"] if use_KS else sd_trend["mean_delta"]
+    return Pi, delta, np.array([mu - d, mu, mu + d]), np.array([sigma] * 3)
+
+
+def i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj: Infercnv, i3_p_val: float = 0.05) -> dict:
+    """.i3HMM_get_sd_trend_by_num_cells_fit, R/inferCNV_i3HMM.R:17-80: mu / sigma over the
+    reference cells (or all observation cells) on the GPU; mean_delta = |qnorm(p, 0, sigma)|.
+    KS_delta (RNG-driven KS tests, :469-493) stays in R and is not provided."""
+    from statistics import NormalDist
+    groups = infercnv_obj.reference_grouped_cell_indices or infercnv_obj.observation_grouped_cell_indices
+    cells = np.concatenate([np.asarray(v) for v in groups.values()])
+    mu, sigma = api.mean_sd(infercnv_obj.expr_data, cells)
+    mean_delta = abs(NormalDist(0.0, sigma).inv_cdf(i3_p_val))        # determine_mean_delta_via_Z, :435-445
+    return {"mu": mu, "sigma": sigma, "mean_delta": mean_delta, "KS_delta": None}
+
+
+def _state_emission_sds(num_cells: int, cnv_mean_sd: dict, cnv_level_to_mean_sd_fit: dict) -> np.ndarray:
+    """.get_state_emission_params, R/inferCNV_HMM.R:586-614: sd = exp(predict(lm(log(sd) ~ log(num_cells)))).
+    A fit is given as (intercept, slope) of that regression."""
+    out = []
+    for lvl in CNV_LEVELS:
+        a, b = cnv_level_to_mean_sd_fit[lvl]
+        out.append(np.exp(a + b * np.log(num_cells)))
+    return np.array(out)
+
+
+def _run_hmm(obj: Infercnv, Pi, delta, mean, sd, groups=None) -> Infercnv:
+    cs, cl = obj.chr_ranges()
+    states = api.viterbi(obj.expr_data, cs, cl, Pi, delta, mean, sd, groups=groups)
+    out = copy.copy(obj)
+    out.expr_data = np.asfortranarray(states, dtype=np.float64)   # the reference stores states as doubles
+    return out
+
+
+def predict_CNV_via_HMM_on_indiv_cells(infercnv_obj: Infercnv, cnv_mean_sd: dict, t: float = 1e-6) -> Infercnv:
+    """R/inferCNV_HMM.R:284-324."""
+    log.info("predict_CNV_via_HMM_on_indiv_cells()")
+    Pi, delta, mean, sd = get_HMM(cnv_mean_sd, t)
+    return _run_hmm(infercnv_obj, Pi, delta, mean, sd)
+
+
+def predict_CNV_via_HMM_on_tumor_subclusters(infercnv_obj: Infercnv, cnv_mean_sd: dict,
+                                             cnv_level_to_mean_sd_fit: dict, t: float = 1e-6) -> Infercnv:
+    """R/inferCNV_HMM.R:345-408."""
+    log.info("predict_CNV_via_HMM_on_tumor_subclusters")
+    if infercnv_obj.tumor_subclusters is None:
+        log.warning("No subclusters defined, so instead running on whole samples")
+        return predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj, True, cnv_mean_sd, cnv_level_to_mean_sd_fit, t)
+    Pi, delta, mean, _ = get_HMM(cnv_mean_sd, t)
+    groups = [np.asarray(idx) for sub in infercnv_obj.tumor_subclusters["subclusters"].values() for idx in sub.values()]
+    sds = np.concatenate([_state_emission_sds(len(g), cnv_mean_sd, cnv_level_to_mean_sd_fit) for g in groups])
+    return _run_hmm(infercnv_obj, Pi, delta, mean, sds, groups)
+
+
+def predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj: Infercnv, cluster_by_groups: bool, cnv_mean_sd: dict,
+                                               cnv_level_to_mean_sd_fit: dict, t: float = 1e-6) -> Infercnv:
+    """R/inferCNV_HMM.R:509-567."""
+    log.info("predict_CNV_via_HMM_on_whole_tumor_samples")
+    Pi, delta, mean, _ = get_HMM(cnv_mean_sd, t)
+    obs = [np.asarray(v) for v in infercnv_obj.observation_grouped_cell_indices.values()]
+    refs = [np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()]
+    groups = (obs if cluster_by_groups else [np.concatenate(obs)]) + refs
+    sds = np.concatenate([_state_emission_sds(len(g), cnv_mean_sd, cnv_level_to_mean_sd_fit) for g in groups])
+    return _run_hmm(infercnv_obj, Pi, delta, mean, sds, groups)
+
+
+def i3HMM_predict_CNV_via_HMM_on_indiv_cells(infercnv_obj: Infercnv, i3_p_val: float = 0.05,
+                                             sd_trend: Optional[dict] = None, t: float = 1e-6,
+                                             use_KS: bool = False) -> Infercnv:
+    """R/inferCNV_i3HMM.R:180-225 (run() passes use_KS = HMM_i3_use_KS = FALSE, ops.R:274)."""
+    if sd_trend is None:
+        sd_trend = i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val)
+    Pi, delta, mean, sd = i3HMM_get_HMM(sd_trend, t, i3_p_val, use_KS)
+    return _run_hmm(infercnv_obj, Pi, delta, mean, sd)
+
+
+def i3HMM_predict_CNV_via_HMM_on_tumor_subclusters(infercnv_obj: Infercnv, i3_p_val: float = 0.05,
+                                                   sd_trend: Optional[dict] = None, t: float = 1e-6,
+                                                   use_KS: bool = False) -> Infercnv:
+    """R/inferCNV_i3HMM.R:249-308: one trace per subcluster on rowMeans, shared sigma."""
+    if sd_trend is None:
+        sd_trend = i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val)
+    Pi, delta, mean, sd = i3HMM_get_HMM(sd_trend, t, i3_p_val, use_KS)
+    groups = [np.asarray(idx) for sub in infercnv_obj.tumor_subclusters["subclusters"].values() for idx in sub.values()]
+    return _run_hmm(infercnv_obj, Pi, delta, mean, np.tile(sd, len(groups)), groups)
+
+
+def i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj: Infercnv, cluster_by_groups: bool = True,
+                                                     i3_p_val: float = 0.05, sd_trend: Optional[dict] = None,
+                                                     t: float = 1e-6, use_KS: bool = False) -> Infercnv:
+    """R/inferCNV_i3HMM.R:332-389."""
+    if sd_trend is None:
+        sd_trend = i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val)
+    Pi, delta, mean, sd = i3HMM_get_HMM(sd_trend, t, i3_p_val, use_KS)
+    obs = [np.asarray(v) for v in infercnv_obj.observation_grouped_cell_indices.values()]
+    refs = [np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()]
+    groups = (obs if cluster_by_groups else [np.concatenate(obs)]) + refs
+    return _run_hmm(infercnv_obj, Pi, delta, mean, np.tile(sd, len(groups)), groups)
+
+
+def assign_HMM_states_to_proxy_expr_vals(infercnv_obj: Infercnv) -> Infercnv:
+    """R/inferCNV_HMM.R:1191-1206 (i6): state -> {0, 0.5, 1, 1.5, 2, 3}.  A 6-entry lookup on the
+    already-downloaded state matrix (not a kernel: the reference does six masked assignments)."""
+    lut = np.array([np.nan, 0.0, 0.5, 1.0, 1.5, 2.0, 3.0])
+    obj = copy.copy(infercnv_obj)
+    st = obj.expr_data.astype(np.int64)
+    out = obj.expr_data.copy()
+    ok = (st >= 1) & (st <= 6)
+    out[ok] = lut[st[ok]]
+    obj.expr_data = out
+    return obj

@@ -39,6 +39,10 @@
 
 typedef long double ldouble;
 
+/* threads used by the element-wise / reduction helpers (drivers with an nthreads argument set it) */
+static int g_threads = 1;
+ORC_API void orc_set_num_threads(int n) { g_threads = n > 0 ? n : 1; }
+
 /* ------------------------------------------------------------------------------------------- */
 /* base-R numerics                                                                             */
 /* ------------------------------------------------------------------------------------------- */
@@ -201,16 +205,19 @@ ORC_API int orc_normalize_by_seq_depth(const double *X, double *Y, int64_t G, in
 
 /* R/inferCNV_ops.R:2756-2769 log2xplus1 */
 ORC_API void orc_log2xplus1(const double *X, double *Y, int64_t n) {
+    #pragma omp parallel for schedule(static) num_threads(g_threads)
     for (int64_t i = 0; i < n; ++i) Y[i] = log2(X[i] + 1.0);
 }
 
 /* R/inferCNV_ops.R:2814-2826 invert_log2: 2^x */
 ORC_API void orc_invert_log2(const double *X, double *Y, int64_t n) {
+    #pragma omp parallel for schedule(static) num_threads(g_threads)
     for (int64_t i = 0; i < n; ++i) Y[i] = pow(2.0, X[i]);
 }
 
 /* R/inferCNV_ops.R:2970-2983 apply_max_threshold_bounds */
 ORC_API void orc_apply_max_threshold_bounds(const double *X, double *Y, int64_t n, double threshold) {
+    #pragma omp parallel for schedule(static) num_threads(g_threads)
     for (int64_t i = 0; i < n; ++i) {
         double v = X[i];
         if (v > threshold) v = threshold;
@@ -228,56 +235,80 @@ ORC_API void orc_apply_max_threshold_bounds(const double *X, double *Y, int64_t 
 ORC_API int orc_ref_means(const double *X, int64_t G, int64_t C, const int32_t *grp_off, const int32_t *grp_idx,
                           int n_grp, int inv_log, double *means) {
     (void)C;
+    /* mean() per gene = LD sum in list order, / n, one LD refinement pass (summary.c).  The loops
+     * run cell-outer so memory is walked contiguously; per gene the additions keep list order. */
+    ldouble *s = (ldouble *)malloc(sizeof(ldouble) * (size_t)G);
+    ldouble *t = (ldouble *)malloc(sizeof(ldouble) * (size_t)G);
+    if (!s || !t) return -1;
     for (int k = 0; k < n_grp; ++k) {
         int64_t n = grp_off[k + 1] - grp_off[k];
         const int32_t *idx = grp_idx + grp_off[k];
-        double *tmp = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
-        if (!tmp) return -1;
-        for (int64_t g = 0; g < G; ++g) {
-            if (inv_log) {
-                for (int64_t i = 0; i < n; ++i) tmp[i] = pow(2.0, X[g + G * (int64_t)idx[i]]) - 1.0;
-                means[g + G * k] = log2(r_mean(tmp, n) + 1.0);
-            } else {
-                means[g + G * k] = r_mean_strided(X + g, n, G, idx);
+#pragma omp parallel num_threads(g_threads)
+        {
+#pragma omp for schedule(static)
+            for (int64_t g = 0; g < G; ++g) s[g] = 0.0L;
+            for (int64_t i = 0; i < n; ++i) {
+                const double *col = X + G * (int64_t)idx[i];
+#pragma omp for schedule(static)
+                for (int64_t g = 0; g < G; ++g) s[g] += inv_log ? (pow(2.0, col[g]) - 1.0) : col[g];
+            }
+#pragma omp for schedule(static)
+            for (int64_t g = 0; g < G; ++g) {
+                s[g] /= (ldouble)n;
+                t[g] = 0.0L;
+            }
+            for (int64_t i = 0; i < n; ++i) {
+                const double *col = X + G * (int64_t)idx[i];
+#pragma omp for schedule(static)
+                for (int64_t g = 0; g < G; ++g) t[g] += ((inv_log ? (pow(2.0, col[g]) - 1.0) : col[g]) - s[g]);
+            }
+#pragma omp for schedule(static)
+            for (int64_t g = 0; g < G; ++g) {
+                double m = (double)(s[g] + t[g] / (ldouble)n);
+                means[g + G * k] = inv_log ? log2(m + 1.0) : m;
             }
         }
-        free(tmp);
     }
+    free(s);
+    free(t);
     return 0;
 }
 
 /* R/inferCNV_ops.R:1742-1786 .subtract_expr */
 ORC_API void orc_subtract_ref(const double *X, double *Y, int64_t G, int64_t C, const double *means, int n_grp,
                               int use_bounds) {
+    double *lo = (double *)malloc(sizeof(double) * (size_t)G * 3);
+    double *hi = lo + G, *mid = lo + 2 * G;
+    double *gm = (double *)malloc(sizeof(double) * (size_t)(n_grp > 0 ? n_grp : 1));
     for (int64_t g = 0; g < G; ++g) {
-        double lo = means[g], hi = means[g];
-        double gm[64];
+        double l = means[g], h = means[g];
         for (int k = 0; k < n_grp; ++k) {
             double m = means[g + G * k];
-            if (k < 64) gm[k] = m;
-            if (m < lo) lo = m;
-            if (m > hi) hi = m;
+            gm[k] = m;
+            if (m < l) l = m;
+            if (m > h) h = m;
         }
-        double mid = (n_grp <= 64) ? r_mean(gm, n_grp) : 0.0;
-        if (n_grp > 64) {
-            double *t = (double *)malloc(sizeof(double) * (size_t)n_grp);
-            for (int k = 0; k < n_grp; ++k) t[k] = means[g + G * k];
-            mid = r_mean(t, n_grp);
-            free(t);
-        }
-        for (int64_t c = 0; c < C; ++c) {
+        lo[g] = l;
+        hi[g] = h;
+        mid[g] = r_mean(gm, n_grp);
+    }
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (int64_t c = 0; c < C; ++c) {
+        for (int64_t g = 0; g < G; ++g) {
             double x = X[g + G * c];
             double y;
             if (use_bounds) {
-                if (x > hi) y = x - hi;
-                else if (x < lo) y = x - lo;
+                if (x > hi[g]) y = x - hi[g];
+                else if (x < lo[g]) y = x - lo[g];
                 else y = 0.0;
             } else {
-                y = x - mid;
+                y = x - mid[g];
             }
             Y[g + G * c] = y;
         }
     }
+    free(lo);
+    free(gm);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -625,6 +656,7 @@ ORC_API int orc_smooth_block(const double *X, double *Y, int64_t G, int64_t C, c
                              const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
                              int apply_log, double threshold, int window, int use_bounds, int nthreads) {
     int64_t n = G * C;
+    orc_set_num_threads(nthreads);
     double *means = (double *)malloc(sizeof(double) * (size_t)(G * n_grp));
     if (!means) return -1;
     if (apply_log) orc_log2xplus1(X, Y, n);
