@@ -68,6 +68,14 @@ ICNV_API const char *icnv_version(void);
 /* Number of kernel launches issued by this library since icnv_init (for bench `gpu_launches`). */
 ICNV_API int64_t icnv_launch_count(void);
 
+/* HMM arithmetic.  mode 0: reference-order IEEE arithmetic for every sequence.  mode 1 (default):
+ * certified fast path - table emission + structured recursion, every arg-max margin checked, and
+ * each sequence whose smallest margin is below 1e-7 recomputed in mode-0 arithmetic; the state
+ * calls are the same as mode 0.  Also settable with the environment variable ICNV_HMM_MODE. */
+ICNV_API int icnv_set_hmm_mode(int mode);
+/* Number of sequences the last Viterbi call recomputed in reference-order arithmetic (syncs). */
+ICNV_API int64_t icnv_hmm_rerun_count(void);
+
 /* ---- host-pointer entry points (what the R shim binds) ---------------------------------------- */
 
 /* .get_normal_gene_mean_bounds, R/inferCNV_ops.R:1708-1735.
@@ -132,7 +140,8 @@ ICNV_API int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32
 
 /* ---- device-pointer entry points ------------------------------------------------------------- */
 /* All pointers are device pointers on the icnv_init() device unless marked host.  `stream` is a
- * cudaStream_t; NULL = the library's own stream.  Asynchronous: the caller synchronises. */
+ * cudaStream_t; NULL = the library's own (non-blocking) stream - pass cudaStreamLegacy ((void*)1) to
+ * run on the legacy default stream.  Asynchronous: the caller synchronises. */
 
 /* Partial sums for group means, fixed summation order so results do not depend on the number of
  * GPUs: cells[0..n_cells) (device, column indices into X) are cut into chunks of `chunk` list

@@ -62,6 +62,16 @@ def launch_count() -> int:
     return int(_lib.load().icnv_launch_count())
 
 
+def set_hmm_mode(mode) -> None:
+    """0 / "exact": reference-order arithmetic; 1 / "fast": certified fast path (default)."""
+    m = {"exact": 0, "fast": 1}.get(mode, mode)
+    _lib.check(_lib.load().icnv_set_hmm_mode(int(m)))
+
+
+def hmm_rerun_count() -> int:
+    return int(_lib.load().icnv_hmm_rerun_count())
+
+
 def ref_means(X, groups, inv_log=False) -> np.ndarray:
     X = _f64(X)
     G, C = X.shape

@@ -163,6 +163,9 @@ int icnv_init(int device) {
     if (e != cudaSuccess) return set_error(ICNV_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     c.device = device;
     c.launches = 0;
+    c.table_uploaded = false;
+    c.hmm_list_count = nullptr;
+    if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : 1;
     c.ready = true;
     return ICNV_OK;
 }

@@ -33,6 +33,8 @@ enum ScratchSlot {
     SLOT_IDX2,
     SLOT_SYNTH,
     SLOT_MF,          // median-filter tile tables
+    SLOT_TABLE,       // emission polynomial table
+    SLOT_LIST,        // sequences to re-run exactly
     SLOT_COUNT
 };
 
@@ -45,6 +47,9 @@ struct Ctx {
     void *slot_ptr[SLOT_COUNT] = {};
     size_t slot_bytes[SLOT_COUNT] = {};
     std::atomic<int64_t> launches{0};
+    int hmm_mode = 1;                 // 0 reference-order arithmetic, 1 certified fast path
+    bool table_uploaded = false;
+    unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list
     std::mutex mu;
 };
 

@@ -49,6 +49,20 @@ struct VitParams {
     uint32_t *bp;      // n_warps * max_len * 32 words
     unsigned long long *counter;
     int *err_flag;     // bit 0: non-finite input, bit 1: underflow
+    // list mode (exact re-run of the sequences the fast path could not certify): item q is the
+    // single sequence (chromosome list[q].x in ORIGINAL order, cell list[q].y), handled by lane 0.
+    const int2 *list;
+    const unsigned int *list_count;
+    const int32_t *chr_start_orig;  // original-order chromosome tables (list mode)
+    const int32_t *chr_len_orig;
+    // certified fast path
+    double a_diag, b_off;      // log Pi diagonal / off-diagonal (all equal)
+    double inv_sd;             // 1 / median sd
+    double tau;                // decision-margin threshold below which a sequence is re-run exactly
+    const double *table;       // device copy of icnv_emis_table
+    int2 *list_out;
+    unsigned int *list_out_count;
+    unsigned int list_cap;
 };
 
 // ---- nmath pnorm_both, upper tail, log.p, argument y >= 0 (Cody 1969) -------------------------------
@@ -160,23 +174,36 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
     uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
     int err = 0;
 
+    const int64_t n_items = p.list ? (int64_t)min(*p.list_count, p.list_cap) : p.n_items;
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(p.counter, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if ((int64_t)item >= p.n_items) break;
-        const int ks = (int)(item / (unsigned long long)p.n_tiles);   // sorted chromosome (longest first)
-        const int64_t tile = (int64_t)(item % (unsigned long long)p.n_tiles);
-        const int cs = p.item_chr_start[ks];
-        const int n = p.item_chr_len[ks];
-        const int64_t c = tile * 32 + lane;
-        const bool active = c < p.C;
-        const int64_t cc = active ? c : (p.C - 1);  // idle lanes shadow the last cell, stores masked
+        if ((int64_t)item >= n_items) break;
+        int ks, cs, n;
+        int64_t c;
+        bool active;
+        if (p.list) {
+            const int2 e = p.list[item];
+            ks = e.x;
+            cs = p.chr_start_orig[ks];
+            n = p.chr_len_orig[ks];
+            c = e.y;
+            active = lane == 0;
+        } else {
+            ks = (int)(item / (unsigned long long)p.n_tiles);   // sorted chromosome (longest first)
+            const int64_t tile = (int64_t)(item % (unsigned long long)p.n_tiles);
+            cs = p.item_chr_start[ks];
+            n = p.item_chr_len[ks];
+            c = tile * 32 + lane;
+            active = c < p.C;
+        }
+        const int64_t cc = (c < p.C) ? c : (p.C - 1);  // idle lanes shadow a valid cell, stores masked
         const double *__restrict__ xcol = p.X + p.G * cc + cs;
         uint8_t *__restrict__ scol = p.states + p.G * cc + cs;
         if (n < 2) {  // HMM.R:1104-1107: not enough to run a trace on -> state 3
             if (active && n == 1) scol[0] = 3;
-            if (MARGIN && active && p.margins) p.margins[p.item_chr_id[ks] + (int64_t)p.K * c] = INFINITY;
+            if (MARGIN && active && p.margins) p.margins[(p.list ? ks : p.item_chr_id[ks]) + (int64_t)p.K * c] = INFINITY;
             continue;
         }
         const double sd = p.sd_col ? p.sd_col[cc] : p.sd;
@@ -253,7 +280,7 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
 #pragma unroll
                 for (int k = 1; k < M; ++k)
                     if (y == k) m = mg[k];
-                p.margins[p.item_chr_id[ks] + (int64_t)p.K * c] = fmin(m, best - second);
+                p.margins[(p.list ? ks : p.item_chr_id[ks]) + (int64_t)p.K * c] = fmin(m, best - second);
             }
         }
         // ---- traceback: y[i] = which.max(logPi[, y[i+1]] + nu[i, ]) = stored first arg-max ------------
@@ -262,6 +289,246 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
             uint32_t word = bp[(int64_t)i * 32 + lane];
             y = (int)((word >> (3 * y)) & 7u);
             if (active) scol[i - 1] = (uint8_t)(y + 1);
+        }
+        __syncwarp();
+    }
+    if (err && p.err_flag) atomicOr(p.err_flag, err);
+}
+
+
+// =================================================================================================
+// certified fast path
+// =================================================================================================
+//
+// Same recursion, two changes that cannot alter a state call without being noticed:
+//  (1) emission.  log(e_k / sum_j e_j) = g(z_k) - log(sum_j e_j) with g(z) = -log(-log Q(z)).  The
+//      second term is the same for every state of a gene, so it shifts all path scores equally and
+//      no arg-max sees it: it is dropped.  g comes from a piecewise degree-4 table
+//      (icnv_emission_table.inc, |error| < 5e-13, checked against 50-digit arithmetic); z beyond the
+//      table falls back to the nmath evaluation.
+//  (2) max_j(nu[j] + logPi[j,k]) uses the structure of .get_HMM's matrix (one diagonal value a,
+//      one off-diagonal value b, R/inferCNV_HMM.R:233-238): the winner is either "stay" (nu[k]+a)
+//      or the best other state (+b), found from the top three of nu+b, with which.max's
+//      first-index rule.
+// Certificate: every arg-max (all states, all genes, and the final one) records the gap between
+// winner and runner-up.  Scores of the two arithmetics differ by at most n * (table error +
+// rounding) ~ 1e-8 for n <= 3000, so a sequence whose smallest gap exceeds tau = 1e-7 has the same
+// trace in both.  Sequences below tau are appended to a list and recomputed by the exact kernel
+// above (list mode); their count is reported.
+#include "icnv_emission_table.inc"
+
+constexpr int TG = 8;        // genes per staged tile
+constexpr int TS = TG + 1;   // padded row stride in doubles (bank-conflict-free column reads)
+constexpr int FAST_WARPS = 8;
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;  // src-size 0: zero-fill, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int M>
+__global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const VitParams p) {
+    extern __shared__ __align__(16) double sm[];
+    double *tab = sm;                                            // [5][ICNV_EMIS_N]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tiles = sm + 5 * ICNV_EMIS_N + warp * (2 * 32 * TS);  // two staged x tiles per warp
+    for (int i = threadIdx.x; i < 5 * ICNV_EMIS_N; i += blockDim.x) tab[i] = p.table[i];
+    __syncthreads();
+
+    const int64_t warp_global = (int64_t)blockIdx.x * FAST_WARPS + warp;
+    uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
+    const double a = p.a_diag, b = p.b_off;
+    int err = 0;
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(p.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= p.n_items) break;
+        const int ks = (int)(item / (unsigned long long)p.n_tiles);
+        const int64_t tile = (int64_t)(item % (unsigned long long)p.n_tiles);
+        const int cs = p.item_chr_start[ks];
+        const int n = p.item_chr_len[ks];
+        const int64_t c0 = tile * 32;
+        const int64_t c = c0 + lane;
+        const bool active = c < p.C;
+        const int64_t cc = active ? c : (p.C - 1);
+        uint8_t *__restrict__ scol = p.states + p.G * cc;
+        if (n < 2) {
+            if (active && n == 1) scol[cs] = 3;
+            continue;
+        }
+        const double inv_sd = p.sd_col ? 1.0 / p.sd_col[cc] : p.inv_sd;
+        const double sd = p.sd_col ? p.sd_col[cc] : p.sd;
+        const int g_lo = cs, g_hi = cs + n;
+        const int b_first = g_lo / TG, b_last = (g_hi - 1) / TG;
+
+        // stage tile `blk` (TG genes x 32 cells) into buffer `buf`: 8 cp.async per lane, each
+        // warp instruction covers 4 cells x 8 consecutive genes (4 x 64 contiguous bytes)
+        auto issue_tile = [&](int blk, int buf) {
+            double *dst = tiles + buf * (32 * TS);
+            const int col = lane & 7;
+            const int64_t gene = (int64_t)blk * TG + col;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int row = q * 4 + (lane >> 3);
+                int64_t cell = c0 + row;
+                if (cell >= p.C) cell = p.C - 1;
+                const bool ok = gene < p.G;
+                const double *src = p.X + p.G * cell + (ok ? gene : 0);
+                cp_async8(dst + row * TS + col, src, ok);
+            }
+        };
+
+        double nu[MAXM];
+        double gapmin = INFINITY;
+        issue_tile(b_first, 0);
+        cp_async_commit();
+        for (int blk = b_first; blk <= b_last; ++blk) {
+            const int buf = (blk - b_first) & 1;
+            if (blk < b_last) {
+                issue_tile(blk + 1, buf ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const double *row = tiles + buf * (32 * TS) + lane * TS;
+#pragma unroll
+            for (int j = 0; j < TG; ++j) {
+                const int g = blk * TG + j;
+                if (g < g_lo || g >= g_hi) continue;  // warp-uniform
+                const int i = g - g_lo;
+                const double x = row[j];
+                if (!is_finite_d(x)) err |= 1;
+                // ---- emissions ------------------------------------------------------------------
+                double le[MAXM];
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const double z = fabs(x - p.mean[k]) * inv_sd;
+                    double v;
+                    if (z < (double)ICNV_EMIS_ZMAX) {
+                        const int idx = __double2int_rz(z * (double)ICNV_EMIS_INVW);
+                        const double u = fma(z, 2.0 * ICNV_EMIS_INVW, -(double)(2 * idx + 1));
+                        const double *t = tab + idx;
+                        v = fma(u, t[4 * ICNV_EMIS_N], t[3 * ICNV_EMIS_N]);
+                        v = fma(u, v, t[2 * ICNV_EMIS_N]);
+                        v = fma(u, v, t[1 * ICNV_EMIS_N]);
+                        v = fma(u, v, t[0]);
+                    } else {  // beyond the table (|x - mean| > 24 sd): nmath evaluation
+                        const double zz = __ddiv_rn(fabs(__dadd_rn(x, -p.mean[k])), sd);
+                        v = -log(-pnorm_upper_log_exact(zz));
+                    }
+                    le[k] = v;
+                }
+                if (i == 0) {
+#pragma unroll
+                    for (int k = 0; k < M; ++k) nu[k] = p.logdelta[k] + le[k];
+                    continue;
+                }
+                // ---- top three of t_j = nu[j] + b, first index on ties ------------------------------
+                double t[MAXM];
+#pragma unroll
+                for (int k = 0; k < M; ++k) t[k] = nu[k] + b;
+                double T1 = t[0];
+                int i1 = 0;
+#pragma unroll
+                for (int k = 1; k < M; ++k)
+                    if (t[k] > T1) {
+                        T1 = t[k];
+                        i1 = k;
+                    }
+                double T2 = -INFINITY;
+                int i2 = -1;
+#pragma unroll
+                for (int k = 0; k < M; ++k)
+                    if (k != i1 && t[k] > T2) {
+                        T2 = t[k];
+                        i2 = k;
+                    }
+                double T3 = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < M; ++k)
+                    if (k != i1 && k != i2 && t[k] > T3) T3 = t[k];
+                // ---- per state: stay (nu[k] + a) against the best other state ---------------------------
+                uint32_t word = 0;
+                double nn[MAXM];
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const bool is1 = (k == i1);
+                    const double other = is1 ? T2 : T1;
+                    const int oi = is1 ? i2 : i1;
+                    const double nxt = (is1 || k == i2) ? T3 : T2;
+                    const double d = nu[k] + a;
+                    const bool stay = (d > other) || (d == other && k < oi);
+                    const double best = stay ? d : other;
+                    const double second = stay ? other : fmax(d, nxt);
+                    gapmin = fmin(gapmin, best - second);
+                    nn[k] = best + le[k];
+                    word |= (uint32_t)(stay ? k : oi) << (3 * k);
+                }
+#pragma unroll
+                for (int k = 0; k < M; ++k) nu[k] = nn[k];
+                bp[(int64_t)i * 32 + lane] = word;
+            }
+            __syncwarp();
+        }
+        // ---- termination ------------------------------------------------------------------------------
+        int y = 0;
+        {
+            double best = nu[0], second = -INFINITY;
+            bool under = (nu[0] == -INFINITY);
+#pragma unroll
+            for (int k = 1; k < M; ++k) {
+                under |= (nu[k] == -INFINITY);
+                if (nu[k] > best) {
+                    second = best;
+                    best = nu[k];
+                    y = k;
+                } else if (nu[k] > second) {
+                    second = nu[k];
+                }
+            }
+            if (under && active) err |= 2;
+            gapmin = fmin(gapmin, best - second);
+        }
+        // uncertified sequences go to the exact kernel (NaN gaps compare false -> also listed)
+        if (active && !(gapmin >= p.tau)) {
+            unsigned pos = atomicAdd(p.list_out_count, 1u);
+            if (pos < p.list_cap) p.list_out[pos] = make_int2(p.item_chr_id[ks], (int)c);
+        }
+        // ---- traceback; states leave as 8-byte words when the layout allows it ---------------------
+        const bool wide = ((p.G & 7) == 0);  // then (G*c + g) is 8-aligned whenever g is
+        unsigned long long pack = 0;
+        for (int i = n - 1; i >= 0; --i) {
+            const int g = g_lo + i;
+            if (wide) {
+                pack |= (unsigned long long)(y + 1) << (8 * (g & 7));
+                if ((g & 7) == 0 || i == 0) {
+                    if (active) {
+                        const int gb = g & ~7;
+                        if (gb >= g_lo && gb + 8 <= g_hi) {
+                            *reinterpret_cast<unsigned long long *>(scol + gb) = pack;
+                        } else {  // ragged first / last block of the chromosome
+                            for (int q = 0; q < 8; ++q) {
+                                const int gg = gb + q;
+                                if (gg >= g_lo && gg < g_hi && gg >= g) scol[gg] = (uint8_t)(pack >> (8 * q));
+                            }
+                        }
+                    }
+                    pack = 0;
+                } 
+            } else if (active) {
+                scol[g] = (uint8_t)(y + 1);
+            }
+            if (i > 0) y = (int)((bp[(int64_t)i * 32 + lane] >> (3 * y)) & 7u);
         }
         __syncwarp();
     }
@@ -352,7 +619,7 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     std::vector<int> order(K);
     for (int k = 0; k < K; ++k) order[k] = k;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chr_len[a] > chr_len[b]; });
-    std::vector<int32_t> h(3 * (size_t)K);
+    std::vector<int32_t> h(5 * (size_t)K);
     int max_len = 1;
     for (int k = 0; k < K; ++k) {
         int o = order[k];
@@ -361,41 +628,118 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
         h[k] = chr_start[o];
         h[K + k] = chr_len[o];
         h[2 * K + k] = o;
+        h[3 * K + k] = chr_start[k];
+        h[4 * K + k] = chr_len[k];
         max_len = std::max(max_len, (int)chr_len[o]);
     }
-    int32_t *d_items = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * 3 * (size_t)K + 64);
+    int32_t *d_items = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * 5 * (size_t)K + 64);
     if (!d_items) return ICNV_E_NOMEM;
-    ICNV_CUDA(cudaMemcpyAsync(d_items, h.data(), sizeof(int32_t) * 3 * (size_t)K, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemcpyAsync(d_items, h.data(), sizeof(int32_t) * 5 * (size_t)K, cudaMemcpyHostToDevice, st));
     p.item_chr_start = d_items;
     p.item_chr_len = d_items + K;
     p.item_chr_id = d_items + 2 * K;
+    p.chr_start_orig = d_items + 3 * K;
+    p.chr_len_orig = d_items + 4 * K;
     p.n_tiles = (C + 31) / 32;
     p.n_items = p.n_tiles * K;
     p.max_len = max_len;
-
-    int per_sm = 0;
-    const bool want_margin = margins != nullptr;
-    auto kern = (m == 6) ? (want_margin ? viterbi_kernel<6, true> : viterbi_kernel<6, false>)
-                         : (want_margin ? viterbi_kernel<3, true> : viterbi_kernel<3, false>);
-    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
-    if (per_sm < 1) per_sm = 1;
-    int64_t blocks = (int64_t)c.sm_count * per_sm;
-    int64_t need_blocks = (p.n_items + 3) / 4;
-    if (blocks > need_blocks) blocks = need_blocks;
-    int64_t n_warps = blocks * 4;
-    uint32_t *d_bp = (uint32_t *)scratch(SLOT_BP, sizeof(uint32_t) * (size_t)n_warps * (size_t)max_len * 32);
-    if (!d_bp) return ICNV_E_NOMEM;
-    unsigned long long *d_counter = (unsigned long long *)scratch(SLOT_MISC2, 64);
-    if (!d_counter) return ICNV_E_NOMEM;
-    ICNV_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
-    p.bp = d_bp;
-    p.counter = d_counter;
+    p.list = nullptr;
+    p.list_count = nullptr;
     p.states = states_u8;
     p.margins = margins;
     p.err_flag = err_flag;
-    kern<<<(unsigned)blocks, 128, 0, st>>>(p);
-    ICNV_CHECK_LAUNCH("viterbi_kernel");
+
+    // counters: [0] work counter of the main launch, [1] work counter of the list launch, [2] list length
+    unsigned long long *d_counter = (unsigned long long *)scratch(SLOT_MISC2, 64);
+    if (!d_counter) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_counter, 0, 3 * sizeof(unsigned long long), st));
+    p.counter = d_counter;
+    c.hmm_list_count = reinterpret_cast<unsigned int *>(d_counter + 2);
+
+    const bool want_margin = margins != nullptr;
+    // the fast path needs .get_HMM's structure: one diagonal and one off-diagonal value
+    bool structured = true;
+    for (int j = 0; j < m && structured; ++j)
+        for (int k = 0; k < m; ++k)
+            if (Pi[j + m * k] != (j == k ? Pi[0] : Pi[1])) structured = false;
+    const bool use_fast = (c.hmm_mode == 1) && structured && !want_margin;
+
+    if (!use_fast) {
+        int per_sm = 0;
+        auto kern = (m == 6) ? (want_margin ? viterbi_kernel<6, true> : viterbi_kernel<6, false>)
+                             : (want_margin ? viterbi_kernel<3, true> : viterbi_kernel<3, false>);
+        ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+        if (per_sm < 1) per_sm = 1;
+        int64_t blocks = (int64_t)c.sm_count * per_sm;
+        int64_t need_blocks = (p.n_items + 3) / 4;
+        if (blocks > need_blocks) blocks = need_blocks;
+        uint32_t *d_bp = (uint32_t *)scratch(SLOT_BP, sizeof(uint32_t) * (size_t)(blocks * 4) * (size_t)max_len * 32);
+        if (!d_bp) return ICNV_E_NOMEM;
+        p.bp = d_bp;
+        kern<<<(unsigned)blocks, 128, 0, st>>>(p);
+        ICNV_CHECK_LAUNCH("viterbi_kernel");
+        return ICNV_OK;
+    }
+
+    // ---- certified fast path + exact re-run of the uncertified sequences --------------------------------
+    double *d_table = (double *)scratch(SLOT_TABLE, sizeof(icnv_emis_table));
+    if (!d_table) return ICNV_E_NOMEM;
+    if (!c.table_uploaded) {
+        ICNV_CUDA(cudaMemcpyAsync(d_table, icnv_emis_table, sizeof(icnv_emis_table), cudaMemcpyHostToDevice, st));
+        ICNV_CUDA(cudaStreamSynchronize(st));
+        c.table_uploaded = true;
+    }
+    const size_t list_cap = (size_t)K * (size_t)C;
+    int2 *d_list = (int2 *)scratch(SLOT_LIST, sizeof(int2) * list_cap);
+    if (!d_list) return ICNV_E_NOMEM;
+    p.a_diag = p.logPi[0];
+    p.b_off = p.logPi[1];
+    p.inv_sd = sd_per_col ? 0.0 : 1.0 / p.sd;
+    p.tau = 1e-7;
+    p.table = d_table;
+    p.list_out = d_list;
+    p.list_out_count = c.hmm_list_count;
+    p.list_cap = (unsigned int)std::min<size_t>(list_cap, 0xffffffffu);
+
+    auto fkern = (m == 6) ? viterbi_fast_kernel<6> : viterbi_fast_kernel<3>;
+    auto lkern = (m == 6) ? viterbi_kernel<6, false> : viterbi_kernel<3, false>;
+    const size_t smem = sizeof(double) * (5 * ICNV_EMIS_N + FAST_WARPS * 2 * 32 * TS);
+    ICNV_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fkern, FAST_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)c.sm_count * per_sm;
+    int64_t need_blocks = (p.n_items + FAST_WARPS - 1) / FAST_WARPS;
+    if (blocks > need_blocks) blocks = need_blocks;
+    const int64_t list_blocks = c.sm_count;  // 4 warps each; the list is short
+    const int64_t n_warps = std::max<int64_t>(blocks * FAST_WARPS, list_blocks * 4);
+    uint32_t *d_bp = (uint32_t *)scratch(SLOT_BP, sizeof(uint32_t) * (size_t)n_warps * (size_t)max_len * 32);
+    if (!d_bp) return ICNV_E_NOMEM;
+    p.bp = d_bp;
+    fkern<<<(unsigned)blocks, FAST_WARPS * 32, smem, st>>>(p);
+    ICNV_CHECK_LAUNCH("viterbi_fast_kernel");
+    // exact re-run of whatever the certificate rejected (list length is read on the device)
+    p.list = d_list;
+    p.list_count = c.hmm_list_count;
+    p.counter = d_counter + 1;
+    lkern<<<(unsigned)list_blocks, 128, 0, st>>>(p);
+    ICNV_CHECK_LAUNCH("viterbi_kernel(list)");
     return ICNV_OK;
+}
+
+int icnv_set_hmm_mode(int mode) {
+    if (mode != 0 && mode != 1) return set_error(ICNV_E_BAD_ARG, "hmm mode must be 0 (reference-order) or 1 (certified fast)");
+    ctx().hmm_mode = mode;
+    return ICNV_OK;
+}
+
+int64_t icnv_hmm_rerun_count(void) {
+    Ctx &c = ctx();
+    if (!c.ready || !c.hmm_list_count) return 0;
+    unsigned int h = 0;
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(&h, c.hmm_list_count, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)h;
 }
 
 }  // extern "C"

@@ -17,7 +17,11 @@ from .api import _i32, groups_to_csr
 
 
 def _stream_ptr():
-    return ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream as the `void *stream` of the device ABI.  torch's default stream is
+    the legacy NULL stream (handle 0), which the ABI reserves for "the library's own stream": pass
+    cudaStreamLegacy (handle 0x1) for it instead, so our launches stay ordered with torch's ops."""
+    h = torch.cuda.current_stream().cuda_stream
+    return ct.c_void_p(h if h else 1)
 
 
 class Engine:

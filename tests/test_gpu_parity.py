@@ -178,6 +178,73 @@ def test_viterbi_cells_bit_identical(api, hmm_fixture, m):
     np.testing.assert_array_equal(got2, want)
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_viterbi_modes_agree_with_oracle_at_scale(api, hmm_fixture, mode):
+    """2e7 cell-genes of the bench's synthetic structure: the certified fast path and the
+    reference-order path must both reproduce the oracle's states exactly."""
+    rng = np.random.default_rng(99)
+    lens = np.array([852, 615, 535, 288, 420, 453, 458, 297, 349, 363, 514, 472, 162, 301, 274, 397, 546, 126, 545,
+                     239, 90, 212])
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(lens.sum()), 1500
+    mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    base = 1.0 + 0.04 * rng.normal(size=(G, C))
+    # smooth-ish CNV segments so that there are real change points with small margins
+    for c in range(0, C, 3):
+        k = rng.integers(0, len(lens))
+        base[cs[k]:cs[k] + lens[k], c] += rng.choice([-0.25, 0.2, 0.45])
+    X = np.asfortranarray(base)
+    Pi, delta = orc.hmm_params(6)
+    want = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sd, nthreads=orc.max_threads())
+    api.set_hmm_mode(mode)
+    try:
+        got = api.viterbi(X, cs, lens, Pi, delta, mean, sd)
+        reruns = api.hmm_rerun_count()
+    finally:
+        api.set_hmm_mode("fast")
+    print(f"\n[viterbi {mode}] {G}x{C}: mismatches {int(np.sum(got != want))}, sequences re-run exactly: {reruns} "
+          f"of {C * len(lens)}")
+    np.testing.assert_array_equal(got, want)
+    if mode == "exact":
+        assert reruns == 0
+
+
+def test_viterbi_fast_path_exact_ties_are_rerun(api):
+    """Two states with identical scores at every gene (dyadic, symmetric means): the certificate
+    sees a zero margin, the sequences are recomputed in reference-order arithmetic, and the
+    first-index tie rule of which.max (HMM.R:1170,1173) decides as in the oracle."""
+    G, C = 200, 40
+    X = np.ones((G, C), order="F")
+    X[50:120, ::2] = 1.25
+    mean, sd = np.array([0.5, 1.5, 3.0]), np.array([0.25] * 3)
+    t = 1e-6
+    Pi = np.full((3, 3), t, order="F")
+    np.fill_diagonal(Pi, 1 - 5 * t)
+    delta = np.array([1 / 3, 1 / 3, 1 / 3])
+    want = orc.viterbi_matrix(X, [0, 150], [150, 50], Pi, delta, mean, sd)
+    got = api.viterbi(X, [0, 150], [150, 50], Pi, delta, mean, sd)
+    reruns = api.hmm_rerun_count()
+    np.testing.assert_array_equal(got, want)
+    assert reruns > 0
+    print(f"\n[viterbi ties] {reruns} of {2 * C} sequences re-run")
+
+
+def test_viterbi_unstructured_transition_matrix_and_far_outliers(api, hmm_fixture):
+    rng = np.random.default_rng(5)
+    G, C = 400, 33
+    mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    X = np.asfortranarray(1.0 + 0.1 * rng.normal(size=(G, C)))
+    X[10, 3] = 9.0          # |x - mean| / sd > 24: beyond the emission table
+    X[200:230, 7] = 40.0
+    Pi, delta = orc.hmm_params(6)
+    want = orc.viterbi_matrix(X, [0], [G], Pi, delta, mean, sd)
+    np.testing.assert_array_equal(api.viterbi(X, [0], [G], Pi, delta, mean, sd), want)
+    Pi2 = Pi.copy()
+    Pi2[0, 1] = 5e-6        # not .get_HMM's structure: generic kernel
+    want2 = orc.viterbi_matrix(X, [0], [G], Pi2, delta, mean, sd)
+    np.testing.assert_array_equal(api.viterbi(X, [0], [G], Pi2, delta, mean, sd), want2)
+
+
 def test_viterbi_group_modes(api, hmm_fixture):
     rng = np.random.default_rng(21)
     lens = [200, 120, 1, 333]
