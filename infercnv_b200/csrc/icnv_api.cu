@@ -164,6 +164,7 @@ int icnv_init(int device) {
     c.device = device;
     c.launches = 0;
     c.table_uploaded = false;
+    c.math_tables_uploaded = false;
     c.hmm_list_count = nullptr;
     if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : 1;
     c.ready = true;

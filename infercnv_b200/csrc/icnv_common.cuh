@@ -35,6 +35,7 @@ enum ScratchSlot {
     SLOT_MF,          // median-filter tile tables
     SLOT_TABLE,       // emission polynomial table
     SLOT_LIST,        // sequences to re-run exactly
+    SLOT_LE,          // per-warp emission rows of the exact re-run
     SLOT_COUNT
 };
 
@@ -49,6 +50,7 @@ struct Ctx {
     std::atomic<int64_t> launches{0};
     int hmm_mode = 1;                 // 0 reference-order arithmetic, 1 certified fast path
     bool table_uploaded = false;
+    bool math_tables_uploaded = false;
     unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list
     std::mutex mu;
 };

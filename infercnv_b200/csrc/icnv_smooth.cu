@@ -16,6 +16,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 
 #include "icnv_common.cuh"
 
@@ -116,10 +118,12 @@ __global__ void __launch_bounds__(256) invlog_finish_kernel(double *__restrict__
 // =================================================================================================
 
 struct Seg {
-    int start;  // first gene of the segment
-    int len;    // number of genes (0 = idle thread)
-    int cs;     // chromosome start
-    int ce;     // chromosome end (exclusive)
+    int start;   // first gene of the segment
+    int len;     // number of genes (0 = idle thread)
+    int cs;      // chromosome start
+    int ce;      // chromosome end (exclusive)
+    int tfirst;  // first thread of this chromosome (== own index for idle threads)
+    int chr;     // chromosome index
 };
 
 struct CellParams {
@@ -138,11 +142,13 @@ struct CellParams {
     const double *lo2, *hi2, *mid2;
     int apply_exp2;
     int *err_flag;
-    int s_elems;  // doubles reserved for the column (G rounded up to even)
+    int s_elems;  // doubles reserved per column buffer (G rounded up to even)
+    int K;
 };
 
-constexpr int LMAX = 24;       // genes per thread kept in registers across the median
 constexpr int CAND_MAX = 64;   // candidates ranked directly at the end of the selection
+
+__device__ unsigned long long g_stats[4];  // [0] median rounds, [1] medians, [2] split exits, [3] gather exits
 
 // ---- block-wide reductions with one __syncthreads each (double-buffered scratch) ----------------
 template <int NW>
@@ -155,59 +161,49 @@ template <int NW>
 __device__ __forceinline__ void block_sum2i(Red<NW> &r, int &phase, int a, int b, int &A, int &B) {
     a = __reduce_add_sync(0xffffffffu, a);
     b = __reduce_add_sync(0xffffffffu, b);
-    int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
         r.i[phase][0][w] = a;
         r.i[phase][1][w] = b;
     }
     __syncthreads();
-    int sa = 0, sb = 0;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-        sa += r.i[phase][0][k];
-        sb += r.i[phase][1][k];
-    }
-    A = sa;
-    B = sb;
+    // second level: every warp folds the NW partials with one redux each (no serial loop over warps)
+    const int pa = (lane < NW) ? r.i[phase][0][lane] : 0;
+    const int pb = (lane < NW) ? r.i[phase][1][lane] : 0;
+    A = __reduce_add_sync(0xffffffffu, pa);
+    B = __reduce_add_sync(0xffffffffu, pb);
     phase ^= 1;
 }
 
 // op: 0 = (min, max), 1 = (sum, sum), 2 = (max, min)
 template <int NW, int OP>
 __device__ __forceinline__ void block_red2d(Red<NW> &r, int &phase, double a, double b, double &A, double &B) {
-    if (OP == 0) {
-        a = warp_min_d(a);
-        b = warp_max_d(b);
-    } else if (OP == 1) {
-        a = warp_sum_d(a);
-        b = warp_sum_d(b);
-    } else {
-        a = warp_max_d(a);
-        b = warp_min_d(b);
-    }
-    int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
+    const double ida = (OP == 0) ? DBL_MAX : ((OP == 1) ? 0.0 : -DBL_MAX);
+    const double idb = (OP == 0) ? -DBL_MAX : ((OP == 1) ? 0.0 : DBL_MAX);
+    auto fold = [&](double &u, double &v) {
+        if (OP == 0) {
+            u = warp_min_d(u);
+            v = warp_max_d(v);
+        } else if (OP == 1) {
+            u = warp_sum_d(u);
+            v = warp_sum_d(v);
+        } else {
+            u = warp_max_d(u);
+            v = warp_min_d(v);
+        }
+    };
+    fold(a, b);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
         r.d[phase][0][w] = a;
         r.d[phase][1][w] = b;
     }
     __syncthreads();
-    double sa = r.d[phase][0][0], sb = r.d[phase][1][0];
-#pragma unroll
-    for (int k = 1; k < NW; ++k) {
-        double ta = r.d[phase][0][k], tb = r.d[phase][1][k];
-        if (OP == 0) {
-            sa = fmin(sa, ta);
-            sb = fmax(sb, tb);
-        } else if (OP == 1) {
-            sa += ta;
-            sb += tb;
-        } else {
-            sa = fmax(sa, ta);
-            sb = fmin(sb, tb);
-        }
-    }
-    A = sa;
-    B = sb;
+    double pa = (lane < NW) ? r.d[phase][0][lane] : ida;
+    double pb = (lane < NW) ? r.d[phase][1][lane] : idb;
+    fold(pa, pb);
+    A = pa;
+    B = pb;
     phase ^= 1;
 }
 
@@ -220,49 +216,67 @@ __device__ __forceinline__ void block_red2d(Red<NW> &r, int &phase, double a, do
 // come from linear interpolation of the empirical CDF inside the bracket; a round that fails to
 // halve the bracket is followed by a bisection round in key space, which bounds the worst case.
 // Once <= CAND_MAX values remain they are gathered into shared memory and ranked directly.
-template <int NT>
-__device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT / 32> &red, int &phase,
+template <int NT, int LMAX>
+__device__ __forceinline__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT / 32> &red, int &phase,
                                double *cand, int *cand_n) {
     constexpr int NW = NT / 32;
     const int kA = (n - 1) >> 1, kB = n >> 1;
 
-    // start: mean / sd bracket guess
+    // start: mean / sd bracket guess from one pass (sum, sum of squares, min, max) and one reduction.
+    // The sd only places the first two pivots, so the one-pass formula's cancellation is harmless.
     double s1 = 0.0, s2 = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
 #pragma unroll
     for (int t = 0; t < LMAX; ++t)
         if (t < len) {
             double v = y[t];
             s1 += v;
+            s2 = fma(v, v, s2);
             mn = fmin(mn, v);
             mx = fmax(mx, v);
         }
-    double S1, dummy, MN, MX;
-    block_red2d<NW, 1>(red, phase, s1, 0.0, S1, dummy);
-    block_red2d<NW, 0>(red, phase, mn, mx, MN, MX);
+    double S1, S2, MN, MX;
+    {
+        s1 = warp_sum_d(s1);
+        s2 = warp_sum_d(s2);
+        mn = warp_min_d(mn);
+        mx = warp_max_d(mx);
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+            red.d[phase][0][w] = s1;
+            red.d[phase][1][w] = s2;
+            red.d[phase ^ 1][0][w] = mn;   // both halves of the scratch: safe, the previous reduction
+            red.d[phase ^ 1][1][w] = mx;   // that used them is two barriers behind
+        }
+        __syncthreads();
+        double a0 = (lane < NW) ? red.d[phase][0][lane] : 0.0;
+        double a1 = (lane < NW) ? red.d[phase][1][lane] : 0.0;
+        double a2 = (lane < NW) ? red.d[phase ^ 1][0][lane] : DBL_MAX;
+        double a3 = (lane < NW) ? red.d[phase ^ 1][1][lane] : -DBL_MAX;
+        S1 = warp_sum_d(a0);
+        S2 = warp_sum_d(a1);
+        MN = warp_min_d(a2);
+        MX = warp_max_d(a3);
+        __syncthreads();  // scratch of both phases is free again
+    }
     if (!(MN < MX)) return MN;  // all equal (or n == 1)
     const double mean = S1 / (double)n;
-#pragma unroll
-    for (int t = 0; t < LMAX; ++t)
-        if (t < len) {
-            double d = y[t] - mean;
-            s2 += d * d;
-        }
-    double S2;
-    block_red2d<NW, 1>(red, phase, s2, 0.0, S2, dummy);
-    const double sd = sqrt(S2 / (double)n);
+    double var = S2 / (double)n - mean * mean;
+    const double sd = var > 0.0 ? sqrt(var) : 0.0;
 
     // invariant: #(x <= lo) <= kA  and  #(x <= hi) >= kB + 1.  lo starts one ulp below the minimum.
     double lo = double_of_key(key_of(MN) - 1ull), hi = MX;
     if (!(lo < MN)) lo = double_of_key(key_of(MN) - 2ull);  // MN == +0.0: one key below is -0.0 == MN
     int Flo = 0, Fhi = n;
-    double p1 = mean - 0.08 * sd, p2 = mean + 0.08 * sd;
+    double p1 = mean - 0.35 * sd, p2 = mean + 0.35 * sd;
     bool force_bisect = false;
     double a_res = 0.0, b_res = 0.0;
     bool done = false;
 
+    if (threadIdx.x == 0) atomicAdd(&g_stats[1], 1ull);
     for (int round = 0; round < 160 && !done; ++round) {
         int m = Fhi - Flo;
         if (m <= CAND_MAX) break;
+        if (threadIdx.x == 0) atomicAdd(&g_stats[0], 1ull);
         // ---- choose pivots strictly inside (lo, hi) ------------------------------------------
         const double lo_eff = lo;
         unsigned long long klo = key_of(lo), khi = key_of(hi);
@@ -276,13 +290,15 @@ __device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT /
             if (force_bisect) {
                 p1 = p2 = pmid;
             } else {
-                double f = ((double)kA + 0.5 * (double)(kB - kA) + 0.5 - (double)Flo) / (double)m;
-                double wfrac = (3.0 * sqrt((double)m) + 8.0) / (double)m;
-                if (wfrac > 0.5) wfrac = 0.5;
-                double span = hi - lo_eff;
-                double pc = lo_eff + span * f;
-                p1 = pc - 0.5 * span * wfrac;
-                p2 = pc + 0.5 * span * wfrac;
+                // pivot placement only has to be identical in every thread, not accurate: float math
+                const float mf = (float)m;
+                const float f = ((float)(kA - Flo) + 0.5f * (float)(kB - kA) + 0.5f) / mf;
+                float wfrac = (3.0f * sqrtf(mf) + 8.0f) / mf;
+                if (wfrac > 0.5f) wfrac = 0.5f;
+                const double span = hi - lo_eff;
+                const double pc = lo_eff + span * (double)f;
+                p1 = pc - span * (double)(0.5f * wfrac);
+                p2 = pc + span * (double)(0.5f * wfrac);
             }
         }
         if (!(p1 > lo && p1 < hi)) p1 = pmid;
@@ -293,13 +309,13 @@ __device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT /
             p2 = t;
         }
         // ---- count ------------------------------------------------------------------------------
+        // y[] is padded with +inf beyond len (see the caller), so no per-element length test is needed
         int c1 = 0, c2 = 0;
 #pragma unroll
-        for (int t = 0; t < LMAX; ++t)
-            if (t < len) {
-                c1 += (y[t] <= p1) ? 1 : 0;
-                c2 += (y[t] <= p2) ? 1 : 0;
-            }
+        for (int t = 0; t < LMAX; ++t) {
+            c1 += (y[t] <= p1) ? 1 : 0;
+            c2 += (y[t] <= p2) ? 1 : 0;
+        }
         int C1, C2;
         block_sum2i<NW>(red, phase, c1, c2, C1, C2);
         // ---- narrow -----------------------------------------------------------------------------
@@ -326,12 +342,11 @@ __device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT /
         if (do_split) {  // s_kA <= split < s_kB: neighbours of the split point
             double below = -DBL_MAX, above = DBL_MAX;
 #pragma unroll
-            for (int t = 0; t < LMAX; ++t)
-                if (t < len) {
-                    double v = y[t];
-                    if (v <= split) below = fmax(below, v);
-                    else above = fmin(above, v);
-                }
+            for (int t = 0; t < LMAX; ++t) {
+                double v = y[t];
+                if (v <= split) below = fmax(below, v);
+                else above = fmin(above, v);  // +inf padding never lowers `above`
+            }
             block_red2d<NW, 2>(red, phase, below, above, a_res, b_res);
             done = true;
             break;
@@ -339,33 +354,41 @@ __device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT /
         int m_new = Fhi - Flo;
         force_bisect = (2 * m_new > m) && !force_bisect;
     }
-    if (done) return (a_res + b_res) * 0.5;
+    if (done) {
+        if (threadIdx.x == 0) atomicAdd(&g_stats[2], 1ull);
+        return (a_res + b_res) * 0.5;
+    }
+    if (threadIdx.x == 0) atomicAdd(&g_stats[3], 1ull);
 
     // ---- gather the <= CAND_MAX candidates in (lo, hi] and rank them --------------------------------
     if (threadIdx.x == 0) *cand_n = 0;
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < LMAX; ++t)
-        if (t < len) {
-            double v = y[t];
-            if (v > lo && v <= hi) {
-                int slot = atomicAdd(cand_n, 1);
-                if (slot < CAND_MAX) cand[slot] = v;
-            }
+    for (int t = 0; t < LMAX; ++t) {
+        double v = y[t];
+        if (v > lo && v <= hi) {  // hi is finite: padding excluded
+            int slot = atomicAdd(cand_n, 1);
+            if (slot < CAND_MAX) cand[slot] = v;
         }
+    }
     __syncthreads();
     int m = *cand_n;
     if (m > CAND_MAX) m = CAND_MAX;  // cannot happen (m == Fhi - Flo); keeps the loop bounded
-    int ra = kA - Flo, rb = kB - Flo;
-    if ((int)threadIdx.x < m) {
-        double v = cand[threadIdx.x];
-        int rank = 0;
-        for (int j = 0; j < m; ++j) {
-            double u = cand[j];
-            rank += (u < v || (u == v && j < (int)threadIdx.x)) ? 1 : 0;
+    const int ra = kA - Flo, rb = kB - Flo;
+    {   // one warp per candidate: the 32 lanes compare it with all (<= 64) candidates, one redux gives its rank
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const double u1 = (lane < m) ? cand[lane] : INFINITY;
+        const double u2 = (lane + 32 < m) ? cand[lane + 32] : INFINITY;
+        for (int i = w; i < m; i += NW) {
+            const double v = cand[i];
+            int cnt = ((u1 < v) || (u1 == v && lane < i)) ? 1 : 0;
+            cnt += ((u2 < v) || (u2 == v && lane + 32 < i)) ? 1 : 0;
+            const int rank = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) {
+                if (rank == ra) cand[CAND_MAX] = v;
+                if (rank == rb) cand[CAND_MAX + 1] = v;
+            }
         }
-        if (rank == ra) cand[CAND_MAX] = v;
-        if (rank == rb) cand[CAND_MAX + 1] = v;
     }
     __syncthreads();
     double a = cand[CAND_MAX], b = cand[CAND_MAX + 1];
@@ -373,141 +396,375 @@ __device__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT /
     return (a + b) * 0.5;
 }
 
+#include "icnv_math_tables.inc"
+__device__ double g_log_tab[128][2];
+__device__ double g_exp_tab[128];
+
+// log2(x + 1) as the reference computes it (add, then log2; ops.R:2760), table + degree-6 polynomial:
+// v = 2^e * m, m in [1,2); c_i = 1/inv_c[i] is the table point next to m, r = m*inv_c - 1 (|r| < 2^-8),
+// log2 v = e + log2 c_i + log2(1 + r).  Error <= 3e-16 (relative, absolute below 1).  ~25 instructions
+// against ~90 for the library log2.
+__device__ __forceinline__ double fast_log2_1p(double x, const double2 *__restrict__ ltab) {
+    const double v = x + 1.0;
+    const int hi = __double2hiint(v);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log2(v);  // zero, negative, denormal, inf, nan
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+    const double2 t = ltab[(hi >> 13) & 127];
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(r, ICNV_LOGC5, ICNV_LOGC4);
+    q = fma(r, q, ICNV_LOGC3);
+    q = fma(r, q, ICNV_LOGC2);
+    q = fma(r, q, ICNV_LOGC1);
+    q = fma(r, q, ICNV_LOGC0);
+    return (double)e + fma(r, q, t.y);
+}
+
+// 2^x (invert_log2, ops.R:2818): x = k/128 + r, 2^x = 2^(k>>7) * T[k & 127] * 2^r, degree-5 polynomial.
+__device__ __forceinline__ double fast_exp2(double x, const double *__restrict__ etab) {
+    if (!(fabs(x) < 1000.0)) return exp2(x);
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    const double kk = fma(x, 128.0, MAGIC);
+    const int ki = __double2loint(kk);
+    const double r = fma(kk - MAGIC, -0.0078125, x);  // exact
+    double q = fma(r, ICNV_EXPC4, ICNV_EXPC3);
+    q = fma(r, q, ICNV_EXPC2);
+    q = fma(r, q, ICNV_EXPC1);
+    q = fma(r, q, ICNV_EXPC0);
+    const double t = etab[ki & 127];
+    const double res = fma(t * r, q, t);
+    return __hiloint2double(__double2hiint(res) + ((ki >> 7) << 20), __double2loint(res));
+}
+
 // dead-band subtraction, .subtract_expr (ops.R:1764-1769): strict inequalities
 __device__ __forceinline__ double sub_bounds(double x, double lo, double hi) {
     return (x > hi) ? (x - hi) : ((x < lo) ? (x - lo) : 0.0);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1) cell_pipeline_kernel(const CellParams p) {
+// ---- mbarrier / bulk-copy (TMA) helpers: the next cell's column is fetched by the copy engine
+//      into shared memory while the CTA works on the current one --------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned a = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// One CTA per cell, persistent over cells.  Per cell:
+//   A  column arrives by bulk copy (issued one cell ahead); element-wise steps applied while moving
+//      it from the landing buffer to the work buffer (coalesced, bounds read coalesced from L2)
+//   B  pyramid smooth via two prefix sums per chromosome: with P = prefix(x), Q = prefix(P),
+//      sum_{|d|<=h} (h+1-|d|) x[i+d] = (Q[i+h] - Q[i-1]) - (Q[i-1] - Q[i-h-2]), zero padding outside the
+//      chromosome being a constant / linear continuation of P / Q.  O(1) work per gene for any window.
+//   C  per-cell median by counting selection on register-resident values
+//   D  centred values back to shared memory, second reference subtraction + 2^x fused into the one
+//      coalesced write of the column
+template <int NT, int LMAX>
+__global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
-    double *s = reinterpret_cast<double *>(smem_raw);       // the cell's gene vector
-    double *invD = s + p.s_elems;                            // 1/D for one-sided truncation, h+1 entries
-    double *cand = invD + (p.h + 2);                         // CAND_MAX + 2
+    double *raw = reinterpret_cast<double *>(smem_raw);      // landing buffer of the bulk copy
+    double *work = raw + p.s_elems;                          // x' -> Q -> centred output
+    double *invD = work + p.s_elems;                         // 1/D for one-sided truncation, h+1 entries
+    double *ptot = invD + (p.h + 2);                         // per chromosome: P and Q at its last gene
+    double *qtot = ptot + p.K;
+    double *tails = qtot + p.K;                              // [2][NW] warp tails of the two scans
+    double *cand = tails + 2 * NW;                           // CAND_MAX + 2
     Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
     int *cand_n = reinterpret_cast<int *>(&red + 1);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cand_n + 2);
+    double2 *ltab = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(bar + 2) + 15) & ~(uintptr_t)15);
+    double *etab = reinterpret_cast<double *>(ltab + 128);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)p.G;
     const int h = p.h;
     const bool do_smooth = p.window >= 2;
     int phase = 0;
+    unsigned parity = 0;
 
     if (do_smooth) {
         double full = (double)(h + 1) * (double)(h + 1);
         for (int r = tid; r <= h; r += NT) invD[r] = 1.0 / (full - 0.5 * (double)r * (double)(r + 1));
     }
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < 128; i += NT) {
+        ltab[i] = make_double2(g_log_tab[i][0], g_log_tab[i][1]);
+        etab[i] = g_exp_tab[i];
+    }
     const Seg seg = p.segs[tid];
+    const int lane_first = max(seg.tfirst - (tid - lane), 0);  // first lane of my chromosome inside this warp
+    const int wfirst = seg.tfirst >> 5;                        // warp holding the chromosome's first thread
     bool bad = false;
+    const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
+    // bulk copies need 16-byte aligned source / size; otherwise the column is loaded by the threads
+    auto tma_ok = [&](int64_t col) {
+        return ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
+    };
+    __syncthreads();  // barrier initialised, invD ready
+    if (tid == 0 && (int64_t)blockIdx.x < p.n_cols) {
+        const int64_t col0 = p.cols ? (int64_t)p.cols[blockIdx.x] : (int64_t)blockIdx.x;
+        if (tma_ok(col0)) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, col_bytes);
+            bulk_g2s(raw, p.X + p.ldx * col0, col_bytes, bar);
+        }
+    }
 
     for (int64_t ci = blockIdx.x; ci < p.n_cols; ci += gridDim.x) {
         const int64_t col = p.cols ? (int64_t)p.cols[ci] : ci;
-        const double *__restrict__ src = p.X + p.ldx * col;
         double *__restrict__ dst = p.Y + p.ldy * ci;
-
-        // ---- stage A: one coalesced read of the column, element-wise steps fused into it --------
-        for (int g0 = tid; g0 < G; g0 += 4 * NT) {
-            double v[4];
+        // ---- stage A ------------------------------------------------------------------------------------
+        if (tma_ok(col)) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            const double *__restrict__ src = p.X + p.ldx * col;
+            for (int g = tid; g < G; g += NT) raw[g] = src[g];
+            __syncthreads();
+        }
+        if (p.apply_log && p.lo1 && p.threshold > 0.0) {
+            // the fused-block configuration: log2(x+1) -> dead-band subtract -> clamp, no per-element mode tests
+            const double thr = p.threshold;
+            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+                double v[4], lo[4], hi[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int g = g0 + u * NT;
-                v[u] = (g < G) ? src[g] : 0.0;
+                for (int u = 0; u < 4; ++u) {
+                    const int g = min(g0 + u * NT, G - 1);
+                    v[u] = raw[g];
+                    lo[u] = p.lo1[g];
+                    hi[u] = p.hi1[g];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    if (!is_finite_d(v[u])) bad = true;
+                    double x = fast_log2_1p(v[u], ltab);
+                    x = sub_bounds(x, lo[u], hi[u]);
+                    x = fmin(fmax(x, -thr), thr);
+                    if (g < G) work[g] = x;
+                }
             }
+        } else {
+        for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+                double v[4], lo[4], hi[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int g = g0 + u * NT;
-                if (g < G) {
-                    double x = v[u];
-                    if (!is_finite_d(x)) bad = true;
-                    if (p.apply_log) x = log2(x + 1.0);
-                    if (p.lo1) x = sub_bounds(x, p.lo1[g], p.hi1[g]);
-                    else if (p.mid1) x = x - p.mid1[g];
-                    if (p.threshold > 0.0) x = fmin(fmax(x, -p.threshold), p.threshold);
-                    s[g] = x;
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    const bool in = g < G;
+                    v[u] = in ? raw[g] : 0.0;
+                    lo[u] = (in && p.lo1) ? p.lo1[g] : ((in && p.mid1) ? p.mid1[g] : 0.0);
+                    hi[u] = (in && p.hi1) ? p.hi1[g] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    if (g < G) {
+                        double x = v[u];
+                        if (!is_finite_d(x)) bad = true;
+                        if (p.apply_log) x = fast_log2_1p(x, ltab);
+                        if (p.lo1) x = sub_bounds(x, lo[u], hi[u]);
+                        else if (p.mid1) x = x - lo[u];
+                        if (p.threshold > 0.0) x = fmin(fmax(x, -p.threshold), p.threshold);
+                        work[g] = x;
+                    }
                 }
             }
         }
-        __syncthreads();
-
-        // ---- stage B: pyramid smooth of this thread's segment, results stay in registers ---------
-        double y[LMAX];
-        {
-            const int a = seg.start, len = seg.len, cs = seg.cs, ce = seg.ce;
-            if (len > 0 && do_smooth && (ce - cs) >= 2) {
-                // weighted window sum N(a) and the two half-window box sums, x = 0 outside [cs, ce)
-                double N = 0.0, Ls = 0.0, Rs = 0.0;
-                int jlo = max(cs, a - h), jhi = min(ce - 1, a + h);
-                for (int j = jlo; j <= jhi; ++j) {
-                    double v = s[j];
-                    int d = j - a;
-                    N = fma((double)(h + 1 - (d < 0 ? -d : d)), v, N);
-                    if (d <= 0) Ls += v;
-                    else Rs += v;
+        __syncthreads();  // landing buffer consumed, work buffer complete
+        if (tid == 0) {   // fetch the next cell's column while this one is processed
+            const int64_t cn = ci + gridDim.x;
+            if (cn < p.n_cols) {
+                const int64_t coln = p.cols ? (int64_t)p.cols[cn] : cn;
+                if (tma_ok(coln)) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, col_bytes);
+                    bulk_g2s(raw, p.X + p.ldx * coln, col_bytes, bar);
                 }
-                if (a + h + 1 < ce) Rs += s[a + h + 1];
+            }
+        }
+
+        // ---- stage B ------------------------------------------------------------------------------------
+        double y[LMAX];
+        const int len = seg.len, a0 = seg.start, cs = seg.cs, ce = seg.ce;
 #pragma unroll
-                for (int t = 0; t < LMAX; ++t) {
-                    if (t < len) {
-                        int i = a + t;
-                        int rl = h - (i - cs);
-                        rl = rl > 0 ? rl : 0;
-                        int rr = h - (ce - 1 - i);
-                        rr = rr > 0 ? rr : 0;
+        for (int q = 0; q < LMAX; ++q) y[q] = (q < len) ? work[a0 + q] : 0.0;
+        if (do_smooth) {
+            // P = inclusive prefix of x inside the chromosome
+#pragma unroll
+            for (int q = 1; q < LMAX; ++q) y[q] += y[q - 1];
+            double tot = y[LMAX - 1];
+            double inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane - d >= lane_first) inc += t;
+            }
+            double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane <= lane_first) exc = 0.0;
+            if (lane == 31) tails[warp] = inc;
+            __syncthreads();
+            double carry = 0.0;
+            for (int u = wfirst; u < warp; ++u) carry += tails[u];
+            const double offP = exc + carry;
+            const double plast = tot + offP;  // P at the segment's last gene (the padding adds zeros)
+#pragma unroll
+            for (int q = 0; q < LMAX; ++q) y[q] = (q < len) ? (y[q] + offP) : 0.0;
+            // Q = inclusive prefix of P
+#pragma unroll
+            for (int q = 1; q < LMAX; ++q) y[q] += y[q - 1];
+            tot = y[LMAX - 1];
+            inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane - d >= lane_first) inc += t;
+            }
+            exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane <= lane_first) exc = 0.0;
+            if (lane == 31) tails[NW + warp] = inc;
+            __syncthreads();  // also: every thread has its x' in registers, work[] may be overwritten
+            carry = 0.0;
+            for (int u = wfirst; u < warp; ++u) carry += tails[NW + u];
+            const double offQ = exc + carry;
+            const double qlast = tot + offQ;
+#pragma unroll
+            for (int q = 0; q < LMAX; ++q)
+                if (q < len) work[a0 + q] = y[q] + offQ;
+            if (len > 0 && a0 + len == ce) {
+                ptot[seg.chr] = plast;
+                qtot[seg.chr] = qlast;
+            }
+            __syncthreads();
+            const int n = ce - cs;
+            if (n >= 2) {
+                const double Pn = ptot[seg.chr], Qn = qtot[seg.chr];
+                const double invD0 = 1.0 / ((double)(h + 1) * (double)(h + 1));
+                const double *Qc = work + cs;
+                auto Qt = [&](int j) -> double {
+                    if (j < 0) return 0.0;
+                    if (j <= n - 1) return Qc[j];
+                    return Qn + (double)(j - (n - 1)) * Pn;
+                };
+#pragma unroll
+                for (int q = 0; q < LMAX; ++q) {
+                    if (q < len) {
+                        const int j = a0 + q - cs;
                         double out;
-                        if (rl == 0 || rr == 0) {
-                            out = N * invD[rl + rr];
-                        } else {  // chromosome shorter than the window: both ends truncated
-                            double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
-                                       0.5 * (double)rr * (double)(rr + 1);
-                            out = N / D;
+                        if (j - h - 2 >= 0 && j + h <= n - 1) {  // window strictly inside the chromosome
+                            const double qb = Qc[j - 1];
+                            out = ((Qc[j + h] - qb) - (qb - Qc[j - h - 2])) * invD0;
+                        } else {
+                            const double qa = Qt(j + h), qb = Qt(j - 1), qc = Qt(j - h - 2);
+                            const double N = (qa - qb) - (qb - qc);
+                            int rl = h - j;
+                            rl = rl > 0 ? rl : 0;
+                            int rr = h - (n - 1 - j);
+                            rr = rr > 0 ? rr : 0;
+                            if (rl == 0 || rr == 0) {
+                                out = N * invD[rl + rr];
+                            } else {  // chromosome shorter than the window: both ends truncated
+                                double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
+                                           0.5 * (double)rr * (double)(rr + 1);
+                                out = N / D;
+                            }
                         }
-                        y[t] = out;
-                        // slide: weights of x[i+1 .. i+h+1] grow by one, those of x[i-h .. i] shrink by one
-                        N += (Rs - Ls);
-                        double xin = (i + 1 < ce) ? s[i + 1] : 0.0;
-                        double xoutL = (i - h >= cs) ? s[i - h] : 0.0;
-                        double xinR = (i + h + 2 < ce) ? s[i + h + 2] : 0.0;
-                        Ls += xin - xoutL;
-                        Rs += xinR - xin;
+                        y[q] = out;
                     } else {
-                        y[t] = 0.0;
+                        y[q] = 0.0;
                     }
                 }
             } else {
+                // single-gene chromosome: left untouched (ops.R:2417); its prefix sum is the value itself
 #pragma unroll
-                for (int t = 0; t < LMAX; ++t) y[t] = (t < len) ? s[a + t] : 0.0;
+                for (int q = 0; q < LMAX; ++q) y[q] = (q < len) ? plast : 0.0;
             }
         }
 
-        // ---- stage C: per-cell centre over all genes ---------------------------------------------------
+        // ---- stage C ------------------------------------------------------------------------------------
         double centre = 0.0;
         if (p.center == 1) {
-            centre = block_median<NT>(y, seg.len, G, red, phase, cand, cand_n);
+#pragma unroll
+            for (int q = 0; q < LMAX; ++q)
+                if (q >= len) y[q] = INFINITY;  // padding never counts as <= pivot
+            centre = block_median<NT, LMAX>(y, len, G, red, phase, cand, cand_n);
         } else if (p.center == 2) {
             double s1 = 0.0;
 #pragma unroll
-            for (int t = 0; t < LMAX; ++t)
-                if (t < seg.len) s1 += y[t];
+            for (int q = 0; q < LMAX; ++q)
+                if (q < len) s1 += y[q];
             double S1, dummy;
             block_red2d<NW, 1>(red, phase, s1, 0.0, S1, dummy);
             centre = S1 / (double)G;
         }
-        __syncthreads();  // every thread is done reading s[] for the smooth
+        __syncthreads();  // every thread is done reading Q from work[]
 #pragma unroll
-        for (int t = 0; t < LMAX; ++t)
-            if (t < seg.len) s[seg.start + t] = y[t] - centre;
+        for (int q = 0; q < LMAX; ++q)
+            if (q < len) work[a0 + q] = y[q] - centre;
         __syncthreads();
 
-        // ---- stage D: second reference subtraction + 2^x fused into the one coalesced write -------------
-        for (int g = tid; g < G; g += NT) {
-            double x = s[g];
-            if (p.lo2) x = sub_bounds(x, p.lo2[g], p.hi2[g]);
-            else if (p.mid2) x = x - p.mid2[g];
-            if (p.apply_exp2) x = exp2(x);
-            dst[g] = x;
+        // ---- stage D ------------------------------------------------------------------------------------
+        if (p.lo2 && p.apply_exp2) {
+            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+                double v[4], lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = min(g0 + u * NT, G - 1);
+                    v[u] = work[g];
+                    lo[u] = p.lo2[g];
+                    hi[u] = p.hi2[g];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    const double x = fast_exp2(sub_bounds(v[u], lo[u], hi[u]), etab);
+                    if (g < G) dst[g] = x;
+                }
+            }
+        } else {
+        for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+                double v[4], lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    const bool in = g < G;
+                    v[u] = in ? work[g] : 0.0;
+                    lo[u] = (in && p.lo2) ? p.lo2[g] : ((in && p.mid2) ? p.mid2[g] : 0.0);
+                    hi[u] = (in && p.hi2) ? p.hi2[g] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    if (g < G) {
+                        double x = v[u];
+                        if (p.lo2) x = sub_bounds(x, lo[u], hi[u]);
+                        else if (p.mid2) x = x - lo[u];
+                        if (p.apply_exp2) x = fast_exp2(x, etab);
+                        dst[g] = x;
+                    }
+                }
+            }
         }
-        __syncthreads();  // s[] is overwritten by the next cell
+        __syncthreads();  // work[] is rewritten by the next cell
     }
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
@@ -516,7 +773,7 @@ __global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1) cell_pipeline_kernel(
 // host-side launchers (device-pointer ABI)
 // =================================================================================================
 
-static int build_segments(int64_t G, const int32_t *chr_start, const int32_t *chr_len, int K, int NT,
+static int build_segments(int64_t G, const int32_t *chr_start, const int32_t *chr_len, int K, int NT, int lmax,
                           std::vector<Seg> &segs) {
     // cover every gene exactly once; genes outside every chromosome range are an argument error
     int64_t covered = 0;
@@ -528,21 +785,24 @@ static int build_segments(int64_t G, const int32_t *chr_start, const int32_t *ch
     if (K > 0 && chr_start[0] != 0) return -1;
     if (covered != G) return -1;
     // L odd: adjacent threads then start an odd number of 8-byte words apart, so the strided
-    // 64-bit shared-memory accesses of the smooth are bank-conflict free within a half-warp.
-    for (int L = 1; L <= LMAX; L += 2) {
+    // 64-bit shared-memory accesses are bank-conflict free within a half-warp.
+    for (int L = 1; L < lmax; L += 2) {
         int64_t n = 0;
         for (int k = 0; k < K; ++k) n += (chr_len[k] + L - 1) / L;
         if (n <= NT) {
-            segs.assign(NT, Seg{0, 0, 0, 0});
+            segs.resize(NT);
             int t = 0;
             for (int k = 0; k < K; ++k) {
                 int pos = chr_start[k], end = chr_start[k] + chr_len[k];
+                const int tfirst = t;
                 while (pos < end) {
                     int len = end - pos < L ? end - pos : L;
-                    segs[t++] = Seg{pos, len, chr_start[k], end};
+                    segs[t] = Seg{pos, len, chr_start[k], end, tfirst, k};
+                    ++t;
                     pos += len;
                 }
             }
+            for (; t < NT; ++t) segs[t] = Seg{0, 0, 0, 0, t, 0};
             return L;
         }
     }
@@ -594,6 +854,17 @@ int icnv_dev_bounds_from_means_f64(const double *means, int64_t G, int n_grp, do
     return ICNV_OK;
 }
 
+ICNV_API int icnv_debug_stats(unsigned long long *out4, int reset) {
+    ICNV_REQUIRE_READY();
+    ICNV_CUDA(cudaDeviceSynchronize());
+    ICNV_CUDA(cudaMemcpyFromSymbol(out4, g_stats, sizeof(unsigned long long) * 4));
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        ICNV_CUDA(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
+    }
+    return ICNV_OK;
+}
+
 int icnv_dev_invlog_finish_f64(double *means, int64_t n, void *stream) {
     ICNV_REQUIRE_READY();
     invlog_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pick_stream(stream)>>>(means, n);
@@ -616,26 +887,41 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         return set_error(ICNV_E_BAD_ARG, "window_length %d is even: the reference's behaviour is accidental there", window);
     if (center < 0 || center > 2) return set_error(ICNV_E_BAD_ARG, "center must be 0, 1 or 2");
     if (n_cols == 0) return ICNV_OK;
-    if (G > (int64_t)512 * LMAX) return set_error(ICNV_E_UNSUPPORTED, "G = %lld exceeds %d genes", (long long)G, 512 * LMAX);
-
     int h = window >= 2 ? (window - 1) / 2 : 0;
     int s_elems = (int)((G + 1) & ~(int64_t)1);
     std::vector<Seg> segs;
-    int NT = 256;
-    int L = build_segments(G, chr_start, chr_len, K, NT, segs);
-    if (L < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
-    if (L == 0) {
-        NT = 512;
-        L = build_segments(G, chr_start, chr_len, K, NT, segs);
-        if (L <= 0) return set_error(ICNV_E_UNSUPPORTED, "G = %lld with K = %d does not fit 512 x %d", (long long)G, K, LMAX);
+    // (threads, genes per thread) variants, smallest first; ICNV_CELL_VARIANT=<index> pins one (tuning)
+    static const int variants[][2] = {{256, 12}, {512, 12}, {512, 24}, {1024, 12}};  // measured: 512x24 beats 1024x12
+    int NT = 0, L = 0, lmax = 0, forced = -1;
+    if (const char *e = getenv("ICNV_CELL_VARIANT")) forced = atoi(e);
+    for (int vi = 0; vi < 4; ++vi) {
+        if (forced >= 0 && vi != forced) continue;
+        L = build_segments(G, chr_start, chr_len, K, variants[vi][0], variants[vi][1], segs);
+        if (L < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
+        if (L > 0) {
+            NT = variants[vi][0];
+            lmax = variants[vi][1];
+            break;
+        }
     }
-    size_t red_bytes = (NT == 256) ? sizeof(Red<8>) : sizeof(Red<16>);
-    size_t smem = sizeof(double) * ((size_t)s_elems + (size_t)(h + 2) + CAND_MAX + 2) + red_bytes + 16;
+    if (NT == 0)
+        return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes in K = %d chromosomes exceeds the kernel's %d genes",
+                         (long long)G, K, 512 * 23);
+    const int NW = NT / 32;
+    size_t red_bytes = (NT == 256) ? sizeof(Red<8>) : (NT == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
+    size_t smem = sizeof(double) * (2 * (size_t)s_elems + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW + CAND_MAX + 2) +
+                  red_bytes + 64 + 128 * 24 + 32;
     if (smem > (size_t)c.smem_optin)
-        return set_error(ICNV_E_UNSUPPORTED, "needs %zu B shared memory per CTA, device allows %d", smem, c.smem_optin);
+        return set_error(ICNV_E_UNSUPPORTED, "G = %lld needs %zu B shared memory per CTA, device allows %d", (long long)G,
+                         smem, c.smem_optin);
 
     cudaStream_t st = pick_stream(stream);
-    Seg *d_segs = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 512);
+    if (!c.math_tables_uploaded) {
+        ICNV_CUDA(cudaMemcpyToSymbol(g_log_tab, icnv_log_tab, sizeof(icnv_log_tab)));
+        ICNV_CUDA(cudaMemcpyToSymbol(g_exp_tab, icnv_exp_tab, sizeof(icnv_exp_tab)));
+        c.math_tables_uploaded = true;
+    }
+    Seg *d_segs = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
     if (!d_segs) return ICNV_E_NOMEM;
     ICNV_CUDA(cudaMemcpyAsync(d_segs, segs.data(), sizeof(Seg) * NT, cudaMemcpyHostToDevice, st));
 
@@ -643,21 +929,23 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     p.X = X; p.G = G; p.ldx = ldx; p.cols = cols; p.n_cols = n_cols; p.Y = Y; p.ldy = ldy; p.segs = d_segs;
     p.apply_log = apply_log; p.lo1 = lo1; p.hi1 = hi1; p.mid1 = mid1; p.threshold = threshold;
     p.window = window; p.h = h; p.center = center; p.lo2 = lo2; p.hi2 = hi2; p.mid2 = mid2;
-    p.apply_exp2 = apply_exp2; p.err_flag = err_flag; p.s_elems = s_elems;
+    p.apply_exp2 = apply_exp2; p.err_flag = err_flag; p.s_elems = s_elems; p.K = K;
 
-    int per_sm = 1;
-    if (NT == 256) {
-        ICNV_CUDA(cudaFuncSetAttribute(cell_pipeline_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cell_pipeline_kernel<256>, 256, smem));
-    } else {
-        ICNV_CUDA(cudaFuncSetAttribute(cell_pipeline_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cell_pipeline_kernel<512>, 512, smem));
-    }
-    if (per_sm < 1) return set_error(ICNV_E_UNSUPPORTED, "cell_pipeline_kernel does not fit on an SM");
-    int64_t grid = (int64_t)c.sm_count * per_sm;  // persistent CTAs: a whole number of waves
-    if (grid > n_cols) grid = n_cols;
-    if (NT == 256) cell_pipeline_kernel<256><<<(unsigned)grid, 256, smem, st>>>(p);
-    else cell_pipeline_kernel<512><<<(unsigned)grid, 512, smem, st>>>(p);
+    auto launch = [&](auto kern) -> int {
+        ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+        // persistent CTAs: a whole number of waves over the SMs
+        int64_t grid = std::min<int64_t>(n_cols, (int64_t)c.sm_count * std::max(per_sm, 1));
+        kern<<<(unsigned)grid, NT, smem, st>>>(p);
+        return ICNV_OK;
+    };
+    int lrc;
+    if (NT == 256) lrc = launch(cell_pipeline_kernel<256, 12>);
+    else if (NT == 512 && lmax == 12) lrc = launch(cell_pipeline_kernel<512, 12>);
+    else if (NT == 1024) lrc = launch(cell_pipeline_kernel<1024, 12>);
+    else lrc = launch(cell_pipeline_kernel<512, 24>);
+    if (lrc) return lrc;
     ICNV_CHECK_LAUNCH("cell_pipeline_kernel");
     return ICNV_OK;
 }

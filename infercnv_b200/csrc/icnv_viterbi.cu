@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
 // Certificate: every arg-max (all states, all genes, and the final one) records the gap between
 // winner and runner-up.  Scores of the two arithmetics differ by at most n * (table error +
 // rounding) ~ 1e-8 for n <= 3000, so a sequence whose smallest gap exceeds tau = 1e-7 has the same
-// trace in both.  Sequences below tau are appended to a list and recomputed by the exact kernel
+// trace in both (tau is 2^-23 in the launcher).  Sequences below tau are appended to a list and recomputed by the exact kernel
 // above (list mode); their count is reported.
 #include "icnv_emission_table.inc"
 
@@ -332,8 +332,14 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// |x - mean| / sd beyond the table (> 24): nmath evaluation, kept out of line (rare)
+__device__ __noinline__ double emission_far(double x, double mean, double sd) {
+    const double zz = __ddiv_rn(fabs(__dadd_rn(x, -mean)), sd);
+    return -log(-pnorm_upper_log_exact(zz));
+}
+
 template <int M>
-__global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const VitParams p) {
+__global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
     double *tab = sm;                                            // [5][ICNV_EMIS_N]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -344,6 +350,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const Vit
     const int64_t warp_global = (int64_t)blockIdx.x * FAST_WARPS + warp;
     uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
     const double a = p.a_diag, b = p.b_off;
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC == rint(v), low word == (int)rint(v)
+    const int tau_hi = __double2hiint(p.tau);
     int err = 0;
 
     for (;;) {
@@ -364,8 +372,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const Vit
             if (active && n == 1) scol[cs] = 3;
             continue;
         }
-        const double inv_sd = p.sd_col ? 1.0 / p.sd_col[cc] : p.inv_sd;
         const double sd = p.sd_col ? p.sd_col[cc] : p.sd;
+        const double scale = (double)ICNV_EMIS_INVW / sd;   // zs = 16 * |x - mean| / sd
         const int g_lo = cs, g_hi = cs + n;
         const int b_first = g_lo / TG, b_last = (g_hi - 1) / TG;
 
@@ -375,19 +383,21 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const Vit
             double *dst = tiles + buf * (32 * TS);
             const int col = lane & 7;
             const int64_t gene = (int64_t)blk * TG + col;
+            const bool ok = gene < p.G;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int row = q * 4 + (lane >> 3);
                 int64_t cell = c0 + row;
                 if (cell >= p.C) cell = p.C - 1;
-                const bool ok = gene < p.G;
                 const double *src = p.X + p.G * cell + (ok ? gene : 0);
                 cp_async8(dst + row * TS + col, src, ok);
             }
         };
 
         double nu[MAXM];
-        double gapmin = INFINITY;
+        // certificate: smallest decision margin seen, tracked through the HIGH WORD of the (non-negative)
+        // gap - monotone in the gap, exact for the power-of-two threshold, two integer ops per check
+        unsigned mg = 0x7fffffffu;
         issue_tile(b_first, 0);
         cp_async_commit();
         for (int blk = b_first; blk <= b_last; ++blk) {
@@ -401,30 +411,28 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const Vit
             }
             __syncwarp();
             const double *row = tiles + buf * (32 * TS) + lane * TS;
-#pragma unroll
-            for (int j = 0; j < TG; ++j) {
-                const int g = blk * TG + j;
-                if (g < g_lo || g >= g_hi) continue;  // warp-uniform
-                const int i = g - g_lo;
+            const int j0 = max(0, g_lo - blk * TG), j1 = min(TG, g_hi - blk * TG);
+#pragma unroll 1
+            for (int j = j0; j < j1; ++j) {
+                const int i = blk * TG + j - g_lo;
                 const double x = row[j];
                 if (!is_finite_d(x)) err |= 1;
-                // ---- emissions ------------------------------------------------------------------
+                // ---- emissions: g(z_k) from the table ------------------------------------------------
                 double le[MAXM];
 #pragma unroll
                 for (int k = 0; k < M; ++k) {
-                    const double z = fabs(x - p.mean[k]) * inv_sd;
+                    const double zs = fabs(x - p.mean[k]) * scale;
                     double v;
-                    if (z < (double)ICNV_EMIS_ZMAX) {
-                        const int idx = __double2int_rz(z * (double)ICNV_EMIS_INVW);
-                        const double u = fma(z, 2.0 * ICNV_EMIS_INVW, -(double)(2 * idx + 1));
-                        const double *t = tab + idx;
+                    if (zs < (double)(ICNV_EMIS_N - 1)) {
+                        const double m = zs + MAGIC;
+                        const double u = zs - (m - MAGIC);
+                        const double *t = tab + __double2loint(m);
                         v = fma(u, t[4 * ICNV_EMIS_N], t[3 * ICNV_EMIS_N]);
                         v = fma(u, v, t[2 * ICNV_EMIS_N]);
                         v = fma(u, v, t[1 * ICNV_EMIS_N]);
                         v = fma(u, v, t[0]);
-                    } else {  // beyond the table (|x - mean| > 24 sd): nmath evaluation
-                        const double zz = __ddiv_rn(fabs(__dadd_rn(x, -p.mean[k])), sd);
-                        v = -log(-pnorm_upper_log_exact(zz));
+                    } else {
+                        v = emission_far(x, p.mean[k], sd);
                     }
                     le[k] = v;
                 }
@@ -433,49 +441,33 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const Vit
                     for (int k = 0; k < M; ++k) nu[k] = p.logdelta[k] + le[k];
                     continue;
                 }
-                // ---- top three of t_j = nu[j] + b, first index on ties ------------------------------
+                // ---- t_k = nu[k] + b with k in the 3 low mantissa bits (a <= 7-ulp perturbation, inside
+                //      the certificate's error budget): the running max then carries its own index ----
                 double t[MAXM];
 #pragma unroll
-                for (int k = 0; k < M; ++k) t[k] = nu[k] + b;
+                for (int k = 0; k < M; ++k) {
+                    const double v = nu[k] + b;
+                    t[k] = __hiloint2double(__double2hiint(v), (__double2loint(v) & ~7) | k);
+                }
                 double T1 = t[0];
-                int i1 = 0;
 #pragma unroll
-                for (int k = 1; k < M; ++k)
-                    if (t[k] > T1) {
-                        T1 = t[k];
-                        i1 = k;
-                    }
-                double T2 = -INFINITY;
-                int i2 = -1;
-#pragma unroll
-                for (int k = 0; k < M; ++k)
-                    if (k != i1 && t[k] > T2) {
-                        T2 = t[k];
-                        i2 = k;
-                    }
-                double T3 = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < M; ++k)
-                    if (k != i1 && k != i2 && t[k] > T3) T3 = t[k];
-                // ---- per state: stay (nu[k] + a) against the best other state ---------------------------
+                for (int k = 1; k < M; ++k) T1 = fmax(T1, t[k]);
+                const int i1 = __double2loint(T1) & 7;
+                // ---- per state: stay (nu[k] + a) or come from the best state (T1).  With a > b the best
+                //      state always stays, so the runner-up is never a third state unless T1 - t[k] is
+                //      itself small - which the second check catches. --------------------------------------
                 uint32_t word = 0;
-                double nn[MAXM];
 #pragma unroll
                 for (int k = 0; k < M; ++k) {
-                    const bool is1 = (k == i1);
-                    const double other = is1 ? T2 : T1;
-                    const int oi = is1 ? i2 : i1;
-                    const double nxt = (is1 || k == i2) ? T3 : T2;
                     const double d = nu[k] + a;
-                    const bool stay = (d > other) || (d == other && k < oi);
-                    const double best = stay ? d : other;
-                    const double second = stay ? other : fmax(d, nxt);
-                    gapmin = fmin(gapmin, best - second);
-                    nn[k] = best + le[k];
-                    word |= (uint32_t)(stay ? k : oi) << (3 * k);
+                    const double e = d - T1;
+                    const int he = __double2hiint(e);
+                    const bool stay = he >= 0;
+                    mg = min(mg, (unsigned)(he & 0x7fffffff));                      // |stay - from_best|
+                    mg = min(mg, (unsigned)__double2hiint(T1 - t[k]) - 1u);         // best vs this state (0 for k == i1 wraps to max)
+                    nu[k] = (stay ? d : T1) + le[k];
+                    word |= (uint32_t)(stay ? k : i1) << (3 * k);
                 }
-#pragma unroll
-                for (int k = 0; k < M; ++k) nu[k] = nn[k];
                 bp[(int64_t)i * 32 + lane] = word;
             }
             __syncwarp();
@@ -497,38 +489,122 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) viterbi_fast_kernel(const Vit
                 }
             }
             if (under && active) err |= 2;
-            gapmin = fmin(gapmin, best - second);
+            const double gap = best - second;
+            if (!(gap >= p.tau)) mg = 0;   // also catches NaN
         }
-        // uncertified sequences go to the exact kernel (NaN gaps compare false -> also listed)
-        if (active && !(gapmin >= p.tau)) {
+        // uncertified sequences go to the exact kernel
+        if (active && (int)mg < tau_hi) {
             unsigned pos = atomicAdd(p.list_out_count, 1u);
             if (pos < p.list_cap) p.list_out[pos] = make_int2(p.item_chr_id[ks], (int)c);
         }
-        // ---- traceback; states leave as 8-byte words when the layout allows it ---------------------
+        // ---- traceback in aligned blocks of 8 genes: the 8 backpointer words are loaded together
+        //      (independent addresses), states leave as one 8-byte word when the layout allows it -----
         const bool wide = ((p.G & 7) == 0);  // then (G*c + g) is 8-aligned whenever g is
-        unsigned long long pack = 0;
-        for (int i = n - 1; i >= 0; --i) {
-            const int g = g_lo + i;
-            if (wide) {
-                pack |= (unsigned long long)(y + 1) << (8 * (g & 7));
-                if ((g & 7) == 0 || i == 0) {
-                    if (active) {
-                        const int gb = g & ~7;
-                        if (gb >= g_lo && gb + 8 <= g_hi) {
-                            *reinterpret_cast<unsigned long long *>(scol + gb) = pack;
-                        } else {  // ragged first / last block of the chromosome
-                            for (int q = 0; q < 8; ++q) {
-                                const int gg = gb + q;
-                                if (gg >= g_lo && gg < g_hi && gg >= g) scol[gg] = (uint8_t)(pack >> (8 * q));
-                            }
+        for (int gb = (g_hi - 1) & ~7; gb + 8 > g_lo; gb -= 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = gb + q - g_lo;
+                w[q] = (i >= 1 && i < n) ? bp[(int64_t)i * 32 + lane] : 0u;
+            }
+            unsigned long long pack = 0;
+#pragma unroll
+            for (int q = 7; q >= 0; --q) {
+                const int g = gb + q;
+                if (g >= g_lo && g < g_hi) {
+                    pack |= (unsigned long long)(y + 1) << (8 * q);
+                    if (g > g_lo) y = (int)((w[q] >> (3 * y)) & 7u);
+                }
+            }
+            if (active) {
+                if (wide && gb >= g_lo && gb + 8 <= g_hi) {
+                    *reinterpret_cast<unsigned long long *>(scol + gb) = pack;
+                } else {  // ragged first / last block of the chromosome, or unaligned layout
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int g = gb + q;
+                        if (g >= g_lo && g < g_hi) scol[g] = (uint8_t)(pack >> (8 * q));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (err && p.err_flag) atomicOr(p.err_flag, err);
+}
+
+// Exact re-run of the sequences the certificate rejected: one warp per sequence.  The 32 lanes
+// evaluate the reference-order emissions of 32 genes at a time (the expensive, embarrassingly
+// parallel part) into a per-warp scratch row; lane 0 then runs the short sequential recursion.
+template <int M>
+__global__ void __launch_bounds__(128) viterbi_list_kernel(const VitParams p, double *__restrict__ le_scratch) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
+    double *__restrict__ leb = le_scratch + warp_global * (int64_t)p.max_len * MAXM;
+    const int64_t n_items = (int64_t)min(*p.list_count, p.list_cap);
+    int err = 0;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(p.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= n_items) break;
+        const int2 e = p.list[item];
+        const int cs = p.chr_start_orig[e.x], n = p.chr_len_orig[e.x];
+        const int64_t c = e.y;
+        const double *__restrict__ xcol = p.X + p.G * c + cs;
+        uint8_t *__restrict__ scol = p.states + p.G * c + cs;
+        const double sd = p.sd_col ? p.sd_col[c] : p.sd;
+        for (int i = lane; i < n; i += 32) {
+            double le[MAXM];
+            emission_exact<M>(xcol[i], p.mean, sd, le);
+#pragma unroll
+            for (int k = 0; k < M; ++k) leb[(int64_t)i * MAXM + k] = le[k];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double nu[MAXM];
+#pragma unroll
+            for (int k = 0; k < M; ++k) nu[k] = __dadd_rn(p.logdelta[k], leb[k]);
+            for (int i = 1; i < n; ++i) {
+                double nn[MAXM];
+                uint32_t word = 0;
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    double best = __dadd_rn(nu[0], p.logPi[0 * M + k]);
+                    int arg = 0;
+#pragma unroll
+                    for (int j = 1; j < M; ++j) {
+                        double v = __dadd_rn(nu[j], p.logPi[j * M + k]);
+                        if (v > best) {
+                            best = v;
+                            arg = j;
                         }
                     }
-                    pack = 0;
-                } 
-            } else if (active) {
-                scol[g] = (uint8_t)(y + 1);
+                    nn[k] = __dadd_rn(best, leb[(int64_t)i * MAXM + k]);
+                    word |= (uint32_t)arg << (3 * k);
+                }
+#pragma unroll
+                for (int k = 0; k < M; ++k) nu[k] = nn[k];
+                bp[(int64_t)i * 32] = word;
             }
-            if (i > 0) y = (int)((bp[(int64_t)i * 32 + lane] >> (3 * y)) & 7u);
+            int y = 0;
+            double best = nu[0];
+            bool under = (nu[0] == -INFINITY);
+#pragma unroll
+            for (int k = 1; k < M; ++k) {
+                under |= (nu[k] == -INFINITY);
+                if (nu[k] > best) {
+                    best = nu[k];
+                    y = k;
+                }
+            }
+            if (under) err |= 2;
+            scol[n - 1] = (uint8_t)(y + 1);
+            for (int i = n - 1; i >= 1; --i) {
+                y = (int)((bp[(int64_t)i * 32] >> (3 * y)) & 7u);
+                scol[i - 1] = (uint8_t)(y + 1);
+            }
         }
         __syncwarp();
     }
@@ -695,14 +771,14 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     p.a_diag = p.logPi[0];
     p.b_off = p.logPi[1];
     p.inv_sd = sd_per_col ? 0.0 : 1.0 / p.sd;
-    p.tau = 1e-7;
+    p.tau = 1.1920928955078125e-07;  // 2^-23: power of two, so the high-word comparison in the kernel is exact
     p.table = d_table;
     p.list_out = d_list;
     p.list_out_count = c.hmm_list_count;
     p.list_cap = (unsigned int)std::min<size_t>(list_cap, 0xffffffffu);
 
     auto fkern = (m == 6) ? viterbi_fast_kernel<6> : viterbi_fast_kernel<3>;
-    auto lkern = (m == 6) ? viterbi_kernel<6, false> : viterbi_kernel<3, false>;
+    auto lkern = (m == 6) ? viterbi_list_kernel<6> : viterbi_list_kernel<3>;
     const size_t smem = sizeof(double) * (5 * ICNV_EMIS_N + FAST_WARPS * 2 * 32 * TS);
     ICNV_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -722,8 +798,10 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     p.list = d_list;
     p.list_count = c.hmm_list_count;
     p.counter = d_counter + 1;
-    lkern<<<(unsigned)list_blocks, 128, 0, st>>>(p);
-    ICNV_CHECK_LAUNCH("viterbi_kernel(list)");
+    double *d_le = (double *)scratch(SLOT_LE, sizeof(double) * (size_t)(list_blocks * 4) * (size_t)max_len * MAXM);
+    if (!d_le) return ICNV_E_NOMEM;
+    lkern<<<(unsigned)list_blocks, 128, 0, st>>>(p, d_le);
+    ICNV_CHECK_LAUNCH("viterbi_list_kernel");
     return ICNV_OK;
 }
 

@@ -33,6 +33,7 @@ class Engine:
         torch.cuda.set_device(self.device)
         _lib.check(self.lib.icnv_init(self.device))
         self.tdev = torch.device("cuda", self.device)
+        self.timing = None   # when set to a list, smooth_block appends (name, start_event, end_event)
 
     # ---- data ---------------------------------------------------------------------------------------
     def synth(self, G, chr_start, chr_len, cells_global, C_total, seed) -> torch.Tensor:
@@ -140,7 +141,13 @@ class Engine:
             pos += len(g)
         b2 = self.bounds(group_means(T, t_lists, False))
         # pass 2: every local cell, one read and one write of the matrix
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self.cell_pipeline(X, None, Y, chr_start, chr_len, apply_log, b1, threshold, window, 1, b2, True, use_bounds, flag)
+        if self.timing is not None:
+            e1.record()
+            self.timing.append(("cell_pipeline_pass2", e0, e1))
         return Y, flag
 
     def viterbi(self, X, chr_start, chr_len, Pi, delta, mean, sd, out=None, want_margins=False):

@@ -57,7 +57,7 @@ def test_center_known_answers_and_median(api):
     want = np.tile(np.array([-3, -2, -1, 0, 1, 2, 3], dtype=float), (3, 1)).T
     np.testing.assert_allclose(api.center(m, "mean"), want, atol=1e-12)
     rng = np.random.default_rng(1)
-    for G in [1, 2, 3, 10, 11, 64, 65, 257, 1000, 4613, 8508, 10000, 11500]:
+    for G in [1, 2, 3, 10, 11, 64, 65, 257, 1000, 2817, 4613, 5633, 8508, 10000, 11264]:
         X = rng.normal(size=(G, 7))
         X[:, 1] = 0.25                      # all equal
         X[: G // 2, 2] = 1.0                # two big tie clusters
@@ -92,7 +92,7 @@ def test_smooth_lengths_and_windows_vs_literal_oracle(api):
         got = api.smooth(X, cs, lens, w)
         want = orc.smooth_by_chromosome(X, cs, lens, w, literal=True)
         err = np.max(np.abs(got - want))
-        assert err < 1e-12, (w, err)
+        assert err < 5e-11, (w, err)   # prefix-sum formulation: ~n^1.5 ulp of cancellation, far inside 1e-5
         # single-gene chromosomes are skipped (ops.R:2417)
         np.testing.assert_array_equal(got[cs[0]], X[cs[0]])
         np.testing.assert_array_equal(got[cs[16]], X[cs[16]])
