@@ -109,6 +109,16 @@ ICNV_API int icnv_smooth_block_f64(const double *X, double *Y, int64_t G, int64_
                                    const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx,
                                    int n_grp, int apply_log, double threshold, int window, int use_bounds);
 
+/* Fused icnv_smooth_block_f64 + per-cell icnv_viterbi_f64 in ONE pass over the matrix: run() steps
+ * 4..14 followed by step 17 for analysis_mode = "cells" (R/inferCNV_ops.R:614-1031, :1235-1309); with
+ * the default prune_outliers = FALSE nothing between those steps touches expr.data.  Y receives the
+ * smoothed matrix (what run() keeps as the preliminary object), states the HMM calls on it. */
+ICNV_API int icnv_smooth_hmm_f64(const double *X, double *Y, int32_t *states, int64_t G, int64_t C,
+                                 const int32_t *chr_start, const int32_t *chr_len, int K, const int32_t *grp_off,
+                                 const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window,
+                                 int use_bounds, int m, const double *Pi, const double *delta, const double *mean,
+                                 const double *sd);
+
 /* Viterbi.dthmm.adj, R/inferCNV_HMM.R:1101-1176, batched over the drivers
  * predict_CNV_via_HMM_on_indiv_cells (HMM.R:284-324), ..._on_tumor_subclusters (:345-408),
  * ..._on_whole_tumor_samples (:509-567) and the i3 twins (R/inferCNV_i3HMM.R:180-389).

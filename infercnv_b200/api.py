@@ -122,6 +122,23 @@ def smooth_block(X, chr_start, chr_len, ref_groups, apply_log=True, threshold=3.
     return Y
 
 
+def smooth_hmm(X, chr_start, chr_len, ref_groups, Pi, delta, mean, sd, apply_log=True, threshold=3.0, window_length=101,
+               use_bounds=True, out=None, out_states=None):
+    """Fused smooth block + per-cell HMM (one upload of the matrix).  Returns (Y, states)."""
+    X = _f64(X)
+    G, C = X.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    off, idx = groups_to_csr(ref_groups)
+    Pi = np.asfortranarray(Pi, dtype=np.float64)
+    delta, mean, sd = (np.ascontiguousarray(v, dtype=np.float64) for v in (delta, mean, sd))
+    Y = np.empty_like(X, order="F") if out is None else out
+    S = np.empty((G, C), dtype=np.int32, order="F") if out_states is None else out_states
+    _lib.check(_lib.load().icnv_smooth_hmm_f64(_p(X), _p(Y), _p(S), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx),
+                                               len(ref_groups), int(bool(apply_log)), float(threshold), int(window_length),
+                                               int(bool(use_bounds)), Pi.shape[0], _p(Pi), _p(delta), _p(mean), _p(sd)))
+    return Y, S
+
+
 def viterbi(X, chr_start, chr_len, Pi, delta, mean, sd, groups=None, want_margins=False, out=None):
     X = _f64(X)
     G, C = X.shape

@@ -112,6 +112,19 @@ static int dev_group_means(const double *dX, int64_t G, int64_t ldx, const int32
     return ICNV_OK;
 }
 
+static void destroy_streams(Ctx &c) {
+    if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.s_h2d) cudaStreamDestroy(c.s_h2d);
+    if (c.s_d2h) cudaStreamDestroy(c.s_d2h);
+    c.stream = c.s_h2d = c.s_d2h = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
+        if (c.ev_comp[i]) cudaEventDestroy(c.ev_comp[i]);
+        if (c.ev_d2h[i]) cudaEventDestroy(c.ev_d2h[i]);
+        c.ev_h2d[i] = c.ev_comp[i] = c.ev_d2h[i] = nullptr;
+    }
+}
+
 }  // namespace icnv
 
 using namespace icnv;
@@ -145,8 +158,7 @@ int icnv_init(int device) {
             c.slot_ptr[s] = nullptr;
             c.slot_bytes[s] = 0;
         }
-        if (c.stream) cudaStreamDestroy(c.stream);
-        c.stream = nullptr;
+        destroy_streams(c);
         c.ready = false;
     }
     cudaError_t e = cudaSetDevice(device);
@@ -160,6 +172,13 @@ int icnv_init(int device) {
     c.sm_count = prop.multiProcessorCount;
     c.smem_optin = (int)prop.sharedMemPerBlockOptin;
     e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c.s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_comp[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev_d2h[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) return set_error(ICNV_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     c.device = device;
     c.launches = 0;
@@ -182,8 +201,7 @@ void icnv_shutdown(void) {
         c.slot_ptr[s] = nullptr;
         c.slot_bytes[s] = 0;
     }
-    cudaStreamDestroy(c.stream);
-    c.stream = nullptr;
+    destroy_streams(c);
     c.ready = false;
 }
 
@@ -345,21 +363,149 @@ int icnv_center_f64(const double *X, double *Y, int64_t G, int64_t C, int use_me
     return host_cell_pipeline(X, Y, G, C, nullptr, nullptr, 0, nullptr, 0, 0, 0, use_median ? 1 : 2, st);
 }
 
+// ---- slab pipeline: cells are independent once the reference means are known, so the matrix moves
+// through the GPU in slabs of SLAB_CELLS columns - H2D of slab i+1, kernels on slab i and D2H of slab
+// i-1 run concurrently on three streams (double-buffered device slabs).  PCIe, not the kernels, bounds
+// the host-pointer entry points; this hides everything but the slower copy direction. ---------------
+static const int64_t SLAB_CELLS = 1024;
+
+struct HmmModel {
+    int m;
+    const double *Pi, *delta, *mean, *sd;
+};
+
+// Y (optional) = smooth block of X; states (optional) = per-cell Viterbi of the block's output (or of X
+// itself when do_smooth == 0).
+static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, int64_t G, int64_t C,
+                         const int32_t *chr_start, const int32_t *chr_len, int K, int do_smooth, const int32_t *grp_off,
+                         const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window, int use_bounds,
+                         const HmmModel *hmm) {
+    cudaStream_t sc = c.stream, sh = c.s_h2d, sd = c.s_d2h;
+    int rc;
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), sc));
+    double *lo1 = nullptr, *hi1 = nullptr, *mid1 = nullptr, *lo2 = nullptr, *hi2 = nullptr, *mid2 = nullptr;
+
+    if (do_smooth) {
+        // ---- reference pre-passes on a compact copy of the reference columns (<= ~10 % of the cells) ----
+        const int64_t n_ref = grp_off[n_grp];
+        double *d_ref = (double *)scratch(SLOT_REFX, sizeof(double) * (size_t)G * (size_t)n_ref);
+        double *d_T = (double *)scratch(SLOT_TMP, sizeof(double) * (size_t)G * (size_t)n_ref);
+        double *d_means = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
+        double *d_b = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)G * 6);
+        int32_t *d_iota = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_ref);
+        if (!d_ref || !d_T || !d_means || !d_b || !d_iota) return ICNV_E_NOMEM;
+        for (int64_t i = 0; i < n_ref;) {  // runs of consecutive cells go up in one copy
+            int64_t j = i + 1;
+            while (j < n_ref && grp_idx[j] == grp_idx[j - 1] + 1) ++j;
+            ICNV_CUDA(cudaMemcpyAsync(d_ref + G * i, X + G * (int64_t)grp_idx[i], sizeof(double) * (size_t)(G * (j - i)),
+                                      cudaMemcpyHostToDevice, sc));
+            i = j;
+        }
+        std::vector<int32_t> iota((size_t)n_ref);
+        std::iota(iota.begin(), iota.end(), 0);
+        ICNV_CUDA(cudaMemcpyAsync(d_iota, iota.data(), sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, sc));
+        ICNV_CUDA(cudaStreamSynchronize(sc));
+        lo1 = d_b; hi1 = d_b + G; mid1 = d_b + 2 * G; lo2 = d_b + 3 * G; hi2 = d_b + 4 * G; mid2 = d_b + 5 * G;
+        if ((rc = dev_group_means(d_ref, G, G, d_iota, grp_off, n_grp, apply_log ? 1 : 0, d_means, sc))) return rc;
+        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo1, hi1, mid1, sc))) return rc;
+        rc = icnv_dev_cell_pipeline_f64(d_ref, G, G, nullptr, n_ref, d_T, G, chr_start, chr_len, K, apply_log,
+                                        use_bounds ? lo1 : nullptr, use_bounds ? hi1 : nullptr, use_bounds ? nullptr : mid1,
+                                        threshold, window, 1, nullptr, nullptr, nullptr, 0, d_flag, sc);
+        if (rc) return rc;
+        if ((rc = dev_group_means(d_T, G, G, d_iota, grp_off, n_grp, 0, d_means, sc))) return rc;
+        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo2, hi2, mid2, sc))) return rc;
+        if (!use_bounds) lo1 = hi1 = lo2 = hi2 = nullptr;
+        else mid1 = mid2 = nullptr;
+    }
+
+    // ---- slabs ------------------------------------------------------------------------------------------
+    const int64_t slab = std::min<int64_t>(SLAB_CELLS, C);
+    const size_t slab_elems = (size_t)G * (size_t)slab;
+    double *dIn[2], *dOut[2] = {nullptr, nullptr};
+    uint8_t *dSt[2] = {nullptr, nullptr};
+    int32_t *dW[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; ++b) {
+        dIn[b] = (double *)scratch(SLOT_SLAB_IN0 + b, sizeof(double) * slab_elems);
+        if (!dIn[b]) return ICNV_E_NOMEM;
+        if (do_smooth) {
+            dOut[b] = (double *)scratch(SLOT_SLAB_OUT0 + b, sizeof(double) * slab_elems);
+            if (!dOut[b]) return ICNV_E_NOMEM;
+        }
+        if (hmm) {
+            dSt[b] = (uint8_t *)scratch(SLOT_SLAB_ST0 + b, slab_elems);
+            dW[b] = (int32_t *)scratch(SLOT_SLAB_W0 + b, sizeof(int32_t) * slab_elems);
+            if (!dSt[b] || !dW[b]) return ICNV_E_NOMEM;
+        }
+    }
+    const int64_t n_slabs = (C + slab - 1) / slab;
+    for (int64_t i = 0; i < n_slabs; ++i) {
+        const int b = (int)(i & 1);
+        const int64_t c0 = i * slab, nc = std::min<int64_t>(slab, C - c0);
+        const size_t bytes = sizeof(double) * (size_t)G * (size_t)nc;
+        // H2D of slab i may start once the kernels of slab i-2 have consumed buffer b
+        if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sh, c.ev_comp[b], 0));
+        ICNV_CUDA(cudaMemcpyAsync(dIn[b], X + G * c0, bytes, cudaMemcpyHostToDevice, sh));
+        ICNV_CUDA(cudaEventRecord(c.ev_h2d[b], sh));
+        // kernels: need the slab on the device and the output buffers of slab i-2 drained
+        ICNV_CUDA(cudaStreamWaitEvent(sc, c.ev_h2d[b], 0));
+        if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sc, c.ev_d2h[b], 0));
+        const double *hmm_in = dIn[b];
+        if (do_smooth) {
+            rc = icnv_dev_cell_pipeline_f64(dIn[b], G, G, nullptr, nc, dOut[b], G, chr_start, chr_len, K, apply_log, lo1, hi1,
+                                            mid1, threshold, window, 1, lo2, hi2, mid2, 1, d_flag, sc);
+            if (rc) return rc;
+            hmm_in = dOut[b];
+        }
+        if (hmm) {
+            rc = icnv_dev_viterbi_f64(hmm_in, G, nc, chr_start, chr_len, K, hmm->m, hmm->Pi, hmm->delta, hmm->mean, hmm->sd,
+                                      0, dSt[b], nullptr, d_flag, sc);
+            if (rc) return rc;
+            if ((rc = icnv_dev_widen_states(dSt[b], dW[b], (int64_t)G * nc, sc))) return rc;
+        }
+        ICNV_CUDA(cudaEventRecord(c.ev_comp[b], sc));
+        // D2H
+        ICNV_CUDA(cudaStreamWaitEvent(sd, c.ev_comp[b], 0));
+        if (do_smooth && Y) ICNV_CUDA(cudaMemcpyAsync(Y + G * c0, dOut[b], bytes, cudaMemcpyDeviceToHost, sd));
+        if (hmm && states)
+            ICNV_CUDA(cudaMemcpyAsync(states + G * c0, dW[b], sizeof(int32_t) * (size_t)G * (size_t)nc, cudaMemcpyDeviceToHost, sd));
+        ICNV_CUDA(cudaEventRecord(c.ev_d2h[b], sd));
+    }
+    ICNV_CUDA(cudaStreamSynchronize(sh));
+    ICNV_CUDA(cudaStreamSynchronize(sd));
+    return check_flag(d_flag, sc);
+}
+
 int icnv_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,
                           const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
                           int apply_log, double threshold, int window, int use_bounds) {
     ICNV_HOST_PROLOGUE();
     if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_smooth_block_f64: bad argument");
-    double *dX, *dY;
-    int rc;
-    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
-    dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
-    if (!dY) return ICNV_E_NOMEM;
-    rc = icnv_dev_smooth_block_f64(dX, dY, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, apply_log, threshold,
-                                   window, use_bounds, st);
+    int rc = validate_chr(G, chr_start, chr_len, K);
     if (rc) return rc;
-    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
-    return check_flag((int *)c.slot_ptr[SLOT_MISC], st);
+    if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, false))) return rc;
+    return host_pipeline(c, X, Y, nullptr, G, C, chr_start, chr_len, K, 1, grp_off, grp_idx, n_grp, apply_log, threshold,
+                         window, use_bounds, nullptr);
+}
+
+/* Fused smooth block + per-cell HMM in one pass over the matrix: run() steps 4..14 and step 17 for
+ * analysis_mode = "cells" with prune_outliers = FALSE (the defaults between them do not touch expr.data).
+ * Saves the second upload of the matrix that two separate calls need. */
+int icnv_smooth_hmm_f64(const double *X, double *Y, int32_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                        const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                        int apply_log, double threshold, int window, int use_bounds, int m, const double *Pi,
+                        const double *delta, const double *mean, const double *sd) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || !states || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd)
+        return set_error(ICNV_E_BAD_ARG, "icnv_smooth_hmm_f64: bad argument");
+    if (m != 6 && m != 3) return set_error(ICNV_E_BAD_ARG, "m must be 6 or 3");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, false))) return rc;
+    HmmModel hm{m, Pi, delta, mean, sd};
+    return host_pipeline(c, X, Y, states, G, C, chr_start, chr_len, K, 1, grp_off, grp_idx, n_grp, apply_log, threshold,
+                         window, use_bounds, &hm);
 }
 
 int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
@@ -373,6 +519,10 @@ int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_s
     if (rc) return rc;
     rc = validate_groups(C, grp_off, grp_idx, n_grp, true);
     if (rc) return rc;
+    if (n_grp == 0 && !margins) {  // per-cell mode: slab pipeline (copies overlap the kernels)
+        HmmModel hm{m, Pi, delta, mean, sd};
+        return host_pipeline(c, X, nullptr, states, G, C, chr_start, chr_len, K, 0, nullptr, nullptr, 0, 0, 0.0, 0, 0, &hm);
+    }
     double *dX;
     if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
     int *d_flag = (int *)scratch(SLOT_MISC, 64);

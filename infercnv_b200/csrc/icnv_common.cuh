@@ -36,6 +36,11 @@ enum ScratchSlot {
     SLOT_TABLE,       // emission polynomial table
     SLOT_LIST,        // sequences to re-run exactly
     SLOT_LE,          // per-warp emission rows of the exact re-run
+    SLOT_SLAB_IN0, SLOT_SLAB_IN1,     // double-buffered cell slabs of the pipelined host entry points
+    SLOT_SLAB_OUT0, SLOT_SLAB_OUT1,
+    SLOT_SLAB_ST0, SLOT_SLAB_ST1,     // uint8 states per slab
+    SLOT_SLAB_W0, SLOT_SLAB_W1,       // int32 states per slab
+    SLOT_REFX,                        // compact copy of the reference cells' columns
     SLOT_COUNT
 };
 
@@ -45,6 +50,8 @@ struct Ctx {
     int sm_count = 0;
     int smem_optin = 0;      // max dynamic shared memory per block (opt-in), bytes
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host entry points
+    cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
     void *slot_ptr[SLOT_COUNT] = {};
     size_t slot_bytes[SLOT_COUNT] = {};
     std::atomic<int64_t> launches{0};

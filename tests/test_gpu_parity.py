@@ -298,6 +298,29 @@ def test_oligodendroglioma_hmm_cells_and_samples(api, oligo, hmm_fixture):
     np.testing.assert_array_equal(got3, want3)
 
 
+def test_multi_slab_host_pipeline_and_fused_call(api, hmm_fixture):
+    """More cells than one slab (1024): the pipelined host entry points (H2D / kernels / D2H
+    overlapped over cell slabs) and the fused smooth+HMM call against the oracle."""
+    rng = np.random.default_rng(77)
+    lens = np.array([120, 1, 60, 150, 41])
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(lens.sum()), 2500
+    counts = rng.poisson(rng.lognormal(0.5, 1.0, size=(G, 1)) * rng.lognormal(0, 0.2, size=(1, C))).astype(np.float64)
+    counts[cs[3]:cs[3] + lens[3], 1200:1400] *= 1.6
+    refs = [np.arange(0, 150), np.array([2400, 2401, 2499, 1024, 1023])]
+    mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    Pi, delta = orc.hmm_params(6)
+    nt = orc.max_threads()
+    want = orc.smooth_block(counts, cs, lens, refs, window=51, nthreads=nt)
+    got = api.smooth_block(counts, cs, lens, refs, window_length=51)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-10
+    want_st = orc.viterbi_matrix(got, cs, lens, Pi, delta, mean, sd, nthreads=nt)
+    np.testing.assert_array_equal(api.viterbi(got, cs, lens, Pi, delta, mean, sd), want_st)
+    Y, S = api.smooth_hmm(counts, cs, lens, refs, Pi, delta, mean, sd, window_length=51)
+    np.testing.assert_array_equal(Y, got)        # same kernels, same order: bitwise equal
+    np.testing.assert_array_equal(S, want_st)
+
+
 # ---- median filter ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("window_size", [3, 7, 9])
 def test_median_filter_vs_oracle(api, window_size):
