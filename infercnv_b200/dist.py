@@ -65,8 +65,21 @@ def plan_shards(n_cells: int, ref_groups: list[np.ndarray], world: int) -> list[
     for g in ref_groups:
         is_ref[g] = True
     others = np.flatnonzero(~is_ref)
-    other_parts = np.array_split(others, world)
     cuts = [split_chunk_aligned(len(g), world) for g in ref_groups]
+    # the non-reference cells even out what the chunk-aligned reference cuts left uneven
+    ref_count = [sum(c[r][1] - c[r][0] for c in cuts) for r in range(world)]
+    base, extra = divmod(n_cells, world)
+    want = [max(0, base + (1 if r < extra else 0) - ref_count[r]) for r in range(world)]
+    scale_fix = len(others) - sum(want)
+    r = 0
+    while scale_fix != 0:                      # rounding leftovers (also when a rank is reference-only)
+        step = 1 if scale_fix > 0 else -1
+        if want[r % world] + step >= 0:
+            want[r % world] += step
+            scale_fix -= step
+        r += 1
+    bounds = np.concatenate([[0], np.cumsum(want)])
+    other_parts = [others[bounds[r]:bounds[r + 1]] for r in range(world)]
     max_chunks = [max((hi - lo + CHUNK - 1) // CHUNK for lo, hi in c) for c in cuts]
     plans = []
     for r in range(world):

@@ -1,0 +1,188 @@
+## infercnv_b200.R - drop-in GPU replacements for inferCNV's smoothing + HMM hot path.
+##
+## Usage (on a box with R, the infercnv package and a B200):
+##   R CMD SHLIB infercnvb200_shim.c -I<repo>/include -L<repo>/infercnv_b200 -linfercnv_b200
+##   dyn.load("<repo>/infercnv_b200/libinfercnv_b200.so"); dyn.load("infercnvb200_shim.so")
+##   source("infercnv_b200.R"); infercnvb200_install()
+##   infercnv::run(...)            # unchanged call; steps 8, 10, 11, 12, 17 now run on the GPU
+##
+## Each replacement has the SAME name and signature as the internal infercnv function it replaces
+## (reference file:line in the comments) and keeps a handle to the original, which it calls whenever
+## the input is outside the validated envelope (see .icnv_ok) or the library reports an error.
+## The S4 object, run() and every other step are untouched.  GPU use can be switched off with
+## options(infercnv.b200 = FALSE).
+
+.icnv_env <- new.env()
+
+.icnv_enabled <- function() {
+    isTRUE(getOption("infercnv.b200", TRUE)) && isTRUE(tryCatch(.Call("icnvR_available"), error = function(e) FALSE))
+}
+
+## envelope: base dense double matrix without NA/NaN/Inf (the R smoother strips NAs per cell,
+## ops.R:2487-2489; expr.data may also be a dgCMatrix, R/inferCNV.R:40)
+.icnv_ok <- function(m) {
+    is.matrix(m) && is.double(m) && !anyNA(m) && all(is.finite(range(m)))
+}
+
+.icnv_chr_codes <- function(infercnv_obj) {
+    chr <- infercnv_obj@gene_order[["chr"]]
+    codes <- as.integer(factor(chr, levels = unique(chr)))   # rows are pre-sorted by chr (R/inferCNV.R:407-413)
+    if (is.unsorted(codes)) return(NULL)
+    codes
+}
+
+.icnv_ref_groups <- function(infercnv_obj) {
+    if (length(infercnv_obj@reference_grouped_cell_indices) > 0) {
+        lapply(infercnv_obj@reference_grouped_cell_indices, as.integer)
+    } else {                                               # ops.R:1686-1689: proxy group of all observations
+        list(proxyNormal = as.integer(unlist(infercnv_obj@observation_grouped_cell_indices)))
+    }
+}
+
+.icnv_keep_names <- function(new, old) { dimnames(new) <- dimnames(old); new }
+
+## subtract_ref_expr_from_obs, R/inferCNV_ops.R:1678
+b200_subtract_ref_expr_from_obs <- function(infercnv_obj, inv_log=FALSE, use_bounds=TRUE) {
+    orig <- .icnv_env$orig$subtract_ref_expr_from_obs
+    m <- infercnv_obj@expr.data
+    if (!.icnv_enabled() || !.icnv_ok(m)) return(orig(infercnv_obj, inv_log=inv_log, use_bounds=use_bounds))
+    futile.logger::flog.info(sprintf("::subtract_ref_expr_from_obs:Start inv_log=%s, use_bounds=%s (B200)", inv_log, use_bounds))
+    res <- tryCatch(.Call("icnvR_subtract_ref", m, .icnv_ref_groups(infercnv_obj), inv_log, use_bounds),
+                    error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, inv_log=inv_log, use_bounds=use_bounds))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    if (!is.null(infercnv_obj@.hspike)) {
+        futile.logger::flog.info("-mirroring for hspike")
+        infercnv_obj@.hspike <- b200_subtract_ref_expr_from_obs(infercnv_obj@.hspike, inv_log=inv_log, use_bounds=use_bounds)
+    }
+    infercnv_obj
+}
+
+## smooth_by_chromosome, R/inferCNV_ops.R:2406
+b200_smooth_by_chromosome <- function(infercnv_obj, window_length, smooth_ends=TRUE) {
+    orig <- .icnv_env$orig$smooth_by_chromosome
+    m <- infercnv_obj@expr.data
+    codes <- .icnv_chr_codes(infercnv_obj)
+    ## even or < 2 windows: the reference's behaviour is accidental / identity - leave it to R
+    if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes) || window_length < 2 || window_length %% 2 == 0)
+        return(orig(infercnv_obj, window_length, smooth_ends))
+    res <- tryCatch(.Call("icnvR_smooth", m, codes, as.integer(window_length)), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, window_length, smooth_ends))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    if (!is.null(infercnv_obj@.hspike)) {
+        futile.logger::flog.info("-mirroring for hspike")
+        infercnv_obj@.hspike <- b200_smooth_by_chromosome(infercnv_obj@.hspike, window_length, smooth_ends)
+    }
+    infercnv_obj
+}
+
+## center_cell_expr_across_chromosome, R/inferCNV_ops.R:2074
+b200_center_cell_expr_across_chromosome <- function(infercnv_obj, method="mean") {
+    orig <- .icnv_env$orig$center_cell_expr_across_chromosome
+    m <- infercnv_obj@expr.data
+    if (!.icnv_enabled() || !.icnv_ok(m)) return(orig(infercnv_obj, method))
+    futile.logger::flog.info("::center_smooth across chromosomes per cell (B200)")
+    res <- tryCatch(.Call("icnvR_center", m, identical(method, "median")), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, method))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    if (!is.null(infercnv_obj@.hspike)) {
+        futile.logger::flog.info("-mirroring for hspike")
+        infercnv_obj@.hspike <- b200_center_cell_expr_across_chromosome(infercnv_obj@.hspike, method)
+    }
+    infercnv_obj
+}
+
+## Viterbi for a set of (group or cell) sequences; used by the six drivers below
+.icnv_hmm <- function(infercnv_obj, HMM_info, groups = NULL, sds = NULL) {
+    m <- infercnv_obj@expr.data
+    codes <- .icnv_chr_codes(infercnv_obj)
+    if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes)) return(NULL)
+    sd <- if (is.null(sds)) HMM_info[["state_emission_params"]]$sd else sds
+    res <- tryCatch(.Call("icnvR_viterbi", m, codes, groups, HMM_info[["state_transitions"]], HMM_info[["delta"]],
+                          HMM_info[["state_emission_params"]]$mean, as.double(sd)), error = function(e) NULL)
+    if (is.null(res)) return(NULL)
+    .icnv_keep_names(res, m)
+}
+
+## predict_CNV_via_HMM_on_indiv_cells, R/inferCNV_HMM.R:284
+b200_predict_CNV_via_HMM_on_indiv_cells <- function(infercnv_obj, cnv_mean_sd=infercnv:::get_spike_dists(infercnv_obj@.hspike), t=1e-6) {
+    res <- .icnv_hmm(infercnv_obj, infercnv:::.get_HMM(cnv_mean_sd, t))
+    if (is.null(res)) return(.icnv_env$orig$predict_CNV_via_HMM_on_indiv_cells(infercnv_obj, cnv_mean_sd, t))
+    infercnv_obj@expr.data <- res
+    infercnv_obj
+}
+
+## predict_CNV_via_HMM_on_tumor_subclusters, R/inferCNV_HMM.R:345
+b200_predict_CNV_via_HMM_on_tumor_subclusters <- function(infercnv_obj,
+        cnv_mean_sd=infercnv:::get_spike_dists(infercnv_obj@.hspike),
+        cnv_level_to_mean_sd_fit=infercnv:::get_hspike_cnv_mean_sd_trend_by_num_cells_fit(infercnv_obj@.hspike), t=1e-6) {
+    orig <- .icnv_env$orig$predict_CNV_via_HMM_on_tumor_subclusters
+    if (is.null(infercnv_obj@tumor_subclusters)) return(orig(infercnv_obj, cnv_mean_sd, cnv_level_to_mean_sd_fit, t))
+    groups <- lapply(unlist(infercnv_obj@tumor_subclusters[["subclusters"]], recursive=FALSE), as.integer)
+    sds <- unlist(lapply(groups, function(g)                       # .get_state_emission_params, HMM.R:586-614
+        infercnv:::.get_state_emission_params(length(g), cnv_mean_sd, cnv_level_to_mean_sd_fit)$sd))
+    res <- .icnv_hmm(infercnv_obj, infercnv:::.get_HMM(cnv_mean_sd, t), groups, sds)
+    if (is.null(res)) return(orig(infercnv_obj, cnv_mean_sd, cnv_level_to_mean_sd_fit, t))
+    infercnv_obj@expr.data <- res
+    infercnv_obj
+}
+
+## predict_CNV_via_HMM_on_whole_tumor_samples, R/inferCNV_HMM.R:509
+b200_predict_CNV_via_HMM_on_whole_tumor_samples <- function(infercnv_obj, cluster_by_groups,
+        cnv_mean_sd=infercnv:::get_spike_dists(infercnv_obj@.hspike),
+        cnv_level_to_mean_sd_fit=infercnv:::get_hspike_cnv_mean_sd_trend_by_num_cells_fit(infercnv_obj@.hspike), t=1e-6) {
+    obs <- infercnv_obj@observation_grouped_cell_indices
+    groups <- c(if (isTRUE(cluster_by_groups)) obs else list(all_observations = unlist(obs)),
+                infercnv_obj@reference_grouped_cell_indices)
+    groups <- lapply(groups, as.integer)
+    sds <- unlist(lapply(groups, function(g)
+        infercnv:::.get_state_emission_params(length(g), cnv_mean_sd, cnv_level_to_mean_sd_fit)$sd))
+    res <- .icnv_hmm(infercnv_obj, infercnv:::.get_HMM(cnv_mean_sd, t), groups, sds)
+    if (is.null(res))
+        return(.icnv_env$orig$predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj, cluster_by_groups, cnv_mean_sd,
+                                                                         cnv_level_to_mean_sd_fit, t))
+    infercnv_obj@expr.data <- res
+    infercnv_obj
+}
+
+## i3HMM_predict_CNV_via_HMM_on_indiv_cells, R/inferCNV_i3HMM.R:180 (group twins analogous; sd_trend stays R's)
+b200_i3HMM_predict_CNV_via_HMM_on_indiv_cells <- function(infercnv_obj, i3_p_val=0.05,
+        sd_trend=infercnv:::.i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val), t=1e-6, use_KS=TRUE) {
+    res <- .icnv_hmm(infercnv_obj, infercnv:::.i3HMM_get_HMM(sd_trend, t=t, i3_p_val=i3_p_val, use_KS=use_KS))
+    if (is.null(res)) return(.icnv_env$orig$i3HMM_predict_CNV_via_HMM_on_indiv_cells(infercnv_obj, i3_p_val, sd_trend, t, use_KS))
+    infercnv_obj@expr.data <- res
+    infercnv_obj
+}
+
+## apply_median_filtering, R/noise_reduction.R:43 (exported)
+b200_apply_median_filtering <- function(infercnv_obj, window_size=7, on_observations=TRUE, on_references=TRUE) {
+    orig <- .icnv_env$orig$apply_median_filtering
+    m <- infercnv_obj@expr.data
+    codes <- .icnv_chr_codes(infercnv_obj)
+    if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes) || window_size %% 2 != 1 || window_size < 3)
+        return(orig(infercnv_obj, window_size, on_observations, on_references))
+    lists <- list()
+    if (on_observations) for (tt in names(infercnv_obj@observation_grouped_cell_indices))
+        lists <- c(lists, lapply(infercnv_obj@tumor_subclusters[["subclusters"]][[tt]], as.integer))
+    if (on_references) lists <- c(lists, lapply(infercnv_obj@reference_grouped_cell_indices, as.integer))
+    res <- tryCatch(.Call("icnvR_median_filter", m, codes, lists, as.integer(window_size)), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, window_size, on_observations, on_references))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    infercnv_obj
+}
+
+infercnvb200_install <- function() {
+    fns <- c("subtract_ref_expr_from_obs", "smooth_by_chromosome", "center_cell_expr_across_chromosome",
+             "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
+             "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
+             "apply_median_filtering")
+    ns <- asNamespace("infercnv")
+    .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
+    for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")
+    invisible(TRUE)
+}
+
+infercnvb200_uninstall <- function() {
+    for (f in names(.icnv_env$orig)) utils::assignInNamespace(f, .icnv_env$orig[[f]], ns = "infercnv")
+    invisible(TRUE)
+}

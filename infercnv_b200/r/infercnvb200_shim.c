@@ -1,0 +1,203 @@
+/*
+ * infercnvb200_shim.c - the `.Call()` glue between R and libinfercnv_b200.so.
+ *
+ * Build on a machine with R:   R CMD SHLIB infercnvb200_shim.c -L<dir> -linfercnv_b200 -I<repo>/include
+ * (tests/test_r_shim_compiles.py compile-checks this file against a minimal mock of Rinternals.h,
+ *  because R is not installable in the build image.)
+ *
+ * Every entry: extract plain vectors from the SEXPs, allocate the result with allocMatrix, make ONE
+ * call into the C ABI, and turn a non-zero status into an R error AFTER all locals are dead
+ * (Rf_error longjmps).  Index vectors arrive 1-based from R and are shifted here.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "infercnv_b200.h"
+
+/* list of integer vectors (1-based) -> CSR (0-based); caller frees *off and *idx */
+static int list_to_csr(SEXP groups, int32_t **off, int32_t **idx) {
+    int n = Rf_length(groups);
+    int64_t total = 0;
+    for (int k = 0; k < n; ++k) total += Rf_length(VECTOR_ELT(groups, k));
+    *off = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1));
+    *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total > 0 ? total : 1));
+    if (!*off || !*idx) return -1;
+    int32_t pos = 0;
+    (*off)[0] = 0;
+    for (int k = 0; k < n; ++k) {
+        SEXP v = VECTOR_ELT(groups, k);
+        const int *p = INTEGER(v);
+        for (int i = 0; i < Rf_length(v); ++i) (*idx)[pos++] = p[i] - 1;
+        (*off)[k + 1] = pos;
+    }
+    return n;
+}
+
+/* as.integer(gene_order$chr) (rows pre-sorted by chr) -> contiguous ranges */
+static int chr_to_ranges(SEXP chr_codes, int32_t **start, int32_t **len) {
+    int G = Rf_length(chr_codes);
+    const int *c = INTEGER(chr_codes);
+    int K = 0;
+    for (int g = 0; g < G; ++g)
+        if (g == 0 || c[g] != c[g - 1]) ++K;
+    *start = (int32_t *)malloc(sizeof(int32_t) * (size_t)(K > 0 ? K : 1));
+    *len = (int32_t *)malloc(sizeof(int32_t) * (size_t)(K > 0 ? K : 1));
+    if (!*start || !*len) return -1;
+    int k = -1;
+    for (int g = 0; g < G; ++g) {
+        if (g == 0 || c[g] != c[g - 1]) {
+            ++k;
+            (*start)[k] = g;
+            (*len)[k] = 0;
+        }
+        (*len)[k] += 1;
+    }
+    return K;
+}
+
+static void fail_if(int rc) {
+    if (rc != 0) Rf_error("infercnv_b200: %s (status %d)", icnv_last_error(), rc);
+}
+
+/* subtract_ref_expr_from_obs: .get_normal_gene_mean_bounds + .subtract_expr (ops.R:1678-1786) */
+SEXP icnvR_subtract_ref(SEXP expr, SEXP ref_groups, SEXP inv_log, SEXP use_bounds) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int32_t *off = NULL, *idx = NULL;
+    int n_grp = list_to_csr(ref_groups, &off, &idx);
+    double *means = (double *)malloc(sizeof(double) * (size_t)(G * (n_grp > 0 ? n_grp : 1)));
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = (n_grp < 0 || !means) ? ICNV_E_NOMEM
+                                   : icnv_ref_means_f64(REAL(expr), G, C, off, idx, n_grp, Rf_asLogical(inv_log), means);
+    if (rc == 0) rc = icnv_subtract_ref_f64(REAL(expr), REAL(ans), G, C, means, n_grp, Rf_asLogical(use_bounds));
+    free(off); free(idx); free(means);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* smooth_by_chromosome (ops.R:2406-2434) */
+SEXP icnvR_smooth(SEXP expr, SEXP chr_codes, SEXP window_length) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int32_t *cs = NULL, *cl = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = K < 0 ? ICNV_E_NOMEM : icnv_smooth_f64(REAL(expr), REAL(ans), G, C, cs, cl, K, Rf_asInteger(window_length));
+    free(cs); free(cl);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* center_cell_expr_across_chromosome (ops.R:2074-2109) */
+SEXP icnvR_center(SEXP expr, SEXP use_median) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = icnv_center_f64(REAL(expr), REAL(ans), G, C, Rf_asLogical(use_median));
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* fused run() steps 4, 8-12, 14 */
+SEXP icnvR_smooth_block(SEXP expr, SEXP chr_codes, SEXP ref_groups, SEXP apply_log, SEXP threshold, SEXP window_length,
+                        SEXP use_bounds) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    int n_grp = list_to_csr(ref_groups, &off, &idx);
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = (K < 0 || n_grp < 0) ? ICNV_E_NOMEM
+                                  : icnv_smooth_block_f64(REAL(expr), REAL(ans), G, C, cs, cl, K, off, idx, n_grp,
+                                                          Rf_asLogical(apply_log), Rf_asReal(threshold),
+                                                          Rf_asInteger(window_length), Rf_asLogical(use_bounds));
+    free(cs); free(cl); free(off); free(idx);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* predict_CNV_via_HMM_on_* / i3HMM_predict_* (HMM.R:284-567, i3HMM.R:180-389): groups = NULL -> per cell */
+SEXP icnvR_viterbi(SEXP expr, SEXP chr_codes, SEXP groups, SEXP Pi, SEXP delta, SEXP mean, SEXP sd) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int m = Rf_length(delta);
+    int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    int n_grp = Rf_isNull(groups) ? 0 : list_to_csr(groups, &off, &idx);
+    int32_t *st = (int32_t *)malloc(sizeof(int32_t) * (size_t)(G * C));
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C)); /* the reference keeps states as doubles (HMM.R:320) */
+    int rc = (K < 0 || n_grp < 0 || !st) ? ICNV_E_NOMEM
+                                         : icnv_viterbi_f64(REAL(expr), G, C, cs, cl, K, off, idx, n_grp, m, REAL(Pi),
+                                                            REAL(delta), REAL(mean), REAL(sd), st, NULL);
+    if (rc == 0) {
+        double *out = REAL(ans);
+        for (int64_t i = 0; i < G * C; ++i) out[i] = (double)st[i];
+    }
+    free(cs); free(cl); free(off); free(idx); free(st);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* apply_median_filtering (noise_reduction.R:43-89) */
+SEXP icnvR_median_filter(SEXP expr, SEXP chr_codes, SEXP index_lists, SEXP window_size) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    int n_grp = list_to_csr(index_lists, &off, &idx);
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = (K < 0 || n_grp < 0) ? ICNV_E_NOMEM
+                                  : icnv_median_filter_f64(REAL(expr), REAL(ans), G, C, cs, cl, K, off, idx, n_grp,
+                                                           Rf_asInteger(window_size));
+    free(cs); free(cl); free(off); free(idx);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* .i3HMM_get_sd_trend_by_num_cells_fit: mu, sigma over the listed cells (i3HMM.R:17-30) */
+SEXP icnvR_mean_sd(SEXP expr, SEXP cells) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int n = Rf_length(cells);
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    double mu = 0, sg = 0;
+    int rc = ICNV_E_NOMEM;
+    if (idx) {
+        for (int i = 0; i < n; ++i) idx[i] = INTEGER(cells)[i] - 1;
+        rc = icnv_mean_sd_f64(REAL(expr), G, C, idx, n, &mu, &sg);
+    }
+    free(idx);
+    fail_if(rc);
+    SEXP ans = PROTECT(Rf_allocVector(REALSXP, 2));
+    REAL(ans)[0] = mu;
+    REAL(ans)[1] = sg;
+    UNPROTECT(1);
+    return ans;
+}
+
+SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
+
+static const R_CallMethodDef call_methods[] = {
+    {"icnvR_subtract_ref", (DL_FUNC)&icnvR_subtract_ref, 4}, {"icnvR_smooth", (DL_FUNC)&icnvR_smooth, 3},
+    {"icnvR_center", (DL_FUNC)&icnvR_center, 2},             {"icnvR_smooth_block", (DL_FUNC)&icnvR_smooth_block, 7},
+    {"icnvR_viterbi", (DL_FUNC)&icnvR_viterbi, 7},           {"icnvR_median_filter", (DL_FUNC)&icnvR_median_filter, 4},
+    {"icnvR_mean_sd", (DL_FUNC)&icnvR_mean_sd, 2},           {"icnvR_available", (DL_FUNC)&icnvR_available, 0},
+    {NULL, NULL, 0}};
+
+void R_init_infercnvb200_shim(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
+
+void R_unload_infercnvb200_shim(DllInfo *dll) {
+    (void)dll;
+    icnv_shutdown();
+}

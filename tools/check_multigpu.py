@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""torchrun --nproc-per-node N tools/check_multigpu.py : the sharded smooth block + HMM must be
+BITWISE equal to the single-GPU result (rank 0 recomputes the whole run alone and compares)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from infercnv_b200 import dist as shard  # noqa: E402
+from infercnv_b200.device import Engine  # noqa: E402
+from infercnv_b200.ops import CNV_LEVELS, get_HMM  # noqa: E402
+
+rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+eng = Engine(local)
+G, C_total = 10000, 1500 * world + 37
+cs, cl = bench.chr_layout(G)
+refs = bench.ref_groups_global(C_total)
+Pi, delta, _, _ = get_HMM({k: {"mean": m, "sd": s} for k, m, s in zip(CNV_LEVELS, bench.I6_MEAN, bench.I6_SD)}, 1e-6)
+plan = shard.plan_shards(C_total, refs, world)[rank]
+X = eng.synth(G, cs, cl, plan.local_cells, C_total, bench.SEED)
+Y, f = eng.smooth_block(X, cs, cl, plan.local_ref_groups(), plan.ref_sizes, plan.max_chunks)
+S, f2 = eng.viterbi(Y, cs, cl, Pi, delta, bench.I6_MEAN, bench.I6_SD)
+torch.cuda.synchronize()
+assert int(f.item()) == 0 and int(f2.item()) == 0
+# gather every rank's rows on rank 0 (variable sizes -> pad)
+n_local = torch.tensor([X.shape[0]], device=X.device)
+sizes = [torch.zeros_like(n_local) for _ in range(world)]
+dist.all_gather(sizes, n_local)
+nmax = int(max(s.item() for s in sizes))
+Yp = torch.zeros((nmax, G), dtype=torch.float64, device=X.device); Yp[: X.shape[0]] = Y
+Sp = torch.zeros((nmax, G), dtype=torch.uint8, device=X.device); Sp[: X.shape[0]] = S
+Ys = [torch.zeros_like(Yp) for _ in range(world)]
+Ss = [torch.zeros_like(Sp) for _ in range(world)]
+dist.all_gather(Ys, Yp)
+dist.all_gather(Ss, Sp)
+ok = True
+if rank == 0:
+    plans = shard.plan_shards(C_total, refs, world)
+    p1 = shard.plan_shards(C_total, refs, 1)[0]
+    X1 = eng.synth(G, cs, cl, p1.local_cells, C_total, bench.SEED)
+    Y1, _ = eng.smooth_block(X1, cs, cl, p1.local_ref_groups(), p1.ref_sizes, [(len(g) + 31) // 32 for g in refs])
+    S1, _ = eng.viterbi(Y1, cs, cl, Pi, delta, bench.I6_MEAN, bench.I6_SD)
+    torch.cuda.synchronize()
+    pos1 = {int(c): i for i, c in enumerate(p1.local_cells)}
+    bad_y = bad_s = 0
+    for r, p in enumerate(plans):
+        idx = torch.tensor([pos1[int(c)] for c in p.local_cells], device=X.device)
+        bad_y += int((Ys[r][: len(idx)] != Y1[idx]).sum().item())
+        bad_s += int((Ss[r][: len(idx)] != S1[idx]).sum().item())
+    ok = bad_y == 0 and bad_s == 0
+    print(f"[check_multigpu] world={world} cells={C_total}: smoothed values differing from 1-GPU run: {bad_y}; "
+          f"states differing: {bad_s}  -> {'BITWISE EQUAL' if ok else 'MISMATCH'}")
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
