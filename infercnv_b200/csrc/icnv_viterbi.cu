@@ -341,10 +341,18 @@ __device__ __noinline__ double emission_far(double x, double mean, double sd) {
 template <int M>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
-    double *tab = sm;                                            // [5][ICNV_EMIS_N]
+    // emission table re-laid as [interval] -> {c0,c1}, {c2,c3}, c4: two 16-byte and one 8-byte load per state
+    constexpr int NTAB = ICNV_EMIS_N + 1;                        // even count keeps the double2 arrays aligned
+    double2 *tab01 = reinterpret_cast<double2 *>(sm);
+    double2 *tab23 = tab01 + NTAB;
+    double *tab4 = reinterpret_cast<double *>(tab23 + NTAB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *tiles = sm + 5 * ICNV_EMIS_N + warp * (2 * 32 * TS);  // two staged x tiles per warp
-    for (int i = threadIdx.x; i < 5 * ICNV_EMIS_N; i += blockDim.x) tab[i] = p.table[i];
+    double *tiles = tab4 + NTAB + warp * (2 * 32 * TS);          // two staged x tiles per warp
+    for (int i = threadIdx.x; i < ICNV_EMIS_N; i += blockDim.x) {
+        tab01[i] = make_double2(p.table[i], p.table[ICNV_EMIS_N + i]);
+        tab23[i] = make_double2(p.table[2 * ICNV_EMIS_N + i], p.table[3 * ICNV_EMIS_N + i]);
+        tab4[i] = p.table[4 * ICNV_EMIS_N + i];
+    }
     __syncthreads();
 
     const int64_t warp_global = (int64_t)blockIdx.x * FAST_WARPS + warp;
@@ -426,11 +434,12 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
                     if (zs < (double)(ICNV_EMIS_N - 1)) {
                         const double m = zs + MAGIC;
                         const double u = zs - (m - MAGIC);
-                        const double *t = tab + __double2loint(m);
-                        v = fma(u, t[4 * ICNV_EMIS_N], t[3 * ICNV_EMIS_N]);
-                        v = fma(u, v, t[2 * ICNV_EMIS_N]);
-                        v = fma(u, v, t[1 * ICNV_EMIS_N]);
-                        v = fma(u, v, t[0]);
+                        const int idx = __double2loint(m);
+                        const double2 c01 = tab01[idx], c23 = tab23[idx];
+                        v = fma(u, tab4[idx], c23.y);
+                        v = fma(u, v, c23.x);
+                        v = fma(u, v, c01.y);
+                        v = fma(u, v, c01.x);
                     } else {
                         v = emission_far(x, p.mean[k], sd);
                     }
@@ -779,7 +788,7 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
 
     auto fkern = (m == 6) ? viterbi_fast_kernel<6> : viterbi_fast_kernel<3>;
     auto lkern = (m == 6) ? viterbi_list_kernel<6> : viterbi_list_kernel<3>;
-    const size_t smem = sizeof(double) * (5 * ICNV_EMIS_N + FAST_WARPS * 2 * 32 * TS);
+    const size_t smem = sizeof(double) * (5 * (ICNV_EMIS_N + 1) + FAST_WARPS * 2 * 32 * TS);
     ICNV_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fkern, FAST_WARPS * 32, smem));

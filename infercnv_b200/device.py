@@ -34,6 +34,7 @@ class Engine:
         _lib.check(self.lib.icnv_init(self.device))
         self.tdev = torch.device("cuda", self.device)
         self.timing = None   # when set to a list, smooth_block appends (name, start_event, end_event)
+        self.collective = True   # False: never enter a collective even if a process group exists
 
     # ---- data ---------------------------------------------------------------------------------------
     def synth(self, G, chr_start, chr_len, cells_global, C_total, seed) -> torch.Tensor:
@@ -123,7 +124,8 @@ class Engine:
             rows = []
             for k in range(n_grp):
                 part = self.group_partial_sums(src, lists[k], log)
-                part = shard.allgather_partials(part, max_chunks[k])
+                if self.collective:
+                    part = shard.allgather_partials(part, max_chunks[k])
                 rows.append(self.combine_partials(part, ref_sizes[k]))
             return torch.stack(rows)
 

@@ -44,6 +44,7 @@ if rank == 0:
     plans = shard.plan_shards(C_total, refs, world)
     p1 = shard.plan_shards(C_total, refs, 1)[0]
     X1 = eng.synth(G, cs, cl, p1.local_cells, C_total, bench.SEED)
+    eng.collective = False   # rank 0 alone: the other ranks are not in this computation
     Y1, _ = eng.smooth_block(X1, cs, cl, p1.local_ref_groups(), p1.ref_sizes, [(len(g) + 31) // 32 for g in refs])
     S1, _ = eng.viterbi(Y1, cs, cl, Pi, delta, bench.I6_MEAN, bench.I6_SD)
     torch.cuda.synchronize()
