@@ -5,11 +5,8 @@
 // as in the reference (noise_reduction.R:102-106: half_window + 1).  Even-count windows average
 // the two middle values (median.default).  Reads the un-filtered input throughout.
 //
-// One thread per output element.  A CTA covers a tile of TI consecutive genes x TJ consecutive
-// list positions; lanes run along genes, so each (di, dj) tap of the window is one coalesced
-// 128-byte read per 16 genes and neighbouring taps hit L1/L2.  The up-to (2r+1)^2 window values of
-// each thread are staged in a thread-private shared-memory column ([tap][thread], conflict free)
-// and the middle order statistics come from an in-place k-th smallest selection (Wirth/Hoare).
+// One thread per output element; see median_filter_kernel for the tile / halo / index-array layout.
+// The middle order statistics come from an in-place k-th smallest selection (Wirth/Hoare).
 #include <cfloat>
 #include <cmath>
 #include <vector>
@@ -36,56 +33,80 @@ struct MfParams {
     int *err_flag;
 };
 
-template <int NT, int TI>
-__global__ void __launch_bounds__(NT) median_filter_kernel(const MfParams p) {
-    extern __shared__ __align__(16) double win[];  // [tap][NT]
+// One CTA = a tile of TI genes x TJ list positions (TI*TJ threads, one output each).  The tile's halo
+// ((TI+2r) x (TJ+2r) values, clamped to the chromosome / index-list block) is loaded ONCE into shared
+// memory, coalesced along genes; every thread then selects its median over a private array of 16-bit
+// indices into that shared halo - nothing but indices ever moves.  12 KB of shared memory per 64-thread
+// CTA for the default window (against 83 KB of private value copies before) keeps ~36 warps per SM busy
+// on what is a chain of dependent shared-memory reads.
+constexpr int MF_TI = 8, MF_TJ = 8, MF_NT = MF_TI * MF_TJ;
+
+__global__ void __launch_bounds__(MF_NT) median_filter_kernel(const MfParams p) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    const int r = p.r;
+    const int HR = MF_TI + 2 * r, HC = MF_TJ + 2 * r;       // halo rows (genes, fast) x cols (cells)
+    const int W = (2 * r + 1) * (2 * r + 1);
+    double *halo = reinterpret_cast<double *>(mf_smem);
+    unsigned short *idx_all = reinterpret_cast<unsigned short *>(halo + HR * HC);
     const MfTile gt = p.gene_tiles[blockIdx.y];
     const MfTile ct = p.cell_tiles[blockIdx.x];
-    const int ti = threadIdx.x % TI, tj = threadIdx.x / TI;
-    if (ti >= gt.len || tj >= ct.len) return;
-    const int i = gt.start + ti, j = ct.start + tj;  // gene row, position in the concatenated list
-    const int r = p.r;
-    const int xa = max(gt.lo, i - r), xb = min(gt.hi - 1, i + r);
-    const int ya = max(ct.lo, j - r), yb = min(ct.hi - 1, j + r);
-    double *a = win + threadIdx.x;
-    int n = 0;
+    const int hi0 = gt.start - r, hj0 = ct.start - r;
     bool bad = false;
-    for (int jj = ya; jj <= yb; ++jj) {
-        const double *col = p.X + p.G * (int64_t)p.cells[jj];
-        for (int ii = xa; ii <= xb; ++ii) {
-            double v = col[ii];
+    // ---- halo: rows inside [gt.lo, gt.hi), list positions inside [ct.lo, ct.hi) -------------------------
+    for (int e = threadIdx.x; e < HR * HC; e += MF_NT) {
+        const int hr = e % HR, hc = e / HR;
+        const int ii = hi0 + hr, jj = hj0 + hc;
+        double v = 0.0;
+        if (ii >= gt.lo && ii < gt.hi && jj >= ct.lo && jj < ct.hi) {
+            v = p.X[ii + p.G * (int64_t)p.cells[jj]];
             bad |= !is_finite_d(v);
-            a[(int64_t)n * NT] = v;
-            ++n;
         }
+        halo[e] = v;
     }
-    // k-th smallest, k = (n-1)/2 (Wirth); afterwards a[0..k-1] <= a[k] <= a[k+1..n-1]
-    const int k = (n - 1) >> 1;
-    int l = 0, rr = n - 1;
-    while (l < rr) {
-        const double x = a[(int64_t)k * NT];
-        int u = l, w = rr;
-        do {
-            while (a[(int64_t)u * NT] < x) ++u;
-            while (x < a[(int64_t)w * NT]) --w;
-            if (u <= w) {
-                double t = a[(int64_t)u * NT];
-                a[(int64_t)u * NT] = a[(int64_t)w * NT];
-                a[(int64_t)w * NT] = t;
-                ++u;
-                --w;
+    __syncthreads();
+    const int ti = threadIdx.x % MF_TI, tj = threadIdx.x / MF_TI;
+    if (ti < gt.len && tj < ct.len) {
+        const int i = gt.start + ti, j = ct.start + tj;
+        const int xa = max(gt.lo, i - r), xb = min(gt.hi - 1, i + r);
+        const int ya = max(ct.lo, j - r), yb = min(ct.hi - 1, j + r);
+        unsigned short *a = idx_all + threadIdx.x;   // [tap][thread]
+        int n = 0;
+        for (int jj = ya; jj <= yb; ++jj)
+            for (int ii = xa; ii <= xb; ++ii) {
+                a[n * MF_NT] = (unsigned short)((jj - hj0) * HR + (ii - hi0));
+                ++n;
             }
-        } while (u <= w);
-        if (w < k) l = u;
-        if (k < u) rr = w;
+        (void)W;
+#define MF_VAL(q) halo[a[(q) * MF_NT]]
+        // k-th smallest, k = (n-1)/2 (Wirth); afterwards val[0..k-1] <= val[k] <= val[k+1..n-1]
+        const int k = (n - 1) >> 1;
+        int l = 0, rr = n - 1;
+        while (l < rr) {
+            const double x = MF_VAL(k);
+            int u = l, w = rr;
+            do {
+                while (MF_VAL(u) < x) ++u;
+                while (x < MF_VAL(w)) --w;
+                if (u <= w) {
+                    const unsigned short t = a[u * MF_NT];
+                    a[u * MF_NT] = a[w * MF_NT];
+                    a[w * MF_NT] = t;
+                    ++u;
+                    --w;
+                }
+            } while (u <= w);
+            if (w < k) l = u;
+            if (k < u) rr = w;
+        }
+        double med = MF_VAL(k);
+        if ((n & 1) == 0) {  // mean of the two middle values
+            double nxt = DBL_MAX;
+            for (int q = k + 1; q < n; ++q) nxt = fmin(nxt, MF_VAL(q));
+            med = (med + nxt) * 0.5;
+        }
+#undef MF_VAL
+        p.Y[i + p.G * (int64_t)p.cells[j]] = med;
     }
-    double med = a[(int64_t)k * NT];
-    if ((n & 1) == 0) {  // mean of the two middle values
-        double nxt = DBL_MAX;
-        for (int q = k + 1; q < n; ++q) nxt = fmin(nxt, a[(int64_t)q * NT]);
-        med = (med + nxt) * 0.5;
-    }
-    p.Y[i + p.G * (int64_t)p.cells[j]] = med;
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
 
@@ -111,16 +132,14 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
         return set_error(ICNV_E_BAD_ARG, "window_size must be an odd number >= 3 (noise_reduction.R:48-50)");
     const int r = (window_size + 1) / 2;
     const int W = (2 * r + 1) * (2 * r + 1);
-    int NT = 128;
-    if ((size_t)W * NT * sizeof(double) > (size_t)c.smem_optin) NT = 64;
-    if ((size_t)W * NT * sizeof(double) > (size_t)c.smem_optin)
-        return set_error(ICNV_E_UNSUPPORTED, "window_size %d needs %zu B of shared memory per CTA", window_size,
-                         (size_t)W * NT * sizeof(double));
+    const size_t smem = sizeof(double) * (size_t)(MF_TI + 2 * r) * (size_t)(MF_TJ + 2 * r) + sizeof(unsigned short) * (size_t)W * MF_NT;
+    if (smem > (size_t)c.smem_optin || (MF_TI + 2 * r) * (MF_TJ + 2 * r) > 65535)
+        return set_error(ICNV_E_UNSUPPORTED, "window_size %d needs %zu B of shared memory per CTA", window_size, smem);
     cudaStream_t st = pick_stream(stream);
     // cells in no list are copied through
     ICNV_CUDA(cudaMemcpyAsync(Y, X, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToDevice, st));
     if (n_grp == 0) return ICNV_OK;
-    const int TI = 16, TJ = NT / TI;
+    const int TI = MF_TI, TJ = MF_TJ;
     std::vector<MfTile> gt, ct;
     make_tiles(chr_start, chr_len, K, TI, gt);
     std::vector<int32_t> g_start(n_grp), g_len(n_grp);
@@ -145,15 +164,9 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     ICNV_CUDA(cudaStreamSynchronize(st));  // tile tables are stack-lifetime host buffers
     MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag};
-    size_t smem = (size_t)W * NT * sizeof(double);
     dim3 grid((unsigned)ct.size(), (unsigned)gt.size());
-    if (NT == 128) {
-        ICNV_CUDA(cudaFuncSetAttribute(median_filter_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        median_filter_kernel<128, 16><<<grid, 128, smem, st>>>(p);
-    } else {
-        ICNV_CUDA(cudaFuncSetAttribute(median_filter_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        median_filter_kernel<64, 16><<<grid, 64, smem, st>>>(p);
-    }
+    ICNV_CUDA(cudaFuncSetAttribute(median_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    median_filter_kernel<<<grid, MF_NT, smem, st>>>(p);
     ICNV_CHECK_LAUNCH("median_filter_kernel");
     return ICNV_OK;
 }
