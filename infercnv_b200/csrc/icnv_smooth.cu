@@ -478,12 +478,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   C  per-cell median by counting selection on register-resident values
 //   D  centred values back to shared memory, second reference subtraction + 2^x fused into the one
 //      coalesced write of the column
-template <int NT, int LMAX>
+// LANDING: the column arrives by bulk copy in a second shared-memory buffer one cell ahead (needs 2 x G x 8 B);
+// without it (G too large for two buffers) stage A reads global memory directly.
+template <int NT, int LMAX, bool LANDING>
 __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     double *raw = reinterpret_cast<double *>(smem_raw);      // landing buffer of the bulk copy
-    double *work = raw + p.s_elems;                          // x' -> Q -> centred output
+    double *work = LANDING ? raw + p.s_elems : raw;          // x' -> Q -> centred output
     double *invD = work + p.s_elems;                         // 1/D for one-sided truncation, h+1 entries
     double *ptot = invD + (p.h + 2);                         // per chromosome: P and Q at its last gene
     double *qtot = ptot + p.K;
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
     const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
     // bulk copies need 16-byte aligned source / size; otherwise the column is loaded by the threads
     auto tma_ok = [&](int64_t col) {
-        return ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
+        return LANDING && ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
     };
     __syncthreads();  // barrier initialised, invD ready
     if (tid == 0 && (int64_t)blockIdx.x < p.n_cols) {
@@ -537,11 +539,12 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
         if (tma_ok(col)) {
             mbar_wait(bar, parity);
             parity ^= 1u;
-        } else {
+        } else if (LANDING) {
             const double *__restrict__ src = p.X + p.ldx * col;
             for (int g = tid; g < G; g += NT) raw[g] = src[g];
             __syncthreads();
         }
+        const double *__restrict__ rawsrc = LANDING ? raw : (p.X + p.ldx * col);
         if (p.apply_log && p.lo1 && p.threshold > 0.0) {
             // the fused-block configuration: log2(x+1) -> dead-band subtract -> clamp, no per-element mode tests
             const double thr = p.threshold;
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int g = min(g0 + u * NT, G - 1);
-                    v[u] = raw[g];
+                    v[u] = rawsrc[g];
                     lo[u] = p.lo1[g];
                     hi[u] = p.hi1[g];
                 }
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
                 for (int u = 0; u < 4; ++u) {
                     const int g = g0 + u * NT;
                     const bool in = g < G;
-                    v[u] = in ? raw[g] : 0.0;
+                    v[u] = in ? rawsrc[g] : 0.0;
                     lo[u] = (in && p.lo1) ? p.lo1[g] : ((in && p.mid1) ? p.mid1[g] : 0.0);
                     hi[u] = (in && p.hi1) ? p.hi1[g] : 0.0;
                 }
@@ -891,10 +894,10 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     int s_elems = (int)((G + 1) & ~(int64_t)1);
     std::vector<Seg> segs;
     // (threads, genes per thread) variants, smallest first; ICNV_CELL_VARIANT=<index> pins one (tuning)
-    static const int variants[][2] = {{256, 12}, {512, 12}, {512, 24}, {1024, 12}};  // measured: 512x24 beats 1024x12
+    static const int variants[][2] = {{256, 12}, {512, 12}, {512, 24}, {1024, 12}, {1024, 24}};  // measured: 512x24 beats 1024x12
     int NT = 0, L = 0, lmax = 0, forced = -1;
     if (const char *e = getenv("ICNV_CELL_VARIANT")) forced = atoi(e);
-    for (int vi = 0; vi < 4; ++vi) {
+    for (int vi = 0; vi < 5; ++vi) {
         if (forced >= 0 && vi != forced) continue;
         L = build_segments(G, chr_start, chr_len, K, variants[vi][0], variants[vi][1], segs);
         if (L < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
@@ -906,11 +909,17 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     }
     if (NT == 0)
         return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes in K = %d chromosomes exceeds the kernel's %d genes",
-                         (long long)G, K, 512 * 23);
+                         (long long)G, K, 1024 * 23);
     const int NW = NT / 32;
     size_t red_bytes = (NT == 256) ? sizeof(Red<8>) : (NT == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
-    size_t smem = sizeof(double) * (2 * (size_t)s_elems + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW + CAND_MAX + 2) +
-                  red_bytes + 64 + 128 * 24 + 32;
+    const size_t smem_rest = sizeof(double) * ((size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW + CAND_MAX + 2) + red_bytes + 64 +
+                             128 * 24 + 32;
+    bool landing = true;
+    size_t smem = sizeof(double) * 2 * (size_t)s_elems + smem_rest;
+    if (smem > (size_t)c.smem_optin) {  // no room for the landing buffer: single-buffer mode
+        landing = false;
+        smem = sizeof(double) * (size_t)s_elems + smem_rest;
+    }
     if (smem > (size_t)c.smem_optin)
         return set_error(ICNV_E_UNSUPPORTED, "G = %lld needs %zu B shared memory per CTA, device allows %d", (long long)G,
                          smem, c.smem_optin);
@@ -941,10 +950,11 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         return ICNV_OK;
     };
     int lrc;
-    if (NT == 256) lrc = launch(cell_pipeline_kernel<256, 12>);
-    else if (NT == 512 && lmax == 12) lrc = launch(cell_pipeline_kernel<512, 12>);
-    else if (NT == 1024) lrc = launch(cell_pipeline_kernel<1024, 12>);
-    else lrc = launch(cell_pipeline_kernel<512, 24>);
+    if (NT == 256) lrc = landing ? launch(cell_pipeline_kernel<256, 12, true>) : launch(cell_pipeline_kernel<256, 12, false>);
+    else if (NT == 512 && lmax == 12) lrc = landing ? launch(cell_pipeline_kernel<512, 12, true>) : launch(cell_pipeline_kernel<512, 12, false>);
+    else if (NT == 512) lrc = landing ? launch(cell_pipeline_kernel<512, 24, true>) : launch(cell_pipeline_kernel<512, 24, false>);
+    else if (lmax == 12) lrc = launch(cell_pipeline_kernel<1024, 12, true>);
+    else lrc = landing ? launch(cell_pipeline_kernel<1024, 24, true>) : launch(cell_pipeline_kernel<1024, 24, false>);
     if (lrc) return lrc;
     ICNV_CHECK_LAUNCH("cell_pipeline_kernel");
     return ICNV_OK;

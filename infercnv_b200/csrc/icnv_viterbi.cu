@@ -339,7 +339,7 @@ __device__ __noinline__ double emission_far(double x, double mean, double sd) {
 }
 
 template <int M>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 3) viterbi_fast_kernel(const VitParams p) {
+__global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
     // emission table re-laid as [interval] -> {c0,c1}, {c2,c3}, c4: two 16-byte and one 8-byte load per state
     constexpr int NTAB = ICNV_EMIS_N + 1;                        // even count keeps the double2 arrays aligned

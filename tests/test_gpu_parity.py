@@ -57,7 +57,7 @@ def test_center_known_answers_and_median(api):
     want = np.tile(np.array([-3, -2, -1, 0, 1, 2, 3], dtype=float), (3, 1)).T
     np.testing.assert_allclose(api.center(m, "mean"), want, atol=1e-12)
     rng = np.random.default_rng(1)
-    for G in [1, 2, 3, 10, 11, 64, 65, 257, 1000, 2817, 4613, 5633, 8508, 10000, 11264]:
+    for G in [1, 2, 3, 10, 11, 64, 65, 257, 1000, 2817, 4613, 5633, 8508, 10000, 11264, 11777, 20000, 23552]:
         X = rng.normal(size=(G, 7))
         X[:, 1] = 0.25                      # all equal
         X[: G // 2, 2] = 1.0                # two big tie clusters
@@ -144,6 +144,29 @@ def test_oligodendroglioma_smooth_block_two_ref_groups(api, oligo):
     got2 = api.smooth_block(X, cs, cl, allobs, use_bounds=False, window_length=51, threshold=2.0)
     want2 = orc.smooth_block(X, cs, cl, allobs, use_bounds=False, window=51, threshold=2.0, nthreads=orc.max_threads())
     assert np.max(np.abs(got2 - want2) / np.abs(want2)) < 1e-11
+
+
+def test_smooth_block_20k_genes_single_buffer_variant(api):
+    """config c5's gene count: two shared-memory buffers no longer fit, the kernel runs its
+    single-buffer / 1024-thread variant."""
+    from infercnv_b200._lib import InfercnvB200Error
+    rng = np.random.default_rng(8)
+    t = np.array([852, 615, 535, 288, 420, 453, 458, 297, 349, 363, 514, 472, 162, 301, 274, 397, 546, 126, 545, 239,
+                  90, 212], dtype=float)
+    G, C = 20000, 48
+    lens = np.floor(t * G / t.sum()).astype(int)
+    lens[0] += G - lens.sum()
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    counts = rng.poisson(rng.lognormal(0.5, 1.0, size=(G, 1)) * rng.lognormal(0, 0.2, size=(1, C))).astype(np.float64)
+    refs = [np.arange(0, 6), np.arange(6, 10)]
+    got = api.smooth_block(counts, cs, lens, refs)
+    want = orc.smooth_block(counts, cs, lens, refs, nthreads=orc.max_threads())
+    rel = np.max(np.abs(got - want) / np.abs(want))
+    print(f"\n[20000 genes] smooth block max rel err vs oracle: {rel:.3e}")
+    assert rel < 1e-10
+    with pytest.raises(InfercnvB200Error) as e:        # beyond 1024 x 23 genes: refused, the R wrapper falls back
+        api.center(np.ones((24000, 2)))
+    assert e.value.code == -4
 
 
 # ---- HMM ------------------------------------------------------------------------------------------------------
