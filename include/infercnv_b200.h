@@ -100,6 +100,13 @@ ICNV_API int icnv_smooth_f64(const double *X, double *Y, int64_t G, int64_t C, c
  * use_median != 0: subtract the per-cell median over all G genes; else the per-cell mean. */
 ICNV_API int icnv_center_f64(const double *X, double *Y, int64_t G, int64_t C, int use_median);
 
+/* Element-wise steps as stand-alone calls (inside icnv_smooth_block_f64 they are fused into the loads
+ * and stores): log2xplus1 (R/inferCNV_ops.R:2756-2769), invert_log2 (:2814-2826),
+ * apply_max_threshold_bounds (:2970-2983).  n = G*C elements, Y may alias X. */
+ICNV_API int icnv_log2xplus1_f64(const double *X, double *Y, int64_t n);
+ICNV_API int icnv_invert_log2_f64(const double *X, double *Y, int64_t n);
+ICNV_API int icnv_apply_max_threshold_bounds_f64(const double *X, double *Y, int64_t n, double threshold);
+
 /* Fused run() steps 4, 8, 9, 10, 11, 12, 14 (R/inferCNV_ops.R:614, 771, 817, 865, 911, 952, 1031):
  * [log2(x+1)] -> subtract ref (bounds) -> clamp +-threshold -> smooth(window) -> centre by
  * median -> subtract ref again -> 2^x.  X is the depth-normalised matrix (after step 3).

@@ -30,6 +30,9 @@ SIGNATURES = {
     "icnv_subtract_ref_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_int, c_int]),
     "icnv_smooth_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, c_int]),
     "icnv_center_f64": (c_int, [_P, _P, c_i64, c_i64, c_int]),
+    "icnv_log2xplus1_f64": (c_int, [_P, _P, c_i64]),
+    "icnv_invert_log2_f64": (c_int, [_P, _P, c_i64]),
+    "icnv_apply_max_threshold_bounds_f64": (c_int, [_P, _P, c_i64, ct.c_double]),
     "icnv_smooth_block_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, ct.c_double, c_int,
                                       c_int]),
     "icnv_smooth_hmm_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, ct.c_double, c_int, c_int,

@@ -109,6 +109,27 @@ def center(X, method="median") -> np.ndarray:
     return Y
 
 
+def log2xplus1(X) -> np.ndarray:
+    X = _f64(X)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_log2xplus1_f64(_p(X), _p(Y), X.size))
+    return Y
+
+
+def invert_log2(X) -> np.ndarray:
+    X = _f64(X)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_invert_log2_f64(_p(X), _p(Y), X.size))
+    return Y
+
+
+def apply_max_threshold_bounds(X, threshold) -> np.ndarray:
+    X = _f64(X)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_apply_max_threshold_bounds_f64(_p(X), _p(Y), X.size, float(threshold)))
+    return Y
+
+
 def smooth_block(X, chr_start, chr_len, ref_groups, apply_log=True, threshold=3.0, window_length=101,
                  use_bounds=True, out=None) -> np.ndarray:
     X = _f64(X)

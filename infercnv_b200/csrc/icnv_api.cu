@@ -17,6 +17,7 @@ int icnv_dev_scatter_group_states(const uint8_t *gs, int64_t G, int64_t C, const
                                   void *stream);
 int icnv_dev_mean_sd_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *out2,
                          void *stream);
+int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, int op, double param, int *err_flag, void *stream);
 }
 
 namespace icnv {
@@ -591,6 +592,28 @@ int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, con
     if (rc) return rc;
     ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
     return check_flag(d_flag, st);
+}
+
+static int host_elementwise(const double *X, double *Y, int64_t n, int op, double param) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || n <= 0) return set_error(ICNV_E_BAD_ARG, "element-wise step: bad argument");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, n, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)n);
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!dY || !d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    if ((rc = icnv_dev_elementwise_f64(dX, dY, n, op, param, d_flag, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    return check_flag(d_flag, st);
+}
+
+int icnv_log2xplus1_f64(const double *X, double *Y, int64_t n) { return host_elementwise(X, Y, n, 0, 0.0); }
+int icnv_invert_log2_f64(const double *X, double *Y, int64_t n) { return host_elementwise(X, Y, n, 1, 0.0); }
+int icnv_apply_max_threshold_bounds_f64(const double *X, double *Y, int64_t n, double threshold) {
+    if (!(threshold > 0.0)) return set_error(ICNV_E_BAD_ARG, "threshold must be positive");
+    return host_elementwise(X, Y, n, 2, threshold);
 }
 
 int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mu,

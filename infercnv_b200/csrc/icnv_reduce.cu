@@ -2,6 +2,7 @@
 // (.i3HMM_get_sd_trend_by_num_cells_fit, R/inferCNV_i3HMM.R:17-30: mu = mean(X[, cells]),
 // sigma = sd(X[, cells])).  Two passes (mean, then centred sum of squares) like R's var(); fixed
 // block -> element assignment and an ordered final combine make the result reproducible.
+#include <algorithm>
 #include <cmath>
 
 #include "icnv_common.cuh"
@@ -52,9 +53,39 @@ __global__ void moment_finish_kernel(const double *__restrict__ partial, int n_p
     }
 }
 
+// element-wise steps of run(): log2xplus1 (ops.R:2756-2769), invert_log2 (ops.R:2814-2826),
+// apply_max_threshold_bounds (ops.R:2970-2983).  Inside the fused block these ride on the loads / stores of
+// cell_pipeline_kernel; as stand-alone steps they are one streaming pass (16 B per element, HBM-bound).
+__global__ void __launch_bounds__(256) elementwise_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t n,
+                                                          int op, double param, int *err_flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) {
+        double v = X[i];
+        bad |= !is_finite_d(v);
+        if (op == 0) v = log2(v + 1.0);
+        else if (op == 1) v = exp2(v);
+        else v = fmin(fmax(v, -param), param);
+        Y[i] = v;
+    }
+    if (bad && err_flag) atomicExch(err_flag, 1);
+}
+
 }  // namespace icnv
 
 using namespace icnv;
+
+extern "C" int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, int op, double param, int *err_flag,
+                                        void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || !Y || n <= 0 || op < 0 || op > 2) return set_error(ICNV_E_BAD_ARG, "icnv_dev_elementwise_f64: bad argument");
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
+    elementwise_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, op, param, err_flag);
+    ICNV_CHECK_LAUNCH("elementwise_kernel");
+    return ICNV_OK;
+}
+
 
 extern "C" int icnv_dev_mean_sd_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *out2,
                                     void *stream) {

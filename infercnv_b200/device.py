@@ -35,6 +35,8 @@ class Engine:
         self.tdev = torch.device("cuda", self.device)
         self.timing = None   # when set to a list, smooth_block appends (name, start_event, end_event)
         self.collective = True   # False: never enter a collective even if a process group exists
+        self._plan_cache = {}
+        self._T = None
 
     # ---- data ---------------------------------------------------------------------------------------
     def synth(self, G, chr_start, chr_len, cells_global, C_total, seed) -> torch.Tensor:
@@ -117,7 +119,18 @@ class Engine:
             ref_sizes = [len(g) for g in ref_groups_local]
         if max_chunks is None:
             max_chunks = [(len(g) + shard.CHUNK - 1) // shard.CHUNK for g in ref_groups_local]
-        d_groups = [torch.from_numpy(g).to(self.tdev) for g in ref_groups_local]
+        key = (tuple(g.tobytes() for g in ref_groups_local), C)
+        cached = self._plan_cache.get(key)
+        if cached is None:       # device copies of the index lists are built once per partition, not per call
+            d_groups = [torch.from_numpy(g).to(self.tdev) for g in ref_groups_local]
+            t_lists, pos = [], 0
+            for g in ref_groups_local:
+                t_lists.append(torch.arange(pos, pos + len(g), dtype=torch.int32, device=self.tdev))
+                pos += len(g)
+            all_ref = torch.cat(d_groups) if pos else None
+            self._plan_cache.clear()
+            cached = self._plan_cache[key] = (d_groups, t_lists, all_ref)
+        d_groups, t_lists, all_ref = cached
         flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
 
         def group_means(src, lists, log):
@@ -132,15 +145,12 @@ class Engine:
         b1 = self.bounds(group_means(X, d_groups, apply_log))
         # pass 1: reference cells only, up to the median centring
         n_ref = int(sum(len(g) for g in ref_groups_local))
-        T = torch.empty((max(n_ref, 1), G), dtype=torch.float64, device=self.tdev)
+        if self._T is None or self._T.shape != (max(n_ref, 1), G):
+            self._T = torch.empty((max(n_ref, 1), G), dtype=torch.float64, device=self.tdev)
+        T = self._T
         if n_ref:
-            all_ref = torch.cat(d_groups)
             self.cell_pipeline(X, all_ref, T, chr_start, chr_len, apply_log, b1, threshold, window, 1, None, False,
                                use_bounds, flag)
-        t_lists, pos = [], 0
-        for g in ref_groups_local:
-            t_lists.append(torch.arange(pos, pos + len(g), dtype=torch.int32, device=self.tdev))
-            pos += len(g)
         b2 = self.bounds(group_means(T, t_lists, False))
         # pass 2: every local cell, one read and one write of the matrix
         if self.timing is not None:

@@ -69,6 +69,39 @@ def subtract_ref_expr_from_obs(infercnv_obj: Infercnv, inv_log: bool = False, us
     return obj
 
 
+def log2xplus1(infercnv_obj: Infercnv) -> Infercnv:
+    """R/inferCNV_ops.R:2756-2769."""
+    log.info("transforming log2xplus1()")
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.log2xplus1(obj.expr_data)
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = log2xplus1(obj.hspike)
+    return obj
+
+
+def invert_log2(infercnv_obj: Infercnv) -> Infercnv:
+    """R/inferCNV_ops.R:2814-2826."""
+    log.info("invert_log2(), computing 2^x")
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.invert_log2(obj.expr_data)
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = invert_log2(obj.hspike)
+    return obj
+
+
+def apply_max_threshold_bounds(infercnv_obj: Infercnv, threshold: float) -> Infercnv:
+    """R/inferCNV_ops.R:2970-2983."""
+    log.info("::process_data:setting max centered expr, threshold set to: +/-: %s", threshold)
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.apply_max_threshold_bounds(obj.expr_data, threshold)
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = apply_max_threshold_bounds(obj.hspike, threshold)
+    return obj
+
+
 def smooth_by_chromosome(infercnv_obj: Infercnv, window_length: int, smooth_ends: bool = True) -> Infercnv:
     """R/inferCNV_ops.R:2406-2434 (`smooth_ends` is accepted and ignored there too)."""
     obj = copy.copy(infercnv_obj)

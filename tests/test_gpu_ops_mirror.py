@@ -1,0 +1,92 @@
+"""The host-side mirror of the R interface (infercnv_b200/ops.py): the reference's own step sequence
+(run() steps 4, 8, 9, 10, 11, 12, 14 - R/inferCNV_ops.R:614-1031) driven function by function, as
+example/example.Rmd and run(up_to_step=...) do, against the reference's bundled result."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _obj(ex, with_hspike=False):
+    from infercnv_b200 import ops
+    X = orc.normalize_by_seq_depth(ex["counts"])           # step 3 (out of scope, test infrastructure)
+    o = ops.Infercnv(expr_data=X, gene_order_chr=ex["chr_codes"],
+                     reference_grouped_cell_indices={"normal": ex["ref_groups"][0]},
+                     observation_grouped_cell_indices={"tumor": ex["obs_groups"][0]},
+                     tumor_subclusters={"subclusters": {"tumor": {"tumor_s1": ex["subclusters"][0]},
+                                                        "normal": {"normal_s1": ex["subclusters"][1]}}})
+    if with_hspike:
+        rng = np.random.default_rng(0)
+        H = rng.poisson(3.0, size=(X.shape[0], 12)).astype(float)
+        o.hspike = ops.Infercnv(expr_data=H, gene_order_chr=ex["chr_codes"],
+                                reference_grouped_cell_indices={"simnormal": np.arange(0, 6)},
+                                observation_grouped_cell_indices={"simtumor": np.arange(6, 12)})
+    return o
+
+
+def test_stepwise_run_sequence_reproduces_the_reference_golden(example_object):
+    from infercnv_b200 import api, ops
+    api.init(0)
+    ex = example_object
+    o = _obj(ex, with_hspike=True)
+    o = ops.log2xplus1(o)                                               # step 4
+    o = ops.subtract_ref_expr_from_obs(o, inv_log=False, use_bounds=True)   # step 8
+    o = ops.apply_max_threshold_bounds(o, threshold=3)                  # step 9
+    o = ops.smooth_by_chromosome(o, window_length=101, smooth_ends=True)    # step 10
+    o = ops.center_cell_expr_across_chromosome(o, method="median")      # step 11
+    o = ops.subtract_ref_expr_from_obs(o, inv_log=False, use_bounds=True)   # step 12
+    o = ops.invert_log2(o)                                              # step 14
+    ref = np.concatenate(ex["ref_groups"])
+    final = orc.clear_noise_via_ref_mean_sd(o.expr_data, ref, 1.5)      # step 22 (denoise) - oracle, not product
+    rel = np.max(np.abs(final - ex["expr"]) / np.abs(ex["expr"]))
+    print(f"\n[ops mirror, stepwise] max rel err vs the reference's expr.data: {rel:.3e}")
+    assert rel < 1e-5 and rel < 1e-11
+    # fused block == stepwise (to rounding), on the main matrix and on the mirrored hspike
+    f = ops.smooth_block(_obj(ex, with_hspike=True))
+    assert np.max(np.abs(f.expr_data - o.expr_data) / np.abs(o.expr_data)) < 1e-12
+    assert o.hspike is not None and f.hspike is not None
+    assert np.max(np.abs(f.hspike.expr_data - o.hspike.expr_data) / np.abs(o.hspike.expr_data)) < 1e-12
+    # hspike mirroring really ran the same step on the spike matrix
+    want_h = orc.smooth_block(_obj(ex, with_hspike=True).hspike.expr_data, *orc.chr_ranges(ex["chr_codes"]),
+                              [np.arange(0, 6)])
+    assert np.max(np.abs(o.hspike.expr_data - want_h) / np.abs(want_h)) < 1e-11
+
+
+def test_hmm_drivers_and_median_filter_through_the_mirror(example_object, hmm_fixture):
+    from infercnv_b200 import ops
+    ex = example_object
+    o = ops.smooth_block(_obj(ex))
+    cnv_mean_sd = {k: {"mean": m, "sd": s} for k, m, s in zip(ops.CNV_LEVELS, hmm_fixture["mean"], hmm_fixture["sd"])}
+    cs, cl = orc.chr_ranges(ex["chr_codes"])
+    Pi, delta = orc.hmm_params(6)
+    cells = ops.predict_CNV_via_HMM_on_indiv_cells(o, cnv_mean_sd, t=1e-6)
+    want = orc.viterbi_matrix(o.expr_data, cs, cl, Pi, delta, hmm_fixture["mean"], hmm_fixture["sd"])
+    np.testing.assert_array_equal(cells.expr_data, want.astype(float))
+    # group modes: per-group sds from a log-log trend as .get_state_emission_params computes them (HMM.R:586-614)
+    fit = {k: (np.log(s), -0.5) for k, s in zip(ops.CNV_LEVELS, hmm_fixture["sd"])}
+    samples = ops.predict_CNV_via_HMM_on_whole_tumor_samples(o, True, cnv_mean_sd, fit, t=1e-6)
+    groups = [ex["obs_groups"][0], ex["ref_groups"][0]]
+    sds = np.concatenate([hmm_fixture["sd"] * len(g) ** -0.5 for g in groups])
+    want_g = orc.viterbi_matrix(o.expr_data, cs, cl, Pi, delta, hmm_fixture["mean"], sds, groups=groups)
+    np.testing.assert_array_equal(samples.expr_data, want_g.astype(float))
+    sub = ops.predict_CNV_via_HMM_on_tumor_subclusters(o, cnv_mean_sd, fit, t=1e-6)
+    sgroups = [ex["subclusters"][0], ex["subclusters"][1]]
+    want_s = orc.viterbi_matrix(o.expr_data, cs, cl, Pi, delta, hmm_fixture["mean"], sds, groups=sgroups)
+    np.testing.assert_array_equal(sub.expr_data, want_s.astype(float))
+    # i3 per cell with mu / sigma from the reference cells
+    i3 = ops.i3HMM_predict_CNV_via_HMM_on_indiv_cells(o, i3_p_val=0.05, t=1e-6, use_KS=False)
+    Pi3, d3, mean3, sd3 = orc.i3_hmm_params(o.expr_data, ex["ref_groups"][0])
+    want3 = orc.viterbi_matrix(o.expr_data, cs, cl, Pi3, d3, mean3, sd3)
+    np.testing.assert_array_equal(i3.expr_data, want3.astype(float))
+    assert set(np.unique(i3.expr_data)).issubset({1.0, 2.0, 3.0})
+    # proxy values (HMM.R:1191-1206)
+    proxy = ops.assign_HMM_states_to_proxy_expr_vals(cells)
+    assert set(np.unique(proxy.expr_data)).issubset({0.0, 0.5, 1.0, 1.5, 2.0, 3.0})
+    # exported apply_median_filtering: subclusters in hclust order for observations, whole groups for references
+    mf = ops.apply_median_filtering(o, window_size=7)
+    want_mf = orc.median_filter(o.expr_data, cs, cl, [ex["subclusters"][0], ex["ref_groups"][0]], 7)
+    np.testing.assert_allclose(mf.expr_data, want_mf, rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        ops.apply_median_filtering(o, window_size=4)
