@@ -63,6 +63,14 @@ def ref_groups_global(C_total: int):
     return [np.arange(0, a, dtype=np.int64), np.arange(a, b, dtype=np.int64)]
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -377,11 +385,14 @@ def main():
             # dominant kernel of the step: the fused per-cell pipeline over all cells (pass 2)
             "roofline": {"kernel": "cell_pipeline_kernel pass 2 (%.0f %% of the step)" % (100 * ms_pass2 / ms_step),
                          "bound": "hbm", "achieved": ach_p2, "peak": peak, "unit": "GB/s", "frac": ach_p2 / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": pass2_bytes,
+                         "traffic": ncu_traffic("cell_pipeline_pass2") if (C_local, G) == (10000, 10000) else None,
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": pass2_bytes,
                          "ms_per_launch": ms_pass2,
                          "note": "16 B per cell-gene (one FP64 read, one FP64 write); instruction-issue bound, see DESIGN.md"},
             "roofline_hmm": {"kernel": "viterbi_fast_kernel<6> + exact re-run list (%.0f %% of the step)" % (100 * ms_hmm / ms_step),
                              "bound": "hbm", "achieved": ach_hmm, "peak": peak, "unit": "GB/s", "frac": ach_hmm / peak,
+                             "traffic": ncu_traffic("viterbi_fast") if (C_local, G) == (10000, 10000) else None,
                              "algorithmic_bytes_per_launch": hmm_bytes, "ms_per_launch": ms_hmm,
                              "sequences_rerun_in_reference_order_arithmetic": reruns,
                              "sequences": int(C_local * len(cs)),
