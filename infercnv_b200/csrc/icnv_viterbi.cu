@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
 //  (1) emission.  log(e_k / sum_j e_j) = g(z_k) - log(sum_j e_j) with g(z) = -log(-log Q(z)).  The
 //      second term is the same for every state of a gene, so it shifts all path scores equally and
 //      no arg-max sees it: it is dropped.  g comes from a piecewise degree-4 table
-//      (icnv_emission_table.inc, |error| < 5e-13, checked against 50-digit arithmetic); z beyond the
+//      (icnv_emission_table.inc, |error| < 5e-13 checked against 50-digit arithmetic, + < 3e-14 for keeping
+//      the cubic / quartic coefficients in single precision); z beyond the
 //      table falls back to the nmath evaluation.
 //  (2) max_j(nu[j] + logPi[j,k]) uses the structure of .get_HMM's matrix (one diagonal value a,
 //      one off-diagonal value b, R/inferCNV_HMM.R:233-238): the winner is either "stay" (nu[k]+a)
@@ -341,17 +342,18 @@ __device__ __noinline__ double emission_far(double x, double mean, double sd) {
 template <int M>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
-    // emission table re-laid as [interval] -> {c0,c1}, {c2,c3}, c4: two 16-byte and one 8-byte load per state
+    // emission table re-laid as [interval] -> {c0, c1} and {c2, (float c3, float c4)}: two 16-byte loads per
+    // state, 32 B instead of 40 B of shared-memory traffic (the table reads are this kernel's tightest
+    // resource).  c3, c4 only weigh u^3, u^4 with |u| <= 1/2: single precision costs < 3e-14.
     constexpr int NTAB = ICNV_EMIS_N + 1;                        // even count keeps the double2 arrays aligned
     double2 *tab01 = reinterpret_cast<double2 *>(sm);
-    double2 *tab23 = tab01 + NTAB;
-    double *tab4 = reinterpret_cast<double *>(tab23 + NTAB);
+    double2 *tab2f = tab01 + NTAB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *tiles = tab4 + NTAB + warp * (2 * 32 * TS);          // two staged x tiles per warp
+    double *tiles = reinterpret_cast<double *>(tab2f + NTAB) + warp * (2 * 32 * TS);   // two staged x tiles per warp
     for (int i = threadIdx.x; i < ICNV_EMIS_N; i += blockDim.x) {
         tab01[i] = make_double2(p.table[i], p.table[ICNV_EMIS_N + i]);
-        tab23[i] = make_double2(p.table[2 * ICNV_EMIS_N + i], p.table[3 * ICNV_EMIS_N + i]);
-        tab4[i] = p.table[4 * ICNV_EMIS_N + i];
+        const float c3 = (float)p.table[3 * ICNV_EMIS_N + i], c4 = (float)p.table[4 * ICNV_EMIS_N + i];
+        tab2f[i] = make_double2(p.table[2 * ICNV_EMIS_N + i], __hiloint2double(__float_as_int(c4), __float_as_int(c3)));
     }
     __syncthreads();
 
@@ -435,9 +437,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
                         const double m = zs + MAGIC;
                         const double u = zs - (m - MAGIC);
                         const int idx = __double2loint(m);
-                        const double2 c01 = tab01[idx], c23 = tab23[idx];
-                        v = fma(u, tab4[idx], c23.y);
-                        v = fma(u, v, c23.x);
+                        const double2 c01 = tab01[idx], c2f = tab2f[idx];
+                        const float hi = fmaf((float)u, __int_as_float(__double2hiint(c2f.y)), __int_as_float(__double2loint(c2f.y)));
+                        v = fma(u, (double)hi, c2f.x);
                         v = fma(u, v, c01.y);
                         v = fma(u, v, c01.x);
                     } else {
@@ -788,7 +790,7 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
 
     auto fkern = (m == 6) ? viterbi_fast_kernel<6> : viterbi_fast_kernel<3>;
     auto lkern = (m == 6) ? viterbi_list_kernel<6> : viterbi_list_kernel<3>;
-    const size_t smem = sizeof(double) * (5 * (ICNV_EMIS_N + 1) + FAST_WARPS * 2 * 32 * TS);
+    const size_t smem = sizeof(double) * (4 * (ICNV_EMIS_N + 1) + FAST_WARPS * 2 * 32 * TS);
     ICNV_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fkern, FAST_WARPS * 32, smem));
