@@ -100,6 +100,15 @@ ICNV_API int icnv_smooth_f64(const double *X, double *Y, int64_t G, int64_t C, c
  * use_median != 0: subtract the per-cell median over all G genes; else the per-cell mean. */
 ICNV_API int icnv_center_f64(const double *X, double *Y, int64_t G, int64_t C, int use_median);
 
+/* The two steps either side of the path, so the reference's bundled example runs
+ * count.data -> expr.data on the GPU end to end:
+ * normalize_counts_by_seq_depth (R/inferCNV_ops.R:3064-3111; normalize_factor < 0 or NaN = median of colSums) and
+ * clear_noise_via_ref_mean_sd (R/inferCNV_ops.R:2302-2346, noise_logistic = FALSE). */
+ICNV_API int icnv_normalize_counts_by_seq_depth_f64(const double *X, double *Y, int64_t G, int64_t C,
+                                                    double normalize_factor);
+ICNV_API int icnv_clear_noise_via_ref_mean_sd_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *idx,
+                                                  int64_t n_idx, double sd_amplifier);
+
 /* Element-wise steps as stand-alone calls (inside icnv_smooth_block_f64 they are fused into the loads
  * and stores): log2xplus1 (R/inferCNV_ops.R:2756-2769), invert_log2 (:2814-2826),
  * apply_max_threshold_bounds (:2970-2983).  n = G*C elements, Y may alias X. */

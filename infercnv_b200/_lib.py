@@ -30,6 +30,8 @@ SIGNATURES = {
     "icnv_subtract_ref_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_int, c_int]),
     "icnv_smooth_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, c_int]),
     "icnv_center_f64": (c_int, [_P, _P, c_i64, c_i64, c_int]),
+    "icnv_normalize_counts_by_seq_depth_f64": (c_int, [_P, _P, c_i64, c_i64, ct.c_double]),
+    "icnv_clear_noise_via_ref_mean_sd_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_i64, ct.c_double]),
     "icnv_log2xplus1_f64": (c_int, [_P, _P, c_i64]),
     "icnv_invert_log2_f64": (c_int, [_P, _P, c_i64]),
     "icnv_apply_max_threshold_bounds_f64": (c_int, [_P, _P, c_i64, ct.c_double]),

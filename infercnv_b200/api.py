@@ -109,6 +109,24 @@ def center(X, method="median") -> np.ndarray:
     return Y
 
 
+def normalize_counts_by_seq_depth(X, normalize_factor=None) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    Y = np.empty_like(X, order="F")
+    nf = -1.0 if normalize_factor is None else float(normalize_factor)
+    _lib.check(_lib.load().icnv_normalize_counts_by_seq_depth_f64(_p(X), _p(Y), G, C, nf))
+    return Y
+
+
+def clear_noise_via_ref_mean_sd(X, cells, sd_amplifier=1.5) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    idx = _i32(cells)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_clear_noise_via_ref_mean_sd_f64(_p(X), _p(Y), G, C, _p(idx), len(idx), float(sd_amplifier)))
+    return Y
+
+
 def log2xplus1(X) -> np.ndarray:
     X = _f64(X)
     Y = np.empty_like(X, order="F")

@@ -18,6 +18,11 @@ int icnv_dev_scatter_group_states(const uint8_t *gs, int64_t G, int64_t C, const
 int icnv_dev_mean_sd_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *out2,
                          void *stream);
 int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, int op, double param, int *err_flag, void *stream);
+int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *sums, double *sds,
+                              void *stream);
+int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C, const double *sums, double factor,
+                               void *stream);
+int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream);
 }
 
 namespace icnv {
@@ -592,6 +597,67 @@ int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, con
     if (rc) return rc;
     ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
     return check_flag(d_flag, st);
+}
+
+/* normalize_counts_by_seq_depth, R/inferCNV_ops.R:3064-3111: x / colSums * normalize_factor; a negative or NaN
+ * factor means "median of the column sums" (the reference's NA default). */
+int icnv_normalize_counts_by_seq_depth_f64(const double *X, double *Y, int64_t G, int64_t C, double normalize_factor) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 1 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_normalize_counts_by_seq_depth_f64: bad argument");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    double *d_sums = (double *)scratch(SLOT_PARTIAL, sizeof(double) * (size_t)C);
+    if (!dY || !d_sums) return ICNV_E_NOMEM;
+    if ((rc = icnv_dev_column_stats_f64(dX, G, nullptr, C, d_sums, nullptr, st))) return rc;
+    if (!(normalize_factor >= 0.0)) {  // median of the C column sums: a C-vector, selected on the host
+        std::vector<double> cs((size_t)C);
+        ICNV_CUDA(cudaMemcpyAsync(cs.data(), d_sums, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+        ICNV_CUDA(cudaStreamSynchronize(st));
+        std::sort(cs.begin(), cs.end());
+        normalize_factor = (C & 1) ? cs[C / 2] : 0.5 * (cs[C / 2 - 1] + cs[C / 2]);
+    }
+    if (!std::isfinite(normalize_factor)) return set_error(ICNV_E_NONFINITE, "Error, normalize factor not estimated");
+    if ((rc = icnv_dev_scale_columns_f64(dX, dY, G, C, d_sums, normalize_factor, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+/* clear_noise_via_ref_mean_sd, R/inferCNV_ops.R:2302-2346 (noise_logistic = FALSE): mu = mean over all values of
+ * the listed cells, s = sd_amplifier * mean over those cells of the per-cell sd; values strictly inside
+ * (mu - s, mu + s) become mu.  idx = reference cells, or all observation cells when there are none. */
+int icnv_clear_noise_via_ref_mean_sd_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx,
+                                         double sd_amplifier) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || !idx || G <= 1 || C <= 0 || n_idx <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_clear_noise_via_ref_mean_sd_f64: bad argument");
+    for (int64_t i = 0; i < n_idx; ++i)
+        if (idx[i] < 0 || idx[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index out of range");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_idx);
+    double *d_stats = (double *)scratch(SLOT_MEANS, sizeof(double) * 2 * (size_t)n_idx);
+    if (!dY || !d_idx || !d_stats) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+    if ((rc = icnv_dev_column_stats_f64(dX, G, d_idx, n_idx, d_stats, d_stats + n_idx, st))) return rc;
+    std::vector<double> h(2 * (size_t)n_idx);
+    ICNV_CUDA(cudaMemcpyAsync(h.data(), d_stats, sizeof(double) * 2 * (size_t)n_idx, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    double tot = 0.0, sdsum = 0.0;   // n_idx-vectors: combined on the host in list order
+    for (int64_t i = 0; i < n_idx; ++i) {
+        tot += h[i];
+        sdsum += h[n_idx + i];
+    }
+    const double mu = tot / ((double)G * (double)n_idx);
+    const double s = (sdsum / (double)n_idx) * sd_amplifier;
+    if ((rc = icnv_dev_clear_noise_f64(dX, dY, G * C, mu - s, mu + s, mu, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
 }
 
 static int host_elementwise(const double *X, double *Y, int64_t n, int op, double param) {

@@ -72,9 +72,100 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const double *__restri
     if (bad && err_flag) atomicExch(err_flag, 1);
 }
 
+// ---- SURVEY section 8(f) "next" rows adjacent to the path: depth normalisation (step 3) and denoise (step 22) ----
+
+// one CTA per listed cell: out[i] = (sum, sd with n-1) of the cell's G values; fixed reduction tree
+__global__ void __launch_bounds__(256) column_stats_kernel(const double *__restrict__ X, int64_t G,
+                                                           const int32_t *__restrict__ cells, int64_t n_cells,
+                                                           double *__restrict__ sums, double *__restrict__ sds) {
+    __shared__ double sh[8];
+    __shared__ double bc;
+    for (int64_t ci = blockIdx.x; ci < n_cells; ci += gridDim.x) {
+        const double *col = X + G * (cells ? (int64_t)cells[ci] : ci);
+        double s = 0.0;
+        for (int64_t g = threadIdx.x; g < G; g += 256) s += col[g];
+        s = warp_sum_d(s);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += sh[w];
+            bc = t;
+        }
+        __syncthreads();
+        const double total = bc;
+        if (sums && threadIdx.x == 0) sums[ci] = total;
+        if (sds) {
+            const double mean = total / (double)G;
+            double q = 0.0;
+            for (int64_t g = threadIdx.x; g < G; g += 256) {
+                const double d = col[g] - mean;
+                q = fma(d, d, q);
+            }
+            q = warp_sum_d(q);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = q;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < 8; ++w) t += sh[w];
+                sds[ci] = sqrt(t / (double)(G - 1));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// .normalize_data_matrix_by_seq_depth (ops.R:3082-3111): (x / colSum) * normalize_factor
+__global__ void __launch_bounds__(256) scale_columns_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t G,
+                                                            int64_t C, const double *__restrict__ sums, double factor) {
+    for (int64_t c = blockIdx.x; c < C; c += gridDim.x) {
+        const double cs = sums[c];
+        for (int64_t g = threadIdx.x; g < G; g += 256) Y[g + G * c] = (X[g + G * c] / cs) * factor;
+    }
+}
+
+// clear_noise_via_ref_mean_sd (ops.R:2302-2346): values strictly inside (lo, hi) become mu
+__global__ void __launch_bounds__(256) clear_noise_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t n,
+                                                          double lo, double hi, double mu) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double v = X[i];
+        Y[i] = (v > lo && v < hi) ? mu : v;
+    }
+}
+
 }  // namespace icnv
 
 using namespace icnv;
+
+extern "C" int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *sums,
+                                         double *sds, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || G <= 1 || n_cells <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_column_stats_f64: bad argument");
+    int64_t blocks = std::min<int64_t>(n_cells, (int64_t)ctx().sm_count * 8);
+    column_stats_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, G, cells, n_cells, sums, sds);
+    ICNV_CHECK_LAUNCH("column_stats_kernel");
+    return ICNV_OK;
+}
+
+extern "C" int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C, const double *sums, double factor,
+                                          void *stream) {
+    ICNV_REQUIRE_READY();
+    int64_t blocks = std::min<int64_t>(C, (int64_t)ctx().sm_count * 8);
+    scale_columns_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, G, C, sums, factor);
+    ICNV_CHECK_LAUNCH("scale_columns_kernel");
+    return ICNV_OK;
+}
+
+extern "C" int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream) {
+    ICNV_REQUIRE_READY();
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
+    clear_noise_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, lo, hi, mu);
+    ICNV_CHECK_LAUNCH("clear_noise_kernel");
+    return ICNV_OK;
+}
 
 extern "C" int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, int op, double param, int *err_flag,
                                         void *stream) {

@@ -69,6 +69,27 @@ def subtract_ref_expr_from_obs(infercnv_obj: Infercnv, inv_log: bool = False, us
     return obj
 
 
+def normalize_counts_by_seq_depth(infercnv_obj: Infercnv, normalize_factor=None) -> Infercnv:
+    """R/inferCNV_ops.R:3064-3111 (no hspike mirroring in the reference: the spike is built after this step)."""
+    log.info("normalizing counts matrix by depth")
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.normalize_counts_by_seq_depth(obj.expr_data, normalize_factor)
+    return obj
+
+
+def clear_noise_via_ref_mean_sd(infercnv_obj: Infercnv, sd_amplifier: float = 1.5) -> Infercnv:
+    """R/inferCNV_ops.R:2302-2346 with noise_logistic=FALSE (hspike mirroring is commented out in the reference)."""
+    if has_reference_cells(infercnv_obj):
+        log.info("denoising using mean(normal) +- sd_amplifier * sd(normal) per gene per cell across all data")
+        cells = np.concatenate([np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()])
+    else:
+        log.info("-no reference cells specified... using mean and sd of all cells as proxy for denoising")
+        cells = np.concatenate([np.asarray(v) for v in infercnv_obj.observation_grouped_cell_indices.values()])
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.clear_noise_via_ref_mean_sd(obj.expr_data, cells, sd_amplifier)
+    return obj
+
+
 def log2xplus1(infercnv_obj: Infercnv) -> Infercnv:
     """R/inferCNV_ops.R:2756-2769."""
     log.info("transforming log2xplus1()")

@@ -171,11 +171,34 @@ b200_apply_median_filtering <- function(infercnv_obj, window_size=7, on_observat
     infercnv_obj
 }
 
+## normalize_counts_by_seq_depth, R/inferCNV_ops.R:3064
+b200_normalize_counts_by_seq_depth <- function(infercnv_obj, normalize_factor=NA) {
+    m <- infercnv_obj@expr.data
+    if (!.icnv_enabled() || !.icnv_ok(m)) return(.icnv_env$orig$normalize_counts_by_seq_depth(infercnv_obj, normalize_factor))
+    res <- tryCatch(.Call("icnvR_normalize", m, as.double(normalize_factor)), error = function(e) NULL)
+    if (is.null(res)) return(.icnv_env$orig$normalize_counts_by_seq_depth(infercnv_obj, normalize_factor))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    infercnv_obj
+}
+
+## clear_noise_via_ref_mean_sd, R/inferCNV_ops.R:2302 (noise_logistic=TRUE stays in R)
+b200_clear_noise_via_ref_mean_sd <- function(infercnv_obj, sd_amplifier=1.5, noise_logistic=FALSE) {
+    orig <- .icnv_env$orig$clear_noise_via_ref_mean_sd
+    m <- infercnv_obj@expr.data
+    if (!.icnv_enabled() || !.icnv_ok(m) || isTRUE(noise_logistic)) return(orig(infercnv_obj, sd_amplifier, noise_logistic))
+    cells <- if (length(infercnv_obj@reference_grouped_cell_indices) > 0)
+        unlist(infercnv_obj@reference_grouped_cell_indices) else unlist(infercnv_obj@observation_grouped_cell_indices)
+    res <- tryCatch(.Call("icnvR_clear_noise", m, as.integer(cells), as.double(sd_amplifier)), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, sd_amplifier, noise_logistic))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    infercnv_obj
+}
+
 infercnvb200_install <- function() {
     fns <- c("subtract_ref_expr_from_obs", "smooth_by_chromosome", "center_cell_expr_across_chromosome",
              "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
              "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
-             "apply_median_filtering")
+             "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd")
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")

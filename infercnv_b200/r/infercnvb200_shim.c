@@ -183,6 +183,36 @@ SEXP icnvR_mean_sd(SEXP expr, SEXP cells) {
     return ans;
 }
 
+/* normalize_counts_by_seq_depth (ops.R:3064-3111); normalize_factor NA -> median of colSums */
+SEXP icnvR_normalize(SEXP expr, SEXP normalize_factor) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    double nf = Rf_asReal(normalize_factor);
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = icnv_normalize_counts_by_seq_depth_f64(REAL(expr), REAL(ans), G, C, (nf == nf) ? nf : -1.0);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* clear_noise_via_ref_mean_sd (ops.R:2302-2346), noise_logistic = FALSE */
+SEXP icnvR_clear_noise(SEXP expr, SEXP cells, SEXP sd_amplifier) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int n = Rf_length(cells);
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = ICNV_E_NOMEM;
+    if (idx) {
+        for (int i = 0; i < n; ++i) idx[i] = INTEGER(cells)[i] - 1;
+        rc = icnv_clear_noise_via_ref_mean_sd_f64(REAL(expr), REAL(ans), G, C, idx, n, Rf_asReal(sd_amplifier));
+    }
+    free(idx);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
 SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
 
 static const R_CallMethodDef call_methods[] = {
@@ -190,6 +220,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_center", (DL_FUNC)&icnvR_center, 2},             {"icnvR_smooth_block", (DL_FUNC)&icnvR_smooth_block, 7},
     {"icnvR_viterbi", (DL_FUNC)&icnvR_viterbi, 7},           {"icnvR_median_filter", (DL_FUNC)&icnvR_median_filter, 4},
     {"icnvR_mean_sd", (DL_FUNC)&icnvR_mean_sd, 2},           {"icnvR_available", (DL_FUNC)&icnvR_available, 0},
+    {"icnvR_normalize", (DL_FUNC)&icnvR_normalize, 2},       {"icnvR_clear_noise", (DL_FUNC)&icnvR_clear_noise, 3},
     {NULL, NULL, 0}};
 
 void R_init_infercnvb200_shim(DllInfo *dll) {

@@ -54,6 +54,29 @@ def test_stepwise_run_sequence_reproduces_the_reference_golden(example_object):
     assert np.max(np.abs(o.hspike.expr_data - want_h) / np.abs(want_h)) < 1e-11
 
 
+def test_whole_bundled_example_runs_on_the_gpu_counts_to_expr(example_object):
+    """count.data -> expr.data of data/infercnv_object_example.rda with EVERY numeric step in the library
+    (steps 3, 4..14 fused, 22): nothing of the oracle on the path, only the reference's stored answer."""
+    from infercnv_b200 import ops
+    ex = example_object
+    o = ops.Infercnv(expr_data=ex["counts"], gene_order_chr=ex["chr_codes"],
+                     reference_grouped_cell_indices={"normal": ex["ref_groups"][0]},
+                     observation_grouped_cell_indices={"tumor": ex["obs_groups"][0]})
+    o = ops.normalize_counts_by_seq_depth(o)
+    o = ops.smooth_block(o, window_length=101, max_centered_threshold=3.0)
+    o = ops.clear_noise_via_ref_mean_sd(o, sd_amplifier=1.5)
+    rel = np.max(np.abs(o.expr_data - ex["expr"]) / np.abs(ex["expr"]))
+    print(f"\n[bundled example, all steps on the GPU] max rel err vs the reference's expr.data: {rel:.3e}")
+    assert rel < 1e-5 and rel < 1e-11
+    from infercnv_b200 import api
+    np.testing.assert_allclose(api.normalize_counts_by_seq_depth(ex["counts"]), orc.normalize_by_seq_depth(ex["counts"]),
+                               rtol=1e-13)
+    np.testing.assert_allclose(api.normalize_counts_by_seq_depth(ex["counts"], 1e4).sum(axis=0), 1e4, rtol=1e-12)
+    ref = np.concatenate(ex["ref_groups"])
+    np.testing.assert_allclose(api.clear_noise_via_ref_mean_sd(ex["expr"], ref, 2.0),
+                               orc.clear_noise_via_ref_mean_sd(ex["expr"], ref, 2.0), rtol=1e-12)
+
+
 def test_hmm_drivers_and_median_filter_through_the_mirror(example_object, hmm_fixture):
     from infercnv_b200 import ops
     ex = example_object
