@@ -404,33 +404,38 @@ __device__ double g_exp_tab[128];
 // v = 2^e * m, m in [1,2); c_i = 1/inv_c[i] is the table point next to m, r = m*inv_c - 1 (|r| < 2^-8),
 // log2 v = e + log2 c_i + log2(1 + r).  Error <= 3e-16 (relative, absolute below 1).  ~25 instructions
 // against ~90 for the library log2.
+__constant__ double k_logc[6] = {ICNV_LOGC0, ICNV_LOGC1, ICNV_LOGC2, ICNV_LOGC3, ICNV_LOGC4, ICNV_LOGC5};
+__constant__ double k_expc[5] = {ICNV_EXPC0, ICNV_EXPC1, ICNV_EXPC2, ICNV_EXPC3, ICNV_EXPC4};
+__device__ __noinline__ double slow_log2(double v) { return log2(v); }
+__device__ __noinline__ double slow_exp2(double x) { return exp2(x); }
+
 __device__ __forceinline__ double fast_log2_1p(double x, const double2 *__restrict__ ltab) {
     const double v = x + 1.0;
     const int hi = __double2hiint(v);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log2(v);  // zero, negative, denormal, inf, nan
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return slow_log2(v);  // zero, negative, denormal, inf, nan
     const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
     const double2 t = ltab[(hi >> 13) & 127];
     const double r = fma(m, t.x, -1.0);
-    double q = fma(r, ICNV_LOGC5, ICNV_LOGC4);
-    q = fma(r, q, ICNV_LOGC3);
-    q = fma(r, q, ICNV_LOGC2);
-    q = fma(r, q, ICNV_LOGC1);
-    q = fma(r, q, ICNV_LOGC0);
+    double q = fma(r, k_logc[5], k_logc[4]);   // constant-bank operands: no immediates to materialise
+    q = fma(r, q, k_logc[3]);
+    q = fma(r, q, k_logc[2]);
+    q = fma(r, q, k_logc[1]);
+    q = fma(r, q, k_logc[0]);
     return (double)e + fma(r, q, t.y);
 }
 
 // 2^x (invert_log2, ops.R:2818): x = k/128 + r, 2^x = 2^(k>>7) * T[k & 127] * 2^r, degree-5 polynomial.
 __device__ __forceinline__ double fast_exp2(double x, const double *__restrict__ etab) {
-    if (!(fabs(x) < 1000.0)) return exp2(x);
+    if (!(fabs(x) < 1000.0)) return slow_exp2(x);
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     const double kk = fma(x, 128.0, MAGIC);
     const int ki = __double2loint(kk);
     const double r = fma(kk - MAGIC, -0.0078125, x);  // exact
-    double q = fma(r, ICNV_EXPC4, ICNV_EXPC3);
-    q = fma(r, q, ICNV_EXPC2);
-    q = fma(r, q, ICNV_EXPC1);
-    q = fma(r, q, ICNV_EXPC0);
+    double q = fma(r, k_expc[4], k_expc[3]);
+    q = fma(r, q, k_expc[2]);
+    q = fma(r, q, k_expc[1]);
+    q = fma(r, q, k_expc[0]);
     const double t = etab[ki & 127];
     const double res = fma(t * r, q, t);
     return __hiloint2double(__double2hiint(res) + ((ki >> 7) << 20), __double2loint(res));
@@ -438,7 +443,8 @@ __device__ __forceinline__ double fast_exp2(double x, const double *__restrict__
 
 // dead-band subtraction, .subtract_expr (ops.R:1764-1769): strict inequalities
 __device__ __forceinline__ double sub_bounds(double x, double lo, double hi) {
-    return (x > hi) ? (x - hi) : ((x < lo) ? (x - lo) : 0.0);
+    // x - clamp(x, lo, hi): x-hi above the band, x-lo below it, exactly 0 inside (lo <= hi always)
+    return x - fmin(fmax(x, lo), hi);
 }
 
 // ---- mbarrier / bulk-copy (TMA) helpers: the next cell's column is fetched by the copy engine
@@ -484,7 +490,9 @@ template <int NT, int LMAX, bool LANDING>
 __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
-    double *raw = reinterpret_cast<double *>(smem_raw);      // landing buffer of the bulk copy
+    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);   // log2 / exp2 tables first: 16-byte aligned by construction
+    double *etab = reinterpret_cast<double *>(ltab + 128);
+    double *raw = etab + 128;                                // landing buffer of the bulk copy
     double *work = LANDING ? raw + p.s_elems : raw;          // x' -> Q -> centred output
     double *invD = work + p.s_elems;                         // 1/D for one-sided truncation, h+1 entries
     double *ptot = invD + (p.h + 2);                         // per chromosome: P and Q at its last gene
@@ -494,8 +502,6 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
     Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
     int *cand_n = reinterpret_cast<int *>(&red + 1);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(cand_n + 2);
-    double2 *ltab = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(bar + 2) + 15) & ~(uintptr_t)15);
-    double *etab = reinterpret_cast<double *>(ltab + 128);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)p.G;
