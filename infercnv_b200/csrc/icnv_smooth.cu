@@ -148,7 +148,8 @@ struct CellParams {
 
 constexpr int CAND_MAX = 64;   // candidates ranked directly at the end of the selection
 
-__device__ unsigned long long g_stats[4];  // [0] median rounds, [1] medians, [2] split exits, [3] gather exits
+__device__ unsigned long long g_stats[16];  // [0] median rounds, [1] medians, [2] split exits, [3] gather exits,
+                                            // [4..9] cycles spent by CTA 0 in: wait, A, B scans, B outputs, C median, D
 
 // ---- block-wide reductions with one __syncthreads each (double-buffered scratch) ----------------
 template <int NW>
@@ -778,6 +779,464 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
 
+
+// =================================================================================================
+// K2 v3: same pipeline, values never leave shared memory
+// =================================================================================================
+//
+// v2 above keeps every thread's smoothed values in a register array across the median, which forces all
+// per-gene loops to be fully unrolled with length predicates (~430 instructions per gene, 170 KB of code).
+// v3 ping-pongs between the two shared-memory buffers instead: the raw column lands in buffer `in`, the
+// element-wise steps write x' to `oth`, the prefix sums run in place there, the smoothed values go back to
+// `in`, and the next cell's bulk copy is issued into `oth` as soon as Q is no longer needed.  All per-gene
+// loops are short rolled loops over the thread's own slice; the median counts straight from shared memory.
+
+// median of the n values vals[a0 .. a0+len) of all threads (same selection as block_median)
+// median of the n values vals[a0 .. a0+len) of all threads (same selection as block_median).  s1 / s2 are this
+// thread's sum and sum of squares of its values (accumulated while they were produced): they only place the
+// first two pivots.  Min / max are not needed: the bracket starts at (-DBL_MAX, DBL_MAX].
+template <int NT>
+__device__ __forceinline__ double block_median_smem(const double *__restrict__ vals, int a0, int len, int n, double s1,
+                                                    double s2, Red<NT / 32> &red, int &phase, double *cand, int *cand_n) {
+    constexpr int NW = NT / 32;
+    const int kA = (n - 1) >> 1, kB = n >> 1;
+    const double *v0 = vals + a0;
+    if (threadIdx.x == 0) {
+        atomicAdd(&g_stats[1], 1ull);
+        *cand_n = 0;   // made visible by the reductions' barriers long before the gather
+    }
+    double S1, S2;
+    block_red2d<NW, 1>(red, phase, s1, s2, S1, S2);
+    const double mean = S1 / (double)n;
+    const double var = S2 / (double)n - mean * mean;
+    const double sd = var > 0.0 ? sqrt(var) : 0.0;
+    // invariant: #(x <= lo) <= kA and #(x <= hi) >= kB + 1
+    double lo = -DBL_MAX, hi = DBL_MAX;
+    int Flo = 0, Fhi = n;
+    // first bracket: mean +- 0.35 sd holds the median of anything roughly unimodal and has near-uniform density
+    // inside, which is what the interpolation rounds assume; a miss is repaired by the min / max pass below
+    double p1 = mean - 0.35 * sd, p2 = mean + 0.35 * sd;
+    bool force_bisect = false;
+    double a_res = 0.0, b_res = 0.0;
+    bool done = false;
+    for (int round = 0; round < 200 && !done; ++round) {
+        const int m = Fhi - Flo;
+        if (m <= CAND_MAX) break;
+        if (threadIdx.x == 0) atomicAdd(&g_stats[0], 1ull);
+        if (round > 0 && (lo == -DBL_MAX || hi == DBL_MAX)) {
+            // rare (zero variance, or a variance lost to cancellation): bound the bracket by the true extremes
+            double mn = DBL_MAX, mx = -DBL_MAX;
+            for (int t = 0; t < len; ++t) {
+                mn = fmin(mn, v0[t]);
+                mx = fmax(mx, v0[t]);
+            }
+            double MN, MX;
+            block_red2d<NW, 0>(red, phase, mn, mx, MN, MX);
+            if (!(MN < MX)) {   // all values equal
+                a_res = b_res = MN;
+                done = true;
+                break;
+            }
+            double below = double_of_key(key_of(MN) - 1ull);
+            if (!(below < MN)) below = double_of_key(key_of(MN) - 2ull);   // MN == +0.0: one key below is -0.0
+            lo = fmax(lo, below);
+            hi = fmin(hi, MX);
+        }
+        if (round > 0) {
+            if (force_bisect) {   // rare: interpolation failed to halve the bracket -> bisect in key space
+                const unsigned long long klo = key_of(lo), khi = key_of(hi);
+                if (khi - klo < 2ull) {   // no double strictly between: every candidate equals hi
+                    a_res = b_res = hi;
+                    done = true;
+                    break;
+                }
+                p1 = p2 = double_of_key(klo + ((khi - klo) >> 1));
+            } else {
+                // pivot placement only has to be identical in every thread, not accurate: cheap float math
+                const float mf = (float)m;
+                const float inv_m = __frcp_rn(mf);
+                const float f = ((float)(kA - Flo) + 0.5f * (float)(kB - kA) + 0.5f) * inv_m;
+                float wfrac = (3.0f * sqrtf(mf) + 8.0f) * inv_m;
+                wfrac = fminf(wfrac, 0.5f);
+                const double span = hi - lo;   // finite after the first round unless the data are degenerate
+                const double pc = lo + span * (double)f;
+                p1 = pc - span * (double)(0.5f * wfrac);
+                p2 = pc + span * (double)(0.5f * wfrac);
+            }
+        }
+        if (!(p1 > lo && p1 < hi) || !(p2 > lo && p2 < hi) || !(p1 <= p2)) {
+            // degenerate placement (infinite span, rounding onto a bound, all-equal data ...): key-space midpoint
+            const unsigned long long klo = key_of(lo), khi = key_of(hi);
+            if (khi - klo < 2ull) {
+                a_res = b_res = hi;
+                done = true;
+                break;
+            }
+            p1 = p2 = double_of_key(klo + ((khi - klo) >> 1));
+        }
+        int c1 = 0, c2 = 0;
+#pragma unroll 4
+        for (int t = 0; t < len; ++t) {
+            const double v = v0[t];
+            c1 += (v <= p1) ? 1 : 0;
+            c2 += (v <= p2) ? 1 : 0;
+        }
+        int C1, C2;
+        block_sum2i<NW>(red, phase, c1, c2, C1, C2);
+        double split = 0.0;
+        bool do_split = false;
+        if (C1 >= kB + 1) {
+            hi = p1;
+            Fhi = C1;
+        } else if (C1 > kA) {
+            split = p1;
+            do_split = true;
+        } else if (C2 >= kB + 1) {
+            lo = p1;
+            Flo = C1;
+            hi = p2;
+            Fhi = C2;
+        } else if (C2 > kA) {
+            split = p2;
+            do_split = true;
+        } else {
+            lo = p2;
+            Flo = C2;
+        }
+        if (do_split) {   // s_kA <= split < s_kB: neighbours of the split point
+            double below = -DBL_MAX, above = DBL_MAX;
+            for (int t = 0; t < len; ++t) {
+                const double v = v0[t];
+                if (v <= split) below = fmax(below, v);
+                else above = fmin(above, v);
+            }
+            block_red2d<NW, 2>(red, phase, below, above, a_res, b_res);
+            done = true;
+            break;
+        }
+        const int m_new = Fhi - Flo;
+        force_bisect = (2 * m_new > m) && !force_bisect;
+    }
+    if (done) {
+        if (threadIdx.x == 0) atomicAdd(&g_stats[2], 1ull);
+        return (a_res + b_res) * 0.5;
+    }
+    if (threadIdx.x == 0) atomicAdd(&g_stats[3], 1ull);
+    // ---- gather the <= CAND_MAX candidates in (lo, hi] and rank them --------------------------------
+    for (int t = 0; t < len; ++t) {
+        const double v = v0[t];
+        if (v > lo && v <= hi) {
+            const int slot = atomicAdd(cand_n, 1);
+            if (slot < CAND_MAX) cand[slot] = v;
+        }
+    }
+    __syncthreads();
+    int m = *cand_n;
+    if (m > CAND_MAX) m = CAND_MAX;   // cannot happen (m == Fhi - Flo); keeps the loop bounded
+    const int ra = kA - Flo, rb = kB - Flo;
+    {   // one warp per candidate: its 32 lanes compare it with all (<= 64) candidates, one redux gives the rank
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const double u1 = (lane < m) ? cand[lane] : INFINITY;
+        const double u2 = (lane + 32 < m) ? cand[lane + 32] : INFINITY;
+        for (int i = w; i < m; i += NW) {
+            const double v = cand[i];
+            int cnt = ((u1 < v) || (u1 == v && lane < i)) ? 1 : 0;
+            cnt += ((u2 < v) || (u2 == v && lane + 32 < i)) ? 1 : 0;
+            const int rank = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) {
+                if (rank == ra) cand[CAND_MAX] = v;
+                if (rank == rb) cand[CAND_MAX + 1] = v;
+            }
+        }
+    }
+    __syncthreads();
+    return (cand[CAND_MAX] + cand[CAND_MAX + 1]) * 0.5;   // cand is next touched a whole cell (many barriers) later
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = NT / 32;
+    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
+    double *etab = reinterpret_cast<double *>(ltab + 128);
+    double *buf0 = etab + 128;
+    double *buf1 = buf0 + p.s_elems;
+    double *invD = buf1 + p.s_elems;
+    double *ptot = invD + (p.h + 2);
+    double *qtot = ptot + p.K;
+    double *tails = qtot + p.K;                              // [2][NW]
+    double *cand = tails + 2 * NW;
+    Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
+    int *cand_n = reinterpret_cast<int *>(&red + 1);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cand_n + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int)p.G;
+    const int h = p.h;
+    const bool do_smooth = p.window >= 2;
+    int phase = 0;
+    unsigned parity = 0;
+    if (do_smooth) {
+        const double full = (double)(h + 1) * (double)(h + 1);
+        for (int r = tid; r <= h; r += NT) invD[r] = 1.0 / (full - 0.5 * (double)r * (double)(r + 1));
+    }
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < 128; i += NT) {
+        ltab[i] = make_double2(g_log_tab[i][0], g_log_tab[i][1]);
+        etab[i] = g_exp_tab[i];
+    }
+    const Seg seg = p.segs[tid];
+    const int len = seg.len, a0 = seg.start, cs = seg.cs, ce = seg.ce, n = ce - cs;
+    const int lane_first = max(seg.tfirst - (tid - lane), 0);
+    const int wfirst = seg.tfirst >> 5;
+    const double invD0 = do_smooth ? 1.0 / ((double)(h + 1) * (double)(h + 1)) : 1.0;
+    bool bad = false;
+    const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
+    auto tma_ok = [&](int64_t col) {
+        return ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
+    };
+    double *in = buf0, *oth = buf1;
+    long long tstamp = clock64();
+    unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    auto lap = [&](int slot) {   // stage timing by one thread of CTA 0 (diagnostic, see icnv_debug_stats)
+        if (tid == 0 && blockIdx.x == 0) {
+            const long long now = clock64();
+            tacc[slot] += (unsigned long long)(now - tstamp);
+            tstamp = now;
+        }
+    };
+    __syncthreads();
+    if (tid == 0 && (int64_t)blockIdx.x < p.n_cols) {
+        const int64_t col0 = p.cols ? (int64_t)p.cols[blockIdx.x] : (int64_t)blockIdx.x;
+        if (tma_ok(col0)) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, col_bytes);
+            bulk_g2s(in, p.X + p.ldx * col0, col_bytes, bar);
+        }
+    }
+
+    for (int64_t ci = blockIdx.x; ci < p.n_cols; ci += gridDim.x) {
+        const int64_t col = p.cols ? (int64_t)p.cols[ci] : ci;
+        double *__restrict__ dst = p.Y + p.ldy * ci;
+        // ---- A: raw column (in) -> x' (oth) -------------------------------------------------------------
+        if (tma_ok(col)) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            const double *__restrict__ src = p.X + p.ldx * col;
+            for (int g = tid; g < G; g += NT) in[g] = src[g];
+            __syncthreads();
+        }
+        lap(0);
+        if (p.apply_log && p.lo1 && p.threshold > 0.0) {
+            const double thr = p.threshold;
+            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+                double v[4], lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = min(g0 + u * NT, G - 1);
+                    v[u] = in[g];
+                    lo[u] = p.lo1[g];
+                    hi[u] = p.hi1[g];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    if (!is_finite_d(v[u])) bad = true;
+                    double x = fast_log2_1p(v[u], ltab);
+                    x = sub_bounds(x, lo[u], hi[u]);
+                    x = fmin(fmax(x, -thr), thr);
+                    if (g < G) oth[g] = x;
+                }
+            }
+        } else {
+            for (int g = tid; g < G; g += NT) {
+                double x = in[g];
+                if (!is_finite_d(x)) bad = true;
+                if (p.apply_log) x = fast_log2_1p(x, ltab);
+                if (p.lo1) x = sub_bounds(x, p.lo1[g], p.hi1[g]);
+                else if (p.mid1) x = x - p.mid1[g];
+                if (p.threshold > 0.0) x = fmin(fmax(x, -p.threshold), p.threshold);
+                oth[g] = x;
+            }
+        }
+        __syncthreads();   // `in` is free, x' complete in `oth`
+        lap(1);
+
+        // ---- B: pyramid smooth oth (x') -> in (smoothed) -------------------------------------------------
+        const double *xs = oth + a0;
+        double ys1 = 0.0, ys2 = 0.0;   // sum / sum of squares of this thread's outputs (first median pivots)
+        if (!do_smooth) {
+            for (int q = 0; q < len; ++q) {
+                const double out = xs[q];
+                in[a0 + q] = out;
+                ys1 += out;
+                ys2 = fma(out, out, ys2);
+            }
+        } else {
+            // pass 1: segment total of x
+            double tot = 0.0;
+#pragma unroll 4
+            for (int q = 0; q < len; ++q) tot += xs[q];
+            double inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane - d >= lane_first) inc += t;
+            }
+            double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane <= lane_first) exc = 0.0;
+            if (lane == 31) tails[warp] = inc;
+            __syncthreads();
+            double carry = 0.0;
+            for (int u = wfirst; u < warp; ++u) carry += tails[u];
+            const double offP = exc + carry;   // P just before this segment
+            // pass 2: segment total of P (P = prefix of x inside the chromosome)
+            double pr = offP, qsum = 0.0;
+#pragma unroll 4
+            for (int q = 0; q < len; ++q) {
+                pr += xs[q];
+                qsum += pr;
+            }
+            const double plast = pr;
+            inc = qsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane - d >= lane_first) inc += t;
+            }
+            exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane <= lane_first) exc = 0.0;
+            if (lane == 31) tails[NW + warp] = inc;
+            __syncthreads();
+            carry = 0.0;
+            for (int u = wfirst; u < warp; ++u) carry += tails[NW + u];
+            const double offQ = exc + carry;   // Q just before this segment
+            // pass 3: Q in place (each thread touches only its own slice)
+            pr = offP;
+            double qv = offQ;
+#pragma unroll 4
+            for (int q = 0; q < len; ++q) {
+                pr += xs[q];
+                qv += pr;
+                oth[a0 + q] = qv;
+            }
+            if (len > 0 && a0 + len == ce) {
+                ptot[seg.chr] = plast;
+                qtot[seg.chr] = qv;
+            }
+            __syncthreads();
+            lap(2);
+            // outputs
+            if (n >= 2) {
+                const double *Qc = oth + cs;
+                const double Pn = ptot[seg.chr], Qn = qtot[seg.chr];
+                auto Qt = [&](int j) -> double {
+                    if (j < 0) return 0.0;
+                    if (j <= n - 1) return Qc[j];
+                    return Qn + (double)(j - (n - 1)) * Pn;
+                };
+                int j = a0 - cs;
+#pragma unroll 2
+                for (int q = 0; q < len; ++q, ++j) {
+                    double out;
+                    if (j - h - 2 >= 0 && j + h <= n - 1) {   // window inside the chromosome
+                        const double qb = Qc[j - 1];
+                        out = ((Qc[j + h] - qb) - (qb - Qc[j - h - 2])) * invD0;
+                    } else {
+                        const double qa = Qt(j + h), qb = Qt(j - 1), qc = Qt(j - h - 2);
+                        const double N = (qa - qb) - (qb - qc);
+                        int rl = h - j;
+                        rl = rl > 0 ? rl : 0;
+                        int rr = h - (n - 1 - j);
+                        rr = rr > 0 ? rr : 0;
+                        if (rl == 0 || rr == 0) {
+                            out = N * invD[rl + rr];
+                        } else {
+                            const double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
+                                             0.5 * (double)rr * (double)(rr + 1);
+                            out = N / D;
+                        }
+                    }
+                    in[a0 + q] = out;
+                    ys1 += out;
+                    ys2 = fma(out, out, ys2);
+                }
+            } else {
+                // single-gene chromosome: left untouched (ops.R:2417); Q of a single element is the element
+                for (int q = 0; q < len; ++q) {
+                    const double out = oth[a0 + q];
+                    in[a0 + q] = out;
+                    ys1 += out;
+                    ys2 = fma(out, out, ys2);
+                }
+            }
+        }
+        __syncthreads();   // smoothed values complete in `in`; Q in `oth` no longer needed
+        lap(3);
+        if (tid == 0) {    // next cell's column lands in `oth` while the median and the epilogue run
+            const int64_t cn = ci + gridDim.x;
+            if (cn < p.n_cols) {
+                const int64_t coln = p.cols ? (int64_t)p.cols[cn] : cn;
+                if (tma_ok(coln)) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, col_bytes);
+                    bulk_g2s(oth, p.X + p.ldx * coln, col_bytes, bar);
+                }
+            }
+        }
+
+        // ---- C: per-cell centre --------------------------------------------------------------------------------
+        double centre = 0.0;
+        if (p.center == 1) {
+            centre = block_median_smem<NT>(in, a0, len, G, ys1, ys2, red, phase, cand, cand_n);
+        } else if (p.center == 2) {
+            double s1 = 0.0;
+            for (int q = 0; q < len; ++q) s1 += in[a0 + q];
+            double S1, dummy;
+            block_red2d<NW, 1>(red, phase, s1, 0.0, S1, dummy);
+            centre = S1 / (double)G;
+        }
+
+        lap(4);
+        // ---- D: centre, second reference subtraction, 2^x fused into the one coalesced write ----------------
+        if (p.lo2 && p.apply_exp2) {
+            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+                double v[4], lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = min(g0 + u * NT, G - 1);
+                    v[u] = in[g];
+                    lo[u] = p.lo2[g];
+                    hi[u] = p.hi2[g];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = g0 + u * NT;
+                    const double x = fast_exp2(sub_bounds(v[u] - centre, lo[u], hi[u]), etab);
+                    if (g < G) dst[g] = x;
+                }
+            }
+        } else {
+            for (int g = tid; g < G; g += NT) {
+                double x = in[g] - centre;
+                if (p.lo2) x = sub_bounds(x, p.lo2[g], p.hi2[g]);
+                else if (p.mid2) x = x - p.mid2[g];
+                if (p.apply_exp2) x = fast_exp2(x, etab);
+                dst[g] = x;
+            }
+        }
+        __syncthreads();   // `in` is rewritten by the next cell's stage A
+        lap(5);
+        double *t = in;    // the next cell landed (or will be loaded) in `oth`
+        in = oth;
+        oth = t;
+    }
+    if (tid == 0 && blockIdx.x == 0)
+        for (int i = 0; i < 6; ++i) atomicAdd(&g_stats[4 + i], tacc[i]);
+    if (bad && p.err_flag) atomicExch(p.err_flag, 1);
+}
+
 // =================================================================================================
 // host-side launchers (device-pointer ABI)
 // =================================================================================================
@@ -866,9 +1325,9 @@ int icnv_dev_bounds_from_means_f64(const double *means, int64_t G, int n_grp, do
 ICNV_API int icnv_debug_stats(unsigned long long *out4, int reset) {
     ICNV_REQUIRE_READY();
     ICNV_CUDA(cudaDeviceSynchronize());
-    ICNV_CUDA(cudaMemcpyFromSymbol(out4, g_stats, sizeof(unsigned long long) * 4));
+    ICNV_CUDA(cudaMemcpyFromSymbol(out4, g_stats, sizeof(unsigned long long) * 16));
     if (reset) {
-        unsigned long long z[4] = {0, 0, 0, 0};
+        unsigned long long z[16] = {};
         ICNV_CUDA(cudaMemcpyToSymbol(g_stats, z, sizeof(z)));
     }
     return ICNV_OK;
@@ -899,6 +1358,50 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     int h = window >= 2 ? (window - 1) / 2 : 0;
     int s_elems = (int)((G + 1) & ~(int64_t)1);
     std::vector<Seg> segs;
+    cudaStream_t st = pick_stream(stream);
+    if (!c.math_tables_uploaded) {
+        ICNV_CUDA(cudaMemcpyToSymbol(g_log_tab, icnv_log_tab, sizeof(icnv_log_tab)));
+        ICNV_CUDA(cudaMemcpyToSymbol(g_exp_tab, icnv_exp_tab, sizeof(icnv_exp_tab)));
+        c.math_tables_uploaded = true;
+    }
+    CellParams p;
+    p.X = X; p.G = G; p.ldx = ldx; p.cols = cols; p.n_cols = n_cols; p.Y = Y; p.ldy = ldy;
+    p.apply_log = apply_log; p.lo1 = lo1; p.hi1 = hi1; p.mid1 = mid1; p.threshold = threshold;
+    p.window = window; p.h = h; p.center = center; p.lo2 = lo2; p.hi2 = hi2; p.mid2 = mid2;
+    p.apply_exp2 = apply_exp2; p.err_flag = err_flag; p.s_elems = s_elems; p.K = K;
+
+    // ---- v3 (values stay in shared memory, two ping-pong buffers) whenever both buffers fit -----------------
+    {
+        int want_v2 = 0, nt3 = (G <= 2048) ? 256 : (G <= 6144 ? 512 : 1024);
+        if (const char *e = getenv("ICNV_CELL_KERNEL")) want_v2 = (atoi(e) == 2);
+        if (const char *e = getenv("ICNV_CELL_NT")) nt3 = atoi(e);
+        if (nt3 != 256 && nt3 != 512 && nt3 != 1024) nt3 = 1024;
+        const int NW3 = nt3 / 32;
+        const size_t red3 = (nt3 == 256) ? sizeof(Red<8>) : (nt3 == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
+        const size_t smem3 = 128 * 24 + sizeof(double) * (2 * (size_t)s_elems + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 +
+                                                         CAND_MAX + 2) + red3 + 64;
+        int L3 = want_v2 ? 0 : build_segments(G, chr_start, chr_len, K, nt3, 1 << 20, segs);
+        if (L3 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
+        if (L3 > 0 && smem3 <= (size_t)c.smem_optin) {
+            Seg *d_segs3 = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
+            if (!d_segs3) return ICNV_E_NOMEM;
+            ICNV_CUDA(cudaMemcpyAsync(d_segs3, segs.data(), sizeof(Seg) * nt3, cudaMemcpyHostToDevice, st));
+            p.segs = d_segs3;
+            const int64_t grid3 = std::min<int64_t>(n_cols, c.sm_count);
+            auto launch3 = [&](auto kern) -> int {
+                ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                kern<<<(unsigned)grid3, nt3, smem3, st>>>(p);
+                return ICNV_OK;
+            };
+            int rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512>) : launch3(cell_pipeline3_kernel<1024>));
+            if (rc3) return rc3;
+            ICNV_CHECK_LAUNCH("cell_pipeline3_kernel");
+            return ICNV_OK;
+        }
+    }
+
+    // ---- v2 (register-resident values): large G where two buffers do not fit ---------------------------------------
     // (threads, genes per thread) variants, smallest first; ICNV_CELL_VARIANT=<index> pins one (tuning)
     static const int variants[][2] = {{256, 12}, {512, 12}, {512, 24}, {1024, 12}, {1024, 24}};  // measured: 512x24 beats 1024x12
     int NT = 0, L = 0, lmax = 0, forced = -1;
@@ -930,21 +1433,10 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         return set_error(ICNV_E_UNSUPPORTED, "G = %lld needs %zu B shared memory per CTA, device allows %d", (long long)G,
                          smem, c.smem_optin);
 
-    cudaStream_t st = pick_stream(stream);
-    if (!c.math_tables_uploaded) {
-        ICNV_CUDA(cudaMemcpyToSymbol(g_log_tab, icnv_log_tab, sizeof(icnv_log_tab)));
-        ICNV_CUDA(cudaMemcpyToSymbol(g_exp_tab, icnv_exp_tab, sizeof(icnv_exp_tab)));
-        c.math_tables_uploaded = true;
-    }
     Seg *d_segs = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
     if (!d_segs) return ICNV_E_NOMEM;
     ICNV_CUDA(cudaMemcpyAsync(d_segs, segs.data(), sizeof(Seg) * NT, cudaMemcpyHostToDevice, st));
-
-    CellParams p;
-    p.X = X; p.G = G; p.ldx = ldx; p.cols = cols; p.n_cols = n_cols; p.Y = Y; p.ldy = ldy; p.segs = d_segs;
-    p.apply_log = apply_log; p.lo1 = lo1; p.hi1 = hi1; p.mid1 = mid1; p.threshold = threshold;
-    p.window = window; p.h = h; p.center = center; p.lo2 = lo2; p.hi2 = hi2; p.mid2 = mid2;
-    p.apply_exp2 = apply_exp2; p.err_flag = err_flag; p.s_elems = s_elems; p.K = K;
+    p.segs = d_segs;
 
     auto launch = [&](auto kern) -> int {
         ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
