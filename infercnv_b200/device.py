@@ -133,14 +133,29 @@ class Engine:
         d_groups, t_lists, all_ref = cached
         flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
 
+        import torch.distributed as tdist
+        world = tdist.get_world_size() if (self.collective and tdist.is_available() and tdist.is_initialized()) else 1
+
         def group_means(src, lists, log):
-            rows = []
-            for k in range(n_grp):
-                part = self.group_partial_sums(src, lists[k], log)
-                if self.collective:
-                    part = shard.allgather_partials(part, max_chunks[k])
-                rows.append(self.combine_partials(part, ref_sizes[k]))
-            return torch.stack(rows)
+            """Per-group means; across ranks ONE all-gather per call carries every group's chunk sums
+            (rank-major, each group zero-padded to its max chunk count - zero chunks do not change a sum)."""
+            parts = [self.group_partial_sums(src, lists[k], log) for k in range(n_grp)]
+            if world > 1:
+                tot = int(sum(max_chunks))
+                packed = torch.zeros((tot, G), dtype=torch.float64, device=self.tdev)
+                pos = 0
+                for k in range(n_grp):
+                    if parts[k].shape[0]:
+                        packed[pos:pos + parts[k].shape[0]] = parts[k]
+                    pos += max_chunks[k]
+                gathered = torch.empty((world * tot, G), dtype=torch.float64, device=self.tdev)
+                tdist.all_gather_into_tensor(gathered, packed)
+                g3 = gathered.view(world, tot, G)
+                pos = 0
+                for k in range(n_grp):
+                    parts[k] = g3[:, pos:pos + max_chunks[k], :].reshape(world * max_chunks[k], G).contiguous()
+                    pos += max_chunks[k]
+            return torch.stack([self.combine_partials(parts[k], ref_sizes[k]) for k in range(n_grp)])
 
         b1 = self.bounds(group_means(X, d_groups, apply_log))
         # pass 1: reference cells only, up to the median centring
