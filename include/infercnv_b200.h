@@ -164,6 +164,11 @@ ICNV_API int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64
 ICNV_API int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mu,
                               double *sigma);
 
+/* Combine per-cell (sum, sd) pairs - e.g. all-gathered from several GPUs - into mu / sigma over all values
+ * of those cells, in list order (what icnv_mean_sd_f64 does internally). */
+ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu,
+                                      double *sigma);
+
 /* ---- device-pointer entry points ------------------------------------------------------------- */
 /* All pointers are device pointers on the icnv_init() device unless marked host.  `stream` is a
  * cudaStream_t; NULL = the library's own (non-blocking) stream - pass cudaStreamLegacy ((void*)1) to
@@ -211,6 +216,10 @@ ICNV_API int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const i
                                   const double *delta /*host*/, const double *mean /*host*/,
                                   const double *sd /*host*/, int sd_per_col, uint8_t *states_u8, double *margins,
                                   int *err_flag, void *stream);
+
+/* Per-cell sum and sd (n-1) of the listed columns (cells == NULL: columns 0..n_cells-1); sums / sds may be NULL. */
+ICNV_API int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *sums,
+                                       double *sds, void *stream);
 
 /* Median filter on device-resident data; index lists are host arrays. */
 ICNV_API int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C,

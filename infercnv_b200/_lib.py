@@ -50,6 +50,8 @@ SIGNATURES = {
     "icnv_dev_smooth_block_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, ct.c_double,
                                           c_int, c_int, _P]),
     "icnv_dev_viterbi_f64": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
+    "icnv_combine_cell_stats": (None, [_P, _P, c_i64, c_i64, _P, _P]),
+    "icnv_dev_column_stats_f64": (c_int, [_P, c_i64, _P, c_i64, _P, _P, _P]),
     "icnv_dev_median_filter_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, _P]),
     "icnv_dev_synth_f64": (c_int, [_P, c_i64, c_i64, c_i64, c_i64, _P, _P, c_int, ct.c_uint64, _P]),
 }

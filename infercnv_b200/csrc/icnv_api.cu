@@ -15,8 +15,6 @@ int icnv_dev_invlog_finish_f64(double *means, int64_t n, void *stream);
 int icnv_dev_widen_states(const uint8_t *s, int32_t *out, int64_t n, void *stream);
 int icnv_dev_scatter_group_states(const uint8_t *gs, int64_t G, int64_t C, const int32_t *grp_of, int32_t *out,
                                   void *stream);
-int icnv_dev_mean_sd_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *out2,
-                         void *stream);
 int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, int op, double param, int *err_flag, void *stream);
 int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *sums, double *sds,
                               void *stream);
@@ -24,6 +22,8 @@ int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C,
                                void *stream);
 int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream);
 }
+extern "C" ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu,
+                                                double *sigma);
 
 namespace icnv {
 
@@ -685,7 +685,7 @@ int icnv_apply_max_threshold_bounds_f64(const double *X, double *Y, int64_t n, d
 int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mu,
                      double *sigma) {
     ICNV_HOST_PROLOGUE();
-    if (!X || !idx || !mu || !sigma || G <= 0 || C <= 0 || n_idx <= 0)
+    if (!X || !idx || !mu || !sigma || G <= 1 || C <= 0 || n_idx <= 0)
         return set_error(ICNV_E_BAD_ARG, "icnv_mean_sd_f64: bad argument");
     for (int64_t i = 0; i < n_idx; ++i)
         if (idx[i] < 0 || idx[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index out of range");
@@ -693,16 +693,33 @@ int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, 
     int rc;
     if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
     int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_idx);
-    double *d_out = (double *)scratch(SLOT_MISC2, 64);
-    if (!d_idx || !d_out) return ICNV_E_NOMEM;
+    double *d_stats = (double *)scratch(SLOT_MEANS, sizeof(double) * 2 * (size_t)n_idx);
+    if (!d_idx || !d_stats) return ICNV_E_NOMEM;
     ICNV_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
-    if ((rc = icnv_dev_mean_sd_f64(dX, G, d_idx, n_idx, d_out, st))) return rc;
-    double h[2];
-    ICNV_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+    // per-cell sum and sd on the device; the n_idx-vectors are combined in list order (the same
+    // combination the multi-GPU driver applies to all-gathered per-cell statistics: identical bits)
+    if ((rc = icnv_dev_column_stats_f64(dX, G, d_idx, n_idx, d_stats, d_stats + n_idx, st))) return rc;
+    std::vector<double> h(2 * (size_t)n_idx);
+    ICNV_CUDA(cudaMemcpyAsync(h.data(), d_stats, sizeof(double) * 2 * (size_t)n_idx, cudaMemcpyDeviceToHost, st));
     ICNV_CUDA(cudaStreamSynchronize(st));
-    *mu = h[0];
-    *sigma = h[1];
+    icnv_combine_cell_stats(h.data(), h.data() + n_idx, n_idx, G, mu, sigma);
     return ICNV_OK;
+}
+
+/* mu, sigma (n-1) over all values of n cells from the cells' own (sum, sd): sum of squares about mu of a cell =
+ * sd_c^2 (G-1) + G (mean_c - mu)^2.  Plain host arithmetic on 2n numbers, in list order. */
+void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu, double *sigma) {
+    double tot = 0.0;
+    for (int64_t i = 0; i < n; ++i) tot += sums[i];
+    const double N = (double)G * (double)n;
+    const double m = tot / N;
+    double ss = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double d = sums[i] / (double)G - m;
+        ss += sds[i] * sds[i] * (double)(G - 1) + (double)G * d * d;
+    }
+    *mu = m;
+    *sigma = std::sqrt(ss / (N - 1.0));
 }
 
 }  // extern "C"

@@ -1,57 +1,16 @@
-// icnv_reduce.cu - K6: mean and sd (n-1) over all values of a set of cells
-// (.i3HMM_get_sd_trend_by_num_cells_fit, R/inferCNV_i3HMM.R:17-30: mu = mean(X[, cells]),
-// sigma = sd(X[, cells])).  Two passes (mean, then centred sum of squares) like R's var(); fixed
-// block -> element assignment and an ordered final combine make the result reproducible.
+// icnv_reduce.cu - small reductions and element-wise passes around the hot path:
+//   K6  per-cell sum / sd (column_stats_kernel): feeds mu / sigma over the reference cells
+//       (.i3HMM_get_sd_trend_by_num_cells_fit, R/inferCNV_i3HMM.R:17-30) and the denoise threshold
+//       (clear_noise_via_ref_mean_sd, R/inferCNV_ops.R:2302-2346); one CTA per cell with a fixed reduction
+//       tree, so per-cell statistics - and anything combined from them in list order - do not depend on
+//       how the cells are spread over GPUs
+//   depth normalisation, denoise and the stand-alone element-wise steps
 #include <algorithm>
 #include <cmath>
 
 #include "icnv_common.cuh"
 
 namespace icnv {
-
-constexpr int RED_BLOCKS = 1184;  // 148 SMs x 8
-constexpr int RED_THREADS = 256;
-
-// pass: 0 -> sum(x), 1 -> sum((x - mean)^2) with mean read from out2[0]
-__global__ void __launch_bounds__(RED_THREADS) cells_moment_kernel(const double *__restrict__ X, int64_t G,
-                                                                   const int32_t *__restrict__ cells, int64_t n_cells,
-                                                                   int pass, const double *__restrict__ out2,
-                                                                   double *__restrict__ partial) {
-    __shared__ double sh[RED_THREADS / 32];
-    const double mean = pass ? out2[0] : 0.0;
-    double s = 0.0;
-    // block b owns cells b, b + gridDim.x, ...; threads stride over the genes of a cell (coalesced)
-    for (int64_t ci = blockIdx.x; ci < n_cells; ci += gridDim.x) {
-        const double *col = X + G * (int64_t)cells[ci];
-        for (int64_t g = threadIdx.x; g < G; g += RED_THREADS) {
-            double v = col[g];
-            if (pass) {
-                double d = v - mean;
-                s = fma(d, d, s);
-            } else {
-                s += v;
-            }
-        }
-    }
-    s = warp_sum_d(s);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < RED_THREADS / 32; ++w) t += sh[w];
-        partial[blockIdx.x] = t;
-    }
-}
-
-__global__ void moment_finish_kernel(const double *__restrict__ partial, int n_partial, double count, int pass,
-                                     double *__restrict__ out2) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < n_partial; ++i) t += partial[i];
-        if (pass == 0) out2[0] = t / count;
-        else out2[1] = sqrt(t / (count - 1.0));
-    }
-}
 
 // element-wise steps of run(): log2xplus1 (ops.R:2756-2769), invert_log2 (ops.R:2814-2826),
 // apply_max_threshold_bounds (ops.R:2970-2983).  Inside the fused block these ride on the loads / stores of
@@ -140,7 +99,7 @@ __global__ void __launch_bounds__(256) clear_noise_kernel(const double *__restri
 
 using namespace icnv;
 
-extern "C" int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *sums,
+extern "C" ICNV_API int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *sums,
                                          double *sds, void *stream) {
     ICNV_REQUIRE_READY();
     if (!X || G <= 1 || n_cells <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_column_stats_f64: bad argument");
@@ -174,25 +133,5 @@ extern "C" int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, i
     int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
     elementwise_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, op, param, err_flag);
     ICNV_CHECK_LAUNCH("elementwise_kernel");
-    return ICNV_OK;
-}
-
-
-extern "C" int icnv_dev_mean_sd_f64(const double *X, int64_t G, const int32_t *cells, int64_t n_cells, double *out2,
-                                    void *stream) {
-    ICNV_REQUIRE_READY();
-    if (!X || !cells || !out2 || G <= 0 || n_cells <= 0)
-        return set_error(ICNV_E_BAD_ARG, "icnv_dev_mean_sd_f64: bad argument");
-    cudaStream_t st = pick_stream(stream);
-    double *d_part = (double *)scratch(SLOT_PARTIAL, sizeof(double) * RED_BLOCKS);
-    if (!d_part) return ICNV_E_NOMEM;
-    int nb = (int)(n_cells < RED_BLOCKS ? n_cells : RED_BLOCKS);
-    double count = (double)G * (double)n_cells;
-    for (int pass = 0; pass < 2; ++pass) {
-        cells_moment_kernel<<<nb, RED_THREADS, 0, st>>>(X, G, cells, n_cells, pass, out2, d_part);
-        ICNV_CHECK_LAUNCH("cells_moment_kernel");
-        moment_finish_kernel<<<1, 32, 0, st>>>(d_part, nb, count, pass, out2);
-        ICNV_CHECK_LAUNCH("moment_finish_kernel");
-    }
     return ICNV_OK;
 }

@@ -193,6 +193,48 @@ class Engine:
                                                  flag.data_ptr(), _stream_ptr()))
         return (st, flag, mg) if want_margins else (st, flag)
 
+    def mean_sd(self, X, groups_local):
+        """mu / sigma over all values of the listed cells across ALL ranks (.i3HMM_get_sd_trend_by_num_cells_fit,
+        R/inferCNV_i3HMM.R:17-30).  groups_local: per group, this rank's LOCAL columns (the planner's slices).
+        Per-cell (sum, sd) are computed on each GPU, all-gathered group by group in rank order - which restores
+        the global list order - and combined by the routine the single-GPU entry point uses: identical bits for
+        any rank count."""
+        import torch.distributed as tdist
+        G = X.shape[1]
+        multi = self.collective and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+        world = tdist.get_world_size() if multi else 1
+        lens = [len(g) for g in groups_local]
+        cat = np.concatenate([np.asarray(g, dtype=np.int32) for g in groups_local]) if sum(lens) else np.zeros(0, np.int32)
+        n = len(cat)
+        stats = torch.zeros((2, max(n, 1)), dtype=torch.float64, device=self.tdev)
+        if n:
+            idx = torch.as_tensor(cat, device=self.tdev)
+            _lib.check(self.lib.icnv_dev_column_stats_f64(X.data_ptr(), G, idx.data_ptr(), n, stats[0].data_ptr(),
+                                                          stats[1].data_ptr(), _stream_ptr()))
+        if not multi:
+            allstats = stats[:, :n].cpu().numpy()
+        else:
+            mine = torch.tensor(lens, dtype=torch.int64, device=self.tdev)
+            all_lens = [torch.zeros_like(mine) for _ in range(world)]
+            tdist.all_gather(all_lens, mine)
+            all_lens = [t.cpu().numpy() for t in all_lens]
+            nmax = int(max(int(l.sum()) for l in all_lens))
+            padded = torch.zeros((2, max(nmax, 1)), dtype=torch.float64, device=self.tdev)
+            padded[:, :n] = stats[:, :n]
+            gathered = [torch.empty_like(padded) for _ in range(world)]
+            tdist.all_gather(gathered, padded)
+            gathered = [g.cpu().numpy() for g in gathered]
+            cols = []
+            for k in range(len(lens)):          # group-major, rank-minor = the global list order
+                for r in range(world):
+                    off = int(all_lens[r][:k].sum())
+                    cols.append(gathered[r][:, off:off + int(all_lens[r][k])])
+            allstats = np.concatenate(cols, axis=1)
+        sums, sds = np.ascontiguousarray(allstats[0]), np.ascontiguousarray(allstats[1])
+        mu, sg = ct.c_double(), ct.c_double()
+        self.lib.icnv_combine_cell_stats(sums.ctypes.data, sds.ctypes.data, len(sums), G, ct.addressof(mu), ct.addressof(sg))
+        return mu.value, sg.value
+
     def median_filter(self, X, chr_start, chr_len, groups_local, window_size=7, out=None):
         C, G = X.shape
         cs, cl = _i32(chr_start), _i32(chr_len)

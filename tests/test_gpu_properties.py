@@ -118,6 +118,18 @@ def test_smooth_block_output_range_and_reference_centering(world):
     assert frac_one > 0.0
 
 
+def test_engine_mean_sd_matches_host_entry_point(world):
+    w = world
+    from infercnv_b200 import api
+    groups = w["plan"].local_ref_groups()
+    mu, sg = w["eng"].mean_sd(w["Y"], groups)
+    Yh = w["Y"][:1200].cpu().numpy().T                         # (G, 1200) Fortran view; refs are the first 1000 cells
+    mu2, sg2 = api.mean_sd(Yh, np.concatenate(groups))
+    assert mu == mu2 and sg == sg2
+    vals = Yh[:, np.concatenate(groups)]
+    assert abs(mu - vals.mean()) < 1e-13 and abs(sg - vals.std(ddof=1)) < 1e-12
+
+
 def test_median_filter_properties(world):
     """Median of a constant block is the constant; positive scaling commutes with the median."""
     w = world

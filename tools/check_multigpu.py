@@ -26,6 +26,7 @@ plan = shard.plan_shards(C_total, refs, world)[rank]
 X = eng.synth(G, cs, cl, plan.local_cells, C_total, bench.SEED)
 Y, f = eng.smooth_block(X, cs, cl, plan.local_ref_groups(), plan.ref_sizes, plan.max_chunks)
 S, f2 = eng.viterbi(Y, cs, cl, Pi, delta, bench.I6_MEAN, bench.I6_SD)
+mu_d, sg_d = eng.mean_sd(Y, plan.local_ref_groups())        # i3 parameters across ranks
 torch.cuda.synchronize()
 assert int(f.item()) == 0 and int(f2.item()) == 0
 # gather every rank's rows on rank 0 (variable sizes -> pad)
@@ -47,6 +48,7 @@ if rank == 0:
     eng.collective = False   # rank 0 alone: the other ranks are not in this computation
     Y1, _ = eng.smooth_block(X1, cs, cl, p1.local_ref_groups(), p1.ref_sizes, [(len(g) + 31) // 32 for g in refs])
     S1, _ = eng.viterbi(Y1, cs, cl, Pi, delta, bench.I6_MEAN, bench.I6_SD)
+    mu_1, sg_1 = eng.mean_sd(Y1, p1.local_ref_groups())
     torch.cuda.synchronize()
     pos1 = {int(c): i for i, c in enumerate(p1.local_cells)}
     bad_y = bad_s = 0
@@ -54,7 +56,8 @@ if rank == 0:
         idx = torch.tensor([pos1[int(c)] for c in p.local_cells], device=X.device)
         bad_y += int((Ys[r][: len(idx)] != Y1[idx]).sum().item())
         bad_s += int((Ss[r][: len(idx)] != S1[idx]).sum().item())
-    ok = bad_y == 0 and bad_s == 0
+    ok = bad_y == 0 and bad_s == 0 and mu_d == mu_1 and sg_d == sg_1
+    print(f"[check_multigpu] i3 mu/sigma over the reference cells: {mu_d!r}, {sg_d!r} (1-GPU: {mu_1!r}, {sg_1!r})")
     print(f"[check_multigpu] world={world} cells={C_total}: smoothed values differing from 1-GPU run: {bad_y}; "
           f"states differing: {bad_s}  -> {'BITWISE EQUAL' if ok else 'MISMATCH'}")
 dist.barrier()
