@@ -444,9 +444,14 @@ __device__ __forceinline__ double fast_exp2(double x, const double *__restrict__
 
 // dead-band subtraction, .subtract_expr (ops.R:1764-1769): strict inequalities
 __device__ __forceinline__ double sub_bounds(double x, double lo, double hi) {
-    // x - clamp(x, lo, hi): x-hi above the band, x-lo below it, exactly 0 inside (lo <= hi always)
-    return x - fmin(fmax(x, lo), hi);
+    // x-hi above the band, x-lo below it, exactly 0 inside (lo <= hi always).  Written with compares and selects:
+    // double-precision fmin / fmax expand to ~17 instructions each on sm_100, this form is 8 in total.
+    const double above = x - hi, below = x - lo;
+    return (x > hi) ? above : ((x < lo) ? below : 0.0);
 }
+
+// apply_max_threshold_bounds (ops.R:2970-2983): clamp to [-thr, thr]
+__device__ __forceinline__ double clamp_sym(double x, double thr) { return (fabs(x) > thr) ? copysign(thr, x) : x; }
 
 // ---- mbarrier / bulk-copy (TMA) helpers: the next cell's column is fetched by the copy engine
 //      into shared memory while the CTA works on the current one --------------------------------
@@ -570,7 +575,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
                     if (!is_finite_d(v[u])) bad = true;
                     double x = fast_log2_1p(v[u], ltab);
                     x = sub_bounds(x, lo[u], hi[u]);
-                    x = fmin(fmax(x, -thr), thr);
+                    x = clamp_sym(x, thr);
                     if (g < G) work[g] = x;
                 }
             }
@@ -594,7 +599,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
                         if (p.apply_log) x = fast_log2_1p(x, ltab);
                         if (p.lo1) x = sub_bounds(x, lo[u], hi[u]);
                         else if (p.mid1) x = x - lo[u];
-                        if (p.threshold > 0.0) x = fmin(fmax(x, -p.threshold), p.threshold);
+                        if (p.threshold > 0.0) x = clamp_sym(x, p.threshold);
                         work[g] = x;
                     }
                 }
@@ -801,10 +806,7 @@ __device__ __forceinline__ double block_median_smem(const double *__restrict__ v
     constexpr int NW = NT / 32;
     const int kA = (n - 1) >> 1, kB = n >> 1;
     const double *v0 = vals + a0;
-    if (threadIdx.x == 0) {
-        atomicAdd(&g_stats[1], 1ull);
-        *cand_n = 0;   // made visible by the reductions' barriers long before the gather
-    }
+    if (threadIdx.x == 0) *cand_n = 0;   // made visible by the reductions' barriers long before the gather
     double S1, S2;
     block_red2d<NW, 1>(red, phase, s1, s2, S1, S2);
     const double mean = S1 / (double)n;
@@ -953,6 +955,125 @@ __device__ __forceinline__ double block_median_smem(const double *__restrict__ v
     return (cand[CAND_MAX] + cand[CAND_MAX + 1]) * 0.5;   // cand is next touched a whole cell (many barriers) later
 }
 
+// ---- median by one histogram pass ----------------------------------------------------------------
+// |mean - median| <= sd for any distribution, so the HIST_NB equal-width bins spanning mean +- sd hold both middle
+// order statistics.  bin(v) = low word of fma(v, scale, C) with C = 1.5*2^52 - (mean - sd)*scale is a monotone
+// function of v evaluated by the same instruction in both passes, so "values in lower bins" are exactly the values
+// ranked below the bin: pass 1 counts (shared-memory atomics for the inner bins, a register for "below"), a
+// block-wide scan finds the bin(s) holding ranks kA and kB, pass 2 gathers those bins' values (<= CAND_MAX,
+// otherwise the bracketing selection above takes over) and they are ranked directly.  Two passes over the
+// values, any thread reads any value: both passes use the coalesced 16-byte mapping.
+constexpr int HIST_NB = 2048;
+
+template <int NT>
+__device__ __forceinline__ bool block_median_hist(const double *__restrict__ vals, int n, double S1, double S2, int *hist,
+                                                  int *hres, int *wcnt, double *cand, int *cand_n, double &result) {
+    constexpr int NW = NT / 32;
+    constexpr int BPT = HIST_NB / NT;   // bins scanned per thread
+    static_assert(HIST_NB % NT == 0 && BPT >= 1 && BPT <= 8, "HIST_NB must be a small multiple of NT");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kA = (n - 1) >> 1, kB = n >> 1;
+    const double mean = S1 / (double)n;
+    const double var = S2 / (double)n - mean * mean;
+    if (!(var > 0.0) || n <= 4 * CAND_MAX) return false;
+    const double sd = sqrt(var);
+    const double scale = (0.5 * HIST_NB) / sd;
+    if (!(scale < 1e290)) return false;
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: integers 0 .. 2^32-1 land in the low word, high word HI0
+    constexpr int HI0 = 0x43380000;
+    const double C = fma(sd - mean, scale, MAGIC);
+    if (tid == 0) {
+        hres[0] = -1;
+        hres[2] = -1;
+        *cand_n = 0;
+    }
+    const double2 *v2 = reinterpret_cast<const double2 *>(vals);
+    const int n2 = (n + 1) >> 1;   // an odd n is padded with +inf (never counted, never gathered)
+    int cb = 0;
+#pragma unroll 2
+    for (int i = tid; i < n2; i += NT) {
+        const double2 v = v2[i];
+        const double tx = fma(v.x, scale, C), ty = fma(v.y, scale, C);
+        const int hx = __double2hiint(tx), hy = __double2hiint(ty);
+        const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
+        if (hx == HI0 && lx < (unsigned)HIST_NB) atomicAdd(&hist[lx], 1);
+        if (hy == HI0 && ly < (unsigned)HIST_NB) atomicAdd(&hist[ly], 1);
+        cb += (hx < HI0) ? 1 : 0;
+        cb += (hy < HI0) ? 1 : 0;
+    }
+    cb = __reduce_add_sync(0xffffffffu, cb);
+    if (lane == 0) wcnt[warp] = cb;
+    __syncthreads();   // histogram complete
+    int cnt[BPT];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < BPT; ++k) {
+        cnt[k] = hist[tid * BPT + k];
+        hist[tid * BPT + k] = 0;   // left clean for the next cell
+        s += cnt[k];
+    }
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wcnt[NW + warp] = inc;
+    __syncthreads();
+    {
+        const int below = __reduce_add_sync(0xffffffffu, (lane < NW) ? wcnt[lane] : 0);
+        const int prev = __reduce_add_sync(0xffffffffu, (lane < warp) ? wcnt[NW + lane] : 0);
+        int o = below + prev + inc - s;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const int c = cnt[k];
+            if (c > 0) {
+                if (o <= kA && kA < o + c) {
+                    hres[0] = tid * BPT + k;
+                    hres[1] = o;
+                }
+                if (o <= kB && kB < o + c) {
+                    hres[2] = tid * BPT + k;
+                    hres[3] = o + c;
+                }
+            }
+            o += c;
+        }
+    }
+    __syncthreads();
+    const int bA = hres[0], offA = hres[1], bB = hres[2], endB = hres[3];
+    if (bA < 0 || bB < 0 || endB - offA > CAND_MAX) return false;   // histogram already zeroed
+    const int m = endB - offA;
+#pragma unroll 2
+    for (int i = tid; i < n2; i += NT) {
+        const double2 v = v2[i];
+        const double tx = fma(v.x, scale, C), ty = fma(v.y, scale, C);
+        const int hx = __double2hiint(tx), hy = __double2hiint(ty);
+        const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
+        if (hx == HI0 && lx >= (unsigned)bA && lx <= (unsigned)bB) cand[atomicAdd(cand_n, 1)] = v.x;
+        if (hy == HI0 && ly >= (unsigned)bA && ly <= (unsigned)bB) cand[atomicAdd(cand_n, 1)] = v.y;
+    }
+    __syncthreads();
+    const int ra = kA - offA, rb = kB - offA;
+    {   // one warp per candidate: its 32 lanes compare it with all (<= 64) candidates, one redux gives the rank
+        const double u1 = (lane < m) ? cand[lane] : INFINITY;
+        const double u2 = (lane + 32 < m) ? cand[lane + 32] : INFINITY;
+        for (int i = warp; i < m; i += NW) {
+            const double v = cand[i];
+            int c = ((u1 < v) || (u1 == v && lane < i)) ? 1 : 0;
+            c += ((u2 < v) || (u2 == v && lane + 32 < i)) ? 1 : 0;
+            const int rank = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) {
+                if (rank == ra) cand[CAND_MAX] = v;
+                if (rank == rb) cand[CAND_MAX + 1] = v;
+            }
+        }
+    }
+    __syncthreads();
+    result = (cand[CAND_MAX] + cand[CAND_MAX + 1]) * 0.5;
+    return true;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -967,8 +1088,14 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
     double *tails = qtot + p.K;                              // [2][NW]
     double *cand = tails + 2 * NW;
     Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
-    int *cand_n = reinterpret_cast<int *>(&red + 1);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cand_n + 2);
+    double *rext = reinterpret_cast<double *>(&red + 1);     // [K][h] linear continuation of Q past each chromosome end
+    double *zslot = rext + p.K * p.h;                        // a 0.0 the edge loads can point at (Q before the start)
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(zslot + 2);
+    int *hist = reinterpret_cast<int *>(bar + 2);            // HIST_NB bins, zero between cells
+    int *hres = hist + HIST_NB;                              // 4 results of the bin search (+4 spare)
+    int *wcnt = hres + 8;                                    // [2][NW]
+    int *cand_n = wcnt + 2 * NW;
+    double *const sm = reinterpret_cast<double *>(smem_raw); // everything below is indexed relative to this
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)p.G;
@@ -980,7 +1107,13 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         const double full = (double)(h + 1) * (double)(h + 1);
         for (int r = tid; r <= h; r += NT) invD[r] = 1.0 / (full - 0.5 * (double)r * (double)(r + 1));
     }
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        zslot[0] = 0.0;
+        buf0[p.s_elems - 1] = INFINITY;   // pad of an odd G: never counted by the median (overwritten when G is even)
+        buf1[p.s_elems - 1] = INFINITY;
+    }
+    for (int i = tid; i < HIST_NB; i += NT) hist[i] = 0;
     for (int i = tid; i < 128; i += NT) {
         ltab[i] = make_double2(g_log_tab[i][0], g_log_tab[i][1]);
         etab[i] = g_exp_tab[i];
@@ -989,22 +1122,25 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
     const int len = seg.len, a0 = seg.start, cs = seg.cs, ce = seg.ce, n = ce - cs;
     const int lane_first = max(seg.tfirst - (tid - lane), 0);
     const int wfirst = seg.tfirst >> 5;
-    const double invD0 = do_smooth ? 1.0 / ((double)(h + 1) * (double)(h + 1)) : 1.0;
     bool bad = false;
     const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
     auto tma_ok = [&](int64_t col) {
         return ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
     };
     double *in = buf0, *oth = buf1;
+#ifdef ICNV_STAGE_TIMERS
     long long tstamp = clock64();
     unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};
-    auto lap = [&](int slot) {   // stage timing by one thread of CTA 0 (diagnostic, see icnv_debug_stats)
+    auto lap = [&](int slot) {   // stage timing by one thread of CTA 0 (diagnostic build, see icnv_debug_stats)
         if (tid == 0 && blockIdx.x == 0) {
             const long long now = clock64();
             tacc[slot] += (unsigned long long)(now - tstamp);
             tstamp = now;
         }
     };
+#else
+    auto lap = [](int) {};
+#endif
     __syncthreads();
     if (tid == 0 && (int64_t)blockIdx.x < p.n_cols) {
         const int64_t col0 = p.cols ? (int64_t)p.cols[blockIdx.x] : (int64_t)blockIdx.x;
@@ -1045,7 +1181,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                     if (!is_finite_d(v[u])) bad = true;
                     double x = fast_log2_1p(v[u], ltab);
                     x = sub_bounds(x, lo[u], hi[u]);
-                    x = fmin(fmax(x, -thr), thr);
+                    x = clamp_sym(x, thr);
                     if (g < G) oth[g] = x;
                 }
             }
@@ -1056,7 +1192,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                 if (p.apply_log) x = fast_log2_1p(x, ltab);
                 if (p.lo1) x = sub_bounds(x, p.lo1[g], p.hi1[g]);
                 else if (p.mid1) x = x - p.mid1[g];
-                if (p.threshold > 0.0) x = fmin(fmax(x, -p.threshold), p.threshold);
+                if (p.threshold > 0.0) x = clamp_sym(x, p.threshold);
                 oth[g] = x;
             }
         }
@@ -1126,37 +1262,36 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                 qtot[seg.chr] = qv;
             }
             __syncthreads();
+            // Q continues linearly past a chromosome's last gene (x is taken as 0 there): Q(n-1+k) = Qn + k*Pn, k = 1..h
+            for (int idx = tid; idx < p.K * h; idx += NT) {
+                const int c = idx / h, k = idx - c * h + 1;
+                rext[idx] = fma((double)k, ptot[c], qtot[c]);
+            }
+            __syncthreads();
             lap(2);
-            // outputs
+            // outputs: N(j) = (Q(j+h) - Q(j-1)) - (Q(j-1) - Q(j-h-2)), one code path for interior and edge genes -
+            // out-of-range Q come from the continuation table or the zero slot by index selection, no branches
             if (n >= 2) {
-                const double *Qc = oth + cs;
-                const double Pn = ptot[seg.chr], Qn = qtot[seg.chr];
-                auto Qt = [&](int j) -> double {
-                    if (j < 0) return 0.0;
-                    if (j <= n - 1) return Qc[j];
-                    return Qn + (double)(j - (n - 1)) * Pn;
-                };
+                const int qoff = (int)(oth - sm) + cs;                       // Q(j) lives at sm[qoff + j], 0 <= j < n
+                const int roff = (int)(rext - sm) + seg.chr * h - n;         // Q(j) at sm[roff + j], n <= j < n + h
+                const int zoff = (int)(zslot - sm);
+                const bool short_chr = n < 2 * h + 1;                        // both ends inside one window
                 int j = a0 - cs;
 #pragma unroll 2
                 for (int q = 0; q < len; ++q, ++j) {
+                    const int ja = j + h, jb = j - 1, jc = j - h - 2;
+                    const double qa = sm[(ja <= n - 1 ? qoff : roff) + ja];
+                    const double qb = sm[jb >= 0 ? qoff + jb : zoff];
+                    const double qc = sm[jc >= 0 ? qoff + jc : zoff];
+                    const double N = (qa - qb) - (qb - qc);
+                    const int rl = max(h - j, 0), rr = max(h - (n - 1 - j), 0);
                     double out;
-                    if (j - h - 2 >= 0 && j + h <= n - 1) {   // window inside the chromosome
-                        const double qb = Qc[j - 1];
-                        out = ((Qc[j + h] - qb) - (qb - Qc[j - h - 2])) * invD0;
+                    if (short_chr && rl > 0 && rr > 0) {
+                        const double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
+                                         0.5 * (double)rr * (double)(rr + 1);
+                        out = N / D;
                     } else {
-                        const double qa = Qt(j + h), qb = Qt(j - 1), qc = Qt(j - h - 2);
-                        const double N = (qa - qb) - (qb - qc);
-                        int rl = h - j;
-                        rl = rl > 0 ? rl : 0;
-                        int rr = h - (n - 1 - j);
-                        rr = rr > 0 ? rr : 0;
-                        if (rl == 0 || rr == 0) {
-                            out = N * invD[rl + rr];
-                        } else {
-                            const double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
-                                             0.5 * (double)rr * (double)(rr + 1);
-                            out = N / D;
-                        }
+                        out = N * invD[rl + rr];
                     }
                     in[a0 + q] = out;
                     ys1 += out;
@@ -1172,7 +1307,17 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                 }
             }
         }
+        ys1 = warp_sum_d(ys1);
+        ys2 = warp_sum_d(ys2);
+        if (lane == 0) {
+            red.d[phase][0][warp] = ys1;
+            red.d[phase][1][warp] = ys2;
+        }
         __syncthreads();   // smoothed values complete in `in`; Q in `oth` no longer needed
+        double S1 = (lane < NW) ? red.d[phase][0][lane] : 0.0, S2 = (lane < NW) ? red.d[phase][1][lane] : 0.0;
+        S1 = warp_sum_d(S1);
+        S2 = warp_sum_d(S2);
+        phase ^= 1;
         lap(3);
         if (tid == 0) {    // next cell's column lands in `oth` while the median and the epilogue run
             const int64_t cn = ci + gridDim.x;
@@ -1189,12 +1334,19 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         // ---- C: per-cell centre --------------------------------------------------------------------------------
         double centre = 0.0;
         if (p.center == 1) {
-            centre = block_median_smem<NT>(in, a0, len, G, ys1, ys2, red, phase, cand, cand_n);
+            if (tid == 0) atomicAdd(&g_stats[1], 1ull);
+            if (block_median_hist<NT>(in, G, S1, S2, hist, hres, wcnt, cand, cand_n, centre)) {
+                if (tid == 0) atomicAdd(&g_stats[10], 1ull);
+            } else {   // tiny or degenerate columns, > CAND_MAX ties in the middle bin: bracketing selection
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < len; ++q) {
+                    const double v = in[a0 + q];
+                    s1 += v;
+                    s2 = fma(v, v, s2);
+                }
+                centre = block_median_smem<NT>(in, a0, len, G, s1, s2, red, phase, cand, cand_n);
+            }
         } else if (p.center == 2) {
-            double s1 = 0.0;
-            for (int q = 0; q < len; ++q) s1 += in[a0 + q];
-            double S1, dummy;
-            block_red2d<NW, 1>(red, phase, s1, 0.0, S1, dummy);
             centre = S1 / (double)G;
         }
 
@@ -1232,8 +1384,10 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         in = oth;
         oth = t;
     }
+#ifdef ICNV_STAGE_TIMERS
     if (tid == 0 && blockIdx.x == 0)
         for (int i = 0; i < 6; ++i) atomicAdd(&g_stats[4 + i], tacc[i]);
+#endif
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
 
@@ -1379,7 +1533,8 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         const int NW3 = nt3 / 32;
         const size_t red3 = (nt3 == 256) ? sizeof(Red<8>) : (nt3 == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
         const size_t smem3 = 128 * 24 + sizeof(double) * (2 * (size_t)s_elems + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 +
-                                                         CAND_MAX + 2) + red3 + 64;
+                                                         CAND_MAX + 2 + (size_t)K * (size_t)h + 2 + 2) + red3 +
+                             sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2) + 64;
         int L3 = want_v2 ? 0 : build_segments(G, chr_start, chr_len, K, nt3, 1 << 20, segs);
         if (L3 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
         if (L3 > 0 && smem3 <= (size_t)c.smem_optin) {

@@ -19,5 +19,5 @@ tot=sum(out[4:10]) or 1
 print("CTA0 cycles by stage [wait, A, B scans, B outputs, C median, D]:", [round(100*out[4+i]/tot,1) for i in range(6)], "total cycles", tot)
 mt=sum(out[10:15]) or 1
 print("median sub-stages [stats, pivots, count, reduce, gather+rank] %:", [round(100*out[10+i]/mt,1) for i in range(5)], "cycles", mt)
-print("median rounds",out[0],"medians",out[1],"rounds/median",out[0]/max(1,out[1]),"split exits",out[2],"gather exits",out[3])
+print("histogram medians", out[10]); print("median rounds",out[0],"medians",out[1],"rounds/median",out[0]/max(1,out[1]),"split exits",out[2],"gather exits",out[3])
 xs=X[5000].cpu().numpy(); print("cell 5000 raw stats", xs.mean(), (xs==0).mean())
