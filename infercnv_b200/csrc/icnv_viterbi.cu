@@ -60,6 +60,7 @@ struct VitParams {
     double inv_sd;             // 1 / median sd
     double tau;                // decision-margin threshold below which a sequence is re-run exactly
     const double *table;       // device copy of icnv_emis_table
+    int means_monotone;        // state means sorted (either direction): the furthest state from any x is an end state
     int2 *list_out;
     unsigned int *list_out_count;
     unsigned int list_cap;
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
 
 constexpr int TG = 8;        // genes per staged tile
 constexpr int TS = TG + 1;   // padded row stride in doubles (bank-conflict-free column reads)
-constexpr int FAST_WARPS = 8;
+constexpr int FAST_WARPS = 16;   // one CTA per SM: the replicated table below is shared by all of them
+constexpr int TAB_REP = 8;       // table replicas: lane l reads replica l & 7, so a 16-byte lookup never bank-conflicts
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -340,25 +342,32 @@ __device__ __noinline__ double emission_far(double x, double mean, double sd) {
 }
 
 template <int M>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const VitParams p) {
+__global__ void __launch_bounds__(FAST_WARPS * 32, 1) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
-    // emission table re-laid as [interval] -> {c0, c1} and {c2, (float c3, float c4)}: two 16-byte loads per
-    // state, 32 B instead of 40 B of shared-memory traffic (the table reads are this kernel's tightest
-    // resource).  c3, c4 only weigh u^3, u^4 with |u| <= 1/2: single precision costs < 3e-14.
-    constexpr int NTAB = ICNV_EMIS_N + 1;                        // even count keeps the double2 arrays aligned
+    // emission table re-laid as [interval][replica] -> {c0, c1} and {c2, (float c3, float c4)}: two 16-byte loads
+    // per state (32 B instead of 40 B; c3, c4 only weigh u^3, u^4 with |u| <= 1/2: single precision costs < 3e-14).
+    // The lanes of a warp look up unrelated intervals, which on a single copy costs ~2.4 x the minimum number of
+    // shared-memory wavefronts in bank conflicts - the table reads are this kernel's tightest resource.  With
+    // TAB_REP = 8 copies interleaved at 16-byte granularity, lane l always reads bank group l & 7: every quarter
+    // warp touches 8 distinct groups, i.e. exactly 4 wavefronts per load.
+    constexpr int NTAB = (ICNV_EMIS_N + 1) * TAB_REP;
     double2 *tab01 = reinterpret_cast<double2 *>(sm);
     double2 *tab2f = tab01 + NTAB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *tiles = reinterpret_cast<double *>(tab2f + NTAB) + warp * (2 * 32 * TS);   // two staged x tiles per warp
-    for (int i = threadIdx.x; i < ICNV_EMIS_N; i += blockDim.x) {
-        tab01[i] = make_double2(p.table[i], p.table[ICNV_EMIS_N + i]);
+    for (int e = threadIdx.x; e < ICNV_EMIS_N * TAB_REP; e += blockDim.x) {
+        const int i = e / TAB_REP;
+        tab01[e] = make_double2(p.table[i], p.table[ICNV_EMIS_N + i]);
         const float c3 = (float)p.table[3 * ICNV_EMIS_N + i], c4 = (float)p.table[4 * ICNV_EMIS_N + i];
-        tab2f[i] = make_double2(p.table[2 * ICNV_EMIS_N + i], __hiloint2double(__float_as_int(c4), __float_as_int(c3)));
+        tab2f[e] = make_double2(p.table[2 * ICNV_EMIS_N + i], __hiloint2double(__float_as_int(c4), __float_as_int(c3)));
     }
     __syncthreads();
+    const double2 *tabA = tab01 + (lane & (TAB_REP - 1)), *tabB = tab2f + (lane & (TAB_REP - 1));   // this lane's replica
 
     const int64_t warp_global = (int64_t)blockIdx.x * FAST_WARPS + warp;
-    uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
+    // backpointers: one 16-bit word per gene and lane - the best previous state (3 bits) and, per state, whether the
+    // path into it comes from that best state (1) or stays (0)
+    uint16_t *__restrict__ bp = reinterpret_cast<uint16_t *>(p.bp + warp_global * (int64_t)p.max_len * 32);
     const double a = p.a_diag, b = p.b_off;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC == rint(v), low word == (int)rint(v)
     const int tau_hi = __double2hiint(p.tau);
@@ -384,6 +393,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
         }
         const double sd = p.sd_col ? p.sd_col[cc] : p.sd;
         const double scale = (double)ICNV_EMIS_INVW / sd;   // zs = 16 * |x - mean| / sd
+        double nms[MAXM];                                   // zs_k = |fma(x, scale, -mean_k * scale)|: one operation per state
+#pragma unroll
+        for (int k = 0; k < M; ++k) nms[k] = -p.mean[k] * scale;
         const int g_lo = cs, g_hi = cs + n;
         const int b_first = g_lo / TG, b_last = (g_hi - 1) / TG;
 
@@ -428,24 +440,47 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
                 const double x = row[j];
                 if (!is_finite_d(x)) err |= 1;
                 // ---- emissions: g(z_k) from the table ------------------------------------------------
-                double le[MAXM];
+                double le[MAXM], zs[MAXM];
 #pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    const double zs = fabs(x - p.mean[k]) * scale;
-                    double v;
-                    if (zs < (double)(ICNV_EMIS_N - 1)) {
-                        const double m = zs + MAGIC;
-                        const double u = zs - (m - MAGIC);
-                        const int idx = __double2loint(m);
-                        const double2 c01 = tab01[idx], c2f = tab2f[idx];
+                for (int k = 0; k < M; ++k) zs[k] = fabs(fma(x, scale, nms[k]));
+                // the state means are monotone (checked by the launcher), so the largest |x - mean_k| is at an end
+                // state: one range test per gene instead of one per state, and a branch-free lookup block
+                const double LIM = (double)(ICNV_EMIS_N - 1);
+                bool in_table = (zs[0] < LIM) && (zs[M - 1] < LIM);
+                if (!p.means_monotone) {
+#pragma unroll
+                    for (int k = 1; k < M - 1; ++k) in_table = in_table && (zs[k] < LIM);
+                }
+                if (in_table) {
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        const double m = zs[k] + MAGIC;
+                        const double u = zs[k] - (m - MAGIC);
+                        const int idx = __double2loint(m) * TAB_REP;
+                        const double2 c01 = tabA[idx], c2f = tabB[idx];
                         const float hi = fmaf((float)u, __int_as_float(__double2hiint(c2f.y)), __int_as_float(__double2loint(c2f.y)));
-                        v = fma(u, (double)hi, c2f.x);
+                        double v = fma(u, (double)hi, c2f.x);
                         v = fma(u, v, c01.y);
-                        v = fma(u, v, c01.x);
-                    } else {
-                        v = emission_far(x, p.mean[k], sd);
+                        le[k] = fma(u, v, c01.x);
                     }
-                    le[k] = v;
+                } else {   // some state further than 24 sd from x (rare): per-state choice, nmath beyond the table
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        double v;
+                        if (zs[k] < LIM) {
+                            const double m = zs[k] + MAGIC;
+                            const double u = zs[k] - (m - MAGIC);
+                            const int idx = __double2loint(m) * TAB_REP;
+                            const double2 c01 = tabA[idx], c2f = tabB[idx];
+                            const float hi = fmaf((float)u, __int_as_float(__double2hiint(c2f.y)), __int_as_float(__double2loint(c2f.y)));
+                            v = fma(u, (double)hi, c2f.x);
+                            v = fma(u, v, c01.y);
+                            v = fma(u, v, c01.x);
+                        } else {
+                            v = emission_far(x, p.mean[k], sd);
+                        }
+                        le[k] = v;
+                    }
                 }
                 if (i == 0) {
 #pragma unroll
@@ -462,14 +497,14 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
                 }
                 double T1 = t[0];
 #pragma unroll
-                for (int k = 1; k < M; ++k) T1 = fmax(T1, t[k]);
+                for (int k = 1; k < M; ++k) T1 = (t[k] > T1) ? t[k] : T1;   // compare + select: fmax() is ~8 instructions in FP64
                 const int i1 = __double2loint(T1) & 7;
                 // ---- per state: stay (nu[k] + a) or come from the best state (T1).  With a > b the best
                 //      state always stays, so the runner-up is never a third state unless T1 - t[k] is
                 //      itself small - which the second check catches. --------------------------------------
-                uint32_t word = 0;
+                uint32_t moved = 0;   // bit k: the path into state k comes from the best state (sign bit of e, shifted in)
 #pragma unroll
-                for (int k = 0; k < M; ++k) {
+                for (int k = M - 1; k >= 0; --k) {
                     const double d = nu[k] + a;
                     const double e = d - T1;
                     const int he = __double2hiint(e);
@@ -477,9 +512,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
                     mg = min(mg, (unsigned)(he & 0x7fffffff));                      // |stay - from_best|
                     mg = min(mg, (unsigned)__double2hiint(T1 - t[k]) - 1u);         // best vs this state (0 for k == i1 wraps to max)
                     nu[k] = (stay ? d : T1) + le[k];
-                    word |= (uint32_t)(stay ? k : i1) << (3 * k);
+                    moved = __funnelshift_l((uint32_t)he, moved, 1);
                 }
-                bp[(int64_t)i * 32 + lane] = word;
+                bp[(int64_t)i * 32 + lane] = (uint16_t)(moved | ((uint32_t)i1 << 8));
             }
             __syncwarp();
         }
@@ -516,7 +551,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int i = gb + q - g_lo;
-                w[q] = (i >= 1 && i < n) ? bp[(int64_t)i * 32 + lane] : 0u;
+                w[q] = (i >= 1 && i < n) ? (uint32_t)bp[(int64_t)i * 32 + lane] : 0u;
             }
             unsigned long long pack = 0;
 #pragma unroll
@@ -524,7 +559,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 2) viterbi_fast_kernel(const 
                 const int g = gb + q;
                 if (g >= g_lo && g < g_hi) {
                     pack |= (unsigned long long)(y + 1) << (8 * q);
-                    if (g > g_lo) y = (int)((w[q] >> (3 * y)) & 7u);
+                    if (g > g_lo) y = ((w[q] >> y) & 1u) ? (int)(w[q] >> 8) : y;
                 }
             }
             if (active) {
@@ -790,7 +825,10 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
 
     auto fkern = (m == 6) ? viterbi_fast_kernel<6> : viterbi_fast_kernel<3>;
     auto lkern = (m == 6) ? viterbi_list_kernel<6> : viterbi_list_kernel<3>;
-    const size_t smem = sizeof(double) * (4 * (ICNV_EMIS_N + 1) + FAST_WARPS * 2 * 32 * TS);
+    const size_t smem = sizeof(double) * (4 * (ICNV_EMIS_N + 1) * TAB_REP + FAST_WARPS * 2 * 32 * TS);
+    p.means_monotone = 1;
+    for (int k = 1; k + 1 < m; ++k)
+        if ((mean[k] - mean[k - 1]) * (mean[k + 1] - mean[k]) < 0.0) p.means_monotone = 0;
     ICNV_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fkern, FAST_WARPS * 32, smem));
