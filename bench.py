@@ -309,7 +309,7 @@ def main():
         hX = torch.empty((C_local, G), dtype=torch.float64, pin_memory=True)
         hX.copy_(X)
         hY = torch.empty((C_local, G), dtype=torch.float64, pin_memory=True)
-        hS = torch.empty((C_local, G), dtype=torch.int32, pin_memory=True)
+        hS = torch.empty((C_local, G), dtype=torch.uint8, pin_memory=True)   # one byte per state, as the R shim asks for
         torch.cuda.synchronize()
         xn, yn, sn = (t.numpy().T for t in (hX, hY, hS))   # (G, C) Fortran views of the pinned buffers
         if world == 1:
@@ -319,7 +319,7 @@ def main():
                 api.smooth_block(xn, cs, cl, ref_local, apply_log=True, threshold=3.0, window_length=101, out=yn)
                 api.viterbi(yn, cs, cl, Pi, delta, I6_MEAN, I6_SD, out=sn)
             h2d = 2 * C_local * G * 8
-            d2h = C_local * G * 8 + C_local * G * 4
+            d2h = C_local * G * 8 + C_local * G
 
             def fused_step():
                 api.smooth_hmm(xn, cs, cl, ref_local, Pi, delta, I6_MEAN, I6_SD, out=yn, out_states=sn)
@@ -349,7 +349,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": G * C_total / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(dt.item()) * 1e3, "steps": n_e2e,
-               "api": "icnv_smooth_block_f64 + icnv_viterbi_f64 (host pointers, two calls as the R shim makes them)"
+               "api": "icnv_smooth_block_f64 + icnv_viterbi_u8_f64 (host pointers, two calls as the R shim makes them)"
                       if world == 1 else "Engine.smooth_block/viterbi with pinned host tensors"}
         if fused_step is not None:   # one upload instead of two: the optional fused entry point
             fused_step()
@@ -357,9 +357,9 @@ def main():
             for _ in range(n_e2e):
                 fused_step()
             dtf = (time.perf_counter() - t0) / n_e2e
-            e2e["fused_call"] = {"value": G * C_total / dtf, "ms_per_step": dtf * 1e3, "api": "icnv_smooth_hmm_f64",
+            e2e["fused_call"] = {"value": G * C_total / dtf, "ms_per_step": dtf * 1e3, "api": "icnv_smooth_hmm_u8_f64",
                                  "h2d_bytes_per_step": int(C_local * G * 8 * 1.1),
-                                 "d2h_bytes_per_step": int(C_local * G * 12)}
+                                 "d2h_bytes_per_step": int(C_local * G * 9)}
 
     # ---- max over ranks ----------------------------------------------------------------------------------------
     t = torch.tensor([ms_step, ms_smooth, ms_hmm, ms_pass2], dtype=torch.float64, device=X.device)

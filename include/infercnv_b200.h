@@ -11,7 +11,8 @@
  * Conventions
  *   layout   R column-major, X[g + G*c]: g = gene (row, chromosome-ordered), c = cell (column).
  *            A cell's gene vector is contiguous.  Sizes are int64 (R long vectors).
- *   dtype    float64 across the ABI (R `double`); states are int32 (1..m, -1 = not assigned).
+ *   dtype    float64 across the ABI (R `double`); states are int32 (1..m, -1 = not assigned), or one byte each
+ *            (1..m, 255 = not assigned) from the *_u8 variants - a quarter of the bytes over PCIe.
  *   indices  0-based everywhere (the R shim subtracts 1).  Index lists are CSR style:
  *            group k owns grp_idx[grp_off[k] .. grp_off[k+1]).
  *   chromosomes  K contiguous row ranges [chr_start[k], chr_start[k]+chr_len[k]) - the reference
@@ -134,6 +135,13 @@ ICNV_API int icnv_smooth_hmm_f64(const double *X, double *Y, int32_t *states, in
                                  const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window,
                                  int use_bounds, int m, const double *Pi, const double *delta, const double *mean,
                                  const double *sd);
+/* same, states as one byte each (1..m): the host-pointer calls are PCIe-bound, and int32 states are a third of
+ * the bytes this call returns.  This is the variant the R shim binds (it widens to R doubles either way). */
+ICNV_API int icnv_smooth_hmm_u8_f64(const double *X, double *Y, uint8_t *states, int64_t G, int64_t C,
+                                    const int32_t *chr_start, const int32_t *chr_len, int K, const int32_t *grp_off,
+                                    const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window,
+                                    int use_bounds, int m, const double *Pi, const double *delta, const double *mean,
+                                    const double *sd);
 
 /* Viterbi.dthmm.adj, R/inferCNV_HMM.R:1101-1176, batched over the drivers
  * predict_CNV_via_HMM_on_indiv_cells (HMM.R:284-324), ..._on_tumor_subclusters (:345-408),
@@ -150,6 +158,11 @@ ICNV_API int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32
                               const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx,
                               int n_grp, int m, const double *Pi, const double *delta, const double *mean,
                               const double *sd, int32_t *states, double *margins);
+/* same, states as uint8 G x C (1..m, 255 where the int32 variant writes -1) */
+ICNV_API int icnv_viterbi_u8_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start,
+                                 const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx,
+                                 int n_grp, int m, const double *Pi, const double *delta, const double *mean,
+                                 const double *sd, uint8_t *states, double *margins);
 
 /* apply_median_filtering / .median_filter, R/noise_reduction.R:43-113.  Blocks = chromosome x one
  * index list (a subcluster for observations, a whole group for references), cells in list order.

@@ -39,7 +39,10 @@ SIGNATURES = {
                                       c_int]),
     "icnv_smooth_hmm_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, ct.c_double, c_int, c_int,
                                     c_int, _P, _P, _P, _P]),
+    "icnv_smooth_hmm_u8_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, ct.c_double, c_int,
+                                       c_int, c_int, _P, _P, _P, _P]),
     "icnv_viterbi_f64": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "icnv_viterbi_u8_f64": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "icnv_median_filter_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int]),
     "icnv_mean_sd_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P, _P]),
     "icnv_dev_group_partial_sums_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, c_int, c_int, _P, _P]),

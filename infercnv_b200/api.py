@@ -163,7 +163,8 @@ def smooth_block(X, chr_start, chr_len, ref_groups, apply_log=True, threshold=3.
 
 def smooth_hmm(X, chr_start, chr_len, ref_groups, Pi, delta, mean, sd, apply_log=True, threshold=3.0, window_length=101,
                use_bounds=True, out=None, out_states=None):
-    """Fused smooth block + per-cell HMM (one upload of the matrix).  Returns (Y, states)."""
+    """Fused smooth block + per-cell HMM (one upload of the matrix).  Returns (Y, states).  States come back as int32
+    by default; pass a uint8 `out_states` for the one-byte wire format (icnv_smooth_hmm_u8_f64)."""
     X = _f64(X)
     G, C = X.shape
     cs, cl = _i32(chr_start), _i32(chr_len)
@@ -172,13 +173,19 @@ def smooth_hmm(X, chr_start, chr_len, ref_groups, Pi, delta, mean, sd, apply_log
     delta, mean, sd = (np.ascontiguousarray(v, dtype=np.float64) for v in (delta, mean, sd))
     Y = np.empty_like(X, order="F") if out is None else out
     S = np.empty((G, C), dtype=np.int32, order="F") if out_states is None else out_states
-    _lib.check(_lib.load().icnv_smooth_hmm_f64(_p(X), _p(Y), _p(S), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx),
-                                               len(ref_groups), int(bool(apply_log)), float(threshold), int(window_length),
-                                               int(bool(use_bounds)), Pi.shape[0], _p(Pi), _p(delta), _p(mean), _p(sd)))
+    if S.dtype not in (np.int32, np.uint8) or S.shape != (G, C) or not S.flags.f_contiguous:
+        raise ValueError("out_states must be a Fortran-ordered (G, C) int32 or uint8 array")
+    lib = _lib.load()
+    fn = lib.icnv_smooth_hmm_u8_f64 if S.dtype == np.uint8 else lib.icnv_smooth_hmm_f64
+    _lib.check(fn(_p(X), _p(Y), _p(S), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx), len(ref_groups), int(bool(apply_log)),
+                  float(threshold), int(window_length), int(bool(use_bounds)), Pi.shape[0], _p(Pi), _p(delta), _p(mean),
+                  _p(sd)))
     return Y, S
 
 
 def viterbi(X, chr_start, chr_len, Pi, delta, mean, sd, groups=None, want_margins=False, out=None):
+    """States (G, C): int32 with -1 = unassigned by default; a uint8 `out` selects the one-byte wire format
+    (icnv_viterbi_u8_f64, 255 = unassigned)."""
     X = _f64(X)
     G, C = X.shape
     cs, cl = _i32(chr_start), _i32(chr_len)
@@ -201,9 +208,13 @@ def viterbi(X, chr_start, chr_len, Pi, delta, mean, sd, groups=None, want_margin
         if sd.size != m * ng:
             raise ValueError("sd must have m entries per group")
     states = np.empty((G, C), dtype=np.int32, order="F") if out is None else out
+    if states.dtype not in (np.int32, np.uint8) or states.shape != (G, C) or not states.flags.f_contiguous:
+        raise ValueError("out must be a Fortran-ordered (G, C) int32 or uint8 array")
     margins = np.empty((K, nseq), dtype=np.float64, order="F") if want_margins else None
-    _lib.check(_lib.load().icnv_viterbi_f64(_p(X), G, C, _p(cs), _p(cl), K, _p(off), _p(idx), ng, m, _p(Pi), _p(delta),
-                                            _p(mean), _p(sd), _p(states), _p(margins)))
+    lib = _lib.load()
+    fn = lib.icnv_viterbi_u8_f64 if states.dtype == np.uint8 else lib.icnv_viterbi_f64
+    _lib.check(fn(_p(X), G, C, _p(cs), _p(cl), K, _p(off), _p(idx), ng, m, _p(Pi), _p(delta), _p(mean), _p(sd), _p(states),
+                  _p(margins)))
     return (states, margins) if want_margins else states
 
 

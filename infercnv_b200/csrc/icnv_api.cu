@@ -13,6 +13,7 @@
 extern "C" {
 int icnv_dev_invlog_finish_f64(double *means, int64_t n, void *stream);
 int icnv_dev_widen_states(const uint8_t *s, int32_t *out, int64_t n, void *stream);
+int icnv_dev_narrow_states(const int32_t *s, uint8_t *out, int64_t n, void *stream);
 int icnv_dev_scatter_group_states(const uint8_t *gs, int64_t G, int64_t C, const int32_t *grp_of, int32_t *out,
                                   void *stream);
 int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, int op, double param, int *err_flag, void *stream);
@@ -382,7 +383,8 @@ struct HmmModel {
 
 // Y (optional) = smooth block of X; states (optional) = per-cell Viterbi of the block's output (or of X
 // itself when do_smooth == 0).
-static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, int64_t G, int64_t C,
+// states (int32, -1 = unassigned) or states8 (uint8, 255 = unassigned): at most one of them is non-NULL.
+static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, uint8_t *states8, int64_t G, int64_t C,
                          const int32_t *chr_start, const int32_t *chr_len, int K, int do_smooth, const int32_t *grp_off,
                          const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window, int use_bounds,
                          const HmmModel *hmm) {
@@ -427,7 +429,12 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, in
     }
 
     // ---- slabs ------------------------------------------------------------------------------------------
-    const int64_t slab = std::min<int64_t>(SLAB_CELLS, C);
+    int64_t slab_cells = SLAB_CELLS;
+    if (const char *e = getenv("ICNV_SLAB_CELLS")) {   // tuning knob
+        const long v = atol(e);
+        if (v >= 32 && v <= 65536) slab_cells = v;
+    }
+    const int64_t slab = std::min<int64_t>(slab_cells, C);
     const size_t slab_elems = (size_t)G * (size_t)slab;
     double *dIn[2], *dOut[2] = {nullptr, nullptr};
     uint8_t *dSt[2] = {nullptr, nullptr};
@@ -441,8 +448,11 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, in
         }
         if (hmm) {
             dSt[b] = (uint8_t *)scratch(SLOT_SLAB_ST0 + b, slab_elems);
-            dW[b] = (int32_t *)scratch(SLOT_SLAB_W0 + b, sizeof(int32_t) * slab_elems);
-            if (!dSt[b] || !dW[b]) return ICNV_E_NOMEM;
+            if (!dSt[b]) return ICNV_E_NOMEM;
+            if (states) {
+                dW[b] = (int32_t *)scratch(SLOT_SLAB_W0 + b, sizeof(int32_t) * slab_elems);
+                if (!dW[b]) return ICNV_E_NOMEM;
+            }
         }
     }
     const int64_t n_slabs = (C + slab - 1) / slab;
@@ -468,7 +478,7 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, in
             rc = icnv_dev_viterbi_f64(hmm_in, G, nc, chr_start, chr_len, K, hmm->m, hmm->Pi, hmm->delta, hmm->mean, hmm->sd,
                                       0, dSt[b], nullptr, d_flag, sc);
             if (rc) return rc;
-            if ((rc = icnv_dev_widen_states(dSt[b], dW[b], (int64_t)G * nc, sc))) return rc;
+            if (states && (rc = icnv_dev_widen_states(dSt[b], dW[b], (int64_t)G * nc, sc))) return rc;
         }
         ICNV_CUDA(cudaEventRecord(c.ev_comp[b], sc));
         // D2H
@@ -476,6 +486,8 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, in
         if (do_smooth && Y) ICNV_CUDA(cudaMemcpyAsync(Y + G * c0, dOut[b], bytes, cudaMemcpyDeviceToHost, sd));
         if (hmm && states)
             ICNV_CUDA(cudaMemcpyAsync(states + G * c0, dW[b], sizeof(int32_t) * (size_t)G * (size_t)nc, cudaMemcpyDeviceToHost, sd));
+        if (hmm && states8)
+            ICNV_CUDA(cudaMemcpyAsync(states8 + G * c0, dSt[b], (size_t)G * (size_t)nc, cudaMemcpyDeviceToHost, sd));
         ICNV_CUDA(cudaEventRecord(c.ev_d2h[b], sd));
     }
     ICNV_CUDA(cudaStreamSynchronize(sh));
@@ -491,34 +503,51 @@ int icnv_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C, cons
     int rc = validate_chr(G, chr_start, chr_len, K);
     if (rc) return rc;
     if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, false))) return rc;
-    return host_pipeline(c, X, Y, nullptr, G, C, chr_start, chr_len, K, 1, grp_off, grp_idx, n_grp, apply_log, threshold,
-                         window, use_bounds, nullptr);
+    return host_pipeline(c, X, Y, nullptr, nullptr, G, C, chr_start, chr_len, K, 1, grp_off, grp_idx, n_grp, apply_log,
+                         threshold, window, use_bounds, nullptr);
 }
 
 /* Fused smooth block + per-cell HMM in one pass over the matrix: run() steps 4..14 and step 17 for
  * analysis_mode = "cells" with prune_outliers = FALSE (the defaults between them do not touch expr.data).
  * Saves the second upload of the matrix that two separate calls need. */
-int icnv_smooth_hmm_f64(const double *X, double *Y, int32_t *states, int64_t G, int64_t C, const int32_t *chr_start,
-                        const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
-                        int apply_log, double threshold, int window, int use_bounds, int m, const double *Pi,
-                        const double *delta, const double *mean, const double *sd) {
+static int smooth_hmm_impl(const double *X, double *Y, int32_t *states, uint8_t *states8, int64_t G, int64_t C,
+                           const int32_t *chr_start, const int32_t *chr_len, int K, const int32_t *grp_off,
+                           const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window, int use_bounds,
+                           int m, const double *Pi, const double *delta, const double *mean, const double *sd) {
     ICNV_HOST_PROLOGUE();
-    if (!X || !Y || !states || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd)
+    if (!X || !Y || (!states && !states8) || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd)
         return set_error(ICNV_E_BAD_ARG, "icnv_smooth_hmm_f64: bad argument");
     if (m != 6 && m != 3) return set_error(ICNV_E_BAD_ARG, "m must be 6 or 3");
     int rc = validate_chr(G, chr_start, chr_len, K);
     if (rc) return rc;
     if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, false))) return rc;
     HmmModel hm{m, Pi, delta, mean, sd};
-    return host_pipeline(c, X, Y, states, G, C, chr_start, chr_len, K, 1, grp_off, grp_idx, n_grp, apply_log, threshold,
-                         window, use_bounds, &hm);
+    return host_pipeline(c, X, Y, states, states8, G, C, chr_start, chr_len, K, 1, grp_off, grp_idx, n_grp, apply_log,
+                         threshold, window, use_bounds, &hm);
 }
 
-int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
-                     const int32_t *grp_off, const int32_t *grp_idx, int n_grp, int m, const double *Pi,
-                     const double *delta, const double *mean, const double *sd, int32_t *states, double *margins) {
+int icnv_smooth_hmm_f64(const double *X, double *Y, int32_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                        const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                        int apply_log, double threshold, int window, int use_bounds, int m, const double *Pi,
+                        const double *delta, const double *mean, const double *sd) {
+    return smooth_hmm_impl(X, Y, states, nullptr, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, apply_log, threshold,
+                           window, use_bounds, m, Pi, delta, mean, sd);
+}
+
+int icnv_smooth_hmm_u8_f64(const double *X, double *Y, uint8_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                           const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                           int apply_log, double threshold, int window, int use_bounds, int m, const double *Pi,
+                           const double *delta, const double *mean, const double *sd) {
+    return smooth_hmm_impl(X, Y, nullptr, states, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, apply_log, threshold,
+                           window, use_bounds, m, Pi, delta, mean, sd);
+}
+
+static int viterbi_impl(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
+                        const int32_t *grp_off, const int32_t *grp_idx, int n_grp, int m, const double *Pi,
+                        const double *delta, const double *mean, const double *sd, int32_t *states, uint8_t *states8,
+                        double *margins) {
     ICNV_HOST_PROLOGUE();
-    if (!X || !states || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd)
+    if (!X || (!states && !states8) || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd)
         return set_error(ICNV_E_BAD_ARG, "icnv_viterbi_f64: bad argument");
     if (m != 6 && m != 3) return set_error(ICNV_E_BAD_ARG, "m must be 6 or 3");
     int rc = validate_chr(G, chr_start, chr_len, K);
@@ -527,7 +556,8 @@ int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_s
     if (rc) return rc;
     if (n_grp == 0 && !margins) {  // per-cell mode: slab pipeline (copies overlap the kernels)
         HmmModel hm{m, Pi, delta, mean, sd};
-        return host_pipeline(c, X, nullptr, states, G, C, chr_start, chr_len, K, 0, nullptr, nullptr, 0, 0, 0.0, 0, 0, &hm);
+        return host_pipeline(c, X, nullptr, states, states8, G, C, chr_start, chr_len, K, 0, nullptr, nullptr, 0, 0, 0.0, 0, 0,
+                             &hm);
     }
     double *dX;
     if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
@@ -575,8 +605,29 @@ int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_s
             ICNV_CUDA(cudaMemcpyAsync(margins, d_mg, sizeof(double) * (size_t)K * (size_t)n_grp, cudaMemcpyDeviceToHost, st));
         ICNV_CUDA(cudaStreamSynchronize(st));  // grp_of / sdm are stack-lifetime host buffers
     }
-    ICNV_CUDA(cudaMemcpyAsync(states, d_out, sizeof(int32_t) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    if (states) {
+        ICNV_CUDA(cudaMemcpyAsync(states, d_out, sizeof(int32_t) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    } else {
+        uint8_t *d_n = (uint8_t *)scratch(SLOT_SLAB_ST0, (size_t)(G * C));
+        if (!d_n) return ICNV_E_NOMEM;
+        if ((rc = icnv_dev_narrow_states(d_out, d_n, G * C, st))) return rc;
+        ICNV_CUDA(cudaMemcpyAsync(states8, d_n, (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    }
     return check_flag(d_flag, st);
+}
+
+int icnv_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
+                     const int32_t *grp_off, const int32_t *grp_idx, int n_grp, int m, const double *Pi,
+                     const double *delta, const double *mean, const double *sd, int32_t *states, double *margins) {
+    return viterbi_impl(X, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, m, Pi, delta, mean, sd, states, nullptr,
+                        margins);
+}
+
+int icnv_viterbi_u8_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
+                        const int32_t *grp_off, const int32_t *grp_idx, int n_grp, int m, const double *Pi,
+                        const double *delta, const double *mean, const double *sd, uint8_t *states, double *margins) {
+    return viterbi_impl(X, G, C, chr_start, chr_len, K, grp_off, grp_idx, n_grp, m, Pi, delta, mean, sd, nullptr, states,
+                        margins);
 }
 
 int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,

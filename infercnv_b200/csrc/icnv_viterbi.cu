@@ -668,6 +668,17 @@ __global__ void __launch_bounds__(256) widen_states_kernel(const uint8_t *__rest
     }
 }
 
+// int32 states -> uint8 (-1 = unassigned -> 255): the one-byte wire format of the *_u8 host entry points
+__global__ void __launch_bounds__(256) narrow_states_kernel(const int32_t *__restrict__ s, uint8_t *__restrict__ out,
+                                                            int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int32_t v = s[i];
+        out[i] = (v < 0) ? (uint8_t)255 : (uint8_t)v;
+    }
+}
+
 // group-mode broadcast: states[g, c] = grp_states[g, grp_of[c]] or -1 (HMM.R:368, 399)
 __global__ void __launch_bounds__(256) scatter_group_states_kernel(const uint8_t *__restrict__ gs, int64_t G, int64_t C,
                                                                    const int32_t *__restrict__ grp_of,
@@ -693,6 +704,15 @@ int icnv_dev_widen_states(const uint8_t *s, int32_t *out, int64_t n, void *strea
     if (blocks > 148 * 32) blocks = 148 * 32;
     widen_states_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(s, out, n);
     ICNV_CHECK_LAUNCH("widen_states_kernel");
+    return ICNV_OK;
+}
+
+int icnv_dev_narrow_states(const int32_t *s, uint8_t *out, int64_t n, void *stream) {
+    ICNV_REQUIRE_READY();
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    narrow_states_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(s, out, n);
+    ICNV_CHECK_LAUNCH("narrow_states_kernel");
     return ICNV_OK;
 }
 

@@ -130,14 +130,15 @@ SEXP icnvR_viterbi(SEXP expr, SEXP chr_codes, SEXP groups, SEXP Pi, SEXP delta, 
     int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL;
     int K = chr_to_ranges(chr_codes, &cs, &cl);
     int n_grp = Rf_isNull(groups) ? 0 : list_to_csr(groups, &off, &idx);
-    int32_t *st = (int32_t *)malloc(sizeof(int32_t) * (size_t)(G * C));
-    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C)); /* the reference keeps states as doubles (HMM.R:320) */
+    /* one byte per state over PCIe (255 = cell in no group); the reference keeps states as doubles (HMM.R:320) */
+    uint8_t *st = (uint8_t *)malloc((size_t)(G * C));
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
     int rc = (K < 0 || n_grp < 0 || !st) ? ICNV_E_NOMEM
-                                         : icnv_viterbi_f64(REAL(expr), G, C, cs, cl, K, off, idx, n_grp, m, REAL(Pi),
-                                                            REAL(delta), REAL(mean), REAL(sd), st, NULL);
+                                         : icnv_viterbi_u8_f64(REAL(expr), G, C, cs, cl, K, off, idx, n_grp, m, REAL(Pi),
+                                                               REAL(delta), REAL(mean), REAL(sd), st, NULL);
     if (rc == 0) {
         double *out = REAL(ans);
-        for (int64_t i = 0; i < G * C; ++i) out[i] = (double)st[i];
+        for (int64_t i = 0; i < G * C; ++i) out[i] = (st[i] == 255) ? -1.0 : (double)st[i];
     }
     free(cs); free(cl); free(off); free(idx); free(st);
     UNPROTECT(1);

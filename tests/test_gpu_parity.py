@@ -282,6 +282,10 @@ def test_viterbi_group_modes(api, hmm_fixture):
     got = api.viterbi(X, cs, lens, Pi, delta, mean, sds, groups=groups)
     np.testing.assert_array_equal(got, want)
     assert (got[:, 26] == -1).all()
+    # one-byte wire format: same states, 255 where the int32 variant says -1
+    got8 = api.viterbi(X, cs, lens, Pi, delta, mean, sds, groups=groups, out=np.empty((G, C), dtype=np.uint8, order="F"))
+    assert got8.dtype == np.uint8
+    np.testing.assert_array_equal(got8, np.where(want < 0, 255, want))
 
 
 def test_viterbi_nonfinite_is_an_error(api, hmm_fixture):
@@ -342,6 +346,13 @@ def test_multi_slab_host_pipeline_and_fused_call(api, hmm_fixture):
     Y, S = api.smooth_hmm(counts, cs, lens, refs, Pi, delta, mean, sd, window_length=51)
     np.testing.assert_array_equal(Y, got)        # same kernels, same order: bitwise equal
     np.testing.assert_array_equal(S, want_st)
+    # one-byte states (icnv_viterbi_u8_f64 / icnv_smooth_hmm_u8_f64): what the R shim binds
+    S8 = np.empty((G, C), dtype=np.uint8, order="F")
+    np.testing.assert_array_equal(api.viterbi(got, cs, lens, Pi, delta, mean, sd, out=S8), want_st)
+    Y8, S8b = api.smooth_hmm(counts, cs, lens, refs, Pi, delta, mean, sd, window_length=51,
+                             out_states=np.empty((G, C), dtype=np.uint8, order="F"))
+    np.testing.assert_array_equal(Y8, got)
+    np.testing.assert_array_equal(S8b, want_st)
 
 
 # ---- median filter ------------------------------------------------------------------------------------------
