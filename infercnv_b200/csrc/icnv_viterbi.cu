@@ -579,21 +579,35 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) viterbi_fast_kernel(const 
     if (err && p.err_flag) atomicOr(p.err_flag, err);
 }
 
-// Exact re-run of the sequences the certificate rejected: one warp per sequence.  The 32 lanes
-// evaluate the reference-order emissions of 32 genes at a time (the expensive, embarrassingly
-// parallel part) into a per-warp scratch row; lane 0 then runs the short sequential recursion.
+// Exact re-run of the sequences the certificate rejected: one CTA (4 warps) per sequence, reference-order
+// arithmetic throughout.  The emissions - ~1100 FP64 instructions per gene, embarrassingly parallel - are
+// evaluated a chunk of LIST_CH genes at a time into shared memory by warps 1..3 while warp 0 runs the
+// recursion on the previous chunk (double-buffered).  The recursion itself is a dependent chain per gene, so
+// it is spread over the states: lane k of warp 0 owns nu[k], fetches the other states' nu by shuffle, forms
+// nu[j] + logPi[j,k] and takes the first arg-max with a comparison tree that prefers the lower index on ties
+// (which.max, HMM.R:1170).  Backpointers stay in shared memory for sequences of up to LIST_BPS genes.
+constexpr int LIST_NT = 128;
+constexpr int LIST_CH = 96 * 4;
+constexpr int LIST_BPS = 2048;
+
 template <int M>
-__global__ void __launch_bounds__(128) viterbi_list_kernel(const VitParams p, double *__restrict__ le_scratch) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t *__restrict__ bp = p.bp + warp_global * (int64_t)p.max_len * 32;
-    double *__restrict__ leb = le_scratch + warp_global * (int64_t)p.max_len * MAXM;
+__global__ void __launch_bounds__(LIST_NT) viterbi_list_kernel(const VitParams p) {
+    __shared__ double le_s[2][LIST_CH][M];
+    __shared__ uint32_t bp_s[LIST_BPS];
+    __shared__ unsigned long long item_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *__restrict__ bp_g = p.bp + (int64_t)blockIdx.x * 4 * (int64_t)p.max_len * 32;   // this CTA's share of the ring
     const int64_t n_items = (int64_t)min(*p.list_count, p.list_cap);
+    const int kk = lane < M ? lane : 0;   // state owned by this lane of warp 0 (lanes >= M shadow state 0)
+    double lp[M];                         // logPi[j, kk], j = 0..M-1
+#pragma unroll
+    for (int j = 0; j < M; ++j) lp[j] = p.logPi[j * M + kk];
     int err = 0;
     for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(p.counter, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        if (tid == 0) item_s = atomicAdd(p.counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = item_s;
+        __syncthreads();
         if ((int64_t)item >= n_items) break;
         const int2 e = p.list[item];
         const int cs = p.chr_start_orig[e.x], n = p.chr_len_orig[e.x];
@@ -601,58 +615,98 @@ __global__ void __launch_bounds__(128) viterbi_list_kernel(const VitParams p, do
         const double *__restrict__ xcol = p.X + p.G * c + cs;
         uint8_t *__restrict__ scol = p.states + p.G * c + cs;
         const double sd = p.sd_col ? p.sd_col[c] : p.sd;
-        for (int i = lane; i < n; i += 32) {
-            double le[MAXM];
-            emission_exact<M>(xcol[i], p.mean, sd, le);
+        uint32_t *bpw = (n <= LIST_BPS) ? bp_s : bp_g;
+        auto produce = [&](int chunk, int first_thread, int n_threads) {
+            const int base = chunk * LIST_CH;
+            for (int q = tid - first_thread; q < LIST_CH && base + q < n; q += n_threads) {
+                double le[MAXM];
+                emission_exact<M>(xcol[base + q], p.mean, sd, le);
 #pragma unroll
-            for (int k = 0; k < M; ++k) leb[(int64_t)i * MAXM + k] = le[k];
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double nu[MAXM];
-#pragma unroll
-            for (int k = 0; k < M; ++k) nu[k] = __dadd_rn(p.logdelta[k], leb[k]);
-            for (int i = 1; i < n; ++i) {
-                double nn[MAXM];
-                uint32_t word = 0;
-#pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    double best = __dadd_rn(nu[0], p.logPi[0 * M + k]);
-                    int arg = 0;
-#pragma unroll
-                    for (int j = 1; j < M; ++j) {
-                        double v = __dadd_rn(nu[j], p.logPi[j * M + k]);
-                        if (v > best) {
-                            best = v;
-                            arg = j;
-                        }
+                for (int k = 0; k < M; ++k) le_s[chunk & 1][q][k] = le[k];
+            }
+        };
+        const int nch = (n + LIST_CH - 1) / LIST_CH;
+        produce(0, 0, LIST_NT);
+        __syncthreads();
+        double nu = 0.0;
+        for (int s = 0; s < nch; ++s) {
+            if (warp > 0) {
+                if (s + 1 < nch) produce(s + 1, 32, LIST_NT - 32);
+            } else {
+                const int base = s * LIST_CH;
+                const int cnt = min(LIST_CH, n - base);
+                for (int q = 0; q < cnt; ++q) {
+                    const double le = le_s[s & 1][q][kk];
+                    if (base + q == 0) {
+                        nu = __dadd_rn(p.logdelta[kk], le);
+                        continue;
                     }
-                    nn[k] = __dadd_rn(best, leb[(int64_t)i * MAXM + k]);
-                    word |= (uint32_t)arg << (3 * k);
-                }
+                    double v[M];
 #pragma unroll
-                for (int k = 0; k < M; ++k) nu[k] = nn[k];
-                bp[(int64_t)i * 32] = word;
-            }
-            int y = 0;
-            double best = nu[0];
-            bool under = (nu[0] == -INFINITY);
+                    for (int j = 0; j < M; ++j) v[j] = __dadd_rn(__shfl_sync(0xffffffffu, nu, j), lp[j]);
+                    double best;
+                    int arg;
+                    if (M == 6) {
+                        const bool t01 = v[1] > v[0], t23 = v[3] > v[2], t45 = v[5] > v[4];
+                        const double b01 = t01 ? v[1] : v[0], b23 = t23 ? v[3] : v[2], b45 = t45 ? v[5] : v[4];
+                        const int a01 = t01 ? 1 : 0, a23 = t23 ? 3 : 2, a45 = t45 ? 5 : 4;
+                        const bool u = b23 > b01;
+                        const double b03 = u ? b23 : b01;
+                        const int a03 = u ? a23 : a01;
+                        const bool w = b45 > b03;
+                        best = w ? b45 : b03;
+                        arg = w ? a45 : a03;
+                    } else {
+                        best = v[0];
+                        arg = 0;
 #pragma unroll
-            for (int k = 1; k < M; ++k) {
-                under |= (nu[k] == -INFINITY);
-                if (nu[k] > best) {
-                    best = nu[k];
-                    y = k;
+                        for (int j = 1; j < M; ++j)
+                            if (v[j] > best) {
+                                best = v[j];
+                                arg = j;
+                            }
+                    }
+                    nu = __dadd_rn(best, le);
+                    const uint32_t word = __reduce_or_sync(0xffffffffu, lane < M ? (uint32_t)arg << (3 * lane) : 0u);
+                    if (lane == 0) bpw[base + q] = word;
                 }
             }
-            if (under) err |= 2;
-            scol[n - 1] = (uint8_t)(y + 1);
-            for (int i = n - 1; i >= 1; --i) {
-                y = (int)((bp[(int64_t)i * 32] >> (3 * y)) & 7u);
-                scol[i - 1] = (uint8_t)(y + 1);
+            __syncthreads();
+        }
+        if (warp == 0) {
+            double fin[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) fin[k] = __shfl_sync(0xffffffffu, nu, k);
+            if (lane == 0) {
+                int y = 0;
+                double best = fin[0];
+                bool under = (fin[0] == -INFINITY);
+#pragma unroll
+                for (int k = 1; k < M; ++k) {
+                    under |= (fin[k] == -INFINITY);
+                    if (fin[k] > best) {
+                        best = fin[k];
+                        y = k;
+                    }
+                }
+                if (under) err |= 2;
+                scol[n - 1] = (uint8_t)(y + 1);
+                for (int i = n - 1; i >= 1;) {   // backpointer words are fetched 8 at a time: their addresses do not depend on y
+                    const int take = min(8, i);
+                    uint32_t w[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w[q] = (q < take) ? bpw[i - q] : 0u;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < take) {
+                            y = (int)((w[q] >> (3 * y)) & 7u);
+                            scol[i - q - 1] = (uint8_t)(y + 1);
+                        }
+                    i -= take;
+                }
             }
         }
-        __syncwarp();
+        __syncthreads();
     }
     if (err && p.err_flag) atomicOr(p.err_flag, err);
 }
@@ -867,9 +921,7 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     p.list = d_list;
     p.list_count = c.hmm_list_count;
     p.counter = d_counter + 1;
-    double *d_le = (double *)scratch(SLOT_LE, sizeof(double) * (size_t)(list_blocks * 4) * (size_t)max_len * MAXM);
-    if (!d_le) return ICNV_E_NOMEM;
-    lkern<<<(unsigned)list_blocks, 128, 0, st>>>(p, d_le);
+    lkern<<<(unsigned)list_blocks, LIST_NT, 0, st>>>(p);
     ICNV_CHECK_LAUNCH("viterbi_list_kernel");
     return ICNV_OK;
 }

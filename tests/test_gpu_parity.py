@@ -252,6 +252,33 @@ def test_viterbi_fast_path_exact_ties_are_rerun(api):
     print(f"\n[viterbi ties] {reruns} of {2 * C} sequences re-run")
 
 
+@pytest.mark.parametrize("m", [6, 3])
+def test_viterbi_rerun_of_long_sequences(api, hmm_fixture, m):
+    """The exact re-run works a chunk of 384 genes at a time and keeps backpointers in shared memory up to 2048 genes:
+    sequences of 2500 / 700 / 385 genes whose state means sit symmetrically around the data (exact ties everywhere)
+    go through both branches, for i6 and i3."""
+    rng = np.random.default_rng(8)
+    lens = [2500, 700, 385]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(np.sum(lens)), 12
+    X = np.ones((G, C), order="F")
+    X[:, 1::2] += 0.05 * rng.normal(size=(G, C // 2))       # half the cells: generic data
+    X[100:400, ::2] = 1.25
+    X[2600:2900, ::2] = 0.75
+    if m == 6:
+        mean, sd = np.array([0.0, 0.5, 0.75, 1.25, 1.5, 2.0]), np.array([0.2] * 6)
+        Pi, delta = orc.hmm_params(6)
+    else:
+        mean, sd = np.array([0.5, 1.5, 3.0]), np.array([0.25] * 3)
+        Pi, delta = orc.hmm_params(3, 1e-6)
+    want = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sd)
+    got = api.viterbi(X, cs, lens, Pi, delta, mean, sd)
+    reruns = api.hmm_rerun_count()
+    np.testing.assert_array_equal(got, want)
+    assert reruns >= 3 * (C // 2)
+    print(f"\n[viterbi long re-runs, m={m}] {reruns} of {3 * C} sequences re-run")
+
+
 def test_viterbi_unstructured_transition_matrix_and_far_outliers(api, hmm_fixture):
     rng = np.random.default_rng(5)
     G, C = 400, 33
