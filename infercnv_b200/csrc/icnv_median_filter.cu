@@ -5,13 +5,17 @@
 // as in the reference (noise_reduction.R:102-106: half_window + 1).  Even-count windows average
 // the two middle values (median.default).  Reads the un-filtered input throughout.
 //
-// One thread per output element; see median_filter_kernel for the tile / halo / index-array layout.
-// The middle order statistics come from an in-place k-th smallest selection (Wirth/Hoare).
+// One thread per output element.  Window sizes 3..9 (radius 2..5) run median_filter_select_kernel: the tile's halo is
+// staged in shared memory and every thread selects its window's median by counting (icnv_median_select.cuh - no
+// data-dependent partitioning, so the lanes of a warp stay together).  Other window sizes use the generic kernel
+// below (in-place Wirth selection over a private index array).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "icnv_common.cuh"
+#include "icnv_median_select.cuh"
 
 namespace icnv {
 
@@ -110,6 +114,46 @@ __global__ void __launch_bounds__(MF_NT) median_filter_kernel(const MfParams p) 
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
 
+// Tile of 32 genes x 8 list positions, 256 threads; a warp covers 32 consecutive genes of one cell, so its halo reads
+// are consecutive doubles (no bank conflicts) and the per-thread tap lists interleave at 2-byte granularity.
+constexpr int MS_TI = 32, MS_TJ = 8, MS_NT = MS_TI * MS_TJ;
+
+template <int R, typename ListT = unsigned short>
+__global__ void __launch_bounds__(MS_NT) median_filter_select_kernel(const MfParams p) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    constexpr int D = 2 * R + 1, HR = MS_TI + 2 * R, HC = MS_TJ + 2 * R;
+    double *halo = reinterpret_cast<double *>(mf_smem);          // +inf outside the block: never counted
+    double *halo0 = halo + HR * HC;                              // 0 outside the block: for the window moments
+    ListT *list = reinterpret_cast<ListT *>(halo0 + HR * HC);   // [D*D][MS_NT] tap offsets
+    const MfTile gt = p.gene_tiles[blockIdx.y];
+    const MfTile ct = p.cell_tiles[blockIdx.x];
+    const int hi0 = gt.start - R, hj0 = ct.start - R;
+    bool bad = false;
+    for (int e = threadIdx.x; e < HR * HC; e += MS_NT) {
+        const int hr = e % HR, hc = e / HR;
+        const int ii = hi0 + hr, jj = hj0 + hc;
+        double v = INFINITY, v0 = 0.0;
+        if (ii >= gt.lo && ii < gt.hi && jj >= ct.lo && jj < ct.hi) {
+            v = p.X[ii + p.G * (int64_t)p.cells[jj]];
+            bad |= !is_finite_d(v);
+            v0 = v;
+        }
+        halo[e] = v;
+        halo0[e] = v0;
+    }
+    __syncthreads();
+    const int ti = threadIdx.x % MS_TI, tj = threadIdx.x / MS_TI;
+    if (ti < gt.len && tj < ct.len) {
+        const int i = gt.start + ti, j = ct.start + tj;
+        const int xa = max(gt.lo, i - R), xb = min(gt.hi - 1, i + R);
+        const int ya = max(ct.lo, j - R), yb = min(ct.hi - 1, j + R);
+        const int n = (xb - xa + 1) * (yb - ya + 1);
+        const double med = window_median<R, ListT>(halo, halo0, HR, tj * HR + ti, list + threadIdx.x, MS_NT, n);
+        p.Y[i + p.G * (int64_t)p.cells[j]] = med;
+    }
+    if (bad && p.err_flag) atomicExch(p.err_flag, 1);
+}
+
 static void make_tiles(const int32_t *start, const int32_t *len, int nblk, int T, std::vector<MfTile> &out) {
     for (int b = 0; b < nblk; ++b) {
         int lo = start[b], hi = start[b] + len[b];
@@ -132,14 +176,19 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
         return set_error(ICNV_E_BAD_ARG, "window_size must be an odd number >= 3 (noise_reduction.R:48-50)");
     const int r = (window_size + 1) / 2;
     const int W = (2 * r + 1) * (2 * r + 1);
-    const size_t smem = sizeof(double) * (size_t)(MF_TI + 2 * r) * (size_t)(MF_TJ + 2 * r) + sizeof(unsigned short) * (size_t)W * MF_NT;
-    if (smem > (size_t)c.smem_optin || (MF_TI + 2 * r) * (MF_TJ + 2 * r) > 65535)
+    bool select_kernel = (r >= 2 && r <= 5);
+    if (const char *e = getenv("ICNV_MF_KERNEL")) select_kernel = select_kernel && (atoi(e) != 0);   // 0: generic kernel (A/B runs)
+    const int TI = select_kernel ? MS_TI : MF_TI, TJ = select_kernel ? MS_TJ : MF_TJ, NT = TI * TJ;
+    bool list32 = false;
+    if (const char *e = getenv("ICNV_MF_LIST32")) list32 = select_kernel && atoi(e) != 0;   // diagnostic
+    const size_t smem = sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
+                        (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT;
+    if (smem > (size_t)c.smem_optin || (TI + 2 * r) * (TJ + 2 * r) > 65535)
         return set_error(ICNV_E_UNSUPPORTED, "window_size %d needs %zu B of shared memory per CTA", window_size, smem);
     cudaStream_t st = pick_stream(stream);
     // cells in no list are copied through
     ICNV_CUDA(cudaMemcpyAsync(Y, X, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToDevice, st));
     if (n_grp == 0) return ICNV_OK;
-    const int TI = MF_TI, TJ = MF_TJ;
     std::vector<MfTile> gt, ct;
     make_tiles(chr_start, chr_len, K, TI, gt);
     std::vector<int32_t> g_start(n_grp), g_len(n_grp);
@@ -165,8 +214,20 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     ICNV_CUDA(cudaStreamSynchronize(st));  // tile tables are stack-lifetime host buffers
     MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag};
     dim3 grid((unsigned)ct.size(), (unsigned)gt.size());
-    ICNV_CUDA(cudaFuncSetAttribute(median_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    median_filter_kernel<<<grid, MF_NT, smem, st>>>(p);
+    auto launch = [&](auto kern) -> int {
+        ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, NT, smem, st>>>(p);
+        return ICNV_OK;
+    };
+    int lrc;
+    if (!select_kernel) lrc = launch(median_filter_kernel);
+    else if (list32 && r == 5) lrc = launch(median_filter_select_kernel<5, unsigned>);
+    else if (list32 && r == 4) lrc = launch(median_filter_select_kernel<4, unsigned>);
+    else if (r == 2) lrc = launch(median_filter_select_kernel<2>);
+    else if (r == 3) lrc = launch(median_filter_select_kernel<3>);
+    else if (r == 4) lrc = launch(median_filter_select_kernel<4>);
+    else lrc = launch(median_filter_select_kernel<5>);
+    if (lrc) return lrc;
     ICNV_CHECK_LAUNCH("median_filter_kernel");
     return ICNV_OK;
 }
