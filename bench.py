@@ -383,7 +383,7 @@ def main():
             "config": workload_config(args, C_total),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             # dominant kernel of the step: the fused per-cell pipeline over all cells (pass 2)
-            "roofline": {"kernel": "cell_pipeline_kernel pass 2 (%.0f %% of the step)" % (100 * ms_pass2 / ms_step),
+            "roofline": {"kernel": "cell_pipeline3_kernel pass 2 (%.0f %% of the step)" % (100 * ms_pass2 / ms_step),
                          "bound": "hbm", "achieved": ach_p2, "peak": peak, "unit": "GB/s", "frac": ach_p2 / peak,
                          "traffic": ncu_traffic("cell_pipeline_pass2") if (C_local, G) == (10000, 10000) else None,
                          "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
@@ -396,7 +396,7 @@ def main():
                              "algorithmic_bytes_per_launch": hmm_bytes, "ms_per_launch": ms_hmm,
                              "sequences_rerun_in_reference_order_arithmetic": reruns,
                              "sequences": int(C_local * len(cs)),
-                             "note": "9 B per cell-gene; FP64 / shared-memory-table bound"},
+                             "note": "9 B per cell-gene (8 read + 1 state byte); instruction-issue / shared-memory-table bound, see DESIGN.md"},
             "roofline_smooth_block": {"kernels": "group means + cell_pipeline pass 1 (reference cells) + pass 2",
                                       "bound": "hbm", "achieved": smooth_bytes / (ms_smooth * 1e-3) / 1e9, "peak": peak,
                                       "unit": "GB/s", "frac": smooth_bytes / (ms_smooth * 1e-3) / 1e9 / peak,

@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "r01"
+TRAFFIC_ONLY = "--traffic-only" in sys.argv   # on the GPU box, before bench.py: it quotes profiles/<tag>_traffic.json
 KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
@@ -30,8 +31,35 @@ def ncu(args):
     return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
 
 
+traffic = {}
+for f, name in (("cellpipe", "cell_pipeline_pass2"), ("vfast", "viterbi_fast"), ("medfilt", "median_filter_w7")):
+    rep = os.path.join(GO, f"{TAG}_prof_{f}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    raw = list(csv.reader(ncu([rep, "--page", "raw", "--csv"]).splitlines()))
+    hh, uu, vv = raw[0], raw[1], raw[2]
+    d = {}
+    with open(os.path.join(PR, f"{TAG}_{f}_ncu_summary.csv"), "w") as out:
+        out.write("metric,unit,value\n")
+        for i, n in enumerate(hh):
+            if n in KEEP or ("issue_stalled" in n and "per_issue_active" in n):
+                out.write(f"{n},{uu[i]},{vv[i]}\n")
+                d[n] = (uu[i], vv[i])
+    mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
+    b = sum(float(d[k][1]) * mult[d[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    traffic[name] = {"dram_bytes_per_launch": b, "ncu_ms": float(d["gpu__time_duration.sum"][1]),
+                     "source": f"profiles/{TAG}_{f}_ncu_summary.csv (ncu --set full, one launch)"}
+    src = ncu([rep, "--page", "source", "--csv", "--print-source", "cuda,sass"])
+    tmp = os.path.join(GO, f"_{f}_src.csv")
+    open(tmp, "w").write(src)
+    hot = subprocess.run([sys.executable, os.path.join(PR, "src_hotspots.py"), tmp, "30"], capture_output=True, text=True).stdout
+    open(os.path.join(PR, f"{TAG}_{f}_hotspots.txt"), "w").write(hot)
+json.dump(traffic, open(os.path.join(PR, f"{TAG}_traffic.json"), "w"), indent=1)
+if TRAFFIC_ONLY:
+    sys.exit(0)
 for f in ("bench", "bench_reference"):
-    shutil.copy(os.path.join(GO, f"{TAG}_{f}.json"), os.path.join(PR, f"{TAG}_{f}.json"))
+    if os.path.exists(os.path.join(GO, f"{TAG}_{f}.json")):
+        shutil.copy(os.path.join(GO, f"{TAG}_{f}.json"), os.path.join(PR, f"{TAG}_{f}.json"))
 shutil.copy(os.path.join(GO, f"{TAG}_launches.csv"), os.path.join(PR, f"{TAG}_launches.csv"))
 
 rows = list(csv.reader(open(os.path.join(GO, f"{TAG}_launches.csv"))))
@@ -54,28 +82,6 @@ with open(os.path.join(PR, f"{TAG}_launches_summary.txt"), "w") as f:
         share = f"{100 * t / tot:6.1f}%" if k in ours else "   n/a "
         f.write(f"{t:10.3f} {n:8d} {t / n:10.4f} {share}  {k[:120]}\n")
 
-traffic = {}
-for f, name in (("cellpipe", "cell_pipeline_pass2"), ("vfast", "viterbi_fast")):
-    rep = os.path.join(GO, f"{TAG}_prof_{f}.ncu-rep")
-    raw = list(csv.reader(ncu([rep, "--page", "raw", "--csv"]).splitlines()))
-    hh, uu, vv = raw[0], raw[1], raw[2]
-    d = {}
-    with open(os.path.join(PR, f"{TAG}_{f}_ncu_summary.csv"), "w") as out:
-        out.write("metric,unit,value\n")
-        for i, n in enumerate(hh):
-            if n in KEEP or ("issue_stalled" in n and "per_issue_active" in n):
-                out.write(f"{n},{uu[i]},{vv[i]}\n")
-                d[n] = (uu[i], vv[i])
-    mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
-    b = sum(float(d[k][1]) * mult[d[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    traffic[name] = {"dram_bytes_per_launch": b, "ncu_ms": float(d["gpu__time_duration.sum"][1]),
-                     "source": f"profiles/{TAG}_{f}_ncu_summary.csv (ncu --set full, one launch)"}
-    src = ncu([rep, "--page", "source", "--csv", "--print-source", "cuda,sass"])
-    tmp = os.path.join(GO, f"_{f}_src.csv")
-    open(tmp, "w").write(src)
-    hot = subprocess.run([sys.executable, os.path.join(PR, "src_hotspots.py"), tmp, "30"], capture_output=True, text=True).stdout
-    open(os.path.join(PR, f"{TAG}_{f}_hotspots.txt"), "w").write(hot)
-json.dump(traffic, open(os.path.join(PR, f"{TAG}_traffic.json"), "w"), indent=1)
 b = json.load(open(os.path.join(PR, f"{TAG}_bench.json")))
 print("value", b["value"], "ms/step", b["ms_per_step"], "e2e", b["e2e"]["value"], b["e2e"]["ms_per_step"], "fused", b["e2e"]["fused_call"]["ms_per_step"])
 print("roofline", b["roofline"]["frac"], b["roofline"]["ms_per_launch"], "hmm", b["roofline_hmm"]["frac"], b["roofline_hmm"]["ms_per_launch"])
