@@ -84,7 +84,7 @@ def measured_peak_gbs():
 class ClockSampler:
     """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -98,11 +98,15 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0 / t1: wall-clock bounds (time.time()) of the timed region.  The sampler is started before the warm-up
+        steps - nvidia-smi needs longer to start than a short timed region lasts - and only the samples stamped
+        inside [t0, t1] are used; if none landed there the samples under the (identical) warm-up load are reported
+        and `window` says so."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -114,6 +118,21 @@ class ClockSampler:
         try:
             rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
             os.unlink(self.path)
+            rows = [r for r in rows if len(r) >= 9]
+            window = "timed region"
+            if t0 is not None and t1 is not None:
+                import datetime
+
+                def stamp(r):
+                    try:
+                        return datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        return None
+                inside = [r for r in rows if stamp(r) is not None and t0 <= stamp(r) <= t1]
+                if inside:
+                    rows = inside
+                else:
+                    window = "warm-up + timed region (no sample was stamped inside the timed region)"
             sm = [float(r[1]) for r in rows if len(r) >= 9]
             mx = [float(r[2]) for r in rows if len(r) >= 9]
             reasons = set()
@@ -125,7 +144,7 @@ class ClockSampler:
                             reasons.add(name)
             if sm:
                 out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                       "samples": len(sm)}
+                       "samples": len(sm), "window": window}
         except Exception:
             pass
         return out
@@ -206,7 +225,7 @@ def workload_config(args, C_total):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=10000, help="cells per GPU")
@@ -237,6 +256,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     eng = Engine(local_rank)
+    sampler = ClockSampler(local_rank)   # started now: nvidia-smi takes longer to come up than a short timed region lasts
+    if rank == 0:
+        sampler.start()
     G = args.genes
     C_total = args.cells * world
     cs, cl = chr_layout(G)
@@ -276,21 +298,20 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launch_count()
     rec = []
     eng.timing = []
     barrier()
+    wall0 = time.time()
     t_start, t_end = ev(), ev()
     t_start.record()
     for _ in range(args.steps):
         step(rec)
     t_end.record()
     barrier()
+    wall1 = time.time()
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
     ms_step = ms_total / args.steps
     ms_smooth = float(np.mean([a.elapsed_time(b) for a, b, _ in rec]))
