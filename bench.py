@@ -82,16 +82,44 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """Clock / throttle-reason sampling during the timed region (B200_PROFILING.md clocks line).
+
+    Two sources run side by side from before the warm-up until after the timed region: an `nvidia-smi -lms 20`
+    child writing CSV to a temp file, and an NVML polling thread in this process (pynvml, same counters).  Samples
+    are selected by wall-clock stamp inside [t0, t1]; nvidia-smi rows win when any landed there, else the NVML
+    thread's, else everything captured under the (identical) warm-up load - `window` / `source` say which."""
 
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    NVML_BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index: int):
         self.proc = None
         self.path = None
         self.gpu = gpu_index
+        self.nvml_rows = []          # (stamp, sm_mhz, sm_max_mhz, reason mask)
+        self._stop = None
+        self._thread = None
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                try:
+                    self.nvml_rows.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx,
+                                           int(reasons(h))))
+                except Exception:
+                    pass
+                self._stop.wait(0.02)
+        except Exception:
+            return
 
     def start(self):
         try:
@@ -101,52 +129,67 @@ class ClockSampler:
                                           "-lms", "20", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        try:
+            import threading
+            self._stop = threading.Event()
+            self._thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._thread = None
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self, t0=None, t1=None):
-        """t0 / t1: wall-clock bounds (time.time()) of the timed region.  The sampler is started before the warm-up
-        steps - nvidia-smi needs longer to start than a short timed region lasts - and only the samples stamped
-        inside [t0, t1] are used; if none landed there the samples under the (identical) warm-up load are reported
-        and `window` says so."""
+        """t0 / t1: wall-clock bounds (time.time()) of the timed region.  The nvidia-smi child is left running for
+        up to a second past t1 so that its stdio buffer holding the timed region's rows reaches the file before it
+        is terminated."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()      # exact PID we started
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
-            os.unlink(self.path)
-            rows = [r for r in rows if len(r) >= 9]
-            window = "timed region"
-            if t0 is not None and t1 is not None:
-                import datetime
-
-                def stamp(r):
+        if t1 is not None:
+            time.sleep(max(0.0, min(1.0, t1 + 1.0 - time.time())))
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        smi = []                     # (stamp, sm, max, [reason names])
+        if self.proc is not None:
+            try:
+                self.proc.terminate()      # exact PID we started
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+            try:
+                for line in open(self.path):
+                    r = line.strip().split(", ")
+                    if len(r) < 9:
+                        continue
                     try:
-                        return datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        smi.append((self._stamp(r[0]), float(r[1]), float(r[2]),
+                                    [n for n, v in zip(self.NAMES, r[5:9]) if v.strip().lower().startswith("active")]))
                     except ValueError:
-                        return None
-                inside = [r for r in rows if stamp(r) is not None and t0 <= stamp(r) <= t1]
-                if inside:
-                    rows = inside
-                else:
-                    window = "warm-up + timed region (no sample was stamped inside the timed region)"
-            sm = [float(r[1]) for r in rows if len(r) >= 9]
-            mx = [float(r[2]) for r in rows if len(r) >= 9]
-            reasons = set()
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for r in rows:
-                if len(r) >= 9:
-                    for name, v in zip(names, r[5:9]):
-                        if v.strip().lower().startswith("active"):
-                            reasons.add(name)
-            if sm:
-                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                       "samples": len(sm), "window": window}
-        except Exception:
-            pass
+                        continue
+                os.unlink(self.path)
+            except Exception:
+                pass
+        nvml = [(t, sm, mx, [n for n, b in self.NVML_BITS.items() if mask & b]) for t, sm, mx, mask in self.nvml_rows]
+
+        def inside(rows):
+            if t0 is None or t1 is None:
+                return rows
+            return [r for r in rows if r[0] is not None and t0 <= r[0] <= t1]
+        for rows, source, window in ((inside(smi), "nvidia-smi", "timed region"),
+                                     (inside(nvml), "nvml", "timed region"),
+                                     (smi, "nvidia-smi", "warm-up + timed region (no sample was stamped inside the timed region)"),
+                                     (nvml, "nvml", "warm-up + timed region (no sample was stamped inside the timed region)")):
+            if rows:
+                out = {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                       "reasons": sorted({n for r in rows for n in r[3]}), "samples": len(rows), "window": window,
+                       "source": source}
+                break
         return out
 
 
