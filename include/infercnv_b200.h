@@ -182,6 +182,41 @@ ICNV_API int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32
 ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu,
                                       double *sigma);
 
+/* ---- CNV region calling on the HMM state matrix (the step after the Viterbi kernels) ---------------------
+ * States use the one-byte wire format of the *_u8 Viterbi variants: 0..6 = state, 255 = unassigned (R's -1).
+ *
+ * .get_state_consensus, R/inferCNV_HMM.R:977-988: consensus[g + G*k] = the most frequent state of gene g over
+ * the cells of group k; ties go to the smallest state, 255 (-1) ordering before every state, as
+ * table() / order(decreasing=TRUE)[1] do.  A byte outside {0..6, 255}: ICNV_E_BAD_ARG. */
+ICNV_API int icnv_state_consensus_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *grp_off,
+                                     const int32_t *grp_idx, int n_grp, uint8_t *consensus);
+
+/* .define_cnv_gene_regions + .get_cnv_gene_region_bounds, R/inferCNV_HMM.R:1006-1087, for n_seq state sequences
+ * (the columns of seqs, G x n_seq): within every chromosome of >= 2 genes (shorter ones are skipped, :1012-1014)
+ * each run of equal states is one region.  Regions are produced in (sequence, chromosome, position) order - the
+ * order get_predicted_CNV_regions numbers them in (:735-760), so region i (0-based) of a call is "region_<i+1>".
+ * gene_start / gene_stop: gene_order$start / $stop as doubles (exact for integer positions below 2^53).
+ * The call leaves the records in the library and reports their number; icnv_cnv_regions_fetch copies them out. */
+ICNV_API int icnv_cnv_regions_u8(const uint8_t *seqs, int64_t G, int64_t n_seq, const int32_t *chr_start,
+                                 const int32_t *chr_len, int K, const double *gene_start, const double *gene_stop,
+                                 int64_t *n_regions);
+
+/* get_predicted_CNV_regions, R/inferCNV_HMM.R:706-764, in one upload of the state matrix: consensus of every
+ * cell group (reference groups + observation groups for by = "consensus", the subclusters for by = "subcluster",
+ * one single-cell group per cell for by = "cell"; the caller orders the groups as the reference does) followed
+ * by region calling on the n_grp consensus sequences.  consensus: optional G x n_grp output (may be NULL). */
+ICNV_API int icnv_predicted_cnv_regions_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                                           const int32_t *chr_len, int K, const double *gene_start,
+                                           const double *gene_stop, const int32_t *grp_off, const int32_t *grp_idx,
+                                           int n_grp, uint8_t *consensus, int64_t *n_regions);
+
+/* Records of the last icnv_cnv_regions_u8 / icnv_predicted_cnv_regions_u8 call; n_regions must be the number that
+ * call reported.  Per region: seq (0-based sequence / group), chr (0-based chromosome), first_gene .. last_gene
+ * (0-based, inclusive), state (0..6, -1 = unassigned), start = min(gene_start), end = max(gene_stop) over its
+ * genes (:1078-1079).  Any output pointer may be NULL. */
+ICNV_API int icnv_cnv_regions_fetch(int64_t n_regions, int32_t *seq, int32_t *chr, int32_t *first_gene,
+                                    int32_t *last_gene, int32_t *state, double *start, double *end);
+
 /* ---- device-pointer entry points ------------------------------------------------------------- */
 /* All pointers are device pointers on the icnv_init() device unless marked host.  `stream` is a
  * cudaStream_t; NULL = the library's own (non-blocking) stream - pass cudaStreamLegacy ((void*)1) to
@@ -239,6 +274,29 @@ ICNV_API int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G, i
                                         const int32_t *chr_start /*host*/, const int32_t *chr_len /*host*/, int K,
                                         const int32_t *grp_off /*host*/, const int32_t *grp_idx /*host*/, int n_grp,
                                         int window_size, void *stream);
+
+/* Region calling on device-resident states (uint8, column stride lds >= G).
+ * icnv_dev_state_counts_u8: counts[(k*G + g)*8 + slot] = number of cells of group k (d_cells[h_grp_off[k] ..
+ * h_grp_off[k+1]), device) whose state at gene g falls in `slot` (0: unassigned, v+1: state v); integer counts, so
+ * ranks holding different cells of a group can add theirs (all-reduce) before icnv_dev_consensus_from_counts.
+ * err_flag |= 4 on a byte outside {0..6, 255}.  Synchronises the stream. */
+ICNV_API int icnv_dev_state_counts_u8(const uint8_t *S, int64_t G, int64_t lds, const int32_t *d_cells,
+                                      const int32_t *h_grp_off /*host*/, int n_grp, uint32_t *d_counts, int *err_flag,
+                                      void *stream);
+ICNV_API int icnv_dev_consensus_from_counts(const uint32_t *d_counts, int64_t G, int n_grp, uint8_t *d_cons,
+                                            void *stream);
+ICNV_API int icnv_dev_state_consensus_u8(const uint8_t *S, int64_t G, int64_t lds, const int32_t *d_cells,
+                                         const int32_t *h_grp_off /*host*/, int n_grp, uint8_t *d_cons, int *err_flag,
+                                         void *stream);
+/* Regions of the n_seq sequences d_seqs[:, d_cols ? d_cols[s] : s]; synchronises; records stay in the library. */
+ICNV_API int icnv_dev_cnv_regions_u8(const uint8_t *d_seqs, int64_t G, int64_t lds, int64_t n_seq,
+                                     const int32_t *d_cols, const int32_t *chr_start /*host*/,
+                                     const int32_t *chr_len /*host*/, int K, const double *gene_start /*host*/,
+                                     const double *gene_stop /*host*/, int64_t *n_regions /*host*/, void *stream);
+/* Device pointers of the last call's records (valid until the next region call); any output may be NULL. */
+ICNV_API int icnv_dev_cnv_regions_records(int64_t *n, const int32_t **seq, const int32_t **chr,
+                                          const int32_t **first_gene, const int32_t **last_gene,
+                                          const int32_t **state, const double **start, const double **end);
 
 /* Deterministic synthetic workload of SURVEY section 8(d) written straight into HBM: counter-based
  * generator keyed by (seed, global cell, gene), so any sharding of the cells yields identical data.

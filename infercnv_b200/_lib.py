@@ -56,6 +56,15 @@ SIGNATURES = {
     "icnv_combine_cell_stats": (None, [_P, _P, c_i64, c_i64, _P, _P]),
     "icnv_dev_column_stats_f64": (c_int, [_P, c_i64, _P, c_i64, _P, _P, _P]),
     "icnv_dev_median_filter_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, _P]),
+    "icnv_state_consensus_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P]),
+    "icnv_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),
+    "icnv_predicted_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P]),
+    "icnv_cnv_regions_fetch": (c_int, [c_i64, _P, _P, _P, _P, _P, _P, _P]),
+    "icnv_dev_state_counts_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),
+    "icnv_dev_consensus_from_counts": (c_int, [_P, c_i64, c_int, _P, _P]),
+    "icnv_dev_state_consensus_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),
+    "icnv_dev_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, c_i64, _P, _P, _P, c_int, _P, _P, _P, _P]),
+    "icnv_dev_cnv_regions_records": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "icnv_dev_synth_f64": (c_int, [_P, c_i64, c_i64, c_i64, c_i64, _P, _P, c_int, ct.c_uint64, _P]),
 }
 

@@ -236,3 +236,66 @@ def mean_sd(X, cells):
     mu, sg = ct.c_double(), ct.c_double()
     _lib.check(_lib.load().icnv_mean_sd_f64(_p(X), G, C, _p(idx), len(idx), ct.addressof(mu), ct.addressof(sg)))
     return mu.value, sg.value
+
+
+# ---- CNV region calling on the state matrix (R/inferCNV_HMM.R:706-1087) ---------------------------------------
+
+def _u8(a) -> np.ndarray:
+    """State matrix in the one-byte wire format (0..6, 255 = unassigned).  int / float matrices as R holds them
+    (-1 = unassigned) are narrowed here; that is marshalling, like the R shim's double -> byte loop."""
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a[:, None]
+    if a.dtype != np.uint8:
+        if np.any(a != np.floor(a)) or a.min() < -1 or a.max() > 254:
+            raise ValueError("states must be integers in -1..254")
+        a = np.where(a < 0, 255, a).astype(np.uint8)
+    return np.asfortranarray(a)
+
+
+REGION_FIELDS = (("seq", np.int32), ("chr", np.int32), ("first_gene", np.int32), ("last_gene", np.int32),
+                 ("state", np.int32), ("start", np.float64), ("end", np.float64))
+
+
+def _fetch_regions(n: int) -> dict:
+    out = {k: np.empty(n, dtype=dt) for k, dt in REGION_FIELDS}
+    _lib.check(_lib.load().icnv_cnv_regions_fetch(n, *[_p(out[k]) for k, _ in REGION_FIELDS]))
+    return out
+
+
+def state_consensus(states, groups) -> np.ndarray:
+    """Modal state per gene per group, (G, n_grp) uint8 (icnv_state_consensus_u8)."""
+    S = _u8(states)
+    G, C = S.shape
+    off, idx = groups_to_csr(groups)
+    cons = np.empty((G, len(groups)), dtype=np.uint8, order="F")
+    _lib.check(_lib.load().icnv_state_consensus_u8(_p(S), G, C, _p(off), _p(idx), len(groups), _p(cons)))
+    return cons
+
+
+def cnv_regions(seqs, chr_start, chr_len, gene_start, gene_stop) -> dict:
+    """Run-length regions of every column of `seqs` (icnv_cnv_regions_u8 + icnv_cnv_regions_fetch): dict of arrays
+    seq, chr, first_gene, last_gene, state, start, end in (sequence, chromosome, position) order."""
+    S = _u8(seqs)
+    G, n_seq = S.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    gs, ge = (np.ascontiguousarray(v, dtype=np.float64) for v in (gene_start, gene_stop))
+    n = ct.c_int64(0)
+    _lib.check(_lib.load().icnv_cnv_regions_u8(_p(S), G, n_seq, _p(cs), _p(cl), len(cs), _p(gs), _p(ge), ct.addressof(n)))
+    return _fetch_regions(int(n.value))
+
+
+def predicted_cnv_regions(states, chr_start, chr_len, gene_start, gene_stop, groups, want_consensus=False):
+    """Consensus of every cell group + region calling in one upload (icnv_predicted_cnv_regions_u8).
+    Returns the region dict, or (regions, consensus) with want_consensus."""
+    S = _u8(states)
+    G, C = S.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    gs, ge = (np.ascontiguousarray(v, dtype=np.float64) for v in (gene_start, gene_stop))
+    off, idx = groups_to_csr(groups)
+    cons = np.empty((G, len(groups)), dtype=np.uint8, order="F") if want_consensus else None
+    n = ct.c_int64(0)
+    _lib.check(_lib.load().icnv_predicted_cnv_regions_u8(_p(S), G, C, _p(cs), _p(cl), len(cs), _p(gs), _p(ge), _p(off), _p(idx),
+                                                         len(groups), _p(cons), ct.addressof(n)))
+    reg = _fetch_regions(int(n.value))
+    return (reg, cons) if want_consensus else reg

@@ -22,6 +22,14 @@ int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, 
 int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C, const double *sums, double factor,
                                void *stream);
 int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream);
+int icnv_dev_state_consensus_u8(const uint8_t *S, int64_t G, int64_t lds, const int32_t *d_cells, const int32_t *h_grp_off,
+                                int n_grp, uint8_t *d_cons, int *d_flag, void *stream);
+int icnv_dev_cnv_regions_u8(const uint8_t *d_seqs, int64_t G, int64_t lds, int64_t n_seq, const int32_t *d_cols,
+                            const int32_t *chr_start, const int32_t *chr_len, int K, const double *gene_start,
+                            const double *gene_stop, int64_t *n_regions, void *stream);
+int icnv_dev_cnv_regions_records(int64_t *n, const int32_t **seq, const int32_t **chr, const int32_t **first_gene,
+                                 const int32_t **last_gene, const int32_t **state, const double **start,
+                                 const double **end);
 }
 extern "C" ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu,
                                                 double *sigma);
@@ -192,6 +200,7 @@ int icnv_init(int device) {
     c.table_uploaded = false;
     c.math_tables_uploaded = false;
     c.hmm_list_count = nullptr;
+    c.rg_n = 0;
     if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : 1;
     c.ready = true;
     return ICNV_OK;
@@ -648,6 +657,119 @@ int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, con
     if (rc) return rc;
     ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
     return check_flag(d_flag, st);
+}
+
+// ---- CNV region calling on the state matrix (R/inferCNV_HMM.R:706-1087) ----------------------------------------
+
+static int check_state_flag(int *d_flag, cudaStream_t st) {
+    int h = 0;
+    ICNV_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    if (h & 4) return set_error(ICNV_E_BAD_ARG, "state outside 0..6 / 255 in the state matrix");
+    return ICNV_OK;
+}
+
+// upload the states and the cell lists, run the consensus into SLOT_RG_CONS
+static int host_consensus(const uint8_t *states, int64_t G, int64_t C, const int32_t *grp_off, const int32_t *grp_idx,
+                          int n_grp, uint8_t **d_cons_out, cudaStream_t st) {
+    uint8_t *dS = (uint8_t *)scratch(SLOT_STATES, (size_t)(G * C));
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)grp_off[n_grp]);
+    uint8_t *d_cons = (uint8_t *)scratch(SLOT_RG_CONS, (size_t)G * (size_t)n_grp);
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!dS || !d_idx || !d_cons || !d_flag) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(dS, states, (size_t)(G * C), cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, grp_idx, sizeof(int32_t) * (size_t)grp_off[n_grp], cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    int rc = icnv_dev_state_consensus_u8(dS, G, G, d_idx, grp_off, n_grp, d_cons, d_flag, st);
+    if (rc) return rc;
+    if ((rc = check_state_flag(d_flag, st))) return rc;
+    *d_cons_out = d_cons;
+    return ICNV_OK;
+}
+
+int icnv_state_consensus_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *grp_off, const int32_t *grp_idx,
+                            int n_grp, uint8_t *consensus) {
+    ICNV_HOST_PROLOGUE();
+    if (!states || !consensus || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_state_consensus_u8: bad argument");
+    int rc = validate_groups(C, grp_off, grp_idx, n_grp, false);
+    if (rc) return rc;
+    uint8_t *d_cons;
+    if ((rc = host_consensus(states, G, C, grp_off, grp_idx, n_grp, &d_cons, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(consensus, d_cons, (size_t)G * (size_t)n_grp, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+static int validate_gene_positions(const double *gene_start, const double *gene_stop, int64_t G) {
+    if (!gene_start || !gene_stop) return set_error(ICNV_E_BAD_ARG, "gene start / stop positions missing");
+    for (int64_t g = 0; g < G; ++g)
+        if (!std::isfinite(gene_start[g]) || !std::isfinite(gene_stop[g]))
+            return set_error(ICNV_E_NONFINITE, "non-finite gene position at gene %lld", (long long)g);
+    return ICNV_OK;
+}
+
+int icnv_cnv_regions_u8(const uint8_t *seqs, int64_t G, int64_t n_seq, const int32_t *chr_start, const int32_t *chr_len,
+                        int K, const double *gene_start, const double *gene_stop, int64_t *n_regions) {
+    ICNV_HOST_PROLOGUE();
+    if (!seqs || !n_regions || G <= 0 || n_seq <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_cnv_regions_u8: bad argument");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if ((rc = validate_gene_positions(gene_start, gene_stop, G))) return rc;
+    uint8_t *dS = (uint8_t *)scratch(SLOT_STATES, (size_t)(G * n_seq));
+    if (!dS) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(dS, seqs, (size_t)(G * n_seq), cudaMemcpyHostToDevice, st));
+    return icnv_dev_cnv_regions_u8(dS, G, G, n_seq, nullptr, chr_start, chr_len, K, gene_start, gene_stop, n_regions, st);
+}
+
+int icnv_predicted_cnv_regions_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                                  const int32_t *chr_len, int K, const double *gene_start, const double *gene_stop,
+                                  const int32_t *grp_off, const int32_t *grp_idx, int n_grp, uint8_t *consensus,
+                                  int64_t *n_regions) {
+    ICNV_HOST_PROLOGUE();
+    if (!states || !n_regions || G <= 0 || C <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_predicted_cnv_regions_u8: bad argument");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, false))) return rc;
+    if ((rc = validate_gene_positions(gene_start, gene_stop, G))) return rc;
+    bool singletons = !consensus;       // by = "cell": every group is one cell, its consensus is its own column
+    for (int k = 0; k < n_grp && singletons; ++k) singletons = grp_off[k + 1] - grp_off[k] == 1;
+    if (singletons) {
+        uint8_t *dS = (uint8_t *)scratch(SLOT_STATES, (size_t)(G * C));
+        int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_grp);
+        if (!dS || !d_idx) return ICNV_E_NOMEM;
+        ICNV_CUDA(cudaMemcpyAsync(dS, states, (size_t)(G * C), cudaMemcpyHostToDevice, st));
+        ICNV_CUDA(cudaMemcpyAsync(d_idx, grp_idx, sizeof(int32_t) * (size_t)n_grp, cudaMemcpyHostToDevice, st));
+        return icnv_dev_cnv_regions_u8(dS, G, G, n_grp, d_idx, chr_start, chr_len, K, gene_start, gene_stop, n_regions, st);
+    }
+    uint8_t *d_cons;
+    if ((rc = host_consensus(states, G, C, grp_off, grp_idx, n_grp, &d_cons, st))) return rc;
+    if (consensus) ICNV_CUDA(cudaMemcpyAsync(consensus, d_cons, (size_t)G * (size_t)n_grp, cudaMemcpyDeviceToHost, st));
+    return icnv_dev_cnv_regions_u8(d_cons, G, G, n_grp, nullptr, chr_start, chr_len, K, gene_start, gene_stop, n_regions, st);
+}
+
+int icnv_cnv_regions_fetch(int64_t n_regions, int32_t *seq, int32_t *chr, int32_t *first_gene, int32_t *last_gene,
+                           int32_t *state, double *start, double *end) {
+    ICNV_HOST_PROLOGUE();
+    int64_t n = 0;
+    const int32_t *d_seq, *d_chr, *d_first, *d_last, *d_state;
+    const double *d_start, *d_end;
+    int rc = icnv_dev_cnv_regions_records(&n, &d_seq, &d_chr, &d_first, &d_last, &d_state, &d_start, &d_end);
+    if (rc) return rc;
+    if (n_regions != n)
+        return set_error(ICNV_E_BAD_ARG, "icnv_cnv_regions_fetch: %lld records asked for, the last region call produced %lld",
+                         (long long)n_regions, (long long)n);
+    if (n == 0) return ICNV_OK;
+    const size_t bi = sizeof(int32_t) * (size_t)n, bd = sizeof(double) * (size_t)n;
+    if (seq) ICNV_CUDA(cudaMemcpyAsync(seq, d_seq, bi, cudaMemcpyDeviceToHost, st));
+    if (chr) ICNV_CUDA(cudaMemcpyAsync(chr, d_chr, bi, cudaMemcpyDeviceToHost, st));
+    if (first_gene) ICNV_CUDA(cudaMemcpyAsync(first_gene, d_first, bi, cudaMemcpyDeviceToHost, st));
+    if (last_gene) ICNV_CUDA(cudaMemcpyAsync(last_gene, d_last, bi, cudaMemcpyDeviceToHost, st));
+    if (state) ICNV_CUDA(cudaMemcpyAsync(state, d_state, bi, cudaMemcpyDeviceToHost, st));
+    if (start) ICNV_CUDA(cudaMemcpyAsync(start, d_start, bd, cudaMemcpyDeviceToHost, st));
+    if (end) ICNV_CUDA(cudaMemcpyAsync(end, d_end, bd, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
 }
 
 /* normalize_counts_by_seq_depth, R/inferCNV_ops.R:3064-3111: x / colSums * normalize_factor; a negative or NaN

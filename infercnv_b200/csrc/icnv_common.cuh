@@ -41,6 +41,12 @@ enum ScratchSlot {
     SLOT_SLAB_ST0, SLOT_SLAB_ST1,     // uint8 states per slab
     SLOT_SLAB_W0, SLOT_SLAB_W1,       // int32 states per slab
     SLOT_REFX,                        // compact copy of the reference cells' columns
+    SLOT_RG_COUNTS,                   // region calling: per (group, gene) state counts
+    SLOT_RG_CONS,                     // consensus sequences (uint8, G x n_grp)
+    SLOT_RG_CHUNKS,                   // cell chunks of the counting kernel
+    SLOT_RG_GENE,                     // chromosome id per gene, chromosome ranges, gene start / stop
+    SLOT_RG_TILES,                    // per-tile region counts and their scanned offsets
+    SLOT_RG_REC,                      // region records of the last call (kept until fetched)
     SLOT_COUNT
 };
 
@@ -59,6 +65,7 @@ struct Ctx {
     bool table_uploaded = false;
     bool math_tables_uploaded = false;
     unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list
+    int64_t rg_n = 0;                 // number of region records held in SLOT_RG_REC
     std::mutex mu;
 };
 

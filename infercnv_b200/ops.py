@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import copy
 import logging
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -34,6 +35,12 @@ class Infercnv:
     count_data: Optional[np.ndarray] = None
     options: dict = field(default_factory=dict)
     hspike: Optional["Infercnv"] = None                     # @.hspike
+    # the rest of @gene_order and the dimnames of @expr.data: only the region reports read them
+    gene_names: Optional[list] = None                       # rownames(gene_order)
+    gene_order_start: Optional[np.ndarray] = None           # gene_order$start
+    gene_order_stop: Optional[np.ndarray] = None            # gene_order$stop
+    cell_names: Optional[list] = None                       # colnames(expr.data)
+    chr_names: Optional[dict] = None                        # label of each gene_order_chr code (default: str(code))
 
     def __post_init__(self):
         self.expr_data = np.asfortranarray(self.expr_data, dtype=np.float64)
@@ -311,3 +318,117 @@ def assign_HMM_states_to_proxy_expr_vals(infercnv_obj: Infercnv) -> Infercnv:
     out[ok] = lut[st[ok]]
     obj.expr_data = out
     return obj
+
+
+# ---- CNV region reports (R/inferCNV_HMM.R:706-1087) ---------------------------------------------------------------
+
+def _chr_label(obj: Infercnv, code) -> str:
+    if obj.chr_names is not None:
+        return str(obj.chr_names[code])
+    return str(code)
+
+
+def _cell_groups(obj: Infercnv, by: str):
+    """get_predicted_CNV_regions, HMM.R:709-733: ordered (name, cell indices) pairs."""
+    names = obj.cell_names if obj.cell_names is not None else [str(i) for i in range(obj.expr_data.shape[1])]
+    refs, obs = obj.reference_grouped_cell_indices, obj.observation_grouped_cell_indices
+    if by == "consensus":
+        return [(n, np.asarray(v)) for n, v in list(refs.items()) + list(obs.items())]
+    if by == "subcluster":          # unlist(tumor_subclusters[["subclusters"]], recursive=FALSE) -> "group.subcluster"
+        return [("%s.%s" % (g, n), np.asarray(v)) for g, sub in obj.tumor_subclusters["subclusters"].items()
+                for n, v in sub.items()]
+    cells = [int(i) for v in list(refs.values()) + list(obs.values()) for i in v]
+    return [(names[i], np.array([i])) for i in cells]
+
+
+def get_predicted_CNV_regions(infercnv_obj: Infercnv, by: str = "consensus") -> list:
+    """R/inferCNV_HMM.R:706-764 on an object whose expr_data holds the HMM states.  One entry per cell group:
+    {"cell_group_name", "cells" (names), "cnv_ranges": {cnv_name, state, chr, start, end} (one row per region,
+    .get_cnv_gene_region_bounds), "gene_regions": {first_gene, last_gene} (0-based inclusive gene ranges of the same
+    regions; the per-gene data.frames of .define_cnv_gene_regions are these ranges of gene_order)}.
+    Consensus, segmentation and bounds run in libinfercnv_b200 (icnv_predicted_cnv_regions_u8)."""
+    if by not in ("consensus", "subcluster", "cell"):
+        raise ValueError("'arg' should be one of 'consensus', 'subcluster', 'cell'")      # match.arg
+    log.info("get_predicted_CNV_regions(%s)", by)
+    obj = infercnv_obj
+    if obj.tumor_subclusters is None:
+        log.warning("get_predicted_CNV_regions() - no subclusters defined, resetting reporting mode to consensus")
+        by = "consensus"
+    if obj.gene_order_start is None or obj.gene_order_stop is None:
+        raise ValueError("gene_order start / stop are needed for the region bounds")
+    groups = _cell_groups(obj, by)
+    names = obj.cell_names if obj.cell_names is not None else [str(i) for i in range(obj.expr_data.shape[1])]
+    cs, cl = obj.chr_ranges()
+    chr_labels = [_chr_label(obj, obj.gene_order_chr[s]) if n > 0 else "" for s, n in zip(cs, cl)]
+    for name, cells in groups:
+        log.info("-processing cell_group_name: %s, size: %d", name, len(cells))
+    reg = api.predicted_cnv_regions(obj.expr_data, cs, cl, obj.gene_order_start, obj.gene_order_stop,
+                                    [c for _, c in groups])
+    bounds = np.searchsorted(reg["seq"], np.arange(len(groups) + 1))      # records are ordered by group
+    out = []
+    for k, (name, cells) in enumerate(groups):
+        a, b = int(bounds[k]), int(bounds[k + 1])
+        chrs = [chr_labels[c] for c in reg["chr"][a:b]]
+        out.append({
+            "cell_group_name": name,
+            "cells": [names[i] for i in cells],
+            "cnv_ranges": {"cnv_name": ["%s-region_%d" % (ch, i + 1) for ch, i in zip(chrs, range(a, b))],
+                           "state": reg["state"][a:b], "chr": chrs, "start": reg["start"][a:b], "end": reg["end"][a:b]},
+            "gene_regions": {"first_gene": reg["first_gene"][a:b], "last_gene": reg["last_gene"][a:b]},
+        })
+    return out
+
+
+def _num(v) -> str:
+    """write.table: integer-valued numbers print without a decimal point, others with 15 significant digits."""
+    return "%d" % v if float(v) == int(v) else "%.15g" % v
+
+
+def generate_cnv_region_reports(infercnv_obj: Infercnv, output_filename_prefix: str, out_dir: str,
+                                ignore_neutral_state=None, by: str = "consensus") -> None:
+    """R/inferCNV_HMM.R:790-869: writes <prefix>.cell_groupings, .pred_cnv_regions.dat, .pred_cnv_genes.dat and
+    .genes_used.dat as write.table(quote=FALSE, sep="\t") lays them out (the gene order file keeps its row names)."""
+    cnv_regions = get_predicted_CNV_regions(infercnv_obj, by)
+    obj = infercnv_obj
+    G = obj.expr_data.shape[0]
+    gene_names = obj.gene_names if obj.gene_names is not None else [str(i) for i in range(G)]
+    gchr = [_chr_label(obj, c) for c in obj.gene_order_chr]
+    gs, ge = [_num(v) for v in obj.gene_order_start], [_num(v) for v in obj.gene_order_stop]
+    keep = (lambda st: True) if ignore_neutral_state is None else (lambda st: st != ignore_neutral_state)
+
+    path = os.path.join(out_dir, output_filename_prefix + ".cell_groupings")
+    log.info("-writing cell clusters file: %s", path)
+    with open(path, "w") as f:
+        f.write("cell_group_name\tcell\n")
+        for g in cnv_regions:
+            f.writelines("%s\t%s\n" % (g["cell_group_name"], c) for c in g["cells"])
+
+    path = os.path.join(out_dir, output_filename_prefix + ".pred_cnv_regions.dat")
+    log.info("-writing cnv regions file: %s", path)
+    with open(path, "w") as f:
+        f.write("cell_group_name\tcnv_name\tstate\tchr\tstart\tend\n")
+        for g in cnv_regions:
+            r = g["cnv_ranges"]
+            f.writelines("%s\t%s\t%s\t%s\t%s\t%s\n" % (g["cell_group_name"], n, _num(st), ch, _num(a), _num(b))
+                         for n, st, ch, a, b in zip(r["cnv_name"], r["state"], r["chr"], r["start"], r["end"]) if keep(st))
+
+    if by == "cell":
+        log.warning("Note, HMM reporting is being done by 'cell', so this may use more memory, write more info to disk, "
+                    "take more time, ...")
+    path = os.path.join(out_dir, output_filename_prefix + ".pred_cnv_genes.dat")
+    log.info("-writing per-gene cnv report: %s", path)
+    with open(path, "w") as f:
+        f.write("cell_group_name\tgene_region_name\tstate\tgene\tchr\tstart\tend\n")
+        for g in cnv_regions:
+            r, gr = g["cnv_ranges"], g["gene_regions"]
+            for n, st, a, b in zip(r["cnv_name"], r["state"], gr["first_gene"], gr["last_gene"]):
+                if keep(st):
+                    head = "%s\t%s\t%s\t" % (g["cell_group_name"], n, _num(st))
+                    f.writelines(head + "%s\t%s\t%s\t%s\n" % (gene_names[i], gchr[i], gs[i], ge[i])
+                                 for i in range(int(a), int(b) + 1))
+
+    path = os.path.join(out_dir, output_filename_prefix + ".genes_used.dat")
+    log.info("-writing gene ordering info: %s", path)
+    with open(path, "w") as f:
+        f.write("chr\tstart\tstop\n")
+        f.writelines("%s\t%s\t%s\t%s\n" % (gene_names[i], gchr[i], gs[i], ge[i]) for i in range(G))

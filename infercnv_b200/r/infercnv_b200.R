@@ -194,11 +194,63 @@ b200_clear_noise_via_ref_mean_sd <- function(infercnv_obj, sd_amplifier=1.5, noi
     infercnv_obj
 }
 
+## get_predicted_CNV_regions, R/inferCNV_HMM.R:706-764: consensus state per cell group, run-length regions per
+## chromosome and their bounds from ONE library call; the returned list has the reference's shape
+## (cell_group_name, cells, gene_regions = named list of per-gene data.frames, cnv_ranges = data.frame), so
+## generate_cnv_region_reports (HMM.R:790-869) and everything downstream of its files run unchanged.
+b200_get_predicted_CNV_regions <- function(infercnv_obj, by=c("consensus", "subcluster", "cell")) {
+    by <- match.arg(by)
+    orig <- .icnv_env$orig$get_predicted_CNV_regions
+    m <- infercnv_obj@expr.data
+    codes <- .icnv_chr_codes(infercnv_obj)
+    go <- infercnv_obj@gene_order
+    if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes) || anyNA(go$start) || anyNA(go$stop)) return(orig(infercnv_obj, by))
+    futile.logger::flog.info(sprintf("get_predicted_CNV_regions(%s) (B200)", by))
+    if (is.null(infercnv_obj@tumor_subclusters)) {
+        futile.logger::flog.warn("get_predicted_CNV_regions() - no subclusters defined, resetting reporting mode to consensus")
+        by <- "consensus"
+    }
+    if (by == "consensus") {                                                      # HMM.R:721-723
+        cell_groups <- c(infercnv_obj@reference_grouped_cell_indices, infercnv_obj@observation_grouped_cell_indices)
+    } else if (by == "subcluster") {                                              # HMM.R:724-725
+        cell_groups <- unlist(infercnv_obj@tumor_subclusters[["subclusters"]], recursive=FALSE)
+    } else {                                                                      # HMM.R:726-729
+        cells <- c(unlist(infercnv_obj@reference_grouped_cell_indices, use.names=FALSE),
+                   unlist(infercnv_obj@observation_grouped_cell_indices, use.names=FALSE))
+        cell_groups <- as.list(cells)
+        names(cell_groups) <- colnames(m)[cells]
+    }
+    res <- tryCatch(.Call("icnvR_cnv_regions", m, codes, as.double(go$start), as.double(go$stop),
+                          lapply(cell_groups, as.integer)), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, by))
+    names(res) <- c("seq", "chr", "first_gene", "last_gene", "state", "start", "end")
+    chr_levels <- unique(go$chr)                       # order of appearance = the order of the chromosome ranges
+    gene_names <- rownames(go)
+    cnv_name <- sprintf("%s-region_%d", as.character(chr_levels[res$chr]), seq_along(res$seq))   # running counter, :758
+    if (is.integer(go$start) && is.integer(go$stop)) { res$start <- as.integer(res$start); res$end <- as.integer(res$end) }
+    by_group <- split(seq_along(res$seq), factor(res$seq, levels = seq_along(cell_groups)))
+    lapply(seq_along(cell_groups), function(k) {
+        sel <- by_group[[k]]
+        futile.logger::flog.info(sprintf("-processing cell_group_name: %s, size: %d", names(cell_groups)[k], length(cell_groups[[k]])))
+        gene_regions <- lapply(sel, function(i) {
+            g <- res$first_gene[i]:res$last_gene[i]
+            data.frame(state = res$state[i], gene = gene_names[g], chr = go$chr[g], start = go$start[g], end = go$stop[g])
+        })
+        names(gene_regions) <- cnv_name[sel]
+        list(cell_group_name = names(cell_groups)[k],
+             cells = colnames(m)[cell_groups[[k]]],
+             gene_regions = gene_regions,
+             cnv_ranges = data.frame(cnv_name = cnv_name[sel], state = res$state[sel], chr = chr_levels[res$chr[sel]],
+                                     start = res$start[sel], end = res$end[sel]))
+    })
+}
+
 infercnvb200_install <- function() {
     fns <- c("subtract_ref_expr_from_obs", "smooth_by_chromosome", "center_cell_expr_across_chromosome",
              "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
              "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
-             "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd")
+             "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd",
+             "get_predicted_CNV_regions")
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")

@@ -214,6 +214,55 @@ SEXP icnvR_clear_noise(SEXP expr, SEXP cells, SEXP sd_amplifier) {
     return ans;
 }
 
+/* get_predicted_CNV_regions (HMM.R:706-764): consensus state per cell group, run-length regions per chromosome and
+ * their bounds in one call.  `states` is the numeric state matrix of the HMM object (-1 = unassigned); it crosses
+ * PCIe as one byte per entry.  Returns list(seq, chr, first_gene, last_gene, state, start, end), one entry per
+ * region in the reference's numbering order, indices 1-based. */
+SEXP icnvR_cnv_regions(SEXP states, SEXP chr_codes, SEXP gene_start, SEXP gene_stop, SEXP groups) {
+    SEXP dim = Rf_getAttrib(states, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    int n_grp = list_to_csr(groups, &off, &idx);
+    uint8_t *st = (uint8_t *)malloc((size_t)(G * C));
+    int64_t n = 0;
+    int not_states = 0;
+    int rc = (K < 0 || n_grp < 0 || !st) ? ICNV_E_NOMEM : 0;
+    if (rc == 0) {
+        const double *x = REAL(states);
+        for (int64_t i = 0; i < G * C && !not_states; ++i) {
+            if (x[i] == -1.0) st[i] = 255;
+            else if (x[i] >= 0.0 && x[i] <= 6.0 && x[i] == (double)(int)x[i]) st[i] = (uint8_t)x[i];
+            else not_states = 1;            /* not a state matrix: the R wrapper falls back to the reference code */
+        }
+    }
+    if (rc == 0 && !not_states)
+        rc = icnv_predicted_cnv_regions_u8(st, G, C, cs, cl, K, REAL(gene_start), REAL(gene_stop), off, idx, n_grp, NULL, &n);
+    free(cs); free(cl); free(off); free(idx); free(st);
+    if (not_states) Rf_error("infercnv_b200: expr.data does not hold HMM states (-1, 0..6)");
+    fail_if(rc);
+    SEXP ans = PROTECT(Rf_allocVector(VECSXP, 7));
+    SEXP v[7];
+    for (int k = 0; k < 7; ++k) {
+        v[k] = Rf_allocVector(k < 4 ? INTSXP : REALSXP, (long)n);
+        SET_VECTOR_ELT(ans, k, v[k]);
+    }
+    int32_t *state = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    rc = !state ? ICNV_E_NOMEM
+                : icnv_cnv_regions_fetch(n, INTEGER(v[0]), INTEGER(v[1]), INTEGER(v[2]), INTEGER(v[3]), state, REAL(v[5]),
+                                         REAL(v[6]));
+    if (rc == 0) {
+        for (int64_t i = 0; i < n; ++i) {
+            for (int k = 0; k < 4; ++k) INTEGER(v[k])[i] += 1;      /* R is 1-based */
+            REAL(v[4])[i] = (double)state[i];                      /* states stay numeric, as in @expr.data */
+        }
+    }
+    free(state);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
 SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
 
 static const R_CallMethodDef call_methods[] = {
@@ -222,6 +271,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_viterbi", (DL_FUNC)&icnvR_viterbi, 7},           {"icnvR_median_filter", (DL_FUNC)&icnvR_median_filter, 4},
     {"icnvR_mean_sd", (DL_FUNC)&icnvR_mean_sd, 2},           {"icnvR_available", (DL_FUNC)&icnvR_available, 0},
     {"icnvR_normalize", (DL_FUNC)&icnvR_normalize, 2},       {"icnvR_clear_noise", (DL_FUNC)&icnvR_clear_noise, 3},
+    {"icnvR_cnv_regions", (DL_FUNC)&icnvR_cnv_regions, 5},
     {NULL, NULL, 0}};
 
 void R_init_infercnvb200_shim(DllInfo *dll) {

@@ -8,6 +8,8 @@ typedef void *(*DL_FUNC)(void);
 typedef struct _DllInfo DllInfo;
 typedef struct { const char *name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
 #define REALSXP 14
+#define INTSXP 13
+#define VECSXP 19
 #define FALSE 0
 extern SEXP R_DimSymbol;
 SEXP Rf_getAttrib(SEXP, SEXP);
@@ -15,6 +17,7 @@ int *INTEGER(SEXP);
 double *REAL(SEXP);
 int Rf_length(SEXP);
 SEXP VECTOR_ELT(SEXP, long);
+SEXP SET_VECTOR_ELT(SEXP, long, SEXP);
 SEXP Rf_allocMatrix(unsigned, int, int);
 SEXP Rf_allocVector(unsigned, long);
 SEXP Rf_protect(SEXP);

@@ -21,6 +21,14 @@ Outputs (all under tests/golden/, committed):
                          -> 8508 genes x 184 cells.  Stored as the filtered raw count matrix so
                          both the oracle and the CUDA path start from identical bytes.
 
+* cnv_regions_fixture.npz - the reference's own known answer for CNV region calling (R/inferCNV_HMM.R:706-1087):
+                         `data/HMM_states.rda` (state matrix, 4613 x 20) is the input; `data/mcmc_obj.rda`
+                         carries what `generate_cnv_region_reports(by="subcluster")` made of it in the
+                         reference's run - `@cnv_regions` (region names, numbered by the running region
+                         counter), `@cell_gene[[i]]$Genes` / `$Cells` (the genes and cells of every
+                         non-neutral region, read back from `.pred_cnv_genes.dat` /
+                         `.cell_groupings`), plus the `gene_order` and `tumor_subclusters` it ran with.
+
 Nothing here is reference source code: it is the reference's *data*, reduced to the matrices the
 hot path consumes, plus this script that made them.
 """
@@ -83,6 +91,46 @@ def hmm_fixture(ref: str) -> None:
         hmm_states=np.asfortranarray(states.astype(np.int8)),
     )
     print("hmm_fixture.npz mu", mu, "sd", 1.0 / np.sqrt(sig), "states", states.shape)
+
+
+def cnv_regions_fixture(ref: str) -> None:
+    m = read_rda(os.path.join(ref, "data/mcmc_obj.rda"))["mcmc_obj"]
+    h = read_rda(os.path.join(ref, "data/HMM_states.rda"))["HMM_states"]
+    states = as_matrix(h)
+    gene_names, cell_names = (np.array(v.value) for v in h.attr["dimnames"].value)
+    go = m.attr["gene_order"]
+    chr_f = go.value[0]
+    assert list(go.attr["row.names"].value) == list(gene_names)
+    sub = m.attr["tumor_subclusters"].value[1]          # $subclusters: list(tumor = list(tumor_s1 = <cells>))
+    sub_names, sub_cells = [], []
+    for gname, grp in zip(sub.attr["names"].value, sub.value):
+        for sname, sc in zip(grp.attr["names"].value, grp.value):
+            sub_names.append(f"{gname}.{sname}")          # unlist(recursive=FALSE) naming, HMM.R:718
+            sub_cells.append(np.asarray(sc.value, dtype=np.int32))
+    levels = m.attr["cnv_regions"].attr["levels"].value
+    names, first, last, count, cells = [], [], [], [], []
+    for cg in m.attr["cell_gene"].value:
+        reg, genes, cl = cg.value
+        names.append(levels[int(reg.value[0]) - 1])
+        g = np.asarray(genes.value)
+        assert np.array_equal(g, np.arange(g[0], g[-1] + 1)), "a region is a run of consecutive genes"
+        first.append(g[0]); last.append(g[-1]); count.append(len(g))
+        cells.append(np.asarray(cl.value, dtype=np.int32))
+    np.savez_compressed(
+        os.path.join(HERE, "cnv_regions_fixture.npz"),
+        hmm_states=np.asfortranarray(states.astype(np.uint8)),
+        gene_names=gene_names, cell_names=cell_names,
+        chr_codes=np.asarray(chr_f.value, dtype=np.int32), chr_levels=np.array(chr_f.attr["levels"].value),
+        gene_start=np.asarray(go.value[1].value, dtype=np.int64), gene_stop=np.asarray(go.value[2].value, dtype=np.int64),
+        subcluster_names=np.array(sub_names), subcluster_cells=np.concatenate(sub_cells),      # 1-based, as in R
+        subcluster_off=np.cumsum([0] + [len(v) for v in sub_cells]).astype(np.int32),
+        ref_idx=np.asarray(m.attr["reference_grouped_cell_indices"].value[0].value, dtype=np.int32),
+        obs_idx=np.asarray(m.attr["observation_grouped_cell_indices"].value[0].value, dtype=np.int32),
+        region_names=np.array(names), region_first_gene=np.array(first, dtype=np.int32),       # 1-based, as in R
+        region_last_gene=np.array(last, dtype=np.int32), region_n_genes=np.array(count, dtype=np.int32),
+        region_cells=np.stack(cells),
+    )
+    print("cnv_regions_fixture.npz states", states.shape, "non-neutral regions", names)
 
 
 def oligodendroglioma(ref: str) -> None:
@@ -169,4 +217,5 @@ if __name__ == "__main__":
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     example_object(ref)
     hmm_fixture(ref)
+    cnv_regions_fixture(ref)
     oligodendroglioma(ref)

@@ -21,5 +21,5 @@ def test_r_wrappers_name_every_replaced_function():
     for fn in ["subtract_ref_expr_from_obs", "smooth_by_chromosome", "center_cell_expr_across_chromosome",
                "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
                "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
-               "apply_median_filtering"]:
+               "apply_median_filtering", "get_predicted_CNV_regions"]:
         assert f"b200_{fn} <- function" in src and f'"{fn}"' in src
