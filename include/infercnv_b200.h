@@ -182,6 +182,32 @@ ICNV_API int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32
 ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu,
                                       double *sigma);
 
+/* ---- gene filters and counts ingest: the steps in front of the path (run() steps 2-3) ------------------------
+ * Per-gene statistics of a dense G x C matrix for the two gene filters of run() step 2:
+ *   sums[g]  = sum over all cells; means[g] = rowMeans as R rounds it (long-double quotient -> double), what
+ *              .below_min_mean_expr_cutoff compares with the cutoff (R/inferCNV_ops.R:2149-2158);
+ *   n_pos[g] = number of cells with x > 0 (NaN counts as not expressed), what require_above_min_cells_ref compares
+ *              with min_cells_per_gene (ops.R:2177-2209).
+ * Any of the three outputs may be NULL. */
+ICNV_API int icnv_gene_stats_f64(const double *X, int64_t G, int64_t C, double *sums, int32_t *n_pos, double *means);
+
+/* remove_genes, R/inferCNV.R:445-457: Y (n_keep x C) = X[keep, ]; keep = increasing 0-based row indices. */
+ICNV_API int icnv_remove_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *keep, int64_t n_keep,
+                                   double *Y);
+
+/* The same statistics for a compressed-sparse-column counts matrix (a dgCMatrix's @p, @i, @x; the reference accepts
+ * one as raw_counts_matrix, R/inferCNV.R:158-160): p[C+1] column pointers, i[nnz] 0-based row indices, x[nnz]. */
+ICNV_API int icnv_csc_gene_stats_f64(const int32_t *p, const int32_t *i, const double *x, int64_t G, int64_t C,
+                                     double *sums, int32_t *n_pos, double *means);
+
+/* Gene removal + normalize_counts_by_seq_depth (ops.R:3064-3111) straight from the compressed columns: Y, dense
+ * G_out x C (G_out = n_keep, or G when keep == NULL), = (x / colSums over the kept genes) * normalize_factor; a
+ * negative or NaN factor means "median of the column sums" (the reference's NA default).  The matrix crosses PCIe
+ * as 12 bytes per stored count instead of 8 bytes per cell-gene.  col_sums: optional C doubles. */
+ICNV_API int icnv_csc_normalize_f64(const int32_t *p, const int32_t *i, const double *x, int64_t G, int64_t C,
+                                    const int32_t *keep, int64_t n_keep, double normalize_factor, double *Y,
+                                    double *col_sums);
+
 /* ---- CNV region calling on the HMM state matrix (the step after the Viterbi kernels) ---------------------
  * States use the one-byte wire format of the *_u8 Viterbi variants: 0..6 = state, 255 = unassigned (R's -1).
  *

@@ -299,3 +299,58 @@ def predicted_cnv_regions(states, chr_start, chr_len, gene_start, gene_stop, gro
                                                          len(groups), _p(cons), ct.addressof(n)))
     reg = _fetch_regions(int(n.value))
     return (reg, cons) if want_consensus else reg
+
+
+# ---- gene filters and counts ingest (run() steps 2-3) -----------------------------------------------------------
+
+def gene_stats(X):
+    """Per-gene (sums, n_pos, means) of a dense matrix (icnv_gene_stats_f64): what .below_min_mean_expr_cutoff and
+    require_above_min_cells_ref compare with their thresholds."""
+    X = _f64(X)
+    G, C = X.shape
+    sums, means = np.empty(G), np.empty(G)
+    n_pos = np.empty(G, dtype=np.int32)
+    _lib.check(_lib.load().icnv_gene_stats_f64(_p(X), G, C, _p(sums), _p(n_pos), _p(means)))
+    return sums, n_pos, means
+
+
+def remove_genes(X, keep) -> np.ndarray:
+    """X[keep, ] for increasing row indices `keep` (icnv_remove_genes_f64)."""
+    X = _f64(X)
+    G, C = X.shape
+    keep = _i32(keep)
+    Y = np.empty((len(keep), C), dtype=np.float64, order="F")
+    _lib.check(_lib.load().icnv_remove_genes_f64(_p(X), G, C, _p(keep), len(keep), _p(Y)))
+    return Y
+
+
+def _csc(p, i, x):
+    p, i = _i32(p), _i32(i)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if len(i) != len(x) or len(p) < 2 or p[-1] != len(x):
+        raise ValueError("inconsistent compressed-column arrays")
+    return p, i, x
+
+
+def csc_gene_stats(p, i, x, n_genes):
+    """gene_stats for a compressed-sparse-column counts matrix (dgCMatrix @p / @i / @x)."""
+    p, i, x = _csc(p, i, x)
+    G, C = int(n_genes), len(p) - 1
+    sums, means = np.empty(G), np.empty(G)
+    n_pos = np.empty(G, dtype=np.int32)
+    _lib.check(_lib.load().icnv_csc_gene_stats_f64(_p(p), _p(i), _p(x), G, C, _p(sums), _p(n_pos), _p(means)))
+    return sums, n_pos, means
+
+
+def csc_normalize(p, i, x, n_genes, keep=None, normalize_factor=None, want_col_sums=False):
+    """Dense depth-normalised matrix (kept genes x cells) straight from compressed columns (icnv_csc_normalize_f64)."""
+    p, i, x = _csc(p, i, x)
+    G, C = int(n_genes), len(p) - 1
+    keep = None if keep is None else _i32(keep)
+    G_out = G if keep is None else len(keep)
+    Y = np.empty((G_out, C), dtype=np.float64, order="F")
+    cs = np.empty(C) if want_col_sums else None
+    nf = -1.0 if normalize_factor is None else float(normalize_factor)
+    _lib.check(_lib.load().icnv_csc_normalize_f64(_p(p), _p(i), _p(x), G, C, _p(keep), 0 if keep is None else len(keep), nf,
+                                                  _p(Y), _p(cs)))
+    return (Y, cs) if want_col_sums else Y

@@ -22,6 +22,15 @@ int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, 
 int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C, const double *sums, double factor,
                                void *stream);
 int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream);
+int icnv_dev_gene_stats_f64(const double *X, int64_t G, int64_t ldx, int64_t C, double *d_sums, int32_t *d_npos, void *stream);
+int icnv_dev_gather_rows_f64(const double *X, int64_t ldx, const int32_t *d_keep, int64_t n_keep, double *Y, int64_t C,
+                             void *stream);
+int icnv_dev_csc_gene_stats_f64(const int32_t *d_i, const double *d_x, int64_t nnz, int64_t G, double *d_sums,
+                                int32_t *d_npos, void *stream);
+int icnv_dev_csc_col_sums_f64(const int32_t *d_p, const int32_t *d_i, const double *d_x, const int32_t *d_keep_map,
+                              int64_t C, double *d_cs, void *stream);
+int icnv_dev_csc_expand_f64(const int32_t *d_p, const int32_t *d_i, const double *d_x, const int32_t *d_keep_map,
+                            int64_t G_out, int64_t C, const double *d_cs, double factor, double *Y, void *stream);
 int icnv_dev_state_consensus_u8(const uint8_t *S, int64_t G, int64_t lds, const int32_t *d_cells, const int32_t *h_grp_off,
                                 int n_grp, uint8_t *d_cons, int *d_flag, void *stream);
 int icnv_dev_cnv_regions_u8(const uint8_t *d_seqs, int64_t G, int64_t lds, int64_t n_seq, const int32_t *d_cols,
@@ -657,6 +666,152 @@ int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64_t C, con
     if (rc) return rc;
     ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
     return check_flag(d_flag, st);
+}
+
+// ---- gene filters and counts ingest (run() steps 2-3; R/inferCNV_ops.R:2124-2209, 3064-3111) ------------------------
+
+// rowMeans as R computes it: a long-double quotient rounded to double (the sums of count data are exact integers)
+static void means_from_sums(const double *sums, int64_t G, int64_t C, double *means) {
+    for (int64_t g = 0; g < G; ++g) means[g] = (double)((long double)sums[g] / (long double)C);
+}
+
+static int download_gene_stats(const double *d_sums, const int32_t *d_npos, int64_t G, int64_t C, double *sums,
+                               int32_t *n_pos, double *means, cudaStream_t st) {
+    std::vector<double> tmp;
+    double *hs = sums;
+    if (!hs) {
+        tmp.resize((size_t)G);
+        hs = tmp.data();
+    }
+    ICNV_CUDA(cudaMemcpyAsync(hs, d_sums, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, st));
+    if (n_pos) ICNV_CUDA(cudaMemcpyAsync(n_pos, d_npos, sizeof(int32_t) * (size_t)G, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    if (means) means_from_sums(hs, G, C, means);
+    return ICNV_OK;
+}
+
+int icnv_gene_stats_f64(const double *X, int64_t G, int64_t C, double *sums, int32_t *n_pos, double *means) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || G <= 0 || C <= 0 || (!sums && !n_pos && !means)) return set_error(ICNV_E_BAD_ARG, "icnv_gene_stats_f64: bad argument");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *d_sums = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G);
+    int32_t *d_npos = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * (size_t)G);
+    if (!d_sums || !d_npos) return ICNV_E_NOMEM;
+    if ((rc = icnv_dev_gene_stats_f64(dX, G, G, C, d_sums, d_npos, st))) return rc;
+    return download_gene_stats(d_sums, d_npos, G, C, sums, n_pos, means, st);
+}
+
+static int validate_keep(const int32_t *keep, int64_t n_keep, int64_t G) {
+    if (!keep || n_keep <= 0 || n_keep > G) return set_error(ICNV_E_BAD_ARG, "the list of genes to keep is empty or too long");
+    for (int64_t i = 0; i < n_keep; ++i)
+        if (keep[i] < 0 || keep[i] >= G || (i > 0 && keep[i] <= keep[i - 1]))
+            return set_error(ICNV_E_BAD_ARG, "genes to keep must be increasing row indices in [0, G)");
+    return ICNV_OK;
+}
+
+int icnv_remove_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *keep, int64_t n_keep, double *Y) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_remove_genes_f64: bad argument");
+    int rc = validate_keep(keep, n_keep, G);
+    if (rc) return rc;
+    double *dX;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(n_keep * C));
+    int32_t *d_keep = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_keep);
+    if (!dY || !d_keep) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_keep, keep, sizeof(int32_t) * (size_t)n_keep, cudaMemcpyHostToDevice, st));
+    if ((rc = icnv_dev_gather_rows_f64(dX, G, d_keep, n_keep, dY, C, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(n_keep * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+static int validate_csc(const int32_t *p, const int32_t *ri, const double *x, int64_t G, int64_t C) {
+    if (!p || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: bad argument");
+    if (p[0] != 0) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: p[0] must be 0");
+    for (int64_t c = 0; c < C; ++c)
+        if (p[c + 1] < p[c]) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: p must be non-decreasing");
+    const int64_t nnz = p[C];
+    if (nnz > 0 && (!ri || !x)) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: i / x missing");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (ri[k] < 0 || ri[k] >= G) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: row index out of range");
+    return ICNV_OK;
+}
+
+// upload p / i / x into SLOT_IN (x first: 8-byte alignment)
+static int upload_csc(const int32_t *p, const int32_t *ri, const double *x, int64_t C, const double **d_x,
+                      const int32_t **d_i, const int32_t **d_p, cudaStream_t st) {
+    const int64_t nnz = p[C];
+    const size_t bx = sizeof(double) * (size_t)std::max<int64_t>(nnz, 1);
+    const size_t bi = (sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1) + 7) & ~(size_t)7;
+    char *base = (char *)scratch(SLOT_IN, bx + bi + sizeof(int32_t) * (size_t)(C + 1));
+    if (!base) return ICNV_E_NOMEM;
+    if (nnz > 0) {
+        ICNV_CUDA(cudaMemcpyAsync(base, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        ICNV_CUDA(cudaMemcpyAsync(base + bx, ri, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    }
+    ICNV_CUDA(cudaMemcpyAsync(base + bx + bi, p, sizeof(int32_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
+    *d_x = (const double *)base;
+    *d_i = (const int32_t *)(base + bx);
+    *d_p = (const int32_t *)(base + bx + bi);
+    return ICNV_OK;
+}
+
+int icnv_csc_gene_stats_f64(const int32_t *p, const int32_t *ri, const double *x, int64_t G, int64_t C, double *sums,
+                            int32_t *n_pos, double *means) {
+    ICNV_HOST_PROLOGUE();
+    int rc = validate_csc(p, ri, x, G, C);
+    if (rc) return rc;
+    if (!sums && !n_pos && !means) return set_error(ICNV_E_BAD_ARG, "icnv_csc_gene_stats_f64: no output requested");
+    const double *d_x;
+    const int32_t *d_i, *d_p;
+    if ((rc = upload_csc(p, ri, x, C, &d_x, &d_i, &d_p, st))) return rc;
+    double *d_sums = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G);
+    int32_t *d_npos = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * (size_t)G);
+    if (!d_sums || !d_npos) return ICNV_E_NOMEM;
+    if ((rc = icnv_dev_csc_gene_stats_f64(d_i, d_x, p[C], G, d_sums, d_npos, st))) return rc;
+    return download_gene_stats(d_sums, d_npos, G, C, sums, n_pos, means, st);
+}
+
+int icnv_csc_normalize_f64(const int32_t *p, const int32_t *ri, const double *x, int64_t G, int64_t C, const int32_t *keep,
+                           int64_t n_keep, double normalize_factor, double *Y, double *col_sums) {
+    ICNV_HOST_PROLOGUE();
+    int rc = validate_csc(p, ri, x, G, C);
+    if (rc) return rc;
+    if (!Y) return set_error(ICNV_E_BAD_ARG, "icnv_csc_normalize_f64: bad argument");
+    const int64_t G_out = keep ? n_keep : G;
+    if (keep && (rc = validate_keep(keep, n_keep, G))) return rc;
+    const double *d_x;
+    const int32_t *d_i, *d_p;
+    if ((rc = upload_csc(p, ri, x, C, &d_x, &d_i, &d_p, st))) return rc;
+    int32_t *d_map = nullptr;
+    std::vector<int32_t> map;
+    if (keep) {
+        map.assign((size_t)G, -1);
+        for (int64_t i = 0; i < n_keep; ++i) map[(size_t)keep[i]] = (int32_t)i;
+        d_map = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)G);
+        if (!d_map) return ICNV_E_NOMEM;
+        ICNV_CUDA(cudaMemcpyAsync(d_map, map.data(), sizeof(int32_t) * (size_t)G, cudaMemcpyHostToDevice, st));
+    }
+    double *d_cs = (double *)scratch(SLOT_PARTIAL, sizeof(double) * (size_t)C);
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G_out * C));
+    if (!d_cs || !dY) return ICNV_E_NOMEM;
+    if ((rc = icnv_dev_csc_col_sums_f64(d_p, d_i, d_x, d_map, C, d_cs, st))) return rc;
+    std::vector<double> cs((size_t)C);
+    ICNV_CUDA(cudaMemcpyAsync(cs.data(), d_cs, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    if (col_sums) std::copy(cs.begin(), cs.end(), col_sums);
+    if (!(normalize_factor >= 0.0)) {   // NA: median of the library sizes (ops.R:3095-3097)
+        std::sort(cs.begin(), cs.end());
+        normalize_factor = (C & 1) ? cs[(size_t)(C / 2)] : 0.5 * (cs[(size_t)(C / 2 - 1)] + cs[(size_t)(C / 2)]);
+    }
+    if (!std::isfinite(normalize_factor)) return set_error(ICNV_E_NONFINITE, "Error, normalize factor not estimated");
+    if ((rc = icnv_dev_csc_expand_f64(d_p, d_i, d_x, d_map, G_out, C, d_cs, normalize_factor, dY, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G_out * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
 }
 
 // ---- CNV region calling on the state matrix (R/inferCNV_HMM.R:706-1087) ----------------------------------------

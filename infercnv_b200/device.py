@@ -245,5 +245,51 @@ class Engine:
                                                        int(window_size), _stream_ptr()))
         return Y
 
+    # ---- CNV region calling on device-resident states (R/inferCNV_HMM.R:706-1087) --------------------------------------
+    def state_counts(self, S: torch.Tensor, groups_local) -> torch.Tensor:
+        """(n_grp, G, 8) int32 counts of the listed LOCAL cells' states per gene (slot 0: unassigned, v + 1: state v)."""
+        C, G = S.shape
+        off, idx = groups_to_csr(groups_local)
+        n_grp = len(groups_local)
+        counts = torch.empty((n_grp, G, 8), dtype=torch.int32, device=self.tdev)
+        d_idx = torch.as_tensor(idx if len(idx) else np.zeros(1, np.int32), device=self.tdev)   # a rank may own no listed cell
+        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+        _lib.check(self.lib.icnv_dev_state_counts_u8(S.data_ptr(), G, S.stride(0), d_idx.data_ptr(), off.ctypes.data, n_grp,
+                                                     counts.data_ptr(), flag.data_ptr(), _stream_ptr()))
+        if int(flag.item()) & 4:
+            raise ValueError("state outside 0..6 / 255 in the state matrix")
+        return counts
+
+    def state_consensus(self, S: torch.Tensor, groups_local) -> torch.Tensor:
+        """.get_state_consensus for every group -> (n_grp, G) uint8.  groups_local: per group, this rank's LOCAL
+        columns (possibly empty).  With a process group the integer counts are summed over ranks (all-reduce), so
+        the consensus is the same for any partition of a group's cells."""
+        import torch.distributed as tdist
+        counts = self.state_counts(S, groups_local)
+        if self.collective and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
+            tdist.all_reduce(counts, op=tdist.ReduceOp.SUM)
+        n_grp, G, _ = counts.shape
+        cons = torch.empty((n_grp, G), dtype=torch.uint8, device=self.tdev)
+        _lib.check(self.lib.icnv_dev_consensus_from_counts(counts.data_ptr(), G, n_grp, cons.data_ptr(), _stream_ptr()))
+        return cons
+
+    def cnv_regions(self, seqs: torch.Tensor, chr_start, chr_len, gene_start, gene_stop, cols=None) -> dict:
+        """Run-length regions + bounds of the rows of `seqs` ((n_seq, G) uint8: consensus sequences, or the state
+        matrix itself with `cols` = the cells to report, by = "cell").  Returns host arrays (api.REGION_FIELDS)."""
+        from .api import REGION_FIELDS
+        n_rows, G = seqs.shape
+        cs, cl = _i32(chr_start), _i32(chr_len)
+        gs, ge = (np.ascontiguousarray(v, dtype=np.float64) for v in (gene_start, gene_stop))
+        d_cols = torch.as_tensor(np.asarray(cols, dtype=np.int32), device=self.tdev) if cols is not None else None
+        n_seq = int(d_cols.numel()) if d_cols is not None else n_rows
+        n = ct.c_int64(0)
+        _lib.check(self.lib.icnv_dev_cnv_regions_u8(seqs.data_ptr(), G, seqs.stride(0), n_seq,
+                                                    d_cols.data_ptr() if d_cols is not None else None, cs.ctypes.data,
+                                                    cl.ctypes.data, len(cs), gs.ctypes.data, ge.ctypes.data,
+                                                    ct.addressof(n), _stream_ptr()))
+        out = {k: np.empty(int(n.value), dtype=dt) for k, dt in REGION_FIELDS}
+        _lib.check(self.lib.icnv_cnv_regions_fetch(int(n.value), *[out[k].ctypes.data for k, _ in REGION_FIELDS]))
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.icnv_launch_count())

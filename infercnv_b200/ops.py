@@ -432,3 +432,84 @@ def generate_cnv_region_reports(infercnv_obj: Infercnv, output_filename_prefix: 
     with open(path, "w") as f:
         f.write("chr\tstart\tstop\n")
         f.writelines("%s\t%s\t%s\t%s\n" % (gene_names[i], gchr[i], gs[i], ge[i]) for i in range(G))
+
+
+# ---- gene filters on the raw counts (run() step 2) ------------------------------------------------------------------
+
+def below_min_mean_expr_cutoff(expr_data, min_mean_expr) -> np.ndarray:
+    """.below_min_mean_expr_cutoff, R/inferCNV_ops.R:2149-2158: (0-based) indices of the genes whose mean over all
+    cells is below the cutoff."""
+    _, _, means = api.gene_stats(expr_data)
+    return np.flatnonzero(means < min_mean_expr)
+
+
+def remove_genes(infercnv_obj: Infercnv, gene_indices_to_remove) -> Infercnv:
+    """remove_genes, R/inferCNV.R:445-457: drops the rows from expr.data, count.data and gene_order."""
+    obj = copy.copy(infercnv_obj)
+    G = obj.expr_data.shape[0]
+    mask = np.ones(G, dtype=bool)
+    mask[np.asarray(gene_indices_to_remove, dtype=np.int64)] = False
+    keep = np.flatnonzero(mask)
+    obj.expr_data = api.remove_genes(obj.expr_data, keep)
+    if obj.count_data is not None:
+        obj.count_data = api.remove_genes(obj.count_data, keep)
+    obj.gene_order_chr = np.asarray(obj.gene_order_chr)[keep]
+    if obj.gene_names is not None:
+        obj.gene_names = [obj.gene_names[i] for i in keep]
+    if obj.gene_order_start is not None:
+        obj.gene_order_start = np.asarray(obj.gene_order_start)[keep]
+    if obj.gene_order_stop is not None:
+        obj.gene_order_stop = np.asarray(obj.gene_order_stop)[keep]
+    return obj
+
+
+def require_above_min_mean_expr_cutoff(infercnv_obj: Infercnv, min_mean_expr_cutoff: float) -> Infercnv:
+    """R/inferCNV_ops.R:2124-2144."""
+    log.info("::above_min_mean_expr_cutoff:Start")
+    indices = below_min_mean_expr_cutoff(infercnv_obj.expr_data, min_mean_expr_cutoff)
+    if len(indices) > 0:
+        log.info("Removing %d genes from matrix as below mean expr threshold: %g", len(indices), min_mean_expr_cutoff)
+        infercnv_obj = remove_genes(infercnv_obj, indices)
+        log.info("There are %d genes and %d cells remaining in the expr matrix.", *infercnv_obj.expr_data.shape)
+    return infercnv_obj
+
+
+def require_above_min_cells_ref(infercnv_obj: Infercnv, min_cells_per_gene: int) -> Infercnv:
+    """R/inferCNV_ops.R:2177-2209: keeps the genes expressed (x > 0) in at least min_cells_per_gene cells."""
+    _, n_pos, _ = api.gene_stats(infercnv_obj.expr_data)
+    passed = np.flatnonzero(n_pos >= min_cells_per_gene)
+    G = infercnv_obj.expr_data.shape[0]
+    num_removed = G - len(passed)
+    if num_removed > 0:
+        log.info("Removed %d genes having fewer than %d min cells per gene = %g %% genes removed here", num_removed,
+                 min_cells_per_gene, num_removed / G * 100)
+        if num_removed == G:
+            log.warning("::All genes removed! Must revisit your data..., cannot continue here.")
+            raise RuntimeError("998")                                   # stop(998)
+        mask = np.ones(G, dtype=bool)
+        mask[passed] = False
+        infercnv_obj = remove_genes(infercnv_obj, np.flatnonzero(mask))
+    else:
+        log.info("no genes removed due to min cells/gene filter")
+    return infercnv_obj
+
+
+def ingest_sparse_counts(p, i, x, n_genes, gene_order_chr, min_mean_expr_cutoff=None, min_cells_per_gene=None,
+                         normalize_factor=None):
+    """run() steps 2-3 on a compressed-sparse-column counts matrix (dgCMatrix @p / @i / @x, 0-based) without ever
+    building the dense counts on the host: the mean-expression filter, then the min-cells filter on what is left
+    (the order run() applies them in, ops.R:560-564), then depth normalisation over the kept genes.  Returns
+    (expr_data dense kept-genes x cells, kept gene indices, chromosome codes of the kept genes)."""
+    G = int(n_genes)
+    _, n_pos, means = api.csc_gene_stats(p, i, x, G)
+    keep = np.ones(G, dtype=bool)
+    if min_mean_expr_cutoff is not None:
+        keep &= ~(means < min_mean_expr_cutoff)
+    if min_cells_per_gene is not None:        # per-gene statistic: removing other genes first does not change it
+        passed = n_pos >= min_cells_per_gene
+        if not np.any(keep & passed):
+            raise RuntimeError("998")
+        keep &= passed
+    kept = np.flatnonzero(keep)
+    expr = api.csc_normalize(p, i, x, G, keep=kept, normalize_factor=normalize_factor)
+    return expr, kept, np.asarray(gene_order_chr)[kept]

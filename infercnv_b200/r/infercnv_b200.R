@@ -174,6 +174,16 @@ b200_apply_median_filtering <- function(infercnv_obj, window_size=7, on_observat
 ## normalize_counts_by_seq_depth, R/inferCNV_ops.R:3064
 b200_normalize_counts_by_seq_depth <- function(infercnv_obj, normalize_factor=NA) {
     m <- infercnv_obj@expr.data
+    if (.icnv_enabled() && methods::is(m, "dgCMatrix") && !anyNA(m@x)) {
+        ## sparse counts (R/inferCNV.R:158-160): the compressed columns cross PCIe, the dense normalised matrix comes back
+        res <- tryCatch(.Call("icnvR_csc_normalize", m@p, m@i, as.double(m@x), dim(m), as.double(normalize_factor)),
+                        error = function(e) NULL)
+        if (!is.null(res)) {
+            futile.logger::flog.info("normalizing counts matrix by depth (B200, sparse input)")
+            infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+            return(infercnv_obj)
+        }
+    }
     if (!.icnv_enabled() || !.icnv_ok(m)) return(.icnv_env$orig$normalize_counts_by_seq_depth(infercnv_obj, normalize_factor))
     res <- tryCatch(.Call("icnvR_normalize", m, as.double(normalize_factor)), error = function(e) NULL)
     if (is.null(res)) return(.icnv_env$orig$normalize_counts_by_seq_depth(infercnv_obj, normalize_factor))

@@ -263,6 +263,21 @@ SEXP icnvR_cnv_regions(SEXP states, SEXP chr_codes, SEXP gene_start, SEXP gene_s
     return ans;
 }
 
+/* normalize_counts_by_seq_depth on a dgCMatrix (R/inferCNV.R:158-160 accepts one): @p, @i, @x (0-based, as the
+ * Matrix package stores them) -> dense depth-normalised G x C matrix; 12 bytes per stored count over PCIe. */
+SEXP icnvR_csc_normalize(SEXP p, SEXP i, SEXP x, SEXP dims, SEXP normalize_factor) {
+    int64_t G = INTEGER(dims)[0], C = INTEGER(dims)[1];
+    double nf = Rf_asReal(normalize_factor);
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = (Rf_length(p) != C + 1) ? ICNV_E_BAD_ARG
+                                     : icnv_csc_normalize_f64(INTEGER(p), INTEGER(i), REAL(x), G, C, NULL, 0,
+                                                              (nf == nf) ? nf : -1.0, REAL(ans), NULL);
+    UNPROTECT(1);
+    if (rc == ICNV_E_BAD_ARG && Rf_length(p) != C + 1) Rf_error("infercnv_b200: @p does not match the matrix dimensions");
+    fail_if(rc);
+    return ans;
+}
+
 SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
 
 static const R_CallMethodDef call_methods[] = {
@@ -271,7 +286,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_viterbi", (DL_FUNC)&icnvR_viterbi, 7},           {"icnvR_median_filter", (DL_FUNC)&icnvR_median_filter, 4},
     {"icnvR_mean_sd", (DL_FUNC)&icnvR_mean_sd, 2},           {"icnvR_available", (DL_FUNC)&icnvR_available, 0},
     {"icnvR_normalize", (DL_FUNC)&icnvR_normalize, 2},       {"icnvR_clear_noise", (DL_FUNC)&icnvR_clear_noise, 3},
-    {"icnvR_cnv_regions", (DL_FUNC)&icnvR_cnv_regions, 5},
+    {"icnvR_cnv_regions", (DL_FUNC)&icnvR_cnv_regions, 5},   {"icnvR_csc_normalize", (DL_FUNC)&icnvR_csc_normalize, 5},
     {NULL, NULL, 0}};
 
 void R_init_infercnvb200_shim(DllInfo *dll) {

@@ -174,3 +174,27 @@ def test_full_size_round_trip_and_run_count():
     assert np.array_equal(back[valid], S[valid])
     assert np.array_equal(reg["start"], reg["first_gene"]) and np.array_equal(reg["end"], reg["last_gene"] + 1.0)
     assert np.all(np.diff(reg["seq"].astype(np.int64) * G + reg["first_gene"]) > 0)      # (sequence, position) order
+
+
+def test_device_resident_states_from_the_viterbi_kernel_to_regions():
+    """Engine path: states stay on the GPU between the HMM and the region calls (no PCIe round trip of the matrix);
+    a strided view (column stride > G) exercises lds != G."""
+    import torch
+    from infercnv_b200.device import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(3)
+    cs, cl = _layout([700, 2, 1, 333])
+    G, C = int(cl.sum()), 130
+    S = _states(rng, G, C, p_noise=0.2, unassigned=0.1)
+    gs = np.arange(G, dtype=np.float64) * 10
+    ge = gs + 95
+    wide = torch.zeros((C, G + 4), dtype=torch.uint8, device="cuda")
+    wide[:, :G] = torch.from_numpy(np.ascontiguousarray(S.T)).cuda()
+    groups = [np.arange(0, 100), np.arange(100, 130), np.array([7])]
+    for dS in (wide[:, :G].contiguous(), wide[:, :G]):
+        cons = eng.state_consensus(dS, groups)
+        want = np.stack([orr.state_consensus(S, g) for g in groups], axis=0)
+        assert np.array_equal(cons.cpu().numpy(), want)
+        _same_regions(eng.cnv_regions(cons, cs, cl, gs, ge), orr.cnv_regions(want.T, cs, cl, gs, ge))
+        cells = [5, 0, 129, 64]
+        _same_regions(eng.cnv_regions(dS, cs, cl, gs, ge, cols=cells), orr.cnv_regions(S[:, cells], cs, cl, gs, ge))
