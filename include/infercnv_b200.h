@@ -110,6 +110,24 @@ ICNV_API int icnv_normalize_counts_by_seq_depth_f64(const double *X, double *Y, 
 ICNV_API int icnv_clear_noise_via_ref_mean_sd_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *idx,
                                                   int64_t n_idx, double sd_amplifier);
 
+/* remove_outliers_norm / .remove_outliers_norm, R/inferCNV_ops.R:1969-2056 (run() step 16): clamp to
+ * [lower_bound, upper_bound].  A NaN bound (R's NA) selects out_method "average_bound" (.get_average_bounds,
+ * ops.R:2734-2742): lower = mean over cells of each cell's smallest value, upper = mean of each cell's largest.
+ * bounds_out: optional double[2] receiving the bounds used. */
+ICNV_API int icnv_remove_outliers_norm_f64(const double *X, double *Y, int64_t G, int64_t C, double lower_bound,
+                                           double upper_bound, double *bounds_out);
+
+/* clear_noise / .clear_noise, R/inferCNV_ops.R:2232-2275 (run() step 22 with a numeric noise_filter): centre = mean
+ * over all values of the listed cells (n_idx == 0: all data); values strictly inside centre +- threshold become
+ * centre, or - noise_logistic != 0 - are pulled towards it by depress_log_signal_midpt_val (slope 20,
+ * R/inferCNV_heatmap.R:2783-2810).  threshold == 0: unchanged copy. */
+ICNV_API int icnv_clear_noise_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx,
+                                  double threshold, int noise_logistic);
+
+/* clear_noise_via_ref_mean_sd(noise_logistic = TRUE), R/inferCNV_ops.R:2325-2329. */
+ICNV_API int icnv_clear_noise_via_ref_mean_sd_logistic_f64(const double *X, double *Y, int64_t G, int64_t C,
+                                                           const int32_t *idx, int64_t n_idx, double sd_amplifier);
+
 /* Element-wise steps as stand-alone calls (inside icnv_smooth_block_f64 they are fused into the loads
  * and stores): log2xplus1 (R/inferCNV_ops.R:2756-2769), invert_log2 (:2814-2826),
  * apply_max_threshold_bounds (:2970-2983).  n = G*C elements, Y may alias X. */

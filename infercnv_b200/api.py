@@ -354,3 +354,38 @@ def csc_normalize(p, i, x, n_genes, keep=None, normalize_factor=None, want_col_s
     _lib.check(_lib.load().icnv_csc_normalize_f64(_p(p), _p(i), _p(x), G, C, _p(keep), 0 if keep is None else len(keep), nf,
                                                   _p(Y), _p(cs)))
     return (Y, cs) if want_col_sums else Y
+
+
+# ---- outlier clamp and noise clearing (run() steps 16, 22) --------------------------------------------------------
+
+def remove_outliers_norm(X, lower_bound=None, upper_bound=None, want_bounds=False):
+    """.remove_outliers_norm (icnv_remove_outliers_norm_f64); a missing bound selects out_method "average_bound"."""
+    X = _f64(X)
+    G, C = X.shape
+    Y = np.empty_like(X, order="F")
+    b = np.empty(2)
+    lo = float("nan") if lower_bound is None else float(lower_bound)
+    hi = float("nan") if upper_bound is None else float(upper_bound)
+    _lib.check(_lib.load().icnv_remove_outliers_norm_f64(_p(X), _p(Y), G, C, lo, hi, _p(b)))
+    return (Y, (float(b[0]), float(b[1]))) if want_bounds else Y
+
+
+def clear_noise(X, cells, threshold, noise_logistic=False) -> np.ndarray:
+    """clear_noise (icnv_clear_noise_f64); cells = reference cells, or None / empty for "all data"."""
+    X = _f64(X)
+    G, C = X.shape
+    idx = None if cells is None or len(cells) == 0 else _i32(cells)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_clear_noise_f64(_p(X), _p(Y), G, C, _p(idx), 0 if idx is None else len(idx), float(threshold),
+                                                int(bool(noise_logistic))))
+    return Y
+
+
+def clear_noise_via_ref_mean_sd_logistic(X, cells, sd_amplifier=1.5) -> np.ndarray:
+    X = _f64(X)
+    G, C = X.shape
+    idx = _i32(cells)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_clear_noise_via_ref_mean_sd_logistic_f64(_p(X), _p(Y), G, C, _p(idx), len(idx),
+                                                                        float(sd_amplifier)))
+    return Y

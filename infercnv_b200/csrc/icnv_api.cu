@@ -22,6 +22,10 @@ int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, 
 int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C, const double *sums, double factor,
                                void *stream);
 int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream);
+int icnv_dev_column_minmax_f64(const double *X, int64_t G, int64_t C, double *mins, double *maxs, void *stream);
+int icnv_dev_clamp_bounds_f64(const double *X, double *Y, int64_t n, double lower, double upper, void *stream);
+int icnv_dev_logistic_adj_f64(const double *X, double *Y, int64_t n, double expr_mean, double delta_midpt, double slope,
+                              void *stream);
 int icnv_dev_gene_stats_f64(const double *X, int64_t G, int64_t ldx, int64_t C, double *d_sums, int32_t *d_npos, void *stream);
 int icnv_dev_gather_rows_f64(const double *X, int64_t ldx, const int32_t *d_keep, int64_t n_keep, double *Y, int64_t C,
                              void *stream);
@@ -983,6 +987,131 @@ int icnv_clear_noise_via_ref_mean_sd_f64(const double *X, double *Y, int64_t G, 
     const double mu = tot / ((double)G * (double)n_idx);
     const double s = (sdsum / (double)n_idx) * sd_amplifier;
     if ((rc = icnv_dev_clear_noise_f64(dX, dY, G * C, mu - s, mu + s, mu, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+// R's mean(): long-double sum, then one refinement pass (summary.c, real_mean)
+static double r_mean_host(const double *x, int64_t n) {
+    long double s = 0.0L;
+    for (int64_t i = 0; i < n; ++i) s += x[i];
+    s /= (long double)n;
+    long double t = 0.0L;
+    for (int64_t i = 0; i < n; ++i) t += (x[i] - s);
+    s += t / (long double)n;
+    return (double)s;
+}
+
+/* remove_outliers_norm / .remove_outliers_norm, R/inferCNV_ops.R:1969-2056 (run() step 16, prune_outliers): values
+ * below lower_bound become lower_bound, values above upper_bound become upper_bound.  Both bounds given (not NaN):
+ * hard thresholds.  Otherwise out_method "average_bound" (.get_average_bounds, ops.R:2734-2742): the mean over
+ * the cells of each cell's smallest value, and of each cell's largest value.  bounds_out (may be NULL) receives the
+ * two bounds used. */
+int icnv_remove_outliers_norm_f64(const double *X, double *Y, int64_t G, int64_t C, double lower_bound, double upper_bound,
+                                  double *bounds_out) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0)
+        return set_error(ICNV_E_BAD_ARG, "Error, something is wrong with the data, either null or no rows or columns");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    if (!dY) return ICNV_E_NOMEM;
+    if (!(lower_bound == lower_bound) || !(upper_bound == upper_bound)) {
+        double *d_mm = (double *)scratch(SLOT_PARTIAL, sizeof(double) * 2 * (size_t)C);
+        if (!d_mm) return ICNV_E_NOMEM;
+        if ((rc = icnv_dev_column_minmax_f64(dX, G, C, d_mm, d_mm + C, st))) return rc;
+        std::vector<double> mm(2 * (size_t)C);
+        ICNV_CUDA(cudaMemcpyAsync(mm.data(), d_mm, sizeof(double) * 2 * (size_t)C, cudaMemcpyDeviceToHost, st));
+        ICNV_CUDA(cudaStreamSynchronize(st));
+        lower_bound = r_mean_host(mm.data(), C);
+        upper_bound = r_mean_host(mm.data() + C, C);
+    }
+    if (bounds_out) {
+        bounds_out[0] = lower_bound;
+        bounds_out[1] = upper_bound;
+    }
+    if ((rc = icnv_dev_clamp_bounds_f64(dX, dY, G * C, lower_bound, upper_bound, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+// mean over all values of the listed cells (idx == NULL: all C cells) and mean of the per-cell sds
+static int host_ref_mean_sd(const double *dX, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mean,
+                            double *mean_sd, cudaStream_t st) {
+    const int64_t n = idx ? n_idx : C;
+    int32_t *d_idx = nullptr;
+    if (idx) {
+        for (int64_t i = 0; i < n_idx; ++i)
+            if (idx[i] < 0 || idx[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index out of range");
+        d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_idx);
+        if (!d_idx) return ICNV_E_NOMEM;
+        ICNV_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+    }
+    double *d_stats = (double *)scratch(SLOT_MEANS, sizeof(double) * 2 * (size_t)n);
+    if (!d_stats) return ICNV_E_NOMEM;
+    int rc = icnv_dev_column_stats_f64(dX, G, d_idx, n, d_stats, d_stats + n, st);
+    if (rc) return rc;
+    std::vector<double> h(2 * (size_t)n);
+    ICNV_CUDA(cudaMemcpyAsync(h.data(), d_stats, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    double tot = 0.0, sdsum = 0.0;   // n-vectors: combined on the host in list order
+    for (int64_t i = 0; i < n; ++i) {
+        tot += h[(size_t)i];
+        sdsum += h[(size_t)(n + i)];
+    }
+    *mean = tot / ((double)G * (double)n);
+    *mean_sd = sdsum / (double)n;
+    return ICNV_OK;
+}
+
+/* clear_noise / .clear_noise, R/inferCNV_ops.R:2232-2275 (run() step 22 with a numeric noise_filter): centre = mean
+ * over all values of the listed cells (reference cells; idx == NULL / n_idx == 0: all data, ops.R:2243-2247).
+ * noise_logistic == 0: values strictly inside (centre - threshold, centre + threshold) become centre;
+ * noise_logistic != 0: depress_log_signal_midpt_val(centre, threshold), slope 20 (R/inferCNV_heatmap.R:2783-2810).
+ * threshold == 0: the matrix is returned unchanged (ops.R:2236-2238). */
+int icnv_clear_noise_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double threshold,
+                         int noise_logistic) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 1 || C <= 0 || n_idx < 0) return set_error(ICNV_E_BAD_ARG, "icnv_clear_noise_f64: bad argument");
+    if (threshold == 0.0) {
+        if (Y != X) memcpy(Y, X, sizeof(double) * (size_t)(G * C));
+        return ICNV_OK;
+    }
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    if (!dY) return ICNV_E_NOMEM;
+    double mu, msd;
+    if ((rc = host_ref_mean_sd(dX, G, C, n_idx > 0 ? idx : nullptr, n_idx, &mu, &msd, st))) return rc;
+    if (noise_logistic)
+        rc = icnv_dev_logistic_adj_f64(dX, dY, G * C, mu, threshold, 20.0, st);
+    else
+        rc = icnv_dev_clear_noise_f64(dX, dY, G * C, mu - threshold, mu + threshold, mu, st);
+    if (rc) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+/* clear_noise_via_ref_mean_sd with noise_logistic = TRUE, R/inferCNV_ops.R:2325-2329: the logistic depression around
+ * the reference mean with midpoint sd_amplifier * mean(per-cell sd). */
+int icnv_clear_noise_via_ref_mean_sd_logistic_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *idx,
+                                                  int64_t n_idx, double sd_amplifier) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || !idx || G <= 1 || C <= 0 || n_idx <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_clear_noise_via_ref_mean_sd_logistic_f64: bad argument");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    if (!dY) return ICNV_E_NOMEM;
+    double mu, msd;
+    if ((rc = host_ref_mean_sd(dX, G, C, idx, n_idx, &mu, &msd, st))) return rc;
+    if ((rc = icnv_dev_logistic_adj_f64(dX, dY, G * C, mu, msd * sd_amplifier, 20.0, st))) return rc;
     ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
     ICNV_CUDA(cudaStreamSynchronize(st));
     return ICNV_OK;

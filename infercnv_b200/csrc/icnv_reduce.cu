@@ -95,6 +95,68 @@ __global__ void __launch_bounds__(256) clear_noise_kernel(const double *__restri
     }
 }
 
+// .get_average_bounds (ops.R:2734-2742): quantile(x, na.rm=TRUE)[[1]] / [[5]] of a cell = its smallest / largest
+// non-NA value.  One CTA per cell; min / max do not depend on the order.
+__global__ void __launch_bounds__(256) column_minmax_kernel(const double *__restrict__ X, int64_t G, int64_t C,
+                                                            double *__restrict__ mins, double *__restrict__ maxs) {
+    __shared__ double sh_lo[8], sh_hi[8];
+    for (int64_t c = blockIdx.x; c < C; c += gridDim.x) {
+        const double *col = X + G * c;
+        double lo = INFINITY, hi = -INFINITY;
+        for (int64_t g = threadIdx.x; g < G; g += 256) {
+            const double v = col[g];
+            lo = fmin(lo, v);      // fmin / fmax return the non-NaN operand: na.rm = TRUE
+            hi = fmax(hi, v);
+        }
+        lo = warp_min_d(lo);
+        hi = warp_max_d(hi);
+        if ((threadIdx.x & 31) == 0) {
+            sh_lo[threadIdx.x >> 5] = lo;
+            sh_hi[threadIdx.x >> 5] = hi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                lo = fmin(lo, sh_lo[w]);
+                hi = fmax(hi, sh_hi[w]);
+            }
+            mins[c] = lo;
+            maxs[c] = hi;
+        }
+        __syncthreads();
+    }
+}
+
+// .remove_outliers_norm (ops.R:2051-2052): data[data < lower] <- lower; data[data > upper] <- upper
+__global__ void __launch_bounds__(256) clamp_bounds_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t n,
+                                                           double lower, double upper) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        double v = X[i];
+        if (v < lower) v = lower;
+        if (v > upper) v = upper;
+        Y[i] = v;
+    }
+}
+
+// .apply_logistic_val_adj (R/inferCNV_heatmap.R:2792-2810) with .logistic (R/SplatterScrape.R:210-212):
+// val = |x - mean|; p = 1 / (1 + exp(-slope (val - midpt))); x -> mean +- p val
+__global__ void __launch_bounds__(256) logistic_adj_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t n,
+                                                           double expr_mean, double delta_midpt, double slope) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double x = X[i];
+        const double val = fabs(x - expr_mean);
+        const double p = 1.0 / (1.0 + exp(-slope * (val - delta_midpt)));
+        double out = x;
+        if (x > expr_mean) out = expr_mean + p * val;
+        else if (x < expr_mean) out = expr_mean - p * val;
+        Y[i] = out;
+    }
+}
+
 }  // namespace icnv
 
 using namespace icnv;
@@ -133,5 +195,33 @@ extern "C" int icnv_dev_elementwise_f64(const double *X, double *Y, int64_t n, i
     int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
     elementwise_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, op, param, err_flag);
     ICNV_CHECK_LAUNCH("elementwise_kernel");
+    return ICNV_OK;
+}
+
+extern "C" int icnv_dev_column_minmax_f64(const double *X, int64_t G, int64_t C, double *mins, double *maxs, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || !mins || !maxs || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_column_minmax_f64: bad argument");
+    int64_t blocks = std::min<int64_t>(C, (int64_t)ctx().sm_count * 8);
+    column_minmax_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, G, C, mins, maxs);
+    ICNV_CHECK_LAUNCH("column_minmax_kernel");
+    return ICNV_OK;
+}
+
+extern "C" int icnv_dev_clamp_bounds_f64(const double *X, double *Y, int64_t n, double lower, double upper, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || !Y || n <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_clamp_bounds_f64: bad argument");
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
+    clamp_bounds_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, lower, upper);
+    ICNV_CHECK_LAUNCH("clamp_bounds_kernel");
+    return ICNV_OK;
+}
+
+extern "C" int icnv_dev_logistic_adj_f64(const double *X, double *Y, int64_t n, double expr_mean, double delta_midpt,
+                                         double slope, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || !Y || n <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_logistic_adj_f64: bad argument");
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
+    logistic_adj_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, expr_mean, delta_midpt, slope);
+    ICNV_CHECK_LAUNCH("logistic_adj_kernel");
     return ICNV_OK;
 }

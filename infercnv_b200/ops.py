@@ -84,8 +84,8 @@ def normalize_counts_by_seq_depth(infercnv_obj: Infercnv, normalize_factor=None)
     return obj
 
 
-def clear_noise_via_ref_mean_sd(infercnv_obj: Infercnv, sd_amplifier: float = 1.5) -> Infercnv:
-    """R/inferCNV_ops.R:2302-2346 with noise_logistic=FALSE (hspike mirroring is commented out in the reference)."""
+def clear_noise_via_ref_mean_sd(infercnv_obj: Infercnv, sd_amplifier: float = 1.5, noise_logistic: bool = False) -> Infercnv:
+    """R/inferCNV_ops.R:2302-2346 (hspike mirroring is commented out in the reference)."""
     if has_reference_cells(infercnv_obj):
         log.info("denoising using mean(normal) +- sd_amplifier * sd(normal) per gene per cell across all data")
         cells = np.concatenate([np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()])
@@ -93,7 +93,46 @@ def clear_noise_via_ref_mean_sd(infercnv_obj: Infercnv, sd_amplifier: float = 1.
         log.info("-no reference cells specified... using mean and sd of all cells as proxy for denoising")
         cells = np.concatenate([np.asarray(v) for v in infercnv_obj.observation_grouped_cell_indices.values()])
     obj = copy.copy(infercnv_obj)
-    obj.expr_data = api.clear_noise_via_ref_mean_sd(obj.expr_data, cells, sd_amplifier)
+    if noise_logistic:
+        obj.expr_data = api.clear_noise_via_ref_mean_sd_logistic(obj.expr_data, cells, sd_amplifier)
+    else:
+        obj.expr_data = api.clear_noise_via_ref_mean_sd(obj.expr_data, cells, sd_amplifier)
+    return obj
+
+
+def clear_noise(infercnv_obj: Infercnv, threshold: float, noise_logistic: bool = False) -> Infercnv:
+    """R/inferCNV_ops.R:2232-2263: noise around the mean of the reference cells (or of all data) within +- threshold."""
+    log.info("********* ::clear_noise:Start. threshold: %s", threshold)
+    if threshold == 0:
+        return infercnv_obj                       # nothing to do
+    cells = (np.concatenate([np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()])
+             if has_reference_cells(infercnv_obj) else None)
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.clear_noise(obj.expr_data, cells, threshold, noise_logistic)
+    return obj
+
+
+def remove_outliers_norm(infercnv_obj: Infercnv, out_method: Optional[str] = "average_bound", lower_bound=None,
+                         upper_bound=None) -> Infercnv:
+    """R/inferCNV_ops.R:1969-2056 (run() step 16): hard bounds when both are given, else "average_bound"."""
+    log.info("::remove_outlier_norm:Start out_method: %s lower_bound: %s upper_bound: %s", out_method, lower_bound, upper_bound)
+    obj = copy.copy(infercnv_obj)
+    if lower_bound is not None and upper_bound is not None:
+        log.info("::remove_outlier_norm: using hard thresholds:  lower_bound: %s upper_bound: %s", lower_bound, upper_bound)
+        obj.expr_data = api.remove_outliers_norm(obj.expr_data, lower_bound, upper_bound)
+    elif out_method is not None:
+        log.info("::remove_outlier_norm using method: %s for defining outliers.", out_method)
+        if out_method != "average_bound":
+            log.error("::remove_outlier_norm:Error, please provide an approved method for outlier removal for visualization.")
+            raise RuntimeError("991")                                    # stop(991)
+        obj.expr_data, (lo, hi) = api.remove_outliers_norm(obj.expr_data, want_bounds=True)
+        log.info("outlier bounds defined between: %g - %g", lo, hi)
+    else:
+        log.error("::remove_outlier_norm:Error, must specify outmethod or define exact bounds")
+        raise RuntimeError("992")                                        # stop(992)
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = remove_outliers_norm(obj.hspike, out_method, lower_bound, upper_bound)
     return obj
 
 

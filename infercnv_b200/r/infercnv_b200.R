@@ -204,6 +204,41 @@ b200_clear_noise_via_ref_mean_sd <- function(infercnv_obj, sd_amplifier=1.5, noi
     infercnv_obj
 }
 
+## remove_outliers_norm, R/inferCNV_ops.R:1969 (run() step 16)
+b200_remove_outliers_norm <- function(infercnv_obj, out_method="average_bound", lower_bound=NA, upper_bound=NA) {
+    orig <- .icnv_env$orig$remove_outliers_norm
+    m <- infercnv_obj@expr.data
+    hard <- !is.na(lower_bound) & !is.na(upper_bound)
+    ## anything but hard bounds / "average_bound" ends in the reference's stop(991) / stop(992): leave it to R
+    if (!.icnv_enabled() || !.icnv_ok(m) || !(hard || identical(out_method, "average_bound")))
+        return(orig(infercnv_obj, out_method, lower_bound, upper_bound))
+    futile.logger::flog.info(paste("::remove_outlier_norm:Start (B200)", "out_method:", out_method, "lower_bound:", lower_bound,
+                                   "upper_bound:", upper_bound))
+    res <- tryCatch(.Call("icnvR_remove_outliers", m, as.double(if (hard) lower_bound else NA),
+                          as.double(if (hard) upper_bound else NA)), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, out_method, lower_bound, upper_bound))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    if (!is.null(infercnv_obj@.hspike)) {
+        futile.logger::flog.info("-mirroring for hspike")
+        infercnv_obj@.hspike <- b200_remove_outliers_norm(infercnv_obj@.hspike, out_method, lower_bound, upper_bound)
+    }
+    infercnv_obj
+}
+
+## clear_noise, R/inferCNV_ops.R:2232 (run() step 22 with a numeric noise_filter)
+b200_clear_noise <- function(infercnv_obj, threshold, noise_logistic=FALSE) {
+    orig <- .icnv_env$orig$clear_noise
+    m <- infercnv_obj@expr.data
+    if (!.icnv_enabled() || !.icnv_ok(m) || threshold == 0) return(orig(infercnv_obj, threshold, noise_logistic))
+    cells <- if (length(infercnv_obj@reference_grouped_cell_indices) > 0)
+        as.integer(unlist(infercnv_obj@reference_grouped_cell_indices)) else NULL
+    res <- tryCatch(.Call("icnvR_clear_noise_threshold", m, cells, as.double(threshold), isTRUE(noise_logistic)),
+                    error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, threshold, noise_logistic))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    infercnv_obj
+}
+
 ## get_predicted_CNV_regions, R/inferCNV_HMM.R:706-764: consensus state per cell group, run-length regions per
 ## chromosome and their bounds from ONE library call; the returned list has the reference's shape
 ## (cell_group_name, cells, gene_regions = named list of per-gene data.frames, cnv_ranges = data.frame), so
@@ -260,7 +295,7 @@ infercnvb200_install <- function() {
              "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
              "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
              "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd",
-             "get_predicted_CNV_regions")
+             "get_predicted_CNV_regions", "remove_outliers_norm", "clear_noise")
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")

@@ -278,6 +278,35 @@ SEXP icnvR_csc_normalize(SEXP p, SEXP i, SEXP x, SEXP dims, SEXP normalize_facto
     return ans;
 }
 
+/* remove_outliers_norm (ops.R:1969-2056): NA bounds select "average_bound" */
+SEXP icnvR_remove_outliers(SEXP expr, SEXP lower_bound, SEXP upper_bound) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = icnv_remove_outliers_norm_f64(REAL(expr), REAL(ans), G, C, Rf_asReal(lower_bound), Rf_asReal(upper_bound), NULL);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
+/* clear_noise (ops.R:2232-2263): cells = reference cells (1-based) or NULL for "all data" */
+SEXP icnvR_clear_noise_threshold(SEXP expr, SEXP cells, SEXP threshold, SEXP noise_logistic) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int n = Rf_isNull(cells) ? 0 : Rf_length(cells);
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = ICNV_E_NOMEM;
+    if (idx) {
+        for (int i = 0; i < n; ++i) idx[i] = INTEGER(cells)[i] - 1;
+        rc = icnv_clear_noise_f64(REAL(expr), REAL(ans), G, C, idx, n, Rf_asReal(threshold), Rf_asLogical(noise_logistic));
+    }
+    free(idx);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
 SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
 
 static const R_CallMethodDef call_methods[] = {
@@ -287,6 +316,8 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_mean_sd", (DL_FUNC)&icnvR_mean_sd, 2},           {"icnvR_available", (DL_FUNC)&icnvR_available, 0},
     {"icnvR_normalize", (DL_FUNC)&icnvR_normalize, 2},       {"icnvR_clear_noise", (DL_FUNC)&icnvR_clear_noise, 3},
     {"icnvR_cnv_regions", (DL_FUNC)&icnvR_cnv_regions, 5},   {"icnvR_csc_normalize", (DL_FUNC)&icnvR_csc_normalize, 5},
+    {"icnvR_remove_outliers", (DL_FUNC)&icnvR_remove_outliers, 3},
+    {"icnvR_clear_noise_threshold", (DL_FUNC)&icnvR_clear_noise_threshold, 4},
     {NULL, NULL, 0}};
 
 void R_init_infercnvb200_shim(DllInfo *dll) {
