@@ -182,6 +182,11 @@ ICNV_API int icnv_viterbi_u8_f64(const double *X, int64_t G, int64_t C, const in
                                  int n_grp, int m, const double *Pi, const double *delta, const double *mean,
                                  const double *sd, uint8_t *states, double *margins);
 
+/* assign_HMM_states_to_proxy_expr_vals, R/inferCNV_HMM.R:1191-1206 (m = 6: states 1..6 -> 0, 0.5, 1, 1.5, 2, 3) and
+ * i3HMM_assign_HMM_states_to_proxy_expr_vals, R/inferCNV_i3HMM.R:405-417 (m = 3: 1..3 -> 0.5, 1, 1.5) on the numeric
+ * state matrix (n entries); any other value (e.g. -1) passes through.  Y may alias X. */
+ICNV_API int icnv_assign_hmm_states_to_proxy_expr_vals_f64(const double *X, double *Y, int64_t n, int m);
+
 /* apply_median_filtering / .median_filter, R/noise_reduction.R:43-113.  Blocks = chromosome x one
  * index list (a subcluster for observations, a whole group for references), cells in list order.
  * Window radius is (window_size+1)/2 as in the reference (noise_reduction.R:102-106).

@@ -56,6 +56,7 @@ SIGNATURES = {
     "icnv_combine_cell_stats": (None, [_P, _P, c_i64, c_i64, _P, _P]),
     "icnv_dev_column_stats_f64": (c_int, [_P, c_i64, _P, c_i64, _P, _P, _P]),
     "icnv_dev_median_filter_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, _P]),
+    "icnv_assign_hmm_states_to_proxy_expr_vals_f64": (c_int, [_P, _P, c_i64, c_int]),
     "icnv_remove_outliers_norm_f64": (c_int, [_P, _P, c_i64, c_i64, ct.c_double, ct.c_double, _P]),
     "icnv_clear_noise_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_i64, ct.c_double, c_int]),
     "icnv_clear_noise_via_ref_mean_sd_logistic_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_i64, ct.c_double]),

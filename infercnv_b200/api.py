@@ -389,3 +389,11 @@ def clear_noise_via_ref_mean_sd_logistic(X, cells, sd_amplifier=1.5) -> np.ndarr
     _lib.check(_lib.load().icnv_clear_noise_via_ref_mean_sd_logistic_f64(_p(X), _p(Y), G, C, _p(idx), len(idx),
                                                                         float(sd_amplifier)))
     return Y
+
+
+def assign_hmm_states_to_proxy_expr_vals(states, m=6) -> np.ndarray:
+    """State matrix -> proxy expression values (icnv_assign_hmm_states_to_proxy_expr_vals_f64)."""
+    X = _f64(states)
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_assign_hmm_states_to_proxy_expr_vals_f64(_p(X), _p(Y), X.size, int(m)))
+    return Y

@@ -22,6 +22,7 @@ int icnv_dev_column_stats_f64(const double *X, int64_t G, const int32_t *cells, 
 int icnv_dev_scale_columns_f64(const double *X, double *Y, int64_t G, int64_t C, const double *sums, double factor,
                                void *stream);
 int icnv_dev_clear_noise_f64(const double *X, double *Y, int64_t n, double lo, double hi, double mu, void *stream);
+int icnv_dev_proxy_vals_f64(const double *X, double *Y, int64_t n, int m, void *stream);
 int icnv_dev_column_minmax_f64(const double *X, int64_t G, int64_t C, double *mins, double *maxs, void *stream);
 int icnv_dev_clamp_bounds_f64(const double *X, double *Y, int64_t n, double lower, double upper, void *stream);
 int icnv_dev_logistic_adj_f64(const double *X, double *Y, int64_t n, double expr_mean, double delta_midpt, double slope,
@@ -1113,6 +1114,23 @@ int icnv_clear_noise_via_ref_mean_sd_logistic_f64(const double *X, double *Y, in
     if ((rc = host_ref_mean_sd(dX, G, C, idx, n_idx, &mu, &msd, st))) return rc;
     if ((rc = icnv_dev_logistic_adj_f64(dX, dY, G * C, mu, msd * sd_amplifier, 20.0, st))) return rc;
     ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+/* assign_HMM_states_to_proxy_expr_vals (HMM.R:1191-1206, m = 6) / i3HMM_assign_HMM_states_to_proxy_expr_vals
+ * (i3HMM.R:405-417, m = 3) on a numeric state matrix of n entries. */
+int icnv_assign_hmm_states_to_proxy_expr_vals_f64(const double *X, double *Y, int64_t n, int m) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || n <= 0 || (m != 6 && m != 3))
+        return set_error(ICNV_E_BAD_ARG, "icnv_assign_hmm_states_to_proxy_expr_vals_f64: bad argument");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, n, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)n);
+    if (!dY) return ICNV_E_NOMEM;
+    if ((rc = icnv_dev_proxy_vals_f64(dX, dY, n, m, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     ICNV_CUDA(cudaStreamSynchronize(st));
     return ICNV_OK;
 }

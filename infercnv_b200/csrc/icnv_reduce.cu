@@ -140,6 +140,32 @@ __global__ void __launch_bounds__(256) clamp_bounds_kernel(const double *__restr
     }
 }
 
+// assign_HMM_states_to_proxy_expr_vals (R/inferCNV_HMM.R:1191-1206; m = 6: 1..6 -> 0, .5, 1, 1.5, 2, 3) and
+// i3HMM_assign_HMM_states_to_proxy_expr_vals (R/inferCNV_i3HMM.R:405-417; m = 3: 1..3 -> .5, 1, 1.5); the sequence of
+// masked assignments there never re-maps a value it has just written, so it is a lookup; other values pass through
+__global__ void __launch_bounds__(256) proxy_vals_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t n,
+                                                         int m) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double v = X[i];
+        double out = v;
+        if (m == 6) {
+            if (v == 1.0) out = 0.0;
+            else if (v == 2.0) out = 0.5;
+            else if (v == 3.0) out = 1.0;
+            else if (v == 4.0) out = 1.5;
+            else if (v == 5.0) out = 2.0;
+            else if (v == 6.0) out = 3.0;
+        } else {
+            if (v == 1.0) out = 0.5;
+            else if (v == 2.0) out = 1.0;
+            else if (v == 3.0) out = 1.5;
+        }
+        Y[i] = out;
+    }
+}
+
 // .apply_logistic_val_adj (R/inferCNV_heatmap.R:2792-2810) with .logistic (R/SplatterScrape.R:210-212):
 // val = |x - mean|; p = 1 / (1 + exp(-slope (val - midpt))); x -> mean +- p val
 __global__ void __launch_bounds__(256) logistic_adj_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t n,
@@ -223,5 +249,14 @@ extern "C" int icnv_dev_logistic_adj_f64(const double *X, double *Y, int64_t n, 
     int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
     logistic_adj_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, expr_mean, delta_midpt, slope);
     ICNV_CHECK_LAUNCH("logistic_adj_kernel");
+    return ICNV_OK;
+}
+
+extern "C" int icnv_dev_proxy_vals_f64(const double *X, double *Y, int64_t n, int m, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!X || !Y || n <= 0 || (m != 6 && m != 3)) return set_error(ICNV_E_BAD_ARG, "icnv_dev_proxy_vals_f64: bad argument");
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx().sm_count * 16);
+    proxy_vals_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(X, Y, n, m);
+    ICNV_CHECK_LAUNCH("proxy_vals_kernel");
     return ICNV_OK;
 }

@@ -347,15 +347,16 @@ def i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj: Infercnv, clu
 
 
 def assign_HMM_states_to_proxy_expr_vals(infercnv_obj: Infercnv) -> Infercnv:
-    """R/inferCNV_HMM.R:1191-1206 (i6): state -> {0, 0.5, 1, 1.5, 2, 3}.  A 6-entry lookup on the
-    already-downloaded state matrix (not a kernel: the reference does six masked assignments)."""
-    lut = np.array([np.nan, 0.0, 0.5, 1.0, 1.5, 2.0, 3.0])
+    """R/inferCNV_HMM.R:1191-1206 (i6): state -> {0, 0.5, 1, 1.5, 2, 3}; other values (-1) are left as they are."""
     obj = copy.copy(infercnv_obj)
-    st = obj.expr_data.astype(np.int64)
-    out = obj.expr_data.copy()
-    ok = (st >= 1) & (st <= 6)
-    out[ok] = lut[st[ok]]
-    obj.expr_data = out
+    obj.expr_data = api.assign_hmm_states_to_proxy_expr_vals(obj.expr_data, 6)
+    return obj
+
+
+def i3HMM_assign_HMM_states_to_proxy_expr_vals(infercnv_obj: Infercnv) -> Infercnv:
+    """R/inferCNV_i3HMM.R:405-417: state -> {0.5, 1, 1.5}."""
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.assign_hmm_states_to_proxy_expr_vals(obj.expr_data, 3)
     return obj
 
 

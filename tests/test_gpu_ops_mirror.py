@@ -107,6 +107,12 @@ def test_hmm_drivers_and_median_filter_through_the_mirror(example_object, hmm_fi
     # proxy values (HMM.R:1191-1206)
     proxy = ops.assign_HMM_states_to_proxy_expr_vals(cells)
     assert set(np.unique(proxy.expr_data)).issubset({0.0, 0.5, 1.0, 1.5, 2.0, 3.0})
+    lut6 = np.array([np.nan, 0.0, 0.5, 1.0, 1.5, 2.0, 3.0])
+    np.testing.assert_array_equal(proxy.expr_data, lut6[cells.expr_data.astype(int)])
+    proxy3 = ops.i3HMM_assign_HMM_states_to_proxy_expr_vals(i3)                       # i3HMM.R:405-417
+    np.testing.assert_array_equal(proxy3.expr_data, np.array([np.nan, 0.5, 1.0, 1.5])[i3.expr_data.astype(int)])
+    tiny = ops.Infercnv(expr_data=np.array([[-1.0, 1.0, 4.0], [6.0, 3.0, 2.5]]), gene_order_chr=np.array([1, 1]))
+    np.testing.assert_array_equal(ops.assign_HMM_states_to_proxy_expr_vals(tiny).expr_data, [[-1.0, 0.0, 1.5], [3.0, 1.0, 2.5]])
     # exported apply_median_filtering: subclusters in hclust order for observations, whole groups for references
     mf = ops.apply_median_filtering(o, window_size=7)
     want_mf = orc.median_filter(o.expr_data, cs, cl, [ex["subclusters"][0], ex["ref_groups"][0]], 7)
