@@ -347,6 +347,16 @@ ICNV_API int icnv_dev_cnv_regions_records(int64_t *n, const int32_t **seq, const
                                           const int32_t **first_gene, const int32_t **last_gene,
                                           const int32_t **state, const double **start, const double **end);
 
+/* Gene filters / ingest / outlier clamp on device-resident data (see the host entry points of the same names):
+ * per-gene sum and number of values > 0 over the C columns (column stride ldx); row gather Y[i + n_keep*c] =
+ * X[keep[i] + ldx*c]; per-cell min / max (NaN skipped); clamp to [lower, upper]. */
+ICNV_API int icnv_dev_gene_stats_f64(const double *X, int64_t G, int64_t ldx, int64_t C, double *sums, int32_t *n_pos,
+                                     void *stream);
+ICNV_API int icnv_dev_gather_rows_f64(const double *X, int64_t ldx, const int32_t *keep, int64_t n_keep, double *Y,
+                                      int64_t C, void *stream);
+ICNV_API int icnv_dev_column_minmax_f64(const double *X, int64_t G, int64_t C, double *mins, double *maxs, void *stream);
+ICNV_API int icnv_dev_clamp_bounds_f64(const double *X, double *Y, int64_t n, double lower, double upper, void *stream);
+
 /* Deterministic synthetic workload of SURVEY section 8(d) written straight into HBM: counter-based
  * generator keyed by (seed, global cell, gene), so any sharding of the cells yields identical data.
  * Fills X (G x n_cells, ld = G) for global cells [cell0, cell0 + n_cells). */

@@ -68,6 +68,10 @@ SIGNATURES = {
     "icnv_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),
     "icnv_predicted_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P]),
     "icnv_cnv_regions_fetch": (c_int, [c_i64, _P, _P, _P, _P, _P, _P, _P]),
+    "icnv_dev_gene_stats_f64": (c_int, [_P, c_i64, c_i64, c_i64, _P, _P, _P]),
+    "icnv_dev_gather_rows_f64": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, _P]),
+    "icnv_dev_column_minmax_f64": (c_int, [_P, c_i64, c_i64, _P, _P, _P]),
+    "icnv_dev_clamp_bounds_f64": (c_int, [_P, _P, c_i64, ct.c_double, ct.c_double, _P]),
     "icnv_dev_state_counts_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),
     "icnv_dev_consensus_from_counts": (c_int, [_P, c_i64, c_int, _P, _P]),
     "icnv_dev_state_consensus_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),

@@ -92,6 +92,49 @@ def plan_shards(n_cells: int, ref_groups: list[np.ndarray], world: int) -> list[
     return plans
 
 
+@dataclass
+class ListShardPlan:
+    """Whole index lists (tumour subclusters, reference groups) owned by one rank: the partition for the steps whose
+    unit is a list in its own cell order - apply_median_filtering's blocks (R/noise_reduction.R:43-89) and the
+    group-mode HMM's rowMeans (R/inferCNV_HMM.R:345-408, 509-567)."""
+    rank: int
+    world: int
+    list_ids: list[int]            # which of the caller's lists this rank owns, in the caller's order
+    cells: np.ndarray              # GLOBAL cell indices of the local columns: the owned lists back to back
+
+    def local_lists(self, lists) -> list[np.ndarray]:
+        """The owned lists as LOCAL column indices (columns ordered as `cells`)."""
+        out, pos = [], 0
+        for k in self.list_ids:
+            n = len(lists[k])
+            out.append(np.arange(pos, pos + n, dtype=np.int32))
+            pos += n
+        return out
+
+
+def plan_list_shards(lists: list[np.ndarray], world: int) -> list[ListShardPlan]:
+    """Assign every list WHOLE to one rank (a list is never split: its cells' order is part of the median filter's
+    window and of nothing else, so no halo exchange is needed), largest first onto the least loaded rank; ties go to
+    the lower rank, so the plan is a pure function of the list sizes.  Cells in no list are in no shard (the median
+    filter copies them, the group HMM leaves them at -1: the caller keeps them)."""
+    lists = [np.asarray(v, dtype=np.int64) for v in lists]
+    seen = np.concatenate(lists) if lists else np.zeros(0, np.int64)
+    if len(np.unique(seen)) != len(seen):
+        raise ValueError("index lists overlap: a cell would live on two ranks")
+    load = [0] * world
+    owner = [0] * len(lists)
+    for k in sorted(range(len(lists)), key=lambda k: (-len(lists[k]), k)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[k] = r
+        load[r] += len(lists[k])
+    plans = []
+    for r in range(world):
+        ids = [k for k in range(len(lists)) if owner[k] == r]
+        cells = np.concatenate([lists[k] for k in ids]) if ids else np.zeros(0, np.int64)
+        plans.append(ListShardPlan(rank=r, world=world, list_ids=ids, cells=cells))
+    return plans
+
+
 def allgather_partials(local, max_chunks: int):
     """All-gather one group's partial sums.  `local` is a torch tensor (n_local_chunks, G) on the
     device of the process group's backend.  Returns (world * max_chunks, G): rank-major, each

@@ -100,3 +100,28 @@ def test_allgather_of_partial_sums_is_bitwise_equal_to_single_process():
     for p in procs:
         p.join(timeout=30)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_list_shards_keep_every_list_whole_and_balance_the_load():
+    rng = np.random.default_rng(0)
+    C = 20000
+    perm = rng.permutation(C)
+    lists, pos = [], 0
+    while pos < C - 600:
+        n = int(rng.integers(50, 501))
+        lists.append(perm[pos:pos + n])
+        pos += n                                            # the last cells are in no list
+    for world in (1, 2, 4, 8):
+        plans = shard.plan_list_shards(lists, world)
+        owned = sorted(k for p in plans for k in p.list_ids)
+        assert owned == list(range(len(lists)))             # every list on exactly one rank
+        for p in plans:
+            assert p.list_ids == sorted(p.list_ids)
+            np.testing.assert_array_equal(p.cells, np.concatenate([lists[k] for k in p.list_ids]))
+            for k, loc in zip(p.list_ids, p.local_lists(lists)):
+                np.testing.assert_array_equal(p.cells[loc], lists[k])      # local columns keep the list's own order
+        loads = [len(p.cells) for p in plans]
+        assert max(loads) - min(loads) <= 500               # within one list of each other
+        assert shard.plan_list_shards(lists, world)[0].list_ids == plans[0].list_ids      # deterministic
+    with pytest.raises(ValueError):
+        shard.plan_list_shards([np.array([1, 2, 3]), np.array([3, 4])], 2)

@@ -53,4 +53,40 @@ from statistics import NormalDist  # noqa: E402
 Pi3, d3, mean3, sd3 = i3HMM_get_HMM({"mu": mu, "sigma": sg, "mean_delta": abs(NormalDist(0, sg).inv_cdf(0.05)), "KS_delta": None}, 1e-6)
 ms = timed(lambda: eng.viterbi(Y, cs, cl, Pi3, d3, mean3, sd3))
 out["viterbi_i3"] = {"ms": ms, "cell_genes_per_s": G * C / ms * 1e3, "algorithmic_GBps": 9 * G * C / ms / 1e6}
+# ---- region calling on the device-resident i6 states (K7), ingest (K8) and the element-wise steps (K9) ----
+from infercnv_b200.ops import CNV_LEVELS, get_HMM  # noqa: E402
+Pi6, d6, _, _ = get_HMM({k: {"mean": m, "sd": s} for k, m, s in zip(CNV_LEVELS, bench.I6_MEAN, bench.I6_SD)}, 1e-6)
+S, _ = eng.viterbi(Y, cs, cl, Pi6, d6, bench.I6_MEAN, bench.I6_SD)
+gs = np.arange(G, dtype=np.float64) * 1000.0
+ge = gs + 5000.0
+ms = timed(lambda: eng.state_consensus(S, groups))
+out["state_consensus_subclusters"] = {"ms": ms, "cell_genes_per_s": G * C / ms * 1e3, "algorithmic_GBps": 1 * G * C / ms / 1e6,
+                                      "groups": len(groups)}
+cons = eng.state_consensus(S, groups)
+ms = timed(lambda: eng.cnv_regions(cons, cs, cl, gs, ge))
+out["cnv_regions_subclusters"] = {"ms": ms, "sequences": len(groups), "regions": int(len(eng.cnv_regions(cons, cs, cl, gs, ge)["seq"]))}
+cells_all = np.arange(C)
+ms = timed(lambda: eng.cnv_regions(S, cs, cl, gs, ge, cols=cells_all), reps=3)
+reg = eng.cnv_regions(S, cs, cl, gs, ge, cols=cells_all)
+out["cnv_regions_by_cell"] = {"ms": ms, "cell_genes_per_s": G * C / ms * 1e3, "algorithmic_GBps": 2 * G * C / ms / 1e6,
+                              "regions": int(len(reg["seq"])), "note": "includes the D2H fetch of the records"}
+import ctypes as ct  # noqa: E402
+from infercnv_b200 import _lib  # noqa: E402
+from infercnv_b200.device import _stream_ptr  # noqa: E402
+lib = _lib.load()
+sums = torch.empty(G, dtype=torch.float64, device="cuda")
+npos = torch.empty(G, dtype=torch.int32, device="cuda")
+ms = timed(lambda: _lib.check(lib.icnv_dev_gene_stats_f64(X.data_ptr(), G, G, C, sums.data_ptr(), npos.data_ptr(), _stream_ptr())))
+out["gene_stats_dense"] = {"ms": ms, "cell_genes_per_s": G * C / ms * 1e3, "algorithmic_GBps": 8 * G * C / ms / 1e6}
+keep = torch.arange(0, G, 1, dtype=torch.int32, device="cuda")[torch.rand(G, device="cuda") > 0.15].contiguous()
+Z = torch.empty((C, int(keep.numel())), dtype=torch.float64, device="cuda")
+ms = timed(lambda: _lib.check(lib.icnv_dev_gather_rows_f64(X.data_ptr(), G, keep.data_ptr(), int(keep.numel()), Z.data_ptr(), C,
+                                                          _stream_ptr())))
+out["remove_genes"] = {"ms": ms, "algorithmic_GBps": 8 * (G + int(keep.numel())) * C / ms / 1e6, "kept": int(keep.numel())}
+mins = torch.empty(C, dtype=torch.float64, device="cuda")
+maxs = torch.empty(C, dtype=torch.float64, device="cuda")
+ms = timed(lambda: _lib.check(lib.icnv_dev_column_minmax_f64(Y.data_ptr(), G, C, mins.data_ptr(), maxs.data_ptr(), _stream_ptr())))
+out["column_minmax"] = {"ms": ms, "algorithmic_GBps": 8 * G * C / ms / 1e6}
+ms = timed(lambda: _lib.check(lib.icnv_dev_clamp_bounds_f64(Y.data_ptr(), F.data_ptr(), G * C, 0.9, 1.1, _stream_ptr())))
+out["clamp_bounds"] = {"ms": ms, "algorithmic_GBps": 16 * G * C / ms / 1e6}
 print(json.dumps(out))

@@ -27,6 +27,11 @@ X = eng.synth(G, cs, cl, plan.local_cells, C_total, bench.SEED)
 Y, f = eng.smooth_block(X, cs, cl, plan.local_ref_groups(), plan.ref_sizes, plan.max_chunks)
 S, f2 = eng.viterbi(Y, cs, cl, Pi, delta, bench.I6_MEAN, bench.I6_SD)
 mu_d, sg_d = eng.mean_sd(Y, plan.local_ref_groups())        # i3 parameters across ranks
+# CNV region consensus of two "sample" groups whose cells are spread over all ranks: integer counts, all-reduced
+obs_global = [np.arange(int(0.10 * C_total), int(0.55 * C_total)), np.arange(int(0.55 * C_total), C_total)]
+pos_of = {int(c): i for i, c in enumerate(plan.local_cells)}
+obs_local = [np.array([pos_of[int(c)] for c in g if int(c) in pos_of], dtype=np.int32) for g in obs_global]
+cons_d = eng.state_consensus(S, obs_local)
 torch.cuda.synchronize()
 assert int(f.item()) == 0 and int(f2.item()) == 0
 # gather every rank's rows on rank 0 (variable sizes -> pad)
@@ -56,7 +61,10 @@ if rank == 0:
         idx = torch.tensor([pos1[int(c)] for c in p.local_cells], device=X.device)
         bad_y += int((Ys[r][: len(idx)] != Y1[idx]).sum().item())
         bad_s += int((Ss[r][: len(idx)] != S1[idx]).sum().item())
-    ok = bad_y == 0 and bad_s == 0 and mu_d == mu_1 and sg_d == sg_1
+    cons_1 = eng.state_consensus(S1, [np.array([pos1[int(c)] for c in g], dtype=np.int32) for g in obs_global])
+    bad_c = int((cons_1 != cons_d).sum().item())
+    print(f"[check_multigpu] group consensus states differing from the 1-GPU run: {bad_c}")
+    ok = bad_y == 0 and bad_s == 0 and mu_d == mu_1 and sg_d == sg_1 and bad_c == 0
     print(f"[check_multigpu] i3 mu/sigma over the reference cells: {mu_d!r}, {sg_d!r} (1-GPU: {mu_1!r}, {sg_1!r})")
     print(f"[check_multigpu] world={world} cells={C_total}: smoothed values differing from 1-GPU run: {bad_y}; "
           f"states differing: {bad_s}  -> {'BITWISE EQUAL' if ok else 'MISMATCH'}")
