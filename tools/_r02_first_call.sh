@@ -2,10 +2,10 @@
 # round-1 GPU budget ran out gets its first run here, then the standing profile set is refreshed.
 set -x
 mkdir -p gpurun_out
-# 1. parity: the whole GPU suite (new files: test_gpu_regions.py, test_gpu_ingest.py, test_gpu_denoise.py)
+# 1. parity: the whole GPU suite (new files: test_gpu_widen_regions.py, test_gpu_widen_ingest.py, test_gpu_widen_denoise.py)
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -5 gpurun_out/r02_pytest_gpu.log
 # 2. memory safety of the new kernels on small cases
-timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_regions.py tests/test_gpu_ingest.py tests/test_gpu_denoise.py -m gpu -x -q -k "not full_size" > gpurun_out/r02_memcheck.log 2>&1; tail -5 gpurun_out/r02_memcheck.log
+timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_widen_regions.py tests/test_gpu_widen_ingest.py tests/test_gpu_widen_denoise.py -m gpu -x -q -k "not full_size" > gpurun_out/r02_memcheck.log 2>&1; tail -5 gpurun_out/r02_memcheck.log
 # 3. the bench line (never under a profiler) and the secondary kernels incl. K7-K9
 timeout 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 600 gpurun_out/r02_bench.json
 timeout 300 python tools/bench_extra.py > gpurun_out/r02_secondary_kernels.json 2> gpurun_out/r02_secondary.err; cat gpurun_out/r02_secondary_kernels.json
