@@ -19,10 +19,14 @@
 #include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <type_traits>
 #include <vector>
 
 // ---- language extensions ------------------------------------------------------------------------------------------
@@ -35,6 +39,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
+#define __constant__
 
 struct uint3 { unsigned x = 0, y = 0, z = 0; };
 struct dim3 {
@@ -51,8 +56,8 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline uint3 threadIdx, blockIdx;
 inline dim3 blockDim, gridDim;
 
-using std::max;
-using std::min;
+template <class A, class B> constexpr std::common_type_t<A, B> min(A a, B b) { return b < a ? (std::common_type_t<A, B>)b : (std::common_type_t<A, B>)a; }
+template <class A, class B> constexpr std::common_type_t<A, B> max(A a, B b) { return a < b ? (std::common_type_t<A, B>)b : (std::common_type_t<A, B>)a; }
 
 // ---- runtime API --------------------------------------------------------------------------------------------------
 typedef int cudaError_t;
@@ -97,6 +102,22 @@ static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t
     if (n) memset(d, v, n);
     return cudaSuccess;
 }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) {
+    if (n) memmove(d, s, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMemcpyToSymbol(T &sym, const void *src, size_t n, size_t off = 0, cudaMemcpyKind = cudaMemcpyHostToDevice) {
+    memcpy((char *)&sym + off, src, n);
+    return cudaSuccess;
+}
+template <class T> static inline cudaError_t cudaMemcpyFromSymbol(void *dst, const T &sym, size_t n, size_t off = 0, cudaMemcpyKind = cudaMemcpyDeviceToHost) {
+    memcpy(dst, (const char *)&sym + off, n);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 
@@ -118,6 +139,10 @@ inline ucontext_t sched_ctx;
 inline Fiber *cur = nullptr;
 inline const std::function<void()> *body = nullptr;
 inline uint64_t warp_slot[2][MAX_THREADS / 32][32];
+inline unsigned warp_posted[2][MAX_THREADS / 32][32];   // collective number (gen + 1) the slot was written for
+constexpr size_t DYN_SMEM_MAX = 227 * 1024;
+alignas(128) inline unsigned char dyn_smem[DYN_SMEM_MAX];
+inline size_t dyn_smem_bytes = 0;
 inline unsigned long long launches = 0, blocks_run = 0;
 
 inline void yield_to_scheduler() { swapcontext(&cur->ctx, &sched_ctx); }
@@ -145,8 +170,18 @@ inline void run_block(unsigned nt, const std::function<void()> &fn) {
         f.state = RUN;
         f.gen = 0;
     }
+    memset(warp_posted, 0, sizeof(warp_posted));
+    if (dyn_smem_bytes) memset(dyn_smem, 0xA5, dyn_smem_bytes);     // shared memory starts undefined in every block
     unsigned alive = nt;
+    unsigned long long passes = 0;
     while (alive > 0) {
+        if (++passes == 200000000ull) {     // no kernel of this library synchronises this often: a live-lock
+            unsigned st[4] = {0, 0, 0, 0};
+            for (unsigned t = 0; t < nt; ++t) st[fibers[t].state]++;
+            fprintf(stderr, "emu: block (%u,%u) still running after 2e8 scheduler passes (run %u, block-wait %u, warp-wait %u, done %u)\n",
+                    blockIdx.x, blockIdx.y, st[0], st[1], st[2], st[3]);
+            abort();
+        }
         bool ran = false;
         for (unsigned t = 0; t < nt; ++t) {
             Fiber &f = fibers[t];
@@ -192,16 +227,41 @@ inline void run_block(unsigned nt, const std::function<void()> &fn) {
 
 struct Cfg {
     dim3 grid, block;
-    Cfg(dim3 g, dim3 b, size_t = 0, cudaStream_t = nullptr) : grid(g), block(b) {}
+    size_t smem;
+    Cfg(dim3 g, dim3 b, size_t s = 0, cudaStream_t = nullptr) : grid(g), block(b), smem(s) {}
 };
 
+// EMU_WATCHDOG=<seconds>: print a native backtrace of wherever the emulation is when the alarm fires, then abort
+inline void watchdog_handler(int) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "emu: watchdog fired; native backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(99);
+}
+inline void arm_watchdog() {
+    static bool armed = false;
+    const char *e = getenv("EMU_WATCHDOG");
+    if (armed || !e) return;
+    armed = true;
+    signal(SIGALRM, watchdog_handler);
+    alarm((unsigned)atoi(e));
+}
+
 inline void launch(const Cfg &cfg, const std::function<void()> &fn) {
+    arm_watchdog();
     if (cfg.block.y != 1 || cfg.block.z != 1 || cfg.grid.z != 1) {
         fprintf(stderr, "emu: only (x, y) grids of 1-D blocks are supported\n");
         abort();
     }
+    if (cfg.smem > DYN_SMEM_MAX) {
+        fprintf(stderr, "emu: %zu bytes of dynamic shared memory exceed the 227 KB of a CTA\n", cfg.smem);
+        abort();
+    }
     gridDim = cfg.grid;
     blockDim = cfg.block;
+    dyn_smem_bytes = cfg.smem;
     ++launches;
     for (unsigned by = 0; by < cfg.grid.y; ++by)
         for (unsigned bx = 0; bx < cfg.grid.x; ++bx) {
@@ -215,13 +275,15 @@ template <class T>
 inline T warp_exchange(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
     Fiber *f = cur;
-    const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = f->gen++ & 1u;
+    const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31, n = ++f->gen, g = n & 1u;
     uint64_t bits = 0;
     memcpy(&bits, &v, sizeof(T));
     warp_slot[g][w][lane] = bits;
+    warp_posted[g][w][lane] = n;
     f->state = WAIT_WARP;
     yield_to_scheduler();
-    if (src_lane < 0 || src_lane > 31 || fibers[w * 32 + (unsigned)src_lane].state == DONE) return v;
+    // a lane that left the kernel before this collective never posted: the result is undefined on the GPU, own value here
+    if (src_lane < 0 || src_lane > 31 || warp_posted[g][w][src_lane] != n) return v;
     T out;
     memcpy(&out, &warp_slot[g][w][src_lane], sizeof(T));
     return out;
@@ -247,7 +309,59 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
     return emu::warp_exchange(v, lane + (int)d <= 31 ? lane + (int)d : lane);
 }
 
+namespace emu {
+// every live lane posts a value; after the release each lane folds the posted values of the live lanes
+template <class T, class F>
+inline T warp_fold(T v, F f) {
+    Fiber *fb = cur;
+    const unsigned tid = threadIdx.x, w = tid >> 5, lane = tid & 31, n = ++fb->gen, g = n & 1u;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    warp_slot[g][w][lane] = bits;
+    warp_posted[g][w][lane] = n;
+    fb->state = WAIT_WARP;
+    yield_to_scheduler();
+    T acc = v;
+    for (unsigned l = 0; l < 32; ++l) {
+        if (l == lane || warp_posted[g][w][l] != n) continue;     // lanes that have left the kernel do not take part
+        T o;
+        memcpy(&o, &warp_slot[g][w][l], sizeof(T));
+        acc = f(acc, o);
+    }
+    return acc;
+}
+}  // namespace emu
+static inline int __reduce_add_sync(unsigned, int v) { return emu::warp_fold(v, [](int a, int b) { return a + b; }); }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return emu::warp_fold(v, [](unsigned a, unsigned b) { return a + b; }); }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return emu::warp_fold(v, [](unsigned a, unsigned b) { return a | b; }); }
+static inline int __reduce_max_sync(unsigned, int v) { return emu::warp_fold(v, [](int a, int b) { return a > b ? a : b; }); }
+static inline int __reduce_min_sync(unsigned, int v) { return emu::warp_fold(v, [](int a, int b) { return a < b ? a : b; }); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    return emu::warp_fold(pred ? 1u << (threadIdx.x & 31) : 0u, [](unsigned a, unsigned b) { return a | b; });
+}
+
 // ---- intrinsics ---------------------------------------------------------------------------------------------------
+// IEEE operations that must not be contracted into an FMA: out of line, so the host compiler cannot fuse them either
+__attribute__((noinline)) static double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+__attribute__((noinline)) static double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+__attribute__((noinline)) static double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline double cospi(double x) { return cos(M_PI * x); }
+static inline double sinpi(double x) { return sin(M_PI * x); }
+static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double v;
+    memcpy(&v, &u, 8);
+    return v;
+}
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {
+    sh &= 31;
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+}
+static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __double2hiint(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(u >> 32); }
 static inline int __double2loint(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(u & 0xffffffffu); }
@@ -258,5 +372,8 @@ static inline double atomicAdd(double *p, double v) { const double o = *p; *p = 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
+static inline unsigned atomicExch(unsigned *p, unsigned v) { const unsigned o = *p; *p = v; return o; }
+static inline unsigned long long atomicExch(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = v; return o; }
 static inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
 static inline int atomicExch(int *p, int v) { const int o = *p; *p = v; return o; }

@@ -1,12 +1,15 @@
-"""The byte / index kernels of the widened rows (region calling, gene filters + sparse ingest, outlier clamp / noise
-clearing, the element-wise steps) executed on the CPU from their own CUDA source text: tests/host/build_emu.py compiles
-icnv_regions.cu, icnv_ingest.cu, icnv_reduce.cu and the host entry points of icnv_api.cu with g++ against a host
-emulation of the CUDA execution model (tests/host/emu/cuda_runtime.h: blocks of fibers, __syncthreads, warp shuffles,
-atomics; divergent barriers abort), and tests/host/run_emulated.py runs the SAME parity tests the B200 box runs
-(tests/test_gpu_widen_*.py) against that build in a subprocess.
+"""The library's kernels executed on the CPU from their own CUDA source text: tests/host/build_emu.py compiles every
+translation unit of infercnv_b200/csrc with g++ against a host emulation of the CUDA execution model
+(tests/host/emu/cuda_runtime.h: the threads of a block are fibers; __syncthreads, warp shuffles / reductions and atomics
+have their CUDA semantics; a divergent barrier or a live-lock aborts; fresh device and shared memory is poisoned), with
+synchronous stand-ins for the few inline-PTX copy primitives (TMA bulk copy + mbarrier, cp.async), and
+tests/host/run_emulated.py runs the SAME parity tests the B200 box runs (-m gpu) against that build in a subprocess.
 
-Test infrastructure only: it exercises the kernels' index arithmetic, barriers and memory accesses without a GPU; it
-says nothing about performance, and the package never loads the emulated library (tests/test_capi_symbols.py)."""
+Test infrastructure only: it exercises the kernels' index arithmetic, barriers, shared-memory hand-offs and memory
+accesses without a GPU - the fused cell pipeline, both Viterbi kernels with the certificate / re-run logic, the median
+filter, and the kernels of the widened rows.  It says nothing about performance, floating-point contraction differs
+from nvcc's in the last bit (the tests' tolerances are unchanged), and the package never loads the emulated library
+(tests/test_capi_symbols.py)."""
 import os
 import shutil
 import subprocess
@@ -18,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
-def test_widened_rows_pass_their_parity_tests_under_the_host_emulation():
+def test_gpu_parity_tests_pass_under_the_host_emulation():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host", "run_emulated.py")], capture_output=True, text=True,
                        timeout=1500)
     tail = "\n".join(r.stdout.splitlines()[-25:]) + r.stderr[-2000:]
