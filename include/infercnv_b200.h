@@ -187,6 +187,16 @@ ICNV_API int icnv_viterbi_u8_f64(const double *X, int64_t G, int64_t C, const in
  * state matrix (n entries); any other value (e.g. -1) passes through.  Y may alias X. */
 ICNV_API int icnv_assign_hmm_states_to_proxy_expr_vals_f64(const double *X, double *Y, int64_t n, int m);
 
+/* predict_CNV_via_HMM_on_tumor_subclusters_per_chr, R/inferCNV_HMM.R:412-471: every chromosome k has its own list of
+ * subclusters - groups chr_grp_off[k] .. chr_grp_off[k+1]) of the CSR lists (grp_off, grp_idx); one Viterbi sequence
+ * per (chromosome, subcluster) on rowMeans(X[chr, cells]) with that group's sds (sd: m per group, the median is used,
+ * HMM.R:1122); the trace is written to the subcluster's cells on that chromosome's genes, cells in no subcluster of a
+ * chromosome get 255 (R's -1, HMM.R:436) there.  A cell in two subclusters of one chromosome: ICNV_E_BAD_ARG. */
+ICNV_API int icnv_viterbi_per_chr_u8_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start,
+                                         const int32_t *chr_len, int K, const int32_t *chr_grp_off,
+                                         const int32_t *grp_off, const int32_t *grp_idx, int m, const double *Pi,
+                                         const double *delta, const double *mean, const double *sd, uint8_t *states);
+
 /* apply_median_filtering / .median_filter, R/noise_reduction.R:43-113.  Blocks = chromosome x one
  * index list (a subcluster for observations, a whole group for references), cells in list order.
  * Window radius is (window_size+1)/2 as in the reference (noise_reduction.R:102-106).
@@ -239,6 +249,14 @@ ICNV_API int icnv_csc_normalize_f64(const int32_t *p, const int32_t *i, const do
  * table() / order(decreasing=TRUE)[1] do.  A byte outside {0..6, 255}: ICNV_E_BAD_ARG. */
 ICNV_API int icnv_state_consensus_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *grp_off,
                                      const int32_t *grp_idx, int n_grp, uint8_t *consensus);
+
+/* The step that ends predict_CNV_via_HMM_on_tumor_subclusters_per_chr (HMM.R:470-483: get_predicted_CNV_regions by
+ * "subcluster", then every region's state written to all cells of its group): out[g, c] = consensus state of c's
+ * group at gene g, for the genes region calling covers (chromosomes with >= 2 genes); other genes and cells in no
+ * group keep their state.  out may alias states. */
+ICNV_API int icnv_apply_state_consensus_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                                           const int32_t *chr_len, int K, const int32_t *grp_off,
+                                           const int32_t *grp_idx, int n_grp, uint8_t *out);
 
 /* .define_cnv_gene_regions + .get_cnv_gene_region_bounds, R/inferCNV_HMM.R:1006-1087, for n_seq state sequences
  * (the columns of seqs, G x n_seq): within every chromosome of >= 2 genes (shorter ones are skipped, :1012-1014)

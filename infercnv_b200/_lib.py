@@ -64,6 +64,8 @@ SIGNATURES = {
     "icnv_remove_genes_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P]),
     "icnv_csc_gene_stats_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, _P, _P]),
     "icnv_csc_normalize_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, c_i64, ct.c_double, _P, _P]),
+    "icnv_viterbi_per_chr_u8_f64": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "icnv_apply_state_consensus_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, _P]),
     "icnv_state_consensus_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P]),
     "icnv_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P]),
     "icnv_predicted_cnv_regions_u8": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P]),

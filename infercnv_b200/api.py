@@ -397,3 +397,44 @@ def assign_hmm_states_to_proxy_expr_vals(states, m=6) -> np.ndarray:
     Y = np.empty_like(X, order="F")
     _lib.check(_lib.load().icnv_assign_hmm_states_to_proxy_expr_vals_f64(_p(X), _p(Y), X.size, int(m)))
     return Y
+
+
+# ---- per-chromosome subcluster HMM (R/inferCNV_HMM.R:412-487) -----------------------------------------------------
+
+def viterbi_per_chr(X, chr_start, chr_len, groups_per_chr, Pi, delta, mean, sds) -> np.ndarray:
+    """One Viterbi sequence per (chromosome, subcluster of that chromosome) on the subcluster's rowMeans
+    (icnv_viterbi_per_chr_u8_f64).  groups_per_chr: per chromosome a list of cell-index arrays; sds: m values per group,
+    chromosome-major in the same order.  Returns uint8 states (G, C), 255 where a cell has no subcluster."""
+    X = _f64(X)
+    G, C = X.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    if len(groups_per_chr) != len(cs):
+        raise ValueError("one list of subclusters per chromosome is needed")
+    flat = [np.asarray(g) for per in groups_per_chr for g in per]
+    chr_off = np.cumsum([0] + [len(per) for per in groups_per_chr]).astype(np.int32)
+    off, idx = groups_to_csr(flat)
+    Pi = np.asfortranarray(Pi, dtype=np.float64)
+    m = Pi.shape[0]
+    delta, mean = (np.ascontiguousarray(v, dtype=np.float64) for v in (delta, mean))
+    sds = np.ascontiguousarray(sds, dtype=np.float64)
+    if sds.size == m:
+        sds = np.tile(sds, len(flat))
+    if sds.size != m * len(flat):
+        raise ValueError("sds must have m entries per (chromosome, subcluster)")
+    S = np.empty((G, C), dtype=np.uint8, order="F")
+    _lib.check(_lib.load().icnv_viterbi_per_chr_u8_f64(_p(X), G, C, _p(cs), _p(cl), len(cs), _p(chr_off), _p(off), _p(idx), m,
+                                                       _p(Pi), _p(delta), _p(mean), _p(sds), _p(S)))
+    return S
+
+
+def apply_state_consensus(states, chr_start, chr_len, groups) -> np.ndarray:
+    """Every cell of a group takes the group's consensus state on the genes region calling covers
+    (icnv_apply_state_consensus_u8)."""
+    S = _u8(states)
+    G, C = S.shape
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    off, idx = groups_to_csr(groups)
+    out = np.empty((G, C), dtype=np.uint8, order="F")
+    _lib.check(_lib.load().icnv_apply_state_consensus_u8(_p(S), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx), len(groups),
+                                                         _p(out)))
+    return out

@@ -36,6 +36,10 @@ int icnv_dev_csc_col_sums_f64(const int32_t *d_p, const int32_t *d_i, const doub
                               int64_t C, double *d_cs, void *stream);
 int icnv_dev_csc_expand_f64(const int32_t *d_p, const int32_t *d_i, const double *d_x, const int32_t *d_keep_map,
                             int64_t G_out, int64_t C, const double *d_cs, double factor, double *Y, void *stream);
+int icnv_dev_scatter_states_per_chr_u8(const uint8_t *gs, int64_t G, int64_t C, const int32_t *d_chr_id, const int32_t *d_grp_of,
+                                       uint8_t *out, void *stream);
+int icnv_dev_apply_consensus_u8(const uint8_t *S, const uint8_t *cons, int64_t G, int64_t C, const int32_t *d_chr_of,
+                                const int32_t *d_grp_of, uint8_t *out, void *stream);
 int icnv_dev_state_consensus_u8(const uint8_t *S, int64_t G, int64_t lds, const int32_t *d_cells, const int32_t *h_grp_off,
                                 int n_grp, uint8_t *d_cons, int *d_flag, void *stream);
 int icnv_dev_cnv_regions_u8(const uint8_t *d_seqs, int64_t G, int64_t lds, int64_t n_seq, const int32_t *d_cols,
@@ -819,6 +823,69 @@ int icnv_csc_normalize_f64(const int32_t *p, const int32_t *ri, const double *x,
     return ICNV_OK;
 }
 
+// ---- per-chromosome subcluster HMM (predict_CNV_via_HMM_on_tumor_subclusters_per_chr, HMM.R:412-487) --------------
+
+int icnv_viterbi_per_chr_u8_f64(const double *X, int64_t G, int64_t C, const int32_t *chr_start, const int32_t *chr_len, int K,
+                                const int32_t *chr_grp_off, const int32_t *grp_off, const int32_t *grp_idx, int m,
+                                const double *Pi, const double *delta, const double *mean, const double *sd,
+                                uint8_t *states) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !states || G <= 0 || C <= 0 || !Pi || !delta || !mean || !sd || !chr_grp_off)
+        return set_error(ICNV_E_BAD_ARG, "icnv_viterbi_per_chr_u8_f64: bad argument");
+    if (m != 6 && m != 3) return set_error(ICNV_E_BAD_ARG, "m must be 6 or 3");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if (chr_grp_off[0] != 0) return set_error(ICNV_E_BAD_ARG, "chr_grp_off[0] must be 0");
+    for (int k = 0; k < K; ++k)
+        if (chr_grp_off[k + 1] < chr_grp_off[k]) return set_error(ICNV_E_BAD_ARG, "chr_grp_off must be non-decreasing");
+    const int n_tot = chr_grp_off[K];
+    if (n_tot <= 0) return set_error(ICNV_E_BAD_ARG, "no subcluster given for any chromosome");
+    if ((rc = validate_groups(C, grp_off, grp_idx, n_tot, false))) return rc;
+    // group of every cell on every chromosome, per-group median sd (HMM.R:1122), chromosome of every gene
+    std::vector<int32_t> grp_of((size_t)K * (size_t)C, -1), chr_id((size_t)G, 0);
+    std::vector<double> sdm((size_t)n_tot);
+    for (int k = 0; k < K; ++k) {
+        for (int32_t g = chr_start[k]; g < chr_start[k] + chr_len[k]; ++g) chr_id[(size_t)g] = k;
+        for (int b = chr_grp_off[k]; b < chr_grp_off[k + 1]; ++b)
+            for (int32_t i = grp_off[b]; i < grp_off[b + 1]; ++i) {
+                int32_t &slot = grp_of[(size_t)k * (size_t)C + (size_t)grp_idx[i]];
+                if (slot >= 0) return set_error(ICNV_E_BAD_ARG, "cell %d is in two subclusters of chromosome %d", grp_idx[i], k);
+                slot = b;
+            }
+    }
+    for (int b = 0; b < n_tot; ++b) {
+        std::vector<double> v(sd + (size_t)m * b, sd + (size_t)m * (b + 1));
+        std::sort(v.begin(), v.end());
+        sdm[(size_t)b] = (m & 1) ? v[m / 2] : 0.5 * (v[m / 2 - 1] + v[m / 2]);
+        if (!(sdm[(size_t)b] > 0.0)) return set_error(ICNV_E_BAD_ARG, "state sd must be positive (group %d)", b);
+    }
+    double *dX;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    const int64_t n_idx = grp_off[n_tot];
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)(n_idx + K * C + G));
+    double *d_xm = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_tot);
+    double *d_sd = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)n_tot);
+    uint8_t *d_st = (uint8_t *)scratch(SLOT_STATES, (size_t)G * (size_t)n_tot);
+    uint8_t *d_out = (uint8_t *)scratch(SLOT_SLAB_ST0, (size_t)(G * C));
+    int *d_flag = (int *)scratch(SLOT_MISC, 64);
+    if (!d_idx || !d_xm || !d_sd || !d_st || !d_out || !d_flag) return ICNV_E_NOMEM;
+    int32_t *d_grp_of = d_idx + n_idx, *d_chr_id = d_grp_of + (int64_t)K * C;
+    ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, grp_idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemcpyAsync(d_grp_of, grp_of.data(), sizeof(int32_t) * grp_of.size(), cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemcpyAsync(d_chr_id, chr_id.data(), sizeof(int32_t) * (size_t)G, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(cudaMemcpyAsync(d_sd, sdm.data(), sizeof(double) * (size_t)n_tot, cudaMemcpyHostToDevice, st));
+    // rowMeans of every (chromosome, subcluster) column over ALL genes - only its own chromosome's rows are used
+    // below; the Viterbi of the other chromosomes' rows is redundant work on a G x n_tot matrix, small next to the
+    // G x C upload
+    if ((rc = dev_group_means(dX, G, G, d_idx, grp_off, n_tot, 0, d_xm, st))) return rc;
+    rc = icnv_dev_viterbi_f64(d_xm, G, n_tot, chr_start, chr_len, K, m, Pi, delta, mean, d_sd, 1, d_st, nullptr, d_flag, st);
+    if (rc) return rc;
+    if ((rc = icnv_dev_scatter_states_per_chr_u8(d_st, G, C, d_chr_id, d_grp_of, d_out, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(states, d_out, (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    return check_flag(d_flag, st);   // synchronises: the host tables above outlive the copies
+}
+
 // ---- CNV region calling on the state matrix (R/inferCNV_HMM.R:706-1087) ----------------------------------------
 
 static int check_state_flag(int *d_flag, cudaStream_t st) {
@@ -856,6 +923,36 @@ int icnv_state_consensus_u8(const uint8_t *states, int64_t G, int64_t C, const i
     uint8_t *d_cons;
     if ((rc = host_consensus(states, G, C, grp_off, grp_idx, n_grp, &d_cons, st))) return rc;
     ICNV_CUDA(cudaMemcpyAsync(consensus, d_cons, (size_t)G * (size_t)n_grp, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+/* get_predicted_CNV_regions(by = "subcluster") + the overwrite loop of HMM.R:472-483 as one pass */
+int icnv_apply_state_consensus_u8(const uint8_t *states, int64_t G, int64_t C, const int32_t *chr_start,
+                                  const int32_t *chr_len, int K, const int32_t *grp_off, const int32_t *grp_idx, int n_grp,
+                                  uint8_t *out) {
+    ICNV_HOST_PROLOGUE();
+    if (!states || !out || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_apply_state_consensus_u8: bad argument");
+    int rc = validate_chr(G, chr_start, chr_len, K);
+    if (rc) return rc;
+    if ((rc = validate_groups(C, grp_off, grp_idx, n_grp, false))) return rc;
+    std::vector<int32_t> tab((size_t)(G + C), -1);     // chr_of[G] (-1: chromosome with < 2 genes) | grp_of[C]
+    for (int k = 0; k < K; ++k)
+        for (int32_t g = chr_start[k]; g < chr_start[k] + chr_len[k]; ++g) tab[(size_t)g] = chr_len[k] >= 2 ? k : -1;
+    for (int b = 0; b < n_grp; ++b)
+        for (int32_t i = grp_off[b]; i < grp_off[b + 1]; ++i) {
+            if (tab[(size_t)G + (size_t)grp_idx[i]] >= 0) return set_error(ICNV_E_BAD_ARG, "cell %d is in two groups", grp_idx[i]);
+            tab[(size_t)G + (size_t)grp_idx[i]] = b;
+        }
+    uint8_t *d_cons;
+    if ((rc = host_consensus(states, G, C, grp_off, grp_idx, n_grp, &d_cons, st))) return rc;   // states now in SLOT_STATES
+    const uint8_t *dS = (const uint8_t *)ctx().slot_ptr[SLOT_STATES];
+    int32_t *d_tab = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * tab.size());
+    uint8_t *d_out = (uint8_t *)scratch(SLOT_SLAB_ST0, (size_t)(G * C));
+    if (!d_tab || !d_out) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int32_t) * tab.size(), cudaMemcpyHostToDevice, st));
+    if ((rc = icnv_dev_apply_consensus_u8(dS, d_cons, G, C, d_tab, d_tab + G, d_out, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(out, d_out, (size_t)(G * C), cudaMemcpyDeviceToHost, st));
     ICNV_CUDA(cudaStreamSynchronize(st));
     return ICNV_OK;
 }

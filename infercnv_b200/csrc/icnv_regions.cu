@@ -246,6 +246,37 @@ __global__ void __launch_bounds__(256) region_finish_kernel(int64_t n, const int
     }
 }
 
+// predict_CNV_via_HMM_on_tumor_subclusters_per_chr (HMM.R:412-487): every chromosome has its own partition of the
+// cells.  gs holds one state sequence per (chromosome, group) column; cell c takes, on the genes of chromosome k,
+// the sequence of its group on that chromosome: out[g, c] = gs[g, grp_of[chr(g) * C + c]], 255 (R's -1) if it has none.
+__global__ void __launch_bounds__(256) scatter_states_per_chr_kernel(const uint8_t *__restrict__ gs, int64_t G, int64_t C,
+                                                                     const int32_t *__restrict__ chr_id,
+                                                                     const int32_t *__restrict__ grp_of,
+                                                                     uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < G * C; i += stride) {
+        const int64_t c = i / G, g = i - c * G;
+        const int grp = grp_of[(int64_t)chr_id[g] * C + c];
+        out[i] = grp < 0 ? (uint8_t)RG_UNASSIGNED : gs[g + G * grp];
+    }
+}
+
+// the consensus step that ends that driver (HMM.R:472-483): every cell of a group takes the group's consensus state
+// on the genes region calling covers (chromosomes with >= 2 genes, chr_of >= 0); everything else keeps its state
+__global__ void __launch_bounds__(256) apply_consensus_kernel(const uint8_t *__restrict__ S, const uint8_t *__restrict__ cons,
+                                                              int64_t G, int64_t C, const int32_t *__restrict__ chr_of,
+                                                              const int32_t *__restrict__ grp_of,
+                                                              uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < G * C; i += stride) {
+        const int64_t c = i / G, g = i - c * G;
+        const int grp = grp_of[c];
+        out[i] = (grp >= 0 && chr_of[g] >= 0) ? cons[g + G * grp] : S[i];
+    }
+}
+
 static inline int64_t round_up4(int64_t n) { return (n + 3) & ~(int64_t)3; }
 
 // record arrays inside SLOT_RG_REC for n regions
@@ -404,6 +435,28 @@ int icnv_dev_cnv_regions_u8(const uint8_t *d_seqs, int64_t G, int64_t lds, int64
     ICNV_CUDA(cudaStreamSynchronize(st));
     c.rg_n = n;
     *n_regions = n;
+    return ICNV_OK;
+}
+
+int icnv_dev_scatter_states_per_chr_u8(const uint8_t *gs, int64_t G, int64_t C, const int32_t *d_chr_id, const int32_t *d_grp_of,
+                                       uint8_t *out, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!gs || !d_chr_id || !d_grp_of || !out || G <= 0 || C <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_dev_scatter_states_per_chr_u8: bad argument");
+    const int64_t blocks = std::min<int64_t>((G * C + 255) / 256, (int64_t)ctx().sm_count * 32);
+    scatter_states_per_chr_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(gs, G, C, d_chr_id, d_grp_of, out);
+    ICNV_CHECK_LAUNCH("scatter_states_per_chr_kernel");
+    return ICNV_OK;
+}
+
+int icnv_dev_apply_consensus_u8(const uint8_t *S, const uint8_t *cons, int64_t G, int64_t C, const int32_t *d_chr_of,
+                                const int32_t *d_grp_of, uint8_t *out, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!S || !cons || !d_chr_of || !d_grp_of || !out || G <= 0 || C <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_dev_apply_consensus_u8: bad argument");
+    const int64_t blocks = std::min<int64_t>((G * C + 255) / 256, (int64_t)ctx().sm_count * 32);
+    apply_consensus_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(S, cons, G, C, d_chr_of, d_grp_of, out);
+    ICNV_CHECK_LAUNCH("apply_consensus_kernel");
     return ICNV_OK;
 }
 

@@ -300,6 +300,32 @@ def predict_CNV_via_HMM_on_tumor_subclusters(infercnv_obj: Infercnv, cnv_mean_sd
     return _run_hmm(infercnv_obj, Pi, delta, mean, sds, groups)
 
 
+def predict_CNV_via_HMM_on_tumor_subclusters_per_chr(infercnv_obj: Infercnv, subclusters_per_chr, cnv_mean_sd: dict,
+                                                     cnv_level_to_mean_sd_fit: dict, t: float = 1e-6) -> Infercnv:
+    """R/inferCNV_HMM.R:412-487.  subclusters_per_chr: {chromosome code: [cell index arrays]} - a partition of the
+    cells per chromosome (Leiden per chromosome in the reference).  One trace per (chromosome, subcluster) on its
+    rowMeans, then every tumour subcluster takes its consensus state per gene (get_predicted_CNV_regions by
+    "subcluster" + the overwrite loop, :470-483)."""
+    log.info("predict_CNV_via_HMM_on_tumor_subclusters_per_chr")
+    if subclusters_per_chr is None:
+        log.warning("No subclusters defined, so instead running on whole samples")
+        return predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj, True, cnv_mean_sd, cnv_level_to_mean_sd_fit, t)
+    Pi, delta, mean, _ = get_HMM(cnv_mean_sd, t)
+    cs, cl = infercnv_obj.chr_ranges()
+    per = [[np.asarray(g) for g in subclusters_per_chr[infercnv_obj.gene_order_chr[s]]] for s in cs]
+    sds = np.concatenate([_state_emission_sds(len(g), cnv_mean_sd, cnv_level_to_mean_sd_fit) for p_ in per for g in p_])
+    states = api.viterbi_per_chr(infercnv_obj.expr_data, cs, cl, per, Pi, delta, mean, sds)
+    log.info("-done predicting CNV based on per chromosome subclusters")
+    log.info("-calculating initial tumor subclusters CNV consensus based on per chromosome predictions")
+    groups = [np.asarray(idx) for sub in infercnv_obj.tumor_subclusters["subclusters"].values() for idx in sub.values()]
+    states = api.apply_state_consensus(states, cs, cl, groups)
+    out = copy.copy(infercnv_obj)
+    st = states.astype(np.float64)
+    st[states == 255] = -1.0                     # the wire format's "unassigned" back to R's -1 (marshalling)
+    out.expr_data = np.asfortranarray(st)
+    return out
+
+
 def predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj: Infercnv, cluster_by_groups: bool, cnv_mean_sd: dict,
                                                cnv_level_to_mean_sd_fit: dict, t: float = 1e-6) -> Infercnv:
     """R/inferCNV_HMM.R:509-567."""

@@ -204,6 +204,31 @@ b200_clear_noise_via_ref_mean_sd <- function(infercnv_obj, sd_amplifier=1.5, noi
     infercnv_obj
 }
 
+## predict_CNV_via_HMM_on_tumor_subclusters_per_chr, R/inferCNV_HMM.R:412 (Leiden + per_chr_hmm_subclusters)
+b200_predict_CNV_via_HMM_on_tumor_subclusters_per_chr <- function(infercnv_obj, subclusters_per_chr,
+        cnv_mean_sd=infercnv:::get_spike_dists(infercnv_obj@.hspike),
+        cnv_level_to_mean_sd_fit=infercnv:::get_hspike_cnv_mean_sd_trend_by_num_cells_fit(infercnv_obj@.hspike), t=1e-6) {
+    orig <- .icnv_env$orig$predict_CNV_via_HMM_on_tumor_subclusters_per_chr
+    m <- infercnv_obj@expr.data
+    codes <- .icnv_chr_codes(infercnv_obj)
+    if (is.null(subclusters_per_chr) || !.icnv_enabled() || !.icnv_ok(m) || is.null(codes))
+        return(orig(infercnv_obj, subclusters_per_chr, cnv_mean_sd, cnv_level_to_mean_sd_fit, t))
+    futile.logger::flog.info("predict_CNV_via_HMM_on_tumor_subclusters_per_chr (B200)")
+    chrs <- unique(infercnv_obj@gene_order$chr)
+    per <- lapply(chrs, function(chr) lapply(subclusters_per_chr[[chr]], as.integer))
+    flat <- unlist(per, recursive=FALSE)
+    sds <- unlist(lapply(flat, function(g)
+        infercnv:::.get_state_emission_params(length(g), cnv_mean_sd, cnv_level_to_mean_sd_fit)$sd))
+    HMM_info <- infercnv:::.get_HMM(cnv_mean_sd, t)
+    tumor_subclusters <- lapply(unlist(infercnv_obj@tumor_subclusters[["subclusters"]], recursive=FALSE), as.integer)
+    res <- tryCatch(.Call("icnvR_viterbi_per_chr", m, codes, flat, as.integer(cumsum(c(0L, lengths(per)))),
+                          HMM_info[["state_transitions"]], HMM_info[["delta"]], HMM_info[["state_emission_params"]]$mean,
+                          as.double(sds), tumor_subclusters), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj, subclusters_per_chr, cnv_mean_sd, cnv_level_to_mean_sd_fit, t))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    infercnv_obj
+}
+
 ## remove_outliers_norm, R/inferCNV_ops.R:1969 (run() step 16)
 b200_remove_outliers_norm <- function(infercnv_obj, out_method="average_bound", lower_bound=NA, upper_bound=NA) {
     orig <- .icnv_env$orig$remove_outliers_norm
@@ -295,7 +320,8 @@ infercnvb200_install <- function() {
              "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
              "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
              "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd",
-             "get_predicted_CNV_regions", "remove_outliers_norm", "clear_noise")
+             "get_predicted_CNV_regions", "remove_outliers_norm", "clear_noise",
+             "predict_CNV_via_HMM_on_tumor_subclusters_per_chr")
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")

@@ -307,6 +307,36 @@ SEXP icnvR_clear_noise_threshold(SEXP expr, SEXP cells, SEXP threshold, SEXP noi
     return ans;
 }
 
+/* predict_CNV_via_HMM_on_tumor_subclusters_per_chr (HMM.R:412-487): groups = the subclusters of all chromosomes, one
+ * after the other (list of 1-based integer vectors), chr_grp_off = where each chromosome's subclusters start (0-based
+ * offsets into that list, K + 1 entries), sds = m values per subcluster.  The per-chromosome traces and the final
+ * per-subcluster consensus (consensus_groups: the tumour subclusters) are both done in the library. */
+SEXP icnvR_viterbi_per_chr(SEXP expr, SEXP chr_codes, SEXP groups, SEXP chr_grp_off, SEXP Pi, SEXP delta, SEXP mean, SEXP sds,
+                           SEXP consensus_groups) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int m = Rf_length(delta);
+    int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL, *coff = NULL, *cidx = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    int n_grp = list_to_csr(groups, &off, &idx);
+    int n_cons = list_to_csr(consensus_groups, &coff, &cidx);
+    uint8_t *st = (uint8_t *)malloc((size_t)(G * C));
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = (K < 0 || n_grp < 0 || n_cons < 0 || !st || Rf_length(chr_grp_off) != K + 1) ? ICNV_E_NOMEM : 0;
+    if (rc == 0)
+        rc = icnv_viterbi_per_chr_u8_f64(REAL(expr), G, C, cs, cl, K, INTEGER(chr_grp_off), off, idx, m, REAL(Pi), REAL(delta),
+                                         REAL(mean), REAL(sds), st);
+    if (rc == 0 && n_cons > 0) rc = icnv_apply_state_consensus_u8(st, G, C, cs, cl, K, coff, cidx, n_cons, st);
+    if (rc == 0) {
+        double *out = REAL(ans);
+        for (int64_t i = 0; i < G * C; ++i) out[i] = st[i] == 255 ? -1.0 : (double)st[i];
+    }
+    free(cs); free(cl); free(off); free(idx); free(coff); free(cidx); free(st);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
 SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
 
 static const R_CallMethodDef call_methods[] = {
@@ -317,6 +347,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_normalize", (DL_FUNC)&icnvR_normalize, 2},       {"icnvR_clear_noise", (DL_FUNC)&icnvR_clear_noise, 3},
     {"icnvR_cnv_regions", (DL_FUNC)&icnvR_cnv_regions, 5},   {"icnvR_csc_normalize", (DL_FUNC)&icnvR_csc_normalize, 5},
     {"icnvR_remove_outliers", (DL_FUNC)&icnvR_remove_outliers, 3},
+    {"icnvR_viterbi_per_chr", (DL_FUNC)&icnvR_viterbi_per_chr, 9},
     {"icnvR_clear_noise_threshold", (DL_FUNC)&icnvR_clear_noise_threshold, 4},
     {NULL, NULL, 0}};
 

@@ -32,7 +32,7 @@ NEVER = ["test_device_resident_states_from_the_viterbi_kernel_to_regions", "test
 SLOW = ["test_multi_slab_host_pipeline_and_fused_call", "test_oligodendroglioma_hmm_cells_and_samples",
         "test_oligodendroglioma_smooth_block_two_ref_groups", "test_viterbi_modes_agree_with_oracle_at_scale"]
 files = ["test_gpu_ops_mirror.py", "test_gpu_parity.py", "test_gpu_widen_denoise.py", "test_gpu_widen_elementwise.py",
-         "test_gpu_widen_ingest.py", "test_gpu_widen_regions.py"]
+         "test_gpu_widen_hmm_per_chr.py", "test_gpu_widen_ingest.py", "test_gpu_widen_regions.py"]
 skip = NEVER + ([] if full else SLOW)
 args = [os.path.join(ROOT, "tests", f) for f in files]
 args += ["-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", " and ".join("not " + d for d in skip)] + extra
