@@ -27,13 +27,14 @@ EMULATED = ["icnv_api.cu", "icnv_regions.cu", "icnv_ingest.cu", "icnv_reduce.cu"
 
 # The asynchronous-copy primitives (inline PTX) get synchronous stand-ins: the copy happens when it is issued - the
 # earliest moment the hardware could perform it, so a buffer that is still being read when its refill is issued shows
-# up as wrong results - and the completion mechanisms are satisfied by construction.  An mbarrier is emulated as a
-# count of completed phases; waiting for a phase that no issued copy can complete aborts instead of spinning.
+# up as wrong results.  An mbarrier is emulated as a count of completed phases; a thread waiting for a phase that is not
+# complete yet yields to the other threads of the block (the issuing thread may not have run yet), and a block in
+# which everybody only waits is reported as a dead-lock.
 PTX_STANDINS = {
     "mbar_init": "{ (void)count; *reinterpret_cast<unsigned long long *>(bar) = 0ull; }",
     "mbar_expect_tx": "{ (void)bar; (void)bytes; }",
     "bulk_g2s": "{ memcpy(dst, src, bytes); *reinterpret_cast<unsigned long long *>(bar) += 1ull; }",
-    "mbar_wait": "{ if (((*reinterpret_cast<unsigned long long *>(bar)) & 1ull) == parity) { fprintf(stderr, \"emu: mbarrier wait on a phase no copy completes\\n\"); abort(); } }",
+    "mbar_wait": "{ while (((*reinterpret_cast<volatile unsigned long long *>(bar)) & 1ull) == parity) emu::spin_yield(); }",
     "fence_proxy_async": "{ }",
     "cp_async8": "{ if (valid) memcpy(smem_dst, gsrc, 8); else memset(smem_dst, 0, 8); }",
     "cp_async_commit": "{ }",

@@ -129,6 +129,7 @@ struct Fiber {
     ucontext_t ctx;
     State state = DONE;
     unsigned gen = 0;          // number of warp collectives this thread has entered
+    bool spun = false;         // came back from a spin-wait iteration (made no progress of its own)
 };
 constexpr size_t STACK_BYTES = 64 * 1024;
 constexpr int MAX_THREADS = 1024;
@@ -144,8 +145,26 @@ constexpr size_t DYN_SMEM_MAX = 227 * 1024;
 alignas(128) inline unsigned char dyn_smem[DYN_SMEM_MAX];
 inline size_t dyn_smem_bytes = 0;
 inline unsigned long long launches = 0, blocks_run = 0;
+inline int order_mode = -1;                 // 0 forward, 1 reverse, 2 random
+inline unsigned long long order_rng = 1;
+inline void read_order_mode() {
+    if (order_mode >= 0) return;
+    const char *e = getenv("EMU_ORDER");
+    order_mode = 0;
+    if (e && !strncmp(e, "reverse", 7)) order_mode = 1;
+    if (e && !strncmp(e, "random", 6)) {
+        order_mode = 2;
+        order_rng = e[6] == ':' ? strtoull(e + 7, nullptr, 10) * 2 + 1 : 12345;
+    }
+}
 
 inline void yield_to_scheduler() { swapcontext(&cur->ctx, &sched_ctx); }
+// one iteration of a spin-wait on memory another thread (or an asynchronous copy) will write: stay runnable, let the
+// others run.  A block in which every runnable thread only spins, pass after pass, is reported as a dead-lock.
+inline void spin_yield() {
+    cur->spun = true;
+    yield_to_scheduler();
+}
 inline void trampoline() {
     (*body)();
     cur->state = DONE;
@@ -173,7 +192,7 @@ inline void run_block(unsigned nt, const std::function<void()> &fn) {
     memset(warp_posted, 0, sizeof(warp_posted));
     if (dyn_smem_bytes) memset(dyn_smem, 0xA5, dyn_smem_bytes);     // shared memory starts undefined in every block
     unsigned alive = nt;
-    unsigned long long passes = 0;
+    unsigned long long passes = 0, idle_passes = 0;
     while (alive > 0) {
         if (++passes == 200000000ull) {     // no kernel of this library synchronises this often: a live-lock
             unsigned st[4] = {0, 0, 0, 0};
@@ -182,14 +201,27 @@ inline void run_block(unsigned nt, const std::function<void()> &fn) {
                     blockIdx.x, blockIdx.y, st[0], st[1], st[2], st[3]);
             abort();
         }
-        bool ran = false;
-        for (unsigned t = 0; t < nt; ++t) {
+        bool ran = false, progress = false;
+        // EMU_ORDER: the order in which the runnable threads of a block are resumed within a scheduler pass -
+        // "forward" (default), "reverse", or "random[:seed]" (a fresh odd-stride permutation every pass).  A kernel
+        // whose results depend on it has a data race (a missing barrier, an unsynchronised hand-off).
+        unsigned start = 0, step = 1;
+        if (order_mode == 1) { start = nt - 1; step = nt - 1; }
+        else if (order_mode == 2) {
+            order_rng = order_rng * 6364136223846793005ull + 1442695040888963407ull;
+            start = (unsigned)(order_rng >> 33) % nt;
+            step = ((unsigned)(order_rng >> 13) % nt) | 1u;          // odd stride: a permutation for power-of-two-multiple sizes
+            if (std::__gcd(step, nt) != 1) step = 1;
+        }
+        for (unsigned i = 0, t = start; i < nt; ++i, t = (t + step) % nt) {
             Fiber &f = fibers[t];
             if (f.state != RUN) continue;
             cur = &f;
             threadIdx.x = t;
+            f.spun = false;
             swapcontext(&sched_ctx, &f.ctx);
             ran = true;
+            progress |= !f.spun;
             if (f.state == DONE) --alive;
         }
         if (alive == 0) break;
@@ -215,6 +247,11 @@ inline void run_block(unsigned nt, const std::function<void()> &fn) {
                     if (fibers[t].state == WAIT_BLOCK) fibers[t].state = RUN;
                 released = true;
             }
+        }
+        idle_passes = (progress || released) ? 0 : idle_passes + 1;
+        if (idle_passes > 1000000) {
+            fprintf(stderr, "emu: block (%u,%u): every runnable thread spins on a condition nobody satisfies\n", blockIdx.x, blockIdx.y);
+            abort();
         }
         if (!released && !ran) {
             fprintf(stderr, "emu: divergent synchronisation in block (%u,%u): the live threads wait at different barriers\n",
@@ -242,15 +279,17 @@ inline void watchdog_handler(int) {
 }
 inline void arm_watchdog() {
     static bool armed = false;
-    const char *e = getenv("EMU_WATCHDOG");
+    const char *e = getenv("EMU_WATCHDOG");      // also turns an abort() anywhere into a native backtrace
     if (armed || !e) return;
     armed = true;
+    signal(SIGABRT, watchdog_handler);
     signal(SIGALRM, watchdog_handler);
     alarm((unsigned)atoi(e));
 }
 
 inline void launch(const Cfg &cfg, const std::function<void()> &fn) {
     arm_watchdog();
+    read_order_mode();
     if (cfg.block.y != 1 || cfg.block.z != 1 || cfg.grid.z != 1) {
         fprintf(stderr, "emu: only (x, y) grids of 1-D blocks are supported\n");
         abort();

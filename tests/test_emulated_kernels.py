@@ -21,9 +21,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
-def test_gpu_parity_tests_pass_under_the_host_emulation():
+@pytest.mark.parametrize("order", ["forward", "reverse"])
+def test_gpu_parity_tests_pass_under_the_host_emulation(order):
+    """`order` = the order in which the emulation resumes the runnable threads of a block (EMU_ORDER; "random:<seed>"
+    also exists): results that depend on it would mean a data race - a missing barrier or an unsynchronised hand-off
+    through shared memory - in one of the kernels."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host", "run_emulated.py")], capture_output=True, text=True,
-                       timeout=1500)
+                       timeout=1500, env=dict(os.environ, EMU_ORDER=order))
     tail = "\n".join(r.stdout.splitlines()[-25:]) + r.stderr[-2000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
