@@ -145,11 +145,41 @@ b200_predict_CNV_via_HMM_on_whole_tumor_samples <- function(infercnv_obj, cluste
     infercnv_obj
 }
 
-## i3HMM_predict_CNV_via_HMM_on_indiv_cells, R/inferCNV_i3HMM.R:180 (group twins analogous; sd_trend stays R's)
+## i3HMM_predict_CNV_via_HMM_on_indiv_cells, R/inferCNV_i3HMM.R:180 (sd_trend stays R's; group twins below)
 b200_i3HMM_predict_CNV_via_HMM_on_indiv_cells <- function(infercnv_obj, i3_p_val=0.05,
         sd_trend=infercnv:::.i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val), t=1e-6, use_KS=TRUE) {
     res <- .icnv_hmm(infercnv_obj, infercnv:::.i3HMM_get_HMM(sd_trend, t=t, i3_p_val=i3_p_val, use_KS=use_KS))
     if (is.null(res)) return(.icnv_env$orig$i3HMM_predict_CNV_via_HMM_on_indiv_cells(infercnv_obj, i3_p_val, sd_trend, t, use_KS))
+    infercnv_obj@expr.data <- res
+    infercnv_obj
+}
+
+## i3HMM_predict_CNV_via_HMM_on_tumor_subclusters, R/inferCNV_i3HMM.R:249: one trace per subcluster on rowMeans, the
+## same three-state parameters for every group (no group-size dependent sd in the i3 model)
+b200_i3HMM_predict_CNV_via_HMM_on_tumor_subclusters <- function(infercnv_obj, i3_p_val=0.05,
+        sd_trend=infercnv:::.i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val), t=1e-6, use_KS=TRUE) {
+    orig <- .icnv_env$orig$i3HMM_predict_CNV_via_HMM_on_tumor_subclusters
+    if (is.null(infercnv_obj@tumor_subclusters)) return(orig(infercnv_obj, i3_p_val, sd_trend, t, use_KS))
+    groups <- lapply(unlist(infercnv_obj@tumor_subclusters[["subclusters"]], recursive=FALSE), as.integer)
+    HMM_info <- infercnv:::.i3HMM_get_HMM(sd_trend, t=t, i3_p_val=i3_p_val, use_KS=use_KS)
+    res <- .icnv_hmm(infercnv_obj, HMM_info, groups, rep(HMM_info[["state_emission_params"]]$sd, length(groups)))
+    if (is.null(res)) return(orig(infercnv_obj, i3_p_val, sd_trend, t, use_KS))
+    infercnv_obj@expr.data <- res
+    infercnv_obj
+}
+
+## i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples, R/inferCNV_i3HMM.R:332
+b200_i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples <- function(infercnv_obj, cluster_by_groups, i3_p_val=0.05,
+        sd_trend=infercnv:::.i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val), t=1e-6, use_KS=TRUE) {
+    obs <- infercnv_obj@observation_grouped_cell_indices
+    groups <- c(if (isTRUE(cluster_by_groups)) obs else list(all_observations = unlist(obs)),
+                infercnv_obj@reference_grouped_cell_indices)
+    groups <- lapply(groups, as.integer)
+    HMM_info <- infercnv:::.i3HMM_get_HMM(sd_trend, t=t, i3_p_val=i3_p_val, use_KS=use_KS)
+    res <- .icnv_hmm(infercnv_obj, HMM_info, groups, rep(HMM_info[["state_emission_params"]]$sd, length(groups)))
+    if (is.null(res))
+        return(.icnv_env$orig$i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj, cluster_by_groups, i3_p_val,
+                                                                               sd_trend, t, use_KS))
     infercnv_obj@expr.data <- res
     infercnv_obj
 }
@@ -321,7 +351,8 @@ infercnvb200_install <- function() {
              "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
              "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd",
              "get_predicted_CNV_regions", "remove_outliers_norm", "clear_noise",
-             "predict_CNV_via_HMM_on_tumor_subclusters_per_chr")
+             "predict_CNV_via_HMM_on_tumor_subclusters_per_chr", "i3HMM_predict_CNV_via_HMM_on_tumor_subclusters",
+             "i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples")
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")

@@ -21,5 +21,49 @@ def test_r_wrappers_name_every_replaced_function():
     for fn in ["subtract_ref_expr_from_obs", "smooth_by_chromosome", "center_cell_expr_across_chromosome",
                "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
                "predict_CNV_via_HMM_on_whole_tumor_samples", "i3HMM_predict_CNV_via_HMM_on_indiv_cells",
-               "apply_median_filtering", "get_predicted_CNV_regions"]:
+               "apply_median_filtering", "get_predicted_CNV_regions", "remove_outliers_norm", "clear_noise",
+               "predict_CNV_via_HMM_on_tumor_subclusters_per_chr", "i3HMM_predict_CNV_via_HMM_on_tumor_subclusters",
+               "i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples", "normalize_counts_by_seq_depth",
+               "clear_noise_via_ref_mean_sd"]:
         assert f"b200_{fn} <- function" in src and f'"{fn}"' in src
+
+
+def test_r_wrappers_have_balanced_brackets_and_registered_call_names():
+    """R is not installable here, so the R file gets the checks that do not need an interpreter: brackets balance
+    outside strings and comments, and every .Call("icnvR_...") names a routine the shim registers."""
+    import re
+    src = open(os.path.join(ROOT, "infercnv_b200", "r", "infercnv_b200.R")).read()
+    stack, line, in_str, i = [], 1, None, 0
+    pairs = {")": "(", "]": "[", "}": "{"}
+    while i < len(src):
+        ch = src[i]
+        if ch == "\n":
+            line += 1
+        if in_str:
+            if ch == "\\":
+                i += 1
+            elif ch == in_str:
+                in_str = None
+        elif ch in "\"'":
+            in_str = ch
+        elif ch == "#":
+            while i < len(src) and src[i] != "\n":
+                i += 1
+            line += 1
+        elif ch in "([{":
+            stack.append((ch, line))
+        elif ch in ")]}":
+            assert stack and stack[-1][0] == pairs[ch], f"unbalanced {ch!r} at line {line}"
+            stack.pop()
+        i += 1
+    assert not stack and in_str is None, f"unclosed {stack[-1] if stack else in_str}"
+    shim = open(os.path.join(ROOT, "infercnv_b200", "r", "infercnvb200_shim.c")).read()
+    registered = dict(re.findall(r'\{"(icnvR_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim))
+    for name, args in re.findall(r'\.Call\("(icnvR_\w+)"((?:[^()]|\((?:[^()]|\((?:[^()]|\([^()]*\))*\))*\))*)\)', src):
+        assert name in registered, f"{name} is not registered in the shim"
+        depth, n = 0, 0
+        for ch in args:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            n += ch == "," and depth == 0
+        assert n == int(registered[name]), f"{name}: {n} arguments passed, {registered[name]} registered"
