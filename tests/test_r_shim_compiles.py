@@ -59,11 +59,17 @@ def test_r_wrappers_have_balanced_brackets_and_registered_call_names():
     assert not stack and in_str is None, f"unclosed {stack[-1] if stack else in_str}"
     shim = open(os.path.join(ROOT, "infercnv_b200", "r", "infercnvb200_shim.c")).read()
     registered = dict(re.findall(r'\{"(icnvR_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim))
-    for name, args in re.findall(r'\.Call\("(icnvR_\w+)"((?:[^()]|\((?:[^()]|\((?:[^()]|\([^()]*\))*\))*\))*)\)', src):
-        assert name in registered, f"{name} is not registered in the shim"
-        depth, n = 0, 0
-        for ch in args:
+    calls = []
+    for m in re.finditer(r'\.Call\("(icnvR_\w+)"', src):
+        depth, n, j = 1, 0, m.end()
+        while depth:                      # walk to the matching parenthesis, counting top-level commas
+            ch = src[j]
             depth += ch in "([{"
             depth -= ch in ")]}"
-            n += ch == "," and depth == 0
+            n += ch == "," and depth == 1
+            j += 1
+        calls.append((m.group(1), n))
+    assert len(calls) >= 13
+    for name, n in calls:
+        assert name in registered, f"{name} is not registered in the shim"
         assert n == int(registered[name]), f"{name}: {n} arguments passed, {registered[name]} registered"
