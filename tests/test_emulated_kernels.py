@@ -33,6 +33,16 @@ def test_gpu_parity_tests_pass_under_the_host_emulation(order):
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
 
 
+@pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
+def test_differential_fuzz_of_edge_shapes_under_the_host_emulation():
+    """Random small shapes - single genes / cells, one-gene chromosomes, windows longer than a chromosome, constant and
+    tie-dominated columns, groups of one - through smooth block, centring, both Viterbi arithmetics (cells and groups,
+    i6 and i3), median filter and region calling, each against the oracle (tests/host/fuzz_emulated.py)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host", "fuzz_emulated.py"), "40", "20260923"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "40 cases ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_the_package_cannot_reach_the_emulated_library():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "infercnv_b200")):
         for f in files:
