@@ -224,6 +224,10 @@ ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int
  * Any of the three outputs may be NULL. */
 ICNV_API int icnv_gene_stats_f64(const double *X, int64_t G, int64_t C, double *sums, int32_t *n_pos, double *means);
 
+/* scale_infercnv_expr, R/inferCNV_ops.R:3174-3186 (run() step 5, scale_data = TRUE): t(scale(t(expr))) - every gene
+ * (row) centred at its mean over the cells and divided by its sd (n - 1).  A constant gene gives NaN, as in R. */
+ICNV_API int icnv_scale_infercnv_expr_f64(const double *X, double *Y, int64_t G, int64_t C);
+
 /* remove_genes, R/inferCNV.R:445-457: Y (n_keep x C) = X[keep, ]; keep = increasing 0-based row indices. */
 ICNV_API int icnv_remove_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *keep, int64_t n_keep,
                                    double *Y);

@@ -438,3 +438,12 @@ def apply_state_consensus(states, chr_start, chr_len, groups) -> np.ndarray:
     _lib.check(_lib.load().icnv_apply_state_consensus_u8(_p(S), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx), len(groups),
                                                          _p(out)))
     return out
+
+
+def scale_infercnv_expr(X) -> np.ndarray:
+    """Per-gene z-scores across the cells (icnv_scale_infercnv_expr_f64)."""
+    X = _f64(X)
+    G, C = X.shape
+    Y = np.empty_like(X, order="F")
+    _lib.check(_lib.load().icnv_scale_infercnv_expr_f64(_p(X), _p(Y), G, C))
+    return Y

@@ -30,6 +30,7 @@ int icnv_dev_logistic_adj_f64(const double *X, double *Y, int64_t n, double expr
 int icnv_dev_gene_stats_f64(const double *X, int64_t G, int64_t ldx, int64_t C, double *d_sums, int32_t *d_npos, void *stream);
 int icnv_dev_gather_rows_f64(const double *X, int64_t ldx, const int32_t *d_keep, int64_t n_keep, double *Y, int64_t C,
                              void *stream);
+int icnv_dev_scale_rows_f64(const double *X, double *Y, int64_t G, int64_t C, double *d_sums, double *d_ss, void *stream);
 int icnv_dev_csc_gene_stats_f64(const int32_t *d_i, const double *d_x, int64_t nnz, int64_t G, double *d_sums,
                                 int32_t *d_npos, void *stream);
 int icnv_dev_csc_col_sums_f64(const int32_t *d_p, const int32_t *d_i, const double *d_x, const int32_t *d_keep_map,
@@ -710,6 +711,23 @@ int icnv_gene_stats_f64(const double *X, int64_t G, int64_t C, double *sums, int
     if (!d_sums || !d_npos) return ICNV_E_NOMEM;
     if ((rc = icnv_dev_gene_stats_f64(dX, G, G, C, d_sums, d_npos, st))) return rc;
     return download_gene_stats(d_sums, d_npos, G, C, sums, n_pos, means, st);
+}
+
+/* scale_infercnv_expr, R/inferCNV_ops.R:3174-3186 (run() step 5 when scale_data = TRUE): every gene centred and scaled
+ * to unit sd (n - 1) across the cells. */
+int icnv_scale_infercnv_expr_f64(const double *X, double *Y, int64_t G, int64_t C) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_scale_infercnv_expr_f64: bad argument");
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(G * C));
+    double *d_stat = (double *)scratch(SLOT_MEANS, sizeof(double) * 2 * (size_t)G);
+    if (!dY || !d_stat) return ICNV_E_NOMEM;
+    if ((rc = icnv_dev_scale_rows_f64(dX, dY, G, C, d_stat, d_stat + G, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
 }
 
 static int validate_keep(const int32_t *keep, int64_t n_keep, int64_t G) {

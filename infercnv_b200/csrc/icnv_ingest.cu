@@ -117,6 +117,49 @@ __global__ void __launch_bounds__(256) csc_expand_kernel(const int32_t *__restri
     }
 }
 
+// scale_infercnv_expr (R/inferCNV_ops.R:3174-3186: t(scale(t(expr)))) - per gene, over the cells: centre at the mean,
+// divide by sqrt(sum((x - mean)^2) / (C - 1)).  The mean is refined once (mean0 + mean(x - mean0), what R's long-double
+// accumulation amounts to in double), so a constant gene is centred to exact zeros and comes out NaN (0 / 0) as in R.
+// Partial sums in the same fixed chunks as the plain sums.  SQUARE = false: sum of (x - mean); true: sum of squares.
+template <bool SQUARE>
+__global__ void __launch_bounds__(256) gene_centered_partial_kernel(const double *__restrict__ X, int64_t G, int64_t ldx,
+                                                                    int64_t C, const double *__restrict__ mean,
+                                                                    double *__restrict__ part) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= G) return;
+    const double m = mean[g];
+    for (int64_t q = blockIdx.y; q * IG_CHUNK < C; q += gridDim.y) {
+        const int64_t c0 = q * IG_CHUNK, c1 = min(C, c0 + IG_CHUNK);
+        double s = 0.0;
+        for (int64_t c = c0; c < c1; ++c) {
+            const double d = X[g + ldx * c] - m;
+            s = SQUARE ? fma(d, d, s) : s + d;
+        }
+        part[g + G * q] = s;
+    }
+}
+
+// mode 0: out[g] = sum / C; mode 1: out[g] += sum / C (mean refinement); mode 2: out[g] = sum
+__global__ void __launch_bounds__(256) combine_partial_kernel(const double *__restrict__ part, int64_t G, int64_t n_chunks,
+                                                              int64_t C, int mode, double *__restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= G) return;
+    double s = 0.0;
+    for (int64_t q = 0; q < n_chunks; ++q) s += part[g + G * q];
+    if (mode == 0) out[g] = s / (double)C;
+    else if (mode == 1) out[g] = out[g] + s / (double)C;
+    else out[g] = s;
+}
+
+__global__ void __launch_bounds__(256) scale_rows_kernel(const double *__restrict__ X, double *__restrict__ Y, int64_t G, int64_t C,
+                                                         const double *__restrict__ mean, const double *__restrict__ ss) {
+    for (int64_t c = blockIdx.x; c < C; c += gridDim.x)
+        for (int64_t g = threadIdx.x; g < G; g += 256) {
+            const double sd = sqrt(ss[g] / (double)(C > 1 ? C - 1 : 1));     // scale(): max(1, n - 1)
+            Y[g + G * c] = (X[g + G * c] - mean[g]) / sd;
+        }
+}
+
 }  // namespace icnv
 
 using namespace icnv;
@@ -140,6 +183,36 @@ int icnv_dev_gene_stats_f64(const double *X, int64_t G, int64_t ldx, int64_t C, 
     ICNV_CHECK_LAUNCH("gene_stats_partial_kernel");
     gene_stats_combine_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(psum, ppos, G, n_chunks, d_sums, d_npos);
     ICNV_CHECK_LAUNCH("gene_stats_combine_kernel");
+    return ICNV_OK;
+}
+
+/* Y = per-gene z-scores of X over its C columns (X, Y: G x C, ld = G); d_mean, d_ss: scratch of G doubles each */
+int icnv_dev_scale_rows_f64(const double *X, double *Y, int64_t G, int64_t C, double *d_mean, double *d_ss, void *stream) {
+    ICNV_REQUIRE_READY();
+    cudaStream_t st = pick_stream(stream);
+    if (!X || !Y || !d_mean || !d_ss || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_scale_rows_f64: bad argument");
+    const int64_t n_chunks = (C + IG_CHUNK - 1) / IG_CHUNK;
+    char *buf = (char *)scratch(SLOT_PARTIAL, (size_t)G * (size_t)n_chunks * 12);
+    if (!buf) return ICNV_E_NOMEM;
+    double *part = (double *)buf;
+    uint32_t *ppos = (uint32_t *)(buf + (size_t)G * (size_t)n_chunks * 8);
+    const dim3 grid((unsigned)((G + 255) / 256), (unsigned)std::min<int64_t>(n_chunks, 65535));
+    const unsigned gblocks = (unsigned)((G + 255) / 256);
+    gene_stats_partial_kernel<<<grid, 256, 0, st>>>(X, G, G, C, part, ppos);
+    ICNV_CHECK_LAUNCH("gene_stats_partial_kernel");
+    combine_partial_kernel<<<gblocks, 256, 0, st>>>(part, G, n_chunks, C, 0, d_mean);
+    ICNV_CHECK_LAUNCH("combine_partial_kernel");
+    gene_centered_partial_kernel<false><<<grid, 256, 0, st>>>(X, G, G, C, d_mean, part);
+    ICNV_CHECK_LAUNCH("gene_centered_partial_kernel");
+    combine_partial_kernel<<<gblocks, 256, 0, st>>>(part, G, n_chunks, C, 1, d_mean);
+    ICNV_CHECK_LAUNCH("combine_partial_kernel");
+    gene_centered_partial_kernel<true><<<grid, 256, 0, st>>>(X, G, G, C, d_mean, part);
+    ICNV_CHECK_LAUNCH("gene_centered_partial_kernel");
+    combine_partial_kernel<<<gblocks, 256, 0, st>>>(part, G, n_chunks, C, 2, d_ss);
+    ICNV_CHECK_LAUNCH("combine_partial_kernel");
+    const int64_t blocks = std::min<int64_t>(C, (int64_t)ctx().sm_count * 8);
+    scale_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, Y, G, C, d_mean, d_ss);
+    ICNV_CHECK_LAUNCH("scale_rows_kernel");
     return ICNV_OK;
 }
 

@@ -579,3 +579,46 @@ def ingest_sparse_counts(p, i, x, n_genes, gene_order_chr, min_mean_expr_cutoff=
     kept = np.flatnonzero(keep)
     expr = api.csc_normalize(p, i, x, G, keep=kept, normalize_factor=normalize_factor)
     return expr, kept, np.asarray(gene_order_chr)[kept]
+
+
+# ---- optional steps inside the path: scaling (step 5) and chromosome-end removal (step 13) -----------------------------
+
+def scale_infercnv_expr(infercnv_obj: Infercnv) -> Infercnv:
+    """R/inferCNV_ops.R:3174-3186: t(scale(t(expr.data))), mirrored onto the hidden spike."""
+    log.info("-scaling expr data")
+    obj = copy.copy(infercnv_obj)
+    obj.expr_data = api.scale_infercnv_expr(obj.expr_data)
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = scale_infercnv_expr(obj.hspike)
+    return obj
+
+
+def _remove_tails(chr_idx, tail_length):
+    """.remove_tails, R/inferCNV_ops.R:2370-2385: the indices of the first and last tail_length genes of a chromosome
+    (a third of it each when the chromosome is shorter than two tails); nothing for tails or chromosomes below 3."""
+    chr_idx = np.asarray(chr_idx)
+    n = len(chr_idx)
+    if tail_length < 3 or n < 3:
+        return np.zeros(0, dtype=np.int64)
+    if n < tail_length * 2:
+        tail_length = n // 3
+    tail_length = int(tail_length)
+    return np.concatenate([chr_idx[:tail_length], chr_idx[n - tail_length:]])
+
+
+def remove_genes_at_ends_of_chromosomes(infercnv_obj: Infercnv, window_length: int) -> Infercnv:
+    """R/inferCNV_ops.R:3000-3045 (run() step 13 when remove_genes_at_chr_ends = TRUE): drops (window_length - 1) / 2
+    genes at both ends of every chromosome from expr.data, count.data and gene_order."""
+    contig_tail = (window_length - 1) / 2
+    cs, cl = infercnv_obj.chr_ranges()
+    remove = np.concatenate([_remove_tails(np.arange(s, s + n), contig_tail) for s, n in zip(cs, cl)] or [np.zeros(0, np.int64)])
+    if len(remove) == 0:
+        log.error("No genes removed at chr ends.... something wrong here")
+        raise RuntimeError("1234")                                   # stop(1234)
+    obj = remove_genes(infercnv_obj, remove)
+    log.info("::process_data:Remove genes at chr ends, new dimensions (r,c) = %s", ",".join(map(str, obj.expr_data.shape)))
+    if obj.hspike is not None:
+        log.info("-mirroring for hspike")
+        obj.hspike = remove_genes_at_ends_of_chromosomes(obj.hspike, window_length)
+    return obj

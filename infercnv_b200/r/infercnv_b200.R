@@ -259,6 +259,22 @@ b200_predict_CNV_via_HMM_on_tumor_subclusters_per_chr <- function(infercnv_obj, 
     infercnv_obj
 }
 
+## scale_infercnv_expr, R/inferCNV_ops.R:3174 (run() step 5 when scale_data = TRUE)
+b200_scale_infercnv_expr <- function(infercnv_obj) {
+    orig <- .icnv_env$orig$scale_infercnv_expr
+    m <- infercnv_obj@expr.data
+    if (!.icnv_enabled() || !.icnv_ok(m)) return(orig(infercnv_obj))
+    futile.logger::flog.info("-scaling expr data (B200)")
+    res <- tryCatch(.Call("icnvR_scale", m), error = function(e) NULL)
+    if (is.null(res)) return(orig(infercnv_obj))
+    infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    if (!is.null(infercnv_obj@.hspike)) {
+        futile.logger::flog.info("-mirroring for hspike")
+        infercnv_obj@.hspike <- b200_scale_infercnv_expr(infercnv_obj@.hspike)
+    }
+    infercnv_obj
+}
+
 ## remove_outliers_norm, R/inferCNV_ops.R:1969 (run() step 16)
 b200_remove_outliers_norm <- function(infercnv_obj, out_method="average_bound", lower_bound=NA, upper_bound=NA) {
     orig <- .icnv_env$orig$remove_outliers_norm
@@ -352,7 +368,7 @@ infercnvb200_install <- function() {
              "apply_median_filtering", "normalize_counts_by_seq_depth", "clear_noise_via_ref_mean_sd",
              "get_predicted_CNV_regions", "remove_outliers_norm", "clear_noise",
              "predict_CNV_via_HMM_on_tumor_subclusters_per_chr", "i3HMM_predict_CNV_via_HMM_on_tumor_subclusters",
-             "i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples")
+             "i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples", "scale_infercnv_expr")
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")

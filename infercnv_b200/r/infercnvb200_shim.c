@@ -337,6 +337,17 @@ SEXP icnvR_viterbi_per_chr(SEXP expr, SEXP chr_codes, SEXP groups, SEXP chr_grp_
     return ans;
 }
 
+/* scale_infercnv_expr (ops.R:3174-3186) */
+SEXP icnvR_scale(SEXP expr) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    SEXP ans = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = icnv_scale_infercnv_expr_f64(REAL(expr), REAL(ans), G, C);
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
 SEXP icnvR_available(void) { return Rf_ScalarLogical(icnv_device_count() > 0 && icnv_init(-1) == 0); }
 
 static const R_CallMethodDef call_methods[] = {
@@ -347,7 +358,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_normalize", (DL_FUNC)&icnvR_normalize, 2},       {"icnvR_clear_noise", (DL_FUNC)&icnvR_clear_noise, 3},
     {"icnvR_cnv_regions", (DL_FUNC)&icnvR_cnv_regions, 5},   {"icnvR_csc_normalize", (DL_FUNC)&icnvR_csc_normalize, 5},
     {"icnvR_remove_outliers", (DL_FUNC)&icnvR_remove_outliers, 3},
-    {"icnvR_viterbi_per_chr", (DL_FUNC)&icnvR_viterbi_per_chr, 9},
+    {"icnvR_viterbi_per_chr", (DL_FUNC)&icnvR_viterbi_per_chr, 9}, {"icnvR_scale", (DL_FUNC)&icnvR_scale, 1},
     {"icnvR_clear_noise_threshold", (DL_FUNC)&icnvR_clear_noise_threshold, 4},
     {NULL, NULL, 0}};
 

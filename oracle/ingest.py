@@ -67,3 +67,37 @@ def ingest_sparse_counts(p, i, x, n_genes, min_mean_expr_cutoff=None, min_cells_
         D, kept = np.asfortranarray(D[ok]), kept[ok]
     with np.errstate(invalid="ignore", divide="ignore"):
         return orc.normalize_by_seq_depth(D, normalize_factor), kept
+
+
+def scale_infercnv_expr(expr_data) -> np.ndarray:
+    """scale_infercnv_expr, R/inferCNV_ops.R:3174-3186: t(scale(t(x))) - scale() centres every column of t(x) (= every
+    gene) at its long-double mean and divides by sqrt(sum(centred^2) / (n - 1))."""
+    X = np.asarray(expr_data, dtype=np.float64)
+    centred = X - row_means(X)[:, None]
+    acc = np.zeros(X.shape[0], dtype=np.longdouble)
+    for c in range(X.shape[1]):
+        acc += centred[:, c].astype(np.longdouble) ** 2
+    sd = np.sqrt((acc / max(1, X.shape[1] - 1)).astype(np.float64))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.asfortranarray(centred / sd[:, None])
+
+
+def remove_tails(chr_idx, tail_length):
+    """.remove_tails, R/inferCNV_ops.R:2370-2385 (indices as given, so 1-based inputs give the reference's answers)."""
+    chr_idx = list(chr_idx)
+    n = len(chr_idx)
+    if tail_length < 3 or n < 3:
+        return []
+    if n < tail_length * 2:
+        tail_length = n // 3
+    tail_length = int(tail_length)
+    return chr_idx[:tail_length] + chr_idx[n - tail_length:]
+
+
+def genes_removed_at_ends_of_chromosomes(chr_start, chr_len, window_length):
+    """remove_genes_at_ends_of_chromosomes, R/inferCNV_ops.R:3000-3017: 0-based indices to drop."""
+    tail = (window_length - 1) / 2
+    out = []
+    for s, n in zip(chr_start, chr_len):
+        out += remove_tails(range(int(s), int(s) + int(n)), tail)
+    return np.array(out, dtype=np.int64)

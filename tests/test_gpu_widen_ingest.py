@@ -95,3 +95,30 @@ def test_sparse_counts_ingest_matches_the_dense_reference_steps(oligo):
     cols = np.flatnonzero(cs > 0)
     dense = orc.normalize_by_seq_depth(D[:, cols], np.median(cs))
     assert np.array_equal(Y[:, cols], dense)
+
+
+def test_scale_and_chromosome_end_removal(example_object):
+    """run() step 5 (scale_data = TRUE) and step 13 (remove_genes_at_chr_ends = TRUE), both mirrored onto @.hspike."""
+    from infercnv_b200 import ops
+    X = example_object["expr"]
+    G, C = X.shape
+    codes = example_object["chr_codes"]
+    H = np.asfortranarray(X[:, :6] ** 2)
+    obj = ops.Infercnv(expr_data=X, gene_order_chr=codes, gene_names=["g%d" % i for i in range(G)],
+                       gene_order_start=np.arange(G), gene_order_stop=np.arange(G) + 5,
+                       hspike=ops.Infercnv(expr_data=H, gene_order_chr=codes))
+    out = ops.scale_infercnv_expr(obj)
+    np.testing.assert_allclose(out.expr_data, ori.scale_infercnv_expr(X), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(out.hspike.expr_data, ori.scale_infercnv_expr(H), rtol=1e-11, atol=1e-13)
+    const = X.copy(order="F")
+    const[7] = 2.5
+    assert np.all(np.isnan(ops.scale_infercnv_expr(ops.Infercnv(expr_data=const, gene_order_chr=codes)).expr_data[7]))   # 0 / 0
+    cs, cl = orc.chr_ranges(codes)
+    out = ops.remove_genes_at_ends_of_chromosomes(obj, 101)
+    rm = ori.genes_removed_at_ends_of_chromosomes(cs, cl, 101)
+    assert 0 < len(rm) < G
+    keep = np.delete(np.arange(G), rm)
+    assert np.array_equal(out.expr_data, X[keep]) and np.array_equal(out.hspike.expr_data, H[keep])
+    assert out.gene_names == ["g%d" % i for i in keep] and np.array_equal(out.gene_order_chr, codes[keep])
+    with pytest.raises(RuntimeError):
+        ops.remove_genes_at_ends_of_chromosomes(obj, 5)           # tails below 3 genes: nothing to remove -> stop(1234)

@@ -52,3 +52,22 @@ def test_sparse_ingest_equals_dense_steps():
     assert np.all(np.isnan(Y[:, 7]))                                       # 0 / 0 in R
     cols = [c for c in range(C) if c != 7]
     assert np.allclose(Y[:, cols].sum(axis=0), 1e5)
+
+
+def test_remove_tails_known_answers():
+    """tests/testthat/test_infer_cnv.R:265-305 (tail_answer_1 .. 5)."""
+    assert ori.remove_tails(range(1, 6), 0) == []
+    assert ori.remove_tails(range(1, 21), 5) == list(range(1, 6)) + list(range(16, 21))
+    assert ori.remove_tails(range(2, 18), 5) == list(range(2, 7)) + list(range(13, 18))
+    assert ori.remove_tails(range(5, 16), 5) == list(range(5, 10)) + list(range(11, 16))
+    assert ori.remove_tails(range(1, 6), 100) == [1, 5]
+    assert ori.genes_removed_at_ends_of_chromosomes([0, 20, 22], [20, 2, 7], 11).tolist() == \
+        list(range(0, 5)) + list(range(15, 20)) + [22, 23, 27, 28]
+
+
+def test_scale_is_the_per_gene_zscore():
+    rng = np.random.default_rng(2)
+    X = rng.lognormal(0, 1, size=(50, 17))
+    Z = ori.scale_infercnv_expr(X)
+    assert np.allclose(Z.mean(axis=1), 0, atol=1e-14) and np.allclose(Z.std(axis=1, ddof=1), 1, rtol=1e-13)
+    assert np.allclose(Z, (X - X.mean(axis=1, keepdims=True)) / X.std(axis=1, ddof=1, keepdims=True), rtol=1e-12, atol=1e-14)
