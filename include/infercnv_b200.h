@@ -232,6 +232,10 @@ ICNV_API int icnv_scale_infercnv_expr_f64(const double *X, double *Y, int64_t G,
 ICNV_API int icnv_remove_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *keep, int64_t n_keep,
                                    double *Y);
 
+/* Rows in any order, repeats allowed: Y (n x C) = X[idx, ] - the reordering of the expression matrix to the genomic
+ * position table in .order_reduce (R/inferCNV.R:352-428; CreateInfercnvObject's ingest). */
+ICNV_API int icnv_gather_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n, double *Y);
+
 /* The same statistics for a compressed-sparse-column counts matrix (a dgCMatrix's @p, @i, @x; the reference accepts
  * one as raw_counts_matrix, R/inferCNV.R:158-160): p[C+1] column pointers, i[nnz] 0-based row indices, x[nnz]. */
 ICNV_API int icnv_csc_gene_stats_f64(const int32_t *p, const int32_t *i, const double *x, int64_t G, int64_t C,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "icnv_clear_noise_via_ref_mean_sd_logistic_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_i64, ct.c_double]),
     "icnv_gene_stats_f64": (c_int, [_P, c_i64, c_i64, _P, _P, _P]),
     "icnv_scale_infercnv_expr_f64": (c_int, [_P, _P, c_i64, c_i64]),
+    "icnv_gather_genes_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P]),
     "icnv_remove_genes_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P]),
     "icnv_csc_gene_stats_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, _P, _P]),
     "icnv_csc_normalize_f64": (c_int, [_P, _P, _P, c_i64, c_i64, _P, c_i64, ct.c_double, _P, _P]),

@@ -447,3 +447,13 @@ def scale_infercnv_expr(X) -> np.ndarray:
     Y = np.empty_like(X, order="F")
     _lib.check(_lib.load().icnv_scale_infercnv_expr_f64(_p(X), _p(Y), G, C))
     return Y
+
+
+def gather_genes(X, idx) -> np.ndarray:
+    """X[idx, ] for any row order (icnv_gather_genes_f64)."""
+    X = _f64(X)
+    G, C = X.shape
+    idx = _i32(idx)
+    Y = np.empty((len(idx), C), dtype=np.float64, order="F")
+    _lib.check(_lib.load().icnv_gather_genes_f64(_p(X), G, C, _p(idx), len(idx), _p(Y)))
+    return Y

@@ -755,6 +755,26 @@ int icnv_remove_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *
     return ICNV_OK;
 }
 
+/* Row selection in any order (rows may repeat): Y (n x C) = X[idx, ].  The ingest step .order_reduce
+ * (R/inferCNV.R:352-428) reorders the expression matrix to the genomic position table with it. */
+int icnv_gather_genes_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n, double *Y) {
+    ICNV_HOST_PROLOGUE();
+    if (!X || !Y || !idx || G <= 0 || C <= 0 || n <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_gather_genes_f64: bad argument");
+    for (int64_t i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= G) return set_error(ICNV_E_BAD_ARG, "row index %d out of range", idx[i]);
+    double *dX;
+    int rc;
+    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dY = (double *)scratch(SLOT_OUT, sizeof(double) * (size_t)(n * C));
+    int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n);
+    if (!dY || !d_idx) return ICNV_E_NOMEM;
+    ICNV_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if ((rc = icnv_dev_gather_rows_f64(dX, G, d_idx, n, dY, C, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(Y, dY, sizeof(double) * (size_t)(n * C), cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
 static int validate_csc(const int32_t *p, const int32_t *ri, const double *x, int64_t G, int64_t C) {
     if (!p || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: bad argument");
     if (p[0] != 0) return set_error(ICNV_E_BAD_ARG, "compressed-column matrix: p[0] must be 0");

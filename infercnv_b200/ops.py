@@ -622,3 +622,38 @@ def remove_genes_at_ends_of_chromosomes(infercnv_obj: Infercnv, window_length: i
         log.info("-mirroring for hspike")
         obj.hspike = remove_genes_at_ends_of_chromosomes(obj.hspike, window_length)
     return obj
+
+
+# ---- ingest: CreateInfercnvObject's gene ordering (R/inferCNV.R:352-428) ----------------------------------------------
+
+def order_reduce(data, data_gene_names, position_gene_names, chr, start, stop):
+    """.order_reduce: keep the genes present both in the expression matrix and in the genomic position table, order
+    them by (chromosome in order of first appearance in the table, start, stop), and reorder the matrix rows to match.
+    The name matching and the sort are index bookkeeping on the host; the matrix rows are gathered by the library.
+    Returns {"expr", "gene_names", "chr", "start", "stop"} or None values when nothing matches (the reference returns
+    list(expr=NULL, order=NULL, chr_order=NULL))."""
+    log.info("::order_reduce:Start.")
+    none = {"expr": None, "gene_names": None, "chr": None, "start": None, "stop": None}
+    if data is None or position_gene_names is None:
+        return none
+    chr, start, stop = np.asarray(chr), np.asarray(start), np.asarray(stop)
+    pos_names = list(position_gene_names)
+    ok = (start + stop) != 0                                             # drop entries at position 0 (:364-370)
+    pos_index = {}
+    for i, n in enumerate(pos_names):
+        if ok[i] and n not in pos_index:
+            pos_index[n] = i
+    data_index = {}
+    for i, n in enumerate(data_gene_names):
+        data_index.setdefault(n, i)
+    keep = [n for n in dict.fromkeys(data_gene_names) if n in pos_index]  # intersect(): order of the first argument
+    if not keep:
+        log.info("::process_data:order_reduce:The position file and the expression file row (gene) names do not match.")
+        return none
+    levels = {c: k for k, c in enumerate(dict.fromkeys(chr[ok].tolist()))}     # factor levels = unique(chr), :398-400
+    p_idx = np.array([pos_index[n] for n in keep])
+    order = np.lexsort((stop[p_idx], start[p_idx], np.array([levels[c] for c in chr[p_idx].tolist()])))   # order(chr,start,stop)
+    sel = p_idx[order]
+    rows = np.array([data_index[keep[i]] for i in order], dtype=np.int32)
+    return {"expr": api.gather_genes(data, rows), "gene_names": [keep[i] for i in order], "chr": chr[sel],
+            "start": start[sel], "stop": stop[sel]}

@@ -122,3 +122,24 @@ def test_scale_and_chromosome_end_removal(example_object):
     assert out.gene_names == ["g%d" % i for i in keep] and np.array_equal(out.gene_order_chr, codes[keep])
     with pytest.raises(RuntimeError):
         ops.remove_genes_at_ends_of_chromosomes(obj, 5)           # tails below 3 genes: nothing to remove -> stop(1234)
+
+
+def test_order_reduce_known_answers():
+    """tests/testthat/test_infer_cnv.R:436-490."""
+    from infercnv_b200 import ops
+    data = np.asfortranarray(np.tile(np.arange(1, 11, dtype=float)[:, None], (1, 2)))          # matrix(rep(1:10,2), ncol=2)
+    names = ["gene_%d" % i for i in range(1, 11)]
+    pos1 = ["gene_%d" % i for i in (10, 5, 8, 3, 4, 9, 1, 7, 6, 2)]
+    r = ops.order_reduce(data, names, pos1, [1, 1, 2, 2, 3, 3, 4, 4, 5, 5], [1, 5] * 5, [4, 9] * 5)
+    assert r["gene_names"] == pos1 and r["expr"][:, 0].tolist() == [10, 5, 8, 3, 4, 9, 1, 7, 6, 2]
+    assert np.array_equal(r["expr"][:, 0], r["expr"][:, 1]) and r["chr"].tolist() == [1, 1, 2, 2, 3, 3, 4, 4, 5, 5]
+    pos2 = ["gene_%d" % i for i in (10, 5, 3, 9, 1, 7)]                                          # dropping genes
+    r = ops.order_reduce(data, names, pos2, [1, 1, 2, 3, 4, 4], [1, 5, 5, 5, 1, 5], [4, 9, 9, 9, 4, 9])
+    assert r["gene_names"] == pos2 and r["expr"][:, 1].tolist() == [10, 5, 3, 9, 1, 7] and r["chr"].tolist() == [1, 1, 2, 3, 4, 4]
+    pos3 = ["GENE_%d" % i for i in (10, 5, 3, 9, 1, 7)]                                          # no matching gene names
+    assert ops.order_reduce(data, names, pos3, [1, 1, 2, 3, 4, 4], [1, 5, 5, 5, 1, 5], [4, 9, 9, 9, 4, 9])["expr"] is None
+    assert ops.order_reduce(None, None, None, None, None, None)["expr"] is None
+    # table not sorted, a chromosome name that sorts differently as text, an entry at position 0
+    r = ops.order_reduce(data, names, ["gene_2", "gene_9", "gene_4", "gene_7", "gene_1"], ["chr10", "chr2", "chr10", "chr2", "chr2"],
+                         [50, 7, 5, 0, 3], [60, 9, 8, 0, 4])
+    assert r["gene_names"] == ["gene_4", "gene_2", "gene_1", "gene_9"] and r["expr"][:, 0].tolist() == [4, 2, 1, 9]
