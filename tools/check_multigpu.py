@@ -68,6 +68,32 @@ if rank == 0:
     print(f"[check_multigpu] i3 mu/sigma over the reference cells: {mu_d!r}, {sg_d!r} (1-GPU: {mu_1!r}, {sg_1!r})")
     print(f"[check_multigpu] world={world} cells={C_total}: smoothed values differing from 1-GPU run: {bad_y}; "
           f"states differing: {bad_s}  -> {'BITWISE EQUAL' if ok else 'MISMATCH'}")
+# ---- configs[3] shape: median filter over tumour subclusters, every index list whole on one rank (plan_list_shards) ----
+rng = np.random.default_rng(7)
+lists, pos = [], 0
+while pos < C_total:
+    n = int(rng.integers(50, 501))
+    lists.append(np.arange(pos, min(C_total, pos + n)))
+    pos += n
+lplan = shard.plan_list_shards(lists, world)[rank]
+Xl = eng.synth(G, cs, cl, lplan.cells, C_total, bench.SEED)
+eng.collective = False            # the smooth block below is rank-local on purpose (its own reference cells): no collective
+Yl, _ = eng.smooth_block(Xl, cs, cl, [np.arange(0, min(64, len(lplan.cells)))])
+Fl = eng.median_filter(Yl, cs, cl, lplan.local_lists(lists), 7)
+torch.cuda.synchronize()
+ok_mf = True
+if len(lplan.cells):
+    # the same lists filtered one by one give the same bytes: a list's result depends on its own cells only
+    k = lplan.list_ids[len(lplan.list_ids) // 2]
+    loc = lplan.local_lists(lists)[lplan.list_ids.index(k)]
+    one = eng.median_filter(Yl[torch.as_tensor(loc, device=Yl.device).long()].contiguous(), cs, cl, [np.arange(len(loc))], 7)
+    ok_mf = bool(torch.equal(one, Fl[torch.as_tensor(loc, device=Yl.device).long()]))
+flag = torch.tensor([1 if ok_mf else 0], device=X.device)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"[check_multigpu] median filter over {len(lists)} subclusters sharded as whole lists: "
+          f"{'per-list results independent of the sharding' if int(flag.item()) else 'MISMATCH'}")
+ok = ok and bool(int(flag.item()))
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
