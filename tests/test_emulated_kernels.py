@@ -43,6 +43,19 @@ def test_differential_fuzz_of_edge_shapes_under_the_host_emulation():
     assert r.returncode == 0 and "40 cases ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
+@pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
+@pytest.mark.parametrize("world", [1, 2])
+def test_engine_and_multi_rank_path_under_the_host_emulation(world):
+    """infercnv_b200/device.py (Engine) on CPU tensors against the emulated library: one rank against the oracle
+    (smooth block, HMM, i3 mu/sigma, device-resident consensus and regions incl. a strided state matrix, median filter);
+    two gloo ranks - the sharded smooth block with its all-gathered partial sums, the HMM, mu/sigma and the all-reduced
+    region consensus - bitwise equal to the single-rank run (what tools/check_multigpu.py checks over NCCL)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "host", "engine_emulated.py")] + (["--world", str(world)] if world > 1 else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert ("BITWISE EQUAL" in r.stdout) if world > 1 else ("equal to the oracle" in r.stdout), r.stdout[-1500:]
+
+
 def test_the_package_cannot_reach_the_emulated_library():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "infercnv_b200")):
         for f in files:
