@@ -262,7 +262,8 @@ def workload_config(args, C_total):
                         f"(BASELINE configs[1] per GPU)",
             "cells_per_gpu": args.cells, "genes": args.genes, "window_length": 101, "hmm": "i6 per cell, t=1e-6",
             "reference_cells": "first 10 % in two groups (6 % / 4 %)", "sharding": f"cells over {args.gpus} GPU(s)",
-            "l2": "inputs (0.8 GB/GPU/pass) exceed the 126 MB L2; no explicit flush"}
+            "l2": "inputs (%.2f GB/GPU/pass) %s the 126 MB L2; no explicit flush" % (
+                args.cells * args.genes * 8 / 1e9, "exceed" if args.cells * args.genes * 8 > 126e6 else "do NOT exceed")}
 
 
 def main():

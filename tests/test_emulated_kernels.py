@@ -56,6 +56,41 @@ def test_engine_and_multi_rank_path_under_the_host_emulation(world):
     assert ("BITWISE EQUAL" in r.stdout) if world > 1 else ("equal to the oracle" in r.stdout), r.stdout[-1500:]
 
 
+@pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_script_reaches_its_json_line_under_the_host_emulation(world):
+    """bench.py itself (workload, warm-up + timed loop, e2e through the host ABI, max over ranks, JSON assembly) at a toy
+    size on the CPU, for 1 rank and for 2 ranks launched the way torchrun launches them.  The numbers are meaningless
+    (emulation, wall clock); the contract keys and the multi-rank control flow are what is checked."""
+    import json
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    args = ["--gpus", str(world), "--cells", "64", "--genes", "1100", "--steps", "2", "--warmup", "3", "--ref-sample-cells", "16"]
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "host", "bench_emulated.py")] + args,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+    outs = [p.communicate(timeout=900) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs[0][1][-1500:] + outs[-1][1][-1500:]
+    lines = [ln for ln in outs[0][0].splitlines() if ln.startswith("{")]
+    assert len(lines) == 1 and all(not o[0].strip() for o in outs[1:])          # ONE JSON line, from rank 0
+    j = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in j, key
+    assert j["n_gpus"] == world and j["steps"] == 2 and j["warmup"] == 3 and j["value"] > 0 and j["gpu_launches"] > 0
+    assert j["dtype"] == "f64" and j["scaling"] == "weak" and "workload" in j["config"] and "model" not in j["config"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(j["roofline"]) and j["roofline"]["bound"] == "hbm"
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(j["e2e"]) and j["e2e"]["h2d_bytes_per_step"] > 0
+    if world == 1:
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(j["cpu_baseline"])
+
+
 def test_the_package_cannot_reach_the_emulated_library():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "infercnv_b200")):
         for f in files:
