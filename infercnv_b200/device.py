@@ -8,6 +8,7 @@ column-major G x C (a cell's genes contiguous).
 from __future__ import annotations
 
 import ctypes as ct
+import os
 
 import numpy as np
 import torch
@@ -35,6 +36,8 @@ class Engine:
         self.tdev = torch.device("cuda", self.device)
         self.timing = None   # when set to a list, smooth_block appends (name, start_event, end_event)
         self.collective = True   # False: never enter a collective even if a process group exists
+        # pass 2 re-uses pass 1's reference columns instead of recomputing them (ICNV_REF_REUSE=0 turns it off)
+        self.reuse_reference_pass = os.environ.get("ICNV_REF_REUSE", "1") != "0"
         self._plan_cache = {}
         self._T = None
 
@@ -160,6 +163,7 @@ class Engine:
         b1 = self.bounds(group_means(X, d_groups, apply_log))
         # pass 1: reference cells only, up to the median centring
         n_ref = int(sum(len(g) for g in ref_groups_local))
+        ref_leading = n_ref > 0 and np.array_equal(np.concatenate(ref_groups_local), np.arange(n_ref))
         if self._T is None or self._T.shape != (max(n_ref, 1), G):
             self._T = torch.empty((max(n_ref, 1), G), dtype=torch.float64, device=self.tdev)
         T = self._T
@@ -171,7 +175,15 @@ class Engine:
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.cell_pipeline(X, None, Y, chr_start, chr_len, apply_log, b1, threshold, window, 1, b2, True, use_bounds, flag)
+        if self.reuse_reference_pass and 0 < n_ref < C and ref_leading:
+            # the reference cells are the leading columns (the shard planner's layout): pass 1 already left their centred,
+            # smoothed values in T, so they only need the second subtraction and 2^x (stage D, bit-identical to running
+            # the whole pipeline again: x - 0.0 == x); the other cells take the full pipeline
+            self.cell_pipeline(T[:n_ref], None, Y[:n_ref], chr_start, chr_len, False, None, 0.0, 0, 0, b2, True, use_bounds, flag)
+            self.cell_pipeline(X[n_ref:], None, Y[n_ref:], chr_start, chr_len, apply_log, b1, threshold, window, 1, b2, True,
+                               use_bounds, flag)
+        else:
+            self.cell_pipeline(X, None, Y, chr_start, chr_len, apply_log, b1, threshold, window, 1, b2, True, use_bounds, flag)
         if self.timing is not None:
             e1.record()
             self.timing.append(("cell_pipeline_pass2", e0, e1))

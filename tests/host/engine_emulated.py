@@ -58,6 +58,15 @@ def single():
     want = orc.smooth_block(Xh, CS, LENS, refs)
     rel = float(np.max(np.abs(Y.numpy().T - want) / np.abs(want)))
     assert rel < 1e-11 and int(flag.item()) == 0, rel
+    # re-using pass 1's reference columns in pass 2 (the default when they are the leading columns) changes no bit
+    assert eng.reuse_reference_pass
+    eng.reuse_reference_pass = False
+    Y_full, _ = eng.smooth_block(X, CS, LENS, refs)
+    eng.reuse_reference_pass = True
+    assert torch.equal(Y, Y_full)
+    Y_scattered, _ = eng.smooth_block(X, CS, LENS, [np.array([3, 50, 7]), np.array([11, 60])])      # not leading: full pipeline
+    want2 = orc.smooth_block(Xh, CS, LENS, [np.array([3, 50, 7]), np.array([11, 60])])
+    assert float(np.max(np.abs(Y_scattered.numpy().T - want2) / np.abs(want2))) < 1e-11
     Pi, delta = orc.hmm_params(6)
     S, f2 = eng.viterbi(Y, CS, LENS, Pi, delta, I6_MEAN, I6_SD)
     want_s = orc.viterbi_matrix(np.asfortranarray(Y.numpy().T), CS, LENS, Pi, delta, I6_MEAN, I6_SD)

@@ -9,6 +9,8 @@ timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_wi
 # 3. the bench line (never under a profiler) and the secondary kernels incl. K7-K9
 timeout 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 600 gpurun_out/r02_bench.json
 timeout 300 python tools/bench_extra.py > gpurun_out/r02_secondary_kernels.json 2> gpurun_out/r02_secondary.err; cat gpurun_out/r02_secondary_kernels.json
+# 3b. A/B of the reference-column reuse in pass 2 (default on since the end of round 1, never timed)
+ICNV_REF_REUSE=0 timeout 300 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/r02_bench_no_ref_reuse.json 2>/dev/null; tail -c 300 gpurun_out/r02_bench_no_ref_reuse.json
 # 4. launch list of the bench command
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
 # 5. ncu --set full of the two hot kernels and the region kernels
