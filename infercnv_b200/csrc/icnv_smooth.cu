@@ -1572,7 +1572,9 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         }
     }
     if (NT == 0)
-        return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes in K = %d chromosomes exceeds the kernel's %d genes",
+        return set_error(ICNV_E_UNSUPPORTED,
+                         "G = %lld genes in K = %d chromosomes need more than the kernel's 1024 per-thread segments of at most "
+                         "23 genes, each inside one chromosome (at most %d genes when they divide evenly)",
                          (long long)G, K, 1024 * 23);
     const int NW = NT / 32;
     size_t red_bytes = (NT == 256) ? sizeof(Red<8>) : (NT == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
