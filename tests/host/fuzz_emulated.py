@@ -18,6 +18,8 @@ from infercnv_b200 import _lib  # noqa: E402
 _lib.LIB_PATH = build_emu.build()
 
 from infercnv_b200 import api  # noqa: E402
+from oracle import denoise as ord_  # noqa: E402
+from oracle import ingest as ori  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from oracle import regions as orr  # noqa: E402
 
@@ -113,6 +115,57 @@ def one_case(rng, case):
     return G, C
 
 
+def _csc(D):
+    p = np.concatenate([[0], np.cumsum((D != 0).sum(axis=0))]).astype(np.int32)
+    i = np.concatenate([np.flatnonzero(D[:, c]) for c in range(D.shape[1])] + [np.zeros(0, int)]).astype(np.int32)
+    x = np.concatenate([D[np.flatnonzero(D[:, c]), c] for c in range(D.shape[1])] + [np.zeros(0)]).astype(np.float64)
+    return p, i, x
+
+
+def widened_case(rng, case):
+    """gene statistics (dense and sparse), row selection, sparse normalisation, outlier clamp, scaling, noise clearing,
+    median-filter windows up to 21, on shapes down to one gene / one cell with empty rows and columns."""
+    G, C = int(rng.integers(1, 70)), int(rng.integers(1, 90))
+    D = rng.poisson(rng.choice([0.05, 0.5, 3.0]), size=(G, C)).astype(float)
+    if rng.random() < 0.3:
+        D[:, rng.integers(0, C)] = 0
+    if rng.random() < 0.3:
+        D[rng.integers(0, G)] = 0
+    sums, npos, means = api.gene_stats(D)
+    assert np.array_equal(sums, D.sum(axis=1)) and np.array_equal(npos, ori.n_cells_expressing(D)), ("gene_stats", case)
+    assert np.array_equal(means, ori.row_means(D)), ("row means", case)
+    p, i, x = _csc(D)
+    s2, n2, m2 = api.csc_gene_stats(p, i, x, G)
+    assert np.array_equal(s2, sums) and np.array_equal(n2, npos) and np.array_equal(m2, means), ("csc stats", case)
+    keep = np.flatnonzero(rng.random(G) < 0.7)
+    keep = keep if len(keep) else np.array([0])
+    assert np.array_equal(api.remove_genes(D, keep), D[keep]), ("remove_genes", case)
+    perm = rng.integers(0, G, size=int(rng.integers(1, 2 * G + 1)))
+    assert np.array_equal(api.gather_genes(D, perm), D[perm]), ("gather_genes", case)
+    for nf in (None, 1e4):
+        Y, cs_ = api.csc_normalize(p, i, x, G, keep=keep, normalize_factor=nf, want_col_sums=True)
+        Dk = np.asfortranarray(D[keep])
+        with np.errstate(all="ignore"):
+            want = orc.normalize_by_seq_depth(Dk, nf)
+        assert np.array_equal(cs_, Dk.sum(axis=0)) and np.array_equal(np.isnan(Y), np.isnan(want)), ("csc_normalize", case)
+        assert np.array_equal(Y[~np.isnan(want)], want[~np.isnan(want)]), ("csc_normalize values", case, nf)
+    E = np.asfortranarray(rng.lognormal(0, 0.3, size=(max(G, 2), C)))
+    got, b = api.remove_outliers_norm(E, want_bounds=True)
+    assert b == ord_.get_average_bounds(E) and np.array_equal(got, ord_.remove_outliers_norm(E)), ("outliers", case)
+    if C >= 2:
+        assert np.allclose(api.scale_infercnv_expr(E), ori.scale_infercnv_expr(E), rtol=1e-10, atol=1e-12), ("scale", case)
+    refs = np.flatnonzero(rng.random(C) < 0.5)
+    thr = float(rng.choice([0.05, 0.3]))
+    g1, w1 = api.clear_noise(E, refs, thr), ord_.clear_noise(E, refs if len(refs) else None, thr)
+    assert np.mean(np.abs(g1 - w1) > 1e-13 * np.abs(w1)) < 0.02, ("clear_noise", case)
+    cs, cl = layout(rng)
+    X = matrix(rng, int(cl.sum()), C)
+    lists = groups_of(rng, C)
+    for ws in (5, 9, 11, 21):
+        assert np.allclose(api.median_filter(X, cs, cl, lists, ws), orc.median_filter(X, cs, cl, lists, ws), rtol=0,
+                           atol=1e-15 * max(1.0, np.abs(X).max())), ("median_filter", ws, case)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -121,6 +174,8 @@ def main():
     shapes = []
     for case in range(n):
         shapes.append(one_case(rng, case))
+        if case % 2 == 0:
+            widened_case(rng, case)
     print(f"{n} cases ok (seed {seed}); genes {min(s[0] for s in shapes)}..{max(s[0] for s in shapes)}, "
           f"cells {min(s[1] for s in shapes)}..{max(s[1] for s in shapes)}")
 
