@@ -426,9 +426,43 @@ __device__ __forceinline__ double fast_log2_1p(double x, const double2 *__restri
     return (double)e + fma(r, q, t.y);
 }
 
+// The same without the range branch: `slow` is raised instead when the argument is outside the fast path's domain (the
+// value returned is then meaningless and the caller re-evaluates with fast_log2_1p).  Lets several evaluations run as one
+// straight-line block - the per-value branch with its convergence barrier costs ~8 issue slots of ~35.
+__device__ __forceinline__ double fast_log2_1p_nc(double x, const double2 *__restrict__ ltab, bool &slow) {
+    const double v = x + 1.0;
+    const int hi = __double2hiint(v);
+    slow |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+    const double2 t = ltab[(hi >> 13) & 127];
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(r, k_logc[5], k_logc[4]);
+    q = fma(r, q, k_logc[3]);
+    q = fma(r, q, k_logc[2]);
+    q = fma(r, q, k_logc[1]);
+    q = fma(r, q, k_logc[0]);
+    return (double)e + fma(r, q, t.y);
+}
+
 // 2^x (invert_log2, ops.R:2818): x = k/128 + r, 2^x = 2^(k>>7) * T[k & 127] * 2^r, degree-5 polynomial.
 __device__ __forceinline__ double fast_exp2(double x, const double *__restrict__ etab) {
     if (!(fabs(x) < 1000.0)) return slow_exp2(x);
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    const double kk = fma(x, 128.0, MAGIC);
+    const int ki = __double2loint(kk);
+    const double r = fma(kk - MAGIC, -0.0078125, x);  // exact
+    double q = fma(r, k_expc[4], k_expc[3]);
+    q = fma(r, q, k_expc[2]);
+    q = fma(r, q, k_expc[1]);
+    q = fma(r, q, k_expc[0]);
+    const double t = etab[ki & 127];
+    const double res = fma(t * r, q, t);
+    return __hiloint2double(__double2hiint(res) + ((ki >> 7) << 20), __double2loint(res));
+}
+
+__device__ __forceinline__ double fast_exp2_nc(double x, const double *__restrict__ etab, bool &slow) {
+    slow |= !(fabs(x) < 1000.0);
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     const double kk = fma(x, 128.0, MAGIC);
     const int ki = __double2loint(kk);
@@ -1165,25 +1199,36 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         }
         lap(0);
         if (p.apply_log && p.lo1 && p.threshold > 0.0) {
+            // groups of four genes NT apart as one straight-line block (no bounds tests, no per-value range branch), then
+            // the < 4 genes a thread has left one at a time
             const double thr = p.threshold;
-            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+            int g0 = tid;
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int g = min(g0 + u * NT, G - 1);
-                    v[u] = in[g];
-                    lo[u] = p.lo1[g];
-                    hi[u] = p.hi1[g];
+                    v[u] = in[g0 + u * NT];
+                    lo[u] = p.lo1[g0 + u * NT];
+                    hi[u] = p.hi1[g0 + u * NT];
+                }
+                bool slow = false;
+                double x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = fast_log2_1p_nc(v[u], ltab, slow);
+                if (slow) {   // zero / negative / denormal / non-finite x + 1 somewhere in the group (rare)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!is_finite_d(v[u])) bad = true;
+                        x[u] = fast_log2_1p(v[u], ltab);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    if (!is_finite_d(v[u])) bad = true;
-                    double x = fast_log2_1p(v[u], ltab);
-                    x = sub_bounds(x, lo[u], hi[u]);
-                    x = clamp_sym(x, thr);
-                    if (g < G) oth[g] = x;
-                }
+                for (int u = 0; u < 4; ++u) oth[g0 + u * NT] = clamp_sym(sub_bounds(x[u], lo[u], hi[u]), thr);
+            }
+            for (int g = g0; g < G; g += NT) {
+                const double v = in[g];
+                if (!is_finite_d(v)) bad = true;
+                oth[g] = clamp_sym(sub_bounds(fast_log2_1p(v, ltab), p.lo1[g], p.hi1[g]), thr);
             }
         } else {
             for (int g = tid; g < G; g += NT) {
@@ -1353,22 +1398,30 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         lap(4);
         // ---- D: centre, second reference subtraction, 2^x fused into the one coalesced write ----------------
         if (p.lo2 && p.apply_exp2) {
-            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+            int g0 = tid;
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int g = min(g0 + u * NT, G - 1);
-                    v[u] = in[g];
-                    lo[u] = p.lo2[g];
-                    hi[u] = p.hi2[g];
+                    v[u] = in[g0 + u * NT];
+                    lo[u] = p.lo2[g0 + u * NT];
+                    hi[u] = p.hi2[g0 + u * NT];
                 }
+                bool slow = false;
+                double x[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    const double x = fast_exp2(sub_bounds(v[u] - centre, lo[u], hi[u]), etab);
-                    if (g < G) dst[g] = x;
+                    v[u] = sub_bounds(v[u] - centre, lo[u], hi[u]);
+                    x[u] = fast_exp2_nc(v[u], etab, slow);
                 }
+                if (slow) {   // |x| >= 1000 or NaN somewhere in the group (rare): library exp2
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = fast_exp2(v[u], etab);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dst[g0 + u * NT] = x[u];
             }
+            for (int g = g0; g < G; g += NT) dst[g] = fast_exp2(sub_bounds(in[g] - centre, p.lo2[g], p.hi2[g]), etab);
         } else {
             for (int g = tid; g < G; g += NT) {
                 double x = in[g] - centre;

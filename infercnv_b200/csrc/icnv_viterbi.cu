@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(128) viterbi_kernel(const VitParams p) {
 
 constexpr int TG = 8;        // genes per staged tile
 constexpr int TS = TG + 1;   // padded row stride in doubles (bank-conflict-free column reads)
-constexpr int FAST_WARPS = 16;   // one CTA per SM: the replicated table below is shared by all of them
+constexpr int FAST_WARPS = 16;   // default warps per CTA (one CTA per SM: the replicated table below is shared by all of them);
+                                 // 20 / 24 are compiled as occupancy variants (ICNV_VFAST_WARPS): 96 / 80 registers per thread,
+                                 // the gene loop stays spill-free, ~19 values are re-loaded from local memory per 8-gene tile
 constexpr int TAB_REP = 8;       // table replicas: lane l reads replica l & 7, so a 16-byte lookup never bank-conflicts
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
@@ -341,8 +343,8 @@ __device__ __noinline__ double emission_far(double x, double mean, double sd) {
     return -log(-pnorm_upper_log_exact(zz));
 }
 
-template <int M>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 1) viterbi_fast_kernel(const VitParams p) {
+template <int M, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
     // emission table re-laid as [interval][replica] -> {c0, c1} and {c2, (float c3, float c4)}: two 16-byte loads
     // per state (32 B instead of 40 B; c3, c4 only weigh u^3, u^4 with |u| <= 1/2: single precision costs < 3e-14).
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, 1) viterbi_fast_kernel(const 
     __syncthreads();
     const double2 *tabA = tab01 + (lane & (TAB_REP - 1)), *tabB = tab2f + (lane & (TAB_REP - 1));   // this lane's replica
 
-    const int64_t warp_global = (int64_t)blockIdx.x * FAST_WARPS + warp;
+    const int64_t warp_global = (int64_t)blockIdx.x * NWARPS + warp;
     // backpointers: one 16-bit word per gene and lane - the best previous state (3 bits) and, per state, whether the
     // path into it comes from that best state (1) or stays (0)
     uint16_t *__restrict__ bp = reinterpret_cast<uint16_t *>(p.bp + warp_global * (int64_t)p.max_len * 32);
@@ -897,25 +899,31 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     p.list_out_count = c.hmm_list_count;
     p.list_cap = (unsigned int)std::min<size_t>(list_cap, 0xffffffffu);
 
-    auto fkern = (m == 6) ? viterbi_fast_kernel<6> : viterbi_fast_kernel<3>;
     auto lkern = (m == 6) ? viterbi_list_kernel<6> : viterbi_list_kernel<3>;
-    const size_t smem = sizeof(double) * (4 * (ICNV_EMIS_N + 1) * TAB_REP + FAST_WARPS * 2 * 32 * TS);
+    // warps per CTA of the fast kernel: 16 (128 registers per thread) unless ICNV_VFAST_WARPS picks an occupancy variant
+    int fw = FAST_WARPS;
+    if (const char *e = getenv("ICNV_VFAST_WARPS")) fw = atoi(e);
+    if (fw != 16 && fw != 20 && fw != 24) fw = FAST_WARPS;
+    void (*fkern)(const VitParams) =
+        (m == 6) ? (fw == 24 ? viterbi_fast_kernel<6, 24> : (fw == 20 ? viterbi_fast_kernel<6, 20> : viterbi_fast_kernel<6, 16>))
+                 : (fw == 24 ? viterbi_fast_kernel<3, 24> : (fw == 20 ? viterbi_fast_kernel<3, 20> : viterbi_fast_kernel<3, 16>));
+    const size_t smem = sizeof(double) * (4 * (ICNV_EMIS_N + 1) * TAB_REP + (size_t)fw * 2 * 32 * TS);
     p.means_monotone = 1;
     for (int k = 1; k + 1 < m; ++k)
         if ((mean[k] - mean[k - 1]) * (mean[k + 1] - mean[k]) < 0.0) p.means_monotone = 0;
     ICNV_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fkern, FAST_WARPS * 32, smem));
+    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fkern, fw * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = (int64_t)c.sm_count * per_sm;
-    int64_t need_blocks = (p.n_items + FAST_WARPS - 1) / FAST_WARPS;
+    int64_t need_blocks = (p.n_items + fw - 1) / fw;
     if (blocks > need_blocks) blocks = need_blocks;
     const int64_t list_blocks = c.sm_count;  // 4 warps each; the list is short
-    const int64_t n_warps = std::max<int64_t>(blocks * FAST_WARPS, list_blocks * 4);
+    const int64_t n_warps = std::max<int64_t>(blocks * fw, list_blocks * 4);
     uint32_t *d_bp = (uint32_t *)scratch(SLOT_BP, sizeof(uint32_t) * (size_t)n_warps * (size_t)max_len * 32);
     if (!d_bp) return ICNV_E_NOMEM;
     p.bp = d_bp;
-    fkern<<<(unsigned)blocks, FAST_WARPS * 32, smem, st>>>(p);
+    fkern<<<(unsigned)blocks, fw * 32, smem, st>>>(p);
     ICNV_CHECK_LAUNCH("viterbi_fast_kernel");
     // exact re-run of whatever the certificate rejected (list length is read on the device)
     p.list = d_list;

@@ -146,6 +146,34 @@ def test_oligodendroglioma_smooth_block_two_ref_groups(api, oligo):
     assert np.max(np.abs(got2 - want2) / np.abs(want2)) < 1e-11
 
 
+def test_smooth_block_slow_paths_of_the_grouped_element_wise_loops(api):
+    """Stage A / D of the fused kernel evaluate log2 / 2^x four genes at a time without a per-value range branch; a value
+    outside the fast path's domain re-evaluates its group.  Zeros (log2(1)), x = -1 (log2(0) = -Inf, clamped to -3 as in R,
+    ops.R:2760 + 2970) and NaN / Inf inputs (error -5), each placed
+    both in a four-gene group and in the per-thread remainder (G = 1300: 256 threads, groups cover genes 0..1023)."""
+    from infercnv_b200._lib import InfercnvB200Error
+    rng = np.random.default_rng(11)
+    lens = np.array([700, 330, 270], dtype=np.int32)
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    G, C = int(lens.sum()), 12
+    X = rng.gamma(2.0, 1.5, size=(G, C))
+    X[rng.random((G, C)) < 0.4] = 0.0
+    refs = [np.arange(0, 4), np.arange(4, 6)]
+    X[[5, 600, 1100, 1299], 7] = -1.0          # x + 1 == 0
+    got = api.smooth_block(X, cs, lens, refs, apply_log=True, threshold=3.0, window_length=101)
+    want = orc.smooth_block(X, cs, lens, refs)
+    assert np.all(np.isfinite(got))
+    rel = np.max(np.abs(got - want) / np.abs(want))
+    assert rel < 1e-11, rel
+    for g in (600, 1250):
+        for bad in (np.nan, np.inf):
+            Xb = X.copy()
+            Xb[g, 9] = bad
+            with pytest.raises(InfercnvB200Error) as e:
+                api.smooth_block(Xb, cs, lens, refs, apply_log=True, threshold=3.0, window_length=101)
+            assert e.value.code == -5
+
+
 def test_smooth_block_20k_genes_single_buffer_variant(api):
     """config c5's gene count: two shared-memory buffers no longer fit, the kernel runs its
     single-buffer / 1024-thread variant."""
