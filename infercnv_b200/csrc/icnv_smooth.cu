@@ -144,6 +144,8 @@ struct CellParams {
     int *err_flag;
     int s_elems;  // doubles reserved per column buffer (G rounded up to even)
     int K;
+    int q_elems;  // cell_pipeline3_kernel<NT, true>: doubles of the landing / padded-Q buffer (G + K (2h + 2), even)
+    int ipad;     // cell_pipeline3_kernel<NT, true>: entries in front of the reciprocal-denominator table (>= longest slice, even)
 };
 
 constexpr int CAND_MAX = 64;   // candidates ranked directly at the end of the selection
@@ -1108,27 +1110,35 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
     return true;
 }
 
-template <int NT>
+// PADQ = true (default when it fits): the prefix sums Q are written to a padded copy of the column - per chromosome h + 2
+// zeros in front (Q(-1) .. Q(-h-2)) and the h values of the linear continuation behind - so the smoothing outputs read
+// Q(j+h), Q(j-1), Q(j-h-2) at fixed offsets from one running pointer instead of selecting among the Q array, the
+// continuation table and a zero slot per load (53 -> ~20 instructions per gene in that loop; results bit-identical).
+// Buffer roles are then fixed instead of ping-pong: buf0 = landing buffer of the bulk copy, later the padded Q;
+// buf1 = x', later the smoothed values that stages C and D read.
+template <int NT, bool PADQ>
 __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
     double *etab = reinterpret_cast<double *>(ltab + 128);
     double *buf0 = etab + 128;
-    double *buf1 = buf0 + p.s_elems;
-    double *invD = buf1 + p.s_elems;
+    double *buf1 = buf0 + (PADQ ? p.q_elems : p.s_elems);
+    double *invD = buf1 + p.s_elems + (PADQ ? p.ipad : 0);   // PADQ: p.ipad (even) copies of invD[0] in front, indices -ipad .. -1
     double *ptot = invD + (p.h + 2);
     double *qtot = ptot + p.K;
     double *tails = qtot + p.K;                              // [2][NW]
     double *cand = tails + 2 * NW;
     Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
     double *rext = reinterpret_cast<double *>(&red + 1);     // [K][h] linear continuation of Q past each chromosome end
-    double *zslot = rext + p.K * p.h;                        // a 0.0 the edge loads can point at (Q before the start)
+    double *zslot = rext + (PADQ ? 0 : p.K * p.h);           // a 0.0 the edge loads can point at (Q before the start)
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(zslot + 2);
     int *hist = reinterpret_cast<int *>(bar + 2);            // HIST_NB bins, zero between cells
     int *hres = hist + HIST_NB;                              // 4 results of the bin search (+4 spare)
     int *wcnt = hres + 8;                                    // [2][NW]
     int *cand_n = wcnt + 2 * NW;
+    int *chr_cs = cand_n + 2;                                // PADQ: [K] chromosome start, [K] chromosome length
+    int *chr_n = chr_cs + p.K;
     double *const sm = reinterpret_cast<double *>(smem_raw); // everything below is indexed relative to this
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1140,6 +1150,8 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
     if (do_smooth) {
         const double full = (double)(h + 1) * (double)(h + 1);
         for (int r = tid; r <= h; r += NT) invD[r] = 1.0 / (full - 0.5 * (double)r * (double)(r + 1));
+        if (PADQ)   // PADQ: IPAD copies of entry 0 in front of the table (see the output loop)
+            for (int r = tid; r < p.ipad; r += NT) invD[-1 - r] = 1.0 / full;
     }
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -1154,8 +1166,28 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
     }
     const Seg seg = p.segs[tid];
     const int len = seg.len, a0 = seg.start, cs = seg.cs, ce = seg.ce, n = ce - cs;
+    if (PADQ) {   // chromosome geometry for the pad loop: empty chromosomes own no thread and keep length 0
+        for (int i = tid; i < p.K; i += NT) chr_n[i] = 0;
+        __syncthreads();
+        if (len > 0 && a0 == cs) {
+            chr_cs[seg.chr] = cs;
+            chr_n[seg.chr] = n;
+        }
+    }
     const int lane_first = max(seg.tfirst - (tid - lane), 0);
     const int wfirst = seg.tfirst >> 5;
+    // PADQ output loop: index of the slice's first reciprocal denominator and its step per gene.  Inside a chromosome of at
+    // least 2h + 1 genes only one end can be within h genes: rl = max(h - j, 0) falls by one per gene (step -1), rr =
+    // max(j - (n - 1 - h), 0) rises (step +1); negative indices are the table's front pad = entry 0, so no clamp is needed
+    // as long as the start index is >= -ipad.  Slices that see both ends (2h + 1 <= n < 2h + 1 + len) take the general loop.
+    int r0I = 0, dI = 0;
+    bool pad_fast = n >= 2 * h + 1;
+    if (PADQ && pad_fast) {
+        const int j0 = a0 - cs, hl = h - j0, hr = j0 - (n - 1 - h);
+        if (hl > 0 && hr + len - 1 > 0) pad_fast = false;
+        else if (hl > 0) { r0I = hl; dI = -1; }
+        else if (hr + len - 1 > 0) { r0I = max(hr, -p.ipad); dI = 1; }
+    }
     bool bad = false;
     const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
     auto tma_ok = [&](int64_t col) {
@@ -1250,7 +1282,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         if (!do_smooth) {
             for (int q = 0; q < len; ++q) {
                 const double out = xs[q];
-                in[a0 + q] = out;
+                if (!PADQ) in[a0 + q] = out;
                 ys1 += out;
                 ys2 = fma(out, out, ys2);
             }
@@ -1293,14 +1325,17 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             carry = 0.0;
             for (int u = wfirst; u < warp; ++u) carry += tails[NW + u];
             const double offQ = exc + carry;   // Q just before this segment
-            // pass 3: Q in place (each thread touches only its own slice)
+            // pass 3: Q in place (each thread touches only its own slice); PADQ: into the padded layout in `in`, where
+            // Q(0) of chromosome c sits at cs + c (2h + 2) + (h + 2)
+            const int pbase = cs + seg.chr * (2 * h + 2) + (h + 2);
+            double *__restrict__ qdst = PADQ ? (in + pbase + (a0 - cs)) : (oth + a0);
             pr = offP;
             double qv = offQ;
 #pragma unroll 4
             for (int q = 0; q < len; ++q) {
                 pr += xs[q];
                 qv += pr;
-                oth[a0 + q] = qv;
+                qdst[q] = qv;
             }
             if (len > 0 && a0 + len == ce) {
                 ptot[seg.chr] = plast;
@@ -1308,15 +1343,66 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             }
             __syncthreads();
             // Q continues linearly past a chromosome's last gene (x is taken as 0 there): Q(n-1+k) = Qn + k*Pn, k = 1..h
-            for (int idx = tid; idx < p.K * h; idx += NT) {
-                const int c = idx / h, k = idx - c * h + 1;
-                rext[idx] = fma((double)k, ptot[c], qtot[c]);
+            if (PADQ) {
+                const int padw = 2 * h + 2;
+                for (int idx = tid; idx < p.K * padw; idx += NT) {
+                    const int c = idx / padw, e = idx - c * padw;
+                    const int nc = chr_n[c];
+                    if (nc >= 2) {
+                        const int base = chr_cs[c] + c * padw;
+                        if (e < h + 2) in[base + e] = 0.0;
+                        else in[base + nc + e] = fma((double)(e - (h + 1)), ptot[c], qtot[c]);
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < p.K * h; idx += NT) {
+                    const int c = idx / h, k = idx - c * h + 1;
+                    rext[idx] = fma((double)k, ptot[c], qtot[c]);
+                }
             }
             __syncthreads();
             lap(2);
             // outputs: N(j) = (Q(j+h) - Q(j-1)) - (Q(j-1) - Q(j-h-2)), one code path for interior and edge genes -
-            // out-of-range Q come from the continuation table or the zero slot by index selection, no branches
-            if (n >= 2) {
+            // out-of-range Q come from the pads (PADQ) or, by index selection, from the continuation table / the zero slot
+            if (n >= 2 && PADQ) {
+                const double *__restrict__ P = in + pbase + (a0 - cs);   // &Q(j0)
+                double *__restrict__ O = oth + a0;
+                const int j0 = a0 - cs;
+                if (pad_fast) {
+                    // the reciprocal denominators of the slice are consecutive entries of the padded table (interior
+                    // genes: the constant entries in front of index 0), read through a pointer that moves by dI per gene
+                    const double *__restrict__ pa = P + h, *__restrict__ pb = P - 1, *__restrict__ pc = P - h - 2;
+                    const double *__restrict__ pI = invD + r0I;
+#pragma unroll 2
+                    for (int q = 0; q < len; ++q) {
+                        const double qb = pb[q];
+                        const double N = (pa[q] - qb) - (qb - pc[q]);
+                        const double out = N * *pI;
+                        pI += dI;
+                        O[q] = out;
+                        ys1 += out;
+                        ys2 = fma(out, out, ys2);
+                    }
+                } else {
+                    for (int q = 0; q < len; ++q) {
+                        const int j = j0 + q;
+                        const double qb = P[q - 1];
+                        const double N = (P[q + h] - qb) - (qb - P[q - h - 2]);
+                        const int rl = max(h - j, 0), rr = max(h - (n - 1 - j), 0);
+                        double out;
+                        if (rl > 0 && rr > 0) {
+                            const double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
+                                             0.5 * (double)rr * (double)(rr + 1);
+                            out = N / D;
+                        } else {
+                            out = N * invD[rl + rr];
+                        }
+                        O[q] = out;
+                        ys1 += out;
+                        ys2 = fma(out, out, ys2);
+                    }
+                }
+            } else if (n >= 2) {
                 const int qoff = (int)(oth - sm) + cs;                       // Q(j) lives at sm[qoff + j], 0 <= j < n
                 const int roff = (int)(rext - sm) + seg.chr * h - n;         // Q(j) at sm[roff + j], n <= j < n + h
                 const int zoff = (int)(zslot - sm);
@@ -1343,10 +1429,11 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                     ys2 = fma(out, out, ys2);
                 }
             } else {
-                // single-gene chromosome: left untouched (ops.R:2417); Q of a single element is the element
+                // single-gene chromosome: left untouched (ops.R:2417); Q of a single element is the element, and with
+                // PADQ x' itself is still in place in `oth`
                 for (int q = 0; q < len; ++q) {
                     const double out = oth[a0 + q];
-                    in[a0 + q] = out;
+                    if (!PADQ) in[a0 + q] = out;
                     ys1 += out;
                     ys2 = fma(out, out, ys2);
                 }
@@ -1358,20 +1445,21 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             red.d[phase][0][warp] = ys1;
             red.d[phase][1][warp] = ys2;
         }
-        __syncthreads();   // smoothed values complete in `in`; Q in `oth` no longer needed
+        __syncthreads();   // smoothed values complete in `in` (PADQ: in `oth`); Q no longer needed
+        double *const sv = PADQ ? oth : in;   // the smoothed column stages C and D read
         double S1 = (lane < NW) ? red.d[phase][0][lane] : 0.0, S2 = (lane < NW) ? red.d[phase][1][lane] : 0.0;
         S1 = warp_sum_d(S1);
         S2 = warp_sum_d(S2);
         phase ^= 1;
         lap(3);
-        if (tid == 0) {    // next cell's column lands in `oth` while the median and the epilogue run
+        if (tid == 0) {    // next cell's column lands where Q was (`oth`; PADQ: `in`) while the median and the epilogue run
             const int64_t cn = ci + gridDim.x;
             if (cn < p.n_cols) {
                 const int64_t coln = p.cols ? (int64_t)p.cols[cn] : cn;
                 if (tma_ok(coln)) {
                     fence_proxy_async();
                     mbar_expect_tx(bar, col_bytes);
-                    bulk_g2s(oth, p.X + p.ldx * coln, col_bytes, bar);
+                    bulk_g2s(PADQ ? in : oth, p.X + p.ldx * coln, col_bytes, bar);
                 }
             }
         }
@@ -1380,16 +1468,16 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         double centre = 0.0;
         if (p.center == 1) {
             if (tid == 0) atomicAdd(&g_stats[1], 1ull);
-            if (block_median_hist<NT>(in, G, S1, S2, hist, hres, wcnt, cand, cand_n, centre)) {
+            if (block_median_hist<NT>(sv, G, S1, S2, hist, hres, wcnt, cand, cand_n, centre)) {
                 if (tid == 0) atomicAdd(&g_stats[10], 1ull);
             } else {   // tiny or degenerate columns, > CAND_MAX ties in the middle bin: bracketing selection
                 double s1 = 0.0, s2 = 0.0;
                 for (int q = 0; q < len; ++q) {
-                    const double v = in[a0 + q];
+                    const double v = sv[a0 + q];
                     s1 += v;
                     s2 = fma(v, v, s2);
                 }
-                centre = block_median_smem<NT>(in, a0, len, G, s1, s2, red, phase, cand, cand_n);
+                centre = block_median_smem<NT>(sv, a0, len, G, s1, s2, red, phase, cand, cand_n);
             }
         } else if (p.center == 2) {
             centre = S1 / (double)G;
@@ -1403,7 +1491,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                 double v[4], lo[4], hi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    v[u] = in[g0 + u * NT];
+                    v[u] = sv[g0 + u * NT];
                     lo[u] = p.lo2[g0 + u * NT];
                     hi[u] = p.hi2[g0 + u * NT];
                 }
@@ -1421,21 +1509,23 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
 #pragma unroll
                 for (int u = 0; u < 4; ++u) dst[g0 + u * NT] = x[u];
             }
-            for (int g = g0; g < G; g += NT) dst[g] = fast_exp2(sub_bounds(in[g] - centre, p.lo2[g], p.hi2[g]), etab);
+            for (int g = g0; g < G; g += NT) dst[g] = fast_exp2(sub_bounds(sv[g] - centre, p.lo2[g], p.hi2[g]), etab);
         } else {
             for (int g = tid; g < G; g += NT) {
-                double x = in[g] - centre;
+                double x = sv[g] - centre;
                 if (p.lo2) x = sub_bounds(x, p.lo2[g], p.hi2[g]);
                 else if (p.mid2) x = x - p.mid2[g];
                 if (p.apply_exp2) x = fast_exp2(x, etab);
                 dst[g] = x;
             }
         }
-        __syncthreads();   // `in` is rewritten by the next cell's stage A
+        __syncthreads();   // the smoothed column is rewritten by the next cell's stage A
         lap(5);
-        double *t = in;    // the next cell landed (or will be loaded) in `oth`
-        in = oth;
-        oth = t;
+        if (!PADQ) {       // the next cell landed (or will be loaded) in `oth`
+            double *t = in;
+            in = oth;
+            oth = t;
+        }
     }
 #ifdef ICNV_STAGE_TIMERS
     if (tid == 0 && blockIdx.x == 0)
@@ -1585,11 +1675,23 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         if (nt3 != 256 && nt3 != 512 && nt3 != 1024) nt3 = 1024;
         const int NW3 = nt3 / 32;
         const size_t red3 = (nt3 == 256) ? sizeof(Red<8>) : (nt3 == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
-        const size_t smem3 = 128 * 24 + sizeof(double) * (2 * (size_t)s_elems + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 +
-                                                         CAND_MAX + 2 + (size_t)K * (size_t)h + 2 + 2) + red3 +
-                             sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2) + 64;
+        // padded-Q layout (see the kernel) whenever it fits; ICNV_CELL_PADQ=0 keeps the ping-pong layout (A/B switch)
+        int padq = 1;
+        if (const char *e = getenv("ICNV_CELL_PADQ")) padq = atoi(e) != 0;
+        const int q_elems = (int)(((int64_t)G + (int64_t)K * (2 * h + 2) + 1) & ~(int64_t)1);
         int L3 = want_v2 ? 0 : build_segments(G, chr_start, chr_len, K, nt3, 1 << 20, segs);
         if (L3 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
+        const int ipad = (L3 + 2) & ~1;   // front pad of the reciprocal-denominator table: >= the longest slice, even
+        auto smem_for = [&](bool pq) {
+            const size_t cols = pq ? (size_t)q_elems + (size_t)s_elems + (size_t)ipad
+                                   : 2 * (size_t)s_elems + (size_t)K * (size_t)h;
+            return 128 * 24 + sizeof(double) * (cols + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 + CAND_MAX + 2 + 2 + 2) +
+                   red3 + sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2 + 2 * (size_t)K + 2) + 64;
+        };
+        if (padq && smem_for(true) > (size_t)c.smem_optin) padq = 0;
+        const size_t smem3 = smem_for(padq != 0);
+        p.q_elems = q_elems;
+        p.ipad = ipad;
         if (L3 > 0 && smem3 <= (size_t)c.smem_optin) {
             Seg *d_segs3 = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
             if (!d_segs3) return ICNV_E_NOMEM;
@@ -1601,8 +1703,13 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
                 kern<<<(unsigned)grid3, nt3, smem3, st>>>(p);
                 return ICNV_OK;
             };
-            int rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256>)
-                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512>) : launch3(cell_pipeline3_kernel<1024>));
+            int rc3;
+            if (padq)
+                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, true>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, true>) : launch3(cell_pipeline3_kernel<1024, true>));
+            else
+                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, false>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, false>) : launch3(cell_pipeline3_kernel<1024, false>));
             if (rc3) return rc3;
             ICNV_CHECK_LAUNCH("cell_pipeline3_kernel");
             return ICNV_OK;

@@ -302,11 +302,21 @@ inline void launch(const Cfg &cfg, const std::function<void()> &fn) {
     blockDim = cfg.block;
     dyn_smem_bytes = cfg.smem;
     ++launches;
+    // canary behind the dynamic shared memory the launch asked for: a store past the end (a size formula in a launcher that
+    // forgot a table) is caught here; a load past the end reads the canary and shows up as a parity failure
+    const size_t guard = DYN_SMEM_MAX - cfg.smem < 4096 ? DYN_SMEM_MAX - cfg.smem : 4096;
     for (unsigned by = 0; by < cfg.grid.y; ++by)
         for (unsigned bx = 0; bx < cfg.grid.x; ++bx) {
             blockIdx.x = bx;
             blockIdx.y = by;
+            memset(dyn_smem + cfg.smem, 0x5C, guard);
             run_block(cfg.block.x, fn);
+            for (size_t i = 0; i < guard; ++i)
+                if (dyn_smem[cfg.smem + i] != 0x5C) {
+                    fprintf(stderr, "emu: block (%u,%u) wrote %zu bytes past its %zu bytes of dynamic shared memory\n", bx, by,
+                            i + 1, cfg.smem);
+                    abort();
+                }
         }
 }
 

@@ -174,6 +174,34 @@ def test_smooth_block_slow_paths_of_the_grouped_element_wise_loops(api):
             assert e.value.code == -5
 
 
+def test_smooth_block_padded_q_layout_is_bit_identical(api, monkeypatch):
+    """cell_pipeline3_kernel<NT, true> (padded Q, fixed buffer roles - the default) against <NT, false> (ping-pong buffers,
+    index-selected edge loads; ICNV_CELL_PADQ=0): the same arithmetic in the same order, so identical bits.  Chromosome
+    lengths cover: shorter than the window (both ends in every window), 2h+1 .. 2h+1+slice (a slice can see both ends),
+    single-gene and two-gene chromosomes, long ones; windows 101, 15, 3 and none; all three thread counts."""
+    rng = np.random.default_rng(5)
+    for lens, C in (([300, 150, 60, 1, 201, 2, 103, 104, 115], 9), ([1500, 101, 102, 900, 77, 400], 5),
+                    ([2900, 2100, 1700, 303], 3)):
+        lens = np.array(lens, dtype=np.int32)
+        cs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+        G = int(lens.sum())
+        X = rng.gamma(2.0, 1.5, size=(G, C))
+        X[rng.random((G, C)) < 0.3] = 0.0
+        refs = [np.arange(0, 2), np.arange(2, 3)]
+        for w in (101, 15, 3):
+            out = {}
+            for flag in ("1", "0"):
+                monkeypatch.setenv("ICNV_CELL_PADQ", flag)
+                out[flag] = api.smooth_block(X, cs, lens, refs, apply_log=True, threshold=3.0, window_length=w)
+            assert np.array_equal(out["1"], out["0"]), (G, w)
+            want = orc.smooth_block(X, cs, lens, refs, window=w)
+            assert np.max(np.abs(out["1"] - want) / np.abs(want)) < 1e-10   # prefix sums over up to 2900 genes
+        for flag in ("1", "0"):
+            monkeypatch.setenv("ICNV_CELL_PADQ", flag)
+            out[flag] = api.smooth(np.log2(X + 1.0), cs, lens, 51)
+        assert np.array_equal(out["1"], out["0"])
+
+
 def test_smooth_block_20k_genes_single_buffer_variant(api):
     """config c5's gene count: two shared-memory buffers no longer fit, the kernel runs its
     single-buffer / 1024-thread variant."""
