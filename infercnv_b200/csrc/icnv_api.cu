@@ -423,39 +423,6 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), sc));
     double *lo1 = nullptr, *hi1 = nullptr, *mid1 = nullptr, *lo2 = nullptr, *hi2 = nullptr, *mid2 = nullptr;
 
-    if (do_smooth) {
-        // ---- reference pre-passes on a compact copy of the reference columns (<= ~10 % of the cells) ----
-        const int64_t n_ref = grp_off[n_grp];
-        double *d_ref = (double *)scratch(SLOT_REFX, sizeof(double) * (size_t)G * (size_t)n_ref);
-        double *d_T = (double *)scratch(SLOT_TMP, sizeof(double) * (size_t)G * (size_t)n_ref);
-        double *d_means = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
-        double *d_b = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)G * 6);
-        int32_t *d_iota = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_ref);
-        if (!d_ref || !d_T || !d_means || !d_b || !d_iota) return ICNV_E_NOMEM;
-        for (int64_t i = 0; i < n_ref;) {  // runs of consecutive cells go up in one copy
-            int64_t j = i + 1;
-            while (j < n_ref && grp_idx[j] == grp_idx[j - 1] + 1) ++j;
-            ICNV_CUDA(cudaMemcpyAsync(d_ref + G * i, X + G * (int64_t)grp_idx[i], sizeof(double) * (size_t)(G * (j - i)),
-                                      cudaMemcpyHostToDevice, sc));
-            i = j;
-        }
-        std::vector<int32_t> iota((size_t)n_ref);
-        std::iota(iota.begin(), iota.end(), 0);
-        ICNV_CUDA(cudaMemcpyAsync(d_iota, iota.data(), sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, sc));
-        ICNV_CUDA(cudaStreamSynchronize(sc));
-        lo1 = d_b; hi1 = d_b + G; mid1 = d_b + 2 * G; lo2 = d_b + 3 * G; hi2 = d_b + 4 * G; mid2 = d_b + 5 * G;
-        if ((rc = dev_group_means(d_ref, G, G, d_iota, grp_off, n_grp, apply_log ? 1 : 0, d_means, sc))) return rc;
-        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo1, hi1, mid1, sc))) return rc;
-        rc = icnv_dev_cell_pipeline_f64(d_ref, G, G, nullptr, n_ref, d_T, G, chr_start, chr_len, K, apply_log,
-                                        use_bounds ? lo1 : nullptr, use_bounds ? hi1 : nullptr, use_bounds ? nullptr : mid1,
-                                        threshold, window, 1, nullptr, nullptr, nullptr, 0, d_flag, sc);
-        if (rc) return rc;
-        if ((rc = dev_group_means(d_T, G, G, d_iota, grp_off, n_grp, 0, d_means, sc))) return rc;
-        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo2, hi2, mid2, sc))) return rc;
-        if (!use_bounds) lo1 = hi1 = lo2 = hi2 = nullptr;
-        else mid1 = mid2 = nullptr;
-    }
-
     // ---- slabs ------------------------------------------------------------------------------------------
     int64_t slab_cells = SLAB_CELLS;
     if (const char *e = getenv("ICNV_SLAB_CELLS")) {   // tuning knob
@@ -484,14 +451,59 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
         }
     }
     const int64_t n_slabs = (C + slab - 1) / slab;
+    // H2D of slab i (buffer i & 1) may start once the kernels of slab i-2 have consumed the buffer
+    auto issue_h2d = [&](int64_t i) -> int {
+        const int b = (int)(i & 1);
+        const int64_t c0 = i * slab, nc = std::min<int64_t>(slab, C - c0);
+        if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sh, c.ev_comp[b], 0));
+        ICNV_CUDA(cudaMemcpyAsync(dIn[b], X + G * c0, sizeof(double) * (size_t)G * (size_t)nc, cudaMemcpyHostToDevice, sh));
+        ICNV_CUDA(cudaEventRecord(c.ev_h2d[b], sh));
+        return ICNV_OK;
+    };
+    int64_t h2d_issued = 0;
+
+    if (do_smooth) {
+        // ---- reference pre-passes on a compact copy of the reference columns (<= ~10 % of the cells) ----
+        const int64_t n_ref = grp_off[n_grp];
+        double *d_ref = (double *)scratch(SLOT_REFX, sizeof(double) * (size_t)G * (size_t)n_ref);
+        double *d_T = (double *)scratch(SLOT_TMP, sizeof(double) * (size_t)G * (size_t)n_ref);
+        double *d_means = (double *)scratch(SLOT_MEANS, sizeof(double) * (size_t)G * (size_t)n_grp);
+        double *d_b = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)G * 6);
+        int32_t *d_iota = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_ref);
+        if (!d_ref || !d_T || !d_means || !d_b || !d_iota) return ICNV_E_NOMEM;
+        for (int64_t i = 0; i < n_ref;) {  // runs of consecutive cells go up in one copy
+            int64_t j = i + 1;
+            while (j < n_ref && grp_idx[j] == grp_idx[j - 1] + 1) ++j;
+            ICNV_CUDA(cudaMemcpyAsync(d_ref + G * i, X + G * (int64_t)grp_idx[i], sizeof(double) * (size_t)(G * (j - i)),
+                                      cudaMemcpyHostToDevice, sc));
+            i = j;
+        }
+        std::vector<int32_t> iota((size_t)n_ref);
+        std::iota(iota.begin(), iota.end(), 0);
+        ICNV_CUDA(cudaMemcpyAsync(d_iota, iota.data(), sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, sc));
+        // the first two slabs queue up behind the reference columns and cross PCIe while the pre-passes run
+        for (; h2d_issued < std::min<int64_t>(2, n_slabs); ++h2d_issued)
+            if ((rc = issue_h2d(h2d_issued))) return rc;
+        ICNV_CUDA(cudaStreamSynchronize(sc));
+        lo1 = d_b; hi1 = d_b + G; mid1 = d_b + 2 * G; lo2 = d_b + 3 * G; hi2 = d_b + 4 * G; mid2 = d_b + 5 * G;
+        if ((rc = dev_group_means(d_ref, G, G, d_iota, grp_off, n_grp, apply_log ? 1 : 0, d_means, sc))) return rc;
+        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo1, hi1, mid1, sc))) return rc;
+        rc = icnv_dev_cell_pipeline_f64(d_ref, G, G, nullptr, n_ref, d_T, G, chr_start, chr_len, K, apply_log,
+                                        use_bounds ? lo1 : nullptr, use_bounds ? hi1 : nullptr, use_bounds ? nullptr : mid1,
+                                        threshold, window, 1, nullptr, nullptr, nullptr, 0, d_flag, sc);
+        if (rc) return rc;
+        if ((rc = dev_group_means(d_T, G, G, d_iota, grp_off, n_grp, 0, d_means, sc))) return rc;
+        if ((rc = icnv_dev_bounds_from_means_f64(d_means, G, n_grp, lo2, hi2, mid2, sc))) return rc;
+        if (!use_bounds) lo1 = hi1 = lo2 = hi2 = nullptr;
+        else mid1 = mid2 = nullptr;
+    }
+
     for (int64_t i = 0; i < n_slabs; ++i) {
         const int b = (int)(i & 1);
         const int64_t c0 = i * slab, nc = std::min<int64_t>(slab, C - c0);
         const size_t bytes = sizeof(double) * (size_t)G * (size_t)nc;
-        // H2D of slab i may start once the kernels of slab i-2 have consumed buffer b
-        if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sh, c.ev_comp[b], 0));
-        ICNV_CUDA(cudaMemcpyAsync(dIn[b], X + G * c0, bytes, cudaMemcpyHostToDevice, sh));
-        ICNV_CUDA(cudaEventRecord(c.ev_h2d[b], sh));
+        for (; h2d_issued <= i; ++h2d_issued)
+            if ((rc = issue_h2d(h2d_issued))) return rc;
         // kernels: need the slab on the device and the output buffers of slab i-2 drained
         ICNV_CUDA(cudaStreamWaitEvent(sc, c.ev_h2d[b], 0));
         if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sc, c.ev_d2h[b], 0));

@@ -1032,8 +1032,10 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
         const double tx = fma(v.x, scale, C), ty = fma(v.y, scale, C);
         const int hx = __double2hiint(tx), hy = __double2hiint(ty);
         const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
-        if (hx == HI0 && lx < (unsigned)HIST_NB) atomicAdd(&hist[lx], 1);
-        if (hy == HI0 && ly < (unsigned)HIST_NB) atomicAdd(&hist[ly], 1);
+        // values outside mean +- sd count into a spare word behind the bins (hres[7], never read): one unconditional
+        // atomic per value instead of a branch around it
+        atomicAdd(&hist[(hx == HI0 && lx < (unsigned)HIST_NB) ? lx : (unsigned)(HIST_NB + 7)], 1);
+        atomicAdd(&hist[(hy == HI0 && ly < (unsigned)HIST_NB) ? ly : (unsigned)(HIST_NB + 7)], 1);
         cb += (hx < HI0) ? 1 : 0;
         cb += (hy < HI0) ? 1 : 0;
     }
@@ -1086,8 +1088,12 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
         const double tx = fma(v.x, scale, C), ty = fma(v.y, scale, C);
         const int hx = __double2hiint(tx), hy = __double2hiint(ty);
         const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
-        if (hx == HI0 && lx >= (unsigned)bA && lx <= (unsigned)bB) cand[atomicAdd(cand_n, 1)] = v.x;
-        if (hy == HI0 && ly >= (unsigned)bA && ly <= (unsigned)bB) cand[atomicAdd(cand_n, 1)] = v.y;
+        const bool gx = hx == HI0 && (lx - (unsigned)bA) <= (unsigned)(bB - bA);
+        const bool gy = hy == HI0 && (ly - (unsigned)bA) <= (unsigned)(bB - bA);
+        if (gx | gy) {   // at most CAND_MAX of the n values: one branch per pair
+            if (gx) cand[atomicAdd(cand_n, 1)] = v.x;
+            if (gy) cand[atomicAdd(cand_n, 1)] = v.y;
+        }
     }
     __syncthreads();
     const int ra = kA - offA, rb = kB - offA;
