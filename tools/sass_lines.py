@@ -44,6 +44,8 @@ def main():
     ap.add_argument("pattern")
     ap.add_argument("--lines", default=None)
     ap.add_argument("--ops", action="store_true", help="opcode histogram per listed line")
+    ap.add_argument("--loops", action="store_true", help="list the loops (backward branches): body length in instructions, "
+                    "source lines it spans - the innermost ones are the per-gene costs quoted in DESIGN.md")
     a = ap.parse_args()
     src = os.path.join(CSRC, a.source)
     with tempfile.TemporaryDirectory() as td:
@@ -53,6 +55,8 @@ def main():
         dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
     text = open(src).read().split("\n")
     lo, hi = (int(v) for v in a.lines.split(":")) if a.lines else (0, 10 ** 9)
+    insts = []      # (address, opcode, source line or None, label in front or None, branch target label or None)
+    pending_label = None
     per_line = collections.Counter()
     per_line_ops = collections.defaultdict(collections.Counter)
     classes = collections.Counter()
@@ -72,6 +76,16 @@ def main():
         if m:
             cur = (os.path.basename(m[1]), int(m[2]))
             continue
+        m = re.match(r"(\.L_x_\d+):", ln)
+        if m:
+            pending_label = m[1]
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)(.*)", ln)
+        if m:
+            tgt = re.search(r"`\((\.L_x_\d+)\)", m[3])
+            insts.append((int(m[1], 16), m[2], cur[1] if cur and cur[0] == os.path.basename(src) else None, pending_label,
+                          tgt[1] if tgt and m[2].startswith("BRA") else None))
+            pending_label = None
         m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", ln)
         if not m or cur is None:
             continue
@@ -85,6 +99,20 @@ def main():
             other_files[cur[0]] += 1
             if a.lines is None:
                 classes[classify(op)] += 1
+    if a.loops:
+        at = {lab: i for i, (_, _, _, lab, _) in enumerate(insts) if lab}
+        print(f"# loops of {a.pattern} (backward branches): instructions in the body, source lines spanned, body opcode classes")
+        for i, (addr, op, line, lab, tgt) in enumerate(insts):
+            if tgt and tgt in at and at[tgt] <= i:
+                body = insts[at[tgt]:i + 1]
+                lines = [b[2] for b in body if b[2]]
+                if a.lines and not (lines and lo <= min(lines) and max(lines) <= hi):
+                    continue
+                cls = collections.Counter(classify(b[1]) for b in body)
+                calls = sum(1 for b in body if b[1].startswith("CALL"))
+                print(f"{len(body):5d} instr  lines {min(lines) if lines else '?'}-{max(lines) if lines else '?'}  "
+                      f"{dict(cls.most_common())}" + (f"  (contains {calls} out-of-line calls: slow paths)" if calls else ""))
+        return 0
     total = sum(per_line.values())
     print(f"# {a.pattern}: {total} instructions attributed to {os.path.basename(src)}"
           + (f" lines {lo}-{hi}" if a.lines else "") + f"; inlined headers: {dict(other_files)}")
