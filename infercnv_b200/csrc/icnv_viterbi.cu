@@ -439,8 +439,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
 #pragma unroll 1
             for (int j = j0; j < j1; ++j) {
                 const int i = blk * TG + j - g_lo;
-                const double x = row[j];
-                if (!is_finite_d(x)) err |= 1;
+                const double x = row[j];   // a non-finite x makes every zs NaN / Inf: it is caught on the rare path below
                 // ---- emissions: g(z_k) from the table ------------------------------------------------
                 double le[MAXM], zs[MAXM];
 #pragma unroll
@@ -466,6 +465,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                         le[k] = fma(u, v, c01.x);
                     }
                 } else {   // some state further than 24 sd from x (rare): per-state choice, nmath beyond the table
+                    if (!is_finite_d(x)) err |= 1;
 #pragma unroll
                     for (int k = 0; k < M; ++k) {
                         double v;
