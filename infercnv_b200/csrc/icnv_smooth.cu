@@ -595,25 +595,35 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
         const double *__restrict__ rawsrc = LANDING ? raw : (p.X + p.ldx * col);
         if (p.apply_log && p.lo1 && p.threshold > 0.0) {
             // the fused-block configuration: log2(x+1) -> dead-band subtract -> clamp, no per-element mode tests
+            // (groups of four genes as one straight-line block, the remainder one at a time: see cell_pipeline3_kernel)
             const double thr = p.threshold;
-            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+            int g0 = tid;
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int g = min(g0 + u * NT, G - 1);
-                    v[u] = rawsrc[g];
-                    lo[u] = p.lo1[g];
-                    hi[u] = p.hi1[g];
+                    v[u] = rawsrc[g0 + u * NT];
+                    lo[u] = p.lo1[g0 + u * NT];
+                    hi[u] = p.hi1[g0 + u * NT];
+                }
+                bool slow = false;
+                double x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = fast_log2_1p_nc(v[u], ltab, slow);
+                if (slow) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!is_finite_d(v[u])) bad = true;
+                        x[u] = fast_log2_1p(v[u], ltab);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    if (!is_finite_d(v[u])) bad = true;
-                    double x = fast_log2_1p(v[u], ltab);
-                    x = sub_bounds(x, lo[u], hi[u]);
-                    x = clamp_sym(x, thr);
-                    if (g < G) work[g] = x;
-                }
+                for (int u = 0; u < 4; ++u) work[g0 + u * NT] = clamp_sym(sub_bounds(x[u], lo[u], hi[u]), thr);
+            }
+            for (int g = g0; g < G; g += NT) {
+                const double v = rawsrc[g];
+                if (!is_finite_d(v)) bad = true;
+                work[g] = clamp_sym(sub_bounds(fast_log2_1p(v, ltab), p.lo1[g], p.hi1[g]), thr);
             }
         } else {
         for (int g0 = tid; g0 < G; g0 += 4 * NT) {
@@ -775,22 +785,30 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
 
         // ---- stage D ------------------------------------------------------------------------------------
         if (p.lo2 && p.apply_exp2) {
-            for (int g0 = tid; g0 < G; g0 += 4 * NT) {
+            int g0 = tid;
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int g = min(g0 + u * NT, G - 1);
-                    v[u] = work[g];
-                    lo[u] = p.lo2[g];
-                    hi[u] = p.hi2[g];
+                    v[u] = work[g0 + u * NT];
+                    lo[u] = p.lo2[g0 + u * NT];
+                    hi[u] = p.hi2[g0 + u * NT];
                 }
+                bool slow = false;
+                double x[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    const double x = fast_exp2(sub_bounds(v[u], lo[u], hi[u]), etab);
-                    if (g < G) dst[g] = x;
+                    v[u] = sub_bounds(v[u], lo[u], hi[u]);
+                    x[u] = fast_exp2_nc(v[u], etab, slow);
                 }
+                if (slow) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = fast_exp2(v[u], etab);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dst[g0 + u * NT] = x[u];
             }
+            for (int g = g0; g < G; g += NT) dst[g] = fast_exp2(sub_bounds(work[g], p.lo2[g], p.hi2[g]), etab);
         } else {
         for (int g0 = tid; g0 < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
@@ -1334,7 +1352,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             // pass 3: Q in place (each thread touches only its own slice); PADQ: into the padded layout in `in`, where
             // Q(0) of chromosome c sits at cs + c (2h + 2) + (h + 2)
             const int pbase = cs + seg.chr * (2 * h + 2) + (h + 2);
-            double *__restrict__ qdst = PADQ ? (in + pbase + (a0 - cs)) : (oth + a0);
+            double *qdst = PADQ ? (in + pbase + (a0 - cs)) : (oth + a0);   // aliases xs in the ping-pong layout
             pr = offP;
             double qv = offQ;
 #pragma unroll 4
