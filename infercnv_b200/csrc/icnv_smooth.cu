@@ -489,6 +489,59 @@ __device__ __forceinline__ double sub_bounds(double x, double lo, double hi) {
 // apply_max_threshold_bounds (ops.R:2970-2983): clamp to [-thr, thr]
 __device__ __forceinline__ double clamp_sym(double x, double thr) { return (fabs(x) > thr) ? copysign(thr, x) : x; }
 
+// Stage A / D of the fused-block configuration for U genes STRIDE apart, as one straight-line block: no bounds tests, and no
+// range branch per value - fast_log2_1p_nc / fast_exp2_nc only raise `slow`, and the group is then re-evaluated through the
+// library path (zero / negative / denormal / non-finite x + 1; |x| >= 1000 or NaN).
+template <int U, int STRIDE>
+__device__ __forceinline__ void stage_a_group(const double *__restrict__ src, double *__restrict__ dstv,
+                                              const double *__restrict__ lo1, const double *__restrict__ hi1, int g0, double thr,
+                                              const double2 *__restrict__ ltab, bool &bad) {
+    double v[U], lo[U], hi[U], x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        v[u] = src[g0 + u * STRIDE];
+        lo[u] = lo1[g0 + u * STRIDE];
+        hi[u] = hi1[g0 + u * STRIDE];
+    }
+    bool slow = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) x[u] = fast_log2_1p_nc(v[u], ltab, slow);
+    if (slow) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!is_finite_d(v[u])) bad = true;
+            x[u] = fast_log2_1p(v[u], ltab);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) dstv[g0 + u * STRIDE] = clamp_sym(sub_bounds(x[u], lo[u], hi[u]), thr);
+}
+
+template <int U, int STRIDE>
+__device__ __forceinline__ void stage_d_group(const double *__restrict__ src, double *__restrict__ dst,
+                                              const double *__restrict__ lo2, const double *__restrict__ hi2, int g0, double centre,
+                                              const double *__restrict__ etab) {
+    double v[U], lo[U], hi[U], x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        v[u] = src[g0 + u * STRIDE];
+        lo[u] = lo2[g0 + u * STRIDE];
+        hi[u] = hi2[g0 + u * STRIDE];
+    }
+    bool slow = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        v[u] = sub_bounds(v[u] - centre, lo[u], hi[u]);
+        x[u] = fast_exp2_nc(v[u], etab, slow);
+    }
+    if (slow) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = fast_exp2(v[u], etab);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) dst[g0 + u * STRIDE] = x[u];
+}
+
 // ---- mbarrier / bulk-copy (TMA) helpers: the next cell's column is fetched by the copy engine
 //      into shared memory while the CTA works on the current one --------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -595,36 +648,15 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
         const double *__restrict__ rawsrc = LANDING ? raw : (p.X + p.ldx * col);
         if (p.apply_log && p.lo1 && p.threshold > 0.0) {
             // the fused-block configuration: log2(x+1) -> dead-band subtract -> clamp, no per-element mode tests
-            // (groups of four genes as one straight-line block, the remainder one at a time: see cell_pipeline3_kernel)
+            // groups of four genes NT apart as one straight-line block, then two, then one (see stage_a_group)
             const double thr = p.threshold;
             int g0 = tid;
-            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
-                double v[4], lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = rawsrc[g0 + u * NT];
-                    lo[u] = p.lo1[g0 + u * NT];
-                    hi[u] = p.hi1[g0 + u * NT];
-                }
-                bool slow = false;
-                double x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = fast_log2_1p_nc(v[u], ltab, slow);
-                if (slow) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (!is_finite_d(v[u])) bad = true;
-                        x[u] = fast_log2_1p(v[u], ltab);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) work[g0 + u * NT] = clamp_sym(sub_bounds(x[u], lo[u], hi[u]), thr);
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) stage_a_group<4, NT>(rawsrc, work, p.lo1, p.hi1, g0, thr, ltab, bad);
+            if (g0 + NT < G) {
+                stage_a_group<2, NT>(rawsrc, work, p.lo1, p.hi1, g0, thr, ltab, bad);
+                g0 += 2 * NT;
             }
-            for (int g = g0; g < G; g += NT) {
-                const double v = rawsrc[g];
-                if (!is_finite_d(v)) bad = true;
-                work[g] = clamp_sym(sub_bounds(fast_log2_1p(v, ltab), p.lo1[g], p.hi1[g]), thr);
-            }
+            if (g0 < G) stage_a_group<1, NT>(rawsrc, work, p.lo1, p.hi1, g0, thr, ltab, bad);
         } else {
         for (int g0 = tid; g0 < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
@@ -785,30 +817,13 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p
 
         // ---- stage D ------------------------------------------------------------------------------------
         if (p.lo2 && p.apply_exp2) {
-            int g0 = tid;
-            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
-                double v[4], lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = work[g0 + u * NT];
-                    lo[u] = p.lo2[g0 + u * NT];
-                    hi[u] = p.hi2[g0 + u * NT];
-                }
-                bool slow = false;
-                double x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = sub_bounds(v[u], lo[u], hi[u]);
-                    x[u] = fast_exp2_nc(v[u], etab, slow);
-                }
-                if (slow) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = fast_exp2(v[u], etab);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) dst[g0 + u * NT] = x[u];
+            int g0 = tid;   // work[] already holds the centred values
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) stage_d_group<4, NT>(work, dst, p.lo2, p.hi2, g0, 0.0, etab);
+            if (g0 + NT < G) {
+                stage_d_group<2, NT>(work, dst, p.lo2, p.hi2, g0, 0.0, etab);
+                g0 += 2 * NT;
             }
-            for (int g = g0; g < G; g += NT) dst[g] = fast_exp2(sub_bounds(work[g], p.lo2[g], p.hi2[g]), etab);
+            if (g0 < G) stage_d_group<1, NT>(work, dst, p.lo2, p.hi2, g0, 0.0, etab);
         } else {
         for (int g0 = tid; g0 < G; g0 += 4 * NT) {
                 double v[4], lo[4], hi[4];
@@ -1256,36 +1271,15 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         lap(0);
         if (p.apply_log && p.lo1 && p.threshold > 0.0) {
             // groups of four genes NT apart as one straight-line block (no bounds tests, no per-value range branch), then
-            // the < 4 genes a thread has left one at a time
+            // two, then one: at 10 000 genes and 1024 threads every thread runs 4 + 4 + (2 or 1)
             const double thr = p.threshold;
             int g0 = tid;
-            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
-                double v[4], lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = in[g0 + u * NT];
-                    lo[u] = p.lo1[g0 + u * NT];
-                    hi[u] = p.hi1[g0 + u * NT];
-                }
-                bool slow = false;
-                double x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = fast_log2_1p_nc(v[u], ltab, slow);
-                if (slow) {   // zero / negative / denormal / non-finite x + 1 somewhere in the group (rare)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (!is_finite_d(v[u])) bad = true;
-                        x[u] = fast_log2_1p(v[u], ltab);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) oth[g0 + u * NT] = clamp_sym(sub_bounds(x[u], lo[u], hi[u]), thr);
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) stage_a_group<4, NT>(in, oth, p.lo1, p.hi1, g0, thr, ltab, bad);
+            if (g0 + NT < G) {
+                stage_a_group<2, NT>(in, oth, p.lo1, p.hi1, g0, thr, ltab, bad);
+                g0 += 2 * NT;
             }
-            for (int g = g0; g < G; g += NT) {
-                const double v = in[g];
-                if (!is_finite_d(v)) bad = true;
-                oth[g] = clamp_sym(sub_bounds(fast_log2_1p(v, ltab), p.lo1[g], p.hi1[g]), thr);
-            }
+            if (g0 < G) stage_a_group<1, NT>(in, oth, p.lo1, p.hi1, g0, thr, ltab, bad);
         } else {
             for (int g = tid; g < G; g += NT) {
                 double x = in[g];
@@ -1511,29 +1505,12 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         // ---- D: centre, second reference subtraction, 2^x fused into the one coalesced write ----------------
         if (p.lo2 && p.apply_exp2) {
             int g0 = tid;
-            for (; g0 + 3 * NT < G; g0 += 4 * NT) {
-                double v[4], lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = sv[g0 + u * NT];
-                    lo[u] = p.lo2[g0 + u * NT];
-                    hi[u] = p.hi2[g0 + u * NT];
-                }
-                bool slow = false;
-                double x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    v[u] = sub_bounds(v[u] - centre, lo[u], hi[u]);
-                    x[u] = fast_exp2_nc(v[u], etab, slow);
-                }
-                if (slow) {   // |x| >= 1000 or NaN somewhere in the group (rare): library exp2
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = fast_exp2(v[u], etab);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) dst[g0 + u * NT] = x[u];
+            for (; g0 + 3 * NT < G; g0 += 4 * NT) stage_d_group<4, NT>(sv, dst, p.lo2, p.hi2, g0, centre, etab);
+            if (g0 + NT < G) {
+                stage_d_group<2, NT>(sv, dst, p.lo2, p.hi2, g0, centre, etab);
+                g0 += 2 * NT;
             }
-            for (int g = g0; g < G; g += NT) dst[g] = fast_exp2(sub_bounds(sv[g] - centre, p.lo2[g], p.hi2[g]), etab);
+            if (g0 < G) stage_d_group<1, NT>(sv, dst, p.lo2, p.hi2, g0, centre, etab);
         } else {
             for (int g = tid; g < G; g += NT) {
                 double x = sv[g] - centre;
