@@ -1155,8 +1155,12 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
 // continuation table and a zero slot per load (53 -> ~20 instructions per gene in that loop; results bit-identical).
 // Buffer roles are then fixed instead of ping-pong: buf0 = landing buffer of the bulk copy, later the padded Q;
 // buf1 = x', later the smoothed values that stages C and D read.
-template <int NT, bool PADQ>
+// LFIX > 0: every busy thread's slice has at most LFIX genes (the launcher's segment length): the three scan passes are then
+// fully unrolled with a per-gene predicate instead of counted loops with remainders (21 -> 12.5 instructions per gene over
+// the three passes); LFIX = 0 is the generic form.
+template <int NT, bool PADQ, int LFIX>
 __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams p) {
+    constexpr bool FIX = LFIX > 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
@@ -1307,8 +1311,9 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         } else {
             // pass 1: segment total of x
             double tot = 0.0;
-#pragma unroll 4
-            for (int q = 0; q < len; ++q) tot += xs[q];
+#pragma unroll(FIX ? LFIX : 4)
+            for (int q = 0; q < (FIX ? LFIX : len); ++q)
+                if (!FIX || q < len) tot += xs[q];
             double inc = tot;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -1324,11 +1329,12 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             const double offP = exc + carry;   // P just before this segment
             // pass 2: segment total of P (P = prefix of x inside the chromosome)
             double pr = offP, qsum = 0.0;
-#pragma unroll 4
-            for (int q = 0; q < len; ++q) {
-                pr += xs[q];
-                qsum += pr;
-            }
+#pragma unroll(FIX ? LFIX : 4)
+            for (int q = 0; q < (FIX ? LFIX : len); ++q)
+                if (!FIX || q < len) {
+                    pr += xs[q];
+                    qsum += pr;
+                }
             const double plast = pr;
             inc = qsum;
 #pragma unroll
@@ -1349,12 +1355,13 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             double *qdst = PADQ ? (in + pbase + (a0 - cs)) : (oth + a0);   // aliases xs in the ping-pong layout
             pr = offP;
             double qv = offQ;
-#pragma unroll 4
-            for (int q = 0; q < len; ++q) {
-                pr += xs[q];
-                qv += pr;
-                qdst[q] = qv;
-            }
+#pragma unroll(FIX ? LFIX : 4)
+            for (int q = 0; q < (FIX ? LFIX : len); ++q)
+                if (!FIX || q < len) {
+                    pr += xs[q];
+                    qv += pr;
+                    qdst[q] = qv;
+                }
             if (len > 0 && a0 + len == ce) {
                 ptot[seg.chr] = plast;
                 qtot[seg.chr] = qv;
@@ -1391,7 +1398,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
                     // genes: the constant entries in front of index 0), read through a pointer that moves by dI per gene
                     const double *__restrict__ pa = P + h, *__restrict__ pb = P - 1, *__restrict__ pc = P - h - 2;
                     const double *__restrict__ pI = invD + r0I;
-#pragma unroll 2
+#pragma unroll 2   // (fully unrolled with a predicate per gene this loop turns into branches: 22.5 against 18.5 per gene)
                     for (int q = 0; q < len; ++q) {
                         const double qb = pb[q];
                         const double N = (pa[q] - qb) - (qb - pc[q]);
@@ -1705,12 +1712,17 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
                 return ICNV_OK;
             };
             int rc3;
-            if (padq)
-                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, true>)
-                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, true>) : launch3(cell_pipeline3_kernel<1024, true>));
+            // fully unrolled slice loops for the segment length of the 10 000-gene configurations (ICNV_CELL_LFIX=0: generic)
+            int lfix = (padq && nt3 == 1024 && L3 == 11) ? 11 : 0;
+            if (const char *e = getenv("ICNV_CELL_LFIX")) if (atoi(e) == 0) lfix = 0;
+            if (lfix == 11)
+                rc3 = launch3(cell_pipeline3_kernel<1024, true, 11>);
+            else if (padq)
+                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, true, 0>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, true, 0>) : launch3(cell_pipeline3_kernel<1024, true, 0>));
             else
-                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, false>)
-                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, false>) : launch3(cell_pipeline3_kernel<1024, false>));
+                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, false, 0>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, false, 0>) : launch3(cell_pipeline3_kernel<1024, false, 0>));
             if (rc3) return rc3;
             ICNV_CHECK_LAUNCH("cell_pipeline3_kernel");
             return ICNV_OK;

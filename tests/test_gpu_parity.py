@@ -202,6 +202,30 @@ def test_smooth_block_padded_q_layout_is_bit_identical(api, monkeypatch):
         assert np.array_equal(out["1"], out["0"])
 
 
+def test_smooth_block_benchmark_layout_unrolled_slices(api, monkeypatch):
+    """10 000 genes in the benchmark's 22 chromosomes: 1024 threads with slices of 11 genes, the layout for which the scan
+    passes are compiled fully unrolled (cell_pipeline3_kernel<1024, true, 11>).  Same bits as the generic form
+    (ICNV_CELL_LFIX=0) and as the ping-pong layout, and the oracle's values."""
+    import bench
+    cs, lens = bench.chr_layout(10000)
+    rng = np.random.default_rng(21)
+    G, C = 10000, 6
+    X = rng.gamma(2.0, 1.5, size=(G, C))
+    X[rng.random((G, C)) < 0.3] = 0.0
+    refs = [np.arange(0, 2), np.arange(2, 3)]
+    out = {}
+    for name, env in (("unrolled", {}), ("generic", {"ICNV_CELL_LFIX": "0"}), ("pingpong", {"ICNV_CELL_PADQ": "0"})):
+        for k in ("ICNV_CELL_LFIX", "ICNV_CELL_PADQ"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out[name] = api.smooth_block(X, cs, lens, refs, apply_log=True, threshold=3.0, window_length=101)
+    assert np.array_equal(out["unrolled"], out["generic"])
+    assert np.array_equal(out["unrolled"], out["pingpong"])
+    want = orc.smooth_block(X, cs, lens, refs)
+    assert np.max(np.abs(out["unrolled"] - want) / np.abs(want)) < 1e-10
+
+
 def test_smooth_block_20k_genes_single_buffer_variant(api):
     """config c5's gene count: two shared-memory buffers no longer fit, the kernel runs its
     single-buffer / 1024-thread variant."""

@@ -11,6 +11,8 @@ timeout 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.
 # 3. A/B of what changed since profiles/r01_bench.json (device-resident value only; every line is one JSON record)
 #    a. cell pipeline: padded Q layout off (the measured ping-pong layout + the new stage A / D groups)
 ICNV_CELL_PADQ=0 timeout 300 $B > gpurun_out/r02_ab_padq0.json 2>/dev/null
+#    a2. counted scan loops instead of the fully unrolled slices
+ICNV_CELL_LFIX=0 timeout 300 $B > gpurun_out/r02_ab_lfix0.json 2>/dev/null
 #    b. reference-column reuse in pass 2 off (default on since the end of round 1)
 ICNV_REF_REUSE=0 timeout 300 $B > gpurun_out/r02_ab_refreuse0.json 2>/dev/null
 #    c. fast Viterbi occupancy variants (default 16 warps per CTA at 128 registers)
