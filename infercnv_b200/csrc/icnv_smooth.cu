@@ -1035,19 +1035,24 @@ __device__ __forceinline__ double block_median_smem(const double *__restrict__ v
 constexpr int HIST_NB = 2048;
 
 template <int NT>
-__device__ __forceinline__ bool block_median_hist(const double *__restrict__ vals, int n, double S1, double S2, int *hist,
+__device__ __forceinline__ bool block_median_hist(const double *__restrict__ vals, int n, double inv_n, double S1, double S2, int *hist,
                                                   int *hres, int *wcnt, double *cand, int *cand_n, double &result) {
     constexpr int NW = NT / 32;
     constexpr int BPT = HIST_NB / NT;   // bins scanned per thread
     static_assert(HIST_NB % NT == 0 && BPT >= 1 && BPT <= 8, "HIST_NB must be a small multiple of NT");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kA = (n - 1) >> 1, kB = n >> 1;
-    const double mean = S1 / (double)n;
-    const double var = S2 / (double)n - mean * mean;
+    // Bin geometry in cheap arithmetic: every thread evaluates the same instruction sequence, so all of them and both
+    // passes bin with identical scale / C, and the median itself never depends on them (the candidates are ranked exactly) -
+    // a single-precision reciprocal square root is enough for "about mean +- sd".  ~25 instead of ~100 instructions per
+    // thread and cell (two divisions, a square root and a third division in double precision before).
+    const double mean = S1 * inv_n;
+    const double var = fma(S2, inv_n, -mean * mean);
     if (!(var > 0.0) || n <= 4 * CAND_MAX) return false;
-    const double sd = sqrt(var);
-    const double scale = (0.5 * HIST_NB) / sd;
-    if (!(scale < 1e290)) return false;
+    const float rs = rsqrtf((float)var);
+    const double sd = var * (double)rs;
+    const double scale = (double)(rs * (0.5f * HIST_NB));
+    if (!(scale < 1e290) || !(scale > 0.0)) return false;   // var outside the single-precision range: bracketing selection
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: integers 0 .. 2^32-1 land in the low word, high word HI0
     constexpr int HI0 = 0x43380000;
     const double C = fma(sd - mean, scale, MAGIC);
@@ -1188,6 +1193,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
     const int G = (int)p.G;
     const int h = p.h;
     const bool do_smooth = p.window >= 2;
+    const double inv_G = 1.0 / (double)G;   // histogram-median bin geometry only
     int phase = 0;
     unsigned parity = 0;
     if (do_smooth) {
@@ -1369,14 +1375,17 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
             __syncthreads();
             // Q continues linearly past a chromosome's last gene (x is taken as 0 there): Q(n-1+k) = Qn + k*Pn, k = 1..h
             if (PADQ) {
+                // a warp per chromosome, lanes over its 2h + 2 pad entries (no integer division per entry)
                 const int padw = 2 * h + 2;
-                for (int idx = tid; idx < p.K * padw; idx += NT) {
-                    const int c = idx / padw, e = idx - c * padw;
+                for (int c = warp; c < p.K; c += NW) {
                     const int nc = chr_n[c];
                     if (nc >= 2) {
                         const int base = chr_cs[c] + c * padw;
-                        if (e < h + 2) in[base + e] = 0.0;
-                        else in[base + nc + e] = fma((double)(e - (h + 1)), ptot[c], qtot[c]);
+                        const double pt = ptot[c], qt = qtot[c];
+                        for (int e = lane; e < padw; e += 32) {
+                            if (e < h + 2) in[base + e] = 0.0;
+                            else in[base + nc + e] = fma((double)(e - (h + 1)), pt, qt);
+                        }
                     }
                 }
             } else {
@@ -1493,7 +1502,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         double centre = 0.0;
         if (p.center == 1) {
             if (tid == 0) atomicAdd(&g_stats[1], 1ull);
-            if (block_median_hist<NT>(sv, G, S1, S2, hist, hres, wcnt, cand, cand_n, centre)) {
+            if (block_median_hist<NT>(sv, G, inv_G, S1, S2, hist, hres, wcnt, cand, cand_n, centre)) {
                 if (tid == 0) atomicAdd(&g_stats[10], 1ull);
             } else {   // tiny or degenerate columns, > CAND_MAX ties in the middle bin: bracketing selection
                 double s1 = 0.0, s2 = 0.0;

@@ -398,6 +398,7 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline double cospi(double x) { return cos(M_PI * x); }
 static inline double sinpi(double x) { return sin(M_PI * x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double __hiloint2double(int hi, int lo) {
     const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
     double v;
