@@ -74,6 +74,8 @@ void *scratch(int slot, size_t bytes) {
     Ctx &c = ctx();
     if (bytes == 0) bytes = 16;
     if (c.slot_bytes[slot] >= bytes) return c.slot_ptr[slot];
+    if (slot == SLOT_SEGS) c.up_segs.clear();          // a new allocation does not hold what was uploaded before
+    if (slot == SLOT_VIT_ITEMS) c.up_items.clear();
     if (c.slot_ptr[slot]) {
         cudaStreamSynchronize(c.stream);
         cudaFree(c.slot_ptr[slot]);
@@ -218,6 +220,8 @@ int icnv_init(int device) {
     c.launches = 0;
     c.table_uploaded = false;
     c.math_tables_uploaded = false;
+    c.up_segs.clear();
+    c.up_items.clear();
     c.hmm_list_count = nullptr;
     c.rg_n = 0;
     if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : 1;
@@ -403,6 +407,7 @@ int icnv_center_f64(const double *X, double *Y, int64_t G, int64_t C, int use_me
 // i-1 run concurrently on three streams (double-buffered device slabs).  PCIe, not the kernels, bounds
 // the host-pointer entry points; this hides everything but the slower copy direction. ---------------
 static const int64_t SLAB_CELLS = 1024;
+static const int64_t SLAB_CELLS_SMOOTH = 256;
 
 struct HmmModel {
     int m;
@@ -424,7 +429,10 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
     double *lo1 = nullptr, *hi1 = nullptr, *mid1 = nullptr, *lo2 = nullptr, *hi2 = nullptr, *mid2 = nullptr;
 
     // ---- slabs ------------------------------------------------------------------------------------------
-    int64_t slab_cells = SLAB_CELLS;
+    // Fill and drain of the copy pipeline cost one slab each way.  Without the HMM a slab's kernel time (~0.05 ms per 256
+    // cells) is far below its PCIe time (0.37 ms), so small slabs only shorten fill / drain; the per-cell Viterbi is bounded
+    // below by its longest chromosome's serial recursion whatever the slab size, so HMM calls keep the measured 1024.
+    int64_t slab_cells = hmm ? SLAB_CELLS : SLAB_CELLS_SMOOTH;
     if (const char *e = getenv("ICNV_SLAB_CELLS")) {   // tuning knob
         const long v = atol(e);
         if (v >= 32 && v <= 65536) slab_cells = v;

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -47,6 +48,7 @@ enum ScratchSlot {
     SLOT_RG_GENE,                     // chromosome id per gene, chromosome ranges, gene start / stop
     SLOT_RG_TILES,                    // per-tile region counts and their scanned offsets
     SLOT_RG_REC,                      // region records of the last call (kept until fetched)
+    SLOT_VIT_ITEMS,                   // chromosome work items of the Viterbi launch (cached: Ctx::up_items)
     SLOT_COUNT
 };
 
@@ -66,8 +68,23 @@ struct Ctx {
     bool math_tables_uploaded = false;
     unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list
     int64_t rg_n = 0;                 // number of region records held in SLOT_RG_REC
+    // what the small per-launch tables (thread segments of the cell pipeline, chromosome items of the Viterbi) held when
+    // they were last uploaded: an unchanged table is not copied again, so the slab loop of the host pipeline enqueues
+    // nothing from pageable host memory (such a copy may synchronise the host with the stream)
+    std::vector<unsigned char> up_segs, up_items;
+    cudaStream_t up_segs_stream = nullptr, up_items_stream = nullptr;   // an upload orders only the stream it was issued on
     std::mutex mu;
 };
+
+// upload `bytes` of `src` to `dst` on `st` unless `cache` says the device copy already holds them and the upload that put
+// them there was ordered on the same stream
+inline cudaError_t upload_if_changed(std::vector<unsigned char> &cache, cudaStream_t &last, void *dst, const void *src,
+                                     size_t bytes, cudaStream_t st) {
+    if (last == st && cache.size() == bytes && memcmp(cache.data(), src, bytes) == 0) return cudaSuccess;
+    cache.assign(static_cast<const unsigned char *>(src), static_cast<const unsigned char *>(src) + bytes);
+    last = st;
+    return cudaMemcpyAsync(dst, cache.data(), bytes, cudaMemcpyHostToDevice, st);
+}
 
 Ctx &ctx();
 int set_error(int code, const char *fmt, ...);

@@ -1712,7 +1712,7 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         if (L3 > 0 && smem3 <= (size_t)c.smem_optin) {
             Seg *d_segs3 = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
             if (!d_segs3) return ICNV_E_NOMEM;
-            ICNV_CUDA(cudaMemcpyAsync(d_segs3, segs.data(), sizeof(Seg) * nt3, cudaMemcpyHostToDevice, st));
+            ICNV_CUDA(upload_if_changed(c.up_segs, c.up_segs_stream, d_segs3, segs.data(), sizeof(Seg) * nt3, st));
             p.segs = d_segs3;
             const int64_t grid3 = std::min<int64_t>(n_cols, c.sm_count);
             auto launch3 = [&](auto kern) -> int {
@@ -1774,7 +1774,7 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
 
     Seg *d_segs = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
     if (!d_segs) return ICNV_E_NOMEM;
-    ICNV_CUDA(cudaMemcpyAsync(d_segs, segs.data(), sizeof(Seg) * NT, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(upload_if_changed(c.up_segs, c.up_segs_stream, d_segs, segs.data(), sizeof(Seg) * NT, st));
     p.segs = d_segs;
 
     auto launch = [&](auto kern) -> int {

@@ -830,9 +830,9 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
         h[4 * K + k] = chr_len[k];
         max_len = std::max(max_len, (int)chr_len[o]);
     }
-    int32_t *d_items = (int32_t *)scratch(SLOT_IDX2, sizeof(int32_t) * 5 * (size_t)K + 64);
+    int32_t *d_items = (int32_t *)scratch(SLOT_VIT_ITEMS, sizeof(int32_t) * 5 * (size_t)K + 64);
     if (!d_items) return ICNV_E_NOMEM;
-    ICNV_CUDA(cudaMemcpyAsync(d_items, h.data(), sizeof(int32_t) * 5 * (size_t)K, cudaMemcpyHostToDevice, st));
+    ICNV_CUDA(upload_if_changed(c.up_items, c.up_items_stream, d_items, h.data(), sizeof(int32_t) * 5 * (size_t)K, st));
     p.item_chr_start = d_items;
     p.item_chr_len = d_items + K;
     p.item_chr_id = d_items + 2 * K;

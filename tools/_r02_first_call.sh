@@ -19,7 +19,7 @@ ICNV_REF_REUSE=0 timeout 300 $B > gpurun_out/r02_ab_refreuse0.json 2>/dev/null
 ICNV_VFAST_WARPS=20 timeout 300 $B > gpurun_out/r02_ab_vfast20.json 2>/dev/null
 ICNV_VFAST_WARPS=24 timeout 300 $B > gpurun_out/r02_ab_vfast24.json 2>/dev/null
 #    d. host pipeline slab size (default 1024 cells; fill + drain of the PCIe pipeline is one slab each way)
-for s in 512 256; do ICNV_SLAB_CELLS=$s timeout 300 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/r02_ab_slab$s.json 2>/dev/null; done
+for s in 1024 512 256; do ICNV_SLAB_CELLS=$s timeout 300 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/r02_ab_slab$s.json 2>/dev/null; done
 for f in gpurun_out/r02_ab_*.json; do echo "$f $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['ms_per_step'], d.get('roofline',{}).get('ms_per_launch'), d.get('roofline_hmm',{}).get('ms_per_launch'), d.get('e2e',{}).get('ms_per_step'))")"; done
 # 4. secondary kernels incl. K7-K9
 timeout 300 python tools/bench_extra.py > gpurun_out/r02_secondary_kernels.json 2> gpurun_out/r02_secondary.err; cat gpurun_out/r02_secondary_kernels.json
