@@ -451,7 +451,8 @@ def main():
             "roofline": {"kernel": "cell_pipeline3_kernel pass 2 (%.0f %% of the step)" % (100 * ms_pass2 / ms_step),
                          "bound": "hbm", "achieved": ach_p2, "peak": peak, "unit": "GB/s", "frac": ach_p2 / peak,
                          "traffic": ncu_traffic("cell_pipeline_pass2") if (C_local, G) == (10000, 10000) else None,
-                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload)",
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch of this workload; "
+                                           "captured before the kernel's instruction diet - the memory traffic, one read and one write of the matrix, is unchanged by it)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": pass2_bytes,
                          "ms_per_launch": ms_pass2,
                          "note": "16 B per cell-gene (one FP64 read, one FP64 write); instruction-issue bound, see DESIGN.md"},
