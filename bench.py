@@ -393,7 +393,15 @@ def main():
             dX = torch.empty_like(X)
             hS8 = torch.empty((C_local, G), dtype=torch.uint8, pin_memory=True)
 
+            # ICNV_BENCH_E2E_PIPELINE=1: copies pipelined against the kernels over cell slabs (Engine.smooth_hmm_host, written
+            # after the last GPU session: opt-in until it has been timed); default: upload, compute, download in sequence
+            pipelined = os.environ.get("ICNV_BENCH_E2E_PIPELINE", "0") == "1"
+
             def e2e_step():
+                if pipelined:
+                    eng.smooth_hmm_host(hX, hY, hS8, dX, Y, states, cs, cl, ref_local, plan.ref_sizes, plan.max_chunks, Pi, delta,
+                                        I6_MEAN, I6_SD)
+                    return
                 dX.copy_(hX, non_blocking=True)
                 eng.smooth_block(dX, cs, cl, ref_local, plan.ref_sizes, plan.max_chunks, out=Y)
                 eng.viterbi(Y, cs, cl, Pi, delta, I6_MEAN, I6_SD, out=states)
@@ -415,7 +423,8 @@ def main():
         e2e = {"value": G * C_total / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(dt.item()) * 1e3, "steps": n_e2e,
                "api": "icnv_smooth_block_f64 + icnv_viterbi_u8_f64 (host pointers, two calls as the R shim makes them)"
-                      if world == 1 else "Engine.smooth_block/viterbi with pinned host tensors"}
+                      if world == 1 else ("Engine.smooth_hmm_host (slab-pipelined copies) with pinned host tensors" if pipelined
+                                          else "Engine.smooth_block/viterbi with pinned host tensors")}
         if fused_step is not None:   # one upload instead of two: the optional fused entry point
             fused_step()
             t0 = time.perf_counter()

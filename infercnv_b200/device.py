@@ -108,14 +108,12 @@ class Engine:
             err_flag.data_ptr() if err_flag is not None else None, _stream_ptr()))
 
     # ---- the hot path ---------------------------------------------------------------------------------------
-    def smooth_block(self, X, chr_start, chr_len, ref_groups_local, ref_sizes=None, max_chunks=None, apply_log=True,
-                     threshold=3.0, window=101, use_bounds=True, out=None):
-        """run() steps 4, 8-12, 14 on this rank's cells.  ref_groups_local: per reference group the
-        LOCAL column indices this rank owns (possibly empty); ref_sizes: GLOBAL group sizes
-        (defaults to the local ones = single GPU).  With a process group initialised the
-        partial sums of the two reference-mean steps are all-gathered (NCCL)."""
+    def _reference_bounds(self, X, chr_start, chr_len, ref_groups_local, ref_sizes, max_chunks, apply_log, threshold, window,
+                          use_bounds, flag):
+        """The two reference-mean steps of the smooth block (ops.R:1678, run() steps 8 and 12): bounds b1 of the log
+        values, pass 1 of the cell pipeline over this rank's reference cells (-> T, centred and smoothed), bounds b2 of T.
+        Only the reference columns of X are read.  Returns (b1, b2, T, n_ref, ref_leading)."""
         C, G = X.shape
-        Y = torch.empty_like(X) if out is None else out
         ref_groups_local = [np.asarray(g, dtype=np.int32) for g in ref_groups_local]
         n_grp = len(ref_groups_local)
         if ref_sizes is None:
@@ -134,7 +132,6 @@ class Engine:
             self._plan_cache.clear()
             cached = self._plan_cache[key] = (d_groups, t_lists, all_ref)
         d_groups, t_lists, all_ref = cached
-        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
 
         import torch.distributed as tdist
         world = tdist.get_world_size() if (self.collective and tdist.is_available() and tdist.is_initialized()) else 1
@@ -171,6 +168,19 @@ class Engine:
             self.cell_pipeline(X, all_ref, T, chr_start, chr_len, apply_log, b1, threshold, window, 1, None, False,
                                use_bounds, flag)
         b2 = self.bounds(group_means(T, t_lists, False))
+        return b1, b2, T, n_ref, ref_leading
+
+    def smooth_block(self, X, chr_start, chr_len, ref_groups_local, ref_sizes=None, max_chunks=None, apply_log=True,
+                     threshold=3.0, window=101, use_bounds=True, out=None):
+        """run() steps 4, 8-12, 14 on this rank's cells.  ref_groups_local: per reference group the
+        LOCAL column indices this rank owns (possibly empty); ref_sizes: GLOBAL group sizes
+        (defaults to the local ones = single GPU).  With a process group initialised the
+        partial sums of the two reference-mean steps are all-gathered (NCCL)."""
+        C, G = X.shape
+        Y = torch.empty_like(X) if out is None else out
+        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+        b1, b2, T, n_ref, ref_leading = self._reference_bounds(X, chr_start, chr_len, ref_groups_local, ref_sizes, max_chunks,
+                                                               apply_log, threshold, window, use_bounds, flag)
         # pass 2: every local cell, one read and one write of the matrix
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -188,6 +198,64 @@ class Engine:
             e1.record()
             self.timing.append(("cell_pipeline_pass2", e0, e1))
         return Y, flag
+
+    def smooth_hmm_host(self, hX, hY, hS, dX, Y, states, chr_start, chr_len, ref_groups_local, ref_sizes, max_chunks, Pi, delta,
+                        mean, sd, slab_cells=1024, apply_log=True, threshold=3.0, window=101, use_bounds=True):
+        """Smooth block + per-cell HMM from / to pinned HOST tensors hX -> hY (float64) and hS (uint8), all (C, G), with the
+        copies pipelined against the kernels over slabs of cells: the multi-rank counterpart of the C host pipeline
+        (icnv_smooth_hmm_u8_f64, which knows no collectives).  The reference columns must be the leading local columns (the
+        shard planner's layout); they go up first, the reference bounds are formed (two all-gathers across ranks), then
+        H2D of slab i+1, pass 2 + Viterbi of slab i and D2H of slab i-1 overlap on three streams.  dX / Y / states are
+        (C, G) device work buffers.  Bit-identical to smooth_block + viterbi on the uploaded matrix."""
+        C, G = hX.shape
+        refs = [np.asarray(g, dtype=np.int32) for g in ref_groups_local]
+        n_ref = int(sum(len(g) for g in refs))
+        if n_ref and not np.array_equal(np.concatenate(refs), np.arange(n_ref)):
+            raise ValueError("smooth_hmm_host: the reference cells must be the leading local columns")
+        on_gpu = dX.is_cuda
+        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+        if n_ref:
+            dX[:n_ref].copy_(hX[:n_ref], non_blocking=True)
+        b1, b2, _, _, _ = self._reference_bounds(dX, chr_start, chr_len, refs, ref_sizes, max_chunks, apply_log, threshold, window,
+                                                 use_bounds, flag)
+        if on_gpu:
+            if getattr(self, "_copy_streams", None) is None:
+                self._copy_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            s_in, s_out = self._copy_streams
+            main = torch.cuda.current_stream()
+            s_in.wait_stream(main)     # the work buffers may still be in use by what was queued before this call
+            s_out.wait_stream(main)
+        flags = [flag]
+        for c0 in range(0, C, slab_cells):
+            c1 = min(C, c0 + slab_cells)
+            u0 = max(c0, n_ref)        # the reference columns are already on the device
+            if on_gpu:
+                ev_in = torch.cuda.Event()
+                with torch.cuda.stream(s_in):
+                    if u0 < c1:
+                        dX[u0:c1].copy_(hX[u0:c1], non_blocking=True)
+                    ev_in.record(s_in)
+                main.wait_event(ev_in)
+            elif u0 < c1:
+                dX[u0:c1].copy_(hX[u0:c1])
+            self.cell_pipeline(dX[c0:c1], None, Y[c0:c1], chr_start, chr_len, apply_log, b1, threshold, window, 1, b2, True,
+                               use_bounds, flag)
+            _, f2 = self.viterbi(Y[c0:c1], chr_start, chr_len, Pi, delta, mean, sd, out=states[c0:c1])
+            flags.append(f2)
+            if on_gpu:
+                ev_c = torch.cuda.Event()
+                ev_c.record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_c)
+                    hY[c0:c1].copy_(Y[c0:c1], non_blocking=True)
+                    hS[c0:c1].copy_(states[c0:c1], non_blocking=True)
+            else:
+                hY[c0:c1].copy_(Y[c0:c1])
+                hS[c0:c1].copy_(states[c0:c1])
+        if on_gpu:
+            main.wait_stream(s_out)
+            torch.cuda.synchronize()
+        return flags
 
     def viterbi(self, X, chr_start, chr_len, Pi, delta, mean, sd, out=None, want_margins=False):
         """Per-cell i6 / i3 Viterbi on device data -> uint8 states (C, G)."""

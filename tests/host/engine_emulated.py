@@ -71,6 +71,11 @@ def single():
     S, f2 = eng.viterbi(Y, CS, LENS, Pi, delta, I6_MEAN, I6_SD)
     want_s = orc.viterbi_matrix(np.asfortranarray(Y.numpy().T), CS, LENS, Pi, delta, I6_MEAN, I6_SD)
     assert np.array_equal(S.numpy().T, want_s) and int(f2.item()) == 0
+    # the slab-pipelined host path (sequential on the CPU) is the same computation
+    hY, hS = torch.empty_like(X), torch.empty((C, G), dtype=torch.uint8)
+    fl = eng.smooth_hmm_host(X.clone(), hY, hS, torch.empty_like(X), torch.empty_like(X), torch.empty((C, G), dtype=torch.uint8), CS,
+                             LENS, refs, None, None, Pi, delta, I6_MEAN, I6_SD, slab_cells=16)
+    assert torch.equal(hY, Y) and torch.equal(hS, S) and all(int(f.item()) == 0 for f in fl)
     mu, sg = eng.mean_sd(Y, refs)
     mu_o, sg_o = orc.mean_sd_over_cells(np.asfortranarray(Y.numpy().T), np.concatenate(refs))
     assert abs(mu - mu_o) < 1e-14 and abs(sg - sg_o) < 1e-13
@@ -111,6 +116,11 @@ def rank_main(rank, world, port):
     Y, f = eng.smooth_block(X, CS, LENS, plan.local_ref_groups(), plan.ref_sizes, plan.max_chunks)
     Pi, delta = orc.hmm_params(6)
     S, f2 = eng.viterbi(Y, CS, LENS, Pi, delta, I6_MEAN, I6_SD)
+    Cl = X.shape[0]
+    hY, hS = torch.empty_like(X), torch.empty((Cl, G), dtype=torch.uint8)
+    eng.smooth_hmm_host(X.clone(), hY, hS, torch.empty_like(X), torch.empty_like(X), torch.empty((Cl, G), dtype=torch.uint8), CS, LENS,
+                        plan.local_ref_groups(), plan.ref_sizes, plan.max_chunks, Pi, delta, I6_MEAN, I6_SD, slab_cells=24)
+    assert torch.equal(hY, Y) and torch.equal(hS, S), "slab-pipelined host path differs from smooth_block + viterbi"
     mu_d, sg_d = eng.mean_sd(Y, plan.local_ref_groups())
     obs_global = [np.arange(int(0.3 * C_total), int(0.6 * C_total)), np.arange(int(0.6 * C_total), C_total)]
     pos_of = {int(c): i for i, c in enumerate(plan.local_cells)}

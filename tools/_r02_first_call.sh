@@ -32,3 +32,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"sta
 # 7. memory safety of the changed kernels on small cases
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "padded_q or slow_paths or golden or viterbi_cells" > gpurun_out/r02_memcheck.log 2>&1; tail -5 gpurun_out/r02_memcheck.log
 ls -la gpurun_out | tail -20
+# 8. (needs --gpus 2; run separately) N = 2: default and slab-pipelined e2e
+#    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/r02_bench_n2.json
+#    ICNV_BENCH_E2E_PIPELINE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/r02_bench_n2_pipelined.json
