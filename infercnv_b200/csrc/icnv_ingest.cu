@@ -31,10 +31,21 @@ __global__ void __launch_bounds__(256) gene_stats_partial_kernel(const double *_
         const int64_t c0 = q * IG_CHUNK, c1 = min(C, c0 + IG_CHUNK);
         double s = 0.0;
         uint32_t n = 0;
-        for (int64_t c = c0; c < c1; ++c) {
-            const double v = X[g + ldx * c];
-            s += v;
-            n += (v > 0.0) ? 1u : 0u;      // NaN > 0 is false: x > 0 & !is.na(x)
+        // eight independent loads in flight per thread (the counted loop issued load, add, load, add: 0.48 of the HBM
+        // roofline measured).  The loads are unconditional - past the chunk's end they re-read its last cell - so that they
+        // can be issued back to back; only the accumulation is predicated, and the sum keeps its cell order.
+        const int nvalid = (int)(c1 - c0);
+        const double *__restrict__ col0 = X + g + ldx * c0;
+        for (int j0 = 0; j0 < IG_CHUNK; j0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = col0[ldx * (int64_t)min(j0 + j, nvalid - 1)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j0 + j < nvalid) {
+                    s += v[j];
+                    n += (v[j] > 0.0) ? 1u : 0u;      // NaN > 0 is false: x > 0 & !is.na(x)
+                }
         }
         psum[g + G * q] = s;
         ppos[g + G * q] = n;
