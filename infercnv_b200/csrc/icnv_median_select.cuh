@@ -9,8 +9,9 @@
 //   1. mean / sd of the window place a first bracket (mean - sd/2, mean + sd/2];
 //   2. one pass over the taps counts the values at or below the bracket and lists the taps inside it; if the
 //      target rank fell outside (skewed or bimodal window) the pass is repeated on the side that holds it;
-//   3. the bracket is narrowed by counting over the LIST only: two value pivots placed by interpolation while
-//      that shrinks it, otherwise one three-way round (less / equal / greater) around an element of the list,
+//   3. the bracket is narrowed by counting over the LIST only: four value pivots placed by interpolation while
+//      that shrinks it (one round is then enough for all but ~1 % of the windows - a warp runs as many rounds as its
+//      slowest lane), otherwise one three-way round (less / equal / greater) around an element of the list,
 //      which always makes progress and finishes tie-dominated windows (de-noised matrices, state matrices) in
 //      one round;
 //   4. at most 16 candidates are left: a sorting network orders them and the rank is read off.
@@ -195,38 +196,44 @@ ICNV_HD double window_median(const double *halo, const double *halo0, int HR, in
             }
             stagnant = false;
         } else {
-            // k sits at fraction f of the bracket's m values; pivots +-6 ranks around it: hit or miss, what is left
-            // fits the final network for the usual m of 25..40
+            // k sits at fraction f of the bracket's m values.  Four value pivots placed by interpolation at about -12, -4,
+            // +4 and +12 ranks around it cut the bracket into pieces of ~8 ranks, so that for the usual m of 25..40 whichever
+            // piece holds the target fits the final network: one round per window, and - what matters on the GPU, where a warp
+            // runs as many rounds as its slowest lane - practically never a second one (two pivots at +-6 left 8..28 % of the
+            // windows with more than MF_CAND candidates).  The counts are exact whatever the placement.
             const double f = ((double)(k - Flo) + 0.5) / (double)m;
-            const double wdt = fmax(6.0 / (double)m, 0.08);
-            const double p1 = lo + span * (f - wdt), p2 = lo + span * (f + wdt);
-            int c1 = 0, c2 = 0;
+            const double w1 = fmax(4.0 / (double)m, 0.05), w2 = fmax(12.0 / (double)m, 0.15);
+            const double pv0 = lo + span * (f - w2), pv1 = lo + span * (f - w1), pv2 = lo + span * (f + w1),
+                         pv3 = lo + span * (f + w2);
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             for (int t = 0; t < cnt; ++t) {
                 const double v = w[list[t * ls]];
-                c1 += (v <= p1) ? 1 : 0;
-                c2 += (v <= p2) ? 1 : 0;
+                c0 += (v <= pv0) ? 1 : 0;
+                c1 += (v <= pv1) ? 1 : 0;
+                c2 += (v <= pv2) ? 1 : 0;
+                c3 += (v <= pv3) ? 1 : 0;
             }
-            const int C1 = L0 + c1, C2 = L0 + c2;
-            if (k < C1) {
-                if (p1 > lo && p1 < hi) {
-                    hi = p1;
-                    Fhi = C1;
-                }
-            } else {
-                if (p1 > lo && p1 < hi) {
-                    lo = p1;
-                    Flo = C1;
-                }
-                if (k < C2) {
-                    if (p2 > lo && p2 < hi) {
-                        hi = p2;
-                        Fhi = C2;
-                    }
-                } else if (p2 > lo && p2 < hi) {
-                    lo = p2;
-                    Flo = C2;
-                }
+            // ascending pivots: the last one with #(v <= p) <= k becomes the lower end, the first one above it the upper end
+            // (pivots outside the open bracket are ignored; the invariant #(v <= lo) = Flo <= k < Fhi = #(v <= hi) is kept)
+            const double lo_in = lo, hi_in = hi;
+            bool have_hi = false;
+#define ICNV_MF_PIVOT(PV, CV)                                  \
+            if ((PV) > lo_in && (PV) < hi_in && !have_hi) {    \
+                const int Cq = L0 + (CV);                      \
+                if (k >= Cq) {                                 \
+                    lo = (PV);                                 \
+                    Flo = Cq;                                  \
+                } else {                                       \
+                    hi = (PV);                                 \
+                    Fhi = Cq;                                  \
+                    have_hi = true;                            \
+                }                                              \
             }
+            ICNV_MF_PIVOT(pv0, c0)
+            ICNV_MF_PIVOT(pv1, c1)
+            ICNV_MF_PIVOT(pv2, c2)
+            ICNV_MF_PIVOT(pv3, c3)
+#undef ICNV_MF_PIVOT
             stagnant = (Fhi - Flo == m);
         }
     }
