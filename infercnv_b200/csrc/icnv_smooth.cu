@@ -1035,12 +1035,13 @@ __device__ __forceinline__ double block_median_smem(const double *__restrict__ v
 constexpr int HIST_NB = 2048;
 
 template <int NT>
-__device__ __forceinline__ bool block_median_hist(const double *__restrict__ vals, int n, double inv_n, double S1, double S2, int *hist,
+__device__ __forceinline__ bool block_median_hist(const double *__restrict__ vals, int n, double inv_n, double S1, double S2, int *hist, int dump_off,
                                                   int *hres, int *wcnt, double *cand, int *cand_n, double &result) {
     constexpr int NW = NT / 32;
     constexpr int BPT = HIST_NB / NT;   // bins scanned per thread
     static_assert(HIST_NB % NT == 0 && BPT >= 1 && BPT <= 8, "HIST_NB must be a small multiple of NT");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned dump = (unsigned)(dump_off + lane);   // index (relative to hist) of this lane's spare word
     const int kA = (n - 1) >> 1, kB = n >> 1;
     // Bin geometry in cheap arithmetic: every thread evaluates the same instruction sequence, so all of them and both
     // passes bin with identical scale / C, and the median itself never depends on them (the candidates are ranked exactly) -
@@ -1070,10 +1071,10 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
         const double tx = fma(v.x, scale, C), ty = fma(v.y, scale, C);
         const int hx = __double2hiint(tx), hy = __double2hiint(ty);
         const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
-        // values outside mean +- sd count into a spare word behind the bins (hres[7], never read): one unconditional
-        // atomic per value instead of a branch around it
-        atomicAdd(&hist[(hx == HI0 && lx < (unsigned)HIST_NB) ? lx : (unsigned)(HIST_NB + 7)], 1);
-        atomicAdd(&hist[(hy == HI0 && ly < (unsigned)HIST_NB) ? ly : (unsigned)(HIST_NB + 7)], 1);
+        // values outside mean +- sd count into this lane's own spare word behind the tables (never read; per lane, so that
+        // a third of the warp does not pile onto one address): one unconditional atomic per value instead of a branch around it
+        atomicAdd(&hist[(hx == HI0 && lx < (unsigned)HIST_NB) ? lx : dump], 1);
+        atomicAdd(&hist[(hy == HI0 && ly < (unsigned)HIST_NB) ? ly : dump], 1);
         cb += (hx < HI0) ? 1 : 0;
         cb += (hy < HI0) ? 1 : 0;
     }
@@ -1187,6 +1188,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
     int *cand_n = wcnt + 2 * NW;
     int *chr_cs = cand_n + 2;                                // PADQ: [K] chromosome start, [K] chromosome length
     int *chr_n = chr_cs + p.K;
+    int *hdump = chr_n + p.K;                                // [32] per-lane spare words of the histogram pass
     double *const sm = reinterpret_cast<double *>(smem_raw); // everything below is indexed relative to this
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1502,7 +1504,7 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
         double centre = 0.0;
         if (p.center == 1) {
             if (tid == 0) atomicAdd(&g_stats[1], 1ull);
-            if (block_median_hist<NT>(sv, G, inv_G, S1, S2, hist, hres, wcnt, cand, cand_n, centre)) {
+            if (block_median_hist<NT>(sv, G, inv_G, S1, S2, hist, (int)(hdump - hist), hres, wcnt, cand, cand_n, centre)) {
                 if (tid == 0) atomicAdd(&g_stats[10], 1ull);
             } else {   // tiny or degenerate columns, > CAND_MAX ties in the middle bin: bracketing selection
                 double s1 = 0.0, s2 = 0.0;
@@ -1703,7 +1705,7 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
             const size_t cols = pq ? (size_t)q_elems + (size_t)s_elems + (size_t)ipad
                                    : 2 * (size_t)s_elems + (size_t)K * (size_t)h;
             return 128 * 24 + sizeof(double) * (cols + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 + CAND_MAX + 2 + 2 + 2) +
-                   red3 + sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2 + 2 * (size_t)K + 2) + 64;
+                   red3 + sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2 + 2 * (size_t)K + 2 + 32) + 64;
         };
         if (padq && smem_for(true) > (size_t)c.smem_optin) padq = 0;
         const size_t smem3 = smem_for(padq != 0);
