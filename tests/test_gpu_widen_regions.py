@@ -198,3 +198,35 @@ def test_device_resident_states_from_the_viterbi_kernel_to_regions():
         _same_regions(eng.cnv_regions(cons, cs, cl, gs, ge), orr.cnv_regions(want.T, cs, cl, gs, ge))
         cells = [5, 0, 129, 64]
         _same_regions(eng.cnv_regions(dS, cs, cl, gs, ge, cols=cells), orr.cnv_regions(S[:, cells], cs, cl, gs, ge))
+
+
+@pytest.mark.skipif(os.environ.get("ICNV_TEST_PIPELINED_HOST") != "1",
+                    reason="Engine.smooth_hmm_host was written after the last GPU session: opt-in (ICNV_TEST_PIPELINED_HOST=1) "
+                           "until its three-stream path has run on a GPU once")
+def test_engine_slab_pipelined_host_path_is_bit_identical():
+    """Engine.smooth_hmm_host (reference columns first, then H2D / pass 2 + Viterbi / D2H overlapped over cell slabs on three
+    streams, pinned host tensors) against smooth_block + viterbi on the uploaded matrix: identical bits."""
+    import torch
+    from infercnv_b200.device import Engine
+    from oracle import oracle as orc
+    eng = Engine(0)
+    cs, cl = _layout([700, 2, 1, 333, 1200, 90])
+    G, C = int(cl.sum()), 700
+    refs = [np.arange(0, 40), np.arange(40, 64)]
+    X = eng.synth(G, cs, cl, np.arange(C), C, 20260923)
+    Y, f1 = eng.smooth_block(X, cs, cl, refs)
+    mean = np.array([0.41234766, 0.84075773, 1.01693983, 1.12238786, 1.23842619, 1.44298781])
+    sd = np.array([0.028893, 0.164549, 0.105553, 0.190574, 0.244093, 0.290072])
+    Pi, delta = orc.hmm_params(6)
+    S, f2 = eng.viterbi(Y, cs, cl, Pi, delta, mean, sd)
+    hX = torch.empty((C, G), dtype=torch.float64, pin_memory=True)
+    hX.copy_(X)
+    hY = torch.empty((C, G), dtype=torch.float64, pin_memory=True)
+    hS = torch.empty((C, G), dtype=torch.uint8, pin_memory=True)
+    for slab in (128, 333):
+        hY.zero_()
+        hS.zero_()
+        flags = eng.smooth_hmm_host(hX, hY, hS, torch.empty_like(X), torch.empty_like(X), torch.empty_like(S), cs, cl, refs, None,
+                                    None, Pi, delta, mean, sd, slab_cells=slab)
+        assert all(int(f.item()) == 0 for f in flags) and int(f1.item()) == 0 and int(f2.item()) == 0
+        assert torch.equal(hY, Y.cpu()) and torch.equal(hS, S.cpu())

@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 B="python bench.py --no-e2e --no-cpu-baseline"
 # 1. parity: the whole GPU suite (new since the last full GPU run: padded-Q identity, grouped element-wise slow paths)
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -5 gpurun_out/r02_pytest_gpu.log
+ICNV_TEST_PIPELINED_HOST=1 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -5 gpurun_out/r02_pytest_gpu.log
 # 2. the bench line of the default path (never under a profiler)
 timeout 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; tail -c 600 gpurun_out/r02_bench.json
 # 3. A/B of what changed since profiles/r01_bench.json (device-resident value only; every line is one JSON record)
