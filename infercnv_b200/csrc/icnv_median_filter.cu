@@ -35,6 +35,7 @@ struct MfParams {
     const MfTile *cell_tiles; // gridDim.x entries
     int r;
     int *err_flag;
+    int use_net;              // radius 4 only: full windows by the key network (window_median_net81), 0 = counting selection
 };
 
 // One CTA = a tile of TI genes x TJ list positions (TI*TJ threads, one output each).  The tile's halo
@@ -118,13 +119,16 @@ __global__ void __launch_bounds__(MF_NT) median_filter_kernel(const MfParams p) 
 // are consecutive doubles (no bank conflicts) and the per-thread tap lists interleave at 2-byte granularity.
 constexpr int MS_TI = 32, MS_TJ = 8, MS_NT = MS_TI * MS_TJ;
 
-template <int R, typename ListT = unsigned short>
-__global__ void __launch_bounds__(MS_NT) median_filter_select_kernel(const MfParams p) {
+// NET (radius 4 only): full windows go through the key network (window_median_net81, ~160 registers per thread); a separate
+// instance, so that the counting-selection kernel keeps its 64 registers and four CTAs per SM.
+template <int R, typename ListT = unsigned short, bool NET = false>
+__global__ void __launch_bounds__(MS_NT, NET ? 2 : 0) median_filter_select_kernel(const MfParams p) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
     constexpr int D = 2 * R + 1, HR = MS_TI + 2 * R, HC = MS_TJ + 2 * R;
     double *halo = reinterpret_cast<double *>(mf_smem);          // +inf outside the block: never counted
     double *halo0 = halo + HR * HC;                              // 0 outside the block: for the window moments
     ListT *list = reinterpret_cast<ListT *>(halo0 + HR * HC);   // [D*D][MS_NT] tap offsets
+    float *kf = reinterpret_cast<float *>(list + (size_t)D * D * MS_NT);   // use_net: single-precision keys of the halo
     const MfTile gt = p.gene_tiles[blockIdx.y];
     const MfTile ct = p.cell_tiles[blockIdx.x];
     const int hi0 = gt.start - R, hj0 = ct.start - R;
@@ -140,15 +144,24 @@ __global__ void __launch_bounds__(MS_NT) median_filter_select_kernel(const MfPar
         }
         halo[e] = v;
         halo0[e] = v0;
+        if (NET) kf[e] = (float)v;
     }
     __syncthreads();
     const int ti = threadIdx.x % MS_TI, tj = threadIdx.x / MS_TI;
+    // a tile whose every window is a full (2R+1)^2 one (no tap outside the chromosome / index-list block): CTA-uniform
+    const bool full_tile = gt.len == MS_TI && ct.len == MS_TJ && gt.start - R >= gt.lo && gt.start + MS_TI + R <= gt.hi &&
+                           ct.start - R >= ct.lo && ct.start + MS_TJ + R <= ct.hi;
     if (ti < gt.len && tj < ct.len) {
         const int i = gt.start + ti, j = ct.start + tj;
-        const int xa = max(gt.lo, i - R), xb = min(gt.hi - 1, i + R);
-        const int ya = max(ct.lo, j - R), yb = min(ct.hi - 1, j + R);
-        const int n = (xb - xa + 1) * (yb - ya + 1);
-        const double med = window_median<R, ListT>(halo, halo0, HR, tj * HR + ti, list + threadIdx.x, MS_NT, n);
+        double med;
+        if (NET && full_tile) {
+            med = window_median_net81<ListT>(halo, halo0, kf, HR, tj * HR + ti, list + threadIdx.x, MS_NT);
+        } else {
+            const int xa = max(gt.lo, i - R), xb = min(gt.hi - 1, i + R);
+            const int ya = max(ct.lo, j - R), yb = min(ct.hi - 1, j + R);
+            const int n = (xb - xa + 1) * (yb - ya + 1);
+            med = window_median<R, ListT>(halo, halo0, HR, tj * HR + ti, list + threadIdx.x, MS_NT, n);
+        }
         p.Y[i + p.G * (int64_t)p.cells[j]] = med;
     }
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
@@ -177,12 +190,17 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     const int r = (window_size + 1) / 2;
     const int W = (2 * r + 1) * (2 * r + 1);
     bool select_kernel = (r >= 2 && r <= 5);
-    if (const char *e = getenv("ICNV_MF_KERNEL")) select_kernel = select_kernel && (atoi(e) != 0);   // 0: generic kernel (A/B runs)
+    int use_net = 0;
+    if (const char *e = getenv("ICNV_MF_KERNEL")) {   // 0: generic kernel; 2: key network for full 9 x 9 windows (A/B runs)
+        select_kernel = select_kernel && (atoi(e) != 0);
+        use_net = (atoi(e) == 2 && r == 4) ? 1 : 0;
+    }
     const int TI = select_kernel ? MS_TI : MF_TI, TJ = select_kernel ? MS_TJ : MF_TJ, NT = TI * TJ;
     bool list32 = false;
     if (const char *e = getenv("ICNV_MF_LIST32")) list32 = select_kernel && atoi(e) != 0;   // diagnostic
     const size_t smem = sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
-                        (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT;
+                        (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT +
+                        (use_net ? sizeof(float) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) : 0);
     if (smem > (size_t)c.smem_optin || (TI + 2 * r) * (TJ + 2 * r) > 65535)
         return set_error(ICNV_E_UNSUPPORTED, "window_size %d needs %zu B of shared memory per CTA", window_size, smem);
     cudaStream_t st = pick_stream(stream);
@@ -212,7 +230,7 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     ICNV_CUDA(cudaMemcpyAsync(d_cells, grp_idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     ICNV_CUDA(cudaStreamSynchronize(st));  // tile tables are stack-lifetime host buffers
-    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag};
+    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net};
     dim3 grid((unsigned)ct.size(), (unsigned)gt.size());
     auto launch = [&](auto kern) -> int {
         ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -220,11 +238,13 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
         return ICNV_OK;
     };
     int lrc;
+    if (list32) use_net = 0;
     if (!select_kernel) lrc = launch(median_filter_kernel);
     else if (list32 && r == 5) lrc = launch(median_filter_select_kernel<5, unsigned>);
     else if (list32 && r == 4) lrc = launch(median_filter_select_kernel<4, unsigned>);
     else if (r == 2) lrc = launch(median_filter_select_kernel<2>);
     else if (r == 3) lrc = launch(median_filter_select_kernel<3>);
+    else if (r == 4 && use_net) lrc = launch(median_filter_select_kernel<4, unsigned short, true>);
     else if (r == 4) lrc = launch(median_filter_select_kernel<4>);
     else lrc = launch(median_filter_select_kernel<5>);
     if (lrc) return lrc;

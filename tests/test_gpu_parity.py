@@ -478,6 +478,35 @@ def test_median_filter_vs_oracle(api, window_size):
     np.testing.assert_array_equal(got[:, 31], X[:, 31])
 
 
+def test_median_filter_key_network_variant_is_exact(api, monkeypatch):
+    """ICNV_MF_KERNEL=2: tiles whose windows are all full 9 x 9 ones (window_size 7) take the median from a comparator
+    network on single-precision keys (window_median_net81) and find its double in a second pass; edge tiles and ties the
+    keys cannot resolve go through the counting selection.  Same values as the default kernel and the oracle on smooth
+    values, a de-noised-like matrix (runs of one constant), state-like small integers and values closer together than single
+    precision resolves."""
+    rng = np.random.default_rng(9)
+    lens = [150, 41, 96, 7]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(np.sum(lens)), 90
+    groups = [np.arange(0, 41), rng.permutation(np.arange(41, 70)), np.arange(70, 77), np.arange(77, 90)]
+    base = 1.0 + 0.1 * rng.normal(size=(G, C))
+    cases = {
+        "smooth": base,
+        "denoised": np.where(np.abs(base - 1.0) < 0.12, 1.000123, base),
+        "states": rng.integers(1, 7, size=(G, C)).astype(float),
+        "sub-float": 1.0 + 1e-10 * rng.integers(0, 50, size=(G, C)),
+    }
+    for name, X in cases.items():
+        X = np.asfortranarray(X)
+        monkeypatch.setenv("ICNV_MF_KERNEL", "2")
+        got = api.median_filter(X, cs, lens, groups, 7)
+        monkeypatch.delenv("ICNV_MF_KERNEL")
+        ref = api.median_filter(X, cs, lens, groups, 7)
+        want = orc.median_filter(X, cs, lens, groups, 7, nthreads=orc.max_threads())
+        assert np.array_equal(got, ref), name
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-15, err_msg=name)
+
+
 def test_median_filter_example_object_subclusters(api, example_object):
     ex = example_object
     cs, cl = orc.chr_ranges(ex["chr_codes"])

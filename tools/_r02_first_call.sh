@@ -35,3 +35,5 @@ ls -la gpurun_out | tail -20
 # 8. (needs --gpus 2; run separately) N = 2: default and slab-pipelined e2e
 #    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/r02_bench_n2.json
 #    ICNV_BENCH_E2E_PIPELINE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --no-cpu-baseline > gpurun_out/r02_bench_n2_pipelined.json
+# 9. median filter: counting selection (default, now with four pivots per round) against the key network for full windows
+ICNV_MF_KERNEL=2 timeout 300 python tools/bench_extra.py > gpurun_out/r02_secondary_kernels_mfnet.json 2>/dev/null; python -c "import json; a=json.load(open('gpurun_out/r02_secondary_kernels.json')); b=json.load(open('gpurun_out/r02_secondary_kernels_mfnet.json')); print('median filter ms: counting', a['median_filter_w7']['ms'], ' key network', b['median_filter_w7']['ms'])"
