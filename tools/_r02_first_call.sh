@@ -13,6 +13,8 @@ timeout 400 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.
 ICNV_CELL_PADQ=0 timeout 300 $B > gpurun_out/r02_ab_padq0.json 2>/dev/null
 #    a2. counted scan loops instead of the fully unrolled slices
 ICNV_CELL_LFIX=0 timeout 300 $B > gpurun_out/r02_ab_lfix0.json 2>/dev/null
+#    a3. 512 threads per CTA (21 genes per thread, ~105 registers) instead of 1024 x 11
+ICNV_CELL_NT=512 timeout 300 $B > gpurun_out/r02_ab_nt512.json 2>/dev/null
 #    b. reference-column reuse in pass 2 off (default on since the end of round 1)
 ICNV_REF_REUSE=0 timeout 300 $B > gpurun_out/r02_ab_refreuse0.json 2>/dev/null
 #    c. fast Viterbi occupancy variants (default 16 warps per CTA at 128 registers)
