@@ -18,8 +18,10 @@
  *   chromosomes  K contiguous row ranges [chr_start[k], chr_start[k]+chr_len[k]) - the reference
  *            pre-sorts rows by chr,start,stop (R/inferCNV.R:407-413).
  *   ownership  caller owns every buffer it passes; inputs are never modified; outputs may alias
- *            inputs only where stated.  The library owns all device memory, streams and pinned
- *            staging and frees them in icnv_shutdown().
+ *            inputs only where stated.  The library owns all device memory, streams and a pinned
+ *            staging ring (two slabs in, two out per GPU): caller memory that is not page-locked -
+ *            an R matrix, a NumPy array - is moved through that ring by the library's copy threads,
+ *            page-locked caller memory is used directly.  Everything is freed in icnv_shutdown().
  *   errors   every entry returns 0 or a negative icnv_status and records a per-thread message
  *            readable through icnv_last_error().  Nothing throws across the ABI.  There is no CPU
  *            fallback: without a usable CUDA device every compute entry returns ICNV_E_NO_DEVICE.
@@ -60,8 +62,24 @@ typedef enum icnv_status {
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 
 /* Select `device` (cudaSetDevice), create the library's stream and scratch pools.  Idempotent for
- * the same device; re-initialises when called with another one.  device < 0 -> device 0. */
+ * the same device; re-initialises when called with another one.  device < 0 -> keep the current
+ * set-up, or device 0 when there is none.  Tuning switches (ICNV_* environment variables, DESIGN.md
+ * section 8) are read here, once, and the ones that are set are reported on stderr. */
 ICNV_API int icnv_init(int device);
+/* Multi-GPU for a single host process - the form the R shim uses (infercnv::run() is one R process;
+ * its num_threads, R/inferCNV_ops.R:388, never reaches this path): initialise n_devices GPUs
+ * (device_ids == NULL: devices 0 .. n-1; n_devices <= 0: every device present).  Afterwards the
+ * host-pointer entry points that stream cells (icnv_smooth_block_f64, icnv_smooth_hmm_*_f64, the
+ * per-cell icnv_viterbi_*_f64) cut the cells into one contiguous range per GPU, driven by one host
+ * thread each; every GPU reduces ALL reference cells itself in list order (they are <= ~10 % of the
+ * matrix and cross PCIe once per GPU), so no inter-GPU exchange is needed and the result is bit-identical
+ * for any device count ("broadcast the ref-cell columns").  All other entry points use
+ * the first device.  icnv_dev_* calls address the device of the calling thread's context (the first). */
+ICNV_API int icnv_init_devices(int n_devices, const int *device_ids);
+ICNV_API int icnv_devices_in_use(void);        /* 0 before initialisation */
+/* Host threads that move the caller's (pageable) matrix into / out of the pinned staging ring; they are
+ * split over the GPUs in use.  0 = default: half the hardware threads, at most 16. */
+ICNV_API int icnv_set_host_threads(int n);
 ICNV_API void icnv_shutdown(void);
 ICNV_API int icnv_device_count(void);          /* >= 0, or a negative icnv_status */
 ICNV_API const char *icnv_last_error(void);    /* never NULL */
@@ -304,6 +322,13 @@ ICNV_API int icnv_cnv_regions_fetch(int64_t n_regions, int32_t *seq, int32_t *ch
 ICNV_API int icnv_dev_group_partial_sums_f64(const double *X, int64_t G, int64_t ldx, const int32_t *cells,
                                              int64_t n_cells, int chunk, int apply_log, double *partial,
                                              void *stream);
+/* Reference bounds (min / max / mean over the groups of the per-gene group means) from chunk sums laid out
+ * [world][tot_rows][G] - what an all-gather of every rank's icnv_dev_group_partial_sums_f64 rows gives; group k owns rows
+ * row_off[k] .. row_off[k+1] of each rank's block, counts[k] is its global size.  Replaces .get_normal_gene_mean_bounds'
+ * per-group mean() (R/inferCNV_ops.R:1708-1735) + the min / max of .subtract_expr (:1742-1786) in one launch. */
+ICNV_API int icnv_dev_bounds_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
+                                               const int32_t *row_off, const int64_t *counts, double *lo, double *hi,
+                                               double *mid, void *stream);
 /* means[g] = (sum_q partial[g + G*q], q ascending) / count */
 ICNV_API int icnv_dev_combine_partials_f64(const double *partial, int64_t G, int64_t n_chunks, int64_t count,
                                            double *means, void *stream);

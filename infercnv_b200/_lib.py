@@ -19,6 +19,9 @@ c_int = ct.c_int
 _P = ct.c_void_p
 SIGNATURES = {
     "icnv_init": (c_int, [c_int]),
+    "icnv_init_devices": (c_int, [c_int, _P]),
+    "icnv_devices_in_use": (c_int, []),
+    "icnv_set_host_threads": (c_int, [c_int]),
     "icnv_shutdown": (None, []),
     "icnv_device_count": (c_int, []),
     "icnv_last_error": (ct.c_char_p, []),
@@ -47,6 +50,7 @@ SIGNATURES = {
     "icnv_mean_sd_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P, _P]),
     "icnv_dev_group_partial_sums_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, c_int, c_int, _P, _P]),
     "icnv_dev_combine_partials_f64": (c_int, [_P, c_i64, c_i64, c_i64, _P, _P]),
+    "icnv_dev_bounds_from_partials_f64": (c_int, [_P, c_i64, c_int, c_i64, c_int, _P, _P, _P, _P, _P, _P]),
     "icnv_dev_bounds_from_means_f64": (c_int, [_P, c_i64, c_int, _P, _P, _P, _P]),
     "icnv_dev_cell_pipeline_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P, c_i64, _P, _P, c_int, c_int, _P, _P, _P,
                                            ct.c_double, c_int, c_int, _P, _P, _P, c_int, _P, _P]),

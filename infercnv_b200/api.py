@@ -50,8 +50,30 @@ def init(device: int = 0) -> None:
     _lib.check(_lib.load().icnv_init(int(device)))
 
 
+def init_devices(device_ids=None) -> int:
+    """Single-process multi-GPU (what the R shim does): the host-pointer calls that stream cells shard them over these
+    devices.  None = every device present.  Returns the number of devices in use."""
+    lib = _lib.load()
+    if device_ids is None:
+        _lib.check(lib.icnv_init_devices(0, None))
+    else:
+        ids = np.ascontiguousarray(device_ids, dtype=np.int32)
+        _lib.check(lib.icnv_init_devices(len(ids), ids.ctypes.data))
+    return int(lib.icnv_devices_in_use())
+
+
 def shutdown() -> None:
     _lib.load().icnv_shutdown()
+
+
+def reinit(device: int = 0) -> None:
+    """Free everything and initialise again - the ICNV_* tuning switches are read from the environment at icnv_init only."""
+    shutdown()
+    init(device)
+
+
+def set_host_threads(n: int) -> None:
+    _lib.check(_lib.load().icnv_set_host_threads(int(n)))
 
 
 def device_count() -> int:

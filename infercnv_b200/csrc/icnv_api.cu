@@ -4,7 +4,12 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <numeric>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "icnv_common.cuh"
@@ -57,9 +62,131 @@ namespace icnv {
 
 static thread_local char g_err[512] = "";
 
-Ctx &ctx() {
-    static Ctx c;
-    return c;
+// One context per device the library was initialised on.  A host thread works on one of them at a time (slot 0 unless
+// the multi-device host pipeline put the thread on another one): every helper below - scratch(), pick_stream(), the
+// launch counter - goes through ctx().
+static Ctx g_ctx[ICNV_MAX_DEVICES];
+static thread_local int tl_slot = 0;
+static int g_slots = 0;
+
+Ctx &ctx() { return g_ctx[tl_slot]; }
+Ctx &ctx_of(int slot) { return g_ctx[slot]; }
+int current_slot() { return tl_slot; }
+void set_current_slot(int s) { tl_slot = s; }
+int device_slots() { return g_slots; }
+
+// ---- host copy pool: pageable caller memory <-> the pinned staging ring --------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread at ~10 GB/s and blocks it, which
+// serialises the three-stream slab pipeline.  The library therefore owns pinned slabs and a few copy threads that move
+// the caller's slab into / out of them at memory bandwidth, so PCIe sees pinned transfers only.
+class CopyPool {
+public:
+    explicit CopyPool(int n) : n_(n) {
+        for (int t = 0; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    // copies up to two (dst, src, bytes) jobs, cut into equal byte ranges over the threads; returns when both are done
+    void copy2(void *d0, const void *s0, size_t n0, void *d1, const void *s1, size_t n1) {
+        if (n0 + n1 == 0) return;
+        std::unique_lock<std::mutex> lk(mu_);
+        job_[0] = {static_cast<char *>(d0), static_cast<const char *>(s0), n0};
+        job_[1] = {static_cast<char *>(d1), static_cast<const char *>(s1), n1};
+        pending_ = n_;
+        ++gen_;
+        cv_.notify_all();
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    struct Job {
+        char *d;
+        const char *s;
+        size_t n;
+    };
+    void loop(int t) {
+        unsigned long long seen = 0;
+        for (;;) {
+            Job j[2];
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                j[0] = job_[0];
+                j[1] = job_[1];
+            }
+            const size_t total = j[0].n + j[1].n;
+            const size_t per = ((total + (size_t)n_ - 1) / (size_t)n_ + 4095) & ~(size_t)4095;
+            size_t lo = per * (size_t)t, hi = std::min(total, lo + per);
+            for (int k = 0; k < 2 && lo < hi; ++k) {   // the byte range [lo, hi) of job 0 followed by job 1
+                const size_t base = k == 0 ? 0 : j[0].n;
+                const size_t a = std::max(lo, base), b = std::min(hi, base + j[k].n);
+                if (a < b) memcpy(j[k].d + (a - base), j[k].s + (a - base), b - a);
+            }
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    Job job_[2] = {};
+    int pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+
+static int g_host_threads = 0;   // 0 = default (icnv_set_host_threads)
+static int pool_threads_per_device() {
+    int n = g_host_threads;
+    if (n <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        n = (int)std::min<unsigned>(16u, std::max<unsigned>(2u, hw / 2));
+    }
+    const int slots = std::max(1, g_slots);
+    return std::max(2, n / slots);
+}
+
+// pinned staging buffer `i` of the current device context (grow-only, freed in icnv_shutdown)
+static void *pinned(int i, size_t bytes) {
+    Ctx &c = ctx();
+    if (c.pin_bytes[i] >= bytes) return c.pin_ptr[i];
+    if (c.pin_ptr[i]) {
+        cudaFreeHost(c.pin_ptr[i]);
+        c.pin_ptr[i] = nullptr;
+        c.pin_bytes[i] = 0;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_error(ICNV_E_NOMEM, "cudaHostAlloc(%zu) for the staging ring failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    c.pin_ptr[i] = p;
+    c.pin_bytes[i] = bytes;
+    return p;
+}
+
+// true when the driver can DMA straight from / to p (cudaHostAlloc / cudaHostRegister memory)
+static bool is_pinned(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
 int set_error(int code, const char *fmt, ...) {
@@ -179,24 +306,56 @@ int icnv_device_count(void) {
     return n;
 }
 
-int icnv_init(int device) {
-    Ctx &c = ctx();
-    std::lock_guard<std::mutex> lk(c.mu);
-    if (device < 0) device = c.ready ? c.device : 0;
-    if (c.ready && c.device == device) return ICNV_OK;
-    int n = icnv_device_count();
-    if (n <= 0) return set_error(ICNV_E_NO_DEVICE, "no CUDA device available (the library has no CPU fallback)");
-    if (device >= n) return set_error(ICNV_E_BAD_ARG, "device %d out of range (%d devices)", device, n);
-    if (c.ready) {
-        cudaSetDevice(c.device);
-        for (int s = 0; s < SLOT_COUNT; ++s) {
-            if (c.slot_ptr[s]) cudaFree(c.slot_ptr[s]);
-            c.slot_ptr[s] = nullptr;
-            c.slot_bytes[s] = 0;
-        }
-        destroy_streams(c);
-        c.ready = false;
+static void free_slot(Ctx &c) {
+    cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    for (int s = 0; s < SLOT_COUNT; ++s) {
+        if (c.slot_ptr[s]) cudaFree(c.slot_ptr[s]);
+        c.slot_ptr[s] = nullptr;
+        c.slot_bytes[s] = 0;
     }
+    for (int i = 0; i < 6; ++i) {
+        if (c.pin_ptr[i]) cudaFreeHost(c.pin_ptr[i]);
+        c.pin_ptr[i] = nullptr;
+        c.pin_bytes[i] = 0;
+    }
+    destroy_streams(c);
+    c.ready = false;
+}
+
+static int env_int(const char *name, int dflt, bool *set = nullptr) {
+    const char *e = getenv(name);
+    if (set) *set = e != nullptr;
+    return e ? atoi(e) : dflt;
+}
+
+// Tuning switches come from the environment ONCE, here - never at launch time - and every one that departs from the
+// default is reported, so a stray variable in a user's shell cannot silently change which kernel runs.
+static void read_options(Ctx &c, bool verbose) {
+    bool set;
+    if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : 1;
+    c.opt_cell_kernel = env_int("ICNV_CELL_KERNEL", 0);
+    c.opt_cell_nt = env_int("ICNV_CELL_NT", 0);
+    c.opt_cell_variant = env_int("ICNV_CELL_VARIANT", -1);
+    c.opt_cell_padq = env_int("ICNV_CELL_PADQ", 1);
+    c.opt_cell_lfix = env_int("ICNV_CELL_LFIX", 1);
+    c.opt_vfast_warps = env_int("ICNV_VFAST_WARPS", 0);
+    c.opt_mf_kernel = env_int("ICNV_MF_KERNEL", -1);
+    c.opt_mf_list32 = env_int("ICNV_MF_LIST32", 0);
+    c.opt_slab_cells = env_int("ICNV_SLAB_CELLS", 0, &set);
+    if (c.opt_slab_cells < 32 || c.opt_slab_cells > 65536) c.opt_slab_cells = 0;
+    if (!verbose) return;
+    static const char *names[] = {"ICNV_HMM_MODE", "ICNV_CELL_KERNEL", "ICNV_CELL_NT", "ICNV_CELL_VARIANT", "ICNV_CELL_PADQ",
+                                  "ICNV_CELL_LFIX", "ICNV_VFAST_WARPS", "ICNV_MF_KERNEL", "ICNV_MF_LIST32", "ICNV_SLAB_CELLS"};
+    for (const char *n : names)
+        if (const char *e = getenv(n)) fprintf(stderr, "[infercnv_b200] non-default tuning switch %s=%s (read once at icnv_init)\n", n, e);
+}
+
+static int init_slot(int slot, int device) {
+    Ctx &c = g_ctx[slot];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.ready && c.device == device) return ICNV_OK;
+    if (c.ready) free_slot(c);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return set_error(ICNV_E_NO_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     cudaDeviceProp prop;
@@ -224,29 +383,83 @@ int icnv_init(int device) {
     c.up_items.clear();
     c.hmm_list_count = nullptr;
     c.rg_n = 0;
-    if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : 1;
+    read_options(c, slot == 0);
     c.ready = true;
     return ICNV_OK;
 }
 
-void icnv_shutdown(void) {
-    Ctx &c = ctx();
-    std::lock_guard<std::mutex> lk(c.mu);
-    if (!c.ready) return;
-    cudaSetDevice(c.device);
-    cudaStreamSynchronize(c.stream);
-    for (int s = 0; s < SLOT_COUNT; ++s) {
-        if (c.slot_ptr[s]) cudaFree(c.slot_ptr[s]);
-        c.slot_ptr[s] = nullptr;
-        c.slot_bytes[s] = 0;
+static std::mutex g_init_mu;
+
+int icnv_init(int device) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    Ctx &c0 = g_ctx[0];
+    if (device < 0) {
+        if (c0.ready) return ICNV_OK;   // keep whatever icnv_init / icnv_init_devices set up
+        device = 0;
     }
-    destroy_streams(c);
-    c.ready = false;
+    if (c0.ready && c0.device == device && g_slots == 1) return ICNV_OK;
+    int n = icnv_device_count();
+    if (n <= 0) return set_error(ICNV_E_NO_DEVICE, "no CUDA device available (the library has no CPU fallback)");
+    if (device >= n) return set_error(ICNV_E_BAD_ARG, "device %d out of range (%d devices)", device, n);
+    for (int s = 1; s < g_slots; ++s)
+        if (g_ctx[s].ready) free_slot(g_ctx[s]);
+    int rc = init_slot(0, device);
+    if (rc) return rc;
+    g_slots = 1;
+    cudaSetDevice(device);
+    return ICNV_OK;
+}
+
+int icnv_init_devices(int n_devices, const int *device_ids) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    int n = icnv_device_count();
+    if (n <= 0) return set_error(ICNV_E_NO_DEVICE, "no CUDA device available (the library has no CPU fallback)");
+    if (n_devices <= 0) n_devices = n;   // "all of them"
+    if (n_devices > ICNV_MAX_DEVICES || n_devices > n)
+        return set_error(ICNV_E_BAD_ARG, "icnv_init_devices: %d devices requested, %d present (at most %d)", n_devices, n,
+                         ICNV_MAX_DEVICES);
+    for (int i = 0; i < n_devices; ++i) {
+        const int d = device_ids ? device_ids[i] : i;
+        if (d < 0 || d >= n) return set_error(ICNV_E_BAD_ARG, "icnv_init_devices: device %d out of range", d);
+        for (int j = 0; j < i; ++j)
+            if ((device_ids ? device_ids[j] : j) == d) return set_error(ICNV_E_BAD_ARG, "icnv_init_devices: device %d listed twice", d);
+    }
+    for (int s = n_devices; s < g_slots; ++s)
+        if (g_ctx[s].ready) free_slot(g_ctx[s]);
+    for (int i = 0; i < n_devices; ++i) {
+        int rc = init_slot(i, device_ids ? device_ids[i] : i);
+        if (rc) return rc;
+    }
+    g_slots = n_devices;
+    cudaSetDevice(g_ctx[0].device);
+    return ICNV_OK;
+}
+
+int icnv_devices_in_use(void) { return g_slots; }
+
+int icnv_set_host_threads(int n) {
+    if (n < 0 || n > 256) return set_error(ICNV_E_BAD_ARG, "icnv_set_host_threads: 0 (default) .. 256");
+    g_host_threads = n;
+    return ICNV_OK;
+}
+
+void icnv_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    for (int s = 0; s < ICNV_MAX_DEVICES; ++s) {
+        Ctx &c = g_ctx[s];
+        std::lock_guard<std::mutex> lk2(c.mu);
+        if (c.ready) free_slot(c);
+    }
+    g_slots = 0;
 }
 
 const char *icnv_last_error(void) { return g_err; }
 const char *icnv_version(void) { return "infercnv_b200 0.1.0 (sm_100a)"; }
-int64_t icnv_launch_count(void) { return ctx().launches.load(); }
+int64_t icnv_launch_count(void) {
+    int64_t n = 0;
+    for (int s = 0; s < std::max(1, g_slots); ++s) n += g_ctx[s].launches.load();
+    return n;
+}
 
 // ---- device-side composition of the smooth block ---------------------------------------------------------
 
@@ -417,31 +630,38 @@ struct HmmModel {
 // Y (optional) = smooth block of X; states (optional) = per-cell Viterbi of the block's output (or of X
 // itself when do_smooth == 0).
 // states (int32, -1 = unassigned) or states8 (uint8, 255 = unassigned): at most one of them is non-NULL.
-static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, uint8_t *states8, int64_t G, int64_t C,
-                         const int32_t *chr_start, const int32_t *chr_len, int K, int do_smooth, const int32_t *grp_off,
-                         const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window, int use_bounds,
-                         const HmmModel *hmm) {
+// Works on the cells [c_lo, c_hi) of the G x C host matrices on the calling thread's device context; the reference
+// groups index the whole matrix (every device reduces all reference cells itself, in list order).
+static int host_pipeline_range(Ctx &c, const double *X, double *Y, int32_t *states, uint8_t *states8, int64_t G, int64_t c_lo,
+                               int64_t c_hi, const int32_t *chr_start, const int32_t *chr_len, int K, int do_smooth,
+                               const int32_t *grp_off, const int32_t *grp_idx, int n_grp, int apply_log, double threshold,
+                               int window, int use_bounds, const HmmModel *hmm, CopyPool *pool) {
     cudaStream_t sc = c.stream, sh = c.s_h2d, sd = c.s_d2h;
     int rc;
+    const int64_t C = c_hi - c_lo;
     int *d_flag = (int *)scratch(SLOT_MISC, 64);
     if (!d_flag) return ICNV_E_NOMEM;
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), sc));
     double *lo1 = nullptr, *hi1 = nullptr, *mid1 = nullptr, *lo2 = nullptr, *hi2 = nullptr, *mid2 = nullptr;
+    // page-locked caller memory goes over PCIe directly; anything else through the pinned ring (pool != NULL)
+    const bool stage_in = pool && !is_pinned(X);
+    const bool stage_out = pool && ((Y && !is_pinned(Y)) || (states && !is_pinned(states)) || (states8 && !is_pinned(states8)));
 
     // ---- slabs ------------------------------------------------------------------------------------------
     // Fill and drain of the copy pipeline cost one slab each way.  Without the HMM a slab's kernel time (~0.05 ms per 256
     // cells) is far below its PCIe time (0.37 ms), so small slabs only shorten fill / drain; the per-cell Viterbi is bounded
     // below by its longest chromosome's serial recursion whatever the slab size, so HMM calls keep the measured 1024.
     int64_t slab_cells = hmm ? SLAB_CELLS : SLAB_CELLS_SMOOTH;
-    if (const char *e = getenv("ICNV_SLAB_CELLS")) {   // tuning knob
-        const long v = atol(e);
-        if (v >= 32 && v <= 65536) slab_cells = v;
-    }
-    const int64_t slab = std::min<int64_t>(slab_cells, C);
+    if (stage_in || stage_out) slab_cells = SLAB_CELLS;   // fewer, larger hand-overs to the copy threads
+    if (c.opt_slab_cells) slab_cells = c.opt_slab_cells;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(slab_cells, C));
     const size_t slab_elems = (size_t)G * (size_t)slab;
     double *dIn[2], *dOut[2] = {nullptr, nullptr};
     uint8_t *dSt[2] = {nullptr, nullptr};
     int32_t *dW[2] = {nullptr, nullptr};
+    double *pIn[2] = {nullptr, nullptr}, *pOut[2] = {nullptr, nullptr};
+    void *pSt[2] = {nullptr, nullptr};
+    const size_t st_elem = states ? sizeof(int32_t) : 1;
     for (int b = 0; b < 2; ++b) {
         dIn[b] = (double *)scratch(SLOT_SLAB_IN0 + b, sizeof(double) * slab_elems);
         if (!dIn[b]) return ICNV_E_NOMEM;
@@ -457,14 +677,60 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
                 if (!dW[b]) return ICNV_E_NOMEM;
             }
         }
+        if (stage_in && !(pIn[b] = (double *)pinned(b, sizeof(double) * slab_elems))) return ICNV_E_NOMEM;
+        if (stage_out && do_smooth && Y && !(pOut[b] = (double *)pinned(2 + b, sizeof(double) * slab_elems))) return ICNV_E_NOMEM;
+        if (stage_out && hmm && !(pSt[b] = pinned(4 + b, st_elem * slab_elems))) return ICNV_E_NOMEM;
     }
     const int64_t n_slabs = (C + slab - 1) / slab;
+    auto slab_cells_of = [&](int64_t i) { return std::min<int64_t>(slab, C - i * slab); };
+    // results of slab j leave the pinned ring for the caller's buffers (after its D2H has completed); together with the
+    // input of slab `in` entering the ring when in >= 0 - one hand-over to the copy threads for both directions
+    auto host_copies = [&](int64_t in, int64_t out) -> int {
+        void *d0 = nullptr, *d1 = nullptr;
+        const void *s0 = nullptr, *s1 = nullptr;
+        size_t n0 = 0, n1 = 0;
+        if (in >= 0 && in < n_slabs && stage_in) {
+            const int b = (int)(in & 1);
+            if (in >= 2) ICNV_CUDA(cudaEventSynchronize(c.ev_h2d[b]));   // the ring slot has been read by slab in-2's H2D
+            d0 = pIn[b];
+            s0 = X + G * (c_lo + in * slab);
+            n0 = sizeof(double) * (size_t)G * (size_t)slab_cells_of(in);
+        }
+        if (out >= 0 && out < n_slabs && stage_out) {
+            const int b = (int)(out & 1);
+            ICNV_CUDA(cudaEventSynchronize(c.ev_d2h[b]));
+            const int64_t c0 = c_lo + out * slab, nc = slab_cells_of(out);
+            if (do_smooth && Y) {
+                d1 = Y + G * c0;
+                s1 = pOut[b];
+                n1 = sizeof(double) * (size_t)G * (size_t)nc;
+            }
+            if (hmm) {   // the states ride along: a third job is not worth a second hand-over
+                char *dst = states ? (char *)(states + G * c0) : (char *)(states8 + G * c0);
+                if (n1 == 0) {
+                    d1 = dst;
+                    s1 = pSt[b];
+                    n1 = st_elem * (size_t)G * (size_t)nc;
+                } else {
+                    pool->copy2(d0, s0, n0, d1, s1, n1);
+                    d0 = dst;
+                    s0 = pSt[b];
+                    n0 = st_elem * (size_t)G * (size_t)nc;
+                    d1 = nullptr;
+                    n1 = 0;
+                }
+            }
+        }
+        pool->copy2(d0, s0, n0, d1, s1, n1);
+        return ICNV_OK;
+    };
     // H2D of slab i (buffer i & 1) may start once the kernels of slab i-2 have consumed the buffer
     auto issue_h2d = [&](int64_t i) -> int {
         const int b = (int)(i & 1);
-        const int64_t c0 = i * slab, nc = std::min<int64_t>(slab, C - c0);
+        const int64_t c0 = c_lo + i * slab, nc = slab_cells_of(i);
         if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sh, c.ev_comp[b], 0));
-        ICNV_CUDA(cudaMemcpyAsync(dIn[b], X + G * c0, sizeof(double) * (size_t)G * (size_t)nc, cudaMemcpyHostToDevice, sh));
+        ICNV_CUDA(cudaMemcpyAsync(dIn[b], stage_in ? pIn[b] : X + G * c0, sizeof(double) * (size_t)G * (size_t)nc,
+                                  cudaMemcpyHostToDevice, sh));
         ICNV_CUDA(cudaEventRecord(c.ev_h2d[b], sh));
         return ICNV_OK;
     };
@@ -479,19 +745,32 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
         double *d_b = (double *)scratch(SLOT_BOUNDS, sizeof(double) * (size_t)G * 6);
         int32_t *d_iota = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_ref);
         if (!d_ref || !d_T || !d_means || !d_b || !d_iota) return ICNV_E_NOMEM;
-        for (int64_t i = 0; i < n_ref;) {  // runs of consecutive cells go up in one copy
+        for (int64_t i = 0; i < n_ref;) {  // runs of consecutive cells go up in one copy (staged: a ring slot at a time)
             int64_t j = i + 1;
             while (j < n_ref && grp_idx[j] == grp_idx[j - 1] + 1) ++j;
-            ICNV_CUDA(cudaMemcpyAsync(d_ref + G * i, X + G * (int64_t)grp_idx[i], sizeof(double) * (size_t)(G * (j - i)),
-                                      cudaMemcpyHostToDevice, sc));
+            if (!stage_in) {
+                ICNV_CUDA(cudaMemcpyAsync(d_ref + G * i, X + G * (int64_t)grp_idx[i], sizeof(double) * (size_t)(G * (j - i)),
+                                          cudaMemcpyHostToDevice, sc));
+            } else {
+                for (int64_t q = i; q < j; q += slab) {
+                    const int64_t nq = std::min<int64_t>(slab, j - q);
+                    const int b = (int)((q / slab) & 1);
+                    ICNV_CUDA(cudaEventSynchronize(c.ev_h2d[b]));   // (a recorded-never event is complete)
+                    pool->copy2(pIn[b], X + G * ((int64_t)grp_idx[i] + (q - i)), sizeof(double) * (size_t)(G * nq), nullptr, nullptr, 0);
+                    ICNV_CUDA(cudaMemcpyAsync(d_ref + G * q, pIn[b], sizeof(double) * (size_t)(G * nq), cudaMemcpyHostToDevice, sc));
+                    ICNV_CUDA(cudaEventRecord(c.ev_h2d[b], sc));
+                }
+            }
             i = j;
         }
         std::vector<int32_t> iota((size_t)n_ref);
         std::iota(iota.begin(), iota.end(), 0);
         ICNV_CUDA(cudaMemcpyAsync(d_iota, iota.data(), sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, sc));
-        // the first two slabs queue up behind the reference columns and cross PCIe while the pre-passes run
-        for (; h2d_issued < std::min<int64_t>(2, n_slabs); ++h2d_issued)
-            if ((rc = issue_h2d(h2d_issued))) return rc;
+        if (!stage_in) {
+            // the first two slabs queue up behind the reference columns and cross PCIe while the pre-passes run
+            for (; h2d_issued < std::min<int64_t>(2, n_slabs); ++h2d_issued)
+                if ((rc = issue_h2d(h2d_issued))) return rc;
+        }
         ICNV_CUDA(cudaStreamSynchronize(sc));
         lo1 = d_b; hi1 = d_b + G; mid1 = d_b + 2 * G; lo2 = d_b + 3 * G; hi2 = d_b + 4 * G; mid2 = d_b + 5 * G;
         if ((rc = dev_group_means(d_ref, G, G, d_iota, grp_off, n_grp, apply_log ? 1 : 0, d_means, sc))) return rc;
@@ -506,12 +785,19 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
         else mid1 = mid2 = nullptr;
     }
 
+    if (stage_in) {   // the first slab enters the ring while the reference pre-passes run on the device
+        if ((rc = host_copies(0, -1))) return rc;
+    }
     for (int64_t i = 0; i < n_slabs; ++i) {
         const int b = (int)(i & 1);
-        const int64_t c0 = i * slab, nc = std::min<int64_t>(slab, C - c0);
+        const int64_t c0 = c_lo + i * slab, nc = slab_cells_of(i);
         const size_t bytes = sizeof(double) * (size_t)G * (size_t)nc;
-        for (; h2d_issued <= i; ++h2d_issued)
-            if ((rc = issue_h2d(h2d_issued))) return rc;
+        if (stage_in) {
+            if (h2d_issued <= i && (rc = issue_h2d(h2d_issued++))) return rc;
+        } else {
+            for (; h2d_issued <= std::min<int64_t>(i + 1, n_slabs - 1); ++h2d_issued)
+                if ((rc = issue_h2d(h2d_issued))) return rc;
+        }
         // kernels: need the slab on the device and the output buffers of slab i-2 drained
         ICNV_CUDA(cudaStreamWaitEvent(sc, c.ev_h2d[b], 0));
         if (i >= 2) ICNV_CUDA(cudaStreamWaitEvent(sc, c.ev_d2h[b], 0));
@@ -529,18 +815,67 @@ static int host_pipeline(Ctx &c, const double *X, double *Y, int32_t *states, ui
             if (states && (rc = icnv_dev_widen_states(dSt[b], dW[b], (int64_t)G * nc, sc))) return rc;
         }
         ICNV_CUDA(cudaEventRecord(c.ev_comp[b], sc));
-        // D2H
+        // D2H (staged: the ring slot of slab i-2 was emptied by host_copies(.., i-2) below, two iterations ago)
         ICNV_CUDA(cudaStreamWaitEvent(sd, c.ev_comp[b], 0));
-        if (do_smooth && Y) ICNV_CUDA(cudaMemcpyAsync(Y + G * c0, dOut[b], bytes, cudaMemcpyDeviceToHost, sd));
+        if (do_smooth && Y) ICNV_CUDA(cudaMemcpyAsync(stage_out ? pOut[b] : Y + G * c0, dOut[b], bytes, cudaMemcpyDeviceToHost, sd));
         if (hmm && states)
-            ICNV_CUDA(cudaMemcpyAsync(states + G * c0, dW[b], sizeof(int32_t) * (size_t)G * (size_t)nc, cudaMemcpyDeviceToHost, sd));
+            ICNV_CUDA(cudaMemcpyAsync(stage_out ? (int32_t *)pSt[b] : states + G * c0, dW[b],
+                                      sizeof(int32_t) * (size_t)G * (size_t)nc, cudaMemcpyDeviceToHost, sd));
         if (hmm && states8)
-            ICNV_CUDA(cudaMemcpyAsync(states8 + G * c0, dSt[b], (size_t)G * (size_t)nc, cudaMemcpyDeviceToHost, sd));
+            ICNV_CUDA(cudaMemcpyAsync(stage_out ? (uint8_t *)pSt[b] : states8 + G * c0, dSt[b], (size_t)G * (size_t)nc,
+                                      cudaMemcpyDeviceToHost, sd));
         ICNV_CUDA(cudaEventRecord(c.ev_d2h[b], sd));
+        // host side of the ring while the device works on slab i: slab i+1 in, slab i-1 out
+        if (stage_in || stage_out)
+            if ((rc = host_copies(stage_in ? i + 1 : -1, stage_out ? i - 1 : -1))) return rc;
     }
+    if (stage_out && (rc = host_copies(-1, n_slabs - 1))) return rc;
     ICNV_CUDA(cudaStreamSynchronize(sh));
     ICNV_CUDA(cudaStreamSynchronize(sd));
     return check_flag(d_flag, sc);
+}
+
+// The cells are cut into one contiguous range per device context; each range is driven by its own host thread (a CUDA
+// context per thread, its own streams, scratch and ring).  One context: the calling thread does the work itself.
+static int host_pipeline(Ctx &c0, const double *X, double *Y, int32_t *states, uint8_t *states8, int64_t G, int64_t C,
+                         const int32_t *chr_start, const int32_t *chr_len, int K, int do_smooth, const int32_t *grp_off,
+                         const int32_t *grp_idx, int n_grp, int apply_log, double threshold, int window, int use_bounds,
+                         const HmmModel *hmm) {
+    const int n_dev = (int)std::min<int64_t>(std::max(1, device_slots()), std::max<int64_t>(1, C / 64));
+    const bool pageable = !is_pinned(X) || (Y && !is_pinned(Y)) || (states && !is_pinned(states)) || (states8 && !is_pinned(states8));
+    const int nt = pool_threads_per_device();
+    if (n_dev <= 1) {
+        std::unique_ptr<CopyPool> pool(pageable ? new CopyPool(nt) : nullptr);
+        return host_pipeline_range(c0, X, Y, states, states8, G, 0, C, chr_start, chr_len, K, do_smooth, grp_off, grp_idx, n_grp,
+                                   apply_log, threshold, window, use_bounds, hmm, pool.get());
+    }
+    std::vector<int> rcs((size_t)n_dev, ICNV_OK);
+    std::vector<std::string> msgs((size_t)n_dev);
+    std::vector<std::thread> th;
+    const int caller_slot = current_slot();
+    for (int d = 0; d < n_dev; ++d) {
+        const int64_t lo = C * d / n_dev, hi = C * (d + 1) / n_dev;
+        th.emplace_back([&, d, lo, hi] {
+            set_current_slot(d);
+            Ctx &c = ctx();
+            std::unique_lock<std::mutex> lk(c.mu, std::defer_lock);
+            if (d != caller_slot) lk.lock();   // the caller already holds its own context's lock
+            int rc = ICNV_OK;
+            if (cudaSetDevice(c.device) != cudaSuccess) rc = set_error(ICNV_E_CUDA, "cudaSetDevice(%d) failed", c.device);
+            if (!rc) {
+                std::unique_ptr<CopyPool> pool(pageable ? new CopyPool(nt) : nullptr);
+                rc = host_pipeline_range(c, X, Y, states, states8, G, lo, hi, chr_start, chr_len, K, do_smooth, grp_off, grp_idx,
+                                         n_grp, apply_log, threshold, window, use_bounds, hmm, pool.get());
+            }
+            rcs[(size_t)d] = rc;
+            if (rc) msgs[(size_t)d] = icnv_last_error();   // the message is per thread: carry it to the caller
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(c0.device);
+    for (int d = 0; d < n_dev; ++d)
+        if (rcs[(size_t)d]) return set_error(rcs[(size_t)d], "device %d: %s", ctx_of(d).device, msgs[(size_t)d].c_str());
+    return ICNV_OK;
 }
 
 int icnv_smooth_block_f64(const double *X, double *Y, int64_t G, int64_t C, const int32_t *chr_start,

@@ -73,8 +73,21 @@ struct Ctx {
     // nothing from pageable host memory (such a copy may synchronise the host with the stream)
     std::vector<unsigned char> up_segs, up_items;
     cudaStream_t up_segs_stream = nullptr, up_items_stream = nullptr;   // an upload orders only the stream it was issued on
+    // pinned staging ring of the host-pointer entry points (pageable caller memory, e.g. an R matrix): two slabs in, two out
+    void *pin_ptr[6] = {};
+    size_t pin_bytes[6] = {};
+    // tuning switches, read from the environment ONCE in icnv_init (never at launch time); -1 / 0 = library default
+    int opt_cell_kernel = 0, opt_cell_nt = 0, opt_cell_variant = -1, opt_cell_padq = 1, opt_cell_lfix = 1;
+    int opt_vfast_warps = 0, opt_mf_kernel = -1, opt_mf_list32 = 0;
+    long opt_slab_cells = 0;
     std::mutex mu;
 };
+
+constexpr int ICNV_MAX_DEVICES = 16;
+int current_slot();            // which of the library's device contexts this host thread works on
+void set_current_slot(int s);
+int device_slots();            // contexts initialised by icnv_init (1) or icnv_init_devices (n)
+Ctx &ctx_of(int slot);
 
 // upload `bytes` of `src` to `dst` on `st` unless `cache` says the device copy already holds them and the upload that put
 // them there was ordered on the same stream

@@ -191,13 +191,13 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     const int W = (2 * r + 1) * (2 * r + 1);
     bool select_kernel = (r >= 2 && r <= 5);
     int use_net = 0;
-    if (const char *e = getenv("ICNV_MF_KERNEL")) {   // 0: generic kernel; 2: key network for full 9 x 9 windows (A/B runs)
-        select_kernel = select_kernel && (atoi(e) != 0);
-        use_net = (atoi(e) == 2 && r == 4) ? 1 : 0;
+    if (c.opt_mf_kernel >= 0) {   // ICNV_MF_KERNEL, read once in icnv_init: 0 generic kernel; 2 key network for full 9 x 9 windows (A/B runs)
+        select_kernel = select_kernel && (c.opt_mf_kernel != 0);
+        use_net = (c.opt_mf_kernel == 2 && r == 4) ? 1 : 0;
     }
     const int TI = select_kernel ? MS_TI : MF_TI, TJ = select_kernel ? MS_TJ : MF_TJ, NT = TI * TJ;
     bool list32 = false;
-    if (const char *e = getenv("ICNV_MF_LIST32")) list32 = select_kernel && atoi(e) != 0;   // diagnostic
+    if (c.opt_mf_list32) list32 = select_kernel;   // diagnostic (ICNV_MF_LIST32 at icnv_init)
     const size_t smem = sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
                         (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT +
                         (use_net ? sizeof(float) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) : 0);

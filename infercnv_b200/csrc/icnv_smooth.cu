@@ -93,6 +93,44 @@ __global__ void __launch_bounds__(256) bounds_from_means_kernel(const double *__
     if (mid) mid[g] = s / (double)n_grp;
 }
 
+// Reference bounds straight from the (all-gathered) chunk sums: per gene and group the chunk rows of every rank are added
+// in rank-major, then chunk order - the global list order, whatever the rank count - divided by the group size, and the
+// min / max / mean over the groups written (ops.R:1708-1735).  One launch instead of a combine per group, a stack and
+// bounds_from_means; zero rows (a rank's padding up to the longest rank) do not change a sum.
+struct PartialBoundsParams {
+    const double *part;   // [world][tot_rows][G]
+    int64_t G, tot_rows;
+    int world, n_grp;
+    int row_off[33];      // rows of group k inside a rank's block: row_off[k] .. row_off[k + 1]
+    double count[32];     // global group sizes
+    double *lo, *hi, *mid;
+};
+
+__global__ void __launch_bounds__(256) bounds_from_partials_kernel(const PartialBoundsParams p) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.G) return;
+    double mn = 0.0, mx = 0.0, sm = 0.0;
+    for (int k = 0; k < p.n_grp; ++k) {
+        double s = 0.0;
+        const int r0 = p.row_off[k], r1 = p.row_off[k + 1];
+        for (int w = 0; w < p.world; ++w) {
+            const double *__restrict__ base = p.part + p.G * ((int64_t)w * p.tot_rows);
+            for (int q = r0; q < r1; ++q) s += base[g + p.G * q];
+        }
+        const double m = s / p.count[k];  // a true division by the count, as mean() does
+        if (k == 0) {
+            mn = m;
+            mx = m;
+        }
+        mn = fmin(mn, m);
+        mx = fmax(mx, m);
+        sm += m;
+    }
+    p.lo[g] = mn;
+    p.hi[g] = mx;
+    if (p.mid) p.mid[g] = sm / (double)p.n_grp;
+}
+
 // inv_log variant of the group mean: log2(mean(2^x - 1) + 1) (ops.R:1714-1717)
 __global__ void __launch_bounds__(256) group_partial_sums_invlog_kernel(const double *__restrict__ X, int64_t G,
                                                                         int64_t ldx, const int32_t *__restrict__ cells,
@@ -1628,6 +1666,32 @@ int icnv_dev_combine_partials_f64(const double *partial, int64_t G, int64_t n_ch
     return ICNV_OK;
 }
 
+int icnv_dev_bounds_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
+                                      const int32_t *row_off, const int64_t *counts, double *lo, double *hi, double *mid,
+                                      void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!partials || !lo || !hi || !row_off || !counts || G <= 0 || world <= 0 || n_grp <= 0 || n_grp > 32 || tot_rows <= 0)
+        return set_error(ICNV_E_BAD_ARG, "icnv_dev_bounds_from_partials_f64: bad argument (at most 32 groups)");
+    PartialBoundsParams p;
+    p.part = partials;
+    p.G = G;
+    p.tot_rows = tot_rows;
+    p.world = world;
+    p.n_grp = n_grp;
+    for (int k = 0; k <= n_grp; ++k) p.row_off[k] = row_off[k];
+    for (int k = 0; k < n_grp; ++k) {
+        if (counts[k] <= 0 || row_off[k + 1] < row_off[k] || row_off[k + 1] > tot_rows)
+            return set_error(ICNV_E_BAD_ARG, "icnv_dev_bounds_from_partials_f64: bad group %d", k);
+        p.count[k] = (double)counts[k];
+    }
+    p.lo = lo;
+    p.hi = hi;
+    p.mid = mid;
+    bounds_from_partials_kernel<<<(unsigned)((G + 255) / 256), 256, 0, pick_stream(stream)>>>(p);
+    ICNV_CHECK_LAUNCH("bounds_from_partials_kernel");
+    return ICNV_OK;
+}
+
 int icnv_dev_bounds_from_means_f64(const double *means, int64_t G, int n_grp, double *lo, double *hi, double *mid,
                                    void *stream) {
     ICNV_REQUIRE_READY();
@@ -1689,14 +1753,14 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     // ---- v3 (values stay in shared memory, two ping-pong buffers) whenever both buffers fit -----------------
     {
         int want_v2 = 0, nt3 = (G <= 2048) ? 256 : (G <= 6144 ? 512 : 1024);
-        if (const char *e = getenv("ICNV_CELL_KERNEL")) want_v2 = (atoi(e) == 2);
-        if (const char *e = getenv("ICNV_CELL_NT")) nt3 = atoi(e);
+        if (ctx().opt_cell_kernel) want_v2 = (ctx().opt_cell_kernel == 2);
+        if (ctx().opt_cell_nt) nt3 = ctx().opt_cell_nt;
         if (nt3 != 256 && nt3 != 512 && nt3 != 1024) nt3 = 1024;
         const int NW3 = nt3 / 32;
         const size_t red3 = (nt3 == 256) ? sizeof(Red<8>) : (nt3 == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
         // padded-Q layout (see the kernel) whenever it fits; ICNV_CELL_PADQ=0 keeps the ping-pong layout (A/B switch)
         int padq = 1;
-        if (const char *e = getenv("ICNV_CELL_PADQ")) padq = atoi(e) != 0;
+        padq = padq && ctx().opt_cell_padq != 0;
         const int q_elems = (int)(((int64_t)G + (int64_t)K * (2 * h + 2) + 1) & ~(int64_t)1);
         int L3 = want_v2 ? 0 : build_segments(G, chr_start, chr_len, K, nt3, 1 << 20, segs);
         if (L3 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
@@ -1725,7 +1789,7 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
             int rc3;
             // fully unrolled slice loops for the segment length of the 10 000-gene configurations (ICNV_CELL_LFIX=0: generic)
             int lfix = (padq && nt3 == 1024 && L3 == 11) ? 11 : 0;
-            if (const char *e = getenv("ICNV_CELL_LFIX")) if (atoi(e) == 0) lfix = 0;
+            if (ctx().opt_cell_lfix == 0) lfix = 0;
             if (lfix == 11)
                 rc3 = launch3(cell_pipeline3_kernel<1024, true, 11>);
             else if (padq)
@@ -1744,7 +1808,7 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     // (threads, genes per thread) variants, smallest first; ICNV_CELL_VARIANT=<index> pins one (tuning)
     static const int variants[][2] = {{256, 12}, {512, 12}, {512, 24}, {1024, 12}, {1024, 24}};  // measured: 512x24 beats 1024x12
     int NT = 0, L = 0, lmax = 0, forced = -1;
-    if (const char *e = getenv("ICNV_CELL_VARIANT")) forced = atoi(e);
+    if (ctx().opt_cell_variant >= 0) forced = ctx().opt_cell_variant;
     for (int vi = 0; vi < 5; ++vi) {
         if (forced >= 0 && vi != forced) continue;
         L = build_segments(G, chr_start, chr_len, K, variants[vi][0], variants[vi][1], segs);

@@ -902,7 +902,7 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     auto lkern = (m == 6) ? viterbi_list_kernel<6> : viterbi_list_kernel<3>;
     // warps per CTA of the fast kernel: 16 (128 registers per thread) unless ICNV_VFAST_WARPS picks an occupancy variant
     int fw = FAST_WARPS;
-    if (const char *e = getenv("ICNV_VFAST_WARPS")) fw = atoi(e);
+    if (c.opt_vfast_warps) fw = c.opt_vfast_warps;   // read once in icnv_init
     if (fw != 16 && fw != 20 && fw != 24) fw = FAST_WARPS;
     void (*fkern)(const VitParams) =
         (m == 6) ? (fw == 24 ? viterbi_fast_kernel<6, 24> : (fw == 20 ? viterbi_fast_kernel<6, 20> : viterbi_fast_kernel<6, 16>))

@@ -41,6 +41,24 @@ class Engine:
         self._plan_cache = {}
         self._T = None
 
+    # ---- process-group plumbing -------------------------------------------------------------------------------------
+    def _world(self) -> int:
+        import torch.distributed as tdist
+        return tdist.get_world_size() if (self.collective and tdist.is_available() and tdist.is_initialized()) else 1
+
+    def _all_gather(self, out: torch.Tensor, part: torch.Tensor) -> None:
+        """out[(world,) + part.shape] <- every rank's `part`.  NCCL: one ncclAllGather on torch's current stream over
+        NVLink.  Any other backend (gloo: several ranks sharing one GPU in the tests, or CPU-only plumbing tests) goes
+        through host memory - same values, same order."""
+        import torch.distributed as tdist
+        if tdist.get_backend() == "nccl":
+            tdist.all_gather_into_tensor(out, part)
+            return
+        host = part.detach().cpu().contiguous()
+        parts = [torch.empty_like(host) for _ in range(tdist.get_world_size())]
+        tdist.all_gather(parts, host)
+        out.copy_(torch.stack(parts).to(out.device))
+
     # ---- data ---------------------------------------------------------------------------------------
     def synth(self, G, chr_start, chr_len, cells_global, C_total, seed) -> torch.Tensor:
         """Synthetic depth-normalised expression for the given GLOBAL cell indices (runs of
@@ -133,31 +151,41 @@ class Engine:
             cached = self._plan_cache[key] = (d_groups, t_lists, all_ref)
         d_groups, t_lists, all_ref = cached
 
-        import torch.distributed as tdist
-        world = tdist.get_world_size() if (self.collective and tdist.is_available() and tdist.is_initialized()) else 1
+        world = self._world()
+        tot = int(sum(max_chunks)) if world > 1 else int(sum((len(g) + shard.CHUNK - 1) // shard.CHUNK for g in ref_groups_local))
+        rows = [0]
+        for k in range(n_grp):
+            rows.append(rows[-1] + (int(max_chunks[k]) if world > 1 else (len(ref_groups_local[k]) + shard.CHUNK - 1) // shard.CHUNK))
+        row_off = np.asarray(rows, dtype=np.int32)
+        counts = np.asarray([int(v) for v in ref_sizes], dtype=np.int64)
+        # persistent exchange buffers: every group's chunk sums are written straight into this rank's block of `packed`
+        # (rows past a group's local chunk count are never written and stay zero), ONE all-gather per reference-mean step
+        # carries them, and one kernel turns the gathered rows into the bounds - no per-step torch ops in between
+        bkey = (G, tot, world, tuple(int(v) for v in row_off), tuple(len(g) for g in ref_groups_local))   # stale rows would poison the padding
+        if getattr(self, "_xbuf_key", None) != bkey:
+            self._xbuf_key = bkey
+            self._packed = torch.zeros((max(tot, 1), G), dtype=torch.float64, device=self.tdev)
+            self._gathered = torch.empty((world, max(tot, 1), G), dtype=torch.float64, device=self.tdev) if world > 1 else None
+            self._bounds = [torch.empty((3, G), dtype=torch.float64, device=self.tdev) for _ in range(2)]
 
-        def group_means(src, lists, log):
-            """Per-group means; across ranks ONE all-gather per call carries every group's chunk sums
-            (rank-major, each group zero-padded to its max chunk count - zero chunks do not change a sum)."""
-            parts = [self.group_partial_sums(src, lists[k], log) for k in range(n_grp)]
+        def group_bounds(src, lists, log, slot):
+            for k in range(n_grp):
+                n = int(lists[k].numel())
+                if n:
+                    _lib.check(self.lib.icnv_dev_group_partial_sums_f64(
+                        src.data_ptr(), G, src.stride(0), lists[k].data_ptr(), n, shard.CHUNK, int(bool(log)),
+                        self._packed.data_ptr() + 8 * G * int(row_off[k]), _stream_ptr()))
+            part = self._packed
             if world > 1:
-                tot = int(sum(max_chunks))
-                packed = torch.zeros((tot, G), dtype=torch.float64, device=self.tdev)
-                pos = 0
-                for k in range(n_grp):
-                    if parts[k].shape[0]:
-                        packed[pos:pos + parts[k].shape[0]] = parts[k]
-                    pos += max_chunks[k]
-                gathered = torch.empty((world * tot, G), dtype=torch.float64, device=self.tdev)
-                tdist.all_gather_into_tensor(gathered, packed)
-                g3 = gathered.view(world, tot, G)
-                pos = 0
-                for k in range(n_grp):
-                    parts[k] = g3[:, pos:pos + max_chunks[k], :].reshape(world * max_chunks[k], G).contiguous()
-                    pos += max_chunks[k]
-            return torch.stack([self.combine_partials(parts[k], ref_sizes[k]) for k in range(n_grp)])
+                self._all_gather(self._gathered, self._packed)
+                part = self._gathered
+            b = self._bounds[slot]
+            _lib.check(self.lib.icnv_dev_bounds_from_partials_f64(part.data_ptr(), G, world, max(tot, 1), n_grp,
+                                                                  row_off.ctypes.data, counts.ctypes.data, b[0].data_ptr(),
+                                                                  b[1].data_ptr(), b[2].data_ptr(), _stream_ptr()))
+            return b[0], b[1], b[2]
 
-        b1 = self.bounds(group_means(X, d_groups, apply_log))
+        b1 = group_bounds(X, d_groups, apply_log, 0)
         # pass 1: reference cells only, up to the median centring
         n_ref = int(sum(len(g) for g in ref_groups_local))
         ref_leading = n_ref > 0 and np.array_equal(np.concatenate(ref_groups_local), np.arange(n_ref))
@@ -167,7 +195,7 @@ class Engine:
         if n_ref:
             self.cell_pipeline(X, all_ref, T, chr_start, chr_len, apply_log, b1, threshold, window, 1, None, False,
                                use_bounds, flag)
-        b2 = self.bounds(group_means(T, t_lists, False))
+        b2 = group_bounds(T, t_lists, False, 1)
         return b1, b2, T, n_ref, ref_leading
 
     def smooth_block(self, X, chr_start, chr_len, ref_groups_local, ref_sizes=None, max_chunks=None, apply_log=True,
@@ -324,6 +352,62 @@ class Engine:
                                                        len(cs), off.ctypes.data, idx.ctypes.data, len(groups_local),
                                                        int(window_size), _stream_ptr()))
         return Y
+
+    def median_filter_sharded(self, Xext, n_local, whole_lists, split_slices, chr_start, chr_len, window_size=7, out=None):
+        """apply_median_filtering (R/noise_reduction.R:43-113) on a cell shard.  Xext: (n_local + n_scratch, G) - the
+        shard's columns followed by scratch rows for the halo columns (n_scratch >= 2 r per split list, r = (window_size
+        + 1) / 2).  whole_lists: index lists (LOCAL columns) that live entirely on this rank (tumour subclusters - the
+        planner keeps them whole).  split_slices: for lists cut over ranks in list order (the reference groups, cut at
+        chunk boundaries by plan_shards), this rank's contiguous slice as LOCAL columns (possibly empty).  The r entries
+        either side of a slice are fetched from the neighbouring ranks (one all-gather of every rank's first / last r
+        columns per split list) into the scratch rows; their own outputs land in scratch rows of `out` and are
+        meaningless.  The first n_local rows of the result equal the single-GPU result bit for bit."""
+        import torch.distributed as tdist
+        r = (int(window_size) + 1) // 2
+        G = Xext.shape[1]
+        world = self._world()
+        Y = torch.empty_like(Xext) if out is None else out
+        lists = [np.asarray(v, dtype=np.int32) for v in whole_lists]
+        n_split = len(split_slices)
+        if world == 1 or n_split == 0:
+            lists += [np.asarray(v, dtype=np.int32) for v in split_slices if len(v)]
+            return self.median_filter(Xext, chr_start, chr_len, lists, window_size, out=Y)
+        if Xext.shape[0] < n_local + 2 * r * n_split:
+            raise ValueError("median_filter_sharded: not enough scratch rows behind the shard")
+        rank = tdist.get_rank()
+        # every rank's first / last r columns of every split list, and the slice lengths
+        edge = torch.zeros((n_split, 2, r, G), dtype=torch.float64, device=self.tdev)
+        lens = torch.zeros(n_split, dtype=torch.float64, device=self.tdev)
+        for k, sl in enumerate(split_slices):
+            n = len(sl)
+            lens[k] = n
+            if n:
+                idx = torch.as_tensor(np.asarray(sl, dtype=np.int64), device=self.tdev)
+                h = min(r, n)
+                edge[k, 0, :h] = Xext[idx[:h]]
+                edge[k, 1, r - h:] = Xext[idx[n - h:]]
+        all_edge = torch.empty((world,) + tuple(edge.shape), dtype=torch.float64, device=self.tdev)
+        all_lens = torch.empty((world, n_split), dtype=torch.float64, device=self.tdev)
+        self._all_gather(all_edge, edge)
+        self._all_gather(all_lens, lens)
+        lens_h = all_lens.cpu().numpy().astype(np.int64)
+        pos = n_local
+        for k, sl in enumerate(split_slices):
+            if not len(sl):
+                continue
+            prev, nxt = shard.halo_sources(lens_h[:, k], rank, r)
+            ext = []
+            for q, cnt in prev:          # the last cnt columns of rank q's slice sit at the end of its tail block
+                Xext[pos:pos + cnt] = all_edge[q, k, 1, r - cnt:]
+                ext += list(range(pos, pos + cnt))
+                pos += cnt
+            ext += [int(v) for v in sl]
+            for q, cnt in nxt:
+                Xext[pos:pos + cnt] = all_edge[q, k, 0, :cnt]
+                ext += list(range(pos, pos + cnt))
+                pos += cnt
+            lists.append(np.asarray(ext, dtype=np.int32))
+        return self.median_filter(Xext, chr_start, chr_len, lists, window_size, out=Y)
 
     # ---- CNV region calling on device-resident states (R/inferCNV_HMM.R:706-1087) --------------------------------------
     def state_counts(self, S: torch.Tensor, groups_local) -> torch.Tensor:

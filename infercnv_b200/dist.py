@@ -58,8 +58,10 @@ def split_chunk_aligned(n: int, world: int, chunk: int = CHUNK) -> list[tuple[in
     return out
 
 
-def plan_shards(n_cells: int, ref_groups: list[np.ndarray], world: int) -> list[ShardPlan]:
-    """Partition the cells of a run over `world` ranks."""
+def plan_shards(n_cells: int, ref_groups: list[np.ndarray], world: int, other_atoms=None) -> list[ShardPlan]:
+    """Partition the cells of a run over `world` ranks.  other_atoms (optional): index lists that partition the
+    non-reference cells and must each stay whole on one rank (tumour subclusters: a subcluster's cell order is the
+    median filter's window, R/noise_reduction.R:60-75); consecutive atoms go to consecutive ranks."""
     ref_groups = [np.asarray(g, dtype=np.int64) for g in ref_groups]
     is_ref = np.zeros(n_cells, dtype=bool)
     for g in ref_groups:
@@ -78,8 +80,23 @@ def plan_shards(n_cells: int, ref_groups: list[np.ndarray], world: int) -> list[
             want[r % world] += step
             scale_fix -= step
         r += 1
-    bounds = np.concatenate([[0], np.cumsum(want)])
-    other_parts = [others[bounds[r]:bounds[r + 1]] for r in range(world)]
+    if other_atoms is None:
+        bounds = np.concatenate([[0], np.cumsum(want)])
+        other_parts = [others[bounds[r]:bounds[r + 1]] for r in range(world)]
+    else:
+        atoms = [np.asarray(a, dtype=np.int64) for a in other_atoms]
+        if not np.array_equal(np.sort(np.concatenate(atoms)) if atoms else np.zeros(0, np.int64), others):
+            raise ValueError("other_atoms must partition the non-reference cells")
+        other_parts, a = [], 0
+        target = np.cumsum(want)
+        done = 0
+        for r in range(world):
+            mine = []
+            while a < len(atoms) and (r == world - 1 or abs(done + len(atoms[a]) - target[r]) <= abs(done - target[r])):
+                mine.append(atoms[a])
+                done += len(atoms[a])
+                a += 1
+            other_parts.append(np.concatenate(mine) if mine else np.zeros(0, np.int64))
     max_chunks = [max((hi - lo + CHUNK - 1) // CHUNK for lo, hi in c) for c in cuts]
     plans = []
     for r in range(world):
@@ -133,6 +150,33 @@ def plan_list_shards(lists: list[np.ndarray], world: int) -> list[ListShardPlan]
         cells = np.concatenate([lists[k] for k in ids]) if ids else np.zeros(0, np.int64)
         plans.append(ListShardPlan(rank=r, world=world, list_ids=ids, cells=cells))
     return plans
+
+
+def halo_sources(slice_lens, rank: int, r: int):
+    """A list whose entries are spread over ranks as contiguous slices (slice_lens[q] entries on rank q, list order =
+    rank order): which entries does `rank` need from its neighbours so that every window of 2r + 1 consecutive list
+    entries around its own entries is complete?  Returns (prev, nxt): lists of (src_rank, k) meaning "the last k entries
+    of src_rank's slice" (prev, in list order) and "the first k entries" (nxt).  Ranks holding fewer than r entries are
+    walked through.  A rank with an empty slice needs nothing."""
+    if slice_lens[rank] == 0:
+        return [], []
+    prev, need = [], r
+    q = rank - 1
+    while need > 0 and q >= 0:
+        k = min(need, int(slice_lens[q]))
+        if k:
+            prev.insert(0, (q, k))
+            need -= k
+        q -= 1
+    nxt, need = [], r
+    q = rank + 1
+    while need > 0 and q < len(slice_lens):
+        k = min(need, int(slice_lens[q]))
+        if k:
+            nxt.append((q, k))
+            need -= k
+        q += 1
+    return prev, nxt
 
 
 def allgather_partials(local, max_chunks: int):

@@ -684,3 +684,87 @@ ORC_API int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+/* Number of processors the machine offers, NOT what OMP_NUM_THREADS asks for (torchrun exports OMP_NUM_THREADS=1 to
+ * every rank, which would silently turn the CPU arm of bench.py into a one-thread run). */
+ORC_API int orc_num_procs(void) {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
+/* ---- synthetic workload (bench.py's CPU arm): CPU twin of the device generator -------------------------------------
+ * Restates infercnv_b200/csrc/icnv_synth.cu (not a reference function: the workload model of SURVEY section 8d) so that
+ * the CPU arm can draw the same cells without loading the product library.  Every value is a pure function of
+ * (seed, global cell, gene).  Values are counts; libm differences between host and device can only move a count when a
+ * uniform lands within an ulp of a CDF step. */
+static uint64_t syn_mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+static uint64_t syn_hash3(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+    return syn_mix64(syn_mix64(syn_mix64(seed ^ 0x243f6a8885a308d3ull) + a) * 0x9fb21c651e98df25ull + b) ^
+           syn_mix64(c + 0x13198a2e03707344ull);
+}
+static double syn_u01(uint64_t h) { return ((double)(h >> 11) + 1.0) * (1.0 / 9007199254740992.0); }
+static double syn_normal(uint64_t h1, uint64_t h2) {
+    return sqrt(-2.0 * log(syn_u01(h1))) * cos(6.283185307179586476925286766559 * syn_u01(h2));
+}
+
+ORC_API int orc_synth(double *X, int64_t G, const int64_t *cells, int64_t n_cells, int64_t C_total, const int32_t *chr_start,
+                      const int32_t *chr_len, int K, uint64_t seed, int nthreads) {
+    int32_t *chr_of = (int32_t *)calloc((size_t)G, sizeof(int32_t));
+    double *m_g = (double *)malloc(sizeof(double) * (size_t)G);
+    if (!chr_of || !m_g) { free(chr_of); free(m_g); return -1; }
+    for (int k = 0; k < K; ++k)
+        for (int32_t g = chr_start[k]; g < chr_start[k] + chr_len[k] && g < G; ++g) chr_of[g] = k;
+    for (int64_t g = 0; g < G; ++g)
+        m_g[g] = exp(0.5 + syn_normal(syn_hash3(seed, 4, (uint64_t)g, 0), syn_hash3(seed, 4, (uint64_t)g, 1)));
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t ci = 0; ci < n_cells; ++ci) {
+        const uint64_t cell = (uint64_t)cells[ci];
+        const double f_c = exp(0.2 * syn_normal(syn_hash3(seed, 1, cell, 0), syn_hash3(seed, 1, cell, 1)));
+        int ev_chr[3] = {-1, -1, -1};
+        double ev_mul[3] = {1.0, 1.0, 1.0};
+        if ((int64_t)cell >= C_total / 10 && syn_u01(syn_hash3(seed, 2, cell, 0)) < 0.3)
+            for (int e = 0; e < 3; ++e) {
+                const uint64_t h = syn_hash3(seed, 3, cell, (uint64_t)e);
+                ev_chr[e] = (int)(h % (uint64_t)K);
+                ev_mul[e] = ((h >> 40) & 1ull) ? 1.5 : 0.5;
+            }
+        double *col = X + G * ci;
+        for (int64_t g = 0; g < G; ++g) {
+            double cnv = 1.0;
+            for (int e = 0; e < 3; ++e)
+                if (chr_of[g] == ev_chr[e]) cnv = ev_mul[e];
+            const double mean = m_g[g] * f_c * cnv;
+            double prod = 1.0;
+            for (int i = 0; i < 10; ++i) prod *= syn_u01(syn_hash3(seed, 5 + (uint64_t)i, cell, (uint64_t)g));
+            const double lambda = -log(prod) * (mean * 0.1);
+            double x;
+            if (lambda < 12.0) {
+                const double u = syn_u01(syn_hash3(seed, 20, cell, (uint64_t)g));
+                double pmf = exp(-lambda), cdf = pmf;
+                int k = 0;
+                while (u > cdf && k < 64) {
+                    ++k;
+                    pmf *= lambda / (double)k;
+                    cdf += pmf;
+                }
+                x = (double)k;
+            } else {
+                const double z = syn_normal(syn_hash3(seed, 21, cell, (uint64_t)g), syn_hash3(seed, 22, cell, (uint64_t)g));
+                x = floor(lambda + sqrt(lambda) * z + 0.5);
+                if (x < 0.0) x = 0.0;
+            }
+            col[g] = x;
+        }
+    }
+    free(chr_of);
+    free(m_g);
+    return 0;
+}

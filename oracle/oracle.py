@@ -88,7 +88,26 @@ def groups_to_csr(groups) -> tuple[np.ndarray, np.ndarray]:
 
 
 def max_threads() -> int:
+    """Threads OpenMP would use by default (honours OMP_NUM_THREADS)."""
     return int(lib().orc_max_threads())
+
+
+def num_procs() -> int:
+    """Processors of the machine, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)."""
+    return int(lib().orc_num_procs())
+
+
+def synth(G, chr_start, chr_len, cells_global, C_total, seed, nthreads=1) -> np.ndarray:
+    """CPU twin of the device workload generator (infercnv_b200/csrc/icnv_synth.cu): (G, n) Fortran array for the given
+    GLOBAL cell indices.  Lets bench.py's CPU arm draw its sample without loading the product library."""
+    cells = np.ascontiguousarray(cells_global, dtype=np.int64)
+    cs, cl = _i32(chr_start), _i32(chr_len)
+    X = np.empty((int(G), len(cells)), dtype=np.float64, order="F")
+    rc = lib().orc_synth(_dp(X), ct.c_int64(int(G)), cells.ctypes.data_as(ct.POINTER(ct.c_int64)), ct.c_int64(len(cells)),
+                         ct.c_int64(int(C_total)), _ip(cs), _ip(cl), len(cs), ct.c_uint64(int(seed)), int(nthreads))
+    if rc:
+        raise MemoryError("orc_synth")
+    return X
 
 
 def pnorm_upper_log(z) -> np.ndarray:

@@ -82,7 +82,7 @@ def build(force: bool = False) -> str:
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
     cmd = [gxx, "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-D__CUDACC__", "-DICNV_EMU", "-Wall", "-Wno-unknown-pragmas",
            "-Wno-attributes", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-mfma",
-           "-ffp-contract=off", "-rdynamic", "-fno-omit-frame-pointer", "-I", os.path.join(HERE, "emu"), "-I", CSRC, "-o", OUT, *files]
+           "-ffp-contract=off", "-pthread", "-rdynamic", "-fno-omit-frame-pointer", "-I", os.path.join(HERE, "emu"), "-I", CSRC, "-o", OUT, *files]
     subprocess.check_call(cmd)
     return OUT
 

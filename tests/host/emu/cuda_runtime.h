@@ -107,6 +107,22 @@ static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcp
     return cudaSuccess;
 }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+// page-locked host memory: plain allocations; every caller pointer reports as pageable, so the host pipeline's staging
+// ring (pageable caller memory -> pinned slab -> device) is the path the emulated tests take
+enum { cudaHostAllocPortable = 1 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes {
+    cudaMemoryType type;
+};
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) {
+    *p = malloc(n);
+    if (!*p) return cudaErrorMemoryAllocation;
+    memset(*p, 0xA5, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 1; return cudaSuccess; }

@@ -192,14 +192,18 @@ def test_smooth_block_padded_q_layout_is_bit_identical(api, monkeypatch):
             out = {}
             for flag in ("1", "0"):
                 monkeypatch.setenv("ICNV_CELL_PADQ", flag)
+                api.reinit()   # tuning switches are read once, at icnv_init
                 out[flag] = api.smooth_block(X, cs, lens, refs, apply_log=True, threshold=3.0, window_length=w)
             assert np.array_equal(out["1"], out["0"]), (G, w)
             want = orc.smooth_block(X, cs, lens, refs, window=w)
             assert np.max(np.abs(out["1"] - want) / np.abs(want)) < 1e-10   # prefix sums over up to 2900 genes
         for flag in ("1", "0"):
             monkeypatch.setenv("ICNV_CELL_PADQ", flag)
+            api.reinit()
             out[flag] = api.smooth(np.log2(X + 1.0), cs, lens, 51)
         assert np.array_equal(out["1"], out["0"])
+    monkeypatch.delenv("ICNV_CELL_PADQ")
+    api.reinit()
 
 
 def test_smooth_block_benchmark_layout_unrolled_slices(api, monkeypatch):
@@ -219,7 +223,11 @@ def test_smooth_block_benchmark_layout_unrolled_slices(api, monkeypatch):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
+        api.reinit()   # tuning switches are read once, at icnv_init
         out[name] = api.smooth_block(X, cs, lens, refs, apply_log=True, threshold=3.0, window_length=101)
+    for k in ("ICNV_CELL_LFIX", "ICNV_CELL_PADQ"):
+        monkeypatch.delenv(k, raising=False)
+    api.reinit()
     assert np.array_equal(out["unrolled"], out["generic"])
     assert np.array_equal(out["unrolled"], out["pingpong"])
     want = orc.smooth_block(X, cs, lens, refs)
@@ -499,8 +507,10 @@ def test_median_filter_key_network_variant_is_exact(api, monkeypatch):
     for name, X in cases.items():
         X = np.asfortranarray(X)
         monkeypatch.setenv("ICNV_MF_KERNEL", "2")
+        api.reinit()   # tuning switches are read once, at icnv_init
         got = api.median_filter(X, cs, lens, groups, 7)
         monkeypatch.delenv("ICNV_MF_KERNEL")
+        api.reinit()
         ref = api.median_filter(X, cs, lens, groups, 7)
         want = orc.median_filter(X, cs, lens, groups, 7, nthreads=orc.max_threads())
         assert np.array_equal(got, ref), name
