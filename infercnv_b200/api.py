@@ -240,12 +240,12 @@ def viterbi(X, chr_start, chr_len, Pi, delta, mean, sd, groups=None, want_margin
     return (states, margins) if want_margins else states
 
 
-def median_filter(X, chr_start, chr_len, groups, window_size=7) -> np.ndarray:
+def median_filter(X, chr_start, chr_len, groups, window_size=7, out=None) -> np.ndarray:
     X = _f64(X)
     G, C = X.shape
     cs, cl = _i32(chr_start), _i32(chr_len)
     off, idx = groups_to_csr(groups)
-    Y = np.empty_like(X, order="F")
+    Y = np.empty_like(X, order="F") if out is None else out
     _lib.check(_lib.load().icnv_median_filter_f64(_p(X), _p(Y), G, C, _p(cs), _p(cl), len(cs), _p(off), _p(idx),
                                                   len(groups), int(window_size)))
     return Y

@@ -21,7 +21,6 @@ from . import api
 
 log = logging.getLogger("infercnv_b200")  # the R functions log through futile.logger's flog.info
 
-CNV_LEVELS = ["cnv:0.01", "cnv:0.5", "cnv:1", "cnv:1.5", "cnv:2", "cnv:3"]  # R/inferCNV_HMM.R:244-256
 
 
 @dataclass
@@ -230,24 +229,7 @@ def apply_median_filtering(infercnv_obj: Infercnv, window_size: int = 7, on_obse
 
 # ---- HMM -----------------------------------------------------------------------------------------------
 
-def get_HMM(cnv_mean_sd: dict, t: float):
-    """.get_HMM, R/inferCNV_HMM.R:230-265: (state_transitions, delta, mean[6], sd[6])."""
-    Pi = np.full((6, 6), t, dtype=np.float64, order="F")
-    np.fill_diagonal(Pi, 1 - 5 * t)
-    delta = np.array([t, t, 1 - 5 * t, t, t, t])
-    mean = np.array([cnv_mean_sd[k]["mean"] for k in CNV_LEVELS], dtype=np.float64)
-    sd = np.array([cnv_mean_sd[k]["sd"] for k in CNV_LEVELS], dtype=np.float64)
-    return Pi, delta, mean, sd
-
-
-def i3HMM_get_HMM(sd_trend: dict, t: float, i3_p_val: float = 0.05, use_KS: bool = False):
-    """.i3HMM_get_HMM, R/inferCNV_i3HMM.R:99-156 (diagonal 1-5t as written there)."""
-    Pi = np.full((3, 3), t, dtype=np.float64, order="F")
-    np.fill_diagonal(Pi, 1 - 5 * t)
-    delta = np.array([t, 1 - 5 * t, t])
-    mu, sigma = sd_trend["mu"], sd_trend["sigma"]
-    d = sd_trend["KS_delta"] if use_KS else sd_trend["mean_delta"]
-    return Pi, delta, np.array([mu - d, mu, mu + d]), np.array([sigma] * 3)
+from .hmm import CNV_LEVELS, get_HMM, i3HMM_get_HMM  # noqa: E402,F401  (parameter tables live in hmm.py)
 
 
 def i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj: Infercnv, i3_p_val: float = 0.05) -> dict:
