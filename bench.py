@@ -276,13 +276,54 @@ def i3_model(mu, sigma):
 
 
 # ---- CPU arm --------------------------------------------------------------------------------------------------------
-def cpu_sample(args, cfg, G, C_total, seed, n_want):
+def usable_cpus() -> int:
+    """Host threads this process may really run at once: the affinity mask, cut by the container's CPU quota (cgroup v2
+    cpu.max / v1 cfs quota).  omp_get_num_procs() alone over-reports inside a quota-limited container, and 2 x the quota
+    in spinning OpenMP threads is many times slower than the quota itself; torchrun's OMP_NUM_THREADS=1 under-reports."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def pick_cpu_threads(cfg, G, C_total, seed, args):
+    """All the host threads the port can USE: time one pass on a small sample at n, n/2 and n/4 threads (n = usable CPUs)
+    and keep the fastest - SMT siblings and memory bandwidth make 'every logical CPU' the slowest choice on some boxes."""
+    n = usable_cpus()
+    cands = sorted({max(1, n), max(1, n // 2), max(1, n // 4)}, reverse=True)
+    if len(cands) == 1:
+        return cands[0], {cands[0]: None}
+    X, cs, cl, ref_local, lists, _, _ = cpu_sample(args, cfg, G, C_total, seed, min(C_total, 8 * n), n)
+    rates = {}
+    for t in cands:
+        step = cpu_step_fn(cfg, X, cs, cl, ref_local, lists, t)
+        t0 = time.perf_counter()
+        step()
+        rates[t] = G * X.shape[1] / (time.perf_counter() - t0)
+    best = max(rates, key=rates.get)
+    return best, rates
+
+
+def cpu_sample(args, cfg, G, C_total, seed, n_want, nt=None):
     """A bounded sample of the workload for the CPU arm: (X, reference groups, median-filter lists) in sample-local
     columns.  i6 configs: every stride-th cell.  c4: a 10 % slice of reference cells plus whole subclusters, so that the
     median filter sees real blocks.  The generator is the C twin of the device one (oracle/, no product library)."""
     from oracle import oracle as orc
     cs, cl = chr_layout(G)
-    nt = orc.num_procs()
+    nt = nt or usable_cpus()
     refs_g = ref_groups_global(C_total)
     lists = None
     if not cfg["median_filter"]:
@@ -384,9 +425,9 @@ def run_reference(args):
                      "note": "the reference's own R functions source()d from its R/ directory; this path ignores num_threads (1 core)"})
         print(json.dumps(base))
         return
-    nt = orc.num_procs()
+    nt, rates = pick_cpu_threads(cfg, G, C_total, seed, args)
     n_want = min(C_total, max(args.ref_sample_cells, 32 * nt))   # >= 32 cells per thread keeps every core fed
-    X, cs, cl, ref_local, lists, what, nt = cpu_sample(args, cfg, G, C_total, seed, n_want)
+    X, cs, cl, ref_local, lists, what, nt = cpu_sample(args, cfg, G, C_total, seed, n_want, nt)
     step = cpu_step_fn(cfg, X, cs, cl, ref_local, lists, nt)
     for _ in range(args.warmup):
         step()
@@ -396,7 +437,8 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     value = G * X.shape[1] / dt
     base.update({"value": value, "ms_per_step": dt * 1e3,
-                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": f"{what} x {G} genes per step"},
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": f"{what} x {G} genes per step",
+                                  "usable_cpus": usable_cpus(), "thread_count_trial_cell_genes_per_s": {str(k): v for k, v in rates.items()}},
                  "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "note": "reference = interpreted R (no Rscript + reference sources on this box); this arm is the C restatement in "
                          "oracle/ with OpenMP over cells on every host core (thread count set explicitly, not from OMP_NUM_THREADS) "
@@ -406,10 +448,9 @@ def run_reference(args):
 
 def cpu_baseline(args, cfg, G, C_total, seed):
     """Oracle port on the host cores over a bounded sample (rank 0, N = 1 only), ~10 s."""
-    from oracle import oracle as orc
-    nt = orc.num_procs()
+    nt, rates = pick_cpu_threads(cfg, G, C_total, seed, args)
     n_want = min(C_total, max(args.ref_sample_cells, 32 * nt))
-    X, cs, cl, ref_local, lists, what, nt = cpu_sample(args, cfg, G, C_total, seed, n_want)
+    X, cs, cl, ref_local, lists, what, nt = cpu_sample(args, cfg, G, C_total, seed, n_want, nt)
     step = cpu_step_fn(cfg, X, cs, cl, ref_local, lists, nt)
     step()
     reps, t_total = 0, 0.0
@@ -419,7 +460,8 @@ def cpu_baseline(args, cfg, G, C_total, seed):
         t_total += time.perf_counter() - t0
         reps += 1
     return {"value": reps * G * X.shape[1] / t_total, "unit": UNIT, "cores": nt, "kind": "port",
-            "sample": f"{what} x {G} genes, {reps} passes, {t_total:.1f} s"}
+            "sample": f"{what} x {G} genes, {reps} passes, {t_total:.1f} s", "usable_cpus": usable_cpus(),
+            "thread_count_trial_cell_genes_per_s": {str(k): v for k, v in rates.items()}}
 
 
 # ---- GPU arm --------------------------------------------------------------------------------------------------------

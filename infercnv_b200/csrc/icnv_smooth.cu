@@ -248,195 +248,6 @@ __device__ __forceinline__ void block_red2d(Red<NW> &r, int &phase, double a, do
     phase ^= 1;
 }
 
-// ---- exact median of the n values spread over the CTA's registers -------------------------------
-// Every thread holds `len` values in y[0..len).  Returns median per R's median.default: the middle
-// order statistic for odd n, the mean of the two middle ones for even n (ops.R:2098).
-//
-// Selection by counting: a bracket (lo, hi] known to contain both middle order statistics is
-// narrowed with two pivots per round (one pass over the registers, one block reduction).  Pivots
-// come from linear interpolation of the empirical CDF inside the bracket; a round that fails to
-// halve the bracket is followed by a bisection round in key space, which bounds the worst case.
-// Once <= CAND_MAX values remain they are gathered into shared memory and ranked directly.
-template <int NT, int LMAX>
-__device__ __forceinline__ double block_median(const double (&y)[LMAX], int len, int n, Red<NT / 32> &red, int &phase,
-                               double *cand, int *cand_n) {
-    constexpr int NW = NT / 32;
-    const int kA = (n - 1) >> 1, kB = n >> 1;
-
-    // start: mean / sd bracket guess from one pass (sum, sum of squares, min, max) and one reduction.
-    // The sd only places the first two pivots, so the one-pass formula's cancellation is harmless.
-    double s1 = 0.0, s2 = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-#pragma unroll
-    for (int t = 0; t < LMAX; ++t)
-        if (t < len) {
-            double v = y[t];
-            s1 += v;
-            s2 = fma(v, v, s2);
-            mn = fmin(mn, v);
-            mx = fmax(mx, v);
-        }
-    double S1, S2, MN, MX;
-    {
-        s1 = warp_sum_d(s1);
-        s2 = warp_sum_d(s2);
-        mn = warp_min_d(mn);
-        mx = warp_max_d(mx);
-        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (lane == 0) {
-            red.d[phase][0][w] = s1;
-            red.d[phase][1][w] = s2;
-            red.d[phase ^ 1][0][w] = mn;   // both halves of the scratch: safe, the previous reduction
-            red.d[phase ^ 1][1][w] = mx;   // that used them is two barriers behind
-        }
-        __syncthreads();
-        double a0 = (lane < NW) ? red.d[phase][0][lane] : 0.0;
-        double a1 = (lane < NW) ? red.d[phase][1][lane] : 0.0;
-        double a2 = (lane < NW) ? red.d[phase ^ 1][0][lane] : DBL_MAX;
-        double a3 = (lane < NW) ? red.d[phase ^ 1][1][lane] : -DBL_MAX;
-        S1 = warp_sum_d(a0);
-        S2 = warp_sum_d(a1);
-        MN = warp_min_d(a2);
-        MX = warp_max_d(a3);
-        __syncthreads();  // scratch of both phases is free again
-    }
-    if (!(MN < MX)) return MN;  // all equal (or n == 1)
-    const double mean = S1 / (double)n;
-    double var = S2 / (double)n - mean * mean;
-    const double sd = var > 0.0 ? sqrt(var) : 0.0;
-
-    // invariant: #(x <= lo) <= kA  and  #(x <= hi) >= kB + 1.  lo starts one ulp below the minimum.
-    double lo = double_of_key(key_of(MN) - 1ull), hi = MX;
-    if (!(lo < MN)) lo = double_of_key(key_of(MN) - 2ull);  // MN == +0.0: one key below is -0.0 == MN
-    int Flo = 0, Fhi = n;
-    double p1 = mean - 0.35 * sd, p2 = mean + 0.35 * sd;
-    bool force_bisect = false;
-    double a_res = 0.0, b_res = 0.0;
-    bool done = false;
-
-    if (threadIdx.x == 0) atomicAdd(&g_stats[1], 1ull);
-    for (int round = 0; round < 160 && !done; ++round) {
-        int m = Fhi - Flo;
-        if (m <= CAND_MAX) break;
-        if (threadIdx.x == 0) atomicAdd(&g_stats[0], 1ull);
-        // ---- choose pivots strictly inside (lo, hi) ------------------------------------------
-        const double lo_eff = lo;
-        unsigned long long klo = key_of(lo), khi = key_of(hi);
-        if (khi - klo < 2ull) {  // no double strictly between: every candidate equals hi
-            a_res = b_res = hi;
-            done = true;
-            break;
-        }
-        double pmid = double_of_key(klo + ((khi - klo) >> 1));
-        if (round > 0) {
-            if (force_bisect) {
-                p1 = p2 = pmid;
-            } else {
-                // pivot placement only has to be identical in every thread, not accurate: float math
-                const float mf = (float)m;
-                const float f = ((float)(kA - Flo) + 0.5f * (float)(kB - kA) + 0.5f) / mf;
-                float wfrac = (3.0f * sqrtf(mf) + 8.0f) / mf;
-                if (wfrac > 0.5f) wfrac = 0.5f;
-                const double span = hi - lo_eff;
-                const double pc = lo_eff + span * (double)f;
-                p1 = pc - span * (double)(0.5f * wfrac);
-                p2 = pc + span * (double)(0.5f * wfrac);
-            }
-        }
-        if (!(p1 > lo && p1 < hi)) p1 = pmid;
-        if (!(p2 > lo && p2 < hi)) p2 = pmid;
-        if (p1 > p2) {
-            double t = p1;
-            p1 = p2;
-            p2 = t;
-        }
-        // ---- count ------------------------------------------------------------------------------
-        // y[] is padded with +inf beyond len (see the caller), so no per-element length test is needed
-        int c1 = 0, c2 = 0;
-#pragma unroll
-        for (int t = 0; t < LMAX; ++t) {
-            c1 += (y[t] <= p1) ? 1 : 0;
-            c2 += (y[t] <= p2) ? 1 : 0;
-        }
-        int C1, C2;
-        block_sum2i<NW>(red, phase, c1, c2, C1, C2);
-        // ---- narrow -----------------------------------------------------------------------------
-        double split = 0.0;
-        bool do_split = false;
-        if (C1 >= kB + 1) {
-            hi = p1;
-            Fhi = C1;
-        } else if (C1 > kA) {
-            split = p1;
-            do_split = true;
-        } else if (C2 >= kB + 1) {
-            lo = p1;
-            Flo = C1;
-            hi = p2;
-            Fhi = C2;
-        } else if (C2 > kA) {
-            split = p2;
-            do_split = true;
-        } else {
-            lo = p2;
-            Flo = C2;
-        }
-        if (do_split) {  // s_kA <= split < s_kB: neighbours of the split point
-            double below = -DBL_MAX, above = DBL_MAX;
-#pragma unroll
-            for (int t = 0; t < LMAX; ++t) {
-                double v = y[t];
-                if (v <= split) below = fmax(below, v);
-                else above = fmin(above, v);  // +inf padding never lowers `above`
-            }
-            block_red2d<NW, 2>(red, phase, below, above, a_res, b_res);
-            done = true;
-            break;
-        }
-        int m_new = Fhi - Flo;
-        force_bisect = (2 * m_new > m) && !force_bisect;
-    }
-    if (done) {
-        if (threadIdx.x == 0) atomicAdd(&g_stats[2], 1ull);
-        return (a_res + b_res) * 0.5;
-    }
-    if (threadIdx.x == 0) atomicAdd(&g_stats[3], 1ull);
-
-    // ---- gather the <= CAND_MAX candidates in (lo, hi] and rank them --------------------------------
-    if (threadIdx.x == 0) *cand_n = 0;
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < LMAX; ++t) {
-        double v = y[t];
-        if (v > lo && v <= hi) {  // hi is finite: padding excluded
-            int slot = atomicAdd(cand_n, 1);
-            if (slot < CAND_MAX) cand[slot] = v;
-        }
-    }
-    __syncthreads();
-    int m = *cand_n;
-    if (m > CAND_MAX) m = CAND_MAX;  // cannot happen (m == Fhi - Flo); keeps the loop bounded
-    const int ra = kA - Flo, rb = kB - Flo;
-    {   // one warp per candidate: the 32 lanes compare it with all (<= 64) candidates, one redux gives its rank
-        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const double u1 = (lane < m) ? cand[lane] : INFINITY;
-        const double u2 = (lane + 32 < m) ? cand[lane + 32] : INFINITY;
-        for (int i = w; i < m; i += NW) {
-            const double v = cand[i];
-            int cnt = ((u1 < v) || (u1 == v && lane < i)) ? 1 : 0;
-            cnt += ((u2 < v) || (u2 == v && lane + 32 < i)) ? 1 : 0;
-            const int rank = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) {
-                if (rank == ra) cand[CAND_MAX] = v;
-                if (rank == rb) cand[CAND_MAX + 1] = v;
-            }
-        }
-    }
-    __syncthreads();
-    double a = cand[CAND_MAX], b = cand[CAND_MAX + 1];
-    __syncthreads();  // cand is reused by the next cell
-    return (a + b) * 0.5;
-}
-
 #include "icnv_math_tables.inc"
 __device__ double g_log_tab[128][2];
 __device__ double g_exp_tab[128];
@@ -607,290 +418,6 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-// One CTA per cell, persistent over cells.  Per cell:
-//   A  column arrives by bulk copy (issued one cell ahead); element-wise steps applied while moving
-//      it from the landing buffer to the work buffer (coalesced, bounds read coalesced from L2)
-//   B  pyramid smooth via two prefix sums per chromosome: with P = prefix(x), Q = prefix(P),
-//      sum_{|d|<=h} (h+1-|d|) x[i+d] = (Q[i+h] - Q[i-1]) - (Q[i-1] - Q[i-h-2]), zero padding outside the
-//      chromosome being a constant / linear continuation of P / Q.  O(1) work per gene for any window.
-//   C  per-cell median by counting selection on register-resident values
-//   D  centred values back to shared memory, second reference subtraction + 2^x fused into the one
-//      coalesced write of the column
-// LANDING: the column arrives by bulk copy in a second shared-memory buffer one cell ahead (needs 2 x G x 8 B);
-// without it (G too large for two buffers) stage A reads global memory directly.
-template <int NT, int LMAX, bool LANDING>
-__global__ void __launch_bounds__(NT, 1) cell_pipeline_kernel(const CellParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NW = NT / 32;
-    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);   // log2 / exp2 tables first: 16-byte aligned by construction
-    double *etab = reinterpret_cast<double *>(ltab + 128);
-    double *raw = etab + 128;                                // landing buffer of the bulk copy
-    double *work = LANDING ? raw + p.s_elems : raw;          // x' -> Q -> centred output
-    double *invD = work + p.s_elems;                         // 1/D for one-sided truncation, h+1 entries
-    double *ptot = invD + (p.h + 2);                         // per chromosome: P and Q at its last gene
-    double *qtot = ptot + p.K;
-    double *tails = qtot + p.K;                              // [2][NW] warp tails of the two scans
-    double *cand = tails + 2 * NW;                           // CAND_MAX + 2
-    Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
-    int *cand_n = reinterpret_cast<int *>(&red + 1);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cand_n + 2);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = (int)p.G;
-    const int h = p.h;
-    const bool do_smooth = p.window >= 2;
-    int phase = 0;
-    unsigned parity = 0;
-
-    if (do_smooth) {
-        double full = (double)(h + 1) * (double)(h + 1);
-        for (int r = tid; r <= h; r += NT) invD[r] = 1.0 / (full - 0.5 * (double)r * (double)(r + 1));
-    }
-    if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < 128; i += NT) {
-        ltab[i] = make_double2(g_log_tab[i][0], g_log_tab[i][1]);
-        etab[i] = g_exp_tab[i];
-    }
-    const Seg seg = p.segs[tid];
-    const int lane_first = max(seg.tfirst - (tid - lane), 0);  // first lane of my chromosome inside this warp
-    const int wfirst = seg.tfirst >> 5;                        // warp holding the chromosome's first thread
-    bool bad = false;
-    const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
-    // bulk copies need 16-byte aligned source / size; otherwise the column is loaded by the threads
-    auto tma_ok = [&](int64_t col) {
-        return LANDING && ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
-    };
-    __syncthreads();  // barrier initialised, invD ready
-    if (tid == 0 && (int64_t)blockIdx.x < p.n_cols) {
-        const int64_t col0 = p.cols ? (int64_t)p.cols[blockIdx.x] : (int64_t)blockIdx.x;
-        if (tma_ok(col0)) {
-            fence_proxy_async();
-            mbar_expect_tx(bar, col_bytes);
-            bulk_g2s(raw, p.X + p.ldx * col0, col_bytes, bar);
-        }
-    }
-
-    for (int64_t ci = blockIdx.x; ci < p.n_cols; ci += gridDim.x) {
-        const int64_t col = p.cols ? (int64_t)p.cols[ci] : ci;
-        double *__restrict__ dst = p.Y + p.ldy * ci;
-        // ---- stage A ------------------------------------------------------------------------------------
-        if (tma_ok(col)) {
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-        } else if (LANDING) {
-            const double *__restrict__ src = p.X + p.ldx * col;
-            for (int g = tid; g < G; g += NT) raw[g] = src[g];
-            __syncthreads();
-        }
-        const double *__restrict__ rawsrc = LANDING ? raw : (p.X + p.ldx * col);
-        if (p.apply_log && p.lo1 && p.threshold > 0.0) {
-            // the fused-block configuration: log2(x+1) -> dead-band subtract -> clamp, no per-element mode tests
-            // groups of four genes NT apart as one straight-line block, then two, then one (see stage_a_group)
-            const double thr = p.threshold;
-            int g0 = tid;
-            for (; g0 + 3 * NT < G; g0 += 4 * NT) stage_a_group<4, NT>(rawsrc, work, p.lo1, p.hi1, g0, thr, ltab, bad);
-            if (g0 + NT < G) {
-                stage_a_group<2, NT>(rawsrc, work, p.lo1, p.hi1, g0, thr, ltab, bad);
-                g0 += 2 * NT;
-            }
-            if (g0 < G) stage_a_group<1, NT>(rawsrc, work, p.lo1, p.hi1, g0, thr, ltab, bad);
-        } else {
-        for (int g0 = tid; g0 < G; g0 += 4 * NT) {
-                double v[4], lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    const bool in = g < G;
-                    v[u] = in ? rawsrc[g] : 0.0;
-                    lo[u] = (in && p.lo1) ? p.lo1[g] : ((in && p.mid1) ? p.mid1[g] : 0.0);
-                    hi[u] = (in && p.hi1) ? p.hi1[g] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    if (g < G) {
-                        double x = v[u];
-                        if (!is_finite_d(x)) bad = true;
-                        if (p.apply_log) x = fast_log2_1p(x, ltab);
-                        if (p.lo1) x = sub_bounds(x, lo[u], hi[u]);
-                        else if (p.mid1) x = x - lo[u];
-                        if (p.threshold > 0.0) x = clamp_sym(x, p.threshold);
-                        work[g] = x;
-                    }
-                }
-            }
-        }
-        __syncthreads();  // landing buffer consumed, work buffer complete
-        if (tid == 0) {   // fetch the next cell's column while this one is processed
-            const int64_t cn = ci + gridDim.x;
-            if (cn < p.n_cols) {
-                const int64_t coln = p.cols ? (int64_t)p.cols[cn] : cn;
-                if (tma_ok(coln)) {
-                    fence_proxy_async();
-                    mbar_expect_tx(bar, col_bytes);
-                    bulk_g2s(raw, p.X + p.ldx * coln, col_bytes, bar);
-                }
-            }
-        }
-
-        // ---- stage B ------------------------------------------------------------------------------------
-        double y[LMAX];
-        const int len = seg.len, a0 = seg.start, cs = seg.cs, ce = seg.ce;
-#pragma unroll
-        for (int q = 0; q < LMAX; ++q) y[q] = (q < len) ? work[a0 + q] : 0.0;
-        if (do_smooth) {
-            // P = inclusive prefix of x inside the chromosome
-#pragma unroll
-            for (int q = 1; q < LMAX; ++q) y[q] += y[q - 1];
-            double tot = y[LMAX - 1];
-            double inc = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                double t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane - d >= lane_first) inc += t;
-            }
-            double exc = __shfl_up_sync(0xffffffffu, inc, 1);
-            if (lane <= lane_first) exc = 0.0;
-            if (lane == 31) tails[warp] = inc;
-            __syncthreads();
-            double carry = 0.0;
-            for (int u = wfirst; u < warp; ++u) carry += tails[u];
-            const double offP = exc + carry;
-            const double plast = tot + offP;  // P at the segment's last gene (the padding adds zeros)
-#pragma unroll
-            for (int q = 0; q < LMAX; ++q) y[q] = (q < len) ? (y[q] + offP) : 0.0;
-            // Q = inclusive prefix of P
-#pragma unroll
-            for (int q = 1; q < LMAX; ++q) y[q] += y[q - 1];
-            tot = y[LMAX - 1];
-            inc = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                double t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane - d >= lane_first) inc += t;
-            }
-            exc = __shfl_up_sync(0xffffffffu, inc, 1);
-            if (lane <= lane_first) exc = 0.0;
-            if (lane == 31) tails[NW + warp] = inc;
-            __syncthreads();  // also: every thread has its x' in registers, work[] may be overwritten
-            carry = 0.0;
-            for (int u = wfirst; u < warp; ++u) carry += tails[NW + u];
-            const double offQ = exc + carry;
-            const double qlast = tot + offQ;
-#pragma unroll
-            for (int q = 0; q < LMAX; ++q)
-                if (q < len) work[a0 + q] = y[q] + offQ;
-            if (len > 0 && a0 + len == ce) {
-                ptot[seg.chr] = plast;
-                qtot[seg.chr] = qlast;
-            }
-            __syncthreads();
-            const int n = ce - cs;
-            if (n >= 2) {
-                const double Pn = ptot[seg.chr], Qn = qtot[seg.chr];
-                const double invD0 = 1.0 / ((double)(h + 1) * (double)(h + 1));
-                const double *Qc = work + cs;
-                auto Qt = [&](int j) -> double {
-                    if (j < 0) return 0.0;
-                    if (j <= n - 1) return Qc[j];
-                    return Qn + (double)(j - (n - 1)) * Pn;
-                };
-#pragma unroll
-                for (int q = 0; q < LMAX; ++q) {
-                    if (q < len) {
-                        const int j = a0 + q - cs;
-                        double out;
-                        if (j - h - 2 >= 0 && j + h <= n - 1) {  // window strictly inside the chromosome
-                            const double qb = Qc[j - 1];
-                            out = ((Qc[j + h] - qb) - (qb - Qc[j - h - 2])) * invD0;
-                        } else {
-                            const double qa = Qt(j + h), qb = Qt(j - 1), qc = Qt(j - h - 2);
-                            const double N = (qa - qb) - (qb - qc);
-                            int rl = h - j;
-                            rl = rl > 0 ? rl : 0;
-                            int rr = h - (n - 1 - j);
-                            rr = rr > 0 ? rr : 0;
-                            if (rl == 0 || rr == 0) {
-                                out = N * invD[rl + rr];
-                            } else {  // chromosome shorter than the window: both ends truncated
-                                double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
-                                           0.5 * (double)rr * (double)(rr + 1);
-                                out = N / D;
-                            }
-                        }
-                        y[q] = out;
-                    } else {
-                        y[q] = 0.0;
-                    }
-                }
-            } else {
-                // single-gene chromosome: left untouched (ops.R:2417); its prefix sum is the value itself
-#pragma unroll
-                for (int q = 0; q < LMAX; ++q) y[q] = (q < len) ? plast : 0.0;
-            }
-        }
-
-        // ---- stage C ------------------------------------------------------------------------------------
-        double centre = 0.0;
-        if (p.center == 1) {
-#pragma unroll
-            for (int q = 0; q < LMAX; ++q)
-                if (q >= len) y[q] = INFINITY;  // padding never counts as <= pivot
-            centre = block_median<NT, LMAX>(y, len, G, red, phase, cand, cand_n);
-        } else if (p.center == 2) {
-            double s1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < LMAX; ++q)
-                if (q < len) s1 += y[q];
-            double S1, dummy;
-            block_red2d<NW, 1>(red, phase, s1, 0.0, S1, dummy);
-            centre = S1 / (double)G;
-        }
-        __syncthreads();  // every thread is done reading Q from work[]
-#pragma unroll
-        for (int q = 0; q < LMAX; ++q)
-            if (q < len) work[a0 + q] = y[q] - centre;
-        __syncthreads();
-
-        // ---- stage D ------------------------------------------------------------------------------------
-        if (p.lo2 && p.apply_exp2) {
-            int g0 = tid;   // work[] already holds the centred values
-            for (; g0 + 3 * NT < G; g0 += 4 * NT) stage_d_group<4, NT>(work, dst, p.lo2, p.hi2, g0, 0.0, etab);
-            if (g0 + NT < G) {
-                stage_d_group<2, NT>(work, dst, p.lo2, p.hi2, g0, 0.0, etab);
-                g0 += 2 * NT;
-            }
-            if (g0 < G) stage_d_group<1, NT>(work, dst, p.lo2, p.hi2, g0, 0.0, etab);
-        } else {
-        for (int g0 = tid; g0 < G; g0 += 4 * NT) {
-                double v[4], lo[4], hi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    const bool in = g < G;
-                    v[u] = in ? work[g] : 0.0;
-                    lo[u] = (in && p.lo2) ? p.lo2[g] : ((in && p.mid2) ? p.mid2[g] : 0.0);
-                    hi[u] = (in && p.hi2) ? p.hi2[g] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int g = g0 + u * NT;
-                    if (g < G) {
-                        double x = v[u];
-                        if (p.lo2) x = sub_bounds(x, lo[u], hi[u]);
-                        else if (p.mid2) x = x - lo[u];
-                        if (p.apply_exp2) x = fast_exp2(x, etab);
-                        dst[g] = x;
-                    }
-                }
-            }
-        }
-        __syncthreads();  // work[] is rewritten by the next cell
-    }
-    if (bad && p.err_flag) atomicExch(p.err_flag, 1);
-}
-
 
 // =================================================================================================
 // K2 v3: same pipeline, values never leave shared memory
@@ -1072,12 +599,14 @@ __device__ __forceinline__ double block_median_smem(const double *__restrict__ v
 // values, any thread reads any value: both passes use the coalesced 16-byte mapping.
 constexpr int HIST_NB = 2048;
 
-template <int NT>
+// n = number of (finite) values, n_slots = slots of `vals` to walk (>= n; the extra slots hold +inf and are neither
+// counted nor gathered).
+template <int NT, int NB = HIST_NB>
 __device__ __forceinline__ bool block_median_hist(const double *__restrict__ vals, int n, double inv_n, double S1, double S2, int *hist, int dump_off,
-                                                  int *hres, int *wcnt, double *cand, int *cand_n, double &result) {
+                                                  int *hres, int *wcnt, double *cand, int *cand_n, double &result, int n_slots = 0) {
     constexpr int NW = NT / 32;
-    constexpr int BPT = HIST_NB / NT;   // bins scanned per thread
-    static_assert(HIST_NB % NT == 0 && BPT >= 1 && BPT <= 8, "HIST_NB must be a small multiple of NT");
+    constexpr int BPT = NB / NT;   // bins scanned per thread
+    static_assert(NB % NT == 0 && BPT >= 1 && BPT <= 8, "the bin count must be a small multiple of NT");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned dump = (unsigned)(dump_off + lane);   // index (relative to hist) of this lane's spare word
     const int kA = (n - 1) >> 1, kB = n >> 1;
@@ -1090,7 +619,7 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
     if (!(var > 0.0) || n <= 4 * CAND_MAX) return false;
     const float rs = rsqrtf((float)var);
     const double sd = var * (double)rs;
-    const double scale = (double)(rs * (0.5f * HIST_NB));
+    const double scale = (double)(rs * (0.5f * NB));
     if (!(scale < 1e290) || !(scale > 0.0)) return false;   // var outside the single-precision range: bracketing selection
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: integers 0 .. 2^32-1 land in the low word, high word HI0
     constexpr int HI0 = 0x43380000;
@@ -1101,7 +630,7 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
         *cand_n = 0;
     }
     const double2 *v2 = reinterpret_cast<const double2 *>(vals);
-    const int n2 = (n + 1) >> 1;   // an odd n is padded with +inf (never counted, never gathered)
+    const int n2 = ((n_slots > 0 ? n_slots : n) + 1) >> 1;   // an odd n is padded with +inf (never counted, never gathered)
     int cb = 0;
 #pragma unroll 2
     for (int i = tid; i < n2; i += NT) {
@@ -1111,8 +640,8 @@ __device__ __forceinline__ bool block_median_hist(const double *__restrict__ val
         const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
         // values outside mean +- sd count into this lane's own spare word behind the tables (never read; per lane, so that
         // a third of the warp does not pile onto one address): one unconditional atomic per value instead of a branch around it
-        atomicAdd(&hist[(hx == HI0 && lx < (unsigned)HIST_NB) ? lx : dump], 1);
-        atomicAdd(&hist[(hy == HI0 && ly < (unsigned)HIST_NB) ? ly : dump], 1);
+        atomicAdd(&hist[(hx == HI0 && lx < (unsigned)NB) ? lx : dump], 1);
+        atomicAdd(&hist[(hy == HI0 && ly < (unsigned)NB) ? ly : dump], 1);
         cb += (hx < HI0) ? 1 : 0;
         cb += (hy < HI0) ? 1 : 0;
     }
@@ -1592,6 +1121,453 @@ __global__ void __launch_bounds__(NT, 1) cell_pipeline3_kernel(const CellParams 
 }
 
 // =================================================================================================
+// K2 v4: ONE shared-memory buffer per cell, so that two cells are in flight on every SM
+// =================================================================================================
+//
+// v3 is bound by the latency of its barrier-separated phases and by shared-memory wavefronts, not by HBM: 512 threads
+// per CTA run a cell in almost the time 1024 threads need (measured: 1.21 against 1.14 ms per 9 000 cells x 10 000
+// genes), but its two 80 KB buffers allow one CTA per SM.  v4 keeps a single padded copy of the column and runs every
+// stage in place, which fits two 512-thread CTAs (two cells) per SM at 10 000 genes; their phases interleave and fill
+// each other's bubbles.
+//
+// Layout: per chromosome c a frame  [slack 0..1][h + 2 front pad][n_c values][h back pad]  (slack makes the value
+// region's parity equal the parity of the chromosome's first gene, so every chromosome lands by its own 16-byte
+// aligned bulk copy).  Stages:
+//   A   x -> x' in place (log2(x+1), dead-band subtraction, clamp); warps walk 32-gene chunks (a descriptor table in
+//       shared memory: slot, gene, count), so global reads of the bounds are coalesced and shared-memory accesses
+//       conflict free
+//   B1  prefix sums P, Q in place over the thread's own slice (three short passes + two segmented warp scans), pads
+//   B2  outputs N(j) = (Q(j+h) - Q(j-1)) - (Q(j-1) - Q(j-h-2)) / D(j) written IN PLACE, shifted down by h + 2 slots:
+//       slot u is last read by output u + h + 2, which is the output stored there.  Outputs are produced in rounds
+//       of V4_R chunks per warp held in registers, one barrier per round; a round's stores only touch slots below
+//       every slot a later round reads.
+//   C   median over the whole buffer (the slots that hold no value are set to +inf, which the histogram ignores)
+//   D   centring, second dead-band subtraction, 2^x, coalesced store of the column
+// The next cell's bulk copies are issued when stage D has drained the buffer; the CTA's wait for them is covered by
+// the other CTA on the SM.
+struct Chr4 {
+    int cs;   // first gene of the chromosome
+    int n;    // genes
+    int fs;   // first slot of the frame
+    int vb;   // slot of the first value while x' / Q live in the frame
+    int fb;   // slot of the first smoothed value (vb - h - 2; vb when nothing is smoothed)
+    int q0;   // index of the chromosome's first 32-gene chunk (entry K: the total)
+};
+
+struct Cell4Params {
+    const double *X;
+    int64_t G, ldx;
+    const int32_t *cols;
+    int64_t n_cols;
+    double *Y;
+    int64_t ldy;
+    const Seg *segs;
+    const Chr4 *chr;    // K + 1 entries (the last one: n = 0, fs = nb, q0 = number of chunks)
+    const int4 *chunks; // per 32-gene chunk: x = slot of its first value (x' / Q layout), y = first gene, z = genes in it,
+                        // w = chromosome | 0x40000000 when every window of the chunk is a full one
+    int apply_log;
+    const double *lo1, *hi1, *mid1;
+    double threshold;
+    int window, h;
+    int center;
+    const double *lo2, *hi2, *mid2;
+    int apply_exp2;
+    int *err_flag;
+    int K;
+    int nb;            // slots of the buffer (even)
+    int n_chunks;
+};
+
+__device__ __forceinline__ void bulk_g2s_multi(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// (a hook for host-side execution models of the copy engine: completes the phase after the issuing thread's copies; the
+// GPU's mbarrier completes by transaction bytes and needs nothing here)
+__device__ __forceinline__ void mbar_host_commit(void *bar) { (void)bar; }
+
+constexpr int V4_R = 6;   // chunks per warp and output round (registers: 2 per chunk and thread)
+constexpr int V4_U = 2;   // chunks per straight-line group of stages A and D (64 registers per thread: 4 spill)
+
+// LFIX > 0: every busy thread's slice has at most LFIX genes: the scan passes are fully unrolled with a predicate per gene.
+template <int NT, int MINB, int NB, int LFIX>
+__global__ void __launch_bounds__(NT, MINB) cell_pipeline4_kernel(const Cell4Params p) {
+    constexpr bool FIX = LFIX > 0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = NT / 32;
+    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
+    double *etab = reinterpret_cast<double *>(ltab + 128);
+    double *buf = etab + 128;
+    double *invD = buf + p.nb;
+    double *ptot = invD + (p.h + 2);
+    double *qtot = ptot + p.K;
+    double *tails = qtot + p.K;                               // [2][NW]
+    double *cand = tails + 2 * NW;
+    Red<NW> &red = *reinterpret_cast<Red<NW> *>(cand + CAND_MAX + 2);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(&red + 1);
+    int4 *ctab = reinterpret_cast<int4 *>(bar + 2);           // [n_chunks] chunk descriptors
+    int *hist = reinterpret_cast<int *>(ctab + p.n_chunks);   // NB bins, zero between cells
+    int *hres = hist + NB;
+    int *wcnt = hres + 8;                                     // [2][NW]
+    int *cand_n = wcnt + 2 * NW;
+    int *hdump = cand_n + 2;                                  // [32] per-lane spare words of the histogram pass
+    Chr4 *chr = reinterpret_cast<Chr4 *>(hdump + 32);         // [K + 1]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = (int)p.G, h = p.h, K = p.K, nb = p.nb, NCH = p.n_chunks;
+    const bool do_smooth = p.window >= 2;
+    const int sh = do_smooth ? h + 2 : 0;   // smoothed values sit this many slots below x' / Q
+    const double inv_G = 1.0 / (double)G;
+    int phase = 0;
+    unsigned parity = 0;
+    if (do_smooth) {
+        const double full = (double)(h + 1) * (double)(h + 1);
+        for (int r = tid; r <= h; r += NT) invD[r] = 1.0 / (full - 0.5 * (double)r * (double)(r + 1));
+    }
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < NB; i += NT) hist[i] = 0;
+    for (int i = tid; i < 128; i += NT) {
+        ltab[i] = make_double2(g_log_tab[i][0], g_log_tab[i][1]);
+        etab[i] = g_exp_tab[i];
+    }
+    for (int i = tid; i <= K; i += NT) chr[i] = p.chr[i];
+    for (int i = tid; i < NCH; i += NT) ctab[i] = p.chunks[i];
+    const Seg seg = p.segs[tid];
+    const int len = seg.len, a0 = seg.start, cs = seg.cs, ce = seg.ce;
+    const int lane_first = max(seg.tfirst - (tid - lane), 0);
+    const int wfirst = seg.tfirst >> 5;
+    bool bad = false;
+    const unsigned col_bytes = (unsigned)(p.G * sizeof(double));
+    auto tma_ok = [&](int64_t col) {
+        return ((col_bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(p.X + p.ldx * col) & 15u) == 0);
+    };
+    __syncthreads();
+    const int my_vb = chr[seg.chr].vb + (a0 - cs);   // slot of this thread's slice while x' / Q live in the frame
+    const int my_fb = my_vb - sh;                    // ... of its smoothed values
+    const double inv0 = do_smooth ? invD[0] : 1.0;
+    // the column of cell `col` -> value slots of the frames: one 16-byte aligned bulk copy per chromosome (the element in
+    // front of an odd first gene / behind an odd end lands in a pad slot, which is rewritten before it is read)
+    auto issue_column = [&](int64_t col) {
+        const double *src = p.X + p.ldx * col;
+        unsigned total = 0;
+        for (int c = 0; c < K; ++c) {
+            const int nc = chr[c].n;
+            if (nc > 0) total += (unsigned)((((chr[c].cs + nc + 1) & ~1) - (chr[c].cs & ~1)) * (int)sizeof(double));
+        }
+        fence_proxy_async();
+        mbar_expect_tx(bar, total);
+        for (int c = 0; c < K; ++c) {
+            const int nc = chr[c].n;
+            if (nc > 0) {
+                const int e0 = chr[c].cs & ~1, e1 = (chr[c].cs + nc + 1) & ~1;
+                bulk_g2s_multi(buf + chr[c].vb - (chr[c].cs & 1), src + e0, (unsigned)((e1 - e0) * (int)sizeof(double)), bar);
+            }
+        }
+        mbar_host_commit(bar);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < p.n_cols) {
+        const int64_t col0 = p.cols ? (int64_t)p.cols[blockIdx.x] : (int64_t)blockIdx.x;
+        if (tma_ok(col0)) issue_column(col0);
+    }
+    const bool fast_a = p.apply_log && p.lo1 && p.threshold > 0.0;
+    const bool fast_d = p.lo2 && p.apply_exp2;
+    const int n_it = (NCH - warp + NW - 1) / NW;   // chunks of this warp: warp, warp + NW, ...
+    const int n_it_cta = (NCH + NW - 1) / NW;      // ... of warp 0: the most any warp has
+
+    for (int64_t ci = blockIdx.x; ci < p.n_cols; ci += gridDim.x) {
+        const int64_t col = p.cols ? (int64_t)p.cols[ci] : ci;
+        double *__restrict__ dst = p.Y + p.ldy * ci;
+        // ---- the column is in the frames -----------------------------------------------------------------------------
+        if (tma_ok(col)) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            const double *__restrict__ src = p.X + p.ldx * col;
+            for (int it = 0; it < n_it; ++it) {
+                const int4 d = ctab[warp + NW * it];
+                if (lane < d.z) buf[d.x + lane] = src[d.y + lane];
+            }
+            __syncthreads();
+        }
+        // ---- A: x -> x' in place ------------------------------------------------------------------------------------------
+        {
+            const double thr = p.threshold;
+            int it = 0;
+            if (fast_a) {
+                // V4_U chunks per step as one straight-line block (no range branch per value: the group is re-evaluated
+                // through the library path when an argument leaves the fast path's domain)
+                for (; it + V4_U <= n_it; it += V4_U) {
+                    int4 d[V4_U];
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u) d[u] = ctab[warp + NW * (it + u)];
+                    double v[V4_U], lo[V4_U], hi[V4_U], x[V4_U];
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u) {
+                        const bool ok = lane < d[u].z;
+                        v[u] = buf[d[u].x + lane];           // slots behind a chromosome's last gene are pad slots
+                        lo[u] = ok ? p.lo1[d[u].y + lane] : 0.0;
+                        hi[u] = ok ? p.hi1[d[u].y + lane] : 0.0;
+                        v[u] = ok ? v[u] : 0.0;
+                    }
+                    bool slow = false;
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u) x[u] = fast_log2_1p_nc(v[u], ltab, slow);
+                    if (slow) {
+#pragma unroll
+                        for (int u = 0; u < V4_U; ++u) {
+                            if (!is_finite_d(v[u])) bad = true;
+                            x[u] = fast_log2_1p(v[u], ltab);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u)
+                        if (lane < d[u].z) buf[d[u].x + lane] = clamp_sym(sub_bounds(x[u], lo[u], hi[u]), thr);
+                }
+            }
+            for (; it < n_it; ++it) {
+                const int4 d = ctab[warp + NW * it];
+                if (lane < d.z) {
+                    const int g = d.y + lane;
+                    double x = buf[d.x + lane];
+                    if (!is_finite_d(x)) bad = true;
+                    if (p.apply_log) x = fast_log2_1p(x, ltab);
+                    if (p.lo1) x = sub_bounds(x, p.lo1[g], p.hi1[g]);
+                    else if (p.mid1) x = x - p.mid1[g];
+                    if (thr > 0.0) x = clamp_sym(x, thr);
+                    buf[d.x + lane] = x;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- B: pyramid smooth in place --------------------------------------------------------------------------------------
+        double ys1 = 0.0, ys2 = 0.0;   // sum / sum of squares of the outputs (bin geometry of the median)
+        if (!do_smooth) {
+            const double *xs = buf + my_fb;
+            for (int q = 0; q < len; ++q) {
+                const double out = xs[q];
+                ys1 += out;
+                ys2 = fma(out, out, ys2);
+            }
+        } else {
+            double *xs = buf + my_vb;
+            // pass 1: slice total of x
+            double tot = 0.0;
+#pragma unroll(FIX ? LFIX : 4)
+            for (int q = 0; q < (FIX ? LFIX : len); ++q)
+                if (!FIX || q < len) tot += xs[q];
+            double inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane - d >= lane_first) inc += t;
+            }
+            double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane <= lane_first) exc = 0.0;
+            if (lane == 31) tails[warp] = inc;
+            __syncthreads();
+            double carry = 0.0;
+            for (int u = wfirst; u < warp; ++u) carry += tails[u];
+            const double offP = exc + carry;   // P just before this slice
+            // pass 2: slice total of P (P = prefix of x inside the chromosome)
+            double pr = offP, qsum = 0.0;
+#pragma unroll(FIX ? LFIX : 4)
+            for (int q = 0; q < (FIX ? LFIX : len); ++q)
+                if (!FIX || q < len) {
+                    pr += xs[q];
+                    qsum += pr;
+                }
+            const double plast = pr;
+            inc = qsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane - d >= lane_first) inc += t;
+            }
+            exc = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane <= lane_first) exc = 0.0;
+            if (lane == 31) tails[NW + warp] = inc;
+            __syncthreads();
+            carry = 0.0;
+            for (int u = wfirst; u < warp; ++u) carry += tails[NW + u];
+            const double offQ = exc + carry;   // Q just before this slice
+            // pass 3: Q in place (each thread touches only its own slice)
+            pr = offP;
+            double qv = offQ;
+#pragma unroll(FIX ? LFIX : 4)
+            for (int q = 0; q < (FIX ? LFIX : len); ++q)
+                if (!FIX || q < len) {
+                    pr += xs[q];
+                    qv += pr;
+                    xs[q] = qv;
+                }
+            if (len > 0 && a0 + len == ce) {
+                ptot[seg.chr] = plast;
+                qtot[seg.chr] = qv;
+            }
+            __syncthreads();
+            // pads, a warp per chromosome: h + 2 zeros in front (Q(-1) .. Q(-h-2)), behind the last gene the linear
+            // continuation Q(n-1+k) = Qn + k Pn, k = 1..h (x is taken as 0 there)
+            for (int c = warp; c < K; c += NW) {
+                const int nc = chr[c].n;
+                if (nc >= 2) {
+                    const int vb = chr[c].vb;
+                    const double pt = ptot[c], qt = qtot[c];
+                    for (int e = lane; e < 2 * h + 2; e += 32) {
+                        if (e < h + 2) buf[vb - 1 - e] = 0.0;
+                        else buf[vb + nc + (e - (h + 2))] = fma((double)(e - (h + 1)), pt, qt);
+                    }
+                }
+            }
+            __syncthreads();
+            // outputs, V4_R chunks per warp and round
+            for (int it0 = 0; it0 < n_it_cta; it0 += V4_R) {   // the same number of rounds (barriers) in every warp
+                double o[V4_R];
+                int wpos[V4_R];
+#pragma unroll
+                for (int r = 0; r < V4_R; ++r) {
+                    wpos[r] = -1;
+                    o[r] = 0.0;
+                    if (it0 + r < n_it) {
+                        const int4 d = ctab[warp + NW * (it0 + r)];
+                        const double *__restrict__ P = buf + d.x + lane;
+                        if (d.w & 0x40000000) {   // every window of the chunk is a full one (a full chunk, too)
+                            const double qb = P[-1];
+                            const double N = (P[h] - qb) - (qb - P[-h - 2]);
+                            const double out = N * inv0;
+                            o[r] = out;
+                            wpos[r] = d.x + lane - sh;
+                            ys1 += out;
+                            ys2 = fma(out, out, ys2);
+                        } else if (lane < d.z) {
+                            const int c = d.w & 0xffff;
+                            const int nc = chr[c].n, j = d.y + lane - chr[c].cs;
+                            double out;
+                            if (nc >= 2) {
+                                const double qb = P[-1];
+                                const double N = (P[h] - qb) - (qb - P[-h - 2]);
+                                const int rl = max(h - j, 0), rr = max(h - (nc - 1 - j), 0);
+                                if (rl > 0 && rr > 0) {   // both ends inside the window (chromosome shorter than it)
+                                    const double D = (double)(h + 1) * (double)(h + 1) - 0.5 * (double)rl * (double)(rl + 1) -
+                                                     0.5 * (double)rr * (double)(rr + 1);
+                                    out = N / D;
+                                } else {
+                                    out = N * invD[rl + rr];
+                                }
+                            } else {
+                                out = P[0];   // single-gene chromosome: left untouched (ops.R:2417); Q of one element is the element
+                            }
+                            o[r] = out;
+                            wpos[r] = d.x + lane - sh;
+                            ys1 += out;
+                            ys2 = fma(out, out, ys2);
+                        }
+                    }
+                }
+                __syncthreads();   // every read of this round is done; its stores touch no slot a later round reads
+#pragma unroll
+                for (int r = 0; r < V4_R; ++r)
+                    if (wpos[r] >= 0) buf[wpos[r]] = o[r];
+            }
+        }
+        // slots that hold no smoothed value -> +inf (the median pass walks the whole buffer)
+        if (p.center == 1) {
+            for (int c = warp; c < K; c += NW) {
+                const int f0 = chr[c].fs, f1 = chr[c].fb, f2 = chr[c].fb + chr[c].n, f3 = chr[c + 1].fs;
+                for (int e = f0 + lane; e < f1; e += 32) buf[e] = INFINITY;
+                for (int e = f2 + lane; e < f3; e += 32) buf[e] = INFINITY;
+            }
+        }
+        ys1 = warp_sum_d(ys1);
+        ys2 = warp_sum_d(ys2);
+        if (lane == 0) {
+            red.d[phase][0][warp] = ys1;
+            red.d[phase][1][warp] = ys2;
+        }
+        __syncthreads();   // smoothed values complete at frame start + j
+        double S1 = (lane < NW) ? red.d[phase][0][lane] : 0.0, S2 = (lane < NW) ? red.d[phase][1][lane] : 0.0;
+        S1 = warp_sum_d(S1);
+        S2 = warp_sum_d(S2);
+        phase ^= 1;
+
+        // ---- C: per-cell centre --------------------------------------------------------------------------------------------
+        double centre = 0.0;
+        if (p.center == 1) {
+            if (tid == 0) atomicAdd(&g_stats[1], 1ull);
+            if (block_median_hist<NT, NB>(buf, G, inv_G, S1, S2, hist, (int)(hdump - hist), hres, wcnt, cand, cand_n, centre, nb)) {
+                if (tid == 0) atomicAdd(&g_stats[10], 1ull);
+            } else {   // tiny or degenerate columns, > CAND_MAX ties in the middle bin: bracketing selection
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = 0; q < len; ++q) {
+                    const double v = buf[my_fb + q];
+                    s1 += v;
+                    s2 = fma(v, v, s2);
+                }
+                centre = block_median_smem<NT>(buf, my_fb, len, G, s1, s2, red, phase, cand, cand_n);
+            }
+        } else if (p.center == 2) {
+            centre = S1 / (double)G;
+        }
+
+        // ---- D: centre, second reference subtraction, 2^x fused into the one coalesced write --------------------------------
+        {
+            int it = 0;
+            if (fast_d) {
+                for (; it + V4_U <= n_it; it += V4_U) {
+                    int4 d[V4_U];
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u) d[u] = ctab[warp + NW * (it + u)];
+                    double v[V4_U], lo[V4_U], hi[V4_U], x[V4_U];
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u) {
+                        const bool ok = lane < d[u].z;
+                        v[u] = buf[d[u].x + lane - sh];
+                        lo[u] = ok ? p.lo2[d[u].y + lane] : 0.0;
+                        hi[u] = ok ? p.hi2[d[u].y + lane] : 0.0;
+                        v[u] = ok ? v[u] : 0.0;
+                    }
+                    bool slow = false;
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u) {
+                        v[u] = sub_bounds(v[u] - centre, lo[u], hi[u]);
+                        x[u] = fast_exp2_nc(v[u], etab, slow);
+                    }
+                    if (slow) {
+#pragma unroll
+                        for (int u = 0; u < V4_U; ++u) x[u] = fast_exp2(v[u], etab);
+                    }
+#pragma unroll
+                    for (int u = 0; u < V4_U; ++u)
+                        if (lane < d[u].z) dst[d[u].y + lane] = x[u];
+                }
+            }
+            for (; it < n_it; ++it) {
+                const int4 d = ctab[warp + NW * it];
+                if (lane < d.z) {
+                    const int g = d.y + lane;
+                    double x = buf[d.x + lane - sh] - centre;
+                    if (p.lo2) x = sub_bounds(x, p.lo2[g], p.hi2[g]);
+                    else if (p.mid2) x = x - p.mid2[g];
+                    if (p.apply_exp2) x = fast_exp2(x, etab);
+                    dst[g] = x;
+                }
+            }
+        }
+        __syncthreads();   // the buffer is free: the next cell's column may land
+        if (tid == 0) {
+            const int64_t cn = ci + gridDim.x;
+            if (cn < p.n_cols) {
+                const int64_t coln = p.cols ? (int64_t)p.cols[cn] : cn;
+                if (tma_ok(coln)) issue_column(coln);
+            }
+        }
+    }
+    if (bad && p.err_flag) atomicExch(p.err_flag, 1);
+}
+
+// =================================================================================================
 // host-side launchers (device-pointer ABI)
 // =================================================================================================
 
@@ -1750,10 +1726,105 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     p.window = window; p.h = h; p.center = center; p.lo2 = lo2; p.hi2 = hi2; p.mid2 = mid2;
     p.apply_exp2 = apply_exp2; p.err_flag = err_flag; p.s_elems = s_elems; p.K = K;
 
+    // ---- v4 (single padded buffer, stages in place): the default -----------------------------------------------------
+    // Two 512-thread CTAs per SM when a CTA's buffer allows it (<= ~12 000 genes at window 101), four 256-thread CTAs for
+    // small columns, else one 1024-thread CTA.  ICNV_CELL_KERNEL=3 (read at icnv_init) selects the two-buffer v3 kernel.
+    if (c.opt_cell_kernel != 3) {
+        const int pad = 2 * h + 2;
+        std::vector<Chr4> chr((size_t)K + 1);
+        int pos = 0, nch = 0;
+        for (int k = 0; k < K; ++k) {
+            Chr4 &e = chr[(size_t)k];
+            e.cs = chr_start[k];
+            e.n = chr_len[k];
+            e.fs = pos;
+            int vb = pos + h + 2;
+            if ((vb ^ e.cs) & 1) ++vb;          // value region and first gene of the same parity: 16-byte aligned bulk copies
+            e.vb = vb;
+            e.fb = window >= 2 ? vb - (h + 2) : vb;
+            e.q0 = nch;
+            nch += (e.n + 31) / 32;
+            pos = vb + e.n + h;
+        }
+        const int nb = (pos + 2 + 1) & ~1;      // + 2: the element behind an odd chromosome end of the last frame
+        chr[(size_t)K] = Chr4{(int)G, 0, nb, nb, nb, nch};
+        (void)pad;
+        std::vector<int4> chunks((size_t)nch);
+        for (int k = 0; k < K; ++k)
+            for (int q = 0; q * 32 < chr[(size_t)k].n; ++q) {
+                const int j0 = q * 32, cnt = std::min(32, chr[(size_t)k].n - j0), nc = chr[(size_t)k].n;
+                const bool full = window >= 2 && cnt == 32 && j0 >= h && j0 + 31 <= nc - 1 - h;
+                chunks[(size_t)(chr[(size_t)k].q0 + q)] = make_int4(chr[(size_t)k].vb + j0, chr[(size_t)k].cs + j0, cnt, k | (full ? 0x40000000 : 0));
+            }
+        auto smem4 = [&](int nt) {
+            const int nw = nt / 32;
+            const size_t red = (nt == 256) ? sizeof(Red<8>) : (nt == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
+            return 128 * 24 + sizeof(double) * ((size_t)nb + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)nw + CAND_MAX + 2) + red + 16 +
+                   sizeof(int) * (1024 + 8 + 2 * (size_t)nw + 2 + 32) + sizeof(Chr4) * ((size_t)K + 1) + sizeof(int4) * (size_t)nch + 16;
+        };
+        const size_t sm_total = 228 * 1024;     // shared memory of an SM; every resident CTA also reserves 1 KB
+        int nt4 = 0, minb = 1;
+        if (c.opt_cell_nt == 256 || c.opt_cell_nt == 512 || c.opt_cell_nt == 1024) {
+            nt4 = c.opt_cell_nt;
+            minb = std::max(1, std::min(nt4 == 256 ? 4 : (nt4 == 512 ? 2 : 1), (int)(sm_total / (smem4(nt4) + 1024))));
+        } else if (4 * (smem4(256) + 1024) <= sm_total && G <= 6144) {
+            nt4 = 256;
+            minb = 4;
+        } else if (2 * (smem4(512) + 1024) <= sm_total) {
+            nt4 = 512;
+            minb = 2;
+        } else {
+            nt4 = 1024;
+            minb = 1;
+        }
+        int L4 = build_segments(G, chr_start, chr_len, K, nt4, 1 << 20, segs);
+        if (L4 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
+        const size_t smem = smem4(nt4);
+        if (L4 > 0 && smem <= (size_t)c.smem_optin) {
+            const size_t off_chr = sizeof(Seg) * 1024, off_chunks = (off_chr + sizeof(Chr4) * ((size_t)K + 1) + 15) & ~(size_t)15;
+            const size_t tab_bytes = off_chunks + sizeof(int4) * (size_t)nch;
+            char *d_tab = (char *)scratch(SLOT_SEGS, tab_bytes);
+            if (!d_tab) return ICNV_E_NOMEM;
+            std::vector<unsigned char> tab(tab_bytes, 0);
+            memcpy(tab.data(), segs.data(), sizeof(Seg) * (size_t)nt4);
+            memcpy(tab.data() + off_chr, chr.data(), sizeof(Chr4) * ((size_t)K + 1));
+            memcpy(tab.data() + off_chunks, chunks.data(), sizeof(int4) * (size_t)nch);
+            ICNV_CUDA(upload_if_changed(c.up_segs, c.up_segs_stream, d_tab, tab.data(), tab.size(), st));
+            Cell4Params q;
+            q.X = X; q.G = G; q.ldx = ldx; q.cols = cols; q.n_cols = n_cols; q.Y = Y; q.ldy = ldy;
+            q.segs = (const Seg *)d_tab;
+            q.chr = (const Chr4 *)(d_tab + off_chr);
+            q.chunks = (const int4 *)(d_tab + off_chunks);
+            q.apply_log = apply_log; q.lo1 = lo1; q.hi1 = hi1; q.mid1 = mid1; q.threshold = threshold;
+            q.window = window; q.h = h; q.center = center; q.lo2 = lo2; q.hi2 = hi2; q.mid2 = mid2;
+            q.apply_exp2 = apply_exp2; q.err_flag = err_flag; q.K = K; q.nb = nb; q.n_chunks = nch;
+            auto launch4 = [&](auto kern) -> int {
+                ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 1;
+                ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt4, smem));
+                const int64_t grid = std::min<int64_t>(n_cols, (int64_t)c.sm_count * std::max(per_sm, 1));
+                kern<<<(unsigned)grid, nt4, smem, st>>>(q);
+                return ICNV_OK;
+            };
+            int rc4;
+            // the slice length of the 10 000-gene / 20 000-gene layouts (21 genes per thread) gets fully unrolled scan passes
+            const bool fix21 = L4 == 21 && c.opt_cell_lfix != 0;
+            if (nt4 == 256) rc4 = (minb >= 4) ? launch4(cell_pipeline4_kernel<256, 4, 1024, 0>) : launch4(cell_pipeline4_kernel<256, 1, 1024, 0>);
+            else if (nt4 == 512 && minb >= 2) rc4 = fix21 ? launch4(cell_pipeline4_kernel<512, 2, 1024, 21>) : launch4(cell_pipeline4_kernel<512, 2, 1024, 0>);
+            else if (nt4 == 512) rc4 = launch4(cell_pipeline4_kernel<512, 1, 1024, 0>);
+            else rc4 = fix21 ? launch4(cell_pipeline4_kernel<1024, 1, 1024, 21>) : launch4(cell_pipeline4_kernel<1024, 1, 1024, 0>);
+            if (rc4) return rc4;
+            ICNV_CHECK_LAUNCH("cell_pipeline4_kernel");
+            return ICNV_OK;
+        }
+        if (c.opt_cell_kernel != 3 && !(L4 > 0))
+            return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes in K = %d chromosomes need more than 1024 per-thread slices", (long long)G, K);
+    }
+
     // ---- v3 (values stay in shared memory, two ping-pong buffers) whenever both buffers fit -----------------
     {
-        int want_v2 = 0, nt3 = (G <= 2048) ? 256 : (G <= 6144 ? 512 : 1024);
-        if (ctx().opt_cell_kernel) want_v2 = (ctx().opt_cell_kernel == 2);
+        const int want_v2 = 0;
+        int nt3 = (G <= 2048) ? 256 : (G <= 6144 ? 512 : 1024);
         if (ctx().opt_cell_nt) nt3 = ctx().opt_cell_nt;
         if (nt3 != 256 && nt3 != 512 && nt3 != 1024) nt3 = 1024;
         const int NW3 = nt3 / 32;
@@ -1804,63 +1875,8 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
         }
     }
 
-    // ---- v2 (register-resident values): large G where two buffers do not fit ---------------------------------------
-    // (threads, genes per thread) variants, smallest first; ICNV_CELL_VARIANT=<index> pins one (tuning)
-    static const int variants[][2] = {{256, 12}, {512, 12}, {512, 24}, {1024, 12}, {1024, 24}};  // measured: 512x24 beats 1024x12
-    int NT = 0, L = 0, lmax = 0, forced = -1;
-    if (ctx().opt_cell_variant >= 0) forced = ctx().opt_cell_variant;
-    for (int vi = 0; vi < 5; ++vi) {
-        if (forced >= 0 && vi != forced) continue;
-        L = build_segments(G, chr_start, chr_len, K, variants[vi][0], variants[vi][1], segs);
-        if (L < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
-        if (L > 0) {
-            NT = variants[vi][0];
-            lmax = variants[vi][1];
-            break;
-        }
-    }
-    if (NT == 0)
-        return set_error(ICNV_E_UNSUPPORTED,
-                         "G = %lld genes in K = %d chromosomes need more than the kernel's 1024 per-thread segments of at most "
-                         "23 genes, each inside one chromosome (at most %d genes when they divide evenly)",
-                         (long long)G, K, 1024 * 23);
-    const int NW = NT / 32;
-    size_t red_bytes = (NT == 256) ? sizeof(Red<8>) : (NT == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
-    const size_t smem_rest = sizeof(double) * ((size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW + CAND_MAX + 2) + red_bytes + 64 +
-                             128 * 24 + 32;
-    bool landing = true;
-    size_t smem = sizeof(double) * 2 * (size_t)s_elems + smem_rest;
-    if (smem > (size_t)c.smem_optin) {  // no room for the landing buffer: single-buffer mode
-        landing = false;
-        smem = sizeof(double) * (size_t)s_elems + smem_rest;
-    }
-    if (smem > (size_t)c.smem_optin)
-        return set_error(ICNV_E_UNSUPPORTED, "G = %lld needs %zu B shared memory per CTA, device allows %d", (long long)G,
-                         smem, c.smem_optin);
-
-    Seg *d_segs = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
-    if (!d_segs) return ICNV_E_NOMEM;
-    ICNV_CUDA(upload_if_changed(c.up_segs, c.up_segs_stream, d_segs, segs.data(), sizeof(Seg) * NT, st));
-    p.segs = d_segs;
-
-    auto launch = [&](auto kern) -> int {
-        ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-        // persistent CTAs: a whole number of waves over the SMs
-        int64_t grid = std::min<int64_t>(n_cols, (int64_t)c.sm_count * std::max(per_sm, 1));
-        kern<<<(unsigned)grid, NT, smem, st>>>(p);
-        return ICNV_OK;
-    };
-    int lrc;
-    if (NT == 256) lrc = landing ? launch(cell_pipeline_kernel<256, 12, true>) : launch(cell_pipeline_kernel<256, 12, false>);
-    else if (NT == 512 && lmax == 12) lrc = landing ? launch(cell_pipeline_kernel<512, 12, true>) : launch(cell_pipeline_kernel<512, 12, false>);
-    else if (NT == 512) lrc = landing ? launch(cell_pipeline_kernel<512, 24, true>) : launch(cell_pipeline_kernel<512, 24, false>);
-    else if (lmax == 12) lrc = launch(cell_pipeline_kernel<1024, 12, true>);
-    else lrc = landing ? launch(cell_pipeline_kernel<1024, 24, true>) : launch(cell_pipeline_kernel<1024, 24, false>);
-    if (lrc) return lrc;
-    ICNV_CHECK_LAUNCH("cell_pipeline_kernel");
-    return ICNV_OK;
+    return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes, window %d: the cell's padded column (%lld doubles) does not fit the %d B of "
+                     "shared memory a CTA can have", (long long)G, window, (long long)(G + (int64_t)K * (2 * h + 3)), c.smem_optin);
 }
 
 }  // extern "C"

@@ -34,6 +34,8 @@ PTX_STANDINS = {
     "mbar_init": "{ (void)count; *reinterpret_cast<unsigned long long *>(bar) = 0ull; }",
     "mbar_expect_tx": "{ (void)bar; (void)bytes; }",
     "bulk_g2s": "{ memcpy(dst, src, bytes); *reinterpret_cast<unsigned long long *>(bar) += 1ull; }",
+    "bulk_g2s_multi": "{ memcpy(dst, src, bytes); (void)bar; }",
+    "mbar_host_commit": "{ *reinterpret_cast<unsigned long long *>(bar) += 1ull; }",
     "mbar_wait": "{ while (((*reinterpret_cast<volatile unsigned long long *>(bar)) & 1ull) == parity) emu::spin_yield(); }",
     "fence_proxy_async": "{ }",
     "cp_async8": "{ if (valid) memcpy(smem_dst, gsrc, 8); else memset(smem_dst, 0, 8); }",

@@ -59,6 +59,11 @@ inline dim3 blockDim, gridDim;
 template <class A, class B> constexpr std::common_type_t<A, B> min(A a, B b) { return b < a ? (std::common_type_t<A, B>)b : (std::common_type_t<A, B>)a; }
 template <class A, class B> constexpr std::common_type_t<A, B> max(A a, B b) { return a < b ? (std::common_type_t<A, B>)b : (std::common_type_t<A, B>)a; }
 
+struct int4 {
+    int x, y, z, w;
+};
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+
 // ---- runtime API --------------------------------------------------------------------------------------------------
 typedef int cudaError_t;
 typedef struct emuStream *cudaStream_t;

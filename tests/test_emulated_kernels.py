@@ -73,8 +73,8 @@ def test_engine_and_multi_rank_path_under_the_host_emulation(world):
 
 
 @pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
-@pytest.mark.parametrize("world", [1, 2])
-def test_bench_script_reaches_its_json_line_under_the_host_emulation(world):
+@pytest.mark.parametrize("world,config", [(1, "c3"), (2, "c3"), (2, "c4")])
+def test_bench_script_reaches_its_json_line_under_the_host_emulation(world, config):
     """bench.py itself (workload, warm-up + timed loop, e2e through the host ABI, max over ranks, JSON assembly) at a toy
     size on the CPU, for 1 rank and for 2 ranks launched the way torchrun launches them.  The numbers are meaningless
     (emulation, wall clock); the contract keys and the multi-rank control flow are what is checked."""
@@ -84,7 +84,8 @@ def test_bench_script_reaches_its_json_line_under_the_host_emulation(world):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    args = ["--gpus", str(world), "--cells", "64", "--genes", "1100", "--steps", "2", "--warmup", "3", "--ref-sample-cells", "16"]
+    args = ["--gpus", str(world), "--config", config, "--steps", "2", "--warmup", "3", "--ref-sample-cells", "16"] + \
+        (["--cells", "64", "--genes", "1100"] if config == "c3" else ["--cells", "700", "--genes", "260"])
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
@@ -100,7 +101,8 @@ def test_bench_script_reaches_its_json_line_under_the_host_emulation(world):
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
         assert key in j, key
     assert j["n_gpus"] == world and j["steps"] == 2 and j["warmup"] == 3 and j["value"] > 0 and j["gpu_launches"] > 0
-    assert j["dtype"] == "f64" and j["scaling"] == "weak" and "workload" in j["config"] and "model" not in j["config"]
+    assert j["dtype"] == "f64" and j["scaling"] == "strong" and "workload" in j["config"] and "model" not in j["config"]
+    assert j["config"]["cells"] == (64 if config == "c3" else 700) and j["config"]["config"] == config
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(j["roofline"]) and j["roofline"]["bound"] == "hbm"
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(j["e2e"]) and j["e2e"]["h2d_bytes_per_step"] > 0
     if world == 1:

@@ -235,8 +235,7 @@ def test_smooth_block_benchmark_layout_unrolled_slices(api, monkeypatch):
 
 
 def test_smooth_block_20k_genes_single_buffer_variant(api):
-    """config c5's gene count: two shared-memory buffers no longer fit, the kernel runs its
-    single-buffer / 1024-thread variant."""
+    """config c5's gene count: one CTA of 1024 threads per SM (the padded column takes 178 KB of shared memory)."""
     from infercnv_b200._lib import InfercnvB200Error
     rng = np.random.default_rng(8)
     t = np.array([852, 615, 535, 288, 420, 453, 458, 297, 349, 363, 514, 472, 162, 301, 274, 397, 546, 126, 545, 239,
@@ -252,8 +251,10 @@ def test_smooth_block_20k_genes_single_buffer_variant(api):
     rel = np.max(np.abs(got - want) / np.abs(want))
     print(f"\n[20000 genes] smooth block max rel err vs oracle: {rel:.3e}")
     assert rel < 1e-10
-    with pytest.raises(InfercnvB200Error) as e:        # beyond 1024 x 23 genes: refused, the R wrapper falls back
-        api.center(np.ones((24000, 2)))
+    z = api.center(np.arange(48000, dtype=np.float64).reshape(24000, 2, order="F"))   # 24 000 genes still fit without pads
+    np.testing.assert_array_equal(z[:, 1], np.arange(24000, 48000) - 35999.5)
+    with pytest.raises(InfercnvB200Error) as e:        # a column that does not fit shared memory: refused, the R wrapper falls back
+        api.center(np.ones((40000, 2)))
     assert e.value.code == -4
 
 
