@@ -1726,10 +1726,68 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
     p.window = window; p.h = h; p.center = center; p.lo2 = lo2; p.hi2 = hi2; p.mid2 = mid2;
     p.apply_exp2 = apply_exp2; p.err_flag = err_flag; p.s_elems = s_elems; p.K = K;
 
-    // ---- v4 (single padded buffer, stages in place): the default -----------------------------------------------------
-    // Two 512-thread CTAs per SM when a CTA's buffer allows it (<= ~12 000 genes at window 101), four 256-thread CTAs for
-    // small columns, else one 1024-thread CTA.  ICNV_CELL_KERNEL=3 (read at icnv_init) selects the two-buffer v3 kernel.
-    if (c.opt_cell_kernel != 3) {
+    // ---- v3 (values stay in shared memory, two ping-pong buffers) whenever both buffers fit -----------------
+    if (c.opt_cell_kernel != 4) {
+        const int want_v2 = 0;
+        int nt3 = (G <= 2048) ? 256 : (G <= 6144 ? 512 : 1024);
+        if (ctx().opt_cell_nt) nt3 = ctx().opt_cell_nt;
+        if (nt3 != 256 && nt3 != 512 && nt3 != 1024) nt3 = 1024;
+        const int NW3 = nt3 / 32;
+        const size_t red3 = (nt3 == 256) ? sizeof(Red<8>) : (nt3 == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
+        // padded-Q layout (see the kernel) whenever it fits; ICNV_CELL_PADQ=0 keeps the ping-pong layout (A/B switch)
+        int padq = 1;
+        padq = padq && ctx().opt_cell_padq != 0;
+        const int q_elems = (int)(((int64_t)G + (int64_t)K * (2 * h + 2) + 1) & ~(int64_t)1);
+        int L3 = want_v2 ? 0 : build_segments(G, chr_start, chr_len, K, nt3, 1 << 20, segs);
+        if (L3 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
+        const int ipad = (L3 + 2) & ~1;   // front pad of the reciprocal-denominator table: >= the longest slice, even
+        auto smem_for = [&](bool pq) {
+            const size_t cols = pq ? (size_t)q_elems + (size_t)s_elems + (size_t)ipad
+                                   : 2 * (size_t)s_elems + (size_t)K * (size_t)h;
+            return 128 * 24 + sizeof(double) * (cols + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 + CAND_MAX + 2 + 2 + 2) +
+                   red3 + sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2 + 2 * (size_t)K + 2 + 32) + 64;
+        };
+        if (padq && smem_for(true) > (size_t)c.smem_optin) padq = 0;
+        const size_t smem3 = smem_for(padq != 0);
+        p.q_elems = q_elems;
+        p.ipad = ipad;
+        if (L3 > 0 && smem3 <= (size_t)c.smem_optin) {
+            Seg *d_segs3 = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
+            if (!d_segs3) return ICNV_E_NOMEM;
+            ICNV_CUDA(upload_if_changed(c.up_segs, c.up_segs_stream, d_segs3, segs.data(), sizeof(Seg) * nt3, st));
+            p.segs = d_segs3;
+            const int64_t grid3 = std::min<int64_t>(n_cols, c.sm_count);
+            auto launch3 = [&](auto kern) -> int {
+                ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                kern<<<(unsigned)grid3, nt3, smem3, st>>>(p);
+                return ICNV_OK;
+            };
+            int rc3;
+            // fully unrolled slice loops for the segment length of the 10 000-gene configurations (ICNV_CELL_LFIX=0: generic)
+            int lfix = (padq && nt3 == 1024 && L3 == 11) ? 11 : 0;
+            if (ctx().opt_cell_lfix == 0) lfix = 0;
+            if (lfix == 11)
+                rc3 = launch3(cell_pipeline3_kernel<1024, true, 11>);
+            else if (padq)
+                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, true, 0>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, true, 0>) : launch3(cell_pipeline3_kernel<1024, true, 0>));
+            else
+                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, false, 0>)
+                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, false, 0>) : launch3(cell_pipeline3_kernel<1024, false, 0>));
+            if (rc3) return rc3;
+            ICNV_CHECK_LAUNCH("cell_pipeline3_kernel");
+            return ICNV_OK;
+        }
+    }
+
+    // ---- v4 (single padded buffer, stages in place): columns too long for v3's two buffers (> ~12 400 genes at window
+    // 101; config c5's 20 000 genes run here, one 1024-thread CTA per SM), or everywhere with ICNV_CELL_KERNEL=4 (read at
+    // icnv_init): two 512-thread CTAs per SM when a CTA's buffer allows it, four 256-thread CTAs for small columns.
+    // Measured at 10 000 genes (profiles/r02_*): v4 with two cells per SM 1.21 ms per 9 000 cells against v3's 1.14 ms -
+    // its chunk-descriptor loops cost more instructions than the second cell in flight wins back - so v3 stays the default
+    // where it fits; at 20 000 genes v4 runs 62 500 cells in 13.8 ms where the register-resident v2 kernel it replaced
+    // took 25.4 ms.
+    {
         const int pad = 2 * h + 2;
         std::vector<Chr4> chr((size_t)K + 1);
         int pos = 0, nch = 0;
@@ -1817,62 +1875,8 @@ int icnv_dev_cell_pipeline_f64(const double *X, int64_t G, int64_t ldx, const in
             ICNV_CHECK_LAUNCH("cell_pipeline4_kernel");
             return ICNV_OK;
         }
-        if (c.opt_cell_kernel != 3 && !(L4 > 0))
+        if (!(L4 > 0))
             return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes in K = %d chromosomes need more than 1024 per-thread slices", (long long)G, K);
-    }
-
-    // ---- v3 (values stay in shared memory, two ping-pong buffers) whenever both buffers fit -----------------
-    {
-        const int want_v2 = 0;
-        int nt3 = (G <= 2048) ? 256 : (G <= 6144 ? 512 : 1024);
-        if (ctx().opt_cell_nt) nt3 = ctx().opt_cell_nt;
-        if (nt3 != 256 && nt3 != 512 && nt3 != 1024) nt3 = 1024;
-        const int NW3 = nt3 / 32;
-        const size_t red3 = (nt3 == 256) ? sizeof(Red<8>) : (nt3 == 512 ? sizeof(Red<16>) : sizeof(Red<32>));
-        // padded-Q layout (see the kernel) whenever it fits; ICNV_CELL_PADQ=0 keeps the ping-pong layout (A/B switch)
-        int padq = 1;
-        padq = padq && ctx().opt_cell_padq != 0;
-        const int q_elems = (int)(((int64_t)G + (int64_t)K * (2 * h + 2) + 1) & ~(int64_t)1);
-        int L3 = want_v2 ? 0 : build_segments(G, chr_start, chr_len, K, nt3, 1 << 20, segs);
-        if (L3 < 0) return set_error(ICNV_E_BAD_ARG, "chromosome ranges must tile [0, G) contiguously");
-        const int ipad = (L3 + 2) & ~1;   // front pad of the reciprocal-denominator table: >= the longest slice, even
-        auto smem_for = [&](bool pq) {
-            const size_t cols = pq ? (size_t)q_elems + (size_t)s_elems + (size_t)ipad
-                                   : 2 * (size_t)s_elems + (size_t)K * (size_t)h;
-            return 128 * 24 + sizeof(double) * (cols + (size_t)(h + 2) + 2 * (size_t)K + 2 * (size_t)NW3 + CAND_MAX + 2 + 2 + 2) +
-                   red3 + sizeof(int) * (HIST_NB + 8 + 2 * (size_t)NW3 + 2 + 2 * (size_t)K + 2 + 32) + 64;
-        };
-        if (padq && smem_for(true) > (size_t)c.smem_optin) padq = 0;
-        const size_t smem3 = smem_for(padq != 0);
-        p.q_elems = q_elems;
-        p.ipad = ipad;
-        if (L3 > 0 && smem3 <= (size_t)c.smem_optin) {
-            Seg *d_segs3 = (Seg *)scratch(SLOT_SEGS, sizeof(Seg) * 1024);
-            if (!d_segs3) return ICNV_E_NOMEM;
-            ICNV_CUDA(upload_if_changed(c.up_segs, c.up_segs_stream, d_segs3, segs.data(), sizeof(Seg) * nt3, st));
-            p.segs = d_segs3;
-            const int64_t grid3 = std::min<int64_t>(n_cols, c.sm_count);
-            auto launch3 = [&](auto kern) -> int {
-                ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-                kern<<<(unsigned)grid3, nt3, smem3, st>>>(p);
-                return ICNV_OK;
-            };
-            int rc3;
-            // fully unrolled slice loops for the segment length of the 10 000-gene configurations (ICNV_CELL_LFIX=0: generic)
-            int lfix = (padq && nt3 == 1024 && L3 == 11) ? 11 : 0;
-            if (ctx().opt_cell_lfix == 0) lfix = 0;
-            if (lfix == 11)
-                rc3 = launch3(cell_pipeline3_kernel<1024, true, 11>);
-            else if (padq)
-                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, true, 0>)
-                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, true, 0>) : launch3(cell_pipeline3_kernel<1024, true, 0>));
-            else
-                rc3 = (nt3 == 256) ? launch3(cell_pipeline3_kernel<256, false, 0>)
-                                   : (nt3 == 512 ? launch3(cell_pipeline3_kernel<512, false, 0>) : launch3(cell_pipeline3_kernel<1024, false, 0>));
-            if (rc3) return rc3;
-            ICNV_CHECK_LAUNCH("cell_pipeline3_kernel");
-            return ICNV_OK;
-        }
     }
 
     return set_error(ICNV_E_UNSUPPORTED, "G = %lld genes, window %d: the cell's padded column (%lld doubles) does not fit the %d B of "
