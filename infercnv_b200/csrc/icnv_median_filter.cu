@@ -167,6 +167,310 @@ __global__ void __launch_bounds__(MS_NT, NET ? 2 : 0) median_filter_select_kerne
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
 
+// =================================================================================================
+// window_size 7 (radius 4, 9 x 9 taps - the default of apply_median_filtering): shared-merge networks on 32-bit keys
+// =================================================================================================
+//
+// The counting selection above redoes all of a window's work for every output although neighbouring windows share 72 of
+// their 81 taps.  Here a tile of 32 genes x 32 list positions is worked on by the whole CTA in stages that keep what is
+// shared (tools/gen_median_merge.py, icnv_median_merge.inc; lane = gene, every list below is per gene):
+//   S0  the halo (40 genes x 40 positions) is loaded once; every value gets a 32-bit key = 24 bits of its position
+//       between the tile's minimum and maximum (monotone) | an 8-bit tag (gene mod 16, position mod 16) that is unique
+//       inside any 9 x 9 window.  Taps outside the chromosome / index-list block get the keys 0 and 0xffffffff in a
+//       checkerboard, so that a truncated window is still 81 keys with its median at rank 40, 41 or 42.
+//   S1  per halo position: the 9 keys around the gene sorted (a "run", 25 comparators); runs of consecutive positions
+//       merged in pairs (P, 18 keys)
+//   S2  P + P -> Q (36 keys, four consecutive positions)
+//   S3  per pair of outputs: the 8 positions they share = Q + Q, of which only ranks 30..43 can still be a median; each
+//       output adds its own ninth run and reads off ranks 39..43 of its 81 keys.
+// ~290 min / max operations per output instead of ~1400 for a network per window (or ~4600 instructions of counting).
+// The median's key carries its tap in the tag, so its double is one shared-memory load away.  Keys order the values up to
+// the 24-bit quantisation: when a neighbour in rank shares the median's quantised value, the rank is settled exactly by
+// counting over the doubles of that quantisation cell (mm_exact_rank); identical values - de-noised matrices - stay cheap
+// there because a cell whose doubles are all equal needs no further selection.
+#define mf_min(a, b) min((unsigned)(a), (unsigned)(b))
+#define mf_max(a, b) max((unsigned)(a), (unsigned)(b))
+#include "icnv_median_merge.inc"
+
+constexpr int MM_TX = 32, MM_TY = 32;            // outputs per tile: genes (lanes) x list positions
+constexpr int MM_HX = MM_TX + 8;                 // halo genes
+constexpr int MM_ROWS = MM_TY + 10;              // halo rows 0 .. TY+9 (row r = position y0 - 5 + r; rows 1 .. TY+8 are used)
+constexpr int MM_NW = 16, MM_NT = MM_NW * 32;
+constexpr int MM_NP = MM_TY / 2 + 3;             // P lists: rows (2t, 2t+1), t = 1 .. TY/2+3
+constexpr int MM_NQ = MM_TY / 2 + 2;             // Q lists: P[q] + P[q+1]
+constexpr int MM_PW = 20, MM_QW = 36;            // words per gene and list (P padded to a multiple of 4)
+constexpr unsigned MM_LOW = 0u, MM_HIGH = 0xffffffffu;
+
+constexpr size_t mm_smem_bytes() {
+    return sizeof(double) * MM_ROWS * MM_HX + sizeof(unsigned) * (size_t)MM_ROWS * MM_HX + sizeof(unsigned) * (size_t)MM_ROWS * 9 * MM_TX +
+           sizeof(unsigned) * (size_t)MM_NP * MM_TX * MM_PW + sizeof(unsigned) * (size_t)MM_NQ * MM_TX * MM_QW + 96 * sizeof(double);
+}
+
+// The value of real rank `rho` (1-based, among the window's taps inside the block) when the key at that rank has the
+// quantised value Q: every tap below the cell ranks below it, so the answer is the (rho - #below)-th smallest double of the
+// cell.  (x0, r0): halo coordinates of the window's first tap.
+__device__ __noinline__ double mm_exact_rank(const unsigned *__restrict__ Kh, const double *__restrict__ Dh, int x0, int r0, unsigned Q,
+                                             int rho) {
+    int below = 0, g = 0;
+    double dmin = INFINITY, dmax = -INFINITY;
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) {
+            const unsigned key = Kh[(r0 + r) * MM_HX + x0 + c];
+            if (key == MM_LOW || key == MM_HIGH) continue;
+            const unsigned q = key >> 8;
+            below += (q < Q) ? 1 : 0;
+            if (q == Q) {
+                const double d = Dh[(r0 + r) * MM_HX + x0 + c];
+                ++g;
+                dmin = d < dmin ? d : dmin;
+                dmax = d > dmax ? d : dmax;
+            }
+        }
+    if (dmin == dmax) return dmin;
+    const int t = rho - below;   // 1 .. g
+    double ans = dmin;
+    for (int r = 0; r < 9; ++r)       // distinct doubles in one cell (rare): rank each member among the members
+        for (int c = 0; c < 9; ++c) {
+            const unsigned key = Kh[(r0 + r) * MM_HX + x0 + c];
+            if (key == MM_LOW || key == MM_HIGH || (key >> 8) != Q) continue;
+            const double d = Dh[(r0 + r) * MM_HX + x0 + c];
+            int lt = 0, eq = 0;
+            for (int r2 = 0; r2 < 9; ++r2)
+                for (int c2 = 0; c2 < 9; ++c2) {
+                    const unsigned k2 = Kh[(r0 + r2) * MM_HX + x0 + c2];
+                    if (k2 == MM_LOW || k2 == MM_HIGH || (k2 >> 8) != Q) continue;
+                    const double d2 = Dh[(r0 + r2) * MM_HX + x0 + c2];
+                    lt += (d2 < d) ? 1 : 0;
+                    eq += (d2 == d) ? 1 : 0;
+                }
+            if (lt < t && t <= lt + eq) ans = d;
+        }
+    return ans;
+}
+
+// the double behind a key of the window whose first tap is (x0, r0): the tag holds the tap's halo coordinates mod 16
+__device__ __forceinline__ double mm_value_of(const double *__restrict__ Dh, unsigned key, int x0, int r0) {
+    const int tx = (int)((key >> 4) & 15u), ty = (int)(key & 15u);
+    const int hx = x0 + ((tx - x0) & 15), r = r0 + ((ty - r0) & 15);
+    return Dh[r * MM_HX + hx];
+}
+
+__global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfParams p) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    double *Dh = reinterpret_cast<double *>(mf_smem);                         // [ROWS][HX] values (0 outside the block)
+    double *redd = Dh + MM_ROWS * MM_HX;                                      // [96] reduction scratch, row table
+    unsigned *Kh = reinterpret_cast<unsigned *>(redd + 96);                   // [ROWS][HX] keys
+    unsigned *Rs = Kh + MM_ROWS * MM_HX;                                      // [ROWS][9][TX] sorted runs
+    unsigned *Ps = Rs + (size_t)MM_ROWS * 9 * MM_TX;                          // [NP][TX][PW]
+    unsigned *Qs = Ps + (size_t)MM_NP * MM_TX * MM_PW;                        // [NQ][TX][QW]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const MfTile gt = p.gene_tiles[blockIdx.y];
+    const MfTile ct = p.cell_tiles[blockIdx.x];
+    const int hi0 = gt.start - 4, hj0 = ct.start - 5;   // halo (hx, r) = gene hi0 + hx, list position hj0 + r
+    // ---- S0: halo, tile range, keys ----------------------------------------------------------------------------------------
+    bool bad = false;
+    double vmin = INFINITY, vmax = -INFINITY;
+    long long *rowbase = reinterpret_cast<long long *>(redd + 40);   // [ROWS] column offset of the row's cell, -1 outside the list
+    for (int r = tid; r < MM_ROWS; r += MM_NT) {
+        const int jj = hj0 + r;
+        rowbase[r] = (jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8) ? (long long)p.G * (long long)p.cells[jj] : -1ll;
+    }
+    __syncthreads();
+    for (int e = tid; e < MM_ROWS * MM_HX; e += MM_NT) {
+        const int r = e / MM_HX, hx = e - r * MM_HX;
+        const int ii = hi0 + hx;
+        const long long rb = rowbase[r];
+        double v = 0.0;
+        if (ii >= gt.lo && ii < gt.hi && rb >= 0) {
+            v = p.X[ii + rb];
+            if (is_finite_d(v)) {
+                vmin = v < vmin ? v : vmin;
+                vmax = v > vmax ? v : vmax;
+            } else {
+                bad = true;
+            }
+        }
+        Dh[e] = v;
+    }
+    vmin = warp_min_d(vmin);
+    vmax = warp_max_d(vmax);
+    if (lane == 0) {
+        redd[warp] = vmin;
+        redd[16 + warp] = vmax;
+    }
+    int *modecnt = reinterpret_cast<int *>(redd + 32);   // [4] matches of the four candidate values, [4] "cell not clean" flag
+    if (tid < 8) modecnt[tid] = 0;
+    __syncthreads();
+    vmin = redd[0];
+    vmax = redd[16];
+#pragma unroll
+    for (int w = 1; w < MM_NW; ++w) {
+        vmin = redd[w] < vmin ? redd[w] : vmin;
+        vmax = redd[16 + w] > vmax ? redd[16 + w] : vmax;
+    }
+    const double QMAX = 16777213.0;   // quantised values 1 .. 2^24 - 2: strictly between the two padding keys
+    const double scale = (vmax > vmin) ? QMAX / (vmax - vmin) : 0.0;
+    // The matrices this filter sees are full of ONE repeated value (exactly 1 after the dead-band subtraction and 2^x, the
+    // reference mean after de-noising): nearly every window's median then has rank neighbours with the same key cell, which
+    // would send it through the exact-rank scan.  Four taps of the tile nominate candidates for that value; the most
+    // frequent one (M) is remembered together with whether its key cell holds nothing but copies of it - then a median whose
+    // key falls into that cell IS M, whatever the ties.
+    const int c_r[4] = {MM_ROWS / 2, MM_ROWS / 2, 3 * MM_ROWS / 4, MM_ROWS / 4};
+    const int c_x[4] = {MM_HX / 2, MM_HX / 4, 3 * MM_HX / 4, MM_HX / 2 + 3};
+    double cand[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // a nominee outside the block nominates nothing (NaN equals no value)
+        const int ii = hi0 + c_x[q];
+        cand[q] = (ii >= gt.lo && ii < gt.hi && rowbase[c_r[q]] >= 0) ? Dh[c_r[q] * MM_HX + c_x[q]] : __longlong_as_double(0x7ff8000000000000ll);
+    }
+    {
+        int cnt[4] = {0, 0, 0, 0};
+        for (int e = tid; e < MM_ROWS * MM_HX; e += MM_NT) {
+            const double v = Dh[e];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cnt[q] += (v == cand[q]) ? 1 : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int tot = __reduce_add_sync(0xffffffffu, cnt[q]);
+            if (lane == 0 && tot) atomicAdd(&modecnt[q], tot);
+        }
+    }
+    __syncthreads();
+    int best = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+        if (modecnt[q] > modecnt[best]) best = q;
+    const double M = cand[best];
+    auto quant = [&](double v) -> unsigned {
+        double qd = (v - vmin) * scale;
+        qd = qd < QMAX ? qd : QMAX;       // (also maps NaN to QMAX)
+        qd = qd > 0.0 ? qd : 0.0;
+        return 1u + __double2uint_rd(qd);
+    };
+    const unsigned qM = quant(M);
+    bool dirty = false;   // a value other than M in M's key cell
+    for (int e = tid; e < MM_ROWS * MM_HX; e += MM_NT) {
+        const int r = e / MM_HX, hx = e - r * MM_HX;
+        const int ii = hi0 + hx;
+        unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
+        if (ii >= gt.lo && ii < gt.hi && rowbase[r] >= 0) {
+            const double v = Dh[e];
+            const unsigned q = quant(v);
+            dirty |= (q == qM) && (v != M);
+            key = (q << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
+        }
+        Kh[e] = key;
+    }
+    if (dirty) modecnt[4] = 1;
+    __syncthreads();
+    const bool mode_clean = modecnt[4] == 0;
+    // ---- S1: sorted runs, pairs ----------------------------------------------------------------------------------------------
+    for (int t = warp; t <= MM_TY / 2 + 4; t += MM_NW) {      // rows 2t, 2t+1
+        unsigned ra[9], rb[9];
+        const int r0 = 2 * t, r1 = 2 * t + 1;
+        const bool ok0 = r0 >= 1 && r0 <= MM_TY + 8, ok1 = r1 >= 1 && r1 <= MM_TY + 8;
+        if (ok0) {
+            unsigned k[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) k[i] = Kh[r0 * MM_HX + lane + i];
+            MF_SORT9(k, ra);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rs[(r0 * 9 + i) * MM_TX + lane] = ra[i];
+        }
+        if (ok1) {
+            unsigned k[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) k[i] = Kh[r1 * MM_HX + lane + i];
+            MF_SORT9(k, rb);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rs[(r1 * 9 + i) * MM_TX + lane] = rb[i];
+        }
+        if (t >= 1 && t <= MM_NP) {      // P[t-1] = rows (2t, 2t+1), both inside 2 .. TY+7
+            unsigned o[MM_PW];
+            MF_MERGE9(ra, rb, o);
+            o[18] = 0u;
+            o[19] = 0u;
+            uint4 *dst = reinterpret_cast<uint4 *>(Ps + ((size_t)(t - 1) * MM_TX + lane) * MM_PW);
+#pragma unroll
+            for (int i = 0; i < MM_PW / 4; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+    }
+    __syncthreads();
+    // ---- S2: Q[q] = P[q] + P[q+1] (rows 2q+2 .. 2q+5) --------------------------------------------------------------------
+    for (int q = warp; q < MM_NQ; q += MM_NW) {
+        unsigned a[MM_PW], b[MM_PW], o[MM_QW];
+        const uint4 *sa = reinterpret_cast<const uint4 *>(Ps + ((size_t)q * MM_TX + lane) * MM_PW);
+        const uint4 *sb = reinterpret_cast<const uint4 *>(Ps + ((size_t)(q + 1) * MM_TX + lane) * MM_PW);
+#pragma unroll
+        for (int i = 0; i < MM_PW / 4; ++i) {
+            const uint4 va = sa[i], vb = sb[i];
+            a[4 * i] = va.x; a[4 * i + 1] = va.y; a[4 * i + 2] = va.z; a[4 * i + 3] = va.w;
+            b[4 * i] = vb.x; b[4 * i + 1] = vb.y; b[4 * i + 2] = vb.z; b[4 * i + 3] = vb.w;
+        }
+        MF_MERGE18(a, b, o);
+        uint4 *dst = reinterpret_cast<uint4 *>(Qs + ((size_t)q * MM_TX + lane) * MM_QW);
+#pragma unroll
+        for (int i = 0; i < MM_QW / 4; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    __syncthreads();
+    // ---- S3: per pair of outputs (2j, 2j+1): core = Q[j] + Q[j+2] (rows 2j+2 .. 2j+9), + row 2j+1 resp. 2j+10 ----------------
+    for (int j = warp; j < MM_TY / 2; j += MM_NW) {
+        unsigned core[14];
+        {
+            unsigned a[MM_QW], b[MM_QW];
+            const uint4 *sa = reinterpret_cast<const uint4 *>(Qs + ((size_t)j * MM_TX + lane) * MM_QW);
+            const uint4 *sb = reinterpret_cast<const uint4 *>(Qs + ((size_t)(j + 2) * MM_TX + lane) * MM_QW);
+#pragma unroll
+            for (int i = 0; i < MM_QW / 4; ++i) {
+                const uint4 va = sa[i], vb = sb[i];
+                a[4 * i] = va.x; a[4 * i + 1] = va.y; a[4 * i + 2] = va.z; a[4 * i + 3] = va.w;
+                b[4 * i] = vb.x; b[4 * i + 1] = vb.y; b[4 * i + 2] = vb.z; b[4 * i + 3] = vb.w;
+            }
+            MF_CORE(a, b, core);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int y = 2 * j + half;                       // output row of the tile; its window: rows y+1 .. y+9
+            const int rex = half == 0 ? 2 * j + 1 : 2 * j + 10;
+            unsigned e[9], s[5];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) e[i] = Rs[(rex * 9 + i) * MM_TX + lane];
+            MF_SELECT(core, e, s);                            // ranks 39 .. 43 of the window's 81 keys
+            if (lane < gt.len && y < ct.len) {
+                const int i = gt.start + lane, jpos = ct.start + y;
+                const int xa = max(gt.lo, i - 4), xb = min(gt.hi - 1, i + 4);
+                const int ya = max(ct.lo, jpos - 4), yb = min(ct.hi - 1, jpos + 4);
+                const int n = (xb - xa + 1) * (yb - ya + 1);
+                // padding keys of the window: a checkerboard, LOW where (hx + r) is even
+                const int w_low = ((lane + y + 1) & 1) ? 40 : 41;
+                const int in_low = (n + ((((xa - hi0) + (ya - hj0)) & 1) ? 0 : 1)) >> 1;
+                const int L = w_low - in_low;
+                const int rho = (n + 1) >> 1;                 // lower middle rank among the window's taps
+                const int k = rho + L;                        // its rank among the 81 keys: 40, 41 or 42
+                const bool even = (n & 1) == 0;
+                const int x0 = lane, r0 = y + 1;
+                const unsigned m1 = s[k - 39], Q1 = m1 >> 8;
+                double v1;
+                if ((s[k - 40] >> 8) == Q1 || (s[k - 38] >> 8) == Q1)
+                    v1 = (Q1 == qM && mode_clean) ? M : mm_exact_rank(Kh, Dh, x0, r0, Q1, rho);
+                else v1 = mm_value_of(Dh, m1, x0, r0);
+                double med = v1;
+                if (even) {
+                    const unsigned m2 = s[k - 38], Q2 = m2 >> 8;
+                    double v2;
+                    if (Q2 == Q1 || (s[k - 37] >> 8) == Q2)
+                        v2 = (Q2 == qM && mode_clean) ? M : mm_exact_rank(Kh, Dh, x0, r0, Q2, rho + 1);
+                    else v2 = mm_value_of(Dh, m2, x0, r0);
+                    med = (v1 + v2) * 0.5;
+                }
+                p.Y[i + p.G * (int64_t)p.cells[jpos]] = med;
+            }
+        }
+    }
+    if (bad && p.err_flag) atomicExch(p.err_flag, 1);
+}
+
 static void make_tiles(const int32_t *start, const int32_t *len, int nblk, int T, std::vector<MfTile> &out) {
     for (int b = 0; b < nblk; ++b) {
         int lo = start[b], hi = start[b] + len[b];
@@ -195,12 +499,16 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
         select_kernel = select_kernel && (c.opt_mf_kernel != 0);
         use_net = (c.opt_mf_kernel == 2 && r == 4) ? 1 : 0;
     }
-    const int TI = select_kernel ? MS_TI : MF_TI, TJ = select_kernel ? MS_TJ : MF_TJ, NT = TI * TJ;
+    // window_size 7 (radius 4): the shared-merge kernel; ICNV_MF_KERNEL=1 (read at icnv_init) keeps the counting selection
+    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel == 3) && mm_smem_bytes() <= (size_t)c.smem_optin;
+    const int TI = merge_kernel ? MM_TX : (select_kernel ? MS_TI : MF_TI), TJ = merge_kernel ? MM_TY : (select_kernel ? MS_TJ : MF_TJ);
+    const int NT = merge_kernel ? MM_NT : TI * TJ;
     bool list32 = false;
     if (c.opt_mf_list32) list32 = select_kernel;   // diagnostic (ICNV_MF_LIST32 at icnv_init)
-    const size_t smem = sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
-                        (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT +
-                        (use_net ? sizeof(float) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) : 0);
+    const size_t smem = merge_kernel ? mm_smem_bytes()
+                                     : sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
+                                           (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT +
+                                           (use_net ? sizeof(float) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) : 0);
     if (smem > (size_t)c.smem_optin || (TI + 2 * r) * (TJ + 2 * r) > 65535)
         return set_error(ICNV_E_UNSUPPORTED, "window_size %d needs %zu B of shared memory per CTA", window_size, smem);
     cudaStream_t st = pick_stream(stream);
@@ -239,7 +547,8 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     };
     int lrc;
     if (list32) use_net = 0;
-    if (!select_kernel) lrc = launch(median_filter_kernel);
+    if (merge_kernel) lrc = launch(median_filter_merge_kernel);
+    else if (!select_kernel) lrc = launch(median_filter_kernel);
     else if (list32 && r == 5) lrc = launch(median_filter_select_kernel<5, unsigned>);
     else if (list32 && r == 4) lrc = launch(median_filter_select_kernel<4, unsigned>);
     else if (r == 2) lrc = launch(median_filter_select_kernel<2>);

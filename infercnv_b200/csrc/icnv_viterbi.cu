@@ -489,18 +489,20 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                     for (int k = 0; k < M; ++k) nu[k] = p.logdelta[k] + le[k];
                     continue;
                 }
-                // ---- t_k = nu[k] + b with k in the 3 low mantissa bits (a <= 7-ulp perturbation, inside
-                //      the certificate's error budget): the running max then carries its own index ----
+                // ---- T1 = max_k (nu[k] + b) and its first index: a compare / select chain carries the index along (strict
+                //      comparison = which.max's first-index rule; scores stay unperturbed, so the certificate's error budget
+                //      is the table error and rounding only) ----
                 double t[MAXM];
 #pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    const double v = nu[k] + b;
-                    t[k] = __hiloint2double(__double2hiint(v), (__double2loint(v) & ~7) | k);
-                }
+                for (int k = 0; k < M; ++k) t[k] = nu[k] + b;
                 double T1 = t[0];
+                int i1 = 0;
 #pragma unroll
-                for (int k = 1; k < M; ++k) T1 = (t[k] > T1) ? t[k] : T1;   // compare + select: fmax() is ~8 instructions in FP64
-                const int i1 = __double2loint(T1) & 7;
+                for (int k = 1; k < M; ++k) {
+                    const bool gt = t[k] > T1;   // compare + select: fmax() is ~8 instructions in FP64
+                    T1 = gt ? t[k] : T1;
+                    i1 = gt ? k : i1;
+                }
                 // ---- per state: stay (nu[k] + a) or come from the best state (T1).  With a > b the best
                 //      state always stays, so the runner-up is never a third state unless T1 - t[k] is
                 //      itself small - which the second check catches. --------------------------------------
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                     const int he = __double2hiint(e);
                     const bool stay = he >= 0;
                     mg = min(mg, (unsigned)(he & 0x7fffffff));                      // |stay - from_best|
-                    mg = min(mg, (unsigned)__double2hiint(T1 - t[k]) - 1u);         // best vs this state (0 for k == i1 wraps to max)
+                    mg = min(mg, (k == i1) ? 0x7fffffffu : (unsigned)__double2hiint(T1 - t[k]));   // best vs every other state (an exact tie: 0)
                     nu[k] = (stay ? d : T1) + le[k];
                     moved = __funnelshift_l((uint32_t)he, moved, 1);
                 }
@@ -860,6 +862,9 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     for (int j = 0; j < m && structured; ++j)
         for (int k = 0; k < m; ++k)
             if (Pi[j + m * k] != (j == k ? Pi[0] : Pi[1])) structured = false;
+    // ... with the diagonal the larger one ("the best state always stays" is what the fast recursion relies on) and every
+    // transition possible (log 0 would poison the margins): t <= 1/6 for i6, 1/3 for i3, and t > 0
+    structured = structured && Pi[0] > Pi[1] && Pi[1] > 0.0;
     const bool use_fast = (c.hmm_mode == 1) && structured && !want_margin;
 
     if (!use_fast) {

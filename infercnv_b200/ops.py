@@ -315,7 +315,9 @@ def predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj: Infercnv, cluster_b
     Pi, delta, mean, _ = get_HMM(cnv_mean_sd, t)
     obs = [np.asarray(v) for v in infercnv_obj.observation_grouped_cell_indices.values()]
     refs = [np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()]
-    groups = (obs if cluster_by_groups else [np.concatenate(obs)]) + refs
+    # cluster_by_groups = FALSE: the reference's c(all_observations = unlist(obs), <reference list>) makes every observation
+    # cell a list element of its own (R coerces the integer vector into the list): one-cell "samples"
+    groups = (obs if cluster_by_groups else [np.asarray([c]) for c in np.concatenate(obs)]) + refs
     sds = np.concatenate([_state_emission_sds(len(g), cnv_mean_sd, cnv_level_to_mean_sd_fit) for g in groups])
     return _run_hmm(infercnv_obj, Pi, delta, mean, sds, groups)
 
@@ -350,7 +352,9 @@ def i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples(infercnv_obj: Infercnv, clu
     Pi, delta, mean, sd = i3HMM_get_HMM(sd_trend, t, i3_p_val, use_KS)
     obs = [np.asarray(v) for v in infercnv_obj.observation_grouped_cell_indices.values()]
     refs = [np.asarray(v) for v in infercnv_obj.reference_grouped_cell_indices.values()]
-    groups = (obs if cluster_by_groups else [np.concatenate(obs)]) + refs
+    # cluster_by_groups = FALSE: the reference's c(all_observations = unlist(obs), <reference list>) makes every observation
+    # cell a list element of its own (R coerces the integer vector into the list): one-cell "samples"
+    groups = (obs if cluster_by_groups else [np.asarray([c]) for c in np.concatenate(obs)]) + refs
     return _run_hmm(infercnv_obj, Pi, delta, mean, np.tile(sd, len(groups)), groups)
 
 

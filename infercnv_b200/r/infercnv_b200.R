@@ -132,7 +132,10 @@ b200_predict_CNV_via_HMM_on_whole_tumor_samples <- function(infercnv_obj, cluste
         cnv_mean_sd=infercnv:::get_spike_dists(infercnv_obj@.hspike),
         cnv_level_to_mean_sd_fit=infercnv:::get_hspike_cnv_mean_sd_trend_by_num_cells_fit(infercnv_obj@.hspike), t=1e-6) {
     obs <- infercnv_obj@observation_grouped_cell_indices
-    groups <- c(if (isTRUE(cluster_by_groups)) obs else list(all_observations = unlist(obs)),
+    ## cluster_by_groups = FALSE: the reference writes c(all_observations = unlist(obs), <list of reference groups>)
+    ## (R/inferCNV_HMM.R:531, R/inferCNV_i3HMM.R:356); c() of an integer vector and a list makes every observation cell a
+    ## list element of its own, i.e. each observation cell is a one-cell "sample" (rowMeans = the cell, sd for num_cells = 1)
+    groups <- c(if (isTRUE(cluster_by_groups)) obs else as.list(unlist(obs, use.names=FALSE)),
                 infercnv_obj@reference_grouped_cell_indices)
     groups <- lapply(groups, as.integer)
     sds <- unlist(lapply(groups, function(g)
@@ -172,7 +175,10 @@ b200_i3HMM_predict_CNV_via_HMM_on_tumor_subclusters <- function(infercnv_obj, i3
 b200_i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples <- function(infercnv_obj, cluster_by_groups, i3_p_val=0.05,
         sd_trend=infercnv:::.i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj, i3_p_val), t=1e-6, use_KS=TRUE) {
     obs <- infercnv_obj@observation_grouped_cell_indices
-    groups <- c(if (isTRUE(cluster_by_groups)) obs else list(all_observations = unlist(obs)),
+    ## cluster_by_groups = FALSE: the reference writes c(all_observations = unlist(obs), <list of reference groups>)
+    ## (R/inferCNV_HMM.R:531, R/inferCNV_i3HMM.R:356); c() of an integer vector and a list makes every observation cell a
+    ## list element of its own, i.e. each observation cell is a one-cell "sample" (rowMeans = the cell, sd for num_cells = 1)
+    groups <- c(if (isTRUE(cluster_by_groups)) obs else as.list(unlist(obs, use.names=FALSE)),
                 infercnv_obj@reference_grouped_cell_indices)
     groups <- lapply(groups, as.integer)
     HMM_info <- infercnv:::.i3HMM_get_HMM(sd_trend, t=t, i3_p_val=i3_p_val, use_KS=use_KS)

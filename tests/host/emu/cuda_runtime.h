@@ -63,6 +63,8 @@ struct int4 {
     int x, y, z, w;
 };
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline unsigned __double2uint_rd(double v) { return v > 0.0 ? (v >= 4294967295.0 ? 4294967295u : (unsigned)v) : 0u; }
 
 // ---- runtime API --------------------------------------------------------------------------------------------------
 typedef int cudaError_t;

@@ -94,6 +94,19 @@ def test_hmm_drivers_and_median_filter_through_the_mirror(example_object, hmm_fi
     sds = np.concatenate([hmm_fixture["sd"] * len(g) ** -0.5 for g in groups])
     want_g = orc.viterbi_matrix(o.expr_data, cs, cl, Pi, delta, hmm_fixture["mean"], sds, groups=groups)
     np.testing.assert_array_equal(samples.expr_data, want_g.astype(float))
+    # cluster_by_groups = FALSE: c(all_observations = unlist(obs), reference_list) in the reference (HMM.R:531) makes every
+    # observation cell its own one-cell sample (sd for num_cells = 1), the reference groups stay groups
+    flat = ops.predict_CNV_via_HMM_on_whole_tumor_samples(o, False, cnv_mean_sd, fit, t=1e-6)
+    groups1 = [np.asarray([c]) for c in ex["obs_groups"][0]] + [ex["ref_groups"][0]]
+    sds1 = np.concatenate([hmm_fixture["sd"] * len(g) ** -0.5 for g in groups1])
+    want_1 = orc.viterbi_matrix(o.expr_data, cs, cl, Pi, delta, hmm_fixture["mean"], sds1, groups=groups1)
+    np.testing.assert_array_equal(flat.expr_data, want_1.astype(float))
+    obs_cols = ex["obs_groups"][0]   # a one-cell sample at sd(num_cells = 1) is the per-cell HMM of that cell
+    np.testing.assert_array_equal(flat.expr_data[:, obs_cols], cells.expr_data[:, obs_cols])
+    i3flat = ops.i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples(o, False, i3_p_val=0.05, t=1e-6, use_KS=False)
+    Pi3f, d3f, mean3f, sd3f = orc.i3_hmm_params(o.expr_data, ex["ref_groups"][0])
+    want_3f = orc.viterbi_matrix(o.expr_data, cs, cl, Pi3f, d3f, mean3f, np.tile(sd3f, len(groups1)), groups=groups1)
+    np.testing.assert_array_equal(i3flat.expr_data, want_3f.astype(float))
     sub = ops.predict_CNV_via_HMM_on_tumor_subclusters(o, cnv_mean_sd, fit, t=1e-6)
     sgroups = [ex["subclusters"][0], ex["subclusters"][1]]
     want_s = orc.viterbi_matrix(o.expr_data, cs, cl, Pi, delta, hmm_fixture["mean"], sds, groups=sgroups)

@@ -321,6 +321,28 @@ def test_viterbi_modes_agree_with_oracle_at_scale(api, hmm_fixture, mode):
         assert reruns == 0
 
 
+@pytest.mark.parametrize("m,t", [(6, 0.18), (3, 0.4), (6, 0.0)])
+def test_viterbi_transition_matrices_outside_the_fast_paths_structure(api, hmm_fixture, m, t):
+    """The certified fast path assumes .get_HMM's matrix with the diagonal the larger entry ("the best state stays") and
+    every transition possible.  A t that makes moving cheaper than staying (t > 1/6 for i6, > 1/3 for i3), or t = 0
+    (log 0 = -inf off the diagonal), must take the reference-order kernel: same states as the oracle."""
+    rng = np.random.default_rng(31 + m)
+    lens = [120, 45, 300]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G, C = int(np.sum(lens)), 40
+    if m == 6:
+        mean, sd = hmm_fixture["mean"], hmm_fixture["sd"]
+    else:
+        mean, sd = np.array([0.8, 1.0, 1.2]), np.array([0.1] * 3)
+    X = _hmm_input(rng, G, C, mean)
+    Pi = np.full((m, m), t, order="F")
+    np.fill_diagonal(Pi, 1 - 5 * t)
+    delta = np.full(m, 1.0 / m)
+    want = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sd)
+    got = api.viterbi(X, cs, lens, Pi, delta, mean, sd)
+    np.testing.assert_array_equal(got, want)
+
+
 def test_viterbi_fast_path_exact_ties_are_rerun(api):
     """Two states with identical scores at every gene (dyadic, symmetric means): the certificate
     sees a zero margin, the sequences are recomputed in reference-order arithmetic, and the
@@ -516,6 +538,40 @@ def test_median_filter_key_network_variant_is_exact(api, monkeypatch):
         want = orc.median_filter(X, cs, lens, groups, 7, nthreads=orc.max_threads())
         assert np.array_equal(got, ref), name
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-15, err_msg=name)
+
+
+def test_median_filter_shared_merge_kernel_edges_and_ties(api):
+    """window_size 7 runs the shared-merge kernel (sorted 9-key runs per list position, pair / quad merges shared between
+    neighbouring outputs, ranks 39..43 of the 81 keys read off per output).  Blocks smaller than the window in either
+    direction (every window truncated, even tap counts -> mean of the two middle values), blocks that end inside a tile,
+    a de-noised-like matrix (most values one constant), small integers, values closer together than the 24-bit keys
+    resolve (the exact rank is then settled on the doubles), and a large spread: all equal to the oracle."""
+    rng = np.random.default_rng(77)
+    lens = [1, 3, 8, 9, 33, 70, 2, 41]
+    cs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    G = int(np.sum(lens))
+    sizes = [1, 2, 5, 9, 40, 33, 64, 3]
+    C = int(np.sum(sizes)) + 4                      # four cells in no list: copied through
+    order = rng.permutation(C)
+    groups, pos = [], 0
+    for n in sizes:
+        groups.append(order[pos:pos + n])
+        pos += n
+    base = 1.0 + 0.1 * rng.normal(size=(G, C))
+    cases = {
+        "smooth": base,
+        "denoised": np.where(np.abs(base - 1.0) < 0.12, 1.000123, base),
+        "states": rng.integers(1, 7, size=(G, C)).astype(float),
+        "sub-key": 1.0 + 1e-12 * rng.integers(0, 50, size=(G, C)) + np.where(rng.random((G, C)) < 0.05, 3.0, 0.0),
+        "spread": np.exp(rng.normal(scale=6.0, size=(G, C))),
+        "constant": np.full((G, C), 2.5),
+    }
+    for name, X in cases.items():
+        X = np.asfortranarray(X)
+        got = api.median_filter(X, cs, lens, groups, 7)
+        want = orc.median_filter(X, cs, lens, groups, 7, nthreads=orc.max_threads())
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-15, err_msg=name)
+        np.testing.assert_array_equal(got[:, order[pos:]], X[:, order[pos:]], err_msg=name)
 
 
 def test_median_filter_example_object_subclusters(api, example_object):
