@@ -14,8 +14,39 @@
 
 .icnv_env <- new.env()
 
+## STATUS: experimental.  The shim is compile-checked against a mock of Rinternals.h and the same C entry points are
+## exercised through ctypes by the repository's GPU tests, but this R layer has not been executed under R yet (no R in the
+## build image); see INTEGRATION.md for the check list of a first run.
+
 .icnv_enabled <- function() {
-    isTRUE(getOption("infercnv.b200", TRUE)) && isTRUE(tryCatch(.Call("icnvR_available"), error = function(e) FALSE))
+    if (!isTRUE(getOption("infercnv.b200", TRUE))) return(FALSE)
+    ok <- .icnv_try(.Call("icnvR_available"), error = function(e) {
+        if (is.null(.icnv_env$warned_unavailable)) {     # once per session: a broken GPU install must not be invisible
+            .icnv_env$warned_unavailable <- TRUE
+            futile.logger::flog.warn(sprintf("infercnv_b200: GPU path unavailable (%s); every step runs the R implementation", conditionMessage(e)))
+        }
+        FALSE
+    })
+    if (!isTRUE(ok) && is.null(.icnv_env$warned_unavailable)) {
+        .icnv_env$warned_unavailable <- TRUE
+        futile.logger::flog.warn("infercnv_b200: no usable CUDA device; every step runs the R implementation")
+    }
+    isTRUE(ok)
+}
+
+## one .Call into the library; an error is LOGGED (never swallowed silently) and turned into NULL = "use the R original"
+.icnv_try <- function(expr, what) {
+    tryCatch(expr, error = function(e) {
+        futile.logger::flog.warn(sprintf("infercnv_b200: %s failed on the GPU (%s); falling back to the R implementation (hours at scale)",
+                                         what, conditionMessage(e)))
+        NULL
+    })
+}
+
+## Single-process multi-GPU: infercnv::run() is one R process and its num_threads never reaches this path
+## (R/inferCNV_ops.R:388); after this call the library shards the cells of the streaming entry points over the devices.
+infercnvb200_init_devices <- function(device_ids = NULL) {
+    .Call("icnvR_init_devices", if (is.null(device_ids)) NULL else as.integer(device_ids))
 }
 
 ## envelope: base dense double matrix without NA/NaN/Inf (the R smoother strips NAs per cell,
@@ -47,8 +78,7 @@ b200_subtract_ref_expr_from_obs <- function(infercnv_obj, inv_log=FALSE, use_bou
     m <- infercnv_obj@expr.data
     if (!.icnv_enabled() || !.icnv_ok(m)) return(orig(infercnv_obj, inv_log=inv_log, use_bounds=use_bounds))
     futile.logger::flog.info(sprintf("::subtract_ref_expr_from_obs:Start inv_log=%s, use_bounds=%s (B200)", inv_log, use_bounds))
-    res <- tryCatch(.Call("icnvR_subtract_ref", m, .icnv_ref_groups(infercnv_obj), inv_log, use_bounds),
-                    error = function(e) NULL)
+    res <- tryCatch(.Call("icnvR_subtract_ref", m, .icnv_ref_groups(infercnv_obj), inv_log, use_bounds), "available")
     if (is.null(res)) return(orig(infercnv_obj, inv_log=inv_log, use_bounds=use_bounds))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     if (!is.null(infercnv_obj@.hspike)) {
@@ -66,7 +96,7 @@ b200_smooth_by_chromosome <- function(infercnv_obj, window_length, smooth_ends=T
     ## even or < 2 windows: the reference's behaviour is accidental / identity - leave it to R
     if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes) || window_length < 2 || window_length %% 2 == 0)
         return(orig(infercnv_obj, window_length, smooth_ends))
-    res <- tryCatch(.Call("icnvR_smooth", m, codes, as.integer(window_length)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_smooth", m, codes, as.integer(window_length)), "smooth")
     if (is.null(res)) return(orig(infercnv_obj, window_length, smooth_ends))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     if (!is.null(infercnv_obj@.hspike)) {
@@ -82,7 +112,7 @@ b200_center_cell_expr_across_chromosome <- function(infercnv_obj, method="mean")
     m <- infercnv_obj@expr.data
     if (!.icnv_enabled() || !.icnv_ok(m)) return(orig(infercnv_obj, method))
     futile.logger::flog.info("::center_smooth across chromosomes per cell (B200)")
-    res <- tryCatch(.Call("icnvR_center", m, identical(method, "median")), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_center", m, identical(method, "median")), "center")
     if (is.null(res)) return(orig(infercnv_obj, method))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     if (!is.null(infercnv_obj@.hspike)) {
@@ -98,8 +128,8 @@ b200_center_cell_expr_across_chromosome <- function(infercnv_obj, method="mean")
     codes <- .icnv_chr_codes(infercnv_obj)
     if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes)) return(NULL)
     sd <- if (is.null(sds)) HMM_info[["state_emission_params"]]$sd else sds
-    res <- tryCatch(.Call("icnvR_viterbi", m, codes, groups, HMM_info[["state_transitions"]], HMM_info[["delta"]],
-                          HMM_info[["state_emission_params"]]$mean, as.double(sd)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_viterbi", m, codes, groups, HMM_info[["state_transitions"]], HMM_info[["delta"]],
+                          HMM_info[["state_emission_params"]]$mean, as.double(sd)), "viterbi")
     if (is.null(res)) return(NULL)
     .icnv_keep_names(res, m)
 }
@@ -201,7 +231,7 @@ b200_apply_median_filtering <- function(infercnv_obj, window_size=7, on_observat
     if (on_observations) for (tt in names(infercnv_obj@observation_grouped_cell_indices))
         lists <- c(lists, lapply(infercnv_obj@tumor_subclusters[["subclusters"]][[tt]], as.integer))
     if (on_references) lists <- c(lists, lapply(infercnv_obj@reference_grouped_cell_indices, as.integer))
-    res <- tryCatch(.Call("icnvR_median_filter", m, codes, lists, as.integer(window_size)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_median_filter", m, codes, lists, as.integer(window_size)), "median_filter")
     if (is.null(res)) return(orig(infercnv_obj, window_size, on_observations, on_references))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     infercnv_obj
@@ -212,8 +242,7 @@ b200_normalize_counts_by_seq_depth <- function(infercnv_obj, normalize_factor=NA
     m <- infercnv_obj@expr.data
     if (.icnv_enabled() && methods::is(m, "dgCMatrix") && !anyNA(m@x)) {
         ## sparse counts (R/inferCNV.R:158-160): the compressed columns cross PCIe, the dense normalised matrix comes back
-        res <- tryCatch(.Call("icnvR_csc_normalize", m@p, m@i, as.double(m@x), dim(m), as.double(normalize_factor)),
-                        error = function(e) NULL)
+        res <- .icnv_try(.Call("icnvR_csc_normalize", m@p, m@i, as.double(m@x), dim(m), as.double(normalize_factor)), "csc_normalize")
         if (!is.null(res)) {
             futile.logger::flog.info("normalizing counts matrix by depth (B200, sparse input)")
             infercnv_obj@expr.data <- .icnv_keep_names(res, m)
@@ -221,7 +250,7 @@ b200_normalize_counts_by_seq_depth <- function(infercnv_obj, normalize_factor=NA
         }
     }
     if (!.icnv_enabled() || !.icnv_ok(m)) return(.icnv_env$orig$normalize_counts_by_seq_depth(infercnv_obj, normalize_factor))
-    res <- tryCatch(.Call("icnvR_normalize", m, as.double(normalize_factor)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_normalize", m, as.double(normalize_factor)), "normalize")
     if (is.null(res)) return(.icnv_env$orig$normalize_counts_by_seq_depth(infercnv_obj, normalize_factor))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     infercnv_obj
@@ -234,7 +263,7 @@ b200_clear_noise_via_ref_mean_sd <- function(infercnv_obj, sd_amplifier=1.5, noi
     if (!.icnv_enabled() || !.icnv_ok(m) || isTRUE(noise_logistic)) return(orig(infercnv_obj, sd_amplifier, noise_logistic))
     cells <- if (length(infercnv_obj@reference_grouped_cell_indices) > 0)
         unlist(infercnv_obj@reference_grouped_cell_indices) else unlist(infercnv_obj@observation_grouped_cell_indices)
-    res <- tryCatch(.Call("icnvR_clear_noise", m, as.integer(cells), as.double(sd_amplifier)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_clear_noise", m, as.integer(cells), as.double(sd_amplifier)), "clear_noise")
     if (is.null(res)) return(orig(infercnv_obj, sd_amplifier, noise_logistic))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     infercnv_obj
@@ -257,9 +286,9 @@ b200_predict_CNV_via_HMM_on_tumor_subclusters_per_chr <- function(infercnv_obj, 
         infercnv:::.get_state_emission_params(length(g), cnv_mean_sd, cnv_level_to_mean_sd_fit)$sd))
     HMM_info <- infercnv:::.get_HMM(cnv_mean_sd, t)
     tumor_subclusters <- lapply(unlist(infercnv_obj@tumor_subclusters[["subclusters"]], recursive=FALSE), as.integer)
-    res <- tryCatch(.Call("icnvR_viterbi_per_chr", m, codes, flat, as.integer(cumsum(c(0L, lengths(per)))),
+    res <- .icnv_try(.Call("icnvR_viterbi_per_chr", m, codes, flat, as.integer(cumsum(c(0L, lengths(per)))),
                           HMM_info[["state_transitions"]], HMM_info[["delta"]], HMM_info[["state_emission_params"]]$mean,
-                          as.double(sds), tumor_subclusters), error = function(e) NULL)
+                          as.double(sds), tumor_subclusters), "viterbi_per_chr")
     if (is.null(res)) return(orig(infercnv_obj, subclusters_per_chr, cnv_mean_sd, cnv_level_to_mean_sd_fit, t))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     infercnv_obj
@@ -271,7 +300,7 @@ b200_scale_infercnv_expr <- function(infercnv_obj) {
     m <- infercnv_obj@expr.data
     if (!.icnv_enabled() || !.icnv_ok(m)) return(orig(infercnv_obj))
     futile.logger::flog.info("-scaling expr data (B200)")
-    res <- tryCatch(.Call("icnvR_scale", m), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_scale", m), "scale")
     if (is.null(res)) return(orig(infercnv_obj))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     if (!is.null(infercnv_obj@.hspike)) {
@@ -291,8 +320,8 @@ b200_remove_outliers_norm <- function(infercnv_obj, out_method="average_bound", 
         return(orig(infercnv_obj, out_method, lower_bound, upper_bound))
     futile.logger::flog.info(paste("::remove_outlier_norm:Start (B200)", "out_method:", out_method, "lower_bound:", lower_bound,
                                    "upper_bound:", upper_bound))
-    res <- tryCatch(.Call("icnvR_remove_outliers", m, as.double(if (hard) lower_bound else NA),
-                          as.double(if (hard) upper_bound else NA)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_remove_outliers", m, as.double(if (hard) lower_bound else NA),
+                          as.double(if (hard) upper_bound else NA)), "remove_outliers")
     if (is.null(res)) return(orig(infercnv_obj, out_method, lower_bound, upper_bound))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     if (!is.null(infercnv_obj@.hspike)) {
@@ -309,8 +338,7 @@ b200_clear_noise <- function(infercnv_obj, threshold, noise_logistic=FALSE) {
     if (!.icnv_enabled() || !.icnv_ok(m) || threshold == 0) return(orig(infercnv_obj, threshold, noise_logistic))
     cells <- if (length(infercnv_obj@reference_grouped_cell_indices) > 0)
         as.integer(unlist(infercnv_obj@reference_grouped_cell_indices)) else NULL
-    res <- tryCatch(.Call("icnvR_clear_noise_threshold", m, cells, as.double(threshold), isTRUE(noise_logistic)),
-                    error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_clear_noise_threshold", m, cells, as.double(threshold), isTRUE(noise_logistic)), "clear_noise_threshold")
     if (is.null(res)) return(orig(infercnv_obj, threshold, noise_logistic))
     infercnv_obj@expr.data <- .icnv_keep_names(res, m)
     infercnv_obj
@@ -342,8 +370,8 @@ b200_get_predicted_CNV_regions <- function(infercnv_obj, by=c("consensus", "subc
         cell_groups <- as.list(cells)
         names(cell_groups) <- colnames(m)[cells]
     }
-    res <- tryCatch(.Call("icnvR_cnv_regions", m, codes, as.double(go$start), as.double(go$stop),
-                          lapply(cell_groups, as.integer)), error = function(e) NULL)
+    res <- .icnv_try(.Call("icnvR_cnv_regions", m, codes, as.double(go$start), as.double(go$stop),
+                          lapply(cell_groups, as.integer)), "cnv_regions")
     if (is.null(res)) return(orig(infercnv_obj, by))
     names(res) <- c("seq", "chr", "first_gene", "last_gene", "state", "start", "end")
     chr_levels <- unique(go$chr)                       # order of appearance = the order of the chromosome ranges
@@ -365,6 +393,47 @@ b200_get_predicted_CNV_regions <- function(infercnv_obj, by=c("consensus", "subc
              cnv_ranges = data.frame(cnv_name = cnv_name[sel], state = res$state[sel], chr = chr_levels[res$chr[sel]],
                                      start = res$start[sel], end = res$end[sel]))
     })
+}
+
+## run() steps 4, 8 .. 12, 14 (and step 17 for analysis_mode = "cells") as ONE library call: one upload of the matrix instead
+## of four round trips through the per-step closures above.  infercnv::run() itself calls the steps one by one
+## (R/inferCNV_ops.R:771, 865, 911, 952, 1031), so this is for callers that drive the steps themselves, or for a maintainer's
+## three-line change in run() (INTEGRATION.md, "fused block").  Input: the object after step 3 (depth-normalised counts, before
+## log2) when apply_log = TRUE, after step 4 otherwise; use_bounds / max_centered_threshold / window_length as in run().
+## HMM_info (optional): the list .get_HMM() / .i3HMM_get_HMM() returns -> per-cell states are predicted on the block's output
+## in the same pass.  Returns list(infercnv_obj = <after step 14>, hmm_obj = <states object or NULL>); NULL when the input is
+## outside the GPU path's envelope (the caller then runs the R steps).
+infercnvb200_run_smooth_block <- function(infercnv_obj, window_length=101, max_centered_threshold=3, use_bounds=TRUE,
+                                          apply_log=TRUE, HMM_info=NULL) {
+    m <- infercnv_obj@expr.data
+    codes <- .icnv_chr_codes(infercnv_obj)
+    if (!.icnv_enabled() || !.icnv_ok(m) || is.null(codes) || window_length < 2 || window_length %% 2 == 0 ||
+        is.na(max_centered_threshold) || !is.numeric(max_centered_threshold)) return(NULL)
+    futile.logger::flog.info(sprintf("::smooth block (steps 4, 8-12, 14%s) in one pass (B200)", if (is.null(HMM_info)) "" else " + per-cell HMM"))
+    refs <- .icnv_ref_groups(infercnv_obj)
+    hmm_obj <- NULL
+    if (is.null(HMM_info)) {
+        res <- .icnv_try(.Call("icnvR_smooth_block", m, codes, refs, isTRUE(apply_log), as.double(max_centered_threshold),
+                               as.integer(window_length), isTRUE(use_bounds)), "smooth_block")
+        if (is.null(res)) return(NULL)
+        infercnv_obj@expr.data <- .icnv_keep_names(res, m)
+    } else {
+        res <- .icnv_try(.Call("icnvR_smooth_hmm", m, codes, refs, isTRUE(apply_log), as.double(max_centered_threshold),
+                               as.integer(window_length), isTRUE(use_bounds), HMM_info[["state_transitions"]], HMM_info[["delta"]],
+                               HMM_info[["state_emission_params"]]$mean, as.double(HMM_info[["state_emission_params"]]$sd)),
+                         "smooth_hmm")
+        if (is.null(res)) return(NULL)
+        infercnv_obj@expr.data <- .icnv_keep_names(res[[1]], m)
+        hmm_obj <- infercnv_obj
+        hmm_obj@expr.data <- .icnv_keep_names(res[[2]], m)
+    }
+    if (!is.null(infercnv_obj@.hspike)) {
+        futile.logger::flog.info("-mirroring for hspike")
+        h <- infercnvb200_run_smooth_block(infercnv_obj@.hspike, window_length, max_centered_threshold, use_bounds, apply_log, NULL)
+        if (is.null(h)) return(NULL)
+        infercnv_obj@.hspike <- h$infercnv_obj
+    }
+    list(infercnv_obj = infercnv_obj, hmm_obj = hmm_obj)
 }
 
 infercnvb200_install <- function() {

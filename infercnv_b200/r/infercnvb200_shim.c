@@ -122,6 +122,44 @@ SEXP icnvR_smooth_block(SEXP expr, SEXP chr_codes, SEXP ref_groups, SEXP apply_l
     return ans;
 }
 
+/* fused run() steps 4, 8-12, 14 AND step 17 for analysis_mode = "cells" (per-cell i6 / i3 HMM on the block's output):
+ * ONE upload of the matrix, the smoothed matrix and one byte per state back.  Returns list(expr, states). */
+SEXP icnvR_smooth_hmm(SEXP expr, SEXP chr_codes, SEXP ref_groups, SEXP apply_log, SEXP threshold, SEXP window_length,
+                      SEXP use_bounds, SEXP Pi, SEXP delta, SEXP mean, SEXP sd) {
+    SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
+    int64_t G = INTEGER(dim)[0], C = INTEGER(dim)[1];
+    int m = Rf_length(delta);
+    int32_t *cs = NULL, *cl = NULL, *off = NULL, *idx = NULL;
+    int K = chr_to_ranges(chr_codes, &cs, &cl);
+    int n_grp = list_to_csr(ref_groups, &off, &idx);
+    uint8_t *st = (uint8_t *)malloc((size_t)(G * C));
+    SEXP ans = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP y = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    SEXP states = PROTECT(Rf_allocMatrix(REALSXP, (int)G, (int)C));
+    int rc = (K < 0 || n_grp < 0 || !st) ? ICNV_E_NOMEM
+                                         : icnv_smooth_hmm_u8_f64(REAL(expr), REAL(y), st, G, C, cs, cl, K, off, idx, n_grp,
+                                                                  Rf_asLogical(apply_log), Rf_asReal(threshold),
+                                                                  Rf_asInteger(window_length), Rf_asLogical(use_bounds), m, REAL(Pi),
+                                                                  REAL(delta), REAL(mean), REAL(sd));
+    if (rc == 0) {
+        double *out = REAL(states);   /* the reference keeps states as doubles (HMM.R:320) */
+        for (int64_t i = 0; i < G * C; ++i) out[i] = (st[i] == 255) ? -1.0 : (double)st[i];
+    }
+    SET_VECTOR_ELT(ans, 0, y);
+    SET_VECTOR_ELT(ans, 1, states);
+    free(cs); free(cl); free(off); free(idx); free(st);
+    UNPROTECT(3);
+    fail_if(rc);
+    return ans;
+}
+
+/* icnv_init_devices: single-process multi-GPU (infercnv::run() is one R process).  ids = NULL: every GPU present. */
+SEXP icnvR_init_devices(SEXP ids) {
+    int rc = Rf_isNull(ids) ? icnv_init_devices(0, NULL) : icnv_init_devices(Rf_length(ids), INTEGER(ids));
+    fail_if(rc);
+    return Rf_ScalarInteger(icnv_devices_in_use());
+}
+
 /* predict_CNV_via_HMM_on_* / i3HMM_predict_* (HMM.R:284-567, i3HMM.R:180-389): groups = NULL -> per cell */
 SEXP icnvR_viterbi(SEXP expr, SEXP chr_codes, SEXP groups, SEXP Pi, SEXP delta, SEXP mean, SEXP sd) {
     SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
@@ -360,6 +398,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_remove_outliers", (DL_FUNC)&icnvR_remove_outliers, 3},
     {"icnvR_viterbi_per_chr", (DL_FUNC)&icnvR_viterbi_per_chr, 9}, {"icnvR_scale", (DL_FUNC)&icnvR_scale, 1},
     {"icnvR_clear_noise_threshold", (DL_FUNC)&icnvR_clear_noise_threshold, 4},
+    {"icnvR_smooth_hmm", (DL_FUNC)&icnvR_smooth_hmm, 11},   {"icnvR_init_devices", (DL_FUNC)&icnvR_init_devices, 1},
     {NULL, NULL, 0}};
 
 void R_init_infercnvb200_shim(DllInfo *dll) {

@@ -29,6 +29,7 @@ int Rf_asInteger(SEXP);
 double Rf_asReal(SEXP);
 int Rf_isNull(SEXP);
 SEXP Rf_ScalarLogical(int);
+SEXP Rf_ScalarInteger(int);
 void Rf_error(const char *, ...) __attribute__((noreturn));
 int R_registerRoutines(DllInfo *, const void *, const R_CallMethodDef *, const void *, const void *);
 int R_useDynamicSymbols(DllInfo *, int);

@@ -4,6 +4,8 @@ known answers.  Needs a B200: run with `pytest -m gpu`.
 Tolerances (BASELINE.json north_star): smoothed matrix within 1e-5 relative; HMM state calls
 bit-identical.  The smooth tests additionally report how far below that the kernels actually are.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -461,6 +463,18 @@ def test_oligodendroglioma_hmm_cells_and_samples(api, oligo, hmm_fixture):
     want3 = orc.viterbi_matrix(S, cs, cl, Pi3, d3, mean3, sd3, nthreads=nt)
     got3 = api.viterbi(S, cs, cl, Pi3, d3, mean3, sd3)
     np.testing.assert_array_equal(got3, want3)
+
+
+def test_viterbi_equals_the_50_digit_restatement_on_c1(api):
+    """The i6 and i3 state calls of ten c1 cells against Viterbi.dthmm.adj evaluated with 50 significant digits
+    (tests/golden/hmm_mpmath_c1.npz, tools/make_hmm_mpmath_fixture.py; smallest arg-max margin 2e-5): the states every faithful
+    double-precision evaluation must return, the reference's R included."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "hmm_mpmath_c1.npz"))
+    X = np.asfortranarray(d["X"])
+    for tag in ("i6", "i3"):
+        got = api.viterbi(X, d["chr_start"], d["chr_len"], np.asfortranarray(d[tag + "_Pi"]), d[tag + "_delta"], d[tag + "_mean"],
+                          d[tag + "_sd"])
+        np.testing.assert_array_equal(got, d[tag + "_states"].astype(got.dtype), err_msg=tag)
 
 
 def test_multi_slab_host_pipeline_and_fused_call(api, hmm_fixture):

@@ -1,5 +1,7 @@
 """Oracle self-consistency for the parts the reference has no fixture for (Viterbi, median filter):
 C restatement vs an independent pure-Python transcription, plus the documented quirks."""
+import os
+
 import numpy as np
 import pytest
 
@@ -112,3 +114,18 @@ def test_i3_params(example_object):
     assert np.isclose(mu, vals.mean(), rtol=1e-13) and np.isclose(sg, vals.std(ddof=1), rtol=1e-12)
     Pi, delta, mean, sd = orc.i3_hmm_params(X, ref)
     assert mean[0] < mean[1] < mean[2] and np.isclose(mean[2] - mean[1], 1.6448536269514722 * sg)
+
+
+def test_oracle_viterbi_equals_the_50_digit_restatement_on_c1():
+    """tests/golden/hmm_mpmath_c1.npz (tools/make_hmm_mpmath_fixture.py): Viterbi.dthmm.adj evaluated with 50 significant
+    digits on ten cells of the bundled oligodendroglioma example (all 22 chromosomes, i6 and i3), with the smallest arg-max
+    margin of every sequence.  The margins (>= 2e-5) are seven orders of magnitude above what double-precision rounding can
+    accumulate over a chromosome, so the exact states are what any faithful double-precision evaluation - the reference's R
+    included - must return; the C oracle returns them."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "hmm_mpmath_c1.npz"))
+    X = np.asfortranarray(d["X"])
+    for tag in ("i6", "i3"):
+        assert d[tag + "_margins"].min() > 1e-6
+        got = orc.viterbi_matrix(X, d["chr_start"], d["chr_len"], np.asfortranarray(d[tag + "_Pi"]), d[tag + "_delta"],
+                                 d[tag + "_mean"], d[tag + "_sd"], nthreads=orc.max_threads())
+        np.testing.assert_array_equal(got, d[tag + "_states"].astype(got.dtype), err_msg=tag)
