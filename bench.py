@@ -386,11 +386,15 @@ def rscript_reference(args, cfg, G, C_total, seed):
         X, cs, cl, ref_local, lists, what, _ = cpu_sample(args, cfg, G, C_total, seed, n)
         with tempfile.TemporaryDirectory() as td:
             X.T.astype("<f8").tofile(os.path.join(td, "x.bin"))      # cells contiguous = R column-major G x n
-            meta = {"G": int(G), "C": int(X.shape[1]), "chr_len": [int(v) for v in cl], "refs": [[int(i) + 1 for i in g] for g in ref_local],
-                    "hmm": cfg["hmm"], "median_filter": bool(cfg["median_filter"]),
-                    "lists": [[int(i) + 1 for i in g] for g in (lists or [])], "i6_mean": list(map(float, I6_MEAN)),
-                    "i6_sd": list(map(float, I6_SD)), "steps": max(1, min(args.steps, 2)), "rdir": rdir}
-            json.dump(meta, open(os.path.join(td, "meta.json"), "w"))
+            np.savetxt(os.path.join(td, "chr_len.txt"), cl, fmt="%d")
+            np.savetxt(os.path.join(td, "i6_mean.txt"), I6_MEAN, fmt="%.17g")
+            np.savetxt(os.path.join(td, "i6_sd.txt"), I6_SD, fmt="%.17g")
+            wl = lambda f, ls: open(os.path.join(td, f), "w").write("\n".join(" ".join(str(int(i) + 1) for i in g) for g in ls) + "\n")  # noqa: E731
+            wl("refs.txt", ref_local)
+            wl("lists.txt", lists or [])
+            open(os.path.join(td, "meta.txt"), "w").write("\n".join([f"G={int(G)}", f"C={int(X.shape[1])}", f"hmm={cfg['hmm']}",
+                                                                     f"median_filter={1 if cfg['median_filter'] else 0}",
+                                                                     f"steps={max(1, min(args.steps, 2))}", f"rdir={rdir}"]) + "\n")
             r = subprocess.run([rs, script, td], capture_output=True, text=True, timeout=3000)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode == 0 and line:

@@ -21,7 +21,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from infercnv_b200 import ops  # noqa: E402
+from mirror import ops  # noqa: E402
 
 
 def main(out_dir):

@@ -329,6 +329,14 @@ ICNV_API int icnv_dev_group_partial_sums_f64(const double *X, int64_t G, int64_t
 ICNV_API int icnv_dev_bounds_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
                                                const int32_t *row_off, const int64_t *counts, double *lo, double *hi,
                                                double *mid, void *stream);
+/* The group means themselves from the same layout of chunk sums: means[g + G*k] (rowMeans of a group spread over ranks -
+ * the group modes of the HMM, R/inferCNV_HMM.R:383 - in the fixed chunk order, so the rank count does not matter). */
+ICNV_API int icnv_dev_means_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
+                                              const int32_t *row_off, const int64_t *counts, double *means, void *stream);
+/* Group-mode broadcast on the device: out[g + G*c] = group_states[g + G*grp_of[c]], 255 where grp_of[c] < 0
+ * (R/inferCNV_HMM.R:368, 399: every cell of a group gets the group's trace, cells in no group stay unassigned). */
+ICNV_API int icnv_dev_scatter_group_states_u8(const uint8_t *group_states, int64_t G, int64_t C, const int32_t *grp_of,
+                                              uint8_t *out, void *stream);
 /* means[g] = (sum_q partial[g + G*q], q ascending) / count */
 ICNV_API int icnv_dev_combine_partials_f64(const double *partial, int64_t G, int64_t n_chunks, int64_t count,
                                            double *means, void *stream);

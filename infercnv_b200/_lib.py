@@ -51,6 +51,8 @@ SIGNATURES = {
     "icnv_dev_group_partial_sums_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, c_int, c_int, _P, _P]),
     "icnv_dev_combine_partials_f64": (c_int, [_P, c_i64, c_i64, c_i64, _P, _P]),
     "icnv_dev_bounds_from_partials_f64": (c_int, [_P, c_i64, c_int, c_i64, c_int, _P, _P, _P, _P, _P, _P]),
+    "icnv_dev_means_from_partials_f64": (c_int, [_P, c_i64, c_int, c_i64, c_int, _P, _P, _P, _P]),
+    "icnv_dev_scatter_group_states_u8": (c_int, [_P, c_i64, c_i64, _P, _P, _P]),
     "icnv_dev_bounds_from_means_f64": (c_int, [_P, c_i64, c_int, _P, _P, _P, _P]),
     "icnv_dev_cell_pipeline_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P, c_i64, _P, _P, c_int, c_int, _P, _P, _P,
                                            ct.c_double, c_int, c_int, _P, _P, _P, c_int, _P, _P]),

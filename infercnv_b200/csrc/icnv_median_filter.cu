@@ -267,30 +267,30 @@ __global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfP
     const MfTile gt = p.gene_tiles[blockIdx.y];
     const MfTile ct = p.cell_tiles[blockIdx.x];
     const int hi0 = gt.start - 4, hj0 = ct.start - 5;   // halo (hx, r) = gene hi0 + hx, list position hj0 + r
-    // ---- S0: halo, tile range, keys ----------------------------------------------------------------------------------------
+    // ---- S0: halo, tile range, keys (a warp per halo row: lanes over the row's 40 genes, no index divisions) ---------------
     bool bad = false;
     double vmin = INFINITY, vmax = -INFINITY;
-    long long *rowbase = reinterpret_cast<long long *>(redd + 40);   // [ROWS] column offset of the row's cell, -1 outside the list
-    for (int r = tid; r < MM_ROWS; r += MM_NT) {
+    int *modecnt = reinterpret_cast<int *>(redd + 32);   // [4] matches of the four candidate values, [4] "cell not clean" flag
+    if (tid < 8) modecnt[tid] = 0;
+    for (int r = warp; r < MM_ROWS; r += MM_NW) {
         const int jj = hj0 + r;
-        rowbase[r] = (jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8) ? (long long)p.G * (long long)p.cells[jj] : -1ll;
-    }
-    __syncthreads();
-    for (int e = tid; e < MM_ROWS * MM_HX; e += MM_NT) {
-        const int r = e / MM_HX, hx = e - r * MM_HX;
-        const int ii = hi0 + hx;
-        const long long rb = rowbase[r];
-        double v = 0.0;
-        if (ii >= gt.lo && ii < gt.hi && rb >= 0) {
-            v = p.X[ii + rb];
-            if (is_finite_d(v)) {
-                vmin = v < vmin ? v : vmin;
-                vmax = v > vmax ? v : vmax;
-            } else {
-                bad = true;
+        const bool row_in = jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
+        const long long rb = row_in ? (long long)p.G * (long long)p.cells[jj] : 0ll;
+#pragma unroll
+        for (int hx = lane; hx < MM_HX; hx += 32) {
+            const int ii = hi0 + hx;
+            double v = 0.0;
+            if (row_in && ii >= gt.lo && ii < gt.hi) {
+                v = p.X[ii + rb];
+                if (is_finite_d(v)) {
+                    vmin = v < vmin ? v : vmin;
+                    vmax = v > vmax ? v : vmax;
+                } else {
+                    bad = true;
+                }
             }
+            Dh[r * MM_HX + hx] = v;
         }
-        Dh[e] = v;
     }
     vmin = warp_min_d(vmin);
     vmax = warp_max_d(vmax);
@@ -298,42 +298,68 @@ __global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfP
         redd[warp] = vmin;
         redd[16 + warp] = vmax;
     }
-    int *modecnt = reinterpret_cast<int *>(redd + 32);   // [4] matches of the four candidate values, [4] "cell not clean" flag
-    if (tid < 8) modecnt[tid] = 0;
     __syncthreads();
-    vmin = redd[0];
-    vmax = redd[16];
-#pragma unroll
-    for (int w = 1; w < MM_NW; ++w) {
-        vmin = redd[w] < vmin ? redd[w] : vmin;
-        vmax = redd[16 + w] > vmax ? redd[16 + w] : vmax;
-    }
-    const double QMAX = 16777213.0;   // quantised values 1 .. 2^24 - 2: strictly between the two padding keys
-    const double scale = (vmax > vmin) ? QMAX / (vmax - vmin) : 0.0;
-    // The matrices this filter sees are full of ONE repeated value (exactly 1 after the dead-band subtraction and 2^x, the
-    // reference mean after de-noising): nearly every window's median then has rank neighbours with the same key cell, which
-    // would send it through the exact-rank scan.  Four taps of the tile nominate candidates for that value; the most
-    // frequent one (M) is remembered together with whether its key cell holds nothing but copies of it - then a median whose
-    // key falls into that cell IS M, whatever the ties.
+    // The matrices this filter sees hold ONE value many times over (exactly 1 after the dead-band subtraction and 2^x, the
+    // reference mean after de-noising).  Four taps of the tile nominate candidates for it; the most frequent one (M) is
+    // remembered together with whether its key cell holds nothing but copies of it - then a median whose key falls into
+    // that cell IS M, however many ties surround it.
     const int c_r[4] = {MM_ROWS / 2, MM_ROWS / 2, 3 * MM_ROWS / 4, MM_ROWS / 4};
     const int c_x[4] = {MM_HX / 2, MM_HX / 4, 3 * MM_HX / 4, MM_HX / 2 + 3};
-    double cand[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {   // a nominee outside the block nominates nothing (NaN equals no value)
-        const int ii = hi0 + c_x[q];
-        cand[q] = (ii >= gt.lo && ii < gt.hi && rowbase[c_r[q]] >= 0) ? Dh[c_r[q] * MM_HX + c_x[q]] : __longlong_as_double(0x7ff8000000000000ll);
-    }
-    {
-        int cnt[4] = {0, 0, 0, 0};
-        for (int e = tid; e < MM_ROWS * MM_HX; e += MM_NT) {
-            const double v = Dh[e];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) cnt[q] += (v == cand[q]) ? 1 : 0;
+    if (warp == 0) {   // tile range and the nominees, once
+        double a = lane < MM_NW ? redd[lane] : INFINITY, b = lane < MM_NW ? redd[16 + lane] : -INFINITY;
+        a = warp_min_d(a);
+        b = warp_max_d(b);
+        if (lane == 0) {
+            redd[40] = a;
+            redd[41] = b;
         }
+        if (lane < 4) {   // a nominee outside the block nominates nothing (NaN equals no value)
+            const int ii = hi0 + c_x[lane], jj = hj0 + c_r[lane];
+            redd[42 + lane] = (ii >= gt.lo && ii < gt.hi && jj >= ct.lo && jj < ct.hi) ? Dh[c_r[lane] * MM_HX + c_x[lane]]
+                                                                                         : __longlong_as_double(0x7ff8000000000000ll);
+        }
+    }
+    __syncthreads();
+    vmin = redd[40];
+    vmax = redd[41];
+    const double QMAX = 16777213.0;   // quantised values 1 .. 2^24 - 2: strictly between the two padding keys
+    const double scale = (vmax > vmin) ? QMAX / (vmax - vmin) : 0.0;
+    auto quant = [&](double v) -> unsigned {
+        double qd = (v - vmin) * scale;
+        qd = qd < QMAX ? qd : QMAX;       // (also maps NaN to QMAX)
+        qd = qd > 0.0 ? qd : 0.0;
+        return 1u + __double2uint_rd(qd);
+    };
+    {
+        const double c0 = redd[42], c1 = redd[43], c2 = redd[44], c3 = redd[45];
+        int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        for (int r = warp; r < MM_ROWS; r += MM_NW) {
+            const int jj = hj0 + r;
+            const bool row_in = jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int tot = __reduce_add_sync(0xffffffffu, cnt[q]);
-            if (lane == 0 && tot) atomicAdd(&modecnt[q], tot);
+            for (int hx = lane; hx < MM_HX; hx += 32) {
+                const int ii = hi0 + hx;
+                const double v = Dh[r * MM_HX + hx];
+                unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
+                if (row_in && ii >= gt.lo && ii < gt.hi) {
+                    key = (quant(v) << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
+                    n0 += (v == c0) ? 1 : 0;
+                    n1 += (v == c1) ? 1 : 0;
+                    n2 += (v == c2) ? 1 : 0;
+                    n3 += (v == c3) ? 1 : 0;
+                }
+                Kh[r * MM_HX + hx] = key;
+            }
+        }
+        n0 = __reduce_add_sync(0xffffffffu, n0);
+        n1 = __reduce_add_sync(0xffffffffu, n1);
+        n2 = __reduce_add_sync(0xffffffffu, n2);
+        n3 = __reduce_add_sync(0xffffffffu, n3);
+        if (lane == 0) {
+            if (n0) atomicAdd(&modecnt[0], n0);
+            if (n1) atomicAdd(&modecnt[1], n1);
+            if (n2) atomicAdd(&modecnt[2], n2);
+            if (n3) atomicAdd(&modecnt[3], n3);
         }
     }
     __syncthreads();
@@ -341,28 +367,20 @@ __global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfP
 #pragma unroll
     for (int q = 1; q < 4; ++q)
         if (modecnt[q] > modecnt[best]) best = q;
-    const double M = cand[best];
-    auto quant = [&](double v) -> unsigned {
-        double qd = (v - vmin) * scale;
-        qd = qd < QMAX ? qd : QMAX;       // (also maps NaN to QMAX)
-        qd = qd > 0.0 ? qd : 0.0;
-        return 1u + __double2uint_rd(qd);
-    };
+    const double M = redd[42 + best];
     const unsigned qM = quant(M);
-    bool dirty = false;   // a value other than M in M's key cell
-    for (int e = tid; e < MM_ROWS * MM_HX; e += MM_NT) {
-        const int r = e / MM_HX, hx = e - r * MM_HX;
-        const int ii = hi0 + hx;
-        unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
-        if (ii >= gt.lo && ii < gt.hi && rowbase[r] >= 0) {
-            const double v = Dh[e];
-            const unsigned q = quant(v);
-            dirty |= (q == qM) && (v != M);
-            key = (q << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
-        }
-        Kh[e] = key;
+    if (modecnt[best] >= 16) {   // worth knowing: is M's key cell clean (nothing but copies of M)?
+        bool dirty = false;
+        for (int r = warp; r < MM_ROWS; r += MM_NW)
+#pragma unroll
+            for (int hx = lane; hx < MM_HX; hx += 32) {
+                const unsigned key = Kh[r * MM_HX + hx];
+                dirty |= (key != MM_LOW) && (key != MM_HIGH) && ((key >> 8) == qM) && (Dh[r * MM_HX + hx] != M);
+            }
+        if (dirty) modecnt[4] = 1;
+    } else if (tid == 0) {
+        modecnt[4] = 1;
     }
-    if (dirty) modecnt[4] = 1;
     __syncthreads();
     const bool mode_clean = modecnt[4] == 0;
     // ---- S1: sorted runs, pairs ----------------------------------------------------------------------------------------------
@@ -450,20 +468,29 @@ __global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfP
                 const int k = rho + L;                        // its rank among the 81 keys: 40, 41 or 42
                 const bool even = (n & 1) == 0;
                 const int x0 = lane, r0 = y + 1;
-                const unsigned m1 = s[k - 39], Q1 = m1 >> 8;
-                double v1;
-                if ((s[k - 40] >> 8) == Q1 || (s[k - 38] >> 8) == Q1)
-                    v1 = (Q1 == qM && mode_clean) ? M : mm_exact_rank(Kh, Dh, x0, r0, Q1, rho);
-                else v1 = mm_value_of(Dh, m1, x0, r0);
+                // the value of the key at index ki of s[] (rank 39 + ki), real rank rk: its tap when no rank neighbour shares its
+                // key cell; when the whole cell lies inside ranks 40..42 its (at most 3) doubles are read and ordered here;
+                // M when the cell is the tile's clean dominant one; the exact-rank scan otherwise
+                auto value_at = [&](int ki, int rk) -> double {
+                    const unsigned Qc = s[ki] >> 8;
+                    const bool tl = (s[ki - 1] >> 8) == Qc, th = (s[ki + 1] >> 8) == Qc;
+                    if (!tl && !th) return mm_value_of(Dh, s[ki], x0, r0);
+                    if (Qc == qM && mode_clean) return M;
+                    int lo = ki, hi = ki;
+                    while (lo > 0 && (s[lo - 1] >> 8) == Qc) --lo;
+                    while (hi < 4 && (s[hi + 1] >> 8) == Qc) ++hi;
+                    if (lo == 0 || hi == 4 || hi - lo > 2) return mm_exact_rank(Kh, Dh, x0, r0, Qc, rk);
+                    double d0 = mm_value_of(Dh, s[lo], x0, r0), d1 = mm_value_of(Dh, s[lo + 1], x0, r0);
+                    double d2 = (hi - lo == 2) ? mm_value_of(Dh, s[lo + 2], x0, r0) : INFINITY;
+                    mf_cswap(d0, d1);
+                    mf_cswap(d1, d2);
+                    mf_cswap(d0, d1);
+                    const int t = ki - lo;
+                    return t == 0 ? d0 : (t == 1 ? d1 : d2);
+                };
+                const double v1 = value_at(k - 39, rho);
                 double med = v1;
-                if (even) {
-                    const unsigned m2 = s[k - 38], Q2 = m2 >> 8;
-                    double v2;
-                    if (Q2 == Q1 || (s[k - 37] >> 8) == Q2)
-                        v2 = (Q2 == qM && mode_clean) ? M : mm_exact_rank(Kh, Dh, x0, r0, Q2, rho + 1);
-                    else v2 = mm_value_of(Dh, m2, x0, r0);
-                    med = (v1 + v2) * 0.5;
-                }
+                if (even) med = (v1 + value_at(k - 38, rho + 1)) * 0.5;
                 p.Y[i + p.G * (int64_t)p.cells[jpos]] = med;
             }
         }

@@ -104,6 +104,7 @@ struct PartialBoundsParams {
     int row_off[33];      // rows of group k inside a rank's block: row_off[k] .. row_off[k + 1]
     double count[32];     // global group sizes
     double *lo, *hi, *mid;
+    double *means;        // optional: the group means themselves, [n_grp][G]
 };
 
 __global__ void __launch_bounds__(256) bounds_from_partials_kernel(const PartialBoundsParams p) {
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256) bounds_from_partials_kernel(const Partial
             for (int q = r0; q < r1; ++q) s += base[g + p.G * q];
         }
         const double m = s / p.count[k];  // a true division by the count, as mean() does
+        if (p.means) p.means[g + p.G * k] = m;
         if (k == 0) {
             mn = m;
             mx = m;
@@ -126,8 +128,10 @@ __global__ void __launch_bounds__(256) bounds_from_partials_kernel(const Partial
         mx = fmax(mx, m);
         sm += m;
     }
-    p.lo[g] = mn;
-    p.hi[g] = mx;
+    if (p.lo) {
+        p.lo[g] = mn;
+        p.hi[g] = mx;
+    }
     if (p.mid) p.mid[g] = sm / (double)p.n_grp;
 }
 
@@ -1642,12 +1646,10 @@ int icnv_dev_combine_partials_f64(const double *partial, int64_t G, int64_t n_ch
     return ICNV_OK;
 }
 
-int icnv_dev_bounds_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
-                                      const int32_t *row_off, const int64_t *counts, double *lo, double *hi, double *mid,
-                                      void *stream) {
-    ICNV_REQUIRE_READY();
-    if (!partials || !lo || !hi || !row_off || !counts || G <= 0 || world <= 0 || n_grp <= 0 || n_grp > 32 || tot_rows <= 0)
-        return set_error(ICNV_E_BAD_ARG, "icnv_dev_bounds_from_partials_f64: bad argument (at most 32 groups)");
+static int launch_partials(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp, const int32_t *row_off,
+                           const int64_t *counts, double *lo, double *hi, double *mid, double *means, void *stream, const char *who) {
+    if (!partials || !row_off || !counts || G <= 0 || world <= 0 || n_grp <= 0 || n_grp > 32 || tot_rows <= 0)
+        return set_error(ICNV_E_BAD_ARG, "%s: bad argument (at most 32 groups per call)", who);
     PartialBoundsParams p;
     p.part = partials;
     p.G = G;
@@ -1657,15 +1659,33 @@ int icnv_dev_bounds_from_partials_f64(const double *partials, int64_t G, int wor
     for (int k = 0; k <= n_grp; ++k) p.row_off[k] = row_off[k];
     for (int k = 0; k < n_grp; ++k) {
         if (counts[k] <= 0 || row_off[k + 1] < row_off[k] || row_off[k + 1] > tot_rows)
-            return set_error(ICNV_E_BAD_ARG, "icnv_dev_bounds_from_partials_f64: bad group %d", k);
+            return set_error(ICNV_E_BAD_ARG, "%s: bad group %d", who, k);
         p.count[k] = (double)counts[k];
     }
     p.lo = lo;
     p.hi = hi;
     p.mid = mid;
+    p.means = means;
     bounds_from_partials_kernel<<<(unsigned)((G + 255) / 256), 256, 0, pick_stream(stream)>>>(p);
     ICNV_CHECK_LAUNCH("bounds_from_partials_kernel");
     return ICNV_OK;
+}
+
+int icnv_dev_bounds_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
+                                      const int32_t *row_off, const int64_t *counts, double *lo, double *hi, double *mid,
+                                      void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!lo || !hi) return set_error(ICNV_E_BAD_ARG, "icnv_dev_bounds_from_partials_f64: bad argument");
+    return launch_partials(partials, G, world, tot_rows, n_grp, row_off, counts, lo, hi, mid, nullptr, stream,
+                           "icnv_dev_bounds_from_partials_f64");
+}
+
+int icnv_dev_means_from_partials_f64(const double *partials, int64_t G, int world, int64_t tot_rows, int n_grp,
+                                     const int32_t *row_off, const int64_t *counts, double *means, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!means) return set_error(ICNV_E_BAD_ARG, "icnv_dev_means_from_partials_f64: bad argument");
+    return launch_partials(partials, G, world, tot_rows, n_grp, row_off, counts, nullptr, nullptr, nullptr, means, stream,
+                           "icnv_dev_means_from_partials_f64");
 }
 
 int icnv_dev_bounds_from_means_f64(const double *means, int64_t G, int n_grp, double *lo, double *hi, double *mid,

@@ -750,11 +750,33 @@ __global__ void __launch_bounds__(256) scatter_group_states_kernel(const uint8_t
     }
 }
 
+// the same with one byte per state (255 = cell in no group)
+__global__ void __launch_bounds__(256) scatter_group_states_u8_kernel(const uint8_t *__restrict__ gs, int64_t G, int64_t C,
+                                                                      const int32_t *__restrict__ grp_of, uint8_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < G * C; i += stride) {
+        int64_t c = i / G, g = i - c * G;
+        int grp = grp_of[c];
+        out[i] = grp < 0 ? (uint8_t)255 : gs[g + G * grp];
+    }
+}
+
 }  // namespace icnv
 
 using namespace icnv;
 
 extern "C" {
+
+int icnv_dev_scatter_group_states_u8(const uint8_t *gs, int64_t G, int64_t C, const int32_t *grp_of, uint8_t *out, void *stream) {
+    ICNV_REQUIRE_READY();
+    if (!gs || !grp_of || !out || G <= 0 || C <= 0) return set_error(ICNV_E_BAD_ARG, "icnv_dev_scatter_group_states_u8: bad argument");
+    int64_t blocks = (G * C + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    scatter_group_states_u8_kernel<<<(unsigned)blocks, 256, 0, pick_stream(stream)>>>(gs, G, C, grp_of, out);
+    ICNV_CHECK_LAUNCH("scatter_group_states_u8_kernel");
+    return ICNV_OK;
+}
 
 int icnv_dev_widen_states(const uint8_t *s, int32_t *out, int64_t n, void *stream) {
     ICNV_REQUIRE_READY();

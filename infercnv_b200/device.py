@@ -59,6 +59,28 @@ class Engine:
         tdist.all_gather(parts, host)
         out.copy_(torch.stack(parts).to(out.device))
 
+    def _all_gather_list(self, t: torch.Tensor):
+        """every rank's `t` (same shape on all ranks) as a list in rank order"""
+        import torch.distributed as tdist
+        world = tdist.get_world_size()
+        if tdist.get_backend() == "nccl":
+            parts = [torch.empty_like(t) for _ in range(world)]
+            tdist.all_gather(parts, t)
+            return parts
+        host = t.detach().cpu().contiguous()
+        parts = [torch.empty_like(host) for _ in range(world)]
+        tdist.all_gather(parts, host)
+        return [x.to(t.device) for x in parts]
+
+    def _all_reduce_sum(self, t: torch.Tensor) -> None:
+        import torch.distributed as tdist
+        if tdist.get_backend() == "nccl":
+            tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
+            return
+        host = t.detach().cpu().contiguous()
+        tdist.all_reduce(host, op=tdist.ReduceOp.SUM)
+        t.copy_(host.to(t.device))
+
     # ---- data ---------------------------------------------------------------------------------------
     def synth(self, G, chr_start, chr_len, cells_global, C_total, seed) -> torch.Tensor:
         """Synthetic depth-normalised expression for the given GLOBAL cell indices (runs of
@@ -301,6 +323,65 @@ class Engine:
                                                  flag.data_ptr(), _stream_ptr()))
         return (st, flag, mg) if want_margins else (st, flag)
 
+    def viterbi_groups(self, X, chr_start, chr_len, Pi, delta, mean, sds, groups_local, group_sizes=None, max_chunks=None, out=None):
+        """Group modes of the HMM (predict_CNV_via_HMM_on_tumor_subclusters / _on_whole_tumor_samples and the i3 twins,
+        R/inferCNV_HMM.R:345-408, 509-567): per group x = rowMeans(X[, group]) (:383), ONE trace per (group, chromosome),
+        written to every cell of the group; cells in no group stay 255.  groups_local: per group this rank's LOCAL columns,
+        a contiguous slice of the group's list cut at multiples of CHUNK (what plan_shards does for the groups it is given) or
+        the whole group; group_sizes / max_chunks: the global sizes and the largest per-rank chunk count (defaults: this
+        rank holds every group whole).  sds: m values per group (.get_state_emission_params), or m values for all.
+        Across ranks the groups' chunk sums are all-gathered (32 groups per exchange) and combined in list order, every rank
+        runs the few group sequences itself and scatters the states to its own cells: identical bits for any rank count."""
+        C, G = X.shape
+        cs, cl = _i32(chr_start), _i32(chr_len)
+        Pi = np.asfortranarray(Pi, dtype=np.float64)
+        m = Pi.shape[0]
+        delta, mean = (np.ascontiguousarray(v, dtype=np.float64) for v in (delta, mean))
+        groups_local = [np.asarray(g, dtype=np.int32) for g in groups_local]
+        n_grp = len(groups_local)
+        sizes = [len(g) for g in groups_local] if group_sizes is None else [int(v) for v in group_sizes]
+        world = self._world()
+        if max_chunks is None:
+            if world > 1 and group_sizes is not None:
+                raise ValueError("viterbi_groups: max_chunks is needed when groups are spread over ranks")
+            max_chunks = [(len(g) + shard.CHUNK - 1) // shard.CHUNK for g in groups_local]
+        sds = np.asarray(sds, dtype=np.float64).reshape(-1)
+        if sds.size == m:
+            sds = np.tile(sds, n_grp)
+        sd_med = np.median(sds.reshape(n_grp, m), axis=1)          # object$pm$sd = median(object$pm$sd), HMM.R:1122
+        means = torch.empty((n_grp, G), dtype=torch.float64, device=self.tdev)
+        for k0 in range(0, n_grp, 32):
+            k1 = min(n_grp, k0 + 32)
+            rows = np.concatenate([[0], np.cumsum([int(max_chunks[k]) for k in range(k0, k1)])]).astype(np.int32)
+            tot = max(int(rows[-1]), 1)
+            packed = torch.zeros((tot, G), dtype=torch.float64, device=self.tdev)
+            for k in range(k0, k1):
+                n = len(groups_local[k])
+                if n:
+                    idx = torch.as_tensor(groups_local[k], device=self.tdev)
+                    _lib.check(self.lib.icnv_dev_group_partial_sums_f64(X.data_ptr(), G, X.stride(0), idx.data_ptr(), n, shard.CHUNK, 0,
+                                                                        packed.data_ptr() + 8 * G * int(rows[k - k0]), _stream_ptr()))
+            part = packed
+            if world > 1:
+                part = torch.empty((world, tot, G), dtype=torch.float64, device=self.tdev)
+                self._all_gather(part, packed)
+            counts = np.asarray(sizes[k0:k1], dtype=np.int64)
+            _lib.check(self.lib.icnv_dev_means_from_partials_f64(part.data_ptr(), G, world, tot, k1 - k0, rows.ctypes.data,
+                                                                 counts.ctypes.data, means[k0].data_ptr(), _stream_ptr()))
+        d_sd = torch.as_tensor(sd_med, device=self.tdev)
+        gst = torch.empty((n_grp, G), dtype=torch.uint8, device=self.tdev)
+        flag = torch.zeros(1, dtype=torch.int32, device=self.tdev)
+        _lib.check(self.lib.icnv_dev_viterbi_f64(means.data_ptr(), G, n_grp, cs.ctypes.data, cl.ctypes.data, len(cs), m, Pi.ctypes.data,
+                                                 delta.ctypes.data, mean.ctypes.data, d_sd.data_ptr(), 1, gst.data_ptr(), None,
+                                                 flag.data_ptr(), _stream_ptr()))
+        grp_of = np.full(C, -1, dtype=np.int32)
+        for k, g in enumerate(groups_local):
+            grp_of[g] = k
+        d_grp_of = torch.as_tensor(grp_of, device=self.tdev)
+        st = torch.empty((C, G), dtype=torch.uint8, device=self.tdev) if out is None else out
+        _lib.check(self.lib.icnv_dev_scatter_group_states_u8(gst.data_ptr(), G, C, d_grp_of.data_ptr(), st.data_ptr(), _stream_ptr()))
+        return st, flag
+
     def mean_sd(self, X, groups_local):
         """mu / sigma over all values of the listed cells across ALL ranks (.i3HMM_get_sd_trend_by_num_cells_fit,
         R/inferCNV_i3HMM.R:17-30).  groups_local: per group, this rank's LOCAL columns (the planner's slices).
@@ -323,15 +404,11 @@ class Engine:
             allstats = stats[:, :n].cpu().numpy()
         else:
             mine = torch.tensor(lens, dtype=torch.int64, device=self.tdev)
-            all_lens = [torch.zeros_like(mine) for _ in range(world)]
-            tdist.all_gather(all_lens, mine)
-            all_lens = [t.cpu().numpy() for t in all_lens]
+            all_lens = [t.cpu().numpy() for t in self._all_gather_list(mine)]
             nmax = int(max(int(l.sum()) for l in all_lens))
             padded = torch.zeros((2, max(nmax, 1)), dtype=torch.float64, device=self.tdev)
             padded[:, :n] = stats[:, :n]
-            gathered = [torch.empty_like(padded) for _ in range(world)]
-            tdist.all_gather(gathered, padded)
-            gathered = [g.cpu().numpy() for g in gathered]
+            gathered = [g.cpu().numpy() for g in self._all_gather_list(padded)]
             cols = []
             for k in range(len(lens)):          # group-major, rank-minor = the global list order
                 for r in range(world):
@@ -431,7 +508,7 @@ class Engine:
         import torch.distributed as tdist
         counts = self.state_counts(S, groups_local)
         if self.collective and tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1:
-            tdist.all_reduce(counts, op=tdist.ReduceOp.SUM)
+            self._all_reduce_sum(counts)
         n_grp, G, _ = counts.shape
         cons = torch.empty((n_grp, G), dtype=torch.uint8, device=self.tdev)
         _lib.check(self.lib.icnv_dev_consensus_from_counts(counts.data_ptr(), G, n_grp, cons.data_ptr(), _stream_ptr()))

@@ -17,7 +17,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import api
+from infercnv_b200 import api
 
 log = logging.getLogger("infercnv_b200")  # the R functions log through futile.logger's flog.info
 
@@ -229,7 +229,7 @@ def apply_median_filtering(infercnv_obj: Infercnv, window_size: int = 7, on_obse
 
 # ---- HMM -----------------------------------------------------------------------------------------------
 
-from .hmm import CNV_LEVELS, get_HMM, i3HMM_get_HMM  # noqa: E402,F401  (parameter tables live in hmm.py)
+from infercnv_b200.hmm import CNV_LEVELS, get_HMM, i3HMM_get_HMM  # noqa: E402,F401  (parameter tables live in hmm.py)
 
 
 def i3HMM_get_sd_trend_by_num_cells_fit(infercnv_obj: Infercnv, i3_p_val: float = 0.05) -> dict:

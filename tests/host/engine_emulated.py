@@ -94,6 +94,12 @@ def single():
         cells = [5, 0, 69, 33]
         got, ref = eng.cnv_regions(dS, CS, LENS, gs, ge, cols=cells), orr.cnv_regions(Sh[:, cells], CS, LENS, gs, ge)
         assert all(np.array_equal(got[k], ref[k]) for k in ref)
+    sds_g = np.concatenate([I6_SD * len(g) ** -0.5 for g in groups])
+    Sg, fg = eng.viterbi_groups(Y, CS, LENS, Pi, delta, I6_MEAN, sds_g, groups)
+    want_g = orc.viterbi_matrix(np.asfortranarray(Y.numpy().T), CS, LENS, Pi, delta, I6_MEAN, sds_g, groups=groups)
+    got_g = Sg.numpy().T.astype(np.int32)
+    got_g[got_g == 255] = -1
+    assert np.array_equal(got_g, want_g) and int(fg.item()) == 0, "group-mode HMM differs from the oracle"
     F = eng.median_filter(Y, CS, LENS, groups[:2], 7)
     want_f = orc.median_filter(np.asfortranarray(Y.numpy().T), CS, LENS, groups[:2], 7)
     assert np.allclose(F.numpy().T, want_f, rtol=0, atol=1e-15)
@@ -127,16 +133,39 @@ def rank_main(rank, world, port):
     obs_local = [np.array([pos_of[int(c)] for c in g if int(c) in pos_of], dtype=np.int32) for g in obs_global]
     cons_d = eng.state_consensus(S, obs_local)
     assert int(f.item()) == 0 and int(f2.item()) == 0
+    # median filter on the shard: the reference groups are cut over the ranks (halos of 4 list entries from the neighbours),
+    # the other cells form one list per rank
+    Yext = torch.zeros((Cl + 8 * len(refs), G), dtype=torch.float64)
+    Yext[:Cl] = Y
+    n_ref_local = sum(len(g) for g in plan.local_ref_groups())
+    own = [np.arange(n_ref_local, Cl, dtype=np.int32)] if Cl > n_ref_local else []
+    Fd = eng.median_filter_sharded(Yext, Cl, own, plan.local_ref_groups(), CS, LENS, 7)[:Cl]
+    # group-mode HMM ("samples"): every cell in one of three groups, each cut over the ranks at chunk boundaries
+    all_groups = refs + [np.setdiff1d(np.arange(C_total), np.concatenate(refs))]
+    gplan = shard.plan_shards(C_total, all_groups, world)[rank]
+    Xg = eng.synth(G, CS, LENS, gplan.local_cells, C_total, SEED)
+    sds_g = np.concatenate([I6_SD * len(g) ** -0.5 for g in all_groups])
+    Sgd, _ = eng.viterbi_groups(Xg, CS, LENS, Pi, delta, I6_MEAN + 1.0, sds_g, gplan.local_ref_groups(), gplan.ref_sizes, gplan.max_chunks)
     n_local = torch.tensor([X.shape[0]])
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(sizes, n_local)
     nmax = int(max(s.item() for s in sizes))
     Yp = torch.zeros((nmax, G), dtype=torch.float64); Yp[: X.shape[0]] = Y
     Sp = torch.zeros((nmax, G), dtype=torch.uint8); Sp[: X.shape[0]] = S
+    Fp = torch.zeros((nmax, G), dtype=torch.float64); Fp[: X.shape[0]] = Fd
     Ys = [torch.zeros_like(Yp) for _ in range(world)]
     Ss = [torch.zeros_like(Sp) for _ in range(world)]
+    Fs = [torch.zeros_like(Fp) for _ in range(world)]
+    ng = torch.tensor([Xg.shape[0]])
+    gsz = [torch.zeros_like(ng) for _ in range(world)]
+    dist.all_gather(gsz, ng)
+    gmax = int(max(v.item() for v in gsz))
+    Gp = torch.zeros((gmax, G), dtype=torch.uint8); Gp[: Xg.shape[0]] = Sgd
+    Gs = [torch.zeros_like(Gp) for _ in range(world)]
+    dist.all_gather(Gs, Gp)
     dist.all_gather(Ys, Yp)
     dist.all_gather(Ss, Sp)
+    dist.all_gather(Fs, Fp)
     ok = True
     if rank == 0:
         plans = shard.plan_shards(C_total, refs, world)
@@ -147,16 +176,28 @@ def rank_main(rank, world, port):
         S1, _ = eng.viterbi(Y1, CS, LENS, Pi, delta, I6_MEAN, I6_SD)
         mu_1, sg_1 = eng.mean_sd(Y1, p1.local_ref_groups())
         pos1 = {int(c): i for i, c in enumerate(p1.local_cells)}
-        bad_y = bad_s = 0
+        lists1 = [np.array([pos1[int(c)] for c in p.other_cells], dtype=np.int32) for p in plans if len(p.other_cells)] + \
+            [np.array([pos1[int(c)] for c in g], dtype=np.int32) for g in refs]
+        F1 = eng.median_filter(Y1, CS, LENS, lists1, 7)
+        bad_y = bad_s = bad_f = 0
         for r, p in enumerate(plans):
             idx = torch.tensor([pos1[int(c)] for c in p.local_cells])
             bad_y += int((Ys[r][: len(idx)] != Y1[idx]).sum().item())
             bad_s += int((Ss[r][: len(idx)] != S1[idx]).sum().item())
+            bad_f += int((Fs[r][: len(idx)] != F1[idx]).sum().item())
         cons_1 = eng.state_consensus(S1, [np.array([pos1[int(c)] for c in g], dtype=np.int32) for g in obs_global])
         bad_c = int((cons_1 != cons_d).sum().item())
-        ok = bad_y == 0 and bad_s == 0 and bad_c == 0 and mu_d == mu_1 and sg_d == sg_1
+        g1 = shard.plan_shards(C_total, all_groups, 1)[0]
+        Xg1 = eng.synth(G, CS, LENS, g1.local_cells, C_total, SEED)
+        Sg1, _ = eng.viterbi_groups(Xg1, CS, LENS, Pi, delta, I6_MEAN + 1.0, sds_g, g1.local_ref_groups())
+        posg = {int(c): i for i, c in enumerate(g1.local_cells)}
+        bad_g = 0
+        for r, p in enumerate(shard.plan_shards(C_total, all_groups, world)):
+            idx = torch.tensor([posg[int(c)] for c in p.local_cells])
+            bad_g += int((Gs[r][: len(idx)] != Sg1[idx]).sum().item())
+        ok = bad_y == 0 and bad_s == 0 and bad_f == 0 and bad_c == 0 and bad_g == 0 and mu_d == mu_1 and sg_d == sg_1
         print(f"engine (emulated, {world} gloo ranks, {C_total} cells): values differing from the 1-rank run {bad_y}, states "
-              f"{bad_s}, consensus {bad_c}, mu/sigma {'equal' if (mu_d, sg_d) == (mu_1, sg_1) else 'DIFFER'} -> "
+              f"{bad_s}, group-mode HMM states {bad_g}, median filter (halo exchange) {bad_f}, consensus {bad_c}, mu/sigma {'equal' if (mu_d, sg_d) == (mu_1, sg_1) else 'DIFFER'} -> "
               f"{'BITWISE EQUAL' if ok else 'MISMATCH'}")
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, 0)

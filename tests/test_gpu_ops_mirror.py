@@ -1,4 +1,4 @@
-"""The host-side mirror of the R interface (infercnv_b200/ops.py): the reference's own step sequence
+"""The host-side mirror of the R interface (mirror/ops.py, test infrastructure): the reference's own step sequence
 (run() steps 4, 8, 9, 10, 11, 12, 14 - R/inferCNV_ops.R:614-1031) driven function by function, as
 example/example.Rmd and run(up_to_step=...) do, against the reference's bundled result."""
 import numpy as np
@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _obj(ex, with_hspike=False):
-    from infercnv_b200 import ops
+    from mirror import ops
     X = orc.normalize_by_seq_depth(ex["counts"])           # step 3 (out of scope, test infrastructure)
     o = ops.Infercnv(expr_data=X, gene_order_chr=ex["chr_codes"],
                      reference_grouped_cell_indices={"normal": ex["ref_groups"][0]},
@@ -27,7 +27,8 @@ def _obj(ex, with_hspike=False):
 
 
 def test_stepwise_run_sequence_reproduces_the_reference_golden(example_object):
-    from infercnv_b200 import api, ops
+    from infercnv_b200 import api
+    from mirror import ops
     api.init(0)
     ex = example_object
     o = _obj(ex, with_hspike=True)
@@ -57,7 +58,7 @@ def test_stepwise_run_sequence_reproduces_the_reference_golden(example_object):
 def test_whole_bundled_example_runs_on_the_gpu_counts_to_expr(example_object):
     """count.data -> expr.data of data/infercnv_object_example.rda with EVERY numeric step in the library
     (steps 3, 4..14 fused, 22): nothing of the oracle on the path, only the reference's stored answer."""
-    from infercnv_b200 import ops
+    from mirror import ops
     ex = example_object
     o = ops.Infercnv(expr_data=ex["counts"], gene_order_chr=ex["chr_codes"],
                      reference_grouped_cell_indices={"normal": ex["ref_groups"][0]},
@@ -78,7 +79,7 @@ def test_whole_bundled_example_runs_on_the_gpu_counts_to_expr(example_object):
 
 
 def test_hmm_drivers_and_median_filter_through_the_mirror(example_object, hmm_fixture):
-    from infercnv_b200 import ops
+    from mirror import ops
     ex = example_object
     o = ops.smooth_block(_obj(ex))
     cnv_mean_sd = {k: {"mean": m, "sd": s} for k, m, s in zip(ops.CNV_LEVELS, hmm_fixture["mean"], hmm_fixture["sd"])}

@@ -15,7 +15,7 @@ def world():
     import bench
     from infercnv_b200 import dist as shard
     from infercnv_b200.device import Engine
-    from infercnv_b200.ops import CNV_LEVELS, get_HMM
+    from infercnv_b200.hmm import CNV_LEVELS, get_HMM
     eng = Engine(0)
     G, C = 10000, 10000
     cs, cl = bench.chr_layout(G)

@@ -26,7 +26,8 @@ def test_remove_outliers_norm_known_answers():
 
 
 def test_remove_outliers_norm_mirror_on_the_reference_example(example_object):
-    from infercnv_b200 import api, ops
+    from infercnv_b200 import api
+    from mirror import ops
     X = example_object["expr"]
     H = np.asfortranarray(X[:, :7] * 1.5)
     obj = ops.Infercnv(expr_data=X, gene_order_chr=example_object["chr_codes"],
@@ -46,7 +47,8 @@ def test_remove_outliers_norm_mirror_on_the_reference_example(example_object):
 
 
 def test_clear_noise_known_answers_and_modes(example_object):
-    from infercnv_b200 import api, ops
+    from infercnv_b200 import api
+    from mirror import ops
     m3 = rmat(range(1, 16), 3)
     # .clear_noise(expr, threshold) with center_pos = 0 is what the reference's unit tests pin; through clear_noise()
     # the centre is the mean of the reference cells, so shift the data to put that mean at 0

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _setup(example_object, hmm_fixture):
-    from infercnv_b200 import ops
+    from mirror import ops
     ex = example_object
     X = orc.smooth_block(orc.normalize_by_seq_depth(ex["counts"]), *orc.chr_ranges(ex["chr_codes"]), ex["ref_groups"])
     obj = ops.Infercnv(expr_data=X, gene_order_chr=ex["chr_codes"],
@@ -25,7 +25,8 @@ def _setup(example_object, hmm_fixture):
 
 
 def test_per_chromosome_subcluster_hmm_and_consensus(example_object, hmm_fixture):
-    from infercnv_b200 import api, ops
+    from infercnv_b200 import api
+    from mirror import ops
     obj, cnv_mean_sd, fit = _setup(example_object, hmm_fixture)
     X = obj.expr_data
     G, C = X.shape

@@ -24,7 +24,7 @@ def _csc(D):
     (matrix_three, 8.4, [1, 2, 3]), (matrix_one, 0, []), (matrix_three, 100, [1, 2, 3, 4, 5]),
 ])
 def test_below_min_mean_expr_cutoff_known_answers(mat, cutoff, answer):
-    from infercnv_b200 import ops
+    from mirror import ops
     assert (ops.below_min_mean_expr_cutoff(mat, cutoff) + 1).tolist() == answer
 
 
@@ -48,7 +48,7 @@ def test_gene_stats_match_the_oracle(shape):
 def test_filters_and_remove_genes_on_the_reference_example(oligo):
     """the reference's bundled oligodendroglioma counts, thresholds of example/run.R (cutoff=1) and run()'s default
     min_cells_per_gene=3: same genes kept as the oracle, rows removed from every slot."""
-    from infercnv_b200 import ops
+    from mirror import ops
     X = oligo["counts"]
     G, C = X.shape
     rng = np.random.default_rng(0)
@@ -71,7 +71,8 @@ def test_filters_and_remove_genes_on_the_reference_example(oligo):
 
 
 def test_sparse_counts_ingest_matches_the_dense_reference_steps(oligo):
-    from infercnv_b200 import api, ops
+    from infercnv_b200 import api
+    from mirror import ops
     D = np.rint(oligo["counts"])                 # whole counts: sums are exact in any order -> bit-identical checks
     rng = np.random.default_rng(2)
     D[rng.random(D.shape) < 0.5] = 0.0
@@ -99,7 +100,7 @@ def test_sparse_counts_ingest_matches_the_dense_reference_steps(oligo):
 
 def test_scale_and_chromosome_end_removal(example_object):
     """run() step 5 (scale_data = TRUE) and step 13 (remove_genes_at_chr_ends = TRUE), both mirrored onto @.hspike."""
-    from infercnv_b200 import ops
+    from mirror import ops
     X = example_object["expr"]
     G, C = X.shape
     codes = example_object["chr_codes"]
@@ -126,7 +127,7 @@ def test_scale_and_chromosome_end_removal(example_object):
 
 def test_order_reduce_known_answers():
     """tests/testthat/test_infer_cnv.R:436-490."""
-    from infercnv_b200 import ops
+    from mirror import ops
     data = np.asfortranarray(np.tile(np.arange(1, 11, dtype=float)[:, None], (1, 2)))          # matrix(rep(1:10,2), ncol=2)
     names = ["gene_%d" % i for i in range(1, 11)]
     pos1 = ["gene_%d" % i for i in (10, 5, 8, 3, 4, 9, 1, 7, 6, 2)]

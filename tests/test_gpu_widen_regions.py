@@ -110,7 +110,7 @@ def test_predicted_regions_consensus_and_cell_modes():
 def test_reference_bundled_known_answer_and_report_files(tmp_path):
     """data/HMM_states.rda -> generate_cnv_region_reports(by="subcluster") == what data/mcmc_obj.rda recorded of
     the reference's own run; the four files byte for byte against the oracle's write.table restatement."""
-    from infercnv_b200 import ops
+    from mirror import ops
     z = np.load(GOLD)
     codes = z["chr_codes"]
     levels = [str(s) for s in z["chr_levels"]]

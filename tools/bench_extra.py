@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from infercnv_b200 import dist as shard  # noqa: E402
 from infercnv_b200.device import Engine  # noqa: E402
-from infercnv_b200.ops import i3HMM_get_HMM  # noqa: E402
+from infercnv_b200.hmm import i3HMM_get_HMM  # noqa: E402
 
 eng = Engine(0)
 G, C = 10000, 10000
@@ -54,7 +54,7 @@ Pi3, d3, mean3, sd3 = i3HMM_get_HMM({"mu": mu, "sigma": sg, "mean_delta": abs(No
 ms = timed(lambda: eng.viterbi(Y, cs, cl, Pi3, d3, mean3, sd3))
 out["viterbi_i3"] = {"ms": ms, "cell_genes_per_s": G * C / ms * 1e3, "algorithmic_GBps": 9 * G * C / ms / 1e6}
 # ---- region calling on the device-resident i6 states (K7), ingest (K8) and the element-wise steps (K9) ----
-from infercnv_b200.ops import CNV_LEVELS, get_HMM  # noqa: E402
+from infercnv_b200.hmm import CNV_LEVELS, get_HMM  # noqa: E402
 Pi6, d6, _, _ = get_HMM({k: {"mean": m, "sd": s} for k, m, s in zip(CNV_LEVELS, bench.I6_MEAN, bench.I6_SD)}, 1e-6)
 S, _ = eng.viterbi(Y, cs, cl, Pi6, d6, bench.I6_MEAN, bench.I6_SD)
 gs = np.arange(G, dtype=np.float64) * 1000.0
