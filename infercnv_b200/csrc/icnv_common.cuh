@@ -49,6 +49,7 @@ enum ScratchSlot {
     SLOT_RG_TILES,                    // per-tile region counts and their scanned offsets
     SLOT_RG_REC,                      // region records of the last call (kept until fetched)
     SLOT_VIT_ITEMS,                   // chromosome work items of the Viterbi launch (cached: Ctx::up_items)
+    SLOT_MF_PRE,                      // median filter: range of the matrix and the value sample of its pre-pass
     SLOT_COUNT
 };
 

@@ -11,7 +11,9 @@
 // below (in-place Wirth selection over a private index array).
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "icnv_common.cuh"
@@ -36,6 +38,8 @@ struct MfParams {
     int r;
     int *err_flag;
     int use_net;              // radius 4 only: full windows by the key network (window_median_net81), 0 = counting selection
+    // shared-merge kernel: the matrix' range (keys quantise over it) and its dominant value (NaN: none), found before the launch
+    double vmin, vmax, mode;
 };
 
 // One CTA = a tile of TI genes x TJ list positions (TI*TJ threads, one output each).  The tile's halo
@@ -167,6 +171,31 @@ __global__ void __launch_bounds__(MS_NT, NET ? 2 : 0) median_filter_select_kerne
     if (bad && p.err_flag) atomicExch(p.err_flag, 1);
 }
 
+// Range of the matrix (finite values) for the key quantisation of the shared-merge kernel, and a sample of its values from
+// which the host picks the dominant one.  One read of the matrix (~0.13 ms per 10^8 values).
+__global__ void __launch_bounds__(256) mf_range_kernel(const double *__restrict__ X, int64_t n, unsigned long long *__restrict__ range,
+                                                       double *__restrict__ sample, int n_sample) {
+    double mn = INFINITY, mx = -INFINITY;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = X[i];
+        if (is_finite_d(v)) {
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+        }
+    }
+    mn = warp_min_d(mn);
+    mx = warp_max_d(mx);
+    if ((threadIdx.x & 31) == 0) {
+        if (mn <= mx) {   // order-preserving integer keys: min / max by integer atomics
+            atomicMin(&range[0], key_of(mn));
+            atomicMax(&range[1], key_of(mx));
+        }
+    }
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_sample) sample[t] = X[(int64_t)((double)t * (double)n / (double)n_sample)];
+}
+
 // =================================================================================================
 // window_size 7 (radius 4, 9 x 9 taps - the default of apply_median_filtering): shared-merge networks on 32-bit keys
 // =================================================================================================
@@ -192,18 +221,17 @@ __global__ void __launch_bounds__(MS_NT, NET ? 2 : 0) median_filter_select_kerne
 #define mf_max(a, b) max((unsigned)(a), (unsigned)(b))
 #include "icnv_median_merge.inc"
 
-constexpr int MM_TX = 32, MM_TY = 32;            // outputs per tile: genes (lanes) x list positions
+constexpr int MM_TX = 32;                        // outputs per tile along the genes (lanes)
 constexpr int MM_HX = MM_TX + 8;                 // halo genes
-constexpr int MM_ROWS = MM_TY + 10;              // halo rows 0 .. TY+9 (row r = position y0 - 5 + r; rows 1 .. TY+8 are used)
-constexpr int MM_NW = 16, MM_NT = MM_NW * 32;
-constexpr int MM_NP = MM_TY / 2 + 3;             // P lists: rows (2t, 2t+1), t = 1 .. TY/2+3
-constexpr int MM_NQ = MM_TY / 2 + 2;             // Q lists: P[q] + P[q+1]
 constexpr int MM_PW = 20, MM_QW = 36;            // words per gene and list (P padded to a multiple of 4)
 constexpr unsigned MM_LOW = 0u, MM_HIGH = 0xffffffffu;
 
-constexpr size_t mm_smem_bytes() {
-    return sizeof(double) * MM_ROWS * MM_HX + sizeof(unsigned) * (size_t)MM_ROWS * MM_HX + sizeof(unsigned) * (size_t)MM_ROWS * 9 * MM_TX +
-           sizeof(unsigned) * (size_t)MM_NP * MM_TX * MM_PW + sizeof(unsigned) * (size_t)MM_NQ * MM_TX * MM_QW + 96 * sizeof(double);
+// TY = outputs per tile along the index list.  Halo rows 0 .. TY+9 (row r = list position y0 - 5 + r; rows 1 .. TY+8 are used);
+// P lists: rows (2t, 2t+1), t = 1 .. TY/2+3; Q lists: P[q] + P[q+1].
+constexpr size_t mm_smem_bytes(int TY) {
+    return sizeof(double) * (size_t)(TY + 10) * MM_HX + sizeof(unsigned) * (size_t)(TY + 10) * MM_HX +
+           sizeof(unsigned) * (size_t)(TY + 10) * 9 * MM_TX + sizeof(unsigned) * (size_t)(TY / 2 + 3) * MM_TX * MM_PW +
+           sizeof(unsigned) * (size_t)(TY / 2 + 2) * MM_TX * MM_QW + 96 * sizeof(double);
 }
 
 // The value of real rank `rho` (1-based, among the window's taps inside the block) when the key at that rank has the
@@ -255,7 +283,9 @@ __device__ __forceinline__ double mm_value_of(const double *__restrict__ Dh, uns
     return Dh[r * MM_HX + hx];
 }
 
-__global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfParams p) {
+template <int MM_TY, int MM_NW, int MINB>
+__global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(const MfParams p) {
+    constexpr int MM_ROWS = MM_TY + 10, MM_NT = MM_NW * 32, MM_NP = MM_TY / 2 + 3, MM_NQ = MM_TY / 2 + 2;
     extern __shared__ __align__(16) unsigned char mf_smem[];
     double *Dh = reinterpret_cast<double *>(mf_smem);                         // [ROWS][HX] values (0 outside the block)
     double *redd = Dh + MM_ROWS * MM_HX;                                      // [96] reduction scratch, row table
@@ -267,122 +297,45 @@ __global__ void __launch_bounds__(MM_NT, 1) median_filter_merge_kernel(const MfP
     const MfTile gt = p.gene_tiles[blockIdx.y];
     const MfTile ct = p.cell_tiles[blockIdx.x];
     const int hi0 = gt.start - 4, hj0 = ct.start - 5;   // halo (hx, r) = gene hi0 + hx, list position hj0 + r
-    // ---- S0: halo, tile range, keys (a warp per halo row: lanes over the row's 40 genes, no index divisions) ---------------
-    bool bad = false;
-    double vmin = INFINITY, vmax = -INFINITY;
-    int *modecnt = reinterpret_cast<int *>(redd + 32);   // [4] matches of the four candidate values, [4] "cell not clean" flag
-    if (tid < 8) modecnt[tid] = 0;
-    for (int r = warp; r < MM_ROWS; r += MM_NW) {
-        const int jj = hj0 + r;
-        const bool row_in = jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
-        const long long rb = row_in ? (long long)p.G * (long long)p.cells[jj] : 0ll;
-#pragma unroll
-        for (int hx = lane; hx < MM_HX; hx += 32) {
-            const int ii = hi0 + hx;
-            double v = 0.0;
-            if (row_in && ii >= gt.lo && ii < gt.hi) {
-                v = p.X[ii + rb];
-                if (is_finite_d(v)) {
-                    vmin = v < vmin ? v : vmin;
-                    vmax = v > vmax ? v : vmax;
-                } else {
-                    bad = true;
-                }
-            }
-            Dh[r * MM_HX + hx] = v;
-        }
-    }
-    vmin = warp_min_d(vmin);
-    vmax = warp_max_d(vmax);
-    if (lane == 0) {
-        redd[warp] = vmin;
-        redd[16 + warp] = vmax;
-    }
-    __syncthreads();
-    // The matrices this filter sees hold ONE value many times over (exactly 1 after the dead-band subtraction and 2^x, the
-    // reference mean after de-noising).  Four taps of the tile nominate candidates for it; the most frequent one (M) is
-    // remembered together with whether its key cell holds nothing but copies of it - then a median whose key falls into
-    // that cell IS M, however many ties surround it.
-    const int c_r[4] = {MM_ROWS / 2, MM_ROWS / 2, 3 * MM_ROWS / 4, MM_ROWS / 4};
-    const int c_x[4] = {MM_HX / 2, MM_HX / 4, 3 * MM_HX / 4, MM_HX / 2 + 3};
-    if (warp == 0) {   // tile range and the nominees, once
-        double a = lane < MM_NW ? redd[lane] : INFINITY, b = lane < MM_NW ? redd[16 + lane] : -INFINITY;
-        a = warp_min_d(a);
-        b = warp_max_d(b);
-        if (lane == 0) {
-            redd[40] = a;
-            redd[41] = b;
-        }
-        if (lane < 4) {   // a nominee outside the block nominates nothing (NaN equals no value)
-            const int ii = hi0 + c_x[lane], jj = hj0 + c_r[lane];
-            redd[42 + lane] = (ii >= gt.lo && ii < gt.hi && jj >= ct.lo && jj < ct.hi) ? Dh[c_r[lane] * MM_HX + c_x[lane]]
-                                                                                         : __longlong_as_double(0x7ff8000000000000ll);
-        }
-    }
-    __syncthreads();
-    vmin = redd[40];
-    vmax = redd[41];
+    // ---- S0: halo and keys in one pass.  The keys quantise over the MATRIX' range (found by mf_range_kernel before the launch),
+    //      so no tile reduction is needed; lanes cover 32 genes of a row, the 8 genes left of four rows share one more step.
+    bool bad = false, dirty = false;
+    const double vmin = p.vmin, M = p.mode;
     const double QMAX = 16777213.0;   // quantised values 1 .. 2^24 - 2: strictly between the two padding keys
-    const double scale = (vmax > vmin) ? QMAX / (vmax - vmin) : 0.0;
+    const double scale = (p.vmax > vmin) ? QMAX / (p.vmax - vmin) : 0.0;
     auto quant = [&](double v) -> unsigned {
         double qd = (v - vmin) * scale;
         qd = qd < QMAX ? qd : QMAX;       // (also maps NaN to QMAX)
         qd = qd > 0.0 ? qd : 0.0;
         return 1u + __double2uint_rd(qd);
     };
-    {
-        const double c0 = redd[42], c1 = redd[43], c2 = redd[44], c3 = redd[45];
-        int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-        for (int r = warp; r < MM_ROWS; r += MM_NW) {
-            const int jj = hj0 + r;
-            const bool row_in = jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
-#pragma unroll
-            for (int hx = lane; hx < MM_HX; hx += 32) {
-                const int ii = hi0 + hx;
-                const double v = Dh[r * MM_HX + hx];
-                unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
-                if (row_in && ii >= gt.lo && ii < gt.hi) {
-                    key = (quant(v) << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
-                    n0 += (v == c0) ? 1 : 0;
-                    n1 += (v == c1) ? 1 : 0;
-                    n2 += (v == c2) ? 1 : 0;
-                    n3 += (v == c3) ? 1 : 0;
-                }
-                Kh[r * MM_HX + hx] = key;
-            }
-        }
-        n0 = __reduce_add_sync(0xffffffffu, n0);
-        n1 = __reduce_add_sync(0xffffffffu, n1);
-        n2 = __reduce_add_sync(0xffffffffu, n2);
-        n3 = __reduce_add_sync(0xffffffffu, n3);
-        if (lane == 0) {
-            if (n0) atomicAdd(&modecnt[0], n0);
-            if (n1) atomicAdd(&modecnt[1], n1);
-            if (n2) atomicAdd(&modecnt[2], n2);
-            if (n3) atomicAdd(&modecnt[3], n3);
-        }
-    }
-    __syncthreads();
-    int best = 0;
-#pragma unroll
-    for (int q = 1; q < 4; ++q)
-        if (modecnt[q] > modecnt[best]) best = q;
-    const double M = redd[42 + best];
+    // The matrices this filter sees hold ONE value many times over (exactly 1 after the dead-band subtraction and 2^x, the
+    // reference mean after de-noising): M, picked by the host from a sample.  A tile whose key cell of M holds nothing but
+    // copies of M ("clean") can answer every median that falls into that cell with M, however many ties surround it.
     const unsigned qM = quant(M);
-    if (modecnt[best] >= 16) {   // worth knowing: is M's key cell clean (nothing but copies of M)?
-        bool dirty = false;
-        for (int r = warp; r < MM_ROWS; r += MM_NW)
-#pragma unroll
-            for (int hx = lane; hx < MM_HX; hx += 32) {
-                const unsigned key = Kh[r * MM_HX + hx];
-                dirty |= (key != MM_LOW) && (key != MM_HIGH) && ((key >> 8) == qM) && (Dh[r * MM_HX + hx] != M);
-            }
-        if (dirty) modecnt[4] = 1;
-    } else if (tid == 0) {
-        modecnt[4] = 1;
-    }
+    int *flags = reinterpret_cast<int *>(redd);
+    if (tid == 0) flags[0] = 0;
+    auto tap = [&](int r, int hx) {
+        const int jj = hj0 + r, ii = hi0 + hx;
+        unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
+        double v = 0.0;
+        if (jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8 && ii >= gt.lo && ii < gt.hi) {
+            v = p.X[ii + p.G * (int64_t)p.cells[jj]];
+            bad |= !is_finite_d(v);
+            const unsigned q = quant(v);
+            dirty |= (q == qM) && (v != M);
+            key = (q << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
+        }
+        Dh[r * MM_HX + hx] = v;
+        Kh[r * MM_HX + hx] = key;
+    };
+    for (int r = warp; r < MM_ROWS; r += MM_NW) tap(r, lane);
+    for (int r4 = 4 * warp; r4 < MM_ROWS; r4 += 4 * MM_NW)
+        if (r4 + (lane >> 3) < MM_ROWS) tap(r4 + (lane >> 3), 32 + (lane & 7));
     __syncthreads();
-    const bool mode_clean = modecnt[4] == 0;
+    if (dirty) flags[0] = 1;
+    __syncthreads();
+    const bool mode_clean = flags[0] == 0 && (M == M);
     // ---- S1: sorted runs, pairs ----------------------------------------------------------------------------------------------
     for (int t = warp; t <= MM_TY / 2 + 4; t += MM_NW) {      // rows 2t, 2t+1
         unsigned ra[9], rb[9];
@@ -527,12 +480,14 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
         use_net = (c.opt_mf_kernel == 2 && r == 4) ? 1 : 0;
     }
     // window_size 7 (radius 4): the shared-merge kernel; ICNV_MF_KERNEL=1 (read at icnv_init) keeps the counting selection
-    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel == 3) && mm_smem_bytes() <= (size_t)c.smem_optin;
-    const int TI = merge_kernel ? MM_TX : (select_kernel ? MS_TI : MF_TI), TJ = merge_kernel ? MM_TY : (select_kernel ? MS_TJ : MF_TJ);
-    const int NT = merge_kernel ? MM_NT : TI * TJ;
+    // (ICNV_MF_KERNEL=3: tiles of 32 list positions, one 512-thread CTA per SM; 4: tiles of 12, two 256-thread CTAs per SM)
+    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel >= 3) && mm_smem_bytes(32) <= (size_t)c.smem_optin;
+    const int mm_ty = (c.opt_mf_kernel == 4) ? 12 : 32, mm_nw = (c.opt_mf_kernel == 4) ? 8 : 16;
+    const int TI = merge_kernel ? MM_TX : (select_kernel ? MS_TI : MF_TI), TJ = merge_kernel ? mm_ty : (select_kernel ? MS_TJ : MF_TJ);
+    const int NT = merge_kernel ? mm_nw * 32 : TI * TJ;
     bool list32 = false;
     if (c.opt_mf_list32) list32 = select_kernel;   // diagnostic (ICNV_MF_LIST32 at icnv_init)
-    const size_t smem = merge_kernel ? mm_smem_bytes()
+    const size_t smem = merge_kernel ? mm_smem_bytes(mm_ty)
                                      : sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
                                            (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT +
                                            (use_net ? sizeof(float) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) : 0);
@@ -565,7 +520,48 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     ICNV_CUDA(cudaMemcpyAsync(d_cells, grp_idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     ICNV_CUDA(cudaStreamSynchronize(st));  // tile tables are stack-lifetime host buffers
-    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net};
+    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net, 0.0, 0.0, 0.0};
+    if (merge_kernel) {
+        // range of the matrix + a sample of its values (the dominant value is the most frequent one of the sample, if any
+        // value takes >= 0.5 % of it)
+        constexpr int NS = 4096;
+        char *d_pre = (char *)scratch(SLOT_MF_PRE, 16 + sizeof(double) * NS);
+        if (!d_pre) return ICNV_E_NOMEM;
+        unsigned long long h_range[2] = {~0ull, 0ull};
+        ICNV_CUDA(cudaMemcpyAsync(d_pre, h_range, sizeof(h_range), cudaMemcpyHostToDevice, st));
+        mf_range_kernel<<<(unsigned)(c.sm_count * 8), 256, 0, st>>>(X, G * C, (unsigned long long *)d_pre, (double *)(d_pre + 16), NS);
+        ICNV_CHECK_LAUNCH("mf_range_kernel");
+        std::vector<double> smp((size_t)NS);
+        ICNV_CUDA(cudaMemcpyAsync(h_range, d_pre, sizeof(h_range), cudaMemcpyDeviceToHost, st));
+        ICNV_CUDA(cudaMemcpyAsync(smp.data(), d_pre + 16, sizeof(double) * NS, cudaMemcpyDeviceToHost, st));
+        ICNV_CUDA(cudaStreamSynchronize(st));
+        auto unkey = [](unsigned long long k) {
+            unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+            double d;
+            memcpy(&d, &u, 8);
+            return d;
+        };
+        p.vmin = h_range[0] <= h_range[1] ? unkey(h_range[0]) : 0.0;
+        p.vmax = h_range[0] <= h_range[1] ? unkey(h_range[1]) : 0.0;
+        std::sort(smp.begin(), smp.end(), [](double a, double b) {   // bitwise order: NaNs and -0 / +0 stay apart, runs are exact copies
+            long long x, y;
+            memcpy(&x, &a, 8);
+            memcpy(&y, &b, 8);
+            return x < y;
+        });
+        int best_n = 0;
+        double best_v = NAN;
+        for (int i = 0; i < NS;) {
+            int j = i + 1;
+            while (j < NS && memcmp(&smp[(size_t)i], &smp[(size_t)j], 8) == 0) ++j;
+            if (j - i > best_n) {
+                best_n = j - i;
+                best_v = smp[(size_t)i];
+            }
+            i = j;
+        }
+        p.mode = (best_n >= NS / 200 && std::isfinite(best_v)) ? best_v : NAN;
+    }
     dim3 grid((unsigned)ct.size(), (unsigned)gt.size());
     auto launch = [&](auto kern) -> int {
         ICNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -574,7 +570,7 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     };
     int lrc;
     if (list32) use_net = 0;
-    if (merge_kernel) lrc = launch(median_filter_merge_kernel);
+    if (merge_kernel) lrc = (mm_ty == 12) ? launch(median_filter_merge_kernel<12, 8, 2>) : launch(median_filter_merge_kernel<32, 16, 1>);
     else if (!select_kernel) lrc = launch(median_filter_kernel);
     else if (list32 && r == 5) lrc = launch(median_filter_select_kernel<5, unsigned>);
     else if (list32 && r == 4) lrc = launch(median_filter_select_kernel<4, unsigned>);
