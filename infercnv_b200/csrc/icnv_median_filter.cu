@@ -315,23 +315,45 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
     const unsigned qM = quant(M);
     int *flags = reinterpret_cast<int *>(redd);
     if (tid == 0) flags[0] = 0;
-    auto tap = [&](int r, int hx) {
-        const int jj = hj0 + r, ii = hi0 + hx;
+    // a tap's value -> its key and the two halo arrays
+    auto put = [&](int r, int hx, bool in, double v) {
         unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
-        double v = 0.0;
-        if (jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8 && ii >= gt.lo && ii < gt.hi) {
-            v = p.X[ii + p.G * (int64_t)p.cells[jj]];
+        if (in) {
             bad |= !is_finite_d(v);
             const unsigned q = quant(v);
             dirty |= (q == qM) && (v != M);
             key = (q << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
         }
-        Dh[r * MM_HX + hx] = v;
+        Dh[r * MM_HX + hx] = in ? v : 0.0;
         Kh[r * MM_HX + hx] = key;
     };
-    for (int r = warp; r < MM_ROWS; r += MM_NW) tap(r, lane);
-    for (int r4 = 4 * warp; r4 < MM_ROWS; r4 += 4 * MM_NW)
-        if (r4 + (lane >> 3) < MM_ROWS) tap(r4 + (lane >> 3), 32 + (lane & 7));
+    // every global load of the tile is issued before the first one is used: first the cell columns of this warp's rows (and
+    // of the four rows whose last 8 genes it takes), then the values - two dependent memory latencies per tile, not two per row
+    constexpr int RPW = (MM_ROWS + MM_NW - 1) / MM_NW;          // rows per warp
+    constexpr int TPW = (MM_ROWS + 4 * MM_NW - 1) / (4 * MM_NW);  // groups of four row tails per warp
+    long long rb[RPW + TPW];
+    bool rin[RPW + TPW];
+#pragma unroll
+    for (int i = 0; i < RPW + TPW; ++i) {
+        const int r = i < RPW ? warp + i * MM_NW : 4 * (warp + (i - RPW) * MM_NW) + (lane >> 3);
+        const int jj = hj0 + r;
+        rin[i] = r < MM_ROWS && jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
+        rb[i] = rin[i] ? (long long)p.G * (long long)p.cells[jj] : 0ll;
+    }
+    double tv[RPW + TPW];
+#pragma unroll
+    for (int i = 0; i < RPW + TPW; ++i) {
+        const int hx = i < RPW ? lane : 32 + (lane & 7);
+        const int ii = hi0 + hx;
+        rin[i] = rin[i] && ii >= gt.lo && ii < gt.hi;
+        tv[i] = rin[i] ? p.X[ii + rb[i]] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < RPW + TPW; ++i) {
+        const int r = i < RPW ? warp + i * MM_NW : 4 * (warp + (i - RPW) * MM_NW) + (lane >> 3);
+        const int hx = i < RPW ? lane : 32 + (lane & 7);
+        if (r < MM_ROWS) put(r, hx, rin[i], tv[i]);
+    }
     __syncthreads();
     if (dirty) flags[0] = 1;
     __syncthreads();
@@ -387,6 +409,10 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
     __syncthreads();
     // ---- S3: per pair of outputs (2j, 2j+1): core = Q[j] + Q[j+2] (rows 2j+2 .. 2j+9), + row 2j+1 resp. 2j+10 ----------------
     for (int j = warp; j < MM_TY / 2; j += MM_NW) {
+        long long ycol[2];   // column offsets of the two outputs, fetched now, needed at the end of the task
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+            ycol[half] = (2 * j + half < ct.len) ? (long long)p.G * (long long)p.cells[ct.start + 2 * j + half] : 0ll;
         unsigned core[14];
         {
             unsigned a[MM_QW], b[MM_QW];
@@ -444,7 +470,7 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
                 const double v1 = value_at(k - 39, rho);
                 double med = v1;
                 if (even) med = (v1 + value_at(k - 38, rho + 1)) * 0.5;
-                p.Y[i + p.G * (int64_t)p.cells[jpos]] = med;
+                p.Y[i + ycol[half]] = med;
             }
         }
     }
