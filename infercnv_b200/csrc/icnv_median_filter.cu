@@ -40,6 +40,7 @@ struct MfParams {
     int use_net;              // radius 4 only: full windows by the key network (window_median_net81), 0 = counting selection
     // shared-merge kernel: the matrix' range (keys quantise over it) and its dominant value (NaN: none), found before the launch
     double vmin, vmax, mode;
+    double scale;             // (2^24 - 3) / (vmax - vmin), 0 if the matrix is constant
 };
 
 // One CTA = a tile of TI genes x TJ list positions (TI*TJ threads, one output each).  The tile's halo
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
     bool bad = false, dirty = false;
     const double vmin = p.vmin, M = p.mode;
     const double QMAX = 16777213.0;   // quantised values 1 .. 2^24 - 2: strictly between the two padding keys
-    const double scale = (p.vmax > vmin) ? QMAX / (p.vmax - vmin) : 0.0;
+    const double scale = p.scale;     // QMAX / (vmax - vmin), 0 for a constant matrix (set by the launcher)
     auto quant = [&](double v) -> unsigned {
         double qd = (v - vmin) * scale;
         qd = qd < QMAX ? qd : QMAX;       // (also maps NaN to QMAX)
@@ -327,26 +328,29 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
         Dh[r * MM_HX + hx] = in ? v : 0.0;
         Kh[r * MM_HX + hx] = key;
     };
-    // every global load of the tile is issued before the first one is used: first the cell columns of this warp's rows (and
-    // of the four rows whose last 8 genes it takes), then the values - two dependent memory latencies per tile, not two per row
+    // the cell column behind each halo row, once per tile (-1: outside the index list's block): the rows' loads then cost one
+    // shared-memory read per tap instead of an index load and a 64-bit multiply
+    long long *rowoff = reinterpret_cast<long long *>(redd) + 8;   // [MM_ROWS] <= 42 of the 96 scratch doubles
+    if (tid < MM_ROWS) {
+        const int jj = hj0 + tid;
+        const bool ok = jj >= ct.lo && jj < ct.hi && tid >= 1 && tid <= MM_TY + 8;
+        rowoff[tid] = ok ? (long long)p.G * (long long)p.cells[jj] : -1ll;
+    }
+    __syncthreads();
+    // every value load of the tile is issued before the first one is used; a warp takes whole rows (lanes = 32 genes) and the
+    // last 8 genes of four rows at a time
     constexpr int RPW = (MM_ROWS + MM_NW - 1) / MM_NW;          // rows per warp
     constexpr int TPW = (MM_ROWS + 4 * MM_NW - 1) / (4 * MM_NW);  // groups of four row tails per warp
-    long long rb[RPW + TPW];
     bool rin[RPW + TPW];
-#pragma unroll
-    for (int i = 0; i < RPW + TPW; ++i) {
-        const int r = i < RPW ? warp + i * MM_NW : 4 * (warp + (i - RPW) * MM_NW) + (lane >> 3);
-        const int jj = hj0 + r;
-        rin[i] = r < MM_ROWS && jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
-        rb[i] = rin[i] ? (long long)p.G * (long long)p.cells[jj] : 0ll;
-    }
     double tv[RPW + TPW];
 #pragma unroll
     for (int i = 0; i < RPW + TPW; ++i) {
+        const int r = i < RPW ? warp + i * MM_NW : 4 * (warp + (i - RPW) * MM_NW) + (lane >> 3);
         const int hx = i < RPW ? lane : 32 + (lane & 7);
         const int ii = hi0 + hx;
-        rin[i] = rin[i] && ii >= gt.lo && ii < gt.hi;
-        tv[i] = rin[i] ? p.X[ii + rb[i]] : 0.0;
+        const long long off = r < MM_ROWS ? rowoff[r] : -1ll;
+        rin[i] = off >= 0 && ii >= gt.lo && ii < gt.hi;
+        tv[i] = rin[i] ? p.X[ii + off] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < RPW + TPW; ++i) {
@@ -409,10 +413,9 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
     __syncthreads();
     // ---- S3: per pair of outputs (2j, 2j+1): core = Q[j] + Q[j+2] (rows 2j+2 .. 2j+9), + row 2j+1 resp. 2j+10 ----------------
     for (int j = warp; j < MM_TY / 2; j += MM_NW) {
-        long long ycol[2];   // column offsets of the two outputs, fetched now, needed at the end of the task
+        long long ycol[2];   // column offsets of the two outputs = halo rows 2j + 5, 2j + 6 of the row table
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
-            ycol[half] = (2 * j + half < ct.len) ? (long long)p.G * (long long)p.cells[ct.start + 2 * j + half] : 0ll;
+        for (int half = 0; half < 2; ++half) ycol[half] = rowoff[2 * j + half + 5];
         unsigned core[14];
         {
             unsigned a[MM_QW], b[MM_QW];
@@ -506,9 +509,9 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
         use_net = (c.opt_mf_kernel == 2 && r == 4) ? 1 : 0;
     }
     // window_size 7 (radius 4): the shared-merge kernel; ICNV_MF_KERNEL=1 (read at icnv_init) keeps the counting selection
-    // (ICNV_MF_KERNEL=3: tiles of 32 list positions, one 512-thread CTA per SM; 4: tiles of 12, two 256-thread CTAs per SM)
-    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel >= 3) && mm_smem_bytes(32) <= (size_t)c.smem_optin;
-    const int mm_ty = (c.opt_mf_kernel == 4) ? 12 : 32, mm_nw = (c.opt_mf_kernel == 4) ? 8 : 16;
+    // (default and ICNV_MF_KERNEL=4: tiles of 12 list positions, two 256-thread CTAs per SM; 3: tiles of 32, one 512-thread CTA)
+    const int mm_ty = (c.opt_mf_kernel == 3) ? 32 : 12, mm_nw = (c.opt_mf_kernel == 3) ? 16 : 8;
+    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel >= 3) && mm_smem_bytes(mm_ty) <= (size_t)c.smem_optin;
     const int TI = merge_kernel ? MM_TX : (select_kernel ? MS_TI : MF_TI), TJ = merge_kernel ? mm_ty : (select_kernel ? MS_TJ : MF_TJ);
     const int NT = merge_kernel ? mm_nw * 32 : TI * TJ;
     bool list32 = false;
@@ -520,8 +523,36 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     if (smem > (size_t)c.smem_optin || (TI + 2 * r) * (TJ + 2 * r) > 65535)
         return set_error(ICNV_E_UNSUPPORTED, "window_size %d needs %zu B of shared memory per CTA", window_size, smem);
     cudaStream_t st = pick_stream(stream);
-    // cells in no list are copied through
-    ICNV_CUDA(cudaMemcpyAsync(Y, X, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToDevice, st));
+    // cells in no list and genes on no chromosome are copied through - one pass over the matrix that is skipped when the
+    // lists and the chromosomes cover everything (the usual call: every cell belongs to one group or subcluster)
+    bool covered = n_grp > 0;
+    {
+        int64_t g_cov = 0;
+        for (int k = 0; k < K; ++k) g_cov += chr_len[k] > 0 ? chr_len[k] : 0;
+        covered = covered && g_cov >= G && grp_off[n_grp] >= C;
+        if (covered) {
+            std::vector<unsigned char> seen((size_t)C, 0);
+            int64_t n_seen = 0;
+            for (int64_t i = 0; i < grp_off[n_grp]; ++i) {
+                const int32_t cell = grp_idx[i];
+                if (cell >= 0 && cell < C && !seen[(size_t)cell]) {
+                    seen[(size_t)cell] = 1;
+                    ++n_seen;
+                }
+            }
+            covered = n_seen == C;
+            std::vector<unsigned char> gseen((size_t)G, 0);   // chromosomes may overlap or leave gaps in a hand-made layout
+            int64_t n_g = 0;
+            for (int k = 0; k < K; ++k)
+                for (int64_t g = chr_start[k]; g < (int64_t)chr_start[k] + chr_len[k]; ++g)
+                    if (g >= 0 && g < G && !gseen[(size_t)g]) {
+                        gseen[(size_t)g] = 1;
+                        ++n_g;
+                    }
+            covered = covered && n_g == G;
+        }
+    }
+    if (!covered) ICNV_CUDA(cudaMemcpyAsync(Y, X, sizeof(double) * (size_t)(G * C), cudaMemcpyDeviceToDevice, st));
     if (n_grp == 0) return ICNV_OK;
     std::vector<MfTile> gt, ct;
     make_tiles(chr_start, chr_len, K, TI, gt);
@@ -546,7 +577,7 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     ICNV_CUDA(cudaMemcpyAsync(d_cells, grp_idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     ICNV_CUDA(cudaStreamSynchronize(st));  // tile tables are stack-lifetime host buffers
-    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net, 0.0, 0.0, 0.0};
+    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net, 0.0, 0.0, 0.0, 0.0};
     if (merge_kernel) {
         // range of the matrix + a sample of its values (the dominant value is the most frequent one of the sample, if any
         // value takes >= 0.5 % of it)
@@ -587,6 +618,7 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
             i = j;
         }
         p.mode = (best_n >= NS / 200 && std::isfinite(best_v)) ? best_v : NAN;
+        p.scale = (p.vmax > p.vmin) ? 16777213.0 / (p.vmax - p.vmin) : 0.0;
     }
     dim3 grid((unsigned)ct.size(), (unsigned)gt.size());
     auto launch = [&](auto kern) -> int {

@@ -343,6 +343,22 @@ __device__ __noinline__ double emission_far(double x, double mean, double sd) {
     return -log(-pnorm_upper_log_exact(zz));
 }
 
+// acc += (v >= lim): a compare and a predicated add (the compiler's own form is compare, select 0 / 1, add)
+__device__ __forceinline__ void count_if_ge(int &acc, double v, double lim) {
+    asm("{ .reg .pred p; setp.ge.f64 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(acc) : "d"(v), "d"(lim));
+}
+
+// both 16-byte halves of interval `idx` from the lane's table replica (`tab_lane` -> its copy of interval 0): the address is
+// ONE multiply-add (the compiler otherwise forms shift + or per state), the second half sits at a constant offset
+__device__ __forceinline__ void table_entry(const double2 *tab_lane, int idx, double2 &c01, double2 &c2f) {
+    constexpr int NTAB_BYTES = (ICNV_EMIS_N + 1) * TAB_REP * 16;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(tab_lane);   // loop-invariant
+    unsigned addr;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"((unsigned)idx), "n"(TAB_REP * 16), "r"(base));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c01.x), "=d"(c01.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(c2f.x), "=d"(c2f.y) : "r"(addr), "n"(NTAB_BYTES));
+}
+
 template <int M, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitParams p) {
     extern __shared__ __align__(16) double sm[];
@@ -364,7 +380,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
         tab2f[e] = make_double2(p.table[2 * ICNV_EMIS_N + i], __hiloint2double(__float_as_int(c4), __float_as_int(c3)));
     }
     __syncthreads();
-    const double2 *tabA = tab01 + (lane & (TAB_REP - 1)), *tabB = tab2f + (lane & (TAB_REP - 1));   // this lane's replica
+    // this lane's replica of interval 0; the second halves (tab2f) follow at a constant distance
+    const double2 *tab_lane = tab01 + (lane & (TAB_REP - 1));
 
     const int64_t warp_global = (int64_t)blockIdx.x * NWARPS + warp;
     // backpointers: one 16-bit word per gene and lane - the best previous state (3 bits) and, per state, whether the
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
     const double a = p.a_diag, b = p.b_off;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC == rint(v), low word == (int)rint(v)
     const int tau_hi = __double2hiint(p.tau);
+    const double e_lim = (a - b) - p.tau;   // the launcher refuses the fast path unless a - b > 4 tau
     int err = 0;
 
     for (;;) {
@@ -422,6 +440,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
         // certificate: smallest decision margin seen, tracked through the HIGH WORD of the (non-negative)
         // gap - monotone in the gap, exact for the power-of-two threshold, two integer ops per check
         unsigned mg = 0x7fffffffu;
+        int near_best = 0;   // states within tau of the best score, summed over the steps (the best one included)
         issue_tile(b_first, 0);
         cp_async_commit();
         for (int blk = b_first; blk <= b_last; ++blk) {
@@ -457,8 +476,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                     for (int k = 0; k < M; ++k) {
                         const double m = zs[k] + MAGIC;
                         const double u = zs[k] - (m - MAGIC);
-                        const int idx = __double2loint(m) * TAB_REP;
-                        const double2 c01 = tabA[idx], c2f = tabB[idx];
+                        double2 c01, c2f;
+                        table_entry(tab_lane, __double2loint(m), c01, c2f);
                         const float hi = fmaf((float)u, __int_as_float(__double2hiint(c2f.y)), __int_as_float(__double2loint(c2f.y)));
                         double v = fma(u, (double)hi, c2f.x);
                         v = fma(u, v, c01.y);
@@ -472,8 +491,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                         if (zs[k] < LIM) {
                             const double m = zs[k] + MAGIC;
                             const double u = zs[k] - (m - MAGIC);
-                            const int idx = __double2loint(m) * TAB_REP;
-                            const double2 c01 = tabA[idx], c2f = tabB[idx];
+                            double2 c01, c2f;
+                            table_entry(tab_lane, __double2loint(m), c01, c2f);
                             const float hi = fmaf((float)u, __int_as_float(__double2hiint(c2f.y)), __int_as_float(__double2loint(c2f.y)));
                             v = fma(u, (double)hi, c2f.x);
                             v = fma(u, v, c01.y);
@@ -514,7 +533,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                     const int he = __double2hiint(e);
                     const bool stay = he >= 0;
                     mg = min(mg, (unsigned)(he & 0x7fffffff));                      // |stay - from_best|
-                    mg = min(mg, (k == i1) ? 0x7fffffffu : (unsigned)__double2hiint(T1 - t[k]));   // best vs every other state (an exact tie: 0)
+                    // best vs every other state: T1 - t[k] = (a - b) - e up to three roundings of the scores, so the gap is
+                    // at least tau iff e <= a - b - tau.  The best state itself has e = a - b: exactly one state per gene may
+                    // exceed the bound - counted here, checked against the number of steps at the end of the sequence.
+                    count_if_ge(near_best, e, e_lim);
                     nu[k] = (stay ? d : T1) + le[k];
                     moved = __funnelshift_l((uint32_t)he, moved, 1);
                 }
@@ -541,6 +563,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
             if (under && active) err |= 2;
             const double gap = best - second;
             if (!(gap >= p.tau)) mg = 0;   // also catches NaN
+            if (near_best != n - 1) mg = 0;   // some step had a second state within tau of the best one (or a NaN score)
         }
         // uncertified sequences go to the exact kernel
         if (active && (int)mg < tau_hi) {
@@ -885,8 +908,9 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
         for (int k = 0; k < m; ++k)
             if (Pi[j + m * k] != (j == k ? Pi[0] : Pi[1])) structured = false;
     // ... with the diagonal the larger one ("the best state always stays" is what the fast recursion relies on) and every
-    // transition possible (log 0 would poison the margins): t <= 1/6 for i6, 1/3 for i3, and t > 0
-    structured = structured && Pi[0] > Pi[1] && Pi[1] > 0.0;
+    // transition possible (log 0 would poison the margins): t <= 1/6 for i6, 1/3 for i3, and t > 0.  The certificate's
+    // best-versus-others check reads the gap off e = stay - from_best, which needs log(diag / offdiag) well above tau.
+    structured = structured && Pi[0] > Pi[1] && Pi[1] > 0.0 && std::log(Pi[0] / Pi[1]) > 1e-6;
     const bool use_fast = (c.hmm_mode == 1) && structured && !want_margin;
 
     if (!use_fast) {

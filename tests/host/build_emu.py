@@ -41,6 +41,8 @@ PTX_STANDINS = {
     "cp_async8": "{ if (valid) memcpy(smem_dst, gsrc, 8); else memset(smem_dst, 0, 8); }",
     "cp_async_commit": "{ }",
     "cp_async_wait": "{ }",
+    "count_if_ge": "{ acc += (v >= lim) ? 1 : 0; }",
+    "table_entry": "{ const double2 *t = tab_lane + (size_t)idx * TAB_REP; c01 = t[0]; c2f = t[(ICNV_EMIS_N + 1) * TAB_REP]; }",
 }
 DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(?P<type>[\w ]+?)\s+(?P<name>\w+)\[\];")
 

@@ -68,13 +68,14 @@ sds_g = np.concatenate([bench.I6_SD * len(g) ** -0.5 for g in all_groups])
 Sg, _ = eng.viterbi_groups(Yg, cs, cl, Pi, delta, bench.I6_MEAN, sds_g, gplan.local_ref_groups(), gplan.ref_sizes, gplan.max_chunks)
 torch.cuda.synchronize()
 assert int(f.item()) == 0 and int(f2.item()) == 0
+print(f"[check_multigpu] rank {rank}: sharded run done ({C_local} local cells)", file=sys.stderr, flush=True)
 
 
 def gather_rows(t):
     """every rank's rows on every rank (variable sizes: padded), through host memory when the backend is not NCCL"""
-    n_local = torch.tensor([t.shape[0]], dtype=torch.int64)
+    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device if backend == "nccl" else "cpu")
     sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local.to(t.device) if backend == "nccl" else n_local)
+    dist.all_gather(sizes, n_local)
     nmax = int(max(int(s.item()) for s in sizes))
     pad = torch.zeros((nmax, t.shape[1]), dtype=t.dtype, device=t.device if backend == "nccl" else "cpu")
     pad[: t.shape[0]] = t if backend == "nccl" else t.cpu()
