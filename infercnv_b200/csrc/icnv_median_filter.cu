@@ -41,6 +41,7 @@ struct MfParams {
     // shared-merge kernel: the matrix' range (keys quantise over it) and its dominant value (NaN: none), found before the launch
     double vmin, vmax, mode;
     double scale;             // (2^24 - 3) / (vmax - vmin), 0 if the matrix is constant
+    const long long *coloff;  // shared-merge kernel: G * cells[i] per list entry
 };
 
 // One CTA = a tile of TI genes x TJ list positions (TI*TJ threads, one output each).  The tile's halo
@@ -328,29 +329,27 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
         Dh[r * MM_HX + hx] = in ? v : 0.0;
         Kh[r * MM_HX + hx] = key;
     };
-    // the cell column behind each halo row, once per tile (-1: outside the index list's block): the rows' loads then cost one
-    // shared-memory read per tap instead of an index load and a 64-bit multiply
-    long long *rowoff = reinterpret_cast<long long *>(redd) + 8;   // [MM_ROWS] <= 42 of the 96 scratch doubles
-    if (tid < MM_ROWS) {
-        const int jj = hj0 + tid;
-        const bool ok = jj >= ct.lo && jj < ct.hi && tid >= 1 && tid <= MM_TY + 8;
-        rowoff[tid] = ok ? (long long)p.G * (long long)p.cells[jj] : -1ll;
-    }
-    __syncthreads();
-    // every value load of the tile is issued before the first one is used; a warp takes whole rows (lanes = 32 genes) and the
-    // last 8 genes of four rows at a time
+    // every global load of the tile is issued before the first one is used: first the column offsets (G * cell, a table the
+    // launcher builds beside the index lists) of this warp's rows and of the four rows whose last 8 genes it takes, then the
+    // values - two dependent memory latencies per tile, not two per row
     constexpr int RPW = (MM_ROWS + MM_NW - 1) / MM_NW;          // rows per warp
     constexpr int TPW = (MM_ROWS + 4 * MM_NW - 1) / (4 * MM_NW);  // groups of four row tails per warp
+    long long rb[RPW + TPW];
     bool rin[RPW + TPW];
-    double tv[RPW + TPW];
 #pragma unroll
     for (int i = 0; i < RPW + TPW; ++i) {
         const int r = i < RPW ? warp + i * MM_NW : 4 * (warp + (i - RPW) * MM_NW) + (lane >> 3);
+        const int jj = hj0 + r;
+        rin[i] = r < MM_ROWS && jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
+        rb[i] = rin[i] ? p.coloff[jj] : 0ll;
+    }
+    double tv[RPW + TPW];
+#pragma unroll
+    for (int i = 0; i < RPW + TPW; ++i) {
         const int hx = i < RPW ? lane : 32 + (lane & 7);
         const int ii = hi0 + hx;
-        const long long off = r < MM_ROWS ? rowoff[r] : -1ll;
-        rin[i] = off >= 0 && ii >= gt.lo && ii < gt.hi;
-        tv[i] = rin[i] ? p.X[ii + off] : 0.0;
+        rin[i] = rin[i] && ii >= gt.lo && ii < gt.hi;
+        tv[i] = rin[i] ? p.X[ii + rb[i]] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < RPW + TPW; ++i) {
@@ -413,9 +412,9 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
     __syncthreads();
     // ---- S3: per pair of outputs (2j, 2j+1): core = Q[j] + Q[j+2] (rows 2j+2 .. 2j+9), + row 2j+1 resp. 2j+10 ----------------
     for (int j = warp; j < MM_TY / 2; j += MM_NW) {
-        long long ycol[2];   // column offsets of the two outputs = halo rows 2j + 5, 2j + 6 of the row table
+        long long ycol[2];   // column offsets of the two outputs, fetched now, needed at the end of the task
 #pragma unroll
-        for (int half = 0; half < 2; ++half) ycol[half] = rowoff[2 * j + half + 5];
+        for (int half = 0; half < 2; ++half) ycol[half] = (2 * j + half < ct.len) ? p.coloff[ct.start + 2 * j + half] : 0ll;
         unsigned core[14];
         {
             unsigned a[MM_QW], b[MM_QW];
@@ -565,7 +564,8 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     if (gt.empty() || ct.empty()) return ICNV_OK;
     if (gt.size() > 65535) return set_error(ICNV_E_UNSUPPORTED, "too many gene tiles (%zu)", gt.size());
     const int64_t n_idx = grp_off[n_grp];
-    size_t bytes = sizeof(MfTile) * (gt.size() + ct.size()) + sizeof(int32_t) * (size_t)n_idx + 64;
+    size_t bytes = sizeof(MfTile) * (gt.size() + ct.size()) + sizeof(int32_t) * (size_t)n_idx + 64 +
+                   (merge_kernel ? sizeof(long long) * (size_t)n_idx + 16 : 0);
     char *d = (char *)scratch(SLOT_MF, bytes);
     int *d_flag = (int *)scratch(SLOT_MISC, 64);
     if (!d || !d_flag) return ICNV_E_NOMEM;
@@ -575,9 +575,17 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     ICNV_CUDA(cudaMemcpyAsync(d_gt, gt.data(), sizeof(MfTile) * gt.size(), cudaMemcpyHostToDevice, st));
     ICNV_CUDA(cudaMemcpyAsync(d_ct, ct.data(), sizeof(MfTile) * ct.size(), cudaMemcpyHostToDevice, st));
     ICNV_CUDA(cudaMemcpyAsync(d_cells, grp_idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+    std::vector<long long> coloff;
+    long long *d_coloff = nullptr;
+    if (merge_kernel) {   // column offsets G * cell beside the lists: one 8-byte load per halo row instead of index + multiply
+        coloff.resize((size_t)n_idx);
+        for (int64_t i = 0; i < n_idx; ++i) coloff[(size_t)i] = (long long)G * (long long)grp_idx[i];
+        d_coloff = reinterpret_cast<long long *>((reinterpret_cast<uintptr_t>(d_cells + n_idx) + 15) & ~(uintptr_t)15);
+        ICNV_CUDA(cudaMemcpyAsync(d_coloff, coloff.data(), sizeof(long long) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
+    }
     ICNV_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     ICNV_CUDA(cudaStreamSynchronize(st));  // tile tables are stack-lifetime host buffers
-    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net, 0.0, 0.0, 0.0, 0.0};
+    MfParams p{X, Y, G, d_cells, d_gt, d_ct, r, d_flag, use_net, 0.0, 0.0, 0.0, 0.0, d_coloff};
     if (merge_kernel) {
         // range of the matrix + a sample of its values (the dominant value is the most frequent one of the sample, if any
         // value takes >= 0.5 % of it)
