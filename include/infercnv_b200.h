@@ -228,6 +228,18 @@ ICNV_API int icnv_median_filter_f64(const double *X, double *Y, int64_t G, int64
 ICNV_API int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, int64_t n_idx, double *mu,
                               double *sigma);
 
+/* parallelDist(t(expr.data[, cells])) with its default method "euclidean" - the distance matrix behind every hclust() of
+ * the reference: R/inferCNV_tumor_subclusters.R:191,411,472,582,609, R/inferCNV_ops.R:1930,3242,
+ * R/inferCNV_heatmap.R:719,755,1062,1079.  cells: n 0-based columns (NULL: all C columns in
+ * order, n is then ignored).  out: R's "dist" vector, n (n - 1) / 2 doubles, the strict lower triangle by columns -
+ * out[n a - a (a + 1) / 2 + (b - a - 1)] for list positions a < b.  Difference form, genes in order, one fused
+ * multiply-add per term (no cancellation for near-identical cells).  n < 2: nothing is written. */
+ICNV_API int icnv_pairwise_dist_f64(const double *X, int64_t G, int64_t C, const int32_t *cells, int64_t n, double *out);
+/* The same distances from the matrix AS parallelDist() RECEIVES IT - observations x variables, column-major, i.e. the
+ * t(expr.data[, cells]) the reference builds at every call site (n cells x G genes, cell a / gene g at x[a + n g]): the R
+ * closure passes its argument through without transposing it back. */
+ICNV_API int icnv_pairwise_dist_rows_f64(const double *x, int64_t n, int64_t G, double *out);
+
 /* Combine per-cell (sum, sd) pairs - e.g. all-gathered from several GPUs - into mu / sigma over all values
  * of those cells, in list order (what icnv_mean_sd_f64 does internally). */
 ICNV_API void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu,
@@ -383,6 +395,11 @@ ICNV_API int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G, i
                                         const int32_t *grp_off /*host*/, const int32_t *grp_idx /*host*/, int n_grp,
                                         int window_size, void *stream);
 
+/* icnv_pairwise_dist_f64 on device pointers: columns X + ldx * (d_cells ? d_cells[a] : a), a < n; out: n (n - 1) / 2
+ * doubles (device).  Asynchronous on `stream`. */
+ICNV_API int icnv_dev_pairwise_dist_f64(const double *X, int64_t G, int64_t ldx, const int32_t *d_cells, int64_t n,
+                                        double *out, void *stream);
+ICNV_API int icnv_dev_pairwise_dist_rows_f64(const double *x, int64_t n, int64_t ldx, int64_t G, double *out, void *stream);
 /* Region calling on device-resident states (uint8, column stride lds >= G).
  * icnv_dev_state_counts_u8: counts[(k*G + g)*8 + slot] = number of cells of group k (d_cells[h_grp_off[k] ..
  * h_grp_off[k+1]), device) whose state at gene g falls in `slot` (0: unassigned, v+1: state v); integer counts, so

@@ -48,6 +48,10 @@ SIGNATURES = {
     "icnv_viterbi_u8_f64": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "icnv_median_filter_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, _P, _P, c_int, c_int]),
     "icnv_mean_sd_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P, _P]),
+    "icnv_pairwise_dist_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P]),
+    "icnv_dev_pairwise_dist_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, _P, _P]),
+    "icnv_pairwise_dist_rows_f64": (c_int, [_P, c_i64, c_i64, _P]),
+    "icnv_dev_pairwise_dist_rows_f64": (c_int, [_P, c_i64, c_i64, c_i64, _P, _P]),
     "icnv_dev_group_partial_sums_f64": (c_int, [_P, c_i64, c_i64, _P, c_i64, c_int, c_int, _P, _P]),
     "icnv_dev_combine_partials_f64": (c_int, [_P, c_i64, c_i64, c_i64, _P, _P]),
     "icnv_dev_bounds_from_partials_f64": (c_int, [_P, c_i64, c_int, c_i64, c_int, _P, _P, _P, _P, _P, _P]),

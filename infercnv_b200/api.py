@@ -260,6 +260,38 @@ def mean_sd(X, cells):
     return mu.value, sg.value
 
 
+def pairwise_dist(X, cells=None, out=None):
+    """parallelDist(t(X[, cells])) (euclidean): R's "dist" vector - n (n - 1) / 2 doubles, the strict lower triangle by
+    columns - for the listed cells (default: all), R/inferCNV_tumor_subclusters.R:191 and the other hclust() call sites."""
+    X = _f64(X)
+    G, C = X.shape
+    idx = None if cells is None else _i32(cells)
+    n = C if idx is None else len(idx)
+    n_out = n * (n - 1) // 2
+    if out is None:
+        out = np.empty(n_out, dtype=np.float64)
+    if out.dtype != np.float64 or out.size != n_out or not out.flags.c_contiguous:
+        raise ValueError("out must be a contiguous float64 vector of n (n - 1) / 2 entries")
+    _lib.check(_lib.load().icnv_pairwise_dist_f64(_p(X), G, C, _p(idx) if idx is not None else None, n, _p(out)))
+    return out
+
+
+def pairwise_dist_rows(x, out=None):
+    """parallelDist(x) for x = observations x variables (the t(expr.data[, cells]) the reference passes), without
+    transposing it back: icnv_pairwise_dist_rows_f64."""
+    x = np.asfortranarray(np.asarray(x, dtype=np.float64))
+    if x.ndim != 2:
+        raise ValueError("x must be a matrix (observations x variables)")
+    n, G = x.shape
+    n_out = n * (n - 1) // 2
+    if out is None:
+        out = np.empty(n_out, dtype=np.float64)
+    if out.dtype != np.float64 or out.size != n_out or not out.flags.c_contiguous:
+        raise ValueError("out must be a contiguous float64 vector of n (n - 1) / 2 entries")
+    _lib.check(_lib.load().icnv_pairwise_dist_rows_f64(_p(x), n, G, _p(out)))
+    return out
+
+
 # ---- CNV region calling on the state matrix (R/inferCNV_HMM.R:706-1087) ---------------------------------------
 
 def _u8(a) -> np.ndarray:

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libinfercnv_b200.so")
 SOURCES = ["icnv_api.cu", "icnv_smooth.cu", "icnv_viterbi.cu", "icnv_median_filter.cu", "icnv_reduce.cu",
-           "icnv_synth.cu", "icnv_regions.cu", "icnv_ingest.cu"]
+           "icnv_synth.cu", "icnv_regions.cu", "icnv_ingest.cu", "icnv_dist.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -1671,6 +1671,43 @@ int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, 
     return ICNV_OK;
 }
 
+int icnv_pairwise_dist_f64(const double *X, int64_t G, int64_t C, const int32_t *cells, int64_t n, double *out) {
+    ICNV_HOST_PROLOGUE();
+    if (!cells) n = C;
+    if (!X || G < 0 || C <= 0 || n < 0 || (n >= 2 && !out)) return set_error(ICNV_E_BAD_ARG, "icnv_pairwise_dist_f64: bad argument");
+    for (int64_t i = 0; cells && i < n; ++i)
+        if (cells[i] < 0 || cells[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index out of range");
+    if (n < 2) return ICNV_OK;
+    const size_t n_out = (size_t)n * (size_t)(n - 1) / 2;
+    double *dX = nullptr, *d_out = (double *)scratch(SLOT_OUT, sizeof(double) * n_out);
+    int32_t *d_idx = cells ? (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n) : nullptr;
+    int rc;
+    if (!d_out || (cells && !d_idx)) return ICNV_E_NOMEM;
+    if (G > 0 && (rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    if (G == 0) dX = d_out;   // never read
+    if (cells) ICNV_CUDA(cudaMemcpyAsync(d_idx, cells, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if ((rc = icnv_dev_pairwise_dist_f64(dX, G, G, d_idx, n, d_out, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
+int icnv_pairwise_dist_rows_f64(const double *x, int64_t n, int64_t G, double *out) {
+    ICNV_HOST_PROLOGUE();
+    if (!x || G < 0 || n < 0 || (n >= 2 && !out)) return set_error(ICNV_E_BAD_ARG, "icnv_pairwise_dist_rows_f64: bad argument");
+    if (n < 2) return ICNV_OK;
+    const size_t n_out = (size_t)n * (size_t)(n - 1) / 2;
+    double *dX = nullptr, *d_out = (double *)scratch(SLOT_OUT, sizeof(double) * n_out);
+    int rc;
+    if (!d_out) return ICNV_E_NOMEM;
+    if (G > 0 && (rc = upload_matrix(x, G * n, &dX, SLOT_IN, st))) return rc;
+    if (G == 0) dX = d_out;   // never read
+    if ((rc = icnv_dev_pairwise_dist_rows_f64(dX, n, n, G, d_out, st))) return rc;
+    ICNV_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    ICNV_CUDA(cudaStreamSynchronize(st));
+    return ICNV_OK;
+}
+
 /* mu, sigma (n-1) over all values of n cells from the cells' own (sum, sd): sum of squares about mu of a cell =
  * sd_c^2 (G-1) + G (mean_c - mu)^2.  Plain host arithmetic on 2n numbers, in list order. */
 void icnv_combine_cell_stats(const double *sums, const double *sds, int64_t n, int64_t G, double *mu, double *sigma) {

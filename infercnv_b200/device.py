@@ -382,6 +382,18 @@ class Engine:
         _lib.check(self.lib.icnv_dev_scatter_group_states_u8(gst.data_ptr(), G, C, d_grp_of.data_ptr(), st.data_ptr(), _stream_ptr()))
         return st, flag
 
+    def pairwise_dist(self, X, cells=None, out=None):
+        """Euclidean distances between the listed local cells (rows of X; default all) as R's "dist" vector, on the device
+        (`hclust(parallelDist(t(expr[, cells])))`, R/inferCNV_tumor_subclusters.R:191): n (n - 1) / 2 doubles."""
+        G = X.shape[1]
+        idx = None if cells is None else torch.as_tensor(np.asarray(cells, dtype=np.int32), device=self.tdev)
+        n = X.shape[0] if idx is None else int(idx.numel())
+        if out is None:
+            out = torch.empty(n * (n - 1) // 2, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.icnv_dev_pairwise_dist_f64(X.data_ptr(), G, X.stride(0), idx.data_ptr() if idx is not None else None,
+                                                       n, out.data_ptr(), _stream_ptr()))
+        return out
+
     def mean_sd(self, X, groups_local):
         """mu / sigma over all values of the listed cells across ALL ranks (.i3HMM_get_sd_trend_by_num_cells_fit,
         R/inferCNV_i3HMM.R:17-30).  groups_local: per group, this rank's LOCAL columns (the planner's slices).

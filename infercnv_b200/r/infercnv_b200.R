@@ -436,6 +436,27 @@ infercnvb200_run_smooth_block <- function(infercnv_obj, window_length=101, max_c
     list(infercnv_obj = infercnv_obj, hmm_obj = hmm_obj)
 }
 
+## parallelDist::parallelDist as the reference calls it before every hclust() - parallelDist(t(expr[, cells]), threads = n)
+## (R/inferCNV_tumor_subclusters.R:191,411,472,582,609; R/inferCNV_ops.R:1930,3242; R/inferCNV_heatmap.R:719,755,1062,1079).
+## Same signature as parallelDist::parallelDist(x, method = "euclidean", diag = FALSE, upper = FALSE, threads = NULL, ...); any
+## method but the default one, a non-matrix / non-double / NA-holding x, or a GPU error goes to the original.  `threads` never
+## reaches the GPU path.  infercnv imports the function (R/inferCNV_constants.R:27), so the replacement is bound in the
+## package's IMPORTS environment (infercnvb200_install); the "dist" object it returns is what hclust() and as.matrix() expect.
+b200_parallelDist <- function(x, method = "euclidean", diag = FALSE, upper = FALSE, threads = NULL, ...) {
+    orig <- .icnv_env$orig_parallelDist
+    ok <- .icnv_enabled() && identical(method, "euclidean") && is.matrix(x) && is.double(x) && !anyNA(x) && nrow(x) >= 2 &&
+        nrow(x) <= 65536          # hclust()'s own limit
+    if (ok) {
+        d <- .icnv_try(.Call("icnvR_pairwise_dist", x), "parallelDist (euclidean)")
+        if (!is.null(d)) {
+            attributes(d) <- list(Size = nrow(x), Labels = rownames(x), Diag = diag, Upper = upper, method = "euclidean",
+                                  call = match.call(), class = "dist")
+            return(d)
+        }
+    }
+    orig(x, method = method, diag = diag, upper = upper, threads = threads, ...)
+}
+
 infercnvb200_install <- function() {
     fns <- c("subtract_ref_expr_from_obs", "smooth_by_chromosome", "center_cell_expr_across_chromosome",
              "predict_CNV_via_HMM_on_indiv_cells", "predict_CNV_via_HMM_on_tumor_subclusters",
@@ -447,10 +468,24 @@ infercnvb200_install <- function() {
     ns <- asNamespace("infercnv")
     .icnv_env$orig <- lapply(stats::setNames(fns, fns), function(f) get(f, envir = ns))
     for (f in fns) utils::assignInNamespace(f, get(paste0("b200_", f)), ns = "infercnv")
+    ## parallelDist is an IMPORT of infercnv: its binding lives in the parent of the namespace ("imports:infercnv")
+    imp <- parent.env(ns)
+    if (exists("parallelDist", envir = imp, inherits = FALSE)) {
+        .icnv_env$orig_parallelDist <- get("parallelDist", envir = imp)
+        unlockBinding("parallelDist", imp)
+        assign("parallelDist", b200_parallelDist, envir = imp)
+        lockBinding("parallelDist", imp)
+    }
     invisible(TRUE)
 }
 
 infercnvb200_uninstall <- function() {
     for (f in names(.icnv_env$orig)) utils::assignInNamespace(f, .icnv_env$orig[[f]], ns = "infercnv")
+    imp <- parent.env(asNamespace("infercnv"))
+    if (!is.null(.icnv_env$orig_parallelDist)) {
+        unlockBinding("parallelDist", imp)
+        assign("parallelDist", .icnv_env$orig_parallelDist, envir = imp)
+        lockBinding("parallelDist", imp)
+    }
     invisible(TRUE)
 }

@@ -222,6 +222,19 @@ SEXP icnvR_mean_sd(SEXP expr, SEXP cells) {
     return ans;
 }
 
+/* parallelDist(x) (method "euclidean") for x = observations x variables, the t(expr.data[, cells]) every hclust() call site
+ * of the reference builds (R/inferCNV_tumor_subclusters.R:191, R/inferCNV_ops.R:1930, ...): the bare "dist" vector, the R
+ * closure attaches Size / Labels / class */
+SEXP icnvR_pairwise_dist(SEXP x) {
+    SEXP dim = Rf_getAttrib(x, R_DimSymbol);
+    int64_t n = INTEGER(dim)[0], G = INTEGER(dim)[1];
+    SEXP ans = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(n * (n - 1) / 2)));
+    int rc = icnv_pairwise_dist_rows_f64(REAL(x), n, G, REAL(ans));
+    UNPROTECT(1);
+    fail_if(rc);
+    return ans;
+}
+
 /* normalize_counts_by_seq_depth (ops.R:3064-3111); normalize_factor NA -> median of colSums */
 SEXP icnvR_normalize(SEXP expr, SEXP normalize_factor) {
     SEXP dim = Rf_getAttrib(expr, R_DimSymbol);
@@ -399,6 +412,7 @@ static const R_CallMethodDef call_methods[] = {
     {"icnvR_viterbi_per_chr", (DL_FUNC)&icnvR_viterbi_per_chr, 9}, {"icnvR_scale", (DL_FUNC)&icnvR_scale, 1},
     {"icnvR_clear_noise_threshold", (DL_FUNC)&icnvR_clear_noise_threshold, 4},
     {"icnvR_smooth_hmm", (DL_FUNC)&icnvR_smooth_hmm, 11},   {"icnvR_init_devices", (DL_FUNC)&icnvR_init_devices, 1},
+    {"icnvR_pairwise_dist", (DL_FUNC)&icnvR_pairwise_dist, 1},
     {NULL, NULL, 0}};
 
 void R_init_infercnvb200_shim(DllInfo *dll) {

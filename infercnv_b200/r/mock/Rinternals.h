@@ -6,6 +6,7 @@
 typedef struct SEXPREC *SEXP;
 typedef void *(*DL_FUNC)(void);
 typedef struct _DllInfo DllInfo;
+typedef ptrdiff_t R_xlen_t;
 typedef struct { const char *name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
 #define REALSXP 14
 #define INTSXP 13

@@ -643,3 +643,18 @@ def order_reduce(data, data_gene_names, position_gene_names, chr, start, stop):
     rows = np.array([data_index[keep[i]] for i in order], dtype=np.int32)
     return {"expr": api.gather_genes(data, rows), "gene_names": [keep[i] for i in order], "chr": chr[sel],
             "start": start[sel], "stop": stop[sel]}
+
+
+# ---- distances for hclust() (parallelDist::parallelDist, an import of the reference: R/inferCNV_constants.R:27) -------------
+
+def parallelDist(x, method: str = "euclidean", threads=None) -> np.ndarray:
+    """`parallelDist(t(expr.data[, cells]), threads=...)` as the reference calls it before every hclust()
+    (R/inferCNV_tumor_subclusters.R:191, R/inferCNV_ops.R:1930, ...): x is observations x variables (cells x genes), the
+    result R's "dist" vector (strict lower triangle by columns).  Only the default method is on the GPU; `threads` is accepted
+    and ignored like every other thread count on this path."""
+    if method != "euclidean":
+        raise NotImplementedError(f"parallelDist(method={method!r}): only 'euclidean' (the reference never passes another)")
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim != 2:
+        raise ValueError("x must be a matrix (observations x variables)")
+    return api.pairwise_dist_rows(x)

@@ -627,6 +627,34 @@ ORC_API int orc_mean_sd_over_cells(const double *X, int64_t G, const int32_t *id
     return 0;
 }
 
+/* parallelDist(t(X[, cells])), method "euclidean" - the input of every hclust() in the reference
+ * (R/inferCNV_tumor_subclusters.R:191,411,472,582,609; R/inferCNV_ops.R:1930,3242; R/inferCNV_heatmap.R:719,755,1062,1079).
+ * parallelDist (CRAN, an Imports: dependency of the reference's DESCRIPTION, not vendored under /root/reference; no version
+ * pin there) computes sqrt(accu(square(A - B))) per pair with Armadillo; stats::dist (R's src/library/stats/src/distance.c,
+ * R_euclidean) computes the same sum gene by gene: dev = x[i] - x[j]; dist += dev * dev; sqrt(dist).  This restates the latter
+ * (the two differ only in the order of the additions, ~1e-16 relative); the result is R's "dist" vector: the strict lower
+ * triangle by columns.  cells = NULL: all C columns.  PARITY UNPINNED by the reference (it holds no distance vectors):
+ * tests/test_oracle_dist.py pins this against scipy.spatial.distance.pdist instead. */
+ORC_API int orc_pairwise_dist(const double *X, int64_t G, int64_t C, const int32_t *cells, int64_t n, double *out, int nthreads) {
+    if (!cells) n = C;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (int64_t a = 0; a < n; ++a) {
+        const double *xa = X + G * (cells ? (int64_t)cells[a] : a);
+        double *o = out + n * a - a * (a + 1) / 2 - a - 1;
+        for (int64_t b = a + 1; b < n; ++b) {
+            const double *xb = X + G * (cells ? (int64_t)cells[b] : b);
+            double d = 0.0;
+            for (int64_t g = 0; g < G; ++g) {
+                const double dev = xa[g] - xb[g];
+                d += dev * dev;
+            }
+            o[b] = sqrt(d);
+        }
+    }
+    return 0;
+}
+
 /* R/inferCNV_ops.R:2302-2346 clear_noise_via_ref_mean_sd (noise_logistic = FALSE):
  * mu = mean(X[, ref]); s = mean_c sd(X[, ref_c]) * sd_amplifier; values strictly inside
  * (mu - s, mu + s) become mu.  Used only to check the bundled golden end to end. */

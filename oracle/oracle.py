@@ -40,8 +40,13 @@ def lib() -> ct.CDLL:
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "liboracle.so")
-        if not os.path.exists(so):
-            build()
+        src = os.path.join(_HERE, "infercnv_oracle.c")
+        if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src) and os.access(_HERE, os.W_OK)):
+            try:
+                build()
+            except (OSError, subprocess.CalledProcessError):
+                if not os.path.exists(so):
+                    raise
         _LIB = ct.CDLL(so)
         _LIB.orc_pnorm_upper_log.restype = ct.c_double
         _LIB.orc_pnorm_upper_log.argtypes = [ct.c_double]
@@ -260,6 +265,19 @@ def mean_sd_over_cells(X, idx):
                                       ct.byref(sg))
     assert rc == 0
     return mu.value, sg.value
+
+
+def pairwise_dist(X, cells=None, nthreads=1) -> np.ndarray:
+    """R's "dist" vector (strict lower triangle by columns) of the euclidean distances between the listed cells."""
+    X = _f(X)
+    G, C = X.shape
+    idx = None if cells is None else _i32(cells)
+    n = C if idx is None else len(idx)
+    out = np.empty(n * (n - 1) // 2, dtype=np.float64)
+    rc = lib().orc_pairwise_dist(_dp(X), ct.c_int64(G), ct.c_int64(C), _ip(idx) if idx is not None else None, ct.c_int64(n),
+                                 _dp(out), int(nthreads))
+    assert rc == 0
+    return out
 
 
 def clear_noise_via_ref_mean_sd(X, ref_idx, sd_amplifier=1.5) -> np.ndarray:

@@ -23,7 +23,7 @@ CSRC = os.path.join(ROOT, "infercnv_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 OUT = os.path.join(OUT_DIR, "libinfercnv_b200_emu.so")
 EMULATED = ["icnv_api.cu", "icnv_regions.cu", "icnv_ingest.cu", "icnv_reduce.cu", "icnv_smooth.cu", "icnv_viterbi.cu",
-            "icnv_median_filter.cu", "icnv_synth.cu"]
+            "icnv_median_filter.cu", "icnv_synth.cu", "icnv_dist.cu"]
 
 # The asynchronous-copy primitives (inline PTX) get synchronous stand-ins: the copy happens when it is issued - the
 # earliest moment the hardware could perform it, so a buffer that is still being read when its refill is issued shows

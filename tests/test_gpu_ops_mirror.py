@@ -133,3 +133,23 @@ def test_hmm_drivers_and_median_filter_through_the_mirror(example_object, hmm_fi
     np.testing.assert_allclose(mf.expr_data, want_mf, rtol=0, atol=1e-15)
     with pytest.raises(ValueError):
         ops.apply_median_filtering(o, window_size=4)
+
+
+def test_parallelDist_as_the_reference_calls_it_before_hclust(example_object):
+    """hc <- hclust(parallelDist(t(tumor_expr_data), threads = ...)) - R/inferCNV_tumor_subclusters.R:191: the distance vector
+    of the observation cells of the bundled example, against the oracle and (when scipy is there) scipy's own pdist."""
+    from mirror import ops
+    expr = example_object["expr"]
+    obs = np.concatenate(example_object["obs_groups"])
+    d = ops.parallelDist(expr[:, obs].T, threads=4)
+    np.testing.assert_allclose(d, orc.pairwise_dist(expr, obs), rtol=1e-13, atol=0)
+    try:
+        from scipy.spatial.distance import pdist
+        from scipy.cluster.hierarchy import linkage
+    except ImportError:
+        return
+    np.testing.assert_allclose(d, pdist(expr[:, obs].T), rtol=1e-13, atol=0)
+    # the tree hclust(method = "ward.D2") builds from it is the tree built from scipy's distances (merge heights equal)
+    np.testing.assert_allclose(linkage(d, method="ward")[:, 2], linkage(pdist(expr[:, obs].T), method="ward")[:, 2], rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        ops.parallelDist(expr[:, obs].T, method="manhattan")

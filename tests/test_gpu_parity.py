@@ -596,3 +596,48 @@ def test_median_filter_example_object_subclusters(api, example_object):
     got = api.median_filter(X, cs, cl, groups, 7)
     want = orc.median_filter(X, cs, cl, groups, 7, nthreads=orc.max_threads())
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-15)
+
+
+# ---- pairwise distances between cells (the input of every hclust() in the reference) -----------------
+@pytest.mark.parametrize("G,C,n", [(1000, 300, 257), (17, 9, 5), (333, 130, 129), (48, 2, 2), (1, 40, 40)])
+def test_pairwise_dist_vs_oracle(api, G, C, n):
+    """icnv_pairwise_dist_f64 = parallelDist(t(X[, cells])) (euclidean) as R's "dist" vector: tile edges (n = 129, 257), a gene
+    count that is no multiple of the 16-gene stage, a shuffled subset of the columns, duplicated cells (distance exactly 0)."""
+    rng = np.random.default_rng(7 + G)
+    X = np.asfortranarray(1.0 + 0.1 * rng.normal(size=(G, C)))
+    cells = rng.permutation(C)[:n].astype(np.int32)
+    if n >= 5:
+        cells[3] = cells[1]          # the same cell twice: distance exactly 0
+        X[:, cells[4]] = X[:, cells[0]] + 1e-9   # near-identical cells keep their relative accuracy (difference form)
+    got = api.pairwise_dist(X, cells)
+    want = orc.pairwise_dist(X, cells, nthreads=orc.max_threads())
+    assert got.shape == (n * (n - 1) // 2,)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+    if n >= 5:
+        assert got[n * 1 - 1 * 2 // 2 + (3 - 1 - 1)] == 0.0   # the pair (1, 3)
+    # the matrix as parallelDist() receives it (observations x variables = t(X[, cells])): same sums in the same order
+    np.testing.assert_array_equal(api.pairwise_dist_rows(np.asfortranarray(X[:, cells].T)), got)
+    all_cells = api.pairwise_dist(X)
+    np.testing.assert_allclose(all_cells, orc.pairwise_dist(X, nthreads=orc.max_threads()), rtol=1e-13, atol=0)
+
+
+def test_pairwise_dist_degenerate_shapes_and_errors(api):
+    X = np.asfortranarray(np.arange(12, dtype=np.float64).reshape(4, 3))
+    assert api.pairwise_dist(X, [2]).size == 0 and api.pairwise_dist(X, []).size == 0
+    np.testing.assert_allclose(api.pairwise_dist(X, [0, 2]), [np.sqrt(4 * 2.0 ** 2)])
+    with pytest.raises(Exception):
+        api.pairwise_dist(X, [0, 3])          # column out of range
+    Xn = X.copy(order="F")
+    Xn[1, 1] = np.nan                          # NaN propagates to the pairs of that cell only (the R wrapper falls back on NA)
+    d = api.pairwise_dist(Xn)
+    assert np.isnan(d[0]) and np.isfinite(d[1]) and np.isnan(d[2])
+
+
+def test_pairwise_dist_example_object(api, example_object):
+    """The bundled example's final matrix (4613 genes x 20 cells), observation cells only - the call
+    hclust(parallelDist(t(tumor_expr_data))) of define_signif_tumor_subclusters makes (R/inferCNV_tumor_subclusters.R:191)."""
+    X = example_object["expr"]
+    obs = np.concatenate(example_object["obs_groups"]).astype(np.int32)
+    got = api.pairwise_dist(X, obs)
+    np.testing.assert_allclose(got, orc.pairwise_dist(X, obs), rtol=1e-13, atol=0)
+    assert got.size == len(obs) * (len(obs) - 1) // 2 and np.all(got > 0)
