@@ -85,8 +85,9 @@ def launch_count() -> int:
 
 
 def set_hmm_mode(mode) -> None:
-    """0 / "exact": reference-order arithmetic; 1 / "fast": certified fast path (default)."""
-    m = {"exact": 0, "fast": 1}.get(mode, mode)
+    """0 / "exact": reference-order arithmetic; 1 / "fast64": certified FP64 pass; 2 / "fast": certified FP32 pass with
+    per-path margins (default).  Sequences a pass cannot certify are recomputed in reference-order arithmetic either way."""
+    m = {"exact": 0, "fast64": 1, "fast": 2}.get(mode, mode)
     _lib.check(_lib.load().icnv_set_hmm_mode(int(m)))
 
 

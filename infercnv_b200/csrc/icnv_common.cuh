@@ -50,6 +50,7 @@ enum ScratchSlot {
     SLOT_RG_REC,                      // region records of the last call (kept until fetched)
     SLOT_VIT_ITEMS,                   // chromosome work items of the Viterbi launch (cached: Ctx::up_items)
     SLOT_MF_PRE,                      // median filter: range of the matrix and the value sample of its pre-pass
+    SLOT_TABLE32,                     // single-precision emission table
     SLOT_COUNT
 };
 
@@ -64,8 +65,8 @@ struct Ctx {
     void *slot_ptr[SLOT_COUNT] = {};
     size_t slot_bytes[SLOT_COUNT] = {};
     std::atomic<int64_t> launches{0};
-    int hmm_mode = 1;                 // 0 reference-order arithmetic, 1 certified fast path
-    bool table_uploaded = false;
+    int hmm_mode = 2;                 // 0 reference-order arithmetic, 1 certified FP64 pass, 2 certified FP32 pass (per-path margins)
+    bool table_uploaded = false, table32_uploaded = false;
     bool math_tables_uploaded = false;
     unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list
     int64_t rg_n = 0;                 // number of region records held in SLOT_RG_REC

@@ -50,6 +50,8 @@ struct dim3 {
 struct uint4 { unsigned x, y, z, w; };
 struct int2 { int x, y; };
 struct double2 { double x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
