@@ -618,6 +618,7 @@ def main():
         mf_bytes = BYTES_MF * n_listed * G
         parts = {"cell_pipeline pass 2": ms_pass2, "viterbi": ms_hmm, "median_filter": ms_mf}
         reruns = int(api.hmm_rerun_count())
+        second_pass = int(api.hmm_second_pass_count())
 
         def roof(name, kernel, nbytes, ms, note, **extra):
             ach = nbytes / (ms * 1e-3) / 1e9
@@ -628,9 +629,9 @@ def main():
             return d
         r_p2 = roof("cell_pipeline_pass2", "cell_pipeline kernel, pass 2 over all local cells", pass2_bytes, ms_pass2,
                     "16 B per cell-gene (one FP64 read, one FP64 write); see DESIGN.md section 3 K2")
-        r_hmm = roof("viterbi_fast", f"viterbi_fast_kernel<{6 if cfg['hmm'] == 'i6' else 3}> + exact re-run list", hmm_bytes, ms_hmm,
+        r_hmm = roof("viterbi_fast", f"viterbi_fast32_kernel<{6 if cfg['hmm'] == 'i6' else 3}> + FP64 second pass + exact re-run list", hmm_bytes, ms_hmm,
                      "9 B per cell-gene (8 read + 1 state byte); see DESIGN.md section 3 K3",
-                     sequences_rerun_in_reference_order_arithmetic=reruns, sequences=int(C_local * len(cs)))
+                     sequences_rerun_in_reference_order_arithmetic=reruns, sequences_second_pass_fp64=second_pass, sequences=int(C_local * len(cs)))
         r_mf = roof("median_filter", "median filter kernel (window 7: 9 x 9 taps)", mf_bytes, ms_mf,
                     "16 B per listed cell-gene; see DESIGN.md section 3 K4") if cfg["median_filter"] else None
         dominant = max(parts, key=parts.get)

@@ -87,13 +87,17 @@ ICNV_API const char *icnv_version(void);
 /* Number of kernel launches issued by this library since icnv_init (for bench `gpu_launches`). */
 ICNV_API int64_t icnv_launch_count(void);
 
-/* HMM arithmetic.  mode 0: reference-order IEEE arithmetic for every sequence.  mode 1 (default):
- * certified fast path - table emission + structured recursion, every arg-max margin checked, and
- * each sequence whose smallest margin is below 1e-7 recomputed in mode-0 arithmetic; the state
- * calls are the same as mode 0.  Also settable with the environment variable ICNV_HMM_MODE. */
+/* HMM arithmetic.  mode 0: reference-order IEEE arithmetic for every sequence.  mode 1: certified FP64 pass - table
+ * emission + structured recursion, every arg-max margin checked, and each sequence whose smallest margin is below 1e-7
+ * recomputed in mode-0 arithmetic.  mode 2 (default): a single-precision pass first, certified by the margins along the
+ * returned path only; what it cannot certify goes through the mode-1 pass, what that cannot certify through mode 0.  The
+ * state calls are the same in all modes.  Also settable with the environment variable ICNV_HMM_MODE (read at icnv_init). */
 ICNV_API int icnv_set_hmm_mode(int mode);
 /* Number of sequences the last Viterbi call recomputed in reference-order arithmetic (syncs). */
 ICNV_API int64_t icnv_hmm_rerun_count(void);
+/* Number of sequences the single-precision pass (mode 2) of the last Viterbi call could not certify and handed to the FP64
+ * pass (syncs); 0 in modes 0 and 1. */
+ICNV_API int64_t icnv_hmm_second_pass_count(void);
 
 /* ---- host-pointer entry points (what the R shim binds) ---------------------------------------- */
 

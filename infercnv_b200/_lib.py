@@ -29,6 +29,7 @@ SIGNATURES = {
     "icnv_launch_count": (c_i64, []),
     "icnv_set_hmm_mode": (c_int, [c_int]),
     "icnv_hmm_rerun_count": (c_i64, []),
+    "icnv_hmm_second_pass_count": (c_i64, []),
     "icnv_ref_means_f64": (c_int, [_P, c_i64, c_i64, _P, _P, c_int, c_int, _P]),
     "icnv_subtract_ref_f64": (c_int, [_P, _P, c_i64, c_i64, _P, c_int, c_int]),
     "icnv_smooth_f64": (c_int, [_P, _P, c_i64, c_i64, _P, _P, c_int, c_int]),

@@ -95,6 +95,11 @@ def hmm_rerun_count() -> int:
     return int(_lib.load().icnv_hmm_rerun_count())
 
 
+def hmm_second_pass_count() -> int:
+    """sequences the single-precision pass of the last Viterbi call handed to the FP64 pass"""
+    return int(_lib.load().icnv_hmm_second_pass_count())
+
+
 def ref_means(X, groups, inv_log=False) -> np.ndarray:
     X = _f64(X)
     G, C = X.shape

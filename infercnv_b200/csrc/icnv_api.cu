@@ -383,6 +383,8 @@ static int init_slot(int slot, int device) {
     c.up_segs.clear();
     c.up_items.clear();
     c.hmm_list_count = nullptr;
+    c.hmm_seq_counts = nullptr;
+    c.hmm_seq_k = 0;
     c.rg_n = 0;
     read_options(c, slot == 0);
     c.ready = true;

@@ -51,6 +51,7 @@ enum ScratchSlot {
     SLOT_VIT_ITEMS,                   // chromosome work items of the Viterbi launch (cached: Ctx::up_items)
     SLOT_MF_PRE,                      // median filter: range of the matrix and the value sample of its pre-pass
     SLOT_TABLE32,                     // single-precision emission table
+    SLOT_SEQ,                         // per-chromosome lists of the sequences for the FP64 second pass
     SLOT_COUNT
 };
 
@@ -69,6 +70,8 @@ struct Ctx {
     bool table_uploaded = false, table32_uploaded = false;
     bool math_tables_uploaded = false;
     unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list
+    unsigned int *hmm_seq_counts = nullptr;  // per-chromosome counts of the sequences the single-precision pass handed on
+    int hmm_seq_k = 0;
     int64_t rg_n = 0;                 // number of region records held in SLOT_RG_REC
     // what the small per-launch tables (thread segments of the cell pipeline, chromosome items of the Viterbi) held when
     // they were last uploaded: an unchanged table is not copied again, so the slab loop of the host pipeline enqueues

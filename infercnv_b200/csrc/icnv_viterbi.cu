@@ -62,6 +62,11 @@ struct VitParams {
     const double *table;       // device copy of icnv_emis_table
     int means_monotone;        // state means sorted (either direction): the furthest state from any x is an end state
     const float4 *table32;     // device copy of icnv_emis_table32 (single-precision first pass)
+    // sequences the single-precision pass could not certify, grouped by (sorted) chromosome so that a warp of the FP64 pass
+    // still works on 32 sequences of one length: seq_cells[ks * C + i], i < seq_counts[ks]
+    int32_t *seq_cells;
+    unsigned int *seq_counts;
+    int seq_mode;              // viterbi_fast_kernel: 1 = the items are tiles of those lists instead of tiles of all cells
     int2 *list_out;
     unsigned int *list_out_count;
     unsigned int list_cap;
@@ -403,19 +408,44 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
     const double e_lim = (a - b) - p.tau;   // the launcher refuses the fast path unless a - b > 4 tau
     int err = 0;
 
+    // second pass with at most 32 chromosomes: lane l holds the number of 32-sequence tiles of chromosomes 0 .. l (a warp scan
+    // of the list lengths), an item number below the total names (chromosome, tile) directly - no empty items are drawn
+    const bool seq_compact = p.seq_mode && p.K <= 32;
+    long long seq_pre = 0, seq_total = 0;
+    if (seq_compact) {
+        long long t = lane < p.K ? ((long long)p.seq_counts[lane] + 31) / 32 : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t += u;
+        }
+        seq_pre = t;
+        seq_total = __shfl_sync(0xffffffffu, t, 31);
+    }
     for (;;) {
         unsigned long long item = 0;
         if (lane == 0) item = atomicAdd(p.counter, 1ull);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if ((int64_t)item >= p.n_items) break;
-        const int ks = (int)(item / (unsigned long long)p.n_tiles);
-        const int64_t tile = (int64_t)(item % (unsigned long long)p.n_tiles);
+        if ((int64_t)item >= (seq_compact ? seq_total : p.n_items)) break;
+        int ks = (int)(item / (unsigned long long)p.n_tiles);
+        int64_t tile = (int64_t)(item % (unsigned long long)p.n_tiles);
+        if (seq_compact) {
+            ks = __popc(__ballot_sync(0xffffffffu, seq_pre <= (long long)item));
+            const long long before = __shfl_sync(0xffffffffu, seq_pre, (ks + 31) & 31);   // lane ks - 1 (unused for ks = 0)
+            tile = (int64_t)item - (ks > 0 ? before : 0);
+        }
         const int cs = p.item_chr_start[ks];
         const int n = p.item_chr_len[ks];
         const int64_t c0 = tile * 32;
-        const int64_t c = c0 + lane;
-        const bool active = c < p.C;
-        const int64_t cc = active ? c : (p.C - 1);
+        int64_t c = c0 + lane;
+        bool active = c < p.C;
+        if (p.seq_mode) {   // second pass: lane = entry c0 + lane of this chromosome's list of uncertified sequences
+            const int64_t cnt = (int64_t)p.seq_counts[ks];
+            if (c0 >= cnt) continue;
+            active = c0 + lane < cnt;
+            c = (int64_t)p.seq_cells[(int64_t)ks * p.C + (active ? c0 + lane : c0)];
+        }
+        const int64_t cc = active ? c : (p.seq_mode ? c : p.C - 1);
         uint8_t *__restrict__ scol = p.states + p.G * cc;
         if (n < 2) {
             if (active && n == 1) scol[cs] = 3;
@@ -441,6 +471,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                 const int row = q * 4 + (lane >> 3);
                 int64_t cell = c0 + row;
                 if (cell >= p.C) cell = p.C - 1;
+                if (p.seq_mode) cell = __shfl_sync(0xffffffffu, (int)cc, row);   // the cell of lane `row`
                 const double *src = p.X + p.G * cell + (ok ? gene : 0);
                 cp_async8(dst + row * TS + col, src, ok, pol);
             }
@@ -813,9 +844,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast32_kernel(const Vi
             }
             cert = fminf(mb, best - second);
         }
-        if (active && (dead || !(cert > VF32_EPS * (float)n))) {   // also catches NaN
-            unsigned pos = atomicAdd(p.list_out_count, 1u);
-            if (pos < p.list_cap) p.list_out[pos] = make_int2(p.item_chr_id[ks], (int)c);
+        if (active && (dead || !(cert > VF32_EPS * (float)n))) {   // also catches NaN: to the FP64 pass
+            const unsigned pos = atomicAdd(p.seq_counts + ks, 1u);
+            p.seq_cells[(int64_t)ks * p.C + pos] = (int32_t)c;      // at most C entries per chromosome
         }
         // ---- traceback (as in the FP64 kernel) ----------------------------------------------------------
         const bool wide = ((p.G & 7) == 0);
@@ -1140,12 +1171,19 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     p.margins = margins;
     p.err_flag = err_flag;
 
-    // counters: [0] work counter of the main launch, [1] work counter of the list launch, [2] list length
-    unsigned long long *d_counter = (unsigned long long *)scratch(SLOT_MISC2, 64);
+    // counters: [0] work counter of the main launch, [1] work counter of the list launch, [2] list length, [3] work counter of
+    // the FP64 second pass; behind them K list lengths of the single-precision pass (one per sorted chromosome)
+    const size_t counter_bytes = 4 * sizeof(unsigned long long) + sizeof(unsigned int) * (size_t)K;
+    unsigned long long *d_counter = (unsigned long long *)scratch(SLOT_MISC2, counter_bytes + 64);
     if (!d_counter) return ICNV_E_NOMEM;
-    ICNV_CUDA(cudaMemsetAsync(d_counter, 0, 3 * sizeof(unsigned long long), st));
+    ICNV_CUDA(cudaMemsetAsync(d_counter, 0, counter_bytes, st));
     p.counter = d_counter;
     c.hmm_list_count = reinterpret_cast<unsigned int *>(d_counter + 2);
+    c.hmm_seq_counts = reinterpret_cast<unsigned int *>(d_counter + 4);
+    c.hmm_seq_k = 0;
+    p.seq_mode = 0;
+    p.seq_cells = nullptr;
+    p.seq_counts = c.hmm_seq_counts;
 
     const bool want_margin = margins != nullptr;
     // the fast path needs .get_HMM's structure: one diagonal and one off-diagonal value
@@ -1223,12 +1261,27 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
         const int64_t need_blocks = (p.n_items + fw - 1) / fw;
         if (blocks > need_blocks) blocks = need_blocks;
         const int64_t list_blocks = c.sm_count;
-        const int64_t n_warps = std::max<int64_t>(blocks * fw, list_blocks * 4);
+        const int64_t n_warps = std::max<int64_t>(std::max<int64_t>(blocks * fw, (int64_t)c.sm_count * FAST_WARPS), list_blocks * 4);
         uint32_t *d_bp = (uint32_t *)scratch(SLOT_BP, sizeof(uint32_t) * (size_t)n_warps * (size_t)max_len * 32);
         if (!d_bp) return ICNV_E_NOMEM;
         p.bp = d_bp;
+        int32_t *d_seq = (int32_t *)scratch(SLOT_SEQ, sizeof(int32_t) * (size_t)K * (size_t)C);
+        if (!d_seq) return ICNV_E_NOMEM;
+        p.seq_cells = d_seq;
+        c.hmm_seq_k = K;
         fkern<<<(unsigned)blocks, fw * 32, smem, st>>>(p);
         ICNV_CHECK_LAUNCH("viterbi_fast32_kernel");
+        // second pass: the sequences the single-precision margins could not certify, 32 of one chromosome per warp, in the FP64
+        // arithmetic with its own (all-decisions) certificate; what that rejects goes on to the reference-order kernel
+        void (*fkern64)(const VitParams) = (m == 6) ? viterbi_fast_kernel<6, 16> : viterbi_fast_kernel<3, 16>;
+        const size_t smem64 = sizeof(double) * (4 * (ICNV_EMIS_N + 1) * TAB_REP + (size_t)FAST_WARPS * 2 * 32 * TS);
+        ICNV_CUDA(cudaFuncSetAttribute(fkern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+        p.seq_mode = 1;
+        p.counter = d_counter + 3;
+        const int64_t blocks64 = std::min<int64_t>(c.sm_count, (n_warps + FAST_WARPS - 1) / FAST_WARPS);
+        fkern64<<<(unsigned)blocks64, FAST_WARPS * 32, smem64, st>>>(p);
+        ICNV_CHECK_LAUNCH("viterbi_fast_kernel (second pass)");
+        p.seq_mode = 0;
         p.list = d_list;
         p.list_count = c.hmm_list_count;
         p.counter = d_counter + 1;
@@ -1275,6 +1328,18 @@ int icnv_set_hmm_mode(int mode) {
         return set_error(ICNV_E_BAD_ARG, "hmm mode must be 0 (reference-order), 1 (certified FP64 pass) or 2 (certified FP32 pass, default)");
     ctx().hmm_mode = mode;
     return ICNV_OK;
+}
+
+/* sequences the single-precision pass of the last Viterbi call handed to the FP64 pass (0 in the other modes) */
+int64_t icnv_hmm_second_pass_count(void) {
+    Ctx &c = ctx();
+    if (!c.ready || !c.hmm_seq_counts || c.hmm_seq_k <= 0) return 0;
+    std::vector<unsigned int> h((size_t)c.hmm_seq_k);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h.data(), c.hmm_seq_counts, sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t n = 0;
+    for (unsigned int v : h) n += v;
+    return n;
 }
 
 int64_t icnv_hmm_rerun_count(void) {

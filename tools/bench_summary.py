@@ -13,9 +13,9 @@ for f in sys.argv[1:]:
         print(f, "REF value %.3e" % d["value"], d["cpu_baseline"])
         continue
     st = d["stage_ms"]
-    print(f, "value %.3e step %.3f ms | smooth %.3f hmm %.3f mf %s | pass2 %.3f ms frac %.3f | hmm frac %.3f | reruns %s" % (
+    print(f, "value %.3e step %.3f ms | smooth %.3f hmm %.3f mf %s | pass2 %.3f ms frac %.3f | hmm frac %.3f | reruns %s second pass %s" % (
         d["value"], d["ms_per_step"], st["smooth_block"], st["hmm"], st["median_filter"], d["roofline_cell_pipeline"]["ms_per_launch"],
-        d["roofline_cell_pipeline"]["frac"], d["roofline_hmm"]["frac"], d["roofline_hmm"].get("sequences_rerun_in_reference_order_arithmetic")))
+        d["roofline_cell_pipeline"]["frac"], d["roofline_hmm"]["frac"], d["roofline_hmm"].get("sequences_rerun_in_reference_order_arithmetic"), d["roofline_hmm"].get("sequences_second_pass_fp64")))
     e = d.get("e2e")
     if e:
         print("     e2e %.3e  %.1f ms  (%s)" % (e["value"], e["ms_per_step"], e.get("host_memory")))
