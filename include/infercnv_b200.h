@@ -87,11 +87,12 @@ ICNV_API const char *icnv_version(void);
 /* Number of kernel launches issued by this library since icnv_init (for bench `gpu_launches`). */
 ICNV_API int64_t icnv_launch_count(void);
 
-/* HMM arithmetic.  mode 0: reference-order IEEE arithmetic for every sequence.  mode 1: certified FP64 pass - table
- * emission + structured recursion, every arg-max margin checked, and each sequence whose smallest margin is below 1e-7
- * recomputed in mode-0 arithmetic.  mode 2 (default): a single-precision pass first, certified by the margins along the
- * returned path only; what it cannot certify goes through the mode-1 pass, what that cannot certify through mode 0.  The
- * state calls are the same in all modes.  Also settable with the environment variable ICNV_HMM_MODE (read at icnv_init). */
+/* HMM arithmetic.  mode 0: reference-order IEEE arithmetic for every sequence.  mode 1 (default): certified FP64 pass -
+ * table emission + structured recursion, every arg-max margin checked, and each sequence whose smallest margin is below
+ * 1e-7 recomputed in mode-0 arithmetic.  mode 2 (option, measured slower on the benchmark data): a single-precision pass
+ * first, certified by the margins along the returned path only; what it cannot certify goes through the mode-1 pass, what
+ * that cannot certify through mode 0.  The state calls are the same in all modes.  Also settable with the environment
+ * variable ICNV_HMM_MODE (read at icnv_init). */
 ICNV_API int icnv_set_hmm_mode(int mode);
 /* Number of sequences the last Viterbi call recomputed in reference-order arithmetic (syncs). */
 ICNV_API int64_t icnv_hmm_rerun_count(void);

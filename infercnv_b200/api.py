@@ -85,9 +85,10 @@ def launch_count() -> int:
 
 
 def set_hmm_mode(mode) -> None:
-    """0 / "exact": reference-order arithmetic; 1 / "fast64": certified FP64 pass; 2 / "fast": certified FP32 pass with
-    per-path margins (default).  Sequences a pass cannot certify are recomputed in reference-order arithmetic either way."""
-    m = {"exact": 0, "fast64": 1, "fast": 2}.get(mode, mode)
+    """0 / "exact": reference-order arithmetic; 1 / "fast" / "fast64": certified FP64 pass (default); 2 / "fast32": a
+    single-precision pass certified by per-path margins first, then the FP64 pass for what it cannot certify (measured slower
+    on the benchmark data, kept as an option).  What no pass certifies is recomputed in reference-order arithmetic."""
+    m = {"exact": 0, "fast": 1, "fast64": 1, "fast32": 2}.get(mode, mode)
     _lib.check(_lib.load().icnv_set_hmm_mode(int(m)))
 
 

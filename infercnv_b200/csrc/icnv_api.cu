@@ -333,7 +333,7 @@ static int env_int(const char *name, int dflt, bool *set = nullptr) {
 // default is reported, so a stray variable in a user's shell cannot silently change which kernel runs.
 static void read_options(Ctx &c, bool verbose) {
     bool set;
-    if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : (e[0] == '1' ? 1 : 2);
+    if (const char *e = getenv("ICNV_HMM_MODE")) c.hmm_mode = (e[0] == '0' || e[0] == 'e') ? 0 : (e[0] == '2' ? 2 : 1);
     c.opt_cell_kernel = env_int("ICNV_CELL_KERNEL", 0);
     c.opt_cell_nt = env_int("ICNV_CELL_NT", 0);
     c.opt_cell_variant = env_int("ICNV_CELL_VARIANT", -1);

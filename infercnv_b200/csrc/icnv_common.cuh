@@ -66,7 +66,7 @@ struct Ctx {
     void *slot_ptr[SLOT_COUNT] = {};
     size_t slot_bytes[SLOT_COUNT] = {};
     std::atomic<int64_t> launches{0};
-    int hmm_mode = 2;                 // 0 reference-order arithmetic, 1 certified FP64 pass, 2 certified FP32 pass (per-path margins)
+    int hmm_mode = 1;                 // 0 reference-order arithmetic, 1 certified FP64 pass (default), 2 FP32 pass first (per-path margins; measured slower)
     bool table_uploaded = false, table32_uploaded = false;
     bool math_tables_uploaded = false;
     unsigned int *hmm_list_count = nullptr;  // device counter of the last Viterbi call's re-run list

@@ -292,7 +292,7 @@ def test_viterbi_cells_bit_identical(api, hmm_fixture, m):
     np.testing.assert_array_equal(got2, want)
 
 
-@pytest.mark.parametrize("mode", ["exact", "fast64", "fast"])
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast32"])
 def test_viterbi_modes_agree_with_oracle_at_scale(api, hmm_fixture, mode):
     """2e7 cell-genes of the bench's synthetic structure: the certified fast path and the
     reference-order path must both reproduce the oracle's states exactly."""
@@ -351,12 +351,15 @@ def test_viterbi_single_precision_pass_on_segmental_changes(api, hmm_fixture, m)
     Pi, delta = orc.hmm_params(m)
     want = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sd, nthreads=orc.max_threads())
     assert len(np.unique(want)) >= 3                      # the data does change state
-    api.set_hmm_mode("fast")
-    got = api.viterbi(X, cs, lens, Pi, delta, mean, sd)
-    reruns = api.hmm_rerun_count()
+    api.set_hmm_mode("fast32")
+    try:
+        got = api.viterbi(X, cs, lens, Pi, delta, mean, sd)
+        reruns = api.hmm_second_pass_count()
+    finally:
+        api.set_hmm_mode("fast")
     n_seq = C * int(np.sum(lens >= 2))
     changes = int(np.sum(want[1:] != want[:-1]))
-    print(f"\n[viterbi fp32 pass, m={m}] {changes} changes of state in {n_seq} sequences, {reruns} sequences re-run exactly")
+    print(f"\n[viterbi fp32 pass, m={m}] {changes} changes of state in {n_seq} sequences, {reruns} sequences handed to the FP64 pass")
     np.testing.assert_array_equal(got, want)
     assert reruns < 0.25 * n_seq
 
@@ -423,9 +426,9 @@ def test_viterbi_rerun_of_long_sequences(api, hmm_fixture, m):
         mean, sd = np.array([0.5, 1.5, 3.0]), np.array([0.25] * 3)
         Pi, delta = orc.hmm_params(3, 1e-6)
     want = orc.viterbi_matrix(X, cs, lens, Pi, delta, mean, sd)
-    # the FP64 pass rejects every sequence that meets a tie anywhere (all three lengths reach the exact kernel); the default
-    # FP32 pass only those whose tie lies on the path it returns - same states either way
-    for mode in ("fast64", "fast"):
+    # the FP64 pass rejects every sequence that meets a tie anywhere (all three lengths reach the exact kernel); with the
+    # optional FP32 pass first only those whose tie lies on the path it returns get that far - same states either way
+    for mode in ("fast", "fast32"):
         api.set_hmm_mode(mode)
         try:
             got = api.viterbi(X, cs, lens, Pi, delta, mean, sd)
@@ -433,7 +436,7 @@ def test_viterbi_rerun_of_long_sequences(api, hmm_fixture, m):
         finally:
             api.set_hmm_mode("fast")
         np.testing.assert_array_equal(got, want)
-        assert reruns >= (3 * (C // 2) if mode == "fast64" else 1)
+        assert reruns >= (3 * (C // 2) if mode == "fast" else 1)
         print(f"\n[viterbi long re-runs, m={m}, {mode}] {reruns} of {3 * C} sequences re-run")
 
 
