@@ -629,7 +629,8 @@ def main():
             return d
         r_p2 = roof("cell_pipeline_pass2", "cell_pipeline kernel, pass 2 over all local cells", pass2_bytes, ms_pass2,
                     "16 B per cell-gene (one FP64 read, one FP64 write); see DESIGN.md section 3 K2")
-        r_hmm = roof("viterbi_fast", f"viterbi_fast32_kernel<{6 if cfg['hmm'] == 'i6' else 3}> + FP64 second pass + exact re-run list", hmm_bytes, ms_hmm,
+        r_hmm = roof("viterbi_fast", (f"viterbi_fast32_kernel<{6 if cfg['hmm'] == 'i6' else 3}> + FP64 second pass + exact re-run list" if os.environ.get("ICNV_HMM_MODE", "1")[:1] == "2"
+                      else f"viterbi_fast_kernel<{6 if cfg['hmm'] == 'i6' else 3}> + exact re-run list"), hmm_bytes, ms_hmm,
                      "9 B per cell-gene (8 read + 1 state byte); see DESIGN.md section 3 K3",
                      sequences_rerun_in_reference_order_arithmetic=reruns, sequences_second_pass_fp64=second_pass, sequences=int(C_local * len(cs)))
         r_mf = roof("median_filter", "median filter kernel (window 7: 9 x 9 taps)", mf_bytes, ms_mf,

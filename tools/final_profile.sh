@@ -17,6 +17,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cell_pipeline -s 8 -c 1 -f -o gpurun_out/${tag}_prof_cellpipe $B > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:viterbi_fast -s 3 -c 1 -f -o gpurun_out/${tag}_prof_vfast $B > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:median_filter_merge -c 1 -f -o gpurun_out/${tag}_prof_medfilt python tools/bench_extra.py > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:median_filter_merge -s 3 -c 1 -f -o gpurun_out/${tag}_prof_medfilt_c4 python bench.py --config c4 --no-e2e --no-cpu-baseline --steps 2 --warmup 3 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pairwise_dist -c 1 -f -o gpurun_out/${tag}_prof_dist python tools/bench_extra.py > /dev/null 2>&1
+timeout 600 python tools/scaling_probe.py > gpurun_out/${tag}_scaling_probe.txt 2>&1
 B5="python bench.py --config c5 --cells 8000 --no-e2e --no-cpu-baseline --steps 2 --warmup 3"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cell_pipeline4 -s 8 -c 1 -f -o gpurun_out/${tag}_prof_cellpipe4_c5 $B5 > /dev/null 2>&1
 ls -la gpurun_out | tail -14
