@@ -1,5 +1,8 @@
 // icnv_api.cu - C ABI of libinfercnv_b200.so: lifecycle, the host-pointer entry points the R shim
 // binds, and the device-side composition of the smooth block.  See include/infercnv_b200.h.
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -79,6 +82,41 @@ int device_slots() { return g_slots; }
 // cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread at ~10 GB/s and blocks it, which
 // serialises the three-stream slab pipeline.  The library therefore owns pinned slabs and a few copy threads that move
 // the caller's slab into / out of them at memory bandwidth, so PCIe sees pinned transfers only.
+// One thread's share of a staging copy, with NON-TEMPORAL stores: the destination (a pinned ring slot the DMA engine reads
+// next, or the caller's result matrix) is not read again by this thread, so writing around the cache saves the write-allocate
+// read of every line - glibc's memcpy only does that above ~3/4 of the last-level cache per call, which is why the
+// end-to-end time dropped by 18 % between 2048- and 4096-cell slabs before this (profiles/r02_e2e_probe.txt).
+static void stream_copy(char *d, const char *s, size_t n) {
+#if defined(__x86_64__) && defined(__SSE2__)
+    if (n < (size_t)1 << 16) {
+        memcpy(d, s, n);
+        return;
+    }
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    memcpy(d, s, head);
+    d += head;
+    s += head;
+    n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + 48), e);
+        s += 64;
+        d += 64;
+    }
+    _mm_sfence();
+    memcpy(d, s, n - blocks * 64);
+#else
+    memcpy(d, s, n);
+#endif
+}
+
 class CopyPool {
 public:
     explicit CopyPool(int n) : n_(n) {
@@ -130,7 +168,7 @@ private:
             for (int k = 0; k < 2 && lo < hi; ++k) {   // the byte range [lo, hi) of job 0 followed by job 1
                 const size_t base = k == 0 ? 0 : j[0].n;
                 const size_t a = std::max(lo, base), b = std::min(hi, base + j[k].n);
-                if (a < b) memcpy(j[k].d + (a - base), j[k].s + (a - base), b - a);
+                if (a < b) stream_copy(j[k].d + (a - base), j[k].s + (a - base), b - a);
             }
             std::lock_guard<std::mutex> lk(mu_);
             if (--pending_ == 0) done_.notify_all();
@@ -655,7 +693,15 @@ static int host_pipeline_range(Ctx &c, const double *X, double *Y, int32_t *stat
     // cells) is far below its PCIe time (0.37 ms), so small slabs only shorten fill / drain; the per-cell Viterbi is bounded
     // below by its longest chromosome's serial recursion whatever the slab size, so HMM calls keep the measured 1024.
     int64_t slab_cells = hmm ? SLAB_CELLS : SLAB_CELLS_SMOOTH;
-    if (stage_in || stage_out) slab_cells = SLAB_CELLS;   // fewer, larger hand-overs to the copy threads
+    if (stage_in || stage_out) {
+        // pageable caller memory: fewer, larger hand-overs to the copy threads - about 320 MB of input per slab (4000 cells at
+        // 10 000 genes: 362 ms against 386 ms with 1024-cell slabs for c3, profiles/r02_e2e_probe.txt), but at least ten slabs
+        // so that filling and draining the pipeline stays a small share
+        int64_t by_bytes = ((int64_t)(320e6 / (8.0 * (double)G)) + 31) / 32 * 32;
+        by_bytes = std::max<int64_t>(256, std::min<int64_t>(8192, by_bytes));
+        const int64_t by_count = std::max<int64_t>(SLAB_CELLS, ((C + 9) / 10 + 31) / 32 * 32);
+        slab_cells = std::min(by_bytes, by_count);
+    }
     if (c.opt_slab_cells) slab_cells = c.opt_slab_cells;
     const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(slab_cells, C));
     const size_t slab_elems = (size_t)G * (size_t)slab;
