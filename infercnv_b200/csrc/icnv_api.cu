@@ -380,11 +380,12 @@ static void read_options(Ctx &c, bool verbose) {
     c.opt_vfast_warps = env_int("ICNV_VFAST_WARPS", 0);
     c.opt_mf_kernel = env_int("ICNV_MF_KERNEL", -1);
     c.opt_mf_list32 = env_int("ICNV_MF_LIST32", 0);
+    c.opt_vit_evict = env_int("ICNV_VIT_EVICT", 1) != 0;
     c.opt_slab_cells = env_int("ICNV_SLAB_CELLS", 0, &set);
     if (c.opt_slab_cells < 32 || c.opt_slab_cells > 65536) c.opt_slab_cells = 0;
     if (!verbose) return;
     static const char *names[] = {"ICNV_HMM_MODE", "ICNV_CELL_KERNEL", "ICNV_CELL_NT", "ICNV_CELL_VARIANT", "ICNV_CELL_PADQ",
-                                  "ICNV_CELL_LFIX", "ICNV_VFAST_WARPS", "ICNV_MF_KERNEL", "ICNV_MF_LIST32", "ICNV_SLAB_CELLS"};
+                                  "ICNV_CELL_LFIX", "ICNV_VFAST_WARPS", "ICNV_MF_KERNEL", "ICNV_MF_LIST32", "ICNV_SLAB_CELLS", "ICNV_VIT_EVICT"};
     for (const char *n : names)
         if (const char *e = getenv(n)) fprintf(stderr, "[infercnv_b200] non-default tuning switch %s=%s (read once at icnv_init)\n", n, e);
 }

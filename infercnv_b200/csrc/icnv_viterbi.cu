@@ -67,6 +67,7 @@ struct VitParams {
     int32_t *seq_cells;
     unsigned int *seq_counts;
     int seq_mode;              // viterbi_fast_kernel: 1 = the items are tiles of those lists instead of tiles of all cells
+    int evict_first;           // L2 policy of the input stream (ICNV_VIT_EVICT, default 1)
     int2 *list_out;
     unsigned int *list_out_count;
     unsigned int list_cap;
@@ -335,9 +336,10 @@ constexpr int TAB_REP = 8;       // table replicas: lane l reads replica l & 7, 
 // The matrix is read once: its lines are marked evict-first in L2 so that they do not push out the backpointer rings, which
 // are written in the forward pass and read back by the trace-back up to a chromosome later (without the hint a third of
 // the ring went to DRAM and back: 1.28 GB of DRAM traffic per 0.9 GB algorithmic).
-__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+__device__ __forceinline__ unsigned long long l2_evict_first_policy(int evict_first) {
     unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (evict_first) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid, unsigned long long pol) {
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
     const double a = p.a_diag, b = p.b_off;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC == rint(v), low word == (int)rint(v)
     const int tau_hi = __double2hiint(p.tau);
-    const unsigned long long pol = l2_evict_first_policy();
+    const unsigned long long pol = l2_evict_first_policy(p.evict_first);
     const double e_lim = (a - b) - p.tau;   // the launcher refuses the fast path unless a - b > 4 tau
     int err = 0;
 
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast32_kernel(const Vi
     uint16_t *__restrict__ bp = reinterpret_cast<uint16_t *>(p.bp + warp_global * (int64_t)p.max_len * 32);
     const float T1p = (float)(p.b_off - p.a_diag - 0.5);   // "come from the best state" in the frame where that state's stay is -1/2
     const float MAGIC = 12582912.0f;                        // 1.5 * 2^23: (v + MAGIC) - MAGIC == rintf(v), low bits == (int)rintf(v)
-    const unsigned long long pol = l2_evict_first_policy();
+    const unsigned long long pol = l2_evict_first_policy(p.evict_first);
     int err = 0;
 
     for (;;) {
@@ -1181,6 +1183,7 @@ int icnv_dev_viterbi_f64(const double *X, int64_t G, int64_t C, const int32_t *c
     c.hmm_list_count = reinterpret_cast<unsigned int *>(d_counter + 2);
     c.hmm_seq_counts = reinterpret_cast<unsigned int *>(d_counter + 4);
     c.hmm_seq_k = 0;
+    p.evict_first = c.opt_vit_evict;
     p.seq_mode = 0;
     p.seq_cells = nullptr;
     p.seq_counts = c.hmm_seq_counts;
