@@ -380,7 +380,7 @@ static void read_options(Ctx &c, bool verbose) {
     c.opt_vfast_warps = env_int("ICNV_VFAST_WARPS", 0);
     c.opt_mf_kernel = env_int("ICNV_MF_KERNEL", -1);
     c.opt_mf_list32 = env_int("ICNV_MF_LIST32", 0);
-    c.opt_vit_evict = env_int("ICNV_VIT_EVICT", 1) != 0;
+    c.opt_vit_evict = env_int("ICNV_VIT_EVICT", 2);
     c.opt_slab_cells = env_int("ICNV_SLAB_CELLS", 0, &set);
     if (c.opt_slab_cells < 32 || c.opt_slab_cells > 65536) c.opt_slab_cells = 0;
     if (!verbose) return;

@@ -83,7 +83,7 @@ struct Ctx {
     size_t pin_bytes[6] = {};
     // tuning switches, read from the environment ONCE in icnv_init (never at launch time); -1 / 0 = library default
     int opt_cell_kernel = 0, opt_cell_nt = 0, opt_cell_variant = -1, opt_cell_padq = 1, opt_cell_lfix = 1;
-    int opt_vfast_warps = 0, opt_mf_kernel = -1, opt_mf_list32 = 0, opt_vit_evict = 1;
+    int opt_vfast_warps = 0, opt_mf_kernel = -1, opt_mf_list32 = 0, opt_vit_evict = 2;
     long opt_slab_cells = 0;
     std::mutex mu;
 };

@@ -67,7 +67,7 @@ struct VitParams {
     int32_t *seq_cells;
     unsigned int *seq_counts;
     int seq_mode;              // viterbi_fast_kernel: 1 = the items are tiles of those lists instead of tiles of all cells
-    int evict_first;           // L2 policy of the input stream (ICNV_VIT_EVICT, default 1)
+    int evict_first;           // L2 policies (ICNV_VIT_EVICT): 0 none, 1 input stream evict_first, 2 (default) ring stores evict_last, 3 = 2 + discard of read ring lines
     int2 *list_out;
     unsigned int *list_out_count;
     unsigned int list_cap;
@@ -333,14 +333,29 @@ constexpr int FAST_WARPS = 16;   // default warps per CTA (one CTA per SM: the r
                                  // the gene loop stays spill-free, ~19 values are re-loaded from local memory per 8-gene tile
 constexpr int TAB_REP = 8;       // table replicas: lane l reads replica l & 7, so a 16-byte lookup never bank-conflicts
 
-// The matrix is read once: its lines are marked evict-first in L2 so that they do not push out the backpointer rings, which
-// are written in the forward pass and read back by the trace-back up to a chromosome later (without the hint a third of
-// the ring went to DRAM and back: 1.28 GB of DRAM traffic per 0.9 GB algorithmic).
+// L2 policies around the backpointer rings (129 MB at 16 warps x 148 SMs x 852 genes: more than the L2 holds beside the input
+// stream), measured at c3 (profiles/r02_hmm_fp32_cascade.md): no hint 13.2 GB of DRAM traffic per launch for 9 GB algorithmic;
+// input lines evict_first 16.7 GB (a 128-byte line holds two 8-gene tiles of a cell and is dropped between them) but 1 % faster;
+// ring stores evict_last 12.8 GB - the default; additionally discarding ring lines the trace-back has read 12.0 GB, 1 % slower.
 __device__ __forceinline__ unsigned long long l2_evict_first_policy(int evict_first) {
     unsigned long long pol;
     if (evict_first) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     else asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
+}
+// backpointer store with an L2 policy (ICNV_VIT_EVICT=2: the ring is kept with evict_last, the input stream is read normally)
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// drop one 128-byte line of the ring from L2 WITHOUT writing it back: the trace-back has read it, the next sequence overwrites it
+__device__ __forceinline__ void l2_discard_line(const void *line) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+}
+__device__ __forceinline__ void bp_store(uint16_t *ptr, uint16_t v, unsigned long long pol, bool hinted) {
+    if (hinted) asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(ptr), "h"(v), "l"(pol) : "memory");
+    else *ptr = v;
 }
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid, unsigned long long pol) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -406,7 +421,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
     const double a = p.a_diag, b = p.b_off;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC == rint(v), low word == (int)rint(v)
     const int tau_hi = __double2hiint(p.tau);
-    const unsigned long long pol = l2_evict_first_policy(p.evict_first);
+    const unsigned long long pol = l2_evict_first_policy(p.evict_first == 1);
+    const unsigned long long pol_ring = l2_evict_last_policy();
     const double e_lim = (a - b) - p.tau;   // the launcher refuses the fast path unless a - b > 4 tau
     int err = 0;
 
@@ -583,7 +599,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                     nu[k] = (stay ? d : T1) + le[k];
                     moved = __funnelshift_l((uint32_t)he, moved, 1);
                 }
-                bp[(int64_t)i * 32 + lane] = (uint16_t)(moved | ((uint32_t)i1 << 8));
+                bp_store(bp + (int64_t)i * 32 + lane, (uint16_t)(moved | ((uint32_t)i1 << 8)), pol_ring, p.evict_first >= 2);
             }
             __syncwarp();
         }
@@ -616,6 +632,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
         // ---- traceback in aligned blocks of 8 genes: the 8 backpointer words are loaded together
         //      (independent addresses), states leave as one 8-byte word when the layout allows it -----
         const bool wide = ((p.G & 7) == 0);  // then (G*c + g) is 8-aligned whenever g is
+        int ring_front = (n + 1) >> 1;       // ICNV_VIT_EVICT=3: 128-byte lines (two gene rows) of the ring at and above this one are dead
         for (int gb = (g_hi - 1) & ~7; gb + 8 > g_lo; gb -= 8) {
             uint32_t w[8];
 #pragma unroll
@@ -631,6 +648,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
                     pack |= (unsigned long long)(y + 1) << (8 * q);
                     if (g > g_lo) y = ((w[q] >> y) & 1u) ? (int)(w[q] >> 8) : y;
                 }
+            }
+            if (p.evict_first == 3) {   // every lane has consumed its words of the rows >= gb - g_lo: those lines are dead
+                __syncwarp();
+                const int first = (max(gb - g_lo, 0) + 1) >> 1;   // first line that lies wholly in rows >= gb - g_lo
+                if (first + lane < ring_front) l2_discard_line(bp + (int64_t)(first + lane) * 64);
+                ring_front = min(ring_front, first);
             }
             if (active) {
                 if (wide && gb >= g_lo && gb + 8 <= g_hi) {
@@ -650,7 +673,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast_kernel(const VitP
 }
 
 // =================================================================================================
-// single-precision first pass of the certified fast path (hmm mode 2, the default)
+// single-precision first pass of the certified fast path (hmm mode 2, an option: measured slower than the FP64 pass alone)
 // =================================================================================================
 //
 // The FP64 fast kernel above spends a third of its issue slots on half-rate FP64 instructions.  Almost every sequence
@@ -700,7 +723,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast32_kernel(const Vi
     uint16_t *__restrict__ bp = reinterpret_cast<uint16_t *>(p.bp + warp_global * (int64_t)p.max_len * 32);
     const float T1p = (float)(p.b_off - p.a_diag - 0.5);   // "come from the best state" in the frame where that state's stay is -1/2
     const float MAGIC = 12582912.0f;                        // 1.5 * 2^23: (v + MAGIC) - MAGIC == rintf(v), low bits == (int)rintf(v)
-    const unsigned long long pol = l2_evict_first_policy(p.evict_first);
+    const unsigned long long pol = l2_evict_first_policy(p.evict_first == 1);
+    const unsigned long long pol_ring = l2_evict_last_policy();
     int err = 0;
 
     for (;;) {
@@ -824,7 +848,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) viterbi_fast32_kernel(const Vi
                     mg[k] = fminf(stay ? mg[k] : cm, fabsf(e));
                     moved = __funnelshift_l((uint32_t)__float_as_int(e), moved, 1);
                 }
-                bp[(int64_t)i * 32 + lane] = (uint16_t)(moved | ((uint32_t)i1 << 8));
+                bp_store(bp + (int64_t)i * 32 + lane, (uint16_t)(moved | ((uint32_t)i1 << 8)), pol_ring, p.evict_first >= 2);
             }
             __syncwarp();
         }

@@ -40,6 +40,9 @@ PTX_STANDINS = {
     "fence_proxy_async": "{ }",
     "cp_async8": "{ if (valid) memcpy(smem_dst, gsrc, 8); else memset(smem_dst, 0, 8); }",
     "l2_evict_first_policy": "{ return 0ull; }",
+    "l2_evict_last_policy": "{ return 0ull; }",
+    "l2_discard_line": "{ (void)line; }",
+    "bp_store": "{ (void)pol; (void)hinted; *ptr = v; }",
     "cp_async_commit": "{ }",
     "cp_async_wait": "{ }",
     "count_if_ge": "{ acc += (v >= lim) ? 1 : 0; }",
