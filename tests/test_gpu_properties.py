@@ -144,3 +144,33 @@ def test_median_filter_properties(world):
     assert bool(torch.equal(F2, F1 * 4.0))
     assert bool(torch.equal(F3, const))
     assert float(F1.min().item()) >= float(X.min().item()) and float(F1.max().item()) <= float(X.max().item())
+
+
+def test_full_size_pairwise_distances_against_an_independent_implementation(world):
+    """3000 smoothed cells x 10 000 genes (4.5e6 pairs): the distance kernel against torch's own FP64 `cdist` on the
+    same device data (an independent implementation: |a|^2 + |b|^2 - 2 a.b form), in R's "dist" order; the fused
+    single-precision HMM cascade (hmm mode "fast32") on the full matrix returns the FP64 pass's states bit for bit."""
+    w = world
+    torch, eng = w["torch"], w["eng"]
+    cells = np.arange(2000, 5000, dtype=np.int32)
+    d = eng.pairwise_dist(w["Y"], cells)
+    torch.cuda.synchronize()
+    sub = w["Y"][torch.as_tensor(cells, device=w["Y"].device).long()]
+    ref = torch.cdist(sub, sub, compute_mode="donot_use_mm_for_euclid_dist")          # exact difference form
+    iu = torch.triu_indices(len(cells), len(cells), offset=1, device=ref.device)
+    want = ref[iu[0], iu[1]]                    # pairs (a, b), a < b, by a then b = the strict lower triangle by columns
+    err = float(((d - want).abs() / want.clamp_min(1e-300)).max().item())
+    print(f"\n[full size] {d.numel()} pairwise distances: max relative deviation from torch.cdist {err:.2e}")
+    assert d.numel() == len(cells) * (len(cells) - 1) // 2 and err < 1e-12
+    assert float(d.min().item()) > 0.0
+    from infercnv_b200 import api
+    S1, _ = eng.viterbi(w["Y"], w["cs"], w["cl"], w["Pi"], w["delta"], w["bench"].I6_MEAN, w["bench"].I6_SD)
+    api.set_hmm_mode("fast32")
+    try:
+        S2, _ = eng.viterbi(w["Y"], w["cs"], w["cl"], w["Pi"], w["delta"], w["bench"].I6_MEAN, w["bench"].I6_SD)
+        torch.cuda.synchronize()
+        second = api.hmm_second_pass_count()
+    finally:
+        api.set_hmm_mode("fast")
+    print(f"[full size] single-precision cascade: {second} of {w['C'] * len(w['cs'])} sequences went on to the FP64 pass")
+    assert int((S1 != S2).sum().item()) == 0 and 0 < second < 0.5 * w["C"] * len(w["cs"])
