@@ -1704,12 +1704,22 @@ int icnv_mean_sd_f64(const double *X, int64_t G, int64_t C, const int32_t *idx, 
         return set_error(ICNV_E_BAD_ARG, "icnv_mean_sd_f64: bad argument");
     for (int64_t i = 0; i < n_idx; ++i)
         if (idx[i] < 0 || idx[i] >= C) return set_error(ICNV_E_BAD_ARG, "cell index out of range");
-    double *dX;
+    // only the listed columns go to the device (the reference cells are a tenth of the matrix): runs of consecutive
+    // indices as one copy each into a compact buffer, the statistics then run over its columns 0 .. n_idx-1
     int rc;
-    if ((rc = upload_matrix(X, G * C, &dX, SLOT_IN, st))) return rc;
+    double *dX = (double *)scratch(SLOT_IN, sizeof(double) * (size_t)G * (size_t)n_idx);
     int32_t *d_idx = (int32_t *)scratch(SLOT_IDX, sizeof(int32_t) * (size_t)n_idx);
     double *d_stats = (double *)scratch(SLOT_MEANS, sizeof(double) * 2 * (size_t)n_idx);
-    if (!d_idx || !d_stats) return ICNV_E_NOMEM;
+    if (!dX || !d_idx || !d_stats) return ICNV_E_NOMEM;
+    std::vector<int32_t> ident((size_t)n_idx);
+    for (int64_t i = 0; i < n_idx;) {
+        int64_t j = i + 1;
+        while (j < n_idx && idx[j] == idx[j - 1] + 1) ++j;
+        ICNV_CUDA(cudaMemcpyAsync(dX + G * i, X + G * (int64_t)idx[i], sizeof(double) * (size_t)G * (size_t)(j - i), cudaMemcpyHostToDevice, st));
+        for (int64_t k = i; k < j; ++k) ident[(size_t)k] = (int32_t)k;
+        i = j;
+    }
+    idx = ident.data();
     ICNV_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * (size_t)n_idx, cudaMemcpyHostToDevice, st));
     // per-cell sum and sd on the device; the n_idx-vectors are combined in list order (the same
     // combination the multi-GPU driver applies to all-gathered per-cell statistics: identical bits)
