@@ -230,8 +230,10 @@ constexpr unsigned MM_LOW = 0u, MM_HIGH = 0xffffffffu;
 
 // TY = outputs per tile along the index list.  Halo rows 0 .. TY+9 (row r = list position y0 - 5 + r; rows 1 .. TY+8 are used);
 // P lists: rows (2t, 2t+1), t = 1 .. TY/2+3; Q lists: P[q] + P[q+1].
-constexpr size_t mm_smem_bytes(int TY) {
-    return sizeof(double) * (size_t)(TY + 10) * MM_HX + sizeof(unsigned) * (size_t)(TY + 10) * MM_HX +
+// DH = false: the tile keeps no copy of the halo's doubles; the few that are needed (the median's own value, the members of a
+// tied key cell) are read from the matrix again (L2), through the tile's table of column offsets.
+constexpr size_t mm_smem_bytes(int TY, bool DH = true) {
+    return (DH ? sizeof(double) * (size_t)(TY + 10) * MM_HX : 0) + sizeof(unsigned) * (size_t)(TY + 10) * MM_HX +
            sizeof(unsigned) * (size_t)(TY + 10) * 9 * MM_TX + sizeof(unsigned) * (size_t)(TY / 2 + 3) * MM_TX * MM_PW +
            sizeof(unsigned) * (size_t)(TY / 2 + 2) * MM_TX * MM_QW + 96 * sizeof(double);
 }
@@ -239,8 +241,21 @@ constexpr size_t mm_smem_bytes(int TY) {
 // The value of real rank `rho` (1-based, among the window's taps inside the block) when the key at that rank has the
 // quantised value Q: every tap below the cell ranks below it, so the answer is the (rho - #below)-th smallest double of the
 // cell.  (x0, r0): halo coordinates of the window's first tap.
-__device__ __noinline__ double mm_exact_rank(const unsigned *__restrict__ Kh, const double *__restrict__ Dh, int x0, int r0, unsigned Q,
-                                             int rho) {
+// the halo's doubles: from the tile's shared copy, or (no copy kept) from the matrix through the tile's column-offset table
+template <bool DH>
+struct MmVals {
+    const double *Dh;            // [ROWS][HX] (DH)
+    const double *X;
+    const long long *rowoff;     // [ROWS] column offset of each halo row (!DH)
+    long long hi0;               // gene of halo column 0
+    __device__ __forceinline__ double operator()(int r, int hx) const {
+        if constexpr (DH) return Dh[r * MM_HX + hx];
+        else return X[hi0 + hx + rowoff[r]];
+    }
+};
+
+template <bool DH>
+__device__ __noinline__ double mm_exact_rank(const unsigned *__restrict__ Kh, const MmVals<DH> Dv, int x0, int r0, unsigned Q, int rho) {
     int below = 0, g = 0;
     double dmin = INFINITY, dmax = -INFINITY;
     for (int r = 0; r < 9; ++r)
@@ -250,7 +265,7 @@ __device__ __noinline__ double mm_exact_rank(const unsigned *__restrict__ Kh, co
             const unsigned q = key >> 8;
             below += (q < Q) ? 1 : 0;
             if (q == Q) {
-                const double d = Dh[(r0 + r) * MM_HX + x0 + c];
+                const double d = Dv(r0 + r, x0 + c);
                 ++g;
                 dmin = d < dmin ? d : dmin;
                 dmax = d > dmax ? d : dmax;
@@ -263,13 +278,13 @@ __device__ __noinline__ double mm_exact_rank(const unsigned *__restrict__ Kh, co
         for (int c = 0; c < 9; ++c) {
             const unsigned key = Kh[(r0 + r) * MM_HX + x0 + c];
             if (key == MM_LOW || key == MM_HIGH || (key >> 8) != Q) continue;
-            const double d = Dh[(r0 + r) * MM_HX + x0 + c];
+            const double d = Dv(r0 + r, x0 + c);
             int lt = 0, eq = 0;
             for (int r2 = 0; r2 < 9; ++r2)
                 for (int c2 = 0; c2 < 9; ++c2) {
                     const unsigned k2 = Kh[(r0 + r2) * MM_HX + x0 + c2];
                     if (k2 == MM_LOW || k2 == MM_HIGH || (k2 >> 8) != Q) continue;
-                    const double d2 = Dh[(r0 + r2) * MM_HX + x0 + c2];
+                    const double d2 = Dv(r0 + r2, x0 + c2);
                     lt += (d2 < d) ? 1 : 0;
                     eq += (d2 == d) ? 1 : 0;
                 }
@@ -279,18 +294,19 @@ __device__ __noinline__ double mm_exact_rank(const unsigned *__restrict__ Kh, co
 }
 
 // the double behind a key of the window whose first tap is (x0, r0): the tag holds the tap's halo coordinates mod 16
-__device__ __forceinline__ double mm_value_of(const double *__restrict__ Dh, unsigned key, int x0, int r0) {
+template <bool DH>
+__device__ __forceinline__ double mm_value_of(const MmVals<DH> &Dv, unsigned key, int x0, int r0) {
     const int tx = (int)((key >> 4) & 15u), ty = (int)(key & 15u);
     const int hx = x0 + ((tx - x0) & 15), r = r0 + ((ty - r0) & 15);
-    return Dh[r * MM_HX + hx];
+    return Dv(r, hx);
 }
 
-template <int MM_TY, int MM_NW, int MINB>
+template <int MM_TY, int MM_NW, int MINB, bool DH = true>
 __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(const MfParams p) {
     constexpr int MM_ROWS = MM_TY + 10, MM_NT = MM_NW * 32, MM_NP = MM_TY / 2 + 3, MM_NQ = MM_TY / 2 + 2;
     extern __shared__ __align__(16) unsigned char mf_smem[];
-    double *Dh = reinterpret_cast<double *>(mf_smem);                         // [ROWS][HX] values (0 outside the block)
-    double *redd = Dh + MM_ROWS * MM_HX;                                      // [96] reduction scratch, row table
+    double *Dh = reinterpret_cast<double *>(mf_smem);                         // [ROWS][HX] values (0 outside the block); DH only
+    double *redd = Dh + (DH ? MM_ROWS * MM_HX : 0);                           // [96] flags, table of the halo rows' column offsets
     unsigned *Kh = reinterpret_cast<unsigned *>(redd + 96);                   // [ROWS][HX] keys
     unsigned *Rs = Kh + MM_ROWS * MM_HX;                                      // [ROWS][9][TX] sorted runs
     unsigned *Ps = Rs + (size_t)MM_ROWS * 9 * MM_TX;                          // [NP][TX][PW]
@@ -317,6 +333,8 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
     const unsigned qM = quant(M);
     int *flags = reinterpret_cast<int *>(redd);
     if (tid == 0) flags[0] = 0;
+    long long *rowoff = reinterpret_cast<long long *>(redd) + 8;   // [MM_ROWS] <= 42 of the 96 scratch doubles (DH = false)
+    const MmVals<DH> Dv{Dh, p.X, rowoff, (long long)hi0};
     // a tap's value -> its key and the two halo arrays
     auto put = [&](int r, int hx, bool in, double v) {
         unsigned key = ((hx + r) & 1) ? MM_HIGH : MM_LOW;
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
             dirty |= (q == qM) && (v != M);
             key = (q << 8) | (unsigned)((hx & 15) << 4) | (unsigned)(r & 15);
         }
-        Dh[r * MM_HX + hx] = in ? v : 0.0;
+        if (DH) Dh[r * MM_HX + hx] = in ? v : 0.0;
         Kh[r * MM_HX + hx] = key;
     };
     // every global load of the tile is issued before the first one is used: first the column offsets (G * cell, a table the
@@ -342,6 +360,7 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
         const int jj = hj0 + r;
         rin[i] = r < MM_ROWS && jj >= ct.lo && jj < ct.hi && r >= 1 && r <= MM_TY + 8;
         rb[i] = rin[i] ? p.coloff[jj] : 0ll;
+        if (!DH && i < RPW && lane == 0 && r < MM_ROWS) rowoff[r] = rb[i];   // read again in S3 only (two barriers later)
     }
     double tv[RPW + TPW];
 #pragma unroll
@@ -455,14 +474,14 @@ __global__ void __launch_bounds__(MM_NW * 32, MINB) median_filter_merge_kernel(c
                 auto value_at = [&](int ki, int rk) -> double {
                     const unsigned Qc = s[ki] >> 8;
                     const bool tl = (s[ki - 1] >> 8) == Qc, th = (s[ki + 1] >> 8) == Qc;
-                    if (!tl && !th) return mm_value_of(Dh, s[ki], x0, r0);
+                    if (!tl && !th) return mm_value_of(Dv, s[ki], x0, r0);
                     if (Qc == qM && mode_clean) return M;
                     int lo = ki, hi = ki;
                     while (lo > 0 && (s[lo - 1] >> 8) == Qc) --lo;
                     while (hi < 4 && (s[hi + 1] >> 8) == Qc) ++hi;
-                    if (lo == 0 || hi == 4 || hi - lo > 2) return mm_exact_rank(Kh, Dh, x0, r0, Qc, rk);
-                    double d0 = mm_value_of(Dh, s[lo], x0, r0), d1 = mm_value_of(Dh, s[lo + 1], x0, r0);
-                    double d2 = (hi - lo == 2) ? mm_value_of(Dh, s[lo + 2], x0, r0) : INFINITY;
+                    if (lo == 0 || hi == 4 || hi - lo > 2) return mm_exact_rank(Kh, Dv, x0, r0, Qc, rk);
+                    double d0 = mm_value_of(Dv, s[lo], x0, r0), d1 = mm_value_of(Dv, s[lo + 1], x0, r0);
+                    double d2 = (hi - lo == 2) ? mm_value_of(Dv, s[lo + 2], x0, r0) : INFINITY;
                     mf_cswap(d0, d1);
                     mf_cswap(d1, d2);
                     mf_cswap(d0, d1);
@@ -509,13 +528,16 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     }
     // window_size 7 (radius 4): the shared-merge kernel; ICNV_MF_KERNEL=1 (read at icnv_init) keeps the counting selection
     // (default and ICNV_MF_KERNEL=4: tiles of 12 list positions, two 256-thread CTAs per SM; 3: tiles of 32, one 512-thread CTA)
-    const int mm_ty = (c.opt_mf_kernel == 3) ? 32 : 12, mm_nw = (c.opt_mf_kernel == 3) ? 16 : 8;
-    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel >= 3) && mm_smem_bytes(mm_ty) <= (size_t)c.smem_optin;
+    // (5: tiles of 16, two 320-thread CTAs per SM, no shared copy of the halo's doubles)
+    const int mm_ty = (c.opt_mf_kernel == 3) ? 32 : (c.opt_mf_kernel == 5 ? 16 : 12);
+    const int mm_nw = (c.opt_mf_kernel == 3) ? 16 : (c.opt_mf_kernel == 5 ? 10 : 8);
+    const bool mm_dh = c.opt_mf_kernel != 5;
+    const bool merge_kernel = (r == 4) && (c.opt_mf_kernel < 0 || c.opt_mf_kernel >= 3) && mm_smem_bytes(mm_ty, mm_dh) <= (size_t)c.smem_optin;
     const int TI = merge_kernel ? MM_TX : (select_kernel ? MS_TI : MF_TI), TJ = merge_kernel ? mm_ty : (select_kernel ? MS_TJ : MF_TJ);
     const int NT = merge_kernel ? mm_nw * 32 : TI * TJ;
     bool list32 = false;
     if (c.opt_mf_list32) list32 = select_kernel;   // diagnostic (ICNV_MF_LIST32 at icnv_init)
-    const size_t smem = merge_kernel ? mm_smem_bytes(mm_ty)
+    const size_t smem = merge_kernel ? mm_smem_bytes(mm_ty, mm_dh)
                                      : sizeof(double) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) * (select_kernel ? 2 : 1) +
                                            (list32 ? sizeof(unsigned) : sizeof(unsigned short)) * (size_t)W * (size_t)NT +
                                            (use_net ? sizeof(float) * (size_t)(TI + 2 * r) * (size_t)(TJ + 2 * r) : 0);
@@ -636,7 +658,9 @@ extern "C" int icnv_dev_median_filter_f64(const double *X, double *Y, int64_t G,
     };
     int lrc;
     if (list32) use_net = 0;
-    if (merge_kernel) lrc = (mm_ty == 12) ? launch(median_filter_merge_kernel<12, 8, 2>) : launch(median_filter_merge_kernel<32, 16, 1>);
+    if (merge_kernel)
+        lrc = (mm_ty == 12) ? launch(median_filter_merge_kernel<12, 8, 2>)
+                            : (mm_ty == 16 ? launch(median_filter_merge_kernel<16, 10, 2, false>) : launch(median_filter_merge_kernel<32, 16, 1>));
     else if (!select_kernel) lrc = launch(median_filter_kernel);
     else if (list32 && r == 5) lrc = launch(median_filter_select_kernel<5, unsigned>);
     else if (list32 && r == 4) lrc = launch(median_filter_select_kernel<4, unsigned>);

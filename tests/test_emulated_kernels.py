@@ -35,7 +35,7 @@ def test_gpu_parity_tests_pass_under_the_host_emulation(order):
 
 @pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
 @pytest.mark.parametrize("env", [{"ICNV_VFAST_WARPS": "24"}, {"ICNV_VFAST_WARPS": "20"}, {"ICNV_HMM_MODE": "2"},
-                                 {"ICNV_CELL_PADQ": "0"}, {"ICNV_CELL_KERNEL": "4"}, {"ICNV_MF_KERNEL": "2"}], ids=lambda e: "-".join(f"{k}={v}" for k, v in e.items()))
+                                 {"ICNV_CELL_PADQ": "0"}, {"ICNV_CELL_KERNEL": "4"}, {"ICNV_MF_KERNEL": "2"}, {"ICNV_MF_KERNEL": "5"}], ids=lambda e: "-".join(f"{k}={v}" for k, v in e.items()))
 def test_kernel_variants_behind_the_tuning_switches_under_the_host_emulation(env):
     """The variants DESIGN.md section 8 lists (Viterbi occupancy variants, the single-precision first pass, the ping-pong layout of the two-buffer cell
     pipeline and the single-buffer v4 kernel at gene counts where v3 is the default) through the parity tests of the path
