@@ -26,6 +26,9 @@ def test_r_wrappers_name_every_replaced_function():
                "i3HMM_predict_CNV_via_HMM_on_whole_tumor_samples", "normalize_counts_by_seq_depth",
                "clear_noise_via_ref_mean_sd"]:
         assert f"b200_{fn} <- function" in src and f'"{fn}"' in src
+    # the one replaced IMPORT (parallelDist::parallelDist, R/inferCNV_constants.R:27): same signature, bound in the imports environment
+    assert 'b200_parallelDist <- function(x, method = "euclidean", diag = FALSE, upper = FALSE, threads = NULL, ...)' in src
+    assert 'assign("parallelDist", b200_parallelDist, envir = imp)' in src and "parent.env(ns)" in src
 
 
 def test_r_wrappers_have_balanced_brackets_and_registered_call_names():
