@@ -103,8 +103,12 @@ def single():
     F = eng.median_filter(Y, CS, LENS, groups[:2], 7)
     want_f = orc.median_filter(np.asfortranarray(Y.numpy().T), CS, LENS, groups[:2], 7)
     assert np.allclose(F.numpy().T, want_f, rtol=0, atol=1e-15)
+    # pairwise distances of a shuffled subset of the local cells on "device" tensors (Engine.pairwise_dist)
+    sub = np.random.default_rng(3).permutation(Y.shape[0])[:37].astype(np.int32)
+    D = eng.pairwise_dist(Y, sub)
+    assert np.allclose(D.numpy(), orc.pairwise_dist(np.asfortranarray(Y.numpy().T), sub), rtol=1e-13, atol=0)
     print(f"engine (emulated, 1 rank): smooth block rel err {rel:.1e}, {S.numel()} states identical, consensus / regions / "
-          f"median filter equal to the oracle")
+          f"median filter / pairwise distances equal to the oracle")
 
 
 def rank_main(rank, world, port):
